@@ -1,0 +1,310 @@
+/*
+ * microclimate_b200.h — C ABI of the B200-native batched-sites soil engine.
+ *
+ * This is the drop-in boundary for ONE path of BiophysicalEcology/Microclimate.jl:
+ *     solve_soil!(cache::MicroCache)            (reference src/simulation.jl:355-819)
+ * batched over S independent sites.  The reference has no FFI for this path (it is a
+ * plain Julia method); a Julia wrapper (julia/MicroclimateB200.jl) strips units from the
+ * reference's own types and `ccall`s the entry points below.  Every entry point cites the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions across the boundary, no torch types;
+ *   - everything is FP64 in unit-stripped SI: K, Pa, m, s, W/m2, kg/m2, J/kg, kg s/m3,
+ *     fractions 0..1, angles in degrees;
+ *   - structure-of-arrays with the SITE index fastest:  x[node][site], f[hour][site],
+ *     out[hour][node][site]  (reference: one Matrix(nsteps, N) per site, time fastest,
+ *     src/outputs.jl:52-58);
+ *   - the caller owns every host array for the duration of the call; the library owns
+ *     device memory; only the handle needs freeing;
+ *   - return value: 0 ok, <0 error (see mc_last_error), >0 number of sites whose status
+ *     word is non-zero (numeric flag).
+ *   - a handle is confined to one host thread at a time and drives ONE GPU; multi-GPU
+ *     runs create one handle per GPU over disjoint, contiguous site ranges (no collective).
+ */
+#ifndef MICROCLIMATE_B200_H
+#define MICROCLIMATE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_MAX_SOIL_NODES 24
+#define MC_SNOW_NODES 8
+#define MC_MAX_ODE_NODES (MC_MAX_SOIL_NODES + MC_SNOW_NODES)
+#define MC_HOURS_PER_DAY 24
+
+/* enums mirror the reference's strategy singletons */
+enum { MC_TIME_NONCONSECUTIVE = 0, MC_TIME_CONSECUTIVE = 1 };   /* src/time_mode/{non_consecutive,consecutive}.jl */
+enum { MC_CONV_FIXED = 0, MC_CONV_TOLERANCE = 1 };              /* src/soil_temperature_convergence/{fixed,tolerance}.jl */
+enum { MC_RAIN_DAILY = 0, MC_RAIN_HOURLY = 1 };                 /* src/rainfall/{daily,hourly}_rainfall.jl */
+enum { MC_MOIST_PRESCRIBED = 0, MC_MOIST_DYNAMIC = 1 };         /* src/soil_moisture/{prescribed,dynamic}.jl */
+enum { MC_INFIL_MATRIC_POTENTIAL = 0, MC_INFIL_MATRIC_FLUX_POTENTIAL = 1 }; /* src/soil_hydraulics/infiltration_algorithm */
+enum { MC_ATMRAD_CAMPBELL_NORMAN = 0, MC_ATMRAD_SWINBANK = 1 }; /* src/radiation/atmospheric */
+enum { MC_AHC_BONACINA = 0, MC_AHC_TANH = 1, MC_AHC_GAUSSIAN = 2, MC_AHC_WESTERMANN = 3 }; /* src/apparent_heat_capacity */
+
+/* per-site status bits (mc_output_soa.status / mc_get_status) */
+enum {
+    MC_STATUS_NAN            = 1,   /* a NaN/Inf reached the soil temperature or moisture state */
+    MC_STATUS_DT_UNDERFLOW   = 2,   /* adaptive step fell below 1e-12 min */
+    MC_STATUS_NEWTON_MAXITER = 4,   /* infiltration Newton loop hit moisture_max_iterations */
+    MC_STATUS_STEP_LIMIT     = 8    /* more than MC_MAX_STEPS_PER_HOUR RK attempts in one hour */
+};
+
+/*
+ * Psychrometric constants.  The arithmetic lives in the un-vendored, un-pinned
+ * FluidProperties.jl (reference Project.toml:29,43) — kept as data so a maintainer with
+ * Julia can set them to whatever that package uses.  Defaults: mc_default_fluid().
+ */
+typedef struct mc_fluid_constants {
+    double molar_mass_water;        /* kg/mol, 0.018016 */
+    double molar_mass_air;          /* kg/mol, 0.028966 */
+    double ideal_gas_departure;     /* 1.0053 */
+    double cp_dry_air;              /* J/kg/K, 1004.84 */
+    double cp_water_vapour;         /* J/kg/K, 1846.40 */
+    double gas_constant;            /* J/mol/K, 8.314462618 */
+    double stefan_boltzmann;        /* W/m2/K4, 5.670374419e-8 */
+    double standard_gravity;        /* m/s2, 9.80665 (Unitful.gn) */
+    double standard_pressure;       /* Pa, 101325 (Unitful.atm) */
+    double latent_heat_a;           /* enthalpy_of_vaporisation(T) = a - b*(T-273.15)  J/kg; a=2.5012e6 */
+    double latent_heat_b;           /* b=2.3787e3 */
+    double molar_latent_heat_a;     /* molar_enthalpy_of_vaporisation(T) = a - b*(T-273.15) J/mol; a=45144 */
+    double molar_latent_heat_b;     /* b=48 */
+} mc_fluid_constants;
+
+/* SnowModel (src/snow/snow_model.jl:3-42) */
+typedef struct mc_snow_desc {
+    double snow_temperature_threshold_C;   /* degC */
+    double snow_density;                   /* g/cm3 */
+    double snow_melt_factor;
+    double undercatch;
+    double rain_multiplier;
+    double rain_melt_factor;
+    double density_function[4];
+    double snow_conductivity;              /* W/m/K; 0 = Aggarwal cubic */
+    double canopy_interception;
+    double min_snow_depth_cm;
+    double node_thresholds_cm[MC_SNOW_NODES];
+    double melt_threshold_C;
+    int32_t ahc_kind;                      /* MC_AHC_* */
+    double ahc_T_low_C, ahc_T_high_C, ahc_window_K, ahc_smoothing_K; /* Bonacina / Tanh */
+    double ahc_T_melt_C, ahc_width_K;                                 /* Gaussian / Westermann */
+    double initial_snow_depth_cm;          /* MicroInputs.initial_snow_depth (model-level here) */
+    double initial_snow_temperature_K;
+    double initial_snow_density;           /* <=0: use default */
+} mc_snow_desc;
+
+/*
+ * mc_model_desc — flattened MicroModel + MicroConfig + time mode
+ * (reference src/types.jl:71-120,174-183; strategy objects in src/time_mode, src/soil_moisture,
+ *  src/soil_temperature_convergence, src/rainfall; solver knobs src/soil_balance/energy/heat_transport_1d.jl:24-29).
+ * Constant across sites, exactly as MicroModel is constant across `reinit!`ed inputs (src/types.jl:143-144).
+ */
+typedef struct mc_model_desc {
+    int32_t n_soil;                         /* N = length(depths) */
+    int32_t n_snow;                         /* 0 (NoSnow) or 8 (SnowModel) */
+    double  depths_m[MC_MAX_SOIL_NODES];    /* MicroModel.depths, metres */
+    double  reference_height_m;             /* last(heights) */
+    double  local_height_m;                 /* first(heights) */
+    /* SoilHeatTransport1D */
+    double  reltol, abstol;                 /* 1e-6, 1e-3 (K) */
+    double  maximum_surface_temperature_K;  /* 85 degC = 358.15 */
+    /* CampbelldeVriesSoilProperties (scalar form) */
+    double  de_vries_shape_factor, recirculation_power, return_flow_threshold;
+    /* CampbellSoilHydraulics plant scalars */
+    double  root_resistance, stomatal_closure_potential, leaf_resistance,
+            stomatal_stability_parameter, root_radius;
+    int32_t infiltration_algorithm;         /* MC_INFIL_* */
+    /* MoninObukhov */
+    double  karman_constant, dyer_constant;
+    /* time mode */
+    int32_t time_mode;                      /* MC_TIME_* */
+    int32_t iterations_per_day;             /* NonConsecutiveDayMode.iterations_per_day */
+    int32_t spinup_first_day;               /* ConsecutiveDayMode.spinup_first_day */
+    /* MicroConfig */
+    int32_t convergence_kind;               /* MC_CONV_* */
+    int32_t convergence_iterations;         /* iterations_per_day / max_iterations_per_day */
+    double  convergence_tolerance_K;
+    int32_t rainfall_schedule;              /* MC_RAIN_* */
+    int32_t moisture_strategy;              /* MC_MOIST_* */
+    double  moisture_tolerance;             /* kg/m2/s */
+    int32_t moisture_max_iterations;
+    double  moisture_timestep_s;
+    double  max_surface_pool;               /* kg/m2 */
+    int32_t atmospheric_radiation;          /* MC_ATMRAD_* */
+    int32_t _pad0;
+    mc_fluid_constants fluid;
+    mc_snow_desc snow;
+} mc_model_desc;
+
+/*
+ * mc_sites_soa — Site + SoilProfile + CampbellHydraulicProfile for S sites
+ * (reference src/site/site.jl:11-22 — only the four fields the hot path reads,
+ *  src/types.jl:14-20, src/soil_hydraulics/campbell.jl:14-19).
+ */
+typedef struct mc_sites_soa {
+    const double* roughness_height;    /* [S] m */
+    const double* slope;               /* [S] degrees */
+    const double* sky_view_fraction;   /* [S] */
+    const double* albedo;              /* [S] Site.albedo */
+    const double* bulk_density;        /* [N][S] kg/m3 */
+    const double* mineral_density;     /* [N][S] kg/m3 */
+    const double* mineral_conductivity;/* [N][S] W/m/K */
+    const double* mineral_heat_capacity;/*[N][S] J/kg/K */
+    const double* air_entry_water_potential;        /* [N][S] J/kg */
+    const double* saturated_hydraulic_conductivity; /* [N][S] kg s/m3 */
+    const double* campbell_b_parameter;             /* [N][S] */
+    const double* root_density;                     /* [N][S] m/m3 */
+} mc_sites_soa;
+
+/*
+ * mc_initial_soa — MicroInputs initial conditions (reference src/types.jl:146-157).
+ * initial_soil_temperature == NULL reproduces `initial_soil_temperature=nothing`
+ * (TINS mean of the first day's air temperature, src/simulation.jl:395-397).
+ */
+typedef struct mc_initial_soa {
+    const double* initial_soil_temperature; /* [N][S] K, or NULL */
+    const double* initial_soil_moisture;    /* [N][S] m3/m3 */
+} mc_initial_soa;
+
+/*
+ * mc_state_soa — everything solve_soil! carries from one hour/day to the next
+ * (locals at src/simulation.jl:369-371,451-452 + the mutable strategy/buffer slots the
+ * reference hides: DynamicSoilMoisture.soil_wetness, the two obukhov_length_prev Refs,
+ * the integrator's stale FSAL slot).  Exposed so runs can be time-chunked / checkpointed.
+ * All pointers are caller-owned host arrays.
+ */
+typedef struct mc_state_soa {
+    double* soil_temperature;   /* [N][S] K */
+    double* soil_moisture;      /* [N][S] */
+    double* sum_phase;          /* [N][S] J/m2 (accumulated latent heat) */
+    double* pool;               /* [S] kg/m2 */
+    double* soil_wetness;       /* [S] */
+    double* obukhov_ode;        /* [S] m   buffers.soil_energy_balance.obukhov_length_prev */
+    double* obukhov_profile;    /* [S] m   buffers.soil_water_profile.obukhov_length_prev */
+    double* deep_temperature_prev; /* [S] K  environment_instant.deep_soil_temperature left over from the previous day */
+    double* fsal;               /* [M][S] K/min  integrator.fsalfirst left over from the previous day-pass */
+    double* snow_temperature;   /* [8][S] K (n_snow>0) or NULL */
+    double* snow_state;         /* [MC_SNOW_STATE_FIELDS][S] (n_snow>0) or NULL */
+    double* snow_node_depths;   /* [8][S] cm (n_snow>0) or NULL */
+    double* q_freeze;           /* [S] W/m2 (n_snow>0) or NULL */
+    int64_t* days_done;         /* [1] days integrated so far (global day index of the next day) */
+} mc_state_soa;
+#define MC_SNOW_STATE_FIELDS 10 /* depth, age, days_since_snow, density, prev_density, cum_melt, extra_snow, active_nodes, sum_phase, prev_hour_depth */
+
+/*
+ * mc_forcing_soa — what solve_soil! reads from cache.output / solar_out / environment_daily
+ * for a chunk of `ndays` days (reference src/simulation.jl:1006-1021,1025-1070):
+ * hourly arrays are [24*ndays][S], daily arrays [ndays][S].
+ */
+typedef struct mc_forcing_soa {
+    const double* pressure;              /* Pa */
+    const double* reference_temperature; /* K */
+    const double* reference_wind_speed;  /* m/s */
+    const double* reference_humidity;    /* 0..1 */
+    const double* cloud_cover;           /* 0..1 */
+    const double* global_radiation;      /* W/m2 (already cloud adjusted) */
+    const double* diffuse_fraction;      /* 0..1 */
+    const double* zenith_angle;          /* deg, capped at 90 */
+    const double* zenith_slope_angle;    /* deg, capped at 90 */
+    const double* rainfall_hourly;       /* kg/m2 per hour; NULL unless MC_RAIN_HOURLY */
+    const double* longwave_radiation;    /* W/m2 user supplied downward longwave, or NULL */
+    /* daily */
+    const double* leaf_area_index;
+    const double* shade;
+    const double* surface_emissivity;
+    const double* cloud_emissivity;
+    const double* soil_wetness;
+    const double* deep_soil_temperature; /* K */
+    const double* rainfall_daily;        /* kg/m2 per day */
+    const double* albedo_daily;          /* or NULL -> Site.albedo */
+    const double* prescribed_soil_moisture; /* [ndays][N][S] or NULL (PrescribedSoilMoisture.precomputed_soil_moisture) */
+    const int32_t* day_of_year;          /* [ndays] MicroProblem.days */
+} mc_forcing_soa;
+
+/*
+ * mc_output_soa — the MicroResult fields solve_soil! writes (reference src/outputs.jl:18-41,
+ * writes at src/simulation.jl:423-444,562-587,788-797).  A NULL pointer deselects a field.
+ * Node fields are [24*ndays][N][S]; scalars [24*ndays][S].  Row convention is the
+ * reference's: hour i of a day is written to row i+1, row 1 of each day is the state at
+ * the start of the output pass, the last hour of the last day is not written.
+ */
+typedef struct mc_output_soa {
+    double* soil_temperature;          /* K */
+    double* soil_moisture;
+    double* soil_water_potential;      /* J/kg */
+    double* soil_humidity;
+    double* soil_thermal_conductivity; /* W/m/K */
+    double* soil_heat_capacity;        /* J/kg/K */
+    double* soil_bulk_density;         /* kg/m3 */
+    double* surface_water;             /* [H][S] kg/m2 */
+    double* sky_temperature;           /* [H][S] K */
+    double* snow_fall;                 /* [H][S] cm/hr */
+    double* snow_depth;                /* [H][S] cm */
+    double* snow_density;              /* [H][S] g/cm3 */
+    double* snow_temperature;          /* [H][8][S] K */
+    int32_t* status;                   /* [S] MC_STATUS_* bits, or NULL */
+} mc_output_soa;
+
+/* device-side work counters, summed over sites (SURVEY §8d definition of algorithmic work) */
+typedef struct mc_counters {
+    uint64_t n_rhs;            /* soil_energy_balance evaluations */
+    uint64_t n_accept;         /* accepted Tsit5 steps */
+    uint64_t n_reject;         /* rejected Tsit5 steps */
+    uint64_t n_obukhov_iter;   /* calc_Obukhov_length iterations (ODE + hourly warm start + moisture profile) */
+    uint64_t n_newton_iter;    /* infiltration Newton iterations */
+    uint64_t n_infil_steps;    /* infiltration_step! calls */
+    uint64_t n_site_days;      /* site-days integrated (all passes of a day count once) */
+    uint64_t n_day_passes;     /* site-day-passes integrated */
+    double   gpu_ms;           /* device time of the last mc_step_days* call (CUDA events) */
+    uint64_t n_kernel_launches;/* kernels launched by the last mc_step_days* call */
+} mc_counters;
+
+typedef struct mc_handle mc_handle;
+
+/* library identity */
+int         mc_abi_version(void);
+const char* mc_backend_name(void);              /* "cuda-sm_100a" */
+void        mc_default_fluid(mc_fluid_constants* out);
+void        mc_default_model(mc_model_desc* out); /* MicroModel()/MicroConfig() defaults, src/types.jl:71-120 */
+
+/* replaces CommonSolve.init(::MicroProblem) for the soil path (src/simulation.jl:141-243):
+ * allocates device state for n_sites sites on CUDA device `device`. */
+int  mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle** out);
+void mc_destroy(mc_handle* h);
+const char* mc_last_error(const mc_handle* h);  /* h may be NULL: last mc_create error */
+
+/* replaces reinit!(cache, inputs) (src/simulation.jl:274-277): new sites, fresh state. */
+int  mc_set_sites(mc_handle* h, const mc_sites_soa* sites, const mc_initial_soa* init);
+
+/* checkpoint / resume of the carried state. */
+int  mc_get_state(mc_handle* h, mc_state_soa* out);
+int  mc_set_state(mc_handle* h, const mc_state_soa* in);
+
+/* replaces solve_soil!(cache) (src/simulation.jl:355-819) for days [day0, day0+ndays) of the
+ * run; host buffers in/out, H2D and D2H included.  day0 must equal the number of days
+ * already integrated (0 after mc_set_sites). */
+int  mc_step_days(mc_handle* h, int64_t day0, int32_t ndays,
+                  const mc_forcing_soa* forcing, mc_output_soa* out);
+
+/* same, but every pointer inside `forcing` and `out` is a DEVICE pointer on the handle's
+ * GPU (day_of_year stays a host pointer); no copies.  Asynchronous on the handle's stream
+ * until mc_synchronize. */
+int  mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays,
+                         const mc_forcing_soa* forcing_dev, mc_output_soa* out_dev);
+int  mc_synchronize(mc_handle* h);
+
+int  mc_get_counters(mc_handle* h, mc_counters* out);
+int  mc_reset_counters(mc_handle* h);
+int  mc_get_status(mc_handle* h, int32_t* status_host /* [S] */);
+
+/* measured FP64 DFMA peak of the handle's device in TFLOP/s (micro-benchmark; SURVEY §8d:
+ * MEASURED_PEAKS.json has no FP64 figure). */
+int  mc_measure_fp64_peak(mc_handle* h, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICROCLIMATE_B200_H */

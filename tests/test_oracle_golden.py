@@ -1,0 +1,207 @@
+"""Pins the CPU oracle (oracle/mc_oracle.cpp) against the reference's own golden vectors.
+
+The goldens are NicheMapR (Fortran) outputs shipped with the reference (test/data/*.csv, committed here
+as tests/golden/*.npz by make_golden.py).  Leaf formulas are pinned tightly through internally consistent
+golden columns; end-to-end profiles are pinned at (much tighter than) the reference's
+own test tolerances (test/micro_testrun_monthly.jl:172-182, test/micro_testrun_daily.jl:206-209).
+CPU only.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import configs
+from microclimate_jl_b200 import _abi as A
+from microclimate_jl_b200 import marshal as M
+from oracle import oracle
+from oracle.oracle import OracleEngine
+
+
+@pytest.fixture(scope="module")
+def L():
+    return oracle.lib()
+
+
+@pytest.fixture(scope="module")
+def g1():
+    return configs.load("config1_monthly.npz")
+
+
+@pytest.fixture(scope="module")
+def g2():
+    return configs.load("config2_daily.npz")
+
+
+def test_goff_gratch_vs_rhloc(L, g1, g2):
+    """RHLOC = min(100, RH * e_sat(TAREF) / e_sat(TALOC)) — exact in NicheMapR's output, both ice and water branches."""
+    for g in (g1, g2):
+        es_ref = np.array([L.mco_goff_gratch(t) for t in g["TAREF"]])
+        es_loc = np.array([L.mco_goff_gratch(t) for t in g["TALOC"]])
+        rhloc = np.minimum(1.0, g["RH"] * es_ref / es_loc)
+        assert np.abs(rhloc - g["RHLOC"]).max() < 1e-6      # <1e-4 %RH (survey: 0.0000 %RH at printed precision)
+    assert (g1["TALOC"].min() < 273.15) and (g2["TALOC"].max() > 273.16)  # both branches exercised
+
+
+def test_goff_gratch_known_values(L):
+    # saturation vapour pressure over water at 100 degC is one atmosphere; over ice at the triple point 6.1071 hPa
+    assert L.mco_goff_gratch(373.15) == pytest.approx(101324.6, rel=1e-6)
+    assert L.mco_goff_gratch(273.15) == pytest.approx(610.71, rel=1e-9)
+
+
+def test_soil_properties_vs_goldens(L, g2):
+    """Campbell-de Vries conductivity / specific heat / density vs tcond, specheat, densit goldens (nodes 1-9)."""
+    p, _ = configs.config2_daily()
+    desc = M.model_desc(p.model, p.time_mode)
+    P = float(g2["pressure"])
+    out3 = (C.c_double * 3)()
+    worst = np.zeros(3)
+    for r in range(0, 720, 7):
+        for k in range(9):
+            L.mco_soil_properties(C.byref(desc), P, g2["soil_nmr"][r, k], g2["soilmoist_nmr"][r, k], 1300.0, 2560.0, 2.5, 870.0, out3)
+            ref = (g2["tcond_nmr"][r, k], g2["specheat_nmr"][r, k], g2["densit_nmr"][r, k])
+            for q in range(3):
+                worst[q] = max(worst[q], abs(out3[q] / ref[q] - 1.0))
+    assert worst[0] < 1e-6      # conductivity (survey: 1.8e-7)
+    assert worst[1] < 1e-12     # specific heat
+    assert worst[2] < 1e-12     # density
+
+
+def test_retention_curve_vs_soilpot(g2):
+    """psi = -|psi_e| (theta_s/theta)^b at the 9 nodes away from the fixture's texture boundary (node 5 is a known NicheMapR indexing quirk)."""
+    ci = np.arange(0, 19, 2)
+    pe, bb = g2["air_entry_water_potential"][ci], g2["campbell_b_parameter"][ci]
+    sat = 1.0 - g2["bulk_density"][ci] / g2["mineral_density"][ci]
+    psi = -np.abs(pe) * (sat / g2["soilmoist_nmr"]) ** bb
+    rel = np.abs(psi / g2["soilpot_nmr"] - 1.0)
+    keep = [0, 1, 2, 3, 5, 6, 7, 8, 9]
+    assert rel[:, keep].max() < 1e-10
+    assert np.all(g2["soilmoist_nmr"][:, 9] == 1.0 - 1.3 / 2.56)   # deepest node always saturated
+
+
+def test_sky_temperature_vs_tskyc(L, g1, g2):
+    p1, _ = configs.config1_monthly()
+    desc = M.model_desc(p1.model, p1.time_mode)
+    for g, cloud in ((g1, g1["cloud"]), (g2, g2["CLDhr"])):
+        sky = np.array([L.mco_sky_temperature(C.byref(desc), 1.0, float(g["pressure"]), g["RH"][i], g["TAREF"][i], 0.96, cloud[i], 0.0)
+                        for i in range(len(g["TAREF"]))])
+        assert np.abs(sky / g["TSKYC"] - 1.0).max() < 2e-3     # the reference's own tolerance (micro_testrun_monthly.jl:179)
+        assert np.abs(sky - g["TSKYC"]).max() < 0.25
+
+
+def test_most_profile_vs_vloc_taloc(L, g1):
+    """Monin-Obukhov local (1 cm) wind and air temperature vs VLOC / TALOC with the golden surface temperature."""
+    p1, _ = configs.config1_monthly()
+    desc = M.model_desc(p1.model, p1.time_mode)
+    out4 = (C.c_double * 4)()
+    Lp = -0.3
+    dv, dT, stable_exact = [], [], []
+    for i in range(288):
+        Ts, Ta, v, zen = g1["soil_nmr"][i, 0], g1["TAREF"][i], g1["VREF"][i], g1["ZEN"][i]
+        L.mco_surface_profile(C.byref(desc), 0.004, Ta, v, zen, Ts, Lp, out4)
+        Lp = out4[3]
+        dv.append(out4[1] / g1["VLOC"][i] - 1.0)
+        dT.append(out4[0] - g1["TALOC"][i])
+        if Ta >= Ts or zen >= 90.0:
+            stable_exact.append(abs(out4[1] - v * np.log(2.5) / np.log(500.0)))
+    assert np.abs(dv).max() < 1e-1        # reference tolerance rtol=1e-1 (micro_testrun_monthly.jl:175); survey saw <=0.8 %
+    assert np.abs(dT).max() < 2.0         # K; reference tolerance rtol=1e-2 on kelvin (~2.7 K)
+    assert max(stable_exact) < 1e-12      # stable branch: VLOC = VREF ln(2.5)/ln(500) exactly
+
+
+def test_config1_monthly_end_to_end(g1):
+    """Config 1 soil temperature: reference asserts rtol=1e-1 on kelvin vs NicheMapR; the oracle is within 1.5 K / 0.1 K rms."""
+    p, _ = configs.config1_monthly()
+    out, eng = configs.run_engine(OracleEngine, p)
+    T = out.soil_temperature[:, :, 0]
+    assert out.status[0] == 0
+    assert np.all(np.isfinite(T)) and T.min() > 200.0 and T.max() < 350.0     # test/example_constructors.jl:19-24
+    d = T - g1["soil_nmr"]
+    assert np.abs(d / g1["soil_nmr"]).max() < 1e-1       # the reference's assertion
+    assert np.abs(d).max() < 1.5 and np.sqrt((d ** 2).mean()) < 0.1
+    assert np.abs(out.sky_temperature[:, 0] / g1["TSKYC"] - 1).max() < 2e-3
+    c = eng.counters()
+    assert c["n_day_passes"] == 36 and c["n_accept"] > 1000
+
+
+def test_config2_daily_end_to_end(g2):
+    """Config 2: reference asserts soil T rtol=1e-1 (first 3 coarse nodes), moisture and conductivity rtol=1e1."""
+    p, _ = configs.config2_daily()
+    out, eng = configs.run_engine(OracleEngine, p)
+    ci = np.arange(0, 19, 2)
+    T, th = out.soil_temperature[:, ci, 0], out.soil_moisture[:, ci, 0]
+    lam = out.soil_thermal_conductivity[:, ci, 0]
+    assert out.status[0] == 0
+    assert np.abs(T[:, :3] / g2["soil_nmr"][:, :3] - 1).max() < 1e-1
+    assert np.all(np.abs(th[:, :8] - g2["soilmoist_nmr"][:, :8]) <= 1e1 * np.maximum(np.abs(th[:, :8]), g2["soilmoist_nmr"][:, :8]))
+    assert np.all(np.abs(lam[:, :3] - g2["tcond_nmr"][:, :3]) <= 1e1 * np.maximum(lam[:, :3], g2["tcond_nmr"][:, :3]))
+    # much tighter than the reference asks
+    d = T - g2["soil_nmr"]
+    assert np.sqrt((d ** 2).mean()) < 0.5 and np.abs(d).max() < 8.0
+    assert np.sqrt(((th - g2["soilmoist_nmr"]) ** 2).mean()) < 0.03
+    assert np.abs(out.sky_temperature[:, 0] - g2["TSKYC"]).max() < 1e-4
+    assert np.all(out.soil_moisture[1:, 18, 0] == 1.0 - 1.3 / 2.56)    # deepest node returned saturated (campbell.jl:340-342)
+    assert np.all((out.soil_moisture >= 0) & (out.soil_moisture <= 1))
+
+
+def _infil_run(L, alg, theta0, ET, nsteps):
+    """reference test/infiltration_algorithm_comparison.jl:9-37"""
+    import microclimate_jl_b200 as mc
+    n = 19
+    depths = 0.15 * np.arange(1, n + 1)
+    model = mc.MicroModel(depths=depths, soil_hydraulic_model=mc.CampbellSoilHydraulics(infiltration_algorithm=alg),
+                          config=mc.MicroConfig(soil_moisture_strategy=mc.DynamicSoilMoisture(1e-6, 200, 360.0)))
+    desc = M.model_desc(model, mc.ConsecutiveDayMode())
+    prof = mc.example_soil_profile(depths, bulk_density=1300.0, mineral_density=2650.0)
+    inp = mc.MicroInputs(site=mc.Site(), soil_profile=prof, environment_daily=None, environment_hourly=None,
+                         initial_soil_moisture=np.full(n, theta0))
+    sb = M.SitesBatch.from_inputs(model, [inp])
+    cs = sb.c_sites()
+    theta = np.full(n, theta0)
+    T = np.full(n, 293.0)
+    L.mco_infiltration_steps(C.byref(desc), C.byref(cs), 101325.0, 0.5, 1.0, ET,
+                             T.ctypes.data_as(C.POINTER(C.c_double)), theta.ctypes.data_as(C.POINTER(C.c_double)), nsteps)
+    return theta
+
+
+def test_infiltration_algorithms_agree(L):
+    """psi-form vs Phi-form agree to rtol=1e-2 (reference test/infiltration_algorithm_comparison.jl:41-63)."""
+    import microclimate_jl_b200 as mc
+    for theta0, ET, n in ((0.25, 5e-7, 20), (0.40, 1e-7, 20)):
+        a = _infil_run(L, mc.MatricPotentialAlgorithm(), theta0, ET, n)
+        b = _infil_run(L, mc.MatricFluxPotentialAlgorithm(), theta0, ET, n)
+        assert not np.isnan(a).any() and not np.isnan(b).any()
+        assert np.allclose(a, b, rtol=1e-2)
+    for alg in (mc.MatricPotentialAlgorithm(), mc.MatricFluxPotentialAlgorithm()):
+        c = _infil_run(L, alg, 0.05, 1e-6, 40)
+        assert not np.isnan(c).any() and np.all((c >= 0) & (c <= 0.51))
+
+
+def test_fastpow_accuracy(L):
+    """FastPower.fastpower is a Float32 approximation: within 1e-3 relative of pow on the controller's range."""
+    for x in (1e-4, 1e-3, 0.03, 0.5, 1.0, 3.0, 50.0):
+        for y in (0.14, 0.08):
+            assert L.mco_fastpow(x, y) == pytest.approx(x ** y, rel=2e-3)
+
+
+def test_phase_transition_freeze_thaw(L):
+    """latent_heat.jl:21-112: a downward 0 degC crossing clamps the layer pair to 0 degC and banks latent heat; thaw releases it."""
+    N = 4
+    depths = np.array([0.0, 0.1, 0.2, 0.4])
+    theta = np.full(N, 0.2)
+    Tpast = np.array([274.15, 274.15, 275.15, 276.15])
+    T = np.array([271.15, 272.65, 275.15, 276.15])
+    S = np.zeros(N)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L.mco_phase_transition(N, p(depths), p(T), p(Tpast), p(S), p(theta))
+    assert T[0] == 273.15 and T[1] == 273.15 and T[2] == 275.15
+    mass = 0.1 * 1000 * 0.2
+    assert S[0] == pytest.approx((274.15 - 0.5 * (271.15 + 272.65)) * mass * 4184.0)
+    assert S[0] <= 333550.0 * mass
+    # thaw back: budget is drawn down and the clamp holds while it lasts
+    Tpast2 = np.array([272.15, 272.15, 275.15, 276.15])
+    T2 = np.array([274.15, 274.15, 275.15, 276.15])
+    S0 = S[0]
+    L.mco_phase_transition(N, p(depths), p(T2), p(Tpast2), p(S), p(theta))
+    assert S[0] == pytest.approx(max(0.0, S0 - 2.0 * mass * 4184.0))
+    assert (T2[0] == 273.15) == (S[0] > 0)
