@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""bench.py — site-days/s of hourly soil temperature + moisture on N B200s (BASELINE.json metric).
+
+A "step" integrates ONE DAY (24 hourly outputs) for every site of the rank's shard of the synthetic grid
+(BASELINE.json config 5: N=19 nodes, consecutive days, dynamic soil moisture, hourly rain, no snow); successive steps
+are successive days, state resident in HBM.  Weak scaling: every rank owns --sites sites.
+
+  value   kernel-only throughput, forcing already in HBM (CUDA events on the engine's stream, max over ranks)
+  e2e     the same metric through the C-ABI call with pinned HOST buffers: H2D forcing + kernel + D2H of the hourly
+          soil T and moisture profiles inside the timed region
+  --impl reference   the CPU path (the oracle port: Julia is not installable here) on all host cores, bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FIELDS = ("soil_temperature", "soil_moisture")
+# executed FP64 flop per site-day of the benchmark grid (DADD + DMUL + 2 DFMA), calibrated with ncu: profiles/README.md
+FLOP_PER_SITE_DAY = None
+ALG_BYTES_PER_SITE_DAY = (10 * 24 + 7) * 8 + 2 * 19 * 24 * 8     # hourly+daily forcing read, hourly T+theta written
+
+
+def _pinned(shape):
+    import torch
+    return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+
+
+def _pin_forcing(fb):
+    from microclimate_jl_b200 import _abi as A
+    for f in A.FORCING_HOURLY + A.FORCING_DAILY:
+        a = getattr(fb, f)
+        if a is not None:
+            p = _pinned(a.shape)
+            p[...] = a
+            setattr(fb, f, p)
+    return fb
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def __enter__(self):
+        def loop():
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop.is_set():
+                try:
+                    o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([x.strip() for x in o.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._t = threading.Thread(target=loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_run(desc, S_total, s0, n_sites, day0, ndays, threads=0):
+    """Time the oracle (CPU restatement of the reference path) on `n_sites` sites x `ndays` days with all host cores."""
+    from microclimate_jl_b200 import marshal as M, synthetic as syn
+    from oracle.oracle import OracleEngine
+    sites = syn.make_sites(s0, s0 + n_sites, S_total)
+    eng = OracleEngine(desc, n_sites)
+    eng.set_sites(sites)
+    times = []
+    for d in range(day0, day0 + ndays):
+        f = syn.make_forcing(s0, s0 + n_sites, S_total, d, 1)
+        out = M.OutputBatch(1, desc.n_soil, n_sites, FIELDS)
+        t = time.perf_counter()
+        eng.step_days(d, f, out, n_threads=threads)
+        times.append(time.perf_counter() - t)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sites", type=int, default=1 << 20, help="sites per GPU (weak scaling)")
+    ap.add_argument("--cpu-sites", type=int, default=0, help="sites of the bounded CPU sample (0 = sized for ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from microclimate_jl_b200 import marshal as M, synthetic as syn
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    S = args.sites
+    S_total = S * max(world, args.gpus)
+    cores = os.cpu_count() or 1
+    config = {"workload": "synthetic site grid (BASELINE config 5): %d sites/GPU x 1 day per step, N=19 soil nodes, ConsecutiveDayMode, "
+                          "DynamicSoilMoisture(1e-6,500,360 s), HourlyRainfall, no snow, hourly T+theta profiles out" % S,
+              "sites_per_gpu": S, "total_sites": S_total, "days_per_step": 1, "n_soil": 19, "seed": syn.SEED,
+              "l2": "inputs_larger_than_L2 (%.2f GB forcing + %.2f GB outputs per step)" % (S * 247 * 8 / 1e9, S * 38 * 24 * 8 / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = args.cpu_sites or max(64, min(S, 768 * cores))
+        times = cpu_run(desc, S_total, 0, n, 0, args.warmup + args.steps)
+        tt = times[args.warmup:]
+        v = n * len(tt) / sum(tt)
+        line = {"impl": "reference", "metric": "site-days/sec (hourly soil T+moisture)", "value": v, "unit": "site-days/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(tt) / len(tt), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "site-days/s", "cores": cores, "kind": "port",
+                                 "sample": "%d sites x 1 day per step (first sites of the grid), OpenMP over sites; Julia reference not installable here" % n},
+                "e2e": {"value": v, "unit": "site-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from microclimate_jl_b200.simulation import SoilEngine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ndays = args.warmup + args.steps
+    s0 = rank * S
+    t_gen = time.perf_counter()
+    sites = syn.make_sites(s0, s0 + S, S_total)
+    eng = SoilEngine(desc, S, device=local_rank)
+    peak_tf = eng.measure_fp64_peak()
+    eng.set_sites(sites)
+    # forcing for all warm-up + timed days: pinned host copy (e2e leg) and device-resident copy (value leg)
+    from microclimate_jl_b200 import _abi as A
+    host_days = [_pin_forcing(syn.make_forcing(s0, s0 + S, S_total, d, 1)) for d in range(2 * ndays)]
+    t_gen = time.perf_counter() - t_gen
+    out_host = M.OutputBatch(1, desc.n_soil, S, ())
+    for f in FIELDS:
+        setattr(out_host, f, _pinned((24, desc.n_soil, S)))
+    h2d = sum(getattr(host_days[0], f).nbytes for f in A.FORCING_HOURLY + A.FORCING_DAILY if getattr(host_days[0], f) is not None)
+    d2h = sum(getattr(out_host, f).nbytes for f in FIELDS) + 4 * S
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value leg: device-resident forcing + outputs -------------------------------------------------------------
+    dev_days = []
+    for fb in host_days[:ndays]:
+        d = {f: torch.from_numpy(getattr(fb, f)).cuda(non_blocking=True) for f in A.FORCING_HOURLY + A.FORCING_DAILY if getattr(fb, f) is not None}
+        dev_days.append(d)
+    out_dev = {f: torch.zeros((24, desc.n_soil, S), dtype=torch.float64, device="cuda") for f in FIELDS}
+    torch.cuda.synchronize()
+    optr = {f: t.data_ptr() for f, t in out_dev.items()}
+    day = 0
+    for _ in range(args.warmup):
+        eng.step_days_device(day, 1, {k: v.data_ptr() for k, v in dev_days[day].items()}, optr)
+        eng.synchronize()
+        day += 1
+    eng.reset_counters()
+    barrier()
+    kernel_ms = []
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.step_days_device(day, 1, {k: v.data_ptr() for k, v in dev_days[day].items()}, optr)
+            eng.synchronize()
+            kernel_ms.append(eng.counters()["gpu_ms"])          # CUDA events around the launch, on the engine's stream
+            day += 1
+        barrier()
+        wall_value = time.perf_counter() - t0
+    dev_time = reduce_max(sum(kernel_ms) * 1e-3)
+    counters = eng.counters()
+    status_bad = int((eng.status() != 0).sum())
+    value = world * S * args.steps / dev_time
+    del dev_days
+    torch.cuda.empty_cache()
+
+    # ---- e2e leg: pinned host buffers through mc_step_days (H2D + kernel + D2H inside the timed region) --------------
+    for _ in range(min(2, args.warmup)):
+        eng.step_days(day, host_days[day], out_host)
+        day += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step_days(day, host_days[day], out_host)
+        day += 1
+    barrier()
+    e2e_time = reduce_max(time.perf_counter() - t0)
+    e2e = world * S * args.steps / e2e_time
+    checksum = float(out_host.soil_temperature[-1, 0, :1024].sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    flop_sd = FLOP_PER_SITE_DAY
+    per_gpu = value / world
+    roof = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf, "peak_how": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+            "achieved": (flop_sd * per_gpu / 1e12) if flop_sd else None, "frac": (flop_sd * per_gpu / 1e12 / peak_tf) if flop_sd else None,
+            "flop_per_site_day": flop_sd, "traffic": None,
+            "hbm": {"achieved": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9, "peak": 6536.0, "unit": "GB/s", "frac": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9 / 6536.0,
+                    "alg_bytes_per_site_day": ALG_BYTES_PER_SITE_DAY},
+            "work_per_site_day": {k: counters[k] / max(1, counters["n_site_days"] - S * args.warmup) for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter")}}
+    line = {"metric": "site-days/sec (hourly soil T+moisture)", "value": value, "unit": "site-days/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_time / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk.summary(),
+            "e2e": {"value": e2e, "unit": "site-days/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_time / args.steps},
+            "gpu_launches": args.steps, "roofline": roof, "flagged_sites": status_bad, "wall_value_s": wall_value, "setup_s": t_gen, "checksum": checksum}
+    if world == 1 and not args.no_cpu_baseline:
+        n = args.cpu_sites or max(64, min(S, 768 * cores))
+        times = cpu_run(desc, S_total, 0, n, 0, 2)
+        line["cpu_baseline"] = {"value": n / times[1], "unit": "site-days/s", "cores": cores, "kind": "port",
+                                "sample": "%d sites x 1 day (day 1 after a 1-day warm-up), OpenMP over sites, %.1f s; C++ restatement of the reference (Julia not installable here)" % (n, times[1])}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

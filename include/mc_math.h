@@ -1,0 +1,231 @@
+/*
+ * mc_math.h — portable, bit-reproducible double-precision elementary functions.
+ *
+ * WHY: the soil path is ill-conditioned at its discontinuities (adaptive step accept/reject, the 1 %
+ * Obukhov stopping rule, the |residual| <= 10 J/kg stomatal Newton exit, Float32 step-size controller):
+ * a 1-ulp difference in ONE libm call is amplified to 1e-2 K / 1e-2 m3/m3 within simulated days (the
+ * CPU oracle shows this against itself, tests/test_conditioning.py).  CUDA's libm and the host's libm
+ * differ in the last bit, so parity through vendor libms can only ever be statistical.  Every
+ * transcendental below is built only from IEEE-754 + - * / sqrt fma and integer bit operations,
+ * which are correctly rounded on both x86-64 and sm_100a, so the CUDA engine and the CPU oracle
+ * produce IDENTICAL bits when compiled without floating-point contraction (-fmad=false / -ffp-contract=off).
+ * The reference itself (Julia) uses its own pure-Julia libm, not glibc; agreement of these functions
+ * with glibc to <= 1-2 ulp (pow/exp10: a few 1e-16 relative) is pinned in tests/test_mc_math.py.
+ *
+ * Algorithms: the classic fdlibm kernels (exp, log, atan, sin/cos kernels), restated; pow and exp10
+ * are exp(y*log x) with the rounding error of the product carried through an fma.
+ *
+ * Shared by microclimate.jl_b200/csrc (device + host-emulation) and oracle/ (host).
+ */
+#ifndef MC_MATH_H
+#define MC_MATH_H
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MCM_FN __host__ __device__ __forceinline__
+#else
+#define MCM_FN static inline
+#endif
+
+namespace mcm {
+
+#if defined(__CUDA_ARCH__)
+MCM_FN uint64_t d2u(double x) { return (uint64_t)__double_as_longlong(x); }
+MCM_FN double u2d(uint64_t u) { return __longlong_as_double((long long)u); }
+MCM_FN double ffma(double a, double b, double c) { return __fma_rn(a, b, c); }
+#else
+MCM_FN uint64_t d2u(double x) { union { double d; uint64_t u; } v; v.d = x; return v.u; }
+MCM_FN double u2d(uint64_t u) { union { double d; uint64_t u; } v; v.u = u; return v.d; }
+MCM_FN double ffma(double a, double b, double c) { return __builtin_fma(a, b, c); }
+#endif
+MCM_FN int32_t hi_word(double x) { return (int32_t)(d2u(x) >> 32); }
+MCM_FN uint32_t lo_word(double x) { return (uint32_t)(d2u(x) & 0xffffffffu); }
+MCM_FN double with_hi(double x, int32_t hi) { return u2d(((uint64_t)(uint32_t)hi << 32) | (d2u(x) & 0xffffffffu)); }
+
+/* ---- exp ---------------------------------------------------------------------------------- */
+MCM_FN double exp(double x)
+{
+    const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
+    const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                 P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (x != x) return x;
+    if (x > 7.09782712893383973096e+02) return u2d(0x7ff0000000000000ULL);
+    if (x < -7.45133219101941108420e+02) return 0.0;
+    double hi = 0.0, lo = 0.0; int k = 0;
+    const double ax = x < 0.0 ? -x : x;
+    if (ax > 0.34657359027997264) {                 /* |x| > 0.5 ln2 */
+        k = (int)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+        hi = x - (double)k * ln2HI;
+        lo = (double)k * ln2LO;
+        x = hi - lo;
+    } else if (ax < 3.725290298461914e-09) {        /* |x| < 2^-28 */
+        return 1.0 + x;
+    }
+    const double t = x * x;
+    const double c = x - t * ffma(t, ffma(t, ffma(t, ffma(t, P5, P4), P3), P2), P1);
+    double y;
+    if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+    y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+    if (k >= -1021) {
+        if (k == 1024) return y * 2.0 * 8.98846567431158e307;   /* 2^1023 */
+        return u2d(d2u(y) + ((uint64_t)(int64_t)k << 52));
+    }
+    return u2d(d2u(y) + ((uint64_t)(int64_t)(k + 1000) << 52)) * 9.33263618503218878990e-302;   /* 2^-1000 */
+}
+
+/* ---- log ---------------------------------------------------------------------------------- */
+MCM_FN double log(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    int32_t hx = hi_word(x); const uint32_t lx = lo_word(x);
+    int k = 0;
+    if (hx < 0x00100000) {                          /* x < 2^-1022 */
+        if (((hx & 0x7fffffff) | lx) == 0) return -u2d(0x7ff0000000000000ULL);   /* log(+-0) = -inf */
+        if (hx < 0) return u2d(0x7ff8000000000000ULL);                            /* log(-#) = NaN */
+        k -= 54; x *= 1.80143985094819840000e+16; hx = hi_word(x);                /* subnormal: scale by 2^54 */
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int32_t i0 = (hx + 0x95f64) & 0x100000;
+    x = with_hi(x, hx | (i0 ^ 0x3ff00000));         /* normalise x or x/2 */
+    k += (i0 >> 20);
+    const double f = x - 1.0;
+    const double dk = (double)k;
+    if ((0x000fffff & (2 + hx)) < 3) {              /* |f| < 2^-20 */
+        if (f == 0.0) { if (k == 0) return 0.0; return dk * ln2_hi + dk * ln2_lo; }
+        const double R = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - R;
+        return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    int32_t i = hx - 0x6147a;
+    const double w = z * z;
+    const int32_t j = 0x6b851 - hx;
+    const double t1 = w * ffma(w, ffma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * ffma(w, ffma(w, ffma(w, Lg7, Lg5), Lg3), Lg1);
+    i |= j;
+    const double R = t2 + t1;
+    if (i > 0) {
+        const double hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+MCM_FN double log10(double x) { return log(x) * 4.34294481903251816668e-01; }
+
+/* exp(a*b) with the rounding error of the product a*b (and an optional low word of b) carried through */
+MCM_FN double exp_prod(double a, double b, double b_lo)
+{
+    const double p = a * b;
+    const double e = ffma(a, b, -p) + a * b_lo;
+    const double r = exp(p);
+    return ffma(r, e, r);
+}
+MCM_FN double exp10(double x) { return exp_prod(x, 2.302585092994046, -2.1707562233822494e-16); }
+MCM_FN double exp2(double x) { return exp_prod(x, 0.6931471805599453, 2.3190468138462996e-17); }
+
+/* pow for the cases the soil path uses: x > 0 (any y), x == 0, and x < 0 with integer-valued y */
+MCM_FN double pow(double x, double y)
+{
+    if (y == 0.0) return 1.0;
+    if (x != x || y != y) return x + y;
+    if (x == 0.0) return y < 0.0 ? u2d(0x7ff0000000000000ULL) : 0.0;
+    if (x < 0.0) {
+        const double yi = floor(y);
+        if (yi != y) return u2d(0x7ff8000000000000ULL);
+        const double r = exp_prod(y, log(-x), 0.0);
+        return (yi * 0.5 != floor(yi * 0.5)) ? -r : r;
+    }
+    return exp_prod(y, log(x), 0.0);
+}
+
+/* ---- atan ---------------------------------------------------------------------------------- */
+MCM_FN double atan(double x)
+{
+    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01, aT2 = 1.42857142725034663711e-01,
+                 aT3 = -1.11111104054623557880e-01, aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
+                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02, aT8 = 4.97687799461593236017e-02,
+                 aT9 = -3.65315727442169155270e-02, aT10 = 1.62858201153657823623e-02;
+    const int32_t hx = hi_word(x);
+    const int32_t ix = hx & 0x7fffffff;
+    double hi_c, lo_c; int id;
+    if (ix >= 0x44100000) {                         /* |x| >= 2^66 */
+        if (x != x) return x + x;
+        const double r = 1.57079632679489655800e+00 + 6.12323399573676603587e-17;
+        return hx > 0 ? r : -r;
+    }
+    if (ix < 0x3fdc0000) {                          /* |x| < 0.4375 */
+        if (ix < 0x3e200000) return x;              /* |x| < 2^-29 */
+        id = -1; hi_c = 0.0; lo_c = 0.0;
+    } else {
+        x = x < 0.0 ? -x : x;
+        if (ix < 0x3ff30000) {                      /* |x| < 1.1875 */
+            if (ix < 0x3fe60000) { id = 0; hi_c = 4.63647609000806093515e-01; lo_c = 2.26987774529616870924e-17; x = (2.0 * x - 1.0) / (2.0 + x); }
+            else { id = 1; hi_c = 7.85398163397448278999e-01; lo_c = 3.06161699786838301793e-17; x = (x - 1.0) / (x + 1.0); }
+        } else {
+            if (ix < 0x40038000) { id = 2; hi_c = 9.82793723247329054082e-01; lo_c = 1.39033110312309984516e-17; x = (x - 1.5) / (1.0 + 1.5 * x); }
+            else { id = 3; hi_c = 1.57079632679489655800e+00; lo_c = 6.12323399573676603587e-17; x = -1.0 / x; }
+        }
+    }
+    const double z = x * x;
+    const double w = z * z;
+    const double s1 = z * ffma(w, ffma(w, ffma(w, ffma(w, ffma(w, aT10, aT8), aT6), aT4), aT2), aT0);
+    const double s2 = w * ffma(w, ffma(w, ffma(w, ffma(w, aT9, aT7), aT5), aT3), aT1);
+    if (id < 0) return x - x * (s1 + s2);
+    const double r = hi_c - ((x * (s1 + s2) - lo_c) - x);
+    return hx < 0 ? -r : r;
+}
+
+/* ---- cos on [-3pi/4, 3pi/4] (the path only needs zenith angles in [0, 90] degrees) ---------- */
+MCM_FN double kernel_cos(double x, double y)
+{
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const int32_t ix = hi_word(x) & 0x7fffffff;
+    const double z = x * x;
+    const double r = z * ffma(z, ffma(z, ffma(z, ffma(z, ffma(z, C6, C5), C4), C3), C2), C1);
+    if (ix < 0x3FD33333) return 1.0 - (0.5 * z - (z * r - x * y));
+    double qx;
+    if (ix > 0x3fe90000) qx = 0.28125;
+    else qx = u2d((uint64_t)(uint32_t)(ix - 0x00200000) << 32);
+    const double hz = 0.5 * z - qx;
+    const double a = 1.0 - qx;
+    return a - (hz - (z * r - x * y));
+}
+MCM_FN double kernel_sin(double x, double y)
+{
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double z = x * x;
+    const double v = z * x;
+    const double r = ffma(z, ffma(z, ffma(z, ffma(z, S6, S5), S4), S3), S2);
+    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+MCM_FN double cos(double x)
+{
+    const double ax = x < 0.0 ? -x : x;
+    if (ax <= 0.78539816339744830962) return kernel_cos(ax, 0.0);
+    if (ax <= 2.35619449019234492885) {             /* one step of pi/2 reduction: cos(x) = -sin(x - pi/2) */
+        const double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+        const double z = ax - pio2_1;
+        const double y0 = z - pio2_1t;
+        const double y1 = (z - y0) - pio2_1t;
+        return -kernel_sin(y0, y1);
+    }
+    return u2d(0x7ff8000000000000ULL);              /* out of the supported range on purpose */
+}
+
+MCM_FN double pow4(double x) { const double x2 = x * x; return x2 * x2; }
+
+}  // namespace mcm
+#endif /* MC_MATH_H */

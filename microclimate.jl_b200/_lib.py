@@ -1,0 +1,82 @@
+"""Loader of the CUDA C-ABI library (csrc/libmicroclimate_b200.so, include/microclimate_b200.h).
+
+The library is built IN-TREE by `build()` (nvcc, sm_100a) so it travels with the repo snapshot.  There is
+no CPU implementation behind this loader: if the library cannot be built/loaded, or no CUDA device is
+present, the engine raises — it never falls back to anything else.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO = os.path.join(CSRC, "libmicroclimate_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "microclimate_b200.h")
+SOURCES = [os.path.join(CSRC, "mc_api.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, "mc_device.cuh"), INCLUDE, os.path.join(os.path.dirname(INCLUDE), "mc_math.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+EXPORTS = ("mc_abi_version", "mc_backend_name", "mc_default_fluid", "mc_default_model", "mc_create", "mc_destroy",
+           "mc_last_error", "mc_set_sites", "mc_get_state", "mc_set_state", "mc_step_days", "mc_step_days_device",
+           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak")
+
+
+def _nvcc():
+    return shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+
+
+def is_stale():
+    return (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libmicroclimate_b200.so (cross-compiles without a GPU)."""
+    if not force and not is_stale():
+        return SO
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libmicroclimate_b200.so (there is no CPU fallback)")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if is_stale():
+        if _nvcc() is None and os.path.exists(SO):
+            pass            # prebuilt library shipped with the snapshot; no compiler on this box
+        else:
+            build()
+    L = C.CDLL(SO)
+    H = C.c_void_p
+    L.mc_abi_version.restype = C.c_int
+    L.mc_backend_name.restype = C.c_char_p
+    L.mc_default_fluid.argtypes = [C.POINTER(A.FluidConstants)]
+    L.mc_default_model.argtypes = [C.POINTER(A.ModelDesc)]
+    L.mc_create.argtypes = [C.POINTER(A.ModelDesc), C.c_int64, C.c_int, C.POINTER(H)]
+    L.mc_destroy.argtypes = [H]
+    L.mc_destroy.restype = None
+    L.mc_last_error.argtypes = [H]
+    L.mc_last_error.restype = C.c_char_p
+    L.mc_set_sites.argtypes = [H, C.POINTER(A.SitesSoA), C.POINTER(A.InitialSoA)]
+    L.mc_get_state.argtypes = [H, C.POINTER(A.StateSoA)]
+    L.mc_set_state.argtypes = [H, C.POINTER(A.StateSoA)]
+    L.mc_step_days.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
+    L.mc_step_days_device.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
+    L.mc_synchronize.argtypes = [H]
+    L.mc_get_counters.argtypes = [H, C.POINTER(A.Counters)]
+    L.mc_reset_counters.argtypes = [H]
+    L.mc_get_status.argtypes = [H, C.POINTER(C.c_int32)]
+    L.mc_measure_fp64_peak.argtypes = [H, C.POINTER(C.c_double)]
+    _lib = L
+    return L

@@ -1,0 +1,443 @@
+/*
+ * mc_api.cu — C ABI of the B200 soil engine (include/microclimate_b200.h) + the CUDA kernels.
+ *
+ * One handle drives one GPU.  Site parameters and the carried per-site state live in HBM as
+ * site-fastest SoA arrays for the lifetime of the handle; mc_step_days streams a chunk of days of
+ * forcing in, launches ONE persistent thread-per-site kernel for the whole chunk, and streams the
+ * selected output rows back.  There is no CPU compute path in this library: without a CUDA
+ * device every entry point fails with an error string.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "mc_device.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define MC_CUDA(h, call)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t _e = (call);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                                      \
+            return -100 - (int)_e;                                                                             \
+        }                                                                                                      \
+    } while (0)
+
+constexpr int BLOCK = 128;
+
+}  // namespace
+
+/* ---------------------------------------------------------------- kernels ---- */
+template <int NA>
+__global__ void __launch_bounds__(BLOCK) soil_chunk_kernel(const mcd::KArgs a)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.S) return;
+    mcd::Counters cn = {};
+    mcd::solve_site<NA>(a, s, cn);
+    if (a.counters) {
+        atomicAdd(a.counters + 0, (unsigned long long)cn.n_rhs);
+        atomicAdd(a.counters + 1, (unsigned long long)cn.n_accept);
+        atomicAdd(a.counters + 2, (unsigned long long)cn.n_reject);
+        atomicAdd(a.counters + 3, (unsigned long long)cn.n_obukhov);
+        atomicAdd(a.counters + 4, (unsigned long long)cn.n_newton);
+        atomicAdd(a.counters + 5, (unsigned long long)cn.n_infil);
+        atomicAdd(a.counters + 6, (unsigned long long)cn.n_day_passes);
+    }
+}
+
+/* fresh state == what init() + the top of solve_soil! establish (reference src/simulation.jl:141-243,383-452) */
+__global__ void init_state_kernel(mcd::KArgs a, int N)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.S) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < N; i++) {
+        const int64_t k = (int64_t)i * a.S + s;
+        a.T[k] = a.has_init_T ? a.init_T[k] : qnan;
+        a.theta[k] = a.init_theta[k];
+        a.sum_phase[k] = 0.0;
+        a.fsal[k] = qnan;
+    }
+    a.pool[s] = 0.0; a.wetness[s] = 0.0; a.L_ode[s] = -0.3; a.L_prof[s] = -0.3; a.tdeep_prev[s] = qnan; a.flags[s] = 0;
+}
+
+/* DFMA throughput micro-benchmark: 8 independent FMA chains per thread */
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+/* ---------------------------------------------------------------- handle ---- */
+struct mc_handle {
+    mc_model_desc model;
+    mcd::DevModel dm;
+    int64_t S = 0;
+    int device = 0;
+    int N = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    /* device arrays (all one arena) */
+    double* arena = nullptr; size_t arena_doubles = 0;
+    double *z0, *slope, *svf, *albedo, *bd, *md, *lam_m, *c_m, *psi_e, *ks, *bb, *rootd, *init_T, *init_theta;
+    double *T, *theta, *sum_phase, *pool, *wetness, *L_ode, *L_prof, *tdeep_prev, *fsal;
+    int32_t* flags = nullptr;
+    unsigned long long* counters = nullptr;
+    bool has_init_T = false, sites_set = false;
+    int64_t days_done = 0;
+    /* chunk staging (grown on demand) */
+    double* stage_in = nullptr; size_t stage_in_doubles = 0;
+    double* stage_out = nullptr; size_t stage_out_doubles = 0;
+    double last_ms = 0.0; unsigned long long last_launches = 0;
+};
+
+static int pick_na(int N) { return N <= 10 ? 10 : (N <= 19 ? 19 : MC_MAX_SOIL_NODES); }
+
+static int validate_model(const mc_model_desc* m, std::string& err)
+{
+    if (!m) { err = "model is NULL"; return -1; }
+    if (m->n_soil < 3 || m->n_soil > MC_MAX_SOIL_NODES) { err = "n_soil must be in 3.." + std::to_string(MC_MAX_SOIL_NODES); return -1; }
+    if (m->n_snow != 0) { err = "SnowModel (n_snow=8) is not implemented on the CUDA path yet"; return -3; }
+    if (!(m->moisture_timestep_s > 0.0) || m->moisture_timestep_s > 3600.0) { err = "moisture_timestep_s must be in (0, 3600]"; return -1; }
+    for (int i = 1; i < m->n_soil; i++) if (!(m->depths_m[i] > m->depths_m[i - 1])) { err = "depths must be strictly increasing"; return -1; }
+    return 0;
+}
+
+template <int NA>
+static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
+{
+    const int grid = (int)((a.S + BLOCK - 1) / BLOCK);
+    soil_chunk_kernel<NA><<<grid, BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+static void fill_site_state_args(mc_handle* h, mcd::KArgs& a)
+{
+    std::memset(&a, 0, sizeof(a));
+    a.S = h->S; a.has_init_T = h->has_init_T;
+    a.z0 = h->z0; a.slope = h->slope; a.svf = h->svf; a.albedo = h->albedo; a.bd = h->bd; a.md = h->md; a.lam_m = h->lam_m; a.c_m = h->c_m;
+    a.psi_e = h->psi_e; a.ks = h->ks; a.bb = h->bb; a.rootd = h->rootd; a.init_T = h->init_T; a.init_theta = h->init_theta;
+    a.T = h->T; a.theta = h->theta; a.sum_phase = h->sum_phase; a.pool = h->pool; a.wetness = h->wetness; a.L_ode = h->L_ode;
+    a.L_prof = h->L_prof; a.tdeep_prev = h->tdeep_prev; a.fsal = h->fsal; a.flags = h->flags; a.counters = h->counters;
+}
+
+/* ---------------------------------------------------------------- C ABI ---- */
+extern "C" {
+
+int mc_abi_version(void) { return 1; }
+const char* mc_backend_name(void) { return "cuda-sm_100a"; }
+
+void mc_default_fluid(mc_fluid_constants* f)
+{
+    f->molar_mass_water = 0.018016; f->molar_mass_air = 0.028966; f->ideal_gas_departure = 1.0053; f->cp_dry_air = 1004.84;
+    f->cp_water_vapour = 1846.40; f->gas_constant = 8.314462618; f->stefan_boltzmann = 5.670374419e-8; f->standard_gravity = 9.80665;
+    f->standard_pressure = 101325.0; f->latent_heat_a = 2.5012e6; f->latent_heat_b = 2.3787e3; f->molar_latent_heat_a = 45144.0;
+    f->molar_latent_heat_b = 48.0;
+}
+
+/* MicroModel()/MicroConfig() defaults (reference src/types.jl:71-120, src/constants.jl:8) */
+void mc_default_model(mc_model_desc* m)
+{
+    std::memset(m, 0, sizeof(*m));
+    static const double dep_cm[19] = {0.0, 1.25, 2.5, 3.75, 5.0, 7.5, 10.0, 12.5, 15.0, 17.5, 20.0, 25.0, 30.0, 40.0, 50.0, 75.0, 100.0, 150.0, 200.0};
+    m->n_soil = 19; m->n_snow = 0;
+    for (int i = 0; i < 19; i++) m->depths_m[i] = dep_cm[i] / 100.0;
+    m->reference_height_m = 2.0; m->local_height_m = 0.01;
+    m->reltol = 1e-6; m->abstol = 1e-3; m->maximum_surface_temperature_K = 273.15 + 85.0;
+    m->de_vries_shape_factor = 0.1; m->recirculation_power = 4.0; m->return_flow_threshold = 0.162;
+    m->root_resistance = 2.5e10; m->stomatal_closure_potential = -1500.0; m->leaf_resistance = 2.0e6;
+    m->stomatal_stability_parameter = 10.0; m->root_radius = 0.001;
+    m->infiltration_algorithm = MC_INFIL_MATRIC_POTENTIAL;
+    m->karman_constant = 0.4; m->dyer_constant = 16.0;
+    m->time_mode = MC_TIME_CONSECUTIVE; m->iterations_per_day = 1; m->spinup_first_day = 0;
+    m->convergence_kind = MC_CONV_FIXED; m->convergence_iterations = 3; m->convergence_tolerance_K = 0.0;
+    m->rainfall_schedule = MC_RAIN_DAILY; m->moisture_strategy = MC_MOIST_PRESCRIBED;
+    m->moisture_tolerance = 1e-6; m->moisture_max_iterations = 500; m->moisture_timestep_s = 360.0;
+    m->max_surface_pool = 10000.0; m->atmospheric_radiation = MC_ATMRAD_CAMPBELL_NORMAN;
+    mc_default_fluid(&m->fluid);
+}
+
+const char* mc_last_error(const mc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle** out)
+{
+    if (out) *out = nullptr;
+    int rc = validate_model(model, g_create_error);
+    if (rc) return rc;
+    if (n_sites <= 0 || !out) { g_create_error = "n_sites must be positive and out non-NULL"; return -1; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU path";
+        return -2;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return -1; }
+    mc_handle* h = new mc_handle();
+    h->model = *model; h->S = n_sites; h->device = device; h->N = model->n_soil;
+    mcd::build_dev_model(*model, h->dm);
+    auto fail = [&](const char* what, cudaError_t ce) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ce); mc_destroy(h); return -100 - (int)ce; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    const size_t S = (size_t)n_sites, N = (size_t)h->N;
+    const size_t per_site = 4 + 5, per_node = 8 + 2 + 4;
+    h->arena_doubles = S * (per_site + per_node * N);
+    if ((e = cudaMalloc(&h->arena, h->arena_doubles * sizeof(double))) != cudaSuccess) return fail("cudaMalloc(state arena)", e);
+    double* p = h->arena;
+    auto take = [&](size_t n) { double* q = p; p += n; return q; };
+    h->z0 = take(S); h->slope = take(S); h->svf = take(S); h->albedo = take(S);
+    h->bd = take(N * S); h->md = take(N * S); h->lam_m = take(N * S); h->c_m = take(N * S);
+    h->psi_e = take(N * S); h->ks = take(N * S); h->bb = take(N * S); h->rootd = take(N * S);
+    h->init_T = take(N * S); h->init_theta = take(N * S);
+    h->T = take(N * S); h->theta = take(N * S); h->sum_phase = take(N * S); h->fsal = take(N * S);
+    h->pool = take(S); h->wetness = take(S); h->L_ode = take(S); h->L_prof = take(S); h->tdeep_prev = take(S);
+    if ((e = cudaMalloc(&h->flags, S * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
+    if ((e = cudaMalloc(&h->counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+    if ((e = cudaMemset(h->counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
+    *out = h;
+    return 0;
+}
+
+void mc_destroy(mc_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->arena); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int mc_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init)
+{
+    if (!h) return -1;
+    if (!s || !init || !init->initial_soil_moisture) { h->err = "sites/init must be non-NULL and initial_soil_moisture given"; return -1; }
+    MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S, N = (size_t)h->N, bS = S * sizeof(double), bNS = N * bS;
+    const double* site_src[4] = {s->roughness_height, s->slope, s->sky_view_fraction, s->albedo};
+    double* site_dst[4] = {h->z0, h->slope, h->svf, h->albedo};
+    const double* node_src[8] = {s->bulk_density, s->mineral_density, s->mineral_conductivity, s->mineral_heat_capacity,
+                                 s->air_entry_water_potential, s->saturated_hydraulic_conductivity, s->campbell_b_parameter, s->root_density};
+    double* node_dst[8] = {h->bd, h->md, h->lam_m, h->c_m, h->psi_e, h->ks, h->bb, h->rootd};
+    for (int k = 0; k < 4; k++) { if (!site_src[k]) { h->err = "mc_sites_soa has a NULL site field"; return -1; } MC_CUDA(h, cudaMemcpyAsync(site_dst[k], site_src[k], bS, cudaMemcpyHostToDevice, h->stream)); }
+    for (int k = 0; k < 8; k++) { if (!node_src[k]) { h->err = "mc_sites_soa has a NULL node field"; return -1; } MC_CUDA(h, cudaMemcpyAsync(node_dst[k], node_src[k], bNS, cudaMemcpyHostToDevice, h->stream)); }
+    h->has_init_T = init->initial_soil_temperature != nullptr;
+    if (h->has_init_T) MC_CUDA(h, cudaMemcpyAsync(h->init_T, init->initial_soil_temperature, bNS, cudaMemcpyHostToDevice, h->stream));
+    MC_CUDA(h, cudaMemcpyAsync(h->init_theta, init->initial_soil_moisture, bNS, cudaMemcpyHostToDevice, h->stream));
+    mcd::KArgs a; fill_site_state_args(h, a);
+    init_state_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(a, h->N);
+    MC_CUDA(h, cudaGetLastError());
+    MC_CUDA(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), h->stream));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->days_done = 0; h->sites_set = true;
+    return 0;
+}
+
+static int copy_state(mc_handle* h, const mc_state_soa* st, bool to_host)
+{
+    MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S, N = (size_t)h->N, bS = S * sizeof(double), bNS = N * bS;
+    struct Item { double* host; double* dev; size_t bytes; };
+    const Item items[] = {{st->soil_temperature, h->T, bNS}, {st->soil_moisture, h->theta, bNS}, {st->sum_phase, h->sum_phase, bNS}, {st->fsal, h->fsal, bNS},
+                          {st->pool, h->pool, bS}, {st->soil_wetness, h->wetness, bS}, {st->obukhov_ode, h->L_ode, bS}, {st->obukhov_profile, h->L_prof, bS},
+                          {st->deep_temperature_prev, h->tdeep_prev, bS}};
+    for (const Item& it : items) {
+        if (!it.host) continue;
+        if (to_host) MC_CUDA(h, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
+        else MC_CUDA(h, cudaMemcpyAsync(it.dev, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (st->days_done) { if (to_host) st->days_done[0] = h->days_done; else h->days_done = st->days_done[0]; }
+    return 0;
+}
+int mc_get_state(mc_handle* h, mc_state_soa* out) { if (!h || !out) return -1; return copy_state(h, out, true); }
+int mc_set_state(mc_handle* h, const mc_state_soa* in) { if (!h || !in) return -1; return copy_state(h, in, false); }
+
+static int check_forcing(mc_handle* h, const mc_forcing_soa* f)
+{
+    const void* req[] = {f->pressure, f->reference_temperature, f->reference_wind_speed, f->reference_humidity, f->cloud_cover, f->global_radiation,
+                         f->diffuse_fraction, f->zenith_angle, f->zenith_slope_angle, f->leaf_area_index, f->shade, f->surface_emissivity,
+                         f->cloud_emissivity, f->soil_wetness, f->deep_soil_temperature, f->rainfall_daily};
+    for (const void* p : req) if (!p) { h->err = "mc_forcing_soa: a required field is NULL"; return -1; }
+    if (h->dm.rain_hourly && !f->rainfall_hourly) { h->err = "HourlyRainfall needs rainfall_hourly"; return -1; }
+    return 0;
+}
+
+int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!h) return -1;
+    if (!h->sites_set) { h->err = "mc_set_sites has not been called"; return -1; }
+    if (!f || !o || ndays <= 0) { h->err = "forcing/out must be non-NULL and ndays positive"; return -1; }
+    if (day0 != h->days_done) { h->err = "day0 must equal the number of days already integrated"; return -2; }
+    if (check_forcing(h, f)) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    mcd::KArgs a; fill_site_state_args(h, a);
+    a.day0 = day0; a.ndays = ndays;
+    a.has_albedo_daily = f->albedo_daily != nullptr; a.has_lw = f->longwave_radiation != nullptr; a.has_presc = f->prescribed_soil_moisture != nullptr;
+    a.f_P = f->pressure; a.f_T = f->reference_temperature; a.f_wind = f->reference_wind_speed; a.f_rh = f->reference_humidity;
+    a.f_cloud = f->cloud_cover; a.f_solar = f->global_radiation; a.f_diffuse = f->diffuse_fraction; a.f_zen = f->zenith_angle;
+    a.f_szen = f->zenith_slope_angle; a.f_rain = f->rainfall_hourly; a.f_lw = f->longwave_radiation;
+    a.d_lai = f->leaf_area_index; a.d_shade = f->shade; a.d_eps = f->surface_emissivity; a.d_epsc = f->cloud_emissivity; a.d_wet = f->soil_wetness;
+    a.d_tdeep = f->deep_soil_temperature; a.d_rain = f->rainfall_daily; a.d_albedo = f->albedo_daily; a.presc = f->prescribed_soil_moisture;
+    a.o_T = o->soil_temperature; a.o_theta = o->soil_moisture; a.o_psi = o->soil_water_potential; a.o_h = o->soil_humidity;
+    a.o_lam = o->soil_thermal_conductivity; a.o_cp = o->soil_heat_capacity; a.o_rho = o->soil_bulk_density; a.o_pool = o->surface_water; a.o_sky = o->sky_temperature;
+    MC_CUDA(h, cudaMemcpyToSymbolAsync(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice, h->stream));
+    MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    const int na = pick_na(h->N);
+    cudaError_t e = na == 10 ? launch_chunk<10>(a, h->stream) : (na == 19 ? launch_chunk<19>(a, h->stream) : launch_chunk<MC_MAX_SOIL_NODES>(a, h->stream));
+    MC_CUDA(h, e);
+    MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    h->last_launches = 1;
+    h->days_done += ndays;
+    return 0;
+}
+
+int mc_synchronize(mc_handle* h)
+{
+    if (!h) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (h->last_launches && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+    return 0;
+}
+
+static int ensure_stage(mc_handle* h, double** buf, size_t* have, size_t need)
+{
+    if (*have >= need) return 0;
+    if (*buf) { MC_CUDA(h, cudaFree(*buf)); *buf = nullptr; *have = 0; }
+    MC_CUDA(h, cudaMalloc(buf, need * sizeof(double)));
+    *have = need;
+    return 0;
+}
+
+int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!h) return -1;
+    if (!f || !o || ndays <= 0) { h->err = "forcing/out must be non-NULL and ndays positive"; return -1; }
+    if (check_forcing(h, f)) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t S = (size_t)h->S, N = (size_t)h->N, H = 24 * (size_t)ndays, D = (size_t)ndays;
+    /* stage forcing */
+    const double* hourly_src[11] = {f->pressure, f->reference_temperature, f->reference_wind_speed, f->reference_humidity, f->cloud_cover,
+                                    f->global_radiation, f->diffuse_fraction, f->zenith_angle, f->zenith_slope_angle, f->rainfall_hourly, f->longwave_radiation};
+    const double* daily_src[8] = {f->leaf_area_index, f->shade, f->surface_emissivity, f->cloud_emissivity, f->soil_wetness, f->deep_soil_temperature,
+                                  f->rainfall_daily, f->albedo_daily};
+    size_t need_in = 0;
+    for (const double* p : hourly_src) if (p) need_in += H * S;
+    for (const double* p : daily_src) if (p) need_in += D * S;
+    if (f->prescribed_soil_moisture) need_in += D * N * S;
+    if (int rc = ensure_stage(h, &h->stage_in, &h->stage_in_doubles, need_in)) return rc;
+    mc_forcing_soa fd; std::memset(&fd, 0, sizeof(fd));
+    const double** hourly_dst[11] = {&fd.pressure, &fd.reference_temperature, &fd.reference_wind_speed, &fd.reference_humidity, &fd.cloud_cover,
+                                     &fd.global_radiation, &fd.diffuse_fraction, &fd.zenith_angle, &fd.zenith_slope_angle, &fd.rainfall_hourly, &fd.longwave_radiation};
+    const double** daily_dst[8] = {&fd.leaf_area_index, &fd.shade, &fd.surface_emissivity, &fd.cloud_emissivity, &fd.soil_wetness, &fd.deep_soil_temperature,
+                                   &fd.rainfall_daily, &fd.albedo_daily};
+    double* p = h->stage_in;
+    for (int k = 0; k < 11; k++) if (hourly_src[k]) { MC_CUDA(h, cudaMemcpyAsync(p, hourly_src[k], H * S * sizeof(double), cudaMemcpyHostToDevice, h->stream)); *hourly_dst[k] = p; p += H * S; }
+    for (int k = 0; k < 8; k++) if (daily_src[k]) { MC_CUDA(h, cudaMemcpyAsync(p, daily_src[k], D * S * sizeof(double), cudaMemcpyHostToDevice, h->stream)); *daily_dst[k] = p; p += D * S; }
+    if (f->prescribed_soil_moisture) { MC_CUDA(h, cudaMemcpyAsync(p, f->prescribed_soil_moisture, D * N * S * sizeof(double), cudaMemcpyHostToDevice, h->stream)); fd.prescribed_soil_moisture = p; p += D * N * S; }
+    fd.day_of_year = f->day_of_year;
+    /* stage outputs */
+    double* node_host[7] = {o->soil_temperature, o->soil_moisture, o->soil_water_potential, o->soil_humidity, o->soil_thermal_conductivity, o->soil_heat_capacity, o->soil_bulk_density};
+    double* scal_host[2] = {o->surface_water, o->sky_temperature};
+    size_t need_out = 0;
+    for (double* q : node_host) if (q) need_out += H * N * S;
+    for (double* q : scal_host) if (q) need_out += H * S;
+    if (int rc = ensure_stage(h, &h->stage_out, &h->stage_out_doubles, need_out ? need_out : 1)) return rc;
+    mc_output_soa od; std::memset(&od, 0, sizeof(od));
+    double** node_dev[7] = {&od.soil_temperature, &od.soil_moisture, &od.soil_water_potential, &od.soil_humidity, &od.soil_thermal_conductivity, &od.soil_heat_capacity, &od.soil_bulk_density};
+    double** scal_dev[2] = {&od.surface_water, &od.sky_temperature};
+    double* q = h->stage_out;
+    for (int k = 0; k < 7; k++) if (node_host[k]) { *node_dev[k] = q; q += H * N * S; }
+    for (int k = 0; k < 2; k++) if (scal_host[k]) { *scal_dev[k] = q; q += H * S; }
+    /* cells the path never writes (e.g. water potential rows under PrescribedSoilMoisture) read back as zero */
+    if (need_out) MC_CUDA(h, cudaMemsetAsync(h->stage_out, 0, need_out * sizeof(double), h->stream));
+    int rc = mc_step_days_device(h, day0, ndays, &fd, &od);
+    if (rc < 0) return rc;
+    for (int k = 0; k < 7; k++) if (node_host[k]) MC_CUDA(h, cudaMemcpyAsync(node_host[k], *node_dev[k], H * N * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    for (int k = 0; k < 2; k++) if (scal_host[k]) MC_CUDA(h, cudaMemcpyAsync(scal_host[k], *scal_dev[k], H * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> status_tmp;
+    int32_t* status_host = o->status;
+    if (!status_host) { status_tmp.resize(S); status_host = status_tmp.data(); }
+    MC_CUDA(h, cudaMemcpyAsync(status_host, h->flags, S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = mc_synchronize(h)) < 0) return rc;
+    int nbad = 0;
+    for (size_t i = 0; i < S; i++) if (status_host[i]) nbad++;
+    return nbad;
+}
+
+int mc_get_counters(mc_handle* h, mc_counters* c)
+{
+    if (!h || !c) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    unsigned long long v[8];
+    MC_CUDA(h, cudaMemcpyAsync(v, h->counters, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memset(c, 0, sizeof(*c));
+    c->n_rhs = v[0]; c->n_accept = v[1]; c->n_reject = v[2]; c->n_obukhov_iter = v[3]; c->n_newton_iter = v[4]; c->n_infil_steps = v[5]; c->n_day_passes = v[6];
+    c->n_site_days = (uint64_t)(h->days_done * h->S);
+    c->gpu_ms = h->last_ms; c->n_kernel_launches = h->last_launches;
+    return 0;
+}
+
+int mc_reset_counters(mc_handle* h)
+{
+    if (!h) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    MC_CUDA(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), h->stream));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mc_get_status(mc_handle* h, int32_t* status_host)
+{
+    if (!h || !status_host) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    MC_CUDA(h, cudaMemcpyAsync(status_host, h->flags, (size_t)h->S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mc_measure_fp64_peak(mc_handle* h, double* tflops)
+{
+    if (!h || !tflops) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop; MC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double* buf = nullptr;
+    MC_CUDA(h, cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(buf, 1024);                 /* warm-up */
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(buf, iters);
+        MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        MC_CUDA(h, cudaStreamSynchronize(h->stream));
+        float ms = 0.f; MC_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    MC_CUDA(h, cudaFree(buf));
+    *tflops = best;
+    return 0;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,1058 @@
+/*
+ * mc_device.cuh — per-site soil heat + moisture integration, one GPU thread per site (sm_100a).
+ *
+ * B200-native restatement of Microclimate.jl's solve_soil! hot path
+ * (reference src/simulation.jl:355-819 and everything below it).  This is NOT a translation of
+ * the Julia control flow: the per-site algorithm is re-organised around what a thread can keep
+ * on chip —
+ *   - theta is constant during an ODE hour, so every theta-only term of the Campbell-de Vries
+ *     soil properties (areal heat capacity, volume fractions, recirculation factor) is hoisted
+ *     out of the right-hand side into a per-hour table;
+ *   - soil temperature is constant during the moisture hour, so the infiltration setup block
+ *     (reference campbell.jl:180-248, recomputed 10x per hour upstream) and the per-node vapour
+ *     densities inside the Newton loop are computed once per hour;
+ *   - forcing is read straight from the site-fastest SoA arrays (a warp reads 32 consecutive
+ *     doubles per knot: one 256 B coalesced request), never copied into per-site buffers;
+ *   - all powers with fixed exponents are strength-reduced (x^4, x^1.75, x^0.75).
+ * Results are the reference algorithm's to within floating-point reassociation (tests compare
+ * against the CPU oracle at 1e-3 K / 1e-5 m3/m3, observed ~1e-9).
+ *
+ * The functions are written against a tiny platform shim so the very same per-site code can be
+ * compiled by g++ for tests/hostemu (a development harness that runs the kernel body on the
+ * CPU where no GPU exists).  The shipped library (mc_api.cu) only ever launches the CUDA kernel.
+ */
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+#include "../../include/microclimate_b200.h"
+#include "../../include/mc_math.h"
+
+#if defined(__CUDACC__)
+#define MC_DEV __device__ __forceinline__
+#define MC_MEMBER __device__ __forceinline__
+#define MC_DEV_NOINLINE __device__ __noinline__
+#define MC_LDG(p) __ldg(p)
+#define MC_CONST_MODEL g_model_c
+#else
+#include <cmath>
+#define MC_DEV static inline
+#define MC_MEMBER inline
+#define MC_DEV_NOINLINE static __attribute__((noinline))
+#define MC_LDG(p) (*(p))
+#define MC_CONST_MODEL g_model_h
+#endif
+
+namespace mcd {
+
+constexpr int MAXN = MC_MAX_SOIL_NODES;
+constexpr double T0C = 273.15;
+constexpr double T_LO = 273.15 - 81.0;              /* heat_transport_1d.jl:159 */
+constexpr double WATER_CP = 4184.0;                 /* src/constants.jl */
+constexpr double WATER_RHO = 1000.0;
+constexpr double LATENT_FUSION = 333550.0;
+constexpr double MW_INFIL = 0.01801528;             /* campbell.jl:176 (differs from FluidProperties' 0.018016 on purpose) */
+constexpr double DV_INFIL = 2.4e-5;                 /* campbell.jl:178 */
+constexpr double RHOCPTKG = 6.003e-8 * 4.184 * 3600.0 * 1.0e8;   /* monin_obukhov.jl:135 */
+constexpr double PI_D = 3.14159265358979323846;
+
+/* ---- model constants, flattened once on the host (mc_api.cu) into constant memory ---- */
+struct DevModel {
+    int N, dynamic, nonconsec, conv_kind, conv_iters, iters_per_day, spinup, rain_hourly, flux_alg, swinbank;
+    int moist_max_it, niter_moist;
+    double depths[MAXN];
+    double dzc[MAXN];       /* ld[i+1]-ld[i-1] (i>=1), ld[1] for i=0, with the zero sentinel at ld[N]   (heat_transport_1d.jl:175-210) */
+    double dzg[MAXN];       /* ld[i+1]-ld[i] */
+    double zref, zloc, reltol, abstol, T_hi;
+    double ga, gc, recirc_pow, theta0;
+    double root_res, PC, RL, SP, root_radius;
+    double kappa, gamma, conv_tol, moist_tol, moist_dt, max_pool;
+    /* FluidProperties constants */
+    double Mw, eps, dep, cpa, cpv, R, sigma, g, P0, Lv_a, Lv_b, Hv_a, Hv_b, Ma_over_R;
+    double schmidt_factor;  /* (0.71/0.60)^0.666, monin_obukhov.jl:406-407 */
+};
+
+#if defined(__CUDACC__)
+__constant__ DevModel g_model_c;
+#else
+static DevModel g_model_h;
+#endif
+
+/* ---- kernel arguments: every array is site-fastest SoA (x[node][site], f[hour][site]) ---- */
+struct KArgs {
+    int64_t S;        /* sites in this launch */
+    int64_t day0;     /* global index of the first day of the chunk */
+    int32_t ndays;    /* days in the chunk */
+    int32_t has_init_T, has_albedo_daily, has_lw, has_presc;
+    /* sites */
+    const double *z0, *slope, *svf, *albedo;
+    const double *bd, *md, *lam_m, *c_m, *psi_e, *ks, *bb, *rootd;
+    const double *init_T, *init_theta;
+    /* carried state */
+    double *T, *theta, *sum_phase, *pool, *wetness, *L_ode, *L_prof, *tdeep_prev, *fsal;
+    int32_t* flags;
+    /* forcing (chunk-relative rows) */
+    const double *f_P, *f_T, *f_wind, *f_rh, *f_cloud, *f_solar, *f_diffuse, *f_zen, *f_szen, *f_rain, *f_lw;
+    const double *d_lai, *d_shade, *d_eps, *d_epsc, *d_wet, *d_tdeep, *d_rain, *d_albedo, *presc;
+    /* outputs (NULL = deselected) */
+    double *o_T, *o_theta, *o_psi, *o_h, *o_lam, *o_cp, *o_rho, *o_pool, *o_sky;
+    unsigned long long* counters;   /* [8]: rhs, accept, reject, obukhov, newton, infil, day_passes, spare */
+};
+
+struct Counters { unsigned int n_rhs, n_accept, n_reject, n_obukhov, n_newton, n_infil, n_day_passes; };
+
+MC_DEV double jmax(double a, double b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }   /* Julia max/min propagate NaN */
+MC_DEV double jmin(double a, double b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
+MC_DEV double jclamp(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+/* ------------------------------------------------------------------------------------------
+ * FluidProperties.jl psychrometrics (un-vendored; constants are data, see mc_fluid_constants)
+ * ------------------------------------------------------------------------------------------ */
+/* vapour_pressure(GoffGratch(), T) [Pa] */
+MC_DEV double goff_gratch(double T)
+{
+    const double Tp = T + 0.01;
+    double loge;
+    if (Tp <= 273.16) {
+        const double r = 273.16 / Tp;
+        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - Tp / 273.16) + 0.7858350313586662 /* mcm::log10(6.1071) */;
+    } else {
+        const double r = 373.16 / Tp;
+        loge = -7.90298 * (r - 1.0) + 5.02808 * mcm::log10(r)
+             - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - Tp / 373.16)) - 1.0)
+             + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314 /* mcm::log10(1013.246) */;
+    }
+    return 100.0 * mcm::exp10(loge);
+}
+
+struct WetAir { double vapour_pressure, vapour_density, specific_heat, density; };
+
+MC_DEV WetAir wet_air(double T, double rh, double P)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    WetAir w;
+    const double e = goff_gratch(T) * rh;
+    w.vapour_pressure = e;
+    const double mr = (m.eps * m.dep * e) / (P - m.dep * e);
+    w.vapour_density = e * m.Mw / (0.998 * m.R * T);
+    const double T_vir = T * ((1.0 + mr / m.eps) / (1.0 + mr));
+    w.density = m.Ma_over_R * P / (0.999 * T_vir);
+    w.specific_heat = (m.cpa + mr * m.cpv) / (1.0 + mr);
+    return w;
+}
+MC_DEV double vapour_density_sat(double T) { const DevModel& m = MC_CONST_MODEL; return goff_gratch(T) * m.Mw / (0.998 * m.R * T); }
+MC_DEV double latent_heat(double T) { const DevModel& m = MC_CONST_MODEL; return m.Lv_a - m.Lv_b * (T - T0C); }
+
+/* atmospheric_radiation (Campbell-Norman / Swinbank), src/radiation/atmospheric */
+MC_DEV double atmospheric_radiation(double e_Pa, double T_air)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    if (m.swinbank) return (9.2e-6 * T_air * T_air) * m.sigma * mcm::pow4(T_air);
+    const double Tp = T_air + 0.01;
+    return (1.72 * mcm::pow((e_Pa / 1000.0) / Tp, 1.0 / 7.0)) * m.sigma * mcm::pow4(Tp);
+}
+
+/* precompute_longwave_sky -> sky temperature (view_factor.jl:23-67) */
+MC_DEV double sky_temperature(double svf, double /*P*/, double rh, double T_ref, double eps_cloud, double cloud, double shade,
+                              bool has_lw, double supplied_lw)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const double cloud_rad = m.sigma * eps_cloud * mcm::pow4(T_ref - 2.0);
+    const double hill_rad = m.sigma * eps_cloud * mcm::pow4(T_ref);
+    double lw_sky;
+    if (has_lw) lw_sky = supplied_lw * (1.0 - shade);
+    else {
+        const double e = goff_gratch(T_ref) * rh;
+        lw_sky = (atmospheric_radiation(e, T_ref) * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - shade);
+    }
+    const double incoming = (lw_sky + shade * hill_rad) * svf + hill_rad * (1.0 - svf);
+    return mcm::pow(incoming / m.sigma, 0.25);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Monin-Obukhov (src/boundary_layer/monin_obukhov.jl)
+ * ------------------------------------------------------------------------------------------ */
+MC_DEV double calc_rho_cp(double Tmean) { return (0.08472 / Tmean) * 4.184e6; }
+MC_DEV double sublayer_stanton(double z0, double ustar) { return 0.62 / mcm::pow(z0 * 100.0 * (ustar * 6000.0) / 12.0, 0.45); }
+MC_DEV double convective_flux(double rho_cp, double dT, double ustar, double Stb, double Sts) { return rho_cp * dT * ustar * Stb / (1.0 + Stb / Sts); }
+MC_DEV double calc_phi_m(double z, double gamma, double L) { return sqrt(sqrt(1.0 - gamma * z / L)); }
+MC_DEV double calc_psi_m(double x) { return 2.0 * mcm::log((1.0 + x) / 2.0) + mcm::log((1.0 + x * x) / 2.0) - 2.0 * mcm::atan(x) + PI_D / 2.0; }
+MC_DEV double calc_psi_h(double x) { return 2.0 * mcm::log((1.0 + x * x) / 2.0); }
+
+struct Obukhov { double L, Sts, Stb, ustar, psi_h, Q; int iters; };
+
+/* calc_Obukhov_length fixed point (monin_obukhov.jl:527-577): <=30 iterations, 1 % relative change */
+MC_DEV Obukhov calc_obukhov(double v_ref, double z0, double z, double lz, double dT, double rho_cp, double L0)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    Obukhov o; o.L = L0; o.Q = 0.0; o.Stb = 0.0; o.Sts = 0.0; o.psi_h = 0.0; o.ustar = 0.0;
+    double rel = 1.0; int count = 0;
+    while (rel > 1.0e-2 && count < 30) {
+        count++;
+        const double x = calc_phi_m(z, 16.0, o.L);
+        const double psi_m = calc_psi_m(x);
+        o.psi_h = calc_psi_h(x);
+        double lrc = lz - psi_m;
+        if (lrc <= 0.0) lrc = 1.0e-6;
+        o.ustar = m.kappa * v_ref / lrc;
+        if (o.ustar < 1.0e-6) o.ustar = 1.0e-6;
+        o.Sts = sublayer_stanton(z0, o.ustar);
+        o.Stb = (0.64 / lrc) * (1.0 - 0.1 * z / o.L);
+        o.Q = convective_flux(rho_cp, dT, o.ustar, o.Stb, o.Sts);
+        const double Lnew = RHOCPTKG * o.ustar * o.ustar * o.ustar / o.Q;
+        rel = fabs((Lnew - o.L) / o.L);
+        o.L = Lnew;
+    }
+    o.iters = count;
+    return o;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Per-site context: what a thread keeps for its site across the whole chunk
+ * ------------------------------------------------------------------------------------------ */
+template <int NA>
+struct HourSoil {           /* theta-only soil property terms, rebuilt once per hour (theta is constant within the ODE hour) */
+    double cap[NA];         /* areal heat capacity of the node's control volume, J/m2/K            (heat_transport_1d.jl:175-190) */
+    double theta[NA], phim[NA], phig[NA], fw[NA], lam_m[NA];
+};
+
+struct HourPar {            /* SoilEnergyInputs scalars (heat_transport_1d.jl:41-63) */
+    double shade, eps_surf, eps_cloud, soil_wetness, albedo, L_prev;
+    double z0, lz, slope, svf;          /* lz = mcm::log(zref/z0) */
+    const double *fP, *fT, *fwind, *frh, *fcloud, *fsolar, *fdiff, *fzen, *fszen;   /* this site's day: base[k*S] is knot k */
+    int64_t S;
+};
+
+MC_DEV double knot_lerp(const double* base, int64_t S, int i, double d)
+{
+    const int i1 = i + 1 > 23 ? 23 : i + 1;      /* 25th knot repeats hour 24 (simulation.jl:990) */
+    return (1.0 - d) * MC_LDG(base + (int64_t)i * S) + d * MC_LDG(base + (int64_t)i1 * S);
+}
+
+/* Campbell-de Vries bulk conductivity of one node (campbell_devries.jl:79-142), T-dependent part only */
+MC_DEV double devries_weight(double lam_c, double lam_f, double ga, double gc)
+{
+    const double r1 = lam_c / lam_f - 1.0;
+    return 2.0 / (3.0 * (1.0 + ga * r1)) + 1.0 / (3.0 * (1.0 + gc * r1));
+}
+MC_DEV double soil_conductivity(double T, double P, double theta, double phim, double phig, double fw, double lam_m)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const double Tc = T - T0C;
+    const double lam_w = 0.554 + 2.24e-3 * Tc - 9.87e-6 * Tc * Tc;
+    const double lam_a = 0.024 + 7.73e-5 * Tc - 2.6e-8 * Tc * Tc;
+    const double Dv = 2.12e-5 * (m.P0 / P) * mcm::pow(T / 273.15, 1.75);      /* campbell_devries.jl:109 */
+    const double rho_hat = 44.65 * (P / m.P0) * (273.15 / T);                   /* :111 */
+    const double Hv = m.Hv_a - m.Hv_b * (T - T0C);
+    const double e0 = goff_gratch(T) * 0.99;
+    const double em = goff_gratch(T - 1.0) * 0.99;
+    const double ep = goff_gratch(T + 1.0) * 0.99;
+    const double dedT = (ep - em) / 2.0;
+    const double lam_g = lam_a + Hv * dedT * fw * rho_hat * Dv / (P - e0);
+    const double lam_f = lam_g + fw * (lam_w - lam_g);
+    const double ww = devries_weight(lam_w, lam_f, m.ga, m.gc);
+    const double wm = devries_weight(lam_m, lam_f, m.ga, m.gc);
+    const double wg = devries_weight(lam_g, lam_f, m.ga, m.gc);
+    return (theta * ww * lam_w + phim * wm * lam_m + phig * wg * lam_g) / (theta * ww + phim * wm + phig * wg);
+}
+
+/* full soil_properties for the output rows (update_soil_properties!, simulation.jl:905-913) */
+MC_DEV void soil_properties_full(double T, double P, double theta, double bd, double md, double lam_m, double c_m,
+                                 double& lam, double& cp, double& rho)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    cp = bd / md * c_m + theta * WATER_CP;
+    rho = theta * WATER_RHO + bd;
+    const double phim = bd / md;
+    const double phig = jmax(0.0, 1.0 - theta - phim);
+    const double fw = 1.0 / (1.0 + mcm::pow(theta / m.theta0, -m.recirc_pow));
+    lam = soil_conductivity(T, P, theta, phim, phig, fw, lam_m);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * soil_energy_balance (heat_transport_1d.jl:137-302), no-snow form: the surface is node 0.
+ * u, du in K and K/min.
+ * ------------------------------------------------------------------------------------------ */
+template <int NA>
+MC_DEV_NOINLINE void soil_rhs(const HourSoil<NA>& hs, const HourPar& hp, const double* __restrict__ u, double t,
+                              double* __restrict__ du, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const int N = m.N;
+    cn.n_rhs++;
+    /* interpolate_forcings (forcing.jl:24-37) */
+    const double xk = t / 60.0;
+    int ik = (int)floor(xk);
+    ik = ik < 0 ? 0 : (ik > 23 ? 23 : ik);
+    const double dk = xk - (double)ik;
+    const double P = knot_lerp(hp.fP, hp.S, ik, dk);
+    const double T_air = knot_lerp(hp.fT, hp.S, ik, dk);
+    const double wind = jmax(knot_lerp(hp.fwind, hp.S, ik, dk), 0.1);
+    const double zen = jmin(90.0, nearbyint(knot_lerp(hp.fzen, hp.S, ik, dk) * 1000.0) / 1000.0);
+    const double solar = jmax(0.0, knot_lerp(hp.fsolar, hp.S, ik, dk));
+    const double cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
+    const double rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
+
+    /* conduction: node conductance G_i = lambda_i(T_i) / dz_i, built on the fly so only two live at a time */
+    const double Ts_node = jclamp(u[0], T_LO, m.T_hi);
+    double T_up = Ts_node;
+    double G_up = soil_conductivity(T_up, P, hs.theta[0], hs.phim[0], hs.phig[0], hs.fw[0], hs.lam_m[0]) / m.dzg[0];
+    double T_i = jclamp(u[1], T_LO, m.T_hi);
+    const double Q_cond = G_up * (T_i - Ts_node);
+#pragma unroll 1
+    for (int i = 1; i < N - 1; i++) {
+        const double T_dn = jclamp(u[i + 1], T_LO, m.T_hi);
+        const double G_i = soil_conductivity(T_i, P, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]) / m.dzg[i];
+        du[i] = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / hs.cap[i];
+        T_up = T_i; T_i = T_dn; G_up = G_i;
+    }
+    du[N - 1] = 0.0;                                         /* Dirichlet bottom node (:291-293) */
+
+    /* shortwave (:223-232) */
+    double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
+    if (hp.slope > 0.0 && zen < 90.0) {
+        const double szen = jmin(90.0, knot_lerp(hp.fszen, hp.S, ik, dk));
+        const double fd = jclamp(knot_lerp(hp.fdiff, hp.S, ik, dk), 0.0, 1.0);
+        const double cz = mcm::cos(zen * PI_D / 180.0), csz = mcm::cos(szen * PI_D / 180.0);
+        Q_solar = jmax(0.0, (((1.0 - fd) * Q_solar) / cz) * csz) + (fd * Q_solar) * hp.svf;
+    }
+    /* longwave (:237-250) */
+    const WetAir wa = wet_air(T_air, rh, P);
+    const double atm = atmospheric_radiation(wa.vapour_pressure, T_air);
+    const double cloud_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air - 2.0);
+    const double hill_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air);
+    const double lw_sky = (atm * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - hp.shade);
+    const double incoming = (lw_sky + hp.shade * hill_rad) * hp.svf + hill_rad * (1.0 - hp.svf);
+    const double Q_ir = incoming - ((1.0 - hp.shade) * m.sigma * hp.eps_surf) * mcm::pow4(Ts_node) - hp.shade * hill_rad;
+
+    /* surface temperature guards (:260-266) */
+    double Ts = Ts_node;
+    if (fabs(Ts - T0C) > 100.0) Ts = T_air + 1.0;
+    if (Ts == T_air) Ts = Ts + 0.1;
+
+    /* surface_fluxes (monin_obukhov.jl:208-245) */
+    const double dT = T_air - Ts;
+    const double rho_cp = calc_rho_cp((Ts + T_air) / 2.0);
+    double Qc;
+    if (T_air >= Ts || zen >= 90.0) {
+        const double ustar = jmax(m.kappa * wind / hp.lz, 1.0e-6);
+        Qc = convective_flux(rho_cp, dT, ustar, 0.64 / hp.lz, sublayer_stanton(hp.z0, ustar));
+    } else {
+        const Obukhov o = calc_obukhov(wind, hp.z0, m.zref, hp.lz, dT, rho_cp, hp.L_prev >= 0.0 ? -0.3 : hp.L_prev);
+        cn.n_obukhov += o.iters;
+        Qc = o.Q;
+    }
+    /* surface_convection_evaporation + evaporation (bulk_transfer.jl:11-81) */
+    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
+    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
+    const double Tsc = Ts < T_LO ? T_LO : Ts;
+    const double Qe = (hp.soil_wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
+
+    du[0] = 60.0 * (Q_solar + Q_ir + Q_cond + Qc + 0.0 /* Q_freeze: snow only */ - Qe) / hs.cap[0];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive Tsit5 with OrdinaryDiffEq's PI controller (third-party arithmetic restated; see the
+ * oracle header for provenance).  Integrator state lives in thread-local arrays.
+ * ------------------------------------------------------------------------------------------ */
+namespace tsit5 {
+constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
+constexpr double a21 = 0.161;
+constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
+constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
+constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365, a54 = -0.09249506636175525;
+constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159, a64 = -0.071584973281401, a65 = -0.028269050394068383;
+constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996, a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
+constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469, bt3 = 0.007880878010261995,
+                 bt4 = -0.1447110071732629, bt5 = 0.5823571654525552, bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
+}
+
+/* FastPower.fastpower(x, y): Float32 log2 rational fit + exp2, as the PI controller uses it */
+MC_DEV float fastlog2f(float x)
+{
+    union { float f; uint32_t u; } v; v.f = x;
+    const uint32_t ux = v.u;
+    const uint32_t ex = (ux & 0x7F800000u) >> 23;
+    float signif, fexp;
+    if (ux & 0x00400000u) { v.u = (ux & 0x007FFFFFu) | 0x3f000000u; signif = v.f; fexp = (float)ex - 126.0f; }
+    else                  { v.u = (ux & 0x007FFFFFu) | 0x3f800000u; signif = v.f; fexp = (float)ex - 127.0f; }
+    signif = signif - 1.0f;
+#if defined(__CUDACC__)
+    return __fadd_rn(fexp, __fdiv_rn(__fmul_rn(signif, __fadd_rn(__fmul_rn(0.338953f, signif), 2.198599f)), __fadd_rn(signif, 1.523692f)));
+#else
+    return fexp + signif * (0.338953f * signif + 2.198599f) / (signif + 1.523692f);
+#endif
+}
+MC_DEV double fastpow(double x, double y)
+{
+#if defined(__CUDACC__)
+    const float l = __fmul_rn(fastlog2f((float)x), (float)y);
+#else
+    const float l = fastlog2f((float)x) * (float)y;
+#endif
+    return (double)(float)mcm::exp2((double)l);
+}
+
+template <int NA>
+struct Integ {
+    double u[NA], uprev[NA], k1[NA], k2[NA], k3[NA], k4[NA], k5[NA], k6[NA], k7[NA], tmp[NA];
+    double t, dt, dtpropose, qold, q11, tstop;
+    int iter, flags; bool accept, u_modified;
+};
+
+MC_DEV double rms_scaled(const double* x, const double* sk, int n) { double s = 0.0; for (int i = 0; i < n; i++) { const double q = x[i] / sk[i]; s += q * q; } return sqrt(s / n); }
+
+/* Hairer-Wanner automatic initial step (OrdinaryDiffEqCore initdt.jl), order 5 */
+template <int NA>
+MC_DEV_NOINLINE double determine_initdt(Integ<NA>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL; const int N = m.N;
+    double* sk = I.tmp; double* f0 = I.k2; double* f1 = I.k3; double* u1 = I.k4;
+    double s0 = 0.0;
+    for (int i = 0; i < N; i++) { sk[i] = m.abstol + fabs(I.u[i]) * m.reltol; const double q = I.u[i] / sk[i]; s0 += q * q; }
+    const double d0 = sqrt(s0 / N);
+    soil_rhs<NA>(hs, hp, I.u, I.t, f0, cn);
+    bool finite = true;
+    for (int i = 0; i < N; i++) if (!isfinite(f0[i])) finite = false;
+    if (!finite) return 1e-12;
+    const double d1 = rms_scaled(f0, sk, N);
+    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+    dt0 = fmin(dt0, 1440.0);
+    for (int i = 0; i < N; i++) u1[i] = I.u[i] + dt0 * f0[i];
+    soil_rhs<NA>(hs, hp, u1, I.t + dt0, f1, cn);
+    double s2 = 0.0;
+    for (int i = 0; i < N; i++) { const double q = (f1[i] - f0[i]) / sk[i]; s2 += q * q; }
+    const double d2 = sqrt(s2 / N) / dt0;
+    const double md = fmax(d1, d2);
+    double dt1;
+    if (md <= 1e-15) dt1 = fmax(1e-6, dt0 * 1e-3);
+    else dt1 = mcm::exp10(-(2.0 + mcm::log10(md)) / 5.0);
+    return fmin(fmin(100.0 * dt0, dt1), 1440.0);
+}
+
+/* one accepted step: loopheader!/perform_step!/loopfooter! until accepted */
+template <int NA>
+MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
+{
+    using namespace tsit5;
+    const DevModel& m = MC_CONST_MODEL; const int N = m.N;
+    int guard = 0;
+    for (;;) {
+        if (I.iter > 0) {
+            if (!I.accept) {
+                I.dt = I.dt / fmin(5.0, I.q11 / 0.9);
+            } else {
+                for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
+                I.dt = I.dtpropose;
+                if (I.u_modified) soil_rhs<NA>(hs, hp, I.u, I.t, I.k1, cn);
+                else for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
+            }
+        } else if (I.u_modified) {
+            for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
+        }
+        I.iter++;
+        I.dt = fmin(1440.0, I.dt);
+        I.dt = fmin(I.dt, I.tstop - I.t);
+        if (!(I.dt > 1e-12) || ++guard > 100000) {
+            I.flags |= (I.dt != I.dt) ? MC_STATUS_NAN : (guard > 100000 ? MC_STATUS_STEP_LIMIT : MC_STATUS_DT_UNDERFLOW);
+            I.t = I.tstop; I.accept = true; I.dtpropose = 1.0;
+            for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
+            return;
+        }
+        const double t = I.t, dt = I.dt;
+        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
+        soil_rhs<NA>(hs, hp, I.tmp, t + c1 * dt, I.k2, cn);
+        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
+        soil_rhs<NA>(hs, hp, I.tmp, t + c2 * dt, I.k3, cn);
+        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
+        soil_rhs<NA>(hs, hp, I.tmp, t + c3 * dt, I.k4, cn);
+        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
+        soil_rhs<NA>(hs, hp, I.tmp, t + c4 * dt, I.k5, cn);
+        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
+        soil_rhs<NA>(hs, hp, I.tmp, t + dt, I.k6, cn);
+        for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
+        soil_rhs<NA>(hs, hp, I.u, t + dt, I.k7, cn);
+        double ss = 0.0;
+        for (int i = 0; i < N; i++) {
+            const double ut = dt * (bt1 * I.k1[i] + bt2 * I.k2[i] + bt3 * I.k3[i] + bt4 * I.k4[i] + bt5 * I.k5[i] + bt6 * I.k6[i] + bt7 * I.k7[i]);
+            const double q = ut / (m.abstol + fmax(fabs(I.uprev[i]), fabs(I.u[i])) * m.reltol);
+            ss += q * q;
+        }
+        const double EEst = sqrt(ss / N);
+        I.u_modified = false;
+        double q;
+        if (EEst == 0.0) q = 0.1;
+        else {
+            I.q11 = fastpow(EEst, 7.0 / 50.0);
+            q = I.q11 / fastpow(I.qold, 2.0 / 25.0);
+            q = fmax(0.1, fmin(5.0, q / 0.9));
+        }
+        I.accept = EEst <= 1.0;
+        if (EEst != EEst) { I.flags |= MC_STATUS_NAN; I.accept = true; q = 1.0; }
+        if (I.accept) {
+            cn.n_accept++;
+            I.qold = fmax(EEst, 1e-4);
+            const double dtnew = I.dt / q;
+            double ttmp = I.t + I.dt;
+            if (fabs(ttmp - I.tstop) < 100.0 * 2.220446049250313e-16 * fmax(I.t, I.tstop)) ttmp = I.tstop;
+            I.t = ttmp;
+            I.dtpropose = fmin(1440.0, dtnew);
+            return;
+        }
+        cn.n_reject++;
+        for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * phase_transition!(::PhaseTransitionLatentHeat), latent_heat.jl:21-112 (sequential over nodes)
+ * ------------------------------------------------------------------------------------------ */
+MC_DEV void phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
+{
+    const double tol = 1.0e-4;
+    for (int i = 0; i < N; i++) {
+        double mean, mean_past;
+        if (i < N - 1) { mean = 0.5 * (T[i] + T[i + 1]); mean_past = 0.5 * (Tpast[i] + Tpast[i + 1]); }
+        else { mean = T[i]; mean_past = Tpast[i]; }
+        double mass = 0.0;
+        if (theta[i] > 0.0) mass = (i < N - 1 ? (depths[i + 1] - depths[i]) : ((depths[i] + 1.0) - depths[i])) * 1000.0 * theta[i];
+        if (theta[i] <= 0.0 || mass <= 0.0) { sum_phase[i] = 0.0; continue; }
+        const double max_latent = LATENT_FUSION * mass;
+        if ((mean_past - T0C > tol) && (mean - T0C <= -tol)) {
+            sum_phase[i] += (mean_past - mean) * mass * WATER_CP;
+            if (sum_phase[i] >= max_latent) sum_phase[i] = max_latent;
+            T[i] = T0C; if (i < N - 1) T[i + 1] = T0C;
+        } else if ((mean_past - T0C < -tol) && (mean - T0C >= tol)) {
+            sum_phase[i] -= (mean - mean_past) * mass * WATER_CP;
+            if (sum_phase[i] <= 0.0) sum_phase[i] = 0.0;
+            else { T[i] = T0C; if (i < N - 1) T[i + 1] = T0C; }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Campbell (1985) water balance.  Arrays use the reference's 1-based buffer indices
+ * (buffer node i <-> soil node i-1; entry 0 unused), campbell.jl:129-361.
+ * ------------------------------------------------------------------------------------------ */
+template <int NA>
+struct HourMoist {              /* per-hour constants of infiltration_step! (soil T and site parameters are fixed within the hour) */
+    double psi_e[NA + 2], sat[NA + 2], bb[NA + 2], ks[NA + 2], nexp[NA + 2], mass[NA + 2], rootR[NA + 2], rootZ[NA + 2];
+    double dz[NA + 2];          /* depth[i+1]-depth[i] with depth[1]=-1e10, depth[L+1]=1e20 */
+    double kvc[NA + 2];         /* 0.66 * Dv * rho_v,sat(T_i)                                   (campbell.jl:307-309) */
+    double rts[NA + 2];         /* R * T_{i-1}                                                  (campbell.jl:224,311,330) */
+    double phi_e[NA + 2], fexp[NA + 2];   /* matric flux potential form only */
+    double rts1;                /* R * Ts[1] */
+};
+
+template <int NA>
+struct InfilWork {
+    double psi[NA + 2], K[NA + 2], h[NA + 2], wc[NA + 2], wcn[NA + 2], phi[NA + 2];
+    double jv[NA + 2], djv[NA + 2], sub[NA + 2], dia[NA + 2], sup[NA + 2], F[NA + 2], cc[NA + 2], rr[NA + 2], uptake[NA + 2], soilR[NA + 2];
+};
+
+struct InfilOut { double evaporation, surface_water_flux; bool hit_max; };
+
+template <int NA>
+MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA>& B, double* theta, double rh_loc, double lai, double ET, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    cn.n_infil++;
+    const int L = m.N;
+    const double g = m.g, dt = m.moist_dt;
+    const bool flux_alg = m.flux_alg != 0;
+    for (int i = 2; i <= L; i++) { B.wcn[i] = theta[i - 2]; B.wc[i] = theta[i - 2]; }
+    /* initial_state_from_water_content! */
+    for (int i = 2; i <= L; i++) {
+        B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
+        if (!flux_alg) B.K[i] = hm.ks[i] * mcm::pow(hm.psi_e[i] / B.psi[i], hm.nexp[i]);
+        else {
+            B.phi[i] = hm.phi_e[i] * mcm::pow(B.wcn[i] / hm.sat[i], hm.bb[i] + 3.0);
+            B.K[i] = hm.ks[i] * mcm::pow(B.phi[i] / hm.phi_e[i], hm.fexp[i]);
+        }
+        B.h[i] = mcm::exp(MW_INFIL * B.psi[i] / hm.rts[i]);
+    }
+    B.psi[L + 1] = hm.psi_e[L];
+    if (flux_alg) B.phi[L + 1] = hm.phi_e[L];
+    B.h[L + 1] = 1.0; B.wc[L + 1] = hm.sat[L + 1]; B.wcn[L + 1] = hm.sat[L + 1];
+    B.K[L + 1] = hm.ks[L];
+    B.psi[1] = B.psi[2]; B.K[1] = 0.0;
+    if (flux_alg) B.phi[1] = 0.0;     /* never written upstream: the zero-initialised buffer value */
+    const double EP = mcm::exp(-0.82 * lai) * ET;
+    const double TP = ET - EP;
+    double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
+    for (int i = 2; i <= L; i++) {
+        B.soilR[i] = hm.rootZ[i] / B.K[i];
+        const double rt = B.soilR[i] + hm.rootR[i];
+        psum += B.psi[i] / rt;
+        rsum += 1.0 / rt;
+    }
+    const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
+    const double RL = m.RL, PC = m.PC, SP = m.SP;
+    int counter = 0;
+    while (counter < m.moist_max_it) {                                       /* stomatal Newton, campbell.jl:270-284 */
+        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
+        const double xp = mcm::pow(psi_leaf / PC, SP);
+        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
+        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
+        psi_leaf = psi_leaf - resid / slope;
+        counter++;
+        if (fabs(resid) <= 10.0) break;
+    }
+    const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
+    for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
+
+    InfilOut out; out.hit_max = true;
+    counter = 0;
+    while (counter < m.moist_max_it) {                                       /* Newton loop, campbell.jl:293-336 */
+        double err = 0.0;
+        counter++; cn.n_newton++;
+        for (int i = 2; i <= L; i++) {
+            if (!flux_alg) B.K[i] = hm.ks[i] * mcm::pow(hm.psi_e[i] / B.psi[i], hm.nexp[i]);
+            else B.K[i] = hm.ks[i] * mcm::pow(B.phi[i] / hm.phi_e[i], hm.fexp[i]);
+        }
+        if (flux_alg) { for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]); B.psi[L + 1] = hm.psi_e[L]; }
+        B.jv[1] = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc);
+        B.djv[1] = EP * MW_INFIL * B.h[2] / (hm.rts1 * (1.0 - rh_loc));
+        for (int i = 2; i <= L; i++) {
+            const double kv = hm.kvc[i] * (hm.sat[i] - (B.wcn[i] + B.wcn[i + 1]) / 2.0) / hm.dz[i];
+            B.jv[i] = kv * (B.h[i + 1] - B.h[i]);
+            B.djv[i] = MW_INFIL * B.h[i] * kv / hm.rts[i];
+        }
+        for (int i = 2; i <= L; i++) {
+            if (!flux_alg) {
+                const double cap = -1.0 * hm.mass[i] * B.wcn[i] / (hm.bb[i] * B.psi[i] * dt);
+                B.sub[i] = -1.0 * B.K[i - 1] / hm.dz[i - 1] + g * hm.nexp[i] * B.K[i - 1] / B.psi[i - 1];
+                B.sup[i] = -1.0 * B.K[i + 1] / hm.dz[i];
+                B.dia[i] = B.K[i] / hm.dz[i - 1] + B.K[i] / hm.dz[i] + cap - g * hm.nexp[i] * B.K[i] / B.psi[i] + B.djv[i - 1] + B.djv[i];
+                B.F[i] = ((B.psi[i] * B.K[i] - B.psi[i - 1] * B.K[i - 1]) / hm.dz[i - 1]
+                        - (B.psi[i + 1] * B.K[i + 1] - B.psi[i] * B.K[i]) / hm.dz[i]) / (1.0 - hm.nexp[i])
+                       + hm.mass[i] * (B.wcn[i] - B.wc[i]) / dt - g * (B.K[i - 1] - B.K[i]) + B.jv[i - 1] - B.jv[i] + B.uptake[i];
+            } else {
+                const double b3 = hm.fexp[i];
+                const double cap = hm.mass[i] * B.wcn[i] / ((hm.bb[i] + 3.0) * B.phi[i] * dt);
+                B.sub[i] = -1.0 / hm.dz[i - 1] - g * b3 * B.K[i - 1] / B.phi[i - 1];
+                B.sup[i] = -1.0 / hm.dz[i];
+                B.dia[i] = 1.0 / hm.dz[i - 1] + 1.0 / hm.dz[i] + cap + g * b3 * B.K[i] / B.phi[i];
+                B.F[i] = (B.phi[i] - B.phi[i - 1]) / hm.dz[i - 1] - (B.phi[i + 1] - B.phi[i]) / hm.dz[i]
+                       + hm.mass[i] * (B.wcn[i] - B.wc[i]) / dt - g * (B.K[i - 1] - B.K[i]) + B.jv[i - 1] - B.jv[i] + B.uptake[i];
+            }
+            err += fabs(B.F[i]);
+        }
+        for (int i = 2; i <= L - 1; i++) {                                   /* thomas_forward_elimination! */
+            B.cc[i] = B.sup[i] / B.dia[i];
+            if (fabs(B.cc[i]) < 1e-8) B.cc[i] = 0.0;
+            B.rr[i] = B.F[i] / B.dia[i];
+            B.dia[i + 1] -= B.sub[i + 1] * B.cc[i];
+            B.F[i + 1] -= B.sub[i + 1] * B.rr[i];
+        }
+        if (!flux_alg) {
+            double dpsi = B.F[L] / B.dia[L];                                 /* lower boundary clamp */
+            B.psi[L] = jmin(B.psi[L] - dpsi, hm.psi_e[L]);
+            for (int i = L - 1; i >= 2; i--) {                               /* interior back-substitution + saturation averaging clamp */
+                dpsi = B.rr[i] - B.cc[i] * dpsi;
+                B.psi[i] -= dpsi;
+                if (B.psi[i] > hm.psi_e[i]) B.psi[i] = (B.psi[i] + dpsi + hm.psi_e[i]) / 2.0;
+            }
+            for (int i = 2; i <= L; i++) {                                   /* recover_water_content! */
+                B.wcn[i] = jmax(hm.sat[i] * mcm::pow(hm.psi_e[i] / B.psi[i], 1.0 / hm.bb[i]), 1e-7);
+                B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
+            }
+        } else {
+            double dphi = B.F[L] / B.dia[L];
+            B.phi[L] -= dphi;
+            if (B.phi[L] < 0.0) B.phi[L] = 1e-6; else if (B.phi[L] > hm.phi_e[L]) B.phi[L] = hm.phi_e[L];
+            for (int i = L - 1; i >= 2; i--) {
+                dphi = B.rr[i] - B.cc[i] * dphi;
+                B.phi[i] -= dphi;
+                if (B.phi[i] < 0.0) B.phi[i] = 1e-6; else if (B.phi[i] > hm.phi_e[i]) B.phi[i] = hm.phi_e[i];
+            }
+            for (int i = 2; i <= L; i++) B.wcn[i] = jmax(hm.sat[i] * mcm::pow(B.phi[i] / hm.phi_e[i], 1.0 / (hm.bb[i] + 3.0)), 1e-7);
+            for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
+            B.psi[L + 1] = hm.psi_e[L];
+        }
+        for (int i = 2; i <= L; i++) B.h[i] = mcm::exp(MW_INFIL * B.psi[i] / hm.rts[i]);
+        B.h[L + 1] = B.h[L];
+        if (err <= m.moist_tol) { out.hit_max = false; break; }
+    }
+    out.surface_water_flux = ((B.psi[2] * B.K[2] - B.psi[3] * B.K[3]) / ((1.0 - hm.nexp[2]) * hm.dz[2]) + g * B.K[2] + TR) * dt;
+    for (int i = 2; i <= L + 1; i++) theta[i - 2] = B.wcn[i];
+    out.evaporation = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc) * dt;
+    return out;
+}
+
+MC_DEV double wet_surface_node(double* theta, double pool, double sat, double half_thickness)
+{
+    if (pool <= 0.0) return pool;
+    const double cap_node = half_thickness * 1000.0;
+    const double capacity = jmax(0.0, (sat - theta[0]) * cap_node);
+    const double delivered = jmin(pool, capacity);
+    theta[0] = jmin(sat, theta[0] + delivered / cap_node);
+    return pool - delivered;
+}
+
+/* per-site accessors over the SoA arrays */
+struct SiteRef {
+    const KArgs* a; int64_t s;
+    MC_MEMBER double node(const double* p, int i) const { return MC_LDG(p + (int64_t)i * a->S + s); }
+    MC_MEMBER double hourly(const double* p, int row) const { return MC_LDG(p + (int64_t)row * a->S + s); }
+    MC_MEMBER double daily(const double* p, int d) const { return MC_LDG(p + (int64_t)d * a->S + s); }
+    MC_MEMBER void put_node(double* p, int row, int node_i, double v) const { if (p) p[((int64_t)row * MC_CONST_MODEL.N + node_i) * a->S + s] = v; }
+    MC_MEMBER void put_scalar(double* p, int row, double v) const { if (p) p[(int64_t)row * a->S + s] = v; }
+};
+
+struct EnvInstant { double lai, shade, eps_surf, eps_cloud, wet_daily, T_deep, rain_daily, albedo, P, T_ref, wind, rh, zenith, cloud, lw; };
+
+MC_DEV EnvInstant get_instant(const SiteRef& r, int day, int row, double site_albedo)
+{
+    const KArgs& a = *r.a; EnvInstant e;
+    e.lai = r.daily(a.d_lai, day); e.shade = r.daily(a.d_shade, day); e.eps_surf = r.daily(a.d_eps, day); e.eps_cloud = r.daily(a.d_epsc, day);
+    e.wet_daily = r.daily(a.d_wet, day); e.T_deep = r.daily(a.d_tdeep, day); e.rain_daily = r.daily(a.d_rain, day);
+    e.albedo = a.has_albedo_daily ? r.daily(a.d_albedo, day) : site_albedo;
+    e.P = r.hourly(a.f_P, row); e.T_ref = r.hourly(a.f_T, row); e.wind = r.hourly(a.f_wind, row); e.rh = r.hourly(a.f_rh, row);
+    e.zenith = r.hourly(a.f_zen, row); e.cloud = r.hourly(a.f_cloud, row);
+    e.lw = a.has_lw ? r.hourly(a.f_lw, row) : 0.0;
+    return e;
+}
+
+/* soil_water_balance! (campbell.jl:378-495) for one hour: MOST profile -> potential evaporation -> pool wetting ->
+ * niter_moist implicit sub-steps.  Returns the new soil_wetness; updates theta, pool, L_prof and the psi/h outputs. */
+template <int NA>
+MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, const double* T0, double* theta, double& pool,
+                                       double soil_wetness, double z0, double& L_prof, double* psi_out, double* h_out,
+                                       int& flags, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
+    const int N = m.N, L = N;
+    const double T_surf = T0[0], T_air = e.T_ref, P = e.P, rh = e.rh;
+    /* atmospheric_surface_profile! restricted to what is consumed here: air temperature at the local height + Q_conv (monin_obukhov.jl:85-206) */
+    const double z = m.zref, hloc = m.zloc;
+    const double lz = mcm::log(z / z0);
+    const double dT = T_air - T_surf;
+    const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
+    double T_loc, Qc;
+    if (T_air >= T_surf || e.zenith >= 90.0) {
+        const double ustar = jmax(m.kappa * e.wind / lz, 1.0e-6);
+        const double Stb = 0.64 / lz, Sts = sublayer_stanton(z0, ustar);
+        Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
+        const double Tz0 = (T_air * Stb + T_surf * Sts) / (Stb + Sts);
+        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
+        else if (hloc == z) T_loc = T_air;
+        else T_loc = Tz0 + (T_air - Tz0) * mcm::log(hloc / z0) / lz;
+    } else {
+        const Obukhov o = calc_obukhov(e.wind, z0, z, lz, dT, rho_cp, L_prof);
+        cn.n_obukhov += o.iters;
+        L_prof = o.L; Qc = o.Q;
+        const double Tz0 = (T_air * o.Stb + T_surf * o.Sts) / (o.Stb + o.Sts);
+        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
+        else if (hloc == z) T_loc = T_air;
+        else {
+            const double x = calc_phi_m(hloc, m.gamma, o.L);
+            const double tl = jmax(mcm::log(hloc / z0) - calc_psi_h(x), 1e-6);
+            T_loc = Tz0 + (T_air - Tz0) * tl / (lz - o.psi_h);
+        }
+    }
+    /* local relative humidity and potential evaporation (campbell.jl:416-440) */
+    const double es_air = goff_gratch(T_air);
+    const double e_ref = es_air * rh;
+    const double rh_ref_prof = jclamp(e_ref / es_air, 0.0, 1.0);
+    const double rh_loc = jclamp((es_air * rh_ref_prof) / goff_gratch(T_loc), 0.0, 0.99);
+    const double hc = jmax(fabs(Qc / (T_surf - T_air)), 0.5);
+    const WetAir wa = wet_air(T_air, rh, P);
+    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
+    const double Tsc = T_surf < T_LO ? T_LO : T_surf;
+    const double Qe = (hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);      /* saturated=true */
+    const double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
+    (void)soil_wetness;
+
+    /* per-hour constants of the implicit solve */
+    HourMoist<NA> hm;
+    for (int i = 1; i <= L; i++) {
+        const double b = r.node(a.bb, i - 1), pe = -fabs(r.node(a.psi_e, i - 1)), ksat = r.node(a.ks, i - 1);
+        hm.psi_e[i] = pe; hm.bb[i] = b; hm.ks[i] = ksat;
+        hm.sat[i] = 1.0 - r.node(a.bd, i - 1) / r.node(a.md, i - 1);
+        hm.nexp[i] = 2.0 + 3.0 / b;
+        hm.fexp[i] = (2.0 * b + 3.0) / (b + 3.0);
+        hm.phi_e[i] = -ksat * pe * b / (b + 3.0);
+    }
+    hm.psi_e[L + 1] = hm.psi_e[L]; hm.sat[L + 1] = hm.sat[L]; hm.bb[L + 1] = hm.bb[L]; hm.ks[L + 1] = hm.ks[L];
+    hm.nexp[L + 1] = hm.nexp[L]; hm.fexp[L + 1] = hm.fexp[L]; hm.phi_e[L + 1] = hm.phi_e[L];
+    /* depth[1] = -1e10, depth[2] = 0, depth[i+1] = depths[i-1], depth[L+1] = 1e20 */
+    auto depth_final = [&](int i) -> double { return i == 1 ? -1e10 : (i == 2 ? 0.0 : (i == L + 1 ? 1e20 : m.depths[i - 2])); };
+    auto depth_mass = [&](int i) -> double { return i <= 2 ? 0.0 : m.depths[i - 2]; };     /* as it stands when layer_water_mass is formed (campbell.jl:228-230) */
+    for (int i = 1; i <= L; i++) hm.dz[i] = depth_final(i + 1) - depth_final(i);
+    for (int i = 2; i <= L; i++) {
+        hm.mass[i] = WATER_RHO * (depth_mass(i + 1) - depth_mass(i - 1)) / 2.0;
+        const double rd = r.node(a.rootd, i - 1);
+        const double thick = depth_final(i + 1) - depth_final(i - 1);
+        if (rd > 0.0) {
+            hm.rootR[i] = m.root_res / (rd * thick / 2.0);
+            hm.rootZ[i] = (1.0 - hm.nexp[i]) * mcm::log(PI_D * m.root_radius * m.root_radius * rd) / (4.0 * PI_D * rd * thick / 2.0);
+        } else { hm.rootR[i] = 1e20; hm.rootZ[i] = 0.0; }
+        const double Ts_i = i <= L ? T0[i - 1] : T0[L - 1];        /* B.Ts[i] = T0[i-1] */
+        hm.kvc[i] = 0.66 * DV_INFIL * vapour_density_sat(Ts_i);
+        hm.rts[i] = m.R * T0[i - 2];                                /* R * B.Ts[i-1] */
+    }
+    hm.rts1 = m.R * T0[0];
+
+    const double sat0 = 1.0 - r.node(a.bd, 0) / r.node(a.md, 0);
+    const double half = (m.depths[1] - m.depths[0]) / 2.0;
+    pool = wet_surface_node(theta, pool, sat0, half);
+    InfilWork<NA> B;
+    InfilOut io; io.evaporation = 0.0; io.surface_water_flux = 0.0; io.hit_max = false;
+    for (int k = 0; k < m.niter_moist; k++) {
+        io = infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn);
+        if (io.hit_max) flags |= MC_STATUS_NEWTON_MAXITER;
+        pool = jclamp(pool - jmax(0.0, io.surface_water_flux) - jmax(0.0, io.evaporation), 0.0, m.max_pool);
+        pool = wet_surface_node(theta, pool, sat0, half);
+    }
+    for (int i = 0; i < N; i++) { psi_out[i] = B.psi[i + 2]; h_out[i] = B.h[i + 2]; }
+    return jclamp(jmax(0.0, io.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
+}
+
+MC_DEV bool is_converged(int iter, int niter, const double* T0, const double* T0_prev, int N)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    if (m.conv_kind == MC_CONV_FIXED) return iter >= niter;
+    if (iter >= niter) return true;
+    if (iter <= 1) return niter <= 1;
+    double mx = 0.0; for (int i = 0; i < N; i++) mx = fmax(mx, fabs(T0[i] - T0_prev[i]));
+    return mx < m.conv_tol;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * solve_soil! for days [day0, day0+ndays) of site s (simulation.jl:355-819)
+ * ------------------------------------------------------------------------------------------ */
+template <int NA>
+MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const int N = m.N;
+    const int nrows = a.ndays * 24;
+    const bool dynamic = m.dynamic != 0, nonconsec = m.nonconsec != 0;
+    SiteRef r; r.a = &a; r.s = s;
+    const int64_t S = a.S;
+
+    HourSoil<NA> hs; HourPar hp; Integ<NA> I;
+    double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_prev_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
+    double psi_out[NA], h_out[NA];
+    for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; hs.lam_m[i] = r.node(a.lam_m, i); }
+    double pool = a.pool[s], wet_dyn = a.wetness[s], L_ode = a.L_ode[s], L_prof = a.L_prof[s], tdeep_stale = a.tdeep_prev[s];
+    int flags = a.flags[s];
+    const double site_albedo = MC_LDG(a.albedo + s);
+    hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
+    I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
+    for (int i = 0; i < N; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
+
+    auto set_day_forcing = [&](int jl) {
+        const int64_t off = (int64_t)jl * 24 * S + s;
+        hp.fP = a.f_P + off; hp.fT = a.f_T + off; hp.fwind = a.f_wind + off; hp.frh = a.f_rh + off; hp.fcloud = a.f_cloud + off;
+        hp.fsolar = a.f_solar + off; hp.fdiff = a.f_diffuse + off; hp.fzen = a.f_zen + off; hp.fszen = a.f_szen + off;
+    };
+    auto hoist_soil = [&]() {      /* theta-only soil property terms for the coming ODE hour */
+        for (int i = 0; i < N; i++) {
+            const double bd = r.node(a.bd, i), md = r.node(a.md, i);
+            const double th = theta[i];
+            const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
+            const double rho = th * WATER_RHO + bd;
+            hs.cap[i] = (rho * cp) * m.dzc[i] / 2.0;
+            hs.theta[i] = th; hs.phim[i] = bd / md; hs.phig[i] = jmax(0.0, 1.0 - th - bd / md);
+            hs.fw[i] = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
+        }
+    };
+    auto tins_mean = [&](int jl) { double ssum = 0.0; for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
+    auto put_potential_row = [&](int row) {
+        if (!a.o_psi) return;
+        for (int i = 0; i < N; i++) r.put_node(a.o_psi, row, i, r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i)));
+    };
+    auto init_humidity = [&](const double* Tn) {      /* initialise_soil_humidity!, dynamic.jl:32-35: always row 1 of the buffer */
+        if (!dynamic || !a.o_h) return;
+        for (int i = 0; i < N; i++) {
+            const double psi = r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i));
+            r.put_node(a.o_h, 0, i, jclamp(mcm::exp(MW_INFIL * psi / (m.R * Tn[i])), 0.0, 1.0));
+        }
+    };
+    auto write_props = [&](int row, const double* Tn, double P) {
+        if (!a.o_lam && !a.o_cp && !a.o_rho) return;
+        for (int i = 0; i < N; i++) {
+            double lam, cp, rho;
+            soil_properties_full(Tn[i], P, theta[i], r.node(a.bd, i), r.node(a.md, i), hs.lam_m[i], r.node(a.c_m, i), lam, cp, rho);
+            r.put_node(a.o_lam, row, i, lam); r.put_node(a.o_cp, row, i, cp); r.put_node(a.o_rho, row, i, rho);
+        }
+    };
+    double sky_T = 0.0;
+    auto set_hour_params = [&](const EnvInstant& e) {
+        hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud; hp.albedo = e.albedo;
+        hp.soil_wetness = dynamic ? wet_dyn : e.wet_daily;
+        sky_T = sky_temperature(hp.svf, e.P, e.rh, e.T_ref, e.eps_cloud, e.cloud, e.shade, a.has_lw != 0, e.lw);
+    };
+
+    EnvInstant env;
+    if (a.day0 == 0) {
+        /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:224-238,853-860) */
+        set_day_forcing(0);
+        env = get_instant(r, 0, 0, site_albedo);
+        for (int i = 0; i < N; i++) I.tmp[i] = a.has_init_T ? T0[i] : 280.0;
+        hoist_soil();
+        hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
+        Counters scratch = {};
+        soil_rhs<NA>(hs, hp, I.tmp, 0.0, I.k1, scratch);
+        /* solve_soil! pre-loop (simulation.jl:395-452) */
+        if (!a.has_init_T) { const double t_init = tins_mean(0); for (int i = 0; i < N; i++) T0[i] = t_init; }
+        for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
+        write_props(0, T0, 101325.0);
+        put_potential_row(0);
+        for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
+        init_humidity(T0);
+        tdeep_stale = env.T_deep;
+        pool = 0.0;
+    }
+
+    for (int jl = 0; jl < a.ndays; jl++) {
+        const int64_t j = a.day0 + jl;
+        set_day_forcing(jl);
+        const int niter = nonconsec ? m.iters_per_day : ((m.spinup && j == 0) ? m.conv_iters : 1);
+        int noon_i = 0; double best = r.hourly(a.f_zen, jl * 24);
+        for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
+        const int midnight_i = (noon_i + 12) % 24;
+        if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516) */
+            for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
+            if (!dynamic && a.has_presc) { for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
+            else for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i);
+            if (!a.has_init_T) { const double t_reset = tins_mean(jl); for (int i = 0; i < N; i++) T0[i] = t_reset; }
+            else for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i);
+        }
+        T0[N - 1] = tdeep_stale;
+        int iter = 0; bool is_last = false;
+        for (int i = 0; i < N; i++) { T0_prev_start[i] = T0[i]; T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
+        while (!is_last) {                                                    /* outer fixed point over day passes (simulation.jl:530) */
+            iter++; cn.n_day_passes++;
+            is_last = is_converged(iter, niter, T0, T0_prev_start, N);
+            for (int i = 0; i < N; i++) T0_prev_start[i] = T0[i];
+            if (!nonconsec) for (int i = 0; i < N; i++) T0[i] = T0_day_start[i];
+            for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
+            const int day_row = jl * 24;
+            if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
+                for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
+                r.put_scalar(a.o_pool, day_row, pool);
+                put_potential_row(day_row);
+                init_humidity(T0);
+                const EnvInstant e0 = get_instant(r, jl, day_row, site_albedo);
+                r.put_scalar(a.o_sky, day_row, sky_temperature(hp.svf, e0.P, e0.rh, e0.T_ref, e0.eps_cloud, e0.cloud, e0.shade, a.has_lw != 0, e0.lw));
+                write_props(day_row, T0, e0.P);
+            }
+            env = get_instant(r, jl, day_row, site_albedo);
+            T0[N - 1] = env.T_deep;
+            set_hour_params(env);
+            hp.L_prev = L_ode;
+            hoist_soil();
+            /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
+            for (int i = 0; i < N; i++) { I.u[i] = T0[i]; I.uprev[i] = T0[i]; }
+            I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
+            I.dt = determine_initdt<NA>(I, hs, hp, cn);
+            for (int i = 0; i < 24; i++) {
+                const int step = jl * 24 + i;
+                for (int k = 0; k < N; k++) T0_before[k] = T0[k];
+                if (i > 0) hoist_soil();
+                hp.L_prev = L_ode;
+                /* step_to_hour! (simulation.jl:888-903) */
+                const double target = (i + 1) * 60.0;
+                I.tstop = target;
+                while (I.t < target - 1e-10) {
+                    tsit5_step<NA>(I, hs, hp, cn);
+                    bool changed = false;
+                    for (int k = 0; k < N; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
+                    if (changed) { for (int k = 0; k < N; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
+                }
+                for (int k = 0; k < N; k++) T0[k] = I.u[k];
+                if (is_last) {
+                    phase_transition(N, m.depths, T0, T0_before, sum_phase, theta);
+                    for (int k = 0; k < N; k++) T0_output[k] = T0[k];
+                }
+                if (i < 23) {
+                    env = get_instant(r, jl, step + 1, site_albedo);
+                    T0[N - 1] = env.T_deep;
+                    set_hour_params(env);
+                }
+                for (int k = 0; k < N; k++) I.u[k] = T0[k];
+                I.u_modified = true;
+                {   /* init_surface_fluxes! (monin_obukhov.jl:247-264): hourly warm start of the Obukhov length */
+                    const double T_air = MC_LDG(hp.fT + (int64_t)i * S);
+                    const double wind = jmax(MC_LDG(hp.fwind + (int64_t)i * S), 0.1);
+                    const double zen = jmin(90.0, nearbyint(MC_LDG(hp.fzen + (int64_t)i * S) * 1000.0) / 1000.0);
+                    const double Ts = T0[0];
+                    if (T_air < Ts && zen < 90.0) {
+                        const Obukhov ob = calc_obukhov(wind, hp.z0, m.zref, hp.lz, T_air - Ts, calc_rho_cp((Ts + T_air) / 2.0), L_ode >= 0.0 ? -0.3 : L_ode);
+                        cn.n_obukhov += ob.iters;
+                        L_ode = ob.L;
+                    }
+                }
+                bool have_infil = false;
+                if (is_last) {
+                    double rain;
+                    if (m.rain_hourly) rain = r.hourly(a.f_rain, step);
+                    else rain = (i == midnight_i) ? env.rain_daily : 0.0;
+                    pool = jclamp(pool + rain, 0.0, m.max_pool);
+                    if (dynamic) {
+                        wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn);
+                        have_infil = true;
+                    }
+                }
+                const int out_row = step + 1;
+                if (is_last && out_row < nrows && !(i == 23 && nonconsec)) {
+                    r.put_scalar(a.o_pool, out_row, pool);
+                    for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
+                    r.put_scalar(a.o_sky, out_row, sky_T);
+                    if (have_infil) for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); }
+                    write_props(out_row, T0, r.hourly(a.f_P, out_row));
+                }
+            }
+        }
+        tdeep_stale = env.T_deep;
+    }
+    for (int i = 0; i < N; i++) {
+        a.T[(int64_t)i * S + s] = T0[i]; a.theta[(int64_t)i * S + s] = theta[i]; a.sum_phase[(int64_t)i * S + s] = sum_phase[i];
+        a.fsal[(int64_t)i * S + s] = I.k1[i];
+        if (!(isfinite(T0[i]) && isfinite(theta[i]))) flags |= MC_STATUS_NAN;
+    }
+    a.pool[s] = pool; a.wetness[s] = wet_dyn; a.L_ode[s] = L_ode; a.L_prof[s] = L_prof; a.tdeep_prev[s] = tdeep_stale;
+    a.flags[s] = flags | I.flags;
+}
+
+/* host side: flatten mc_model_desc into DevModel (run once per handle) */
+static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
+{
+    memset(&d, 0, sizeof(d));
+    d.N = md.n_soil;
+    d.dynamic = md.moisture_strategy == MC_MOIST_DYNAMIC;
+    d.nonconsec = md.time_mode == MC_TIME_NONCONSECUTIVE;
+    d.conv_kind = md.convergence_kind; d.conv_iters = md.convergence_iterations; d.iters_per_day = md.iterations_per_day;
+    d.spinup = md.spinup_first_day; d.rain_hourly = md.rainfall_schedule == MC_RAIN_HOURLY;
+    d.flux_alg = md.infiltration_algorithm == MC_INFIL_MATRIC_FLUX_POTENTIAL;
+    d.swinbank = md.atmospheric_radiation == MC_ATMRAD_SWINBANK;
+    d.moist_max_it = md.moisture_max_iterations;
+    d.niter_moist = (int)(3600.0 / md.moisture_timestep_s);
+    const int N = md.n_soil;
+    double ld[MC_MAX_SOIL_NODES + 1];
+    for (int i = 0; i < N; i++) { d.depths[i] = md.depths_m[i]; ld[i] = md.depths_m[i]; }
+    ld[N] = 0.0;                                          /* zero sentinel (heat_transport_1d.jl:127,173) */
+    for (int i = 0; i < N; i++) {
+        d.dzc[i] = i == 0 ? ld[1] : ld[i + 1] - ld[i - 1];
+        d.dzg[i] = ld[i + 1] - ld[i];
+    }
+    d.zref = md.reference_height_m; d.zloc = md.local_height_m; d.reltol = md.reltol; d.abstol = md.abstol;
+    d.T_hi = md.maximum_surface_temperature_K;
+    d.ga = md.de_vries_shape_factor; d.gc = 1.0 - 2.0 * d.ga; d.recirc_pow = md.recirculation_power; d.theta0 = md.return_flow_threshold;
+    d.root_res = md.root_resistance; d.PC = md.stomatal_closure_potential; d.RL = md.leaf_resistance;
+    d.SP = md.stomatal_stability_parameter; d.root_radius = md.root_radius;
+    d.kappa = md.karman_constant; d.gamma = md.dyer_constant; d.conv_tol = md.convergence_tolerance_K;
+    d.moist_tol = md.moisture_tolerance; d.moist_dt = md.moisture_timestep_s; d.max_pool = md.max_surface_pool;
+    const mc_fluid_constants& f = md.fluid;
+    d.Mw = f.molar_mass_water; d.eps = f.molar_mass_water / f.molar_mass_air; d.dep = f.ideal_gas_departure;
+    d.cpa = f.cp_dry_air; d.cpv = f.cp_water_vapour; d.R = f.gas_constant; d.sigma = f.stefan_boltzmann; d.g = f.standard_gravity;
+    d.P0 = f.standard_pressure; d.Lv_a = f.latent_heat_a; d.Lv_b = f.latent_heat_b; d.Hv_a = f.molar_latent_heat_a; d.Hv_b = f.molar_latent_heat_b;
+    d.Ma_over_R = f.molar_mass_air / f.gas_constant;
+    d.schmidt_factor = mcm::pow(0.71 / 0.60, 0.666);
+}
+
+
+} // namespace mcd

@@ -304,6 +304,15 @@ class OutputBatch:
         c.status = self.status.ctypes.data_as(C.POINTER(C.c_int32))
         return c
 
+    def assign_rows(self, row0: int, part: "OutputBatch"):
+        """Copy a day-chunk's rows into this batch at row offset `row0` (time-chunked runs)."""
+        H = 24 * part.ndays
+        for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS + ("snow_temperature",):
+            dst, src = getattr(self, f), getattr(part, f)
+            if dst is not None and src is not None:
+                dst[row0:row0 + H] = src
+        self.status |= part.status
+
     def site_result(self, s: int) -> T.MicroResult:
         """Un-marshal one site into the reference's per-site (nsteps, N) layout."""
         r = T.MicroResult()

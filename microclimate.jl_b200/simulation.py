@@ -1,0 +1,162 @@
+"""Batched-sites soil engine — the host-side mirror of the reference's `solve_soil!` entry
+(src/simulation.jl:355-819) and of its many-sites idiom `reinit!(cache, inputs); solve!(cache)`
+(src/simulation.jl:266-277): ONE MicroModel, MANY MicroInputs.
+
+Everything here is marshalling and orchestration; all arithmetic runs in the CUDA library behind the
+C ABI (include/microclimate_b200.h).  No CUDA device -> RuntimeError (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+from . import _lib
+from . import marshal as M
+from . import types as T
+
+
+class SoilEngine:
+    """One handle = one GPU, S sites resident in HBM (mc_create / mc_set_sites / mc_step_days / mc_destroy)."""
+
+    def __init__(self, desc: A.ModelDesc, n_sites: int, device: int = 0):
+        self.desc, self.S, self.device = desc, int(n_sites), int(device)
+        self._L = _lib.lib()
+        self.h = C.c_void_p()
+        rc = self._L.mc_create(C.byref(desc), self.S, self.device, C.byref(self.h))
+        if rc != 0:
+            msg = self._L.mc_last_error(None)
+            self.h = None
+            raise RuntimeError(f"mc_create failed (rc={rc}): {msg.decode() if msg else ''}")
+
+    # -- lifetime --------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.mc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            msg = self._L.mc_last_error(self.h)
+            raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    # -- reference-shaped operations ----------------------------------------------------------------
+    def set_sites(self, sites: M.SitesBatch):
+        """reinit!(cache, inputs): new sites, fresh state (src/simulation.jl:274-277)."""
+        if sites.S != self.S or sites.N != self.desc.n_soil:
+            raise ValueError(f"SitesBatch is {sites.N} nodes x {sites.S} sites; engine expects {self.desc.n_soil} x {self.S}")
+        cs, ci = sites.c_sites(), sites.c_initial()
+        self._check(self._L.mc_set_sites(self.h, C.byref(cs), C.byref(ci)), "mc_set_sites")
+
+    def step_days(self, day0: int, forcing: M.ForcingBatch, out: M.OutputBatch) -> int:
+        """solve_soil! for days [day0, day0+forcing.ndays): host buffers in/out, H2D + kernel + D2H.
+        Returns the number of sites whose status word is non-zero."""
+        if forcing.S != self.S or out.S != self.S or out.ndays != forcing.ndays:
+            raise ValueError("forcing/output batch shapes do not match the engine")
+        cf, co = forcing.c_struct(), out.c_struct()
+        return self._check(self._L.mc_step_days(self.h, day0, forcing.ndays, C.byref(cf), C.byref(co)), "mc_step_days")
+
+    def step_days_device(self, day0: int, ndays: int, forcing_ptrs: dict, output_ptrs: dict):
+        """Same with DEVICE pointers (ints) already resident on this GPU; asynchronous until synchronize()."""
+        cf, co = A.ForcingSoA(), A.OutputSoA()
+        pd = C.POINTER(C.c_double)
+        for k, v in forcing_ptrs.items():
+            setattr(cf, k, C.cast(C.c_void_p(int(v)), pd))
+        for k, v in output_ptrs.items():
+            setattr(co, k, C.cast(C.c_void_p(int(v)), pd))
+        self._check(self._L.mc_step_days_device(self.h, day0, ndays, C.byref(cf), C.byref(co)), "mc_step_days_device")
+
+    def synchronize(self):
+        self._check(self._L.mc_synchronize(self.h), "mc_synchronize")
+
+    def counters(self) -> dict:
+        c = A.Counters()
+        self._check(self._L.mc_get_counters(self.h, C.byref(c)), "mc_get_counters")
+        return c.as_dict()
+
+    def reset_counters(self):
+        self._check(self._L.mc_reset_counters(self.h), "mc_reset_counters")
+
+    def status(self) -> np.ndarray:
+        st = np.zeros(self.S, dtype=np.int32)
+        self._check(self._L.mc_get_status(self.h, st.ctypes.data_as(C.POINTER(C.c_int32))), "mc_get_status")
+        return st
+
+    def get_state(self) -> M.StateBatch:
+        st = M.StateBatch(self.desc.n_soil, self.desc.n_snow, self.S)
+        cs = st.c_struct()
+        self._check(self._L.mc_get_state(self.h, C.byref(cs)), "mc_get_state")
+        return st
+
+    def set_state(self, st: M.StateBatch):
+        cs = st.c_struct()
+        self._check(self._L.mc_set_state(self.h, C.byref(cs)), "mc_set_state")
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._check(self._L.mc_measure_fp64_peak(self.h, C.byref(v)), "mc_measure_fp64_peak")
+        return v.value
+
+
+def site_shards(n_sites: int, n_shards: int):
+    """Contiguous, near-equal site ranges [lo, hi) — the only partitioning the path needs (no collective)."""
+    base, rem = divmod(n_sites, n_shards)
+    out, lo = [], 0
+    for g in range(n_shards):
+        hi = lo + base + (1 if g < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, days: Sequence[int],
+                       time_mode=None, fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS,
+                       chunk_days: Optional[int] = None, device: int = 0) -> M.OutputBatch:
+    """Batched `solve_soil!`: one model, many inputs -> one OutputBatch (site-fastest); `site_result(s)`
+    un-marshals a site into the reference's (nsteps, N) MicroResult layout.
+
+    `chunk_days` streams time in chunks with the carried state resident on the GPU (results are identical
+    to a single chunk: the state carried between chunks is exactly what the reference carries between days)."""
+    time_mode = time_mode if time_mode is not None else T.NonConsecutiveDayMode()
+    if len(inputs) == 0:
+        raise ValueError("inputs must be non-empty")
+    desc = M.model_desc(model, time_mode, inputs0=inputs[0])
+    sites = M.SitesBatch.from_inputs(model, inputs)
+    forcing = M.ForcingBatch.from_inputs(model, inputs, days)
+    ndays, S = len(days), len(inputs)
+    out = M.OutputBatch(ndays, desc.n_soil, S, fields, desc.n_snow)
+    with SoilEngine(desc, S, device) as eng:
+        eng.set_sites(sites)
+        if not chunk_days or chunk_days >= ndays:
+            eng.step_days(0, forcing, out)
+        else:
+            d0 = 0
+            while d0 < ndays:
+                d1 = min(ndays, d0 + chunk_days)
+                part = M.OutputBatch(d1 - d0, desc.n_soil, S, fields, desc.n_snow)
+                eng.step_days(d0, forcing.day_slice(d0, d1), part)
+                out.assign_rows(24 * d0, part)
+                d0 = d1
+            out.status[:] = eng.status()
+    return out
+
+
+def solve_soil(problem: T.MicroProblem, **kw) -> T.MicroResult:
+    """Single-site convenience mirroring `solve(problem)` for the soil path."""
+    out = solve_soil_batched(problem.model, [problem.inputs], days=problem.days, time_mode=problem.time_mode, **kw)
+    return out.site_result(0)

@@ -22,6 +22,7 @@
  * K/min exactly as the reference (src/simulation.jl:856, heat_transport_1d.jl:279).
  */
 #include "../include/microclimate_b200.h"
+#include "../include/mc_math.h"   /* bit-reproducible exp/log/pow/atan/cos shared with the CUDA engine (see its header) */
 
 #include <algorithm>
 #include <cmath>
@@ -65,14 +66,14 @@ static double goff_gratch(double T)
     double loge;
     if (Tp <= 273.16) {
         const double r = 273.16 / Tp;
-        loge = -9.09718 * (r - 1.0) - 3.56654 * std::log10(r) + 0.876793 * (1.0 - Tp / 273.16) + std::log10(6.1071);
+        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - Tp / 273.16) + 0.7858350313586662 /* log10(6.1071) */;
     } else {
         const double r = 373.16 / Tp;
-        loge = -7.90298 * (r - 1.0) + 5.02808 * std::log10(r)
-             - 1.3816e-7 * (std::pow(10.0, 11.344 * (1.0 - Tp / 373.16)) - 1.0)
-             + 8.1328e-3 * (std::pow(10.0, -3.49149 * (r - 1.0)) - 1.0) + std::log10(1013.246);
+        loge = -7.90298 * (r - 1.0) + 5.02808 * mcm::log10(r)
+             - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - Tp / 373.16)) - 1.0)
+             + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314 /* log10(1013.246) */;
     }
-    return 100.0 * std::pow(10.0, loge);
+    return 100.0 * mcm::exp10(loge);
 }
 
 struct WetAir { double vapour_pressure, vapour_density, specific_heat, density, mixing_ratio; };
@@ -151,7 +152,7 @@ static SoilProps soil_properties(const mc_model_desc& m, double P, double T, dou
     o.density = theta * WATER_DENSITY + bulk_density;
     const double lam_w = 0.554 + 2.24e-3 * Tc - 9.87e-6 * Tc * Tc;     /* :104 */
     const double lam_a = 0.024 + 7.73e-5 * Tc - 2.6e-8 * Tc * Tc;      /* :106 */
-    const double Dv = VAPOUR_DIFFUSIVITY_STP * (fc.standard_pressure / P) * std::pow(T / 273.15, 1.75);  /* :109 */
+    const double Dv = VAPOUR_DIFFUSIVITY_STP * (fc.standard_pressure / P) * mcm::pow(T / 273.15, 1.75);  /* :109 */
     const double rho_hat = VAPOUR_MOLAR_DENSITY_STP * (P / fc.standard_pressure) * (273.15 / T);        /* :111 */
     const double Hv = molar_enthalpy_of_vaporisation(fc, T);                                            /* :112 */
     const double e0 = goff_gratch(T) * 0.99;                                                            /* :117 */
@@ -160,7 +161,7 @@ static SoilProps soil_properties(const mc_model_desc& m, double P, double T, dou
     const double dedT = (ep - em) / 2.0;                                                                /* :122 */
     const double phi_m = bulk_density / mineral_density;
     const double phi_g = jmax(0.0, 1.0 - theta - phi_m);
-    const double fw = 1.0 / (1.0 + std::pow(theta / m.return_flow_threshold, -m.recirculation_power));  /* :127 */
+    const double fw = 1.0 / (1.0 + mcm::pow(theta / m.return_flow_threshold, -m.recirculation_power));  /* :127 */
     const double lam_g = lam_a + Hv * dedT * fw * rho_hat * Dv / (P - e0);                              /* :130 */
     const double lam_f = lam_g + fw * (lam_w - lam_g);                                                  /* :132 */
     const double ww = weight(lam_w, lam_f), wm = weight(mineral_conductivity, lam_f), wg = weight(lam_g, lam_f);
@@ -175,13 +176,13 @@ static SoilProps soil_properties(const mc_model_desc& m, double P, double T, dou
 static const double RHOCPTKG_SI = 6.003e-8 * 4.184 * 3600.0 * 1.0e8;   /* :135,:234  cal min2/cm4 -> J s2/m4 */
 
 static inline double calc_rho_cp(double Tmean) { return (0.08472 / Tmean) * 4.184e6; }                 /* :280-282 */
-static inline double sublayer_stanton(double z0, double ustar) { return 0.62 / std::pow(z0 * 100.0 * (ustar * 6000.0) / 12.0, 0.45); } /* :414-416 */
+static inline double sublayer_stanton(double z0, double ustar) { return 0.62 / mcm::pow(z0 * 100.0 * (ustar * 6000.0) / 12.0, 0.45); } /* :414-416 */
 static inline double bulk_stanton(double lzr) { return 0.64 / lzr; }                                    /* :423-425 */
 static inline double bulk_stanton(double lzr, double z, double L) { return (0.64 / lzr) * (1.0 - 0.1 * z / L); } /* :432-434 */
 static inline double convective_flux(double rho_cp, double dT, double ustar, double Stb, double Sts) { return rho_cp * dT * ustar * Stb / (1.0 + Stb / Sts); } /* :386-388 */
 static inline double calc_phi_m(double z, double gamma, double L) { return std::sqrt(std::sqrt(1.0 - gamma * z / L)); } /* :464-468 */
-static inline double calc_psi_m(double x) { return 2.0 * std::log((1.0 + x) / 2.0) + std::log((1.0 + x * x) / 2.0) - 2.0 * std::atan(x) + M_PI / 2.0; } /* :491-493 */
-static inline double calc_psi_h(double x) { return 2.0 * std::log((1.0 + std::pow(x, 2.0)) / 2.0); }   /* :516-518 */
+static inline double calc_psi_m(double x) { return 2.0 * mcm::log((1.0 + x) / 2.0) + mcm::log((1.0 + x * x) / 2.0) - 2.0 * mcm::atan(x) + M_PI / 2.0; } /* :491-493 */
+static inline double calc_psi_h(double x) { return 2.0 * mcm::log((1.0 + x * x) / 2.0); }   /* :516-518 */
 
 struct ObukhovOut { double L, Sts, Stb, ustar, psi_h, Q, T_z0; int iters; };
 
@@ -196,7 +197,7 @@ static ObukhovOut calc_obukhov(double T_ref, double T_surf, double v_ref, double
         const double x = calc_phi_m(z, gamma, o.L);
         const double psi_m = calc_psi_m(x);
         o.psi_h = calc_psi_h(x);
-        double lrc = std::log(z / z0) - psi_m;
+        double lrc = mcm::log(z / z0) - psi_m;
         if (lrc <= 0.0) lrc = tiny;
         o.ustar = kappa * v_ref / lrc;
         if (o.ustar < tiny) o.ustar = tiny;
@@ -219,7 +220,7 @@ static void surface_fluxes(const mc_model_desc& m, double T_surf, double T_air, 
                            double z0, double zref, double L_prev, double& Qc, double& dT, Counters& cn)
 {
     const double kappa = m.karman_constant;
-    const double lzr = std::log(zref / z0);
+    const double lzr = mcm::log(zref / z0);
     dT = T_air - T_surf;
     const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
     if (T_air >= T_surf || zenith >= 90.0) {
@@ -246,7 +247,7 @@ static double evaporation_Q(const mc_fluid_constants& fc, double T_surf, double 
 }
 
 static inline double heat_transfer_coefficient(double Qc, double dT) { return dT == 0.0 ? 0.5 : jmax(std::fabs(Qc / dT), 0.5); } /* monin_obukhov.jl:397-398 */
-static inline double mass_transfer_coefficient(double hc, double cp, double rho) { return (hc / (cp * rho)) * std::pow(0.71 / 0.60, 0.666); } /* :406-407 */
+static inline double mass_transfer_coefficient(double hc, double cp, double rho) { return (hc / (cp * rho)) * mcm::pow(0.71 / 0.60, 0.666); } /* :406-407 */
 
 /* surface_convection_evaporation, bulk_transfer.jl:55-81 */
 static void surface_convection_evaporation(const mc_model_desc& m, double T_surf, double T_air, double wind, double rh,
@@ -266,9 +267,9 @@ static double atmospheric_radiation(const mc_model_desc& m, double e_Pa, double 
 {
     const double sigma = m.fluid.stefan_boltzmann;
     if (m.atmospheric_radiation == MC_ATMRAD_SWINBANK)
-        return (9.2e-6 * T_air * T_air) * sigma * std::pow(T_air, 4);
+        return (9.2e-6 * T_air * T_air) * sigma * mcm::pow4(T_air);
     const double Tp = T_air + 0.01;
-    return (1.72 * std::pow((e_Pa / 1000.0) / Tp, 1.0 / 7.0)) * sigma * std::pow(Tp, 4);
+    return (1.72 * mcm::pow((e_Pa / 1000.0) / Tp, 1.0 / 7.0)) * sigma * mcm::pow4(Tp);
 }
 
 /* precompute_longwave_sky -> sky temperature only (the RHS recomputes the fluxes itself),
@@ -277,8 +278,8 @@ static double sky_temperature(const mc_model_desc& m, double svf, double P, doub
                               double cloud, double shade, bool has_lw, double supplied_lw)
 {
     const double sigma = m.fluid.stefan_boltzmann;
-    const double cloud_rad = sigma * eps_cloud * std::pow(T_ref - 2.0, 4);
-    const double hill_rad = sigma * eps_cloud * std::pow(T_ref, 4);
+    const double cloud_rad = sigma * eps_cloud * mcm::pow4(T_ref - 2.0);
+    const double hill_rad = sigma * eps_cloud * mcm::pow4(T_ref);
     double lw_sky;
     if (has_lw) lw_sky = supplied_lw * (1.0 - shade);
     else {
@@ -288,7 +289,7 @@ static double sky_temperature(const mc_model_desc& m, double svf, double P, doub
     }
     const double lw_veg = shade * hill_rad;
     const double incoming = (lw_sky + lw_veg) * svf + hill_rad * (1.0 - svf);
-    return std::pow(incoming / sigma, 0.25);
+    return mcm::pow(incoming / sigma, 0.25);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -351,19 +352,19 @@ static void soil_energy_balance(const double* u, const RhsParams& p, double t, d
 
     double Q_solar = (1.0 - p.albedo) * f.solar * (1.0 - p.shade);                         /* :223 */
     if (s.slope > 0.0 && f.zenith < 90.0) {                                                /* :224-232 */
-        const double cz = std::cos(f.zenith * M_PI / 180.0), csz = std::cos(f.slope_zenith * M_PI / 180.0);
+        const double cz = mcm::cos(f.zenith * M_PI / 180.0), csz = mcm::cos(f.slope_zenith * M_PI / 180.0);
         const double direct = (1.0 - f.diffuse_fraction) * Q_solar, diffuse = f.diffuse_fraction * Q_solar;
         Q_solar = jmax(0.0, (direct / cz) * csz) + diffuse * s.svf;
     }
     const WetAir wa = wet_air(m.fluid, f.air_temperature, f.humidity, f.pressure);         /* :239 */
     const double atm = atmospheric_radiation(m, wa.vapour_pressure, f.air_temperature);
-    const double cloud_rad = sigma * p.eps_cloud * std::pow(f.air_temperature - 2.0, 4);
-    const double hill_rad = sigma * p.eps_cloud * std::pow(f.air_temperature, 4);
+    const double cloud_rad = sigma * p.eps_cloud * mcm::pow4(f.air_temperature - 2.0);
+    const double hill_rad = sigma * p.eps_cloud * mcm::pow4(f.air_temperature);
     const double lw_sky = (atm * (1.0 - f.cloud) + cloud_rad * f.cloud) * (1.0 - p.shade);
     const double lw_veg = p.shade * hill_rad;
     const double incoming = (lw_sky + lw_veg) * s.svf + hill_rad * (1.0 - s.svf);
     const double out_coeff = (1.0 - p.shade) * sigma * p.eps_surf;
-    const double Q_ir = incoming - out_coeff * std::pow(T[j], 4) - p.shade * hill_rad;     /* :250 */
+    const double Q_ir = incoming - out_coeff * mcm::pow4(T[j]) - p.shade * hill_rad;     /* :250 */
 
     const double cond_ref = (t == 0.0 && j > 0) ? T[0] : T[j];                             /* :255 */
     const double Q_cond = j < M - 1 ? G[j] * (T[j + 1] - cond_ref) : 0.0;
@@ -417,7 +418,7 @@ static inline float fastlog2f(float x)
 static inline double fastpow(double x, double y)
 {
     const float l = fastlog2f((float)x) * (float)y;
-    return (double)(float)std::exp2((double)l);   /* correctly rounded Float32 exp2 */
+    return (double)(float)mcm::exp2((double)l);   /* correctly rounded Float32 exp2 */
 }
 
 struct Integrator {
@@ -453,7 +454,7 @@ static double determine_initdt(const Integrator& I, const RhsParams& p, Counters
     const double md = std::max(d1, d2);
     double dt1;
     if (md <= 1e-15) dt1 = std::max(1e-6, dt0 * 1e-3);
-    else dt1 = std::pow(10.0, -(2.0 + std::log10(md)) / 5.0);
+    else dt1 = mcm::exp10(-(2.0 + mcm::log10(md)) / 5.0);
     return std::min(std::min(100.0 * dt0, dt1), dtmax);
 }
 
@@ -636,20 +637,20 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
     /* initial_state_from_water_content! + state_to_water_potential! (:220-221) */
     if (!flux_alg) {
         for (int i = 2; i <= L; i++) {
-            B.psi[i] = B.psi_e[i] * std::pow(B.sat[i] / B.wcn[i], bb(i));
-            B.K[i] = ks(i) * std::pow(B.psi_e[i] / B.psi[i], B.nexp[i]);
+            B.psi[i] = B.psi_e[i] * mcm::pow(B.sat[i] / B.wcn[i], bb(i));
+            B.K[i] = ks(i) * mcm::pow(B.psi_e[i] / B.psi[i], B.nexp[i]);
         }
         B.psi[L + 1] = B.psi_e[L];
     } else {
         for (int i = 2; i <= L; i++) {
-            B.phi[i] = B.phi_e[i] * std::pow(B.wcn[i] / B.sat[i], bb(i) + 3.0);
-            B.K[i] = ks(i) * std::pow(B.phi[i] / B.phi_e[i], B.fexp[i]);
+            B.phi[i] = B.phi_e[i] * mcm::pow(B.wcn[i] / B.sat[i], bb(i) + 3.0);
+            B.K[i] = ks(i) * mcm::pow(B.phi[i] / B.phi_e[i], B.fexp[i]);
         }
         B.phi[L + 1] = B.phi_e[L];
-        for (int i = 2; i <= L; i++) B.psi[i] = B.psi_e[i] * std::pow(B.sat[i] / B.wcn[i], bb(i));
+        for (int i = 2; i <= L; i++) B.psi[i] = B.psi_e[i] * mcm::pow(B.sat[i] / B.wcn[i], bb(i));
         B.psi[L + 1] = B.psi_e[L];
     }
-    for (int i = 2; i <= L; i++) B.h[i] = std::exp(Mw * B.psi[i] / (R * B.Ts[i - 1]));      /* :223-225 */
+    for (int i = 2; i <= L; i++) B.h[i] = mcm::exp(Mw * B.psi[i] / (R * B.Ts[i - 1]));      /* :223-225 */
     for (int i = 2; i <= L; i++) B.mass[i] = WATER_DENSITY * (B.depth[i + 1] - B.depth[i - 1]) / 2.0;   /* :228-230 */
     B.h[L + 1] = 1.0; B.wc[L + 1] = B.sat[L + 1]; B.wcn[L + 1] = B.sat[L + 1];              /* :232-237 */
     B.depth[1] = -1e10; B.depth[L + 1] = 1e20; B.K[L + 1] = ks(L);
@@ -657,11 +658,11 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
         const double rd = s.rootd[i - 1];
         if (rd > 0.0) {
             B.rootR[i] = m.root_resistance / (rd * (B.depth[i + 1] - B.depth[i - 1]) / 2.0);
-            B.rootZ[i] = B.ncomp[i] * std::log(M_PI * m.root_radius * m.root_radius * rd) / (4.0 * M_PI * rd * (B.depth[i + 1] - B.depth[i - 1]) / 2.0);
+            B.rootZ[i] = B.ncomp[i] * mcm::log(M_PI * m.root_radius * m.root_radius * rd) / (4.0 * M_PI * rd * (B.depth[i + 1] - B.depth[i - 1]) / 2.0);
         } else { B.rootR[i] = 1e20; B.rootZ[i] = 0.0; }
     }
     B.psi[1] = B.psi[2]; B.K[1] = 0.0;                                                      /* :250-251 */
-    const double EP = std::exp(-0.82 * lai) * ET;                                           /* :254-255 */
+    const double EP = mcm::exp(-0.82 * lai) * ET;                                           /* :254-255 */
     const double TP = ET - EP;
     double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;                                          /* :258-267 */
     for (int i = 2; i <= L; i++) {
@@ -674,14 +675,14 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
     int counter = 0;
     while (counter < max_it) {                                                              /* :270-284 */
         if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
-        const double xp = std::pow(psi_leaf / PC, SP);
+        const double xp = mcm::pow(psi_leaf / PC, SP);
         const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
         const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
         psi_leaf = psi_leaf - resid / slope;
         counter++;
         if (std::fabs(resid) <= 10.0) break;
     }
-    const double xp = std::pow(psi_leaf / PC, SP);                                          /* :285-289 */
+    const double xp = mcm::pow(psi_leaf / PC, SP);                                          /* :285-289 */
     const double TR = TP / (1.0 + xp);
     for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (B.rootR[i] + B.soilR[i]);
 
@@ -691,10 +692,10 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
         double err = 0.0;
         counter++; cn.n_newton++;
         for (int i = 2; i <= L; i++) {
-            if (!flux_alg) B.K[i] = ks(i) * std::pow(B.psi_e[i] / B.psi[i], B.nexp[i]);
-            else B.K[i] = ks(i) * std::pow(B.phi[i] / B.phi_e[i], B.fexp[i]);
+            if (!flux_alg) B.K[i] = ks(i) * mcm::pow(B.psi_e[i] / B.psi[i], B.nexp[i]);
+            else B.K[i] = ks(i) * mcm::pow(B.phi[i] / B.phi_e[i], B.fexp[i]);
         }
-        if (flux_alg) { for (int i = 2; i <= L; i++) B.psi[i] = B.psi_e[i] * std::pow(B.sat[i] / B.wcn[i], bb(i)); B.psi[L + 1] = B.psi_e[L]; }
+        if (flux_alg) { for (int i = 2; i <= L; i++) B.psi[i] = B.psi_e[i] * mcm::pow(B.sat[i] / B.wcn[i], bb(i)); B.psi[L + 1] = B.psi_e[L]; }
         B.jv[1] = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc);                                  /* :301-302 */
         B.djv[1] = EP * Mw * B.h[2] / (R * B.Ts[1] * (1.0 - rh_loc));
         for (int i = 2; i <= L; i++) {                                                      /* :307-312 */
@@ -745,15 +746,15 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
         }
         if (!flux_alg) {                                                                    /* recover_water_content! */
             for (int i = 2; i <= L; i++) {
-                B.wcn[i] = jmax(B.sat[i] * std::pow(B.psi_e[i] / B.psi[i], B.binv[i]), 1e-7);
-                B.psi[i] = B.psi_e[i] * std::pow(B.sat[i] / B.wcn[i], bb(i));
+                B.wcn[i] = jmax(B.sat[i] * mcm::pow(B.psi_e[i] / B.psi[i], B.binv[i]), 1e-7);
+                B.psi[i] = B.psi_e[i] * mcm::pow(B.sat[i] / B.wcn[i], bb(i));
             }
         } else {
-            for (int i = 2; i <= L; i++) B.wcn[i] = jmax(B.sat[i] * std::pow(B.phi[i] / B.phi_e[i], 1.0 / (bb(i) + 3.0)), 1e-7);
-            for (int i = 2; i <= L; i++) B.psi[i] = B.psi_e[i] * std::pow(B.sat[i] / B.wcn[i], bb(i));
+            for (int i = 2; i <= L; i++) B.wcn[i] = jmax(B.sat[i] * mcm::pow(B.phi[i] / B.phi_e[i], 1.0 / (bb(i) + 3.0)), 1e-7);
+            for (int i = 2; i <= L; i++) B.psi[i] = B.psi_e[i] * mcm::pow(B.sat[i] / B.wcn[i], bb(i));
             B.psi[L + 1] = B.psi_e[L];
         }
-        for (int i = 2; i <= L; i++) B.h[i] = std::exp(Mw * B.psi[i] / (R * B.Ts[i - 1]));  /* :329-332 */
+        for (int i = 2; i <= L; i++) B.h[i] = mcm::exp(Mw * B.psi[i] / (R * B.Ts[i - 1]));  /* :329-332 */
         B.h[L + 1] = B.h[L];
         if (err <= tolr) { out.hit_max = false; break; }
     }
@@ -786,7 +787,7 @@ static void surface_profile(const mc_model_desc& m, double z0, const EnvInstant&
 {
     const double z = m.reference_height_m, h = m.local_height_m, kappa = m.karman_constant, gamma = m.dyer_constant;
     const double T_ref = e.T_ref;
-    const double lzr = std::log(z / z0);
+    const double lzr = mcm::log(z / z0);
     const double dT = T_ref - T_surf;
     const double rho_cp = calc_rho_cp((T_surf + T_ref) / 2.0);
     if (T_ref >= T_surf || e.zenith >= 90.0) {
@@ -795,7 +796,7 @@ static void surface_profile(const mc_model_desc& m, double z0, const EnvInstant&
         const double Tz0 = (T_ref * bulk_stanton(lzr) + T_surf * sublayer_stanton(z0, ustar)) / (bulk_stanton(lzr) + sublayer_stanton(z0, ustar));
         if (h < z0) T_loc = T_surf + (Tz0 - T_surf) * (h / z0);
         else if (h == z) T_loc = T_ref;
-        else T_loc = Tz0 + (T_ref - Tz0) * std::log(h / z0) / lzr;
+        else T_loc = Tz0 + (T_ref - Tz0) * mcm::log(h / z0) / lzr;
     } else {
         ObukhovOut o = calc_obukhov(T_ref, T_surf, e.wind, z0, z, kappa, dT, rho_cp, 16.0, 30, 1e-2, L_prof);
         cn.n_obukhov += o.iters;
@@ -805,8 +806,8 @@ static void surface_profile(const mc_model_desc& m, double z0, const EnvInstant&
         else {
             const double x = calc_phi_m(h, gamma, o.L);
             const double psi_h2 = calc_psi_h(x);
-            const double tl = jmax(std::log(h / z0) - psi_h2, 1e-6);
-            T_loc = o.T_z0 + (T_ref - o.T_z0) * tl / (std::log(z / z0) - o.psi_h);
+            const double tl = jmax(mcm::log(h / z0) - psi_h2, 1e-6);
+            T_loc = o.T_z0 + (T_ref - o.T_z0) * tl / (mcm::log(z / z0) - o.psi_h);
         }
     }
 }
@@ -829,7 +830,7 @@ static WaterOut soil_water_balance(InfilBuffers& B, const mc_model_desc& m, cons
     const double rh_loc = jclamp(wref.vapour_pressure / wloc.vapour_pressure, 0.0, 0.99);    /* :418 */
     const double hc = jmax(std::fabs(Qc / (T_surf - T_air)), 0.5);                           /* :419 */
     const WetAir wa = wet_air(fc, T_air, rh, P);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * std::pow(0.71 / 0.60, 0.666); /* :423 */
+    const double hd = (hc / (wa.specific_heat * wa.density)) * mcm::pow(0.71 / 0.60, 0.666); /* :423 */
     const double Qe = evaporation_Q(fc, T_surf, T_air, rh, 1.0, hd, P, soil_wetness, true);  /* :424-434 */
     const double Lv = enthalpy_of_vaporisation(fc, T_surf);
     double EP = jmax(1e-7, Qe / Lv);                                                         /* :436 */
@@ -980,14 +981,14 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
     I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.EEst = 1; I.tstop_next = 1440.0;
     for (int i = 0; i < M; i++) { I.fsalfirst[i] = st.fsal[i]; I.fsallast[i] = st.fsal[i]; }
     auto put_water_potential_row = [&](int row) {
-        for (int i = 0; i < N; i++) io.put_node(o.soil_water_potential, row, i, site.psi_e[i] * std::pow(sat[i] / theta[i], site.bb[i]));
+        for (int i = 0; i < N; i++) io.put_node(o.soil_water_potential, row, i, site.psi_e[i] * mcm::pow(sat[i] / theta[i], site.bb[i]));
     };
     auto init_soil_humidity = [&](int row, const double* Tn) {   /* initialise_soil_humidity!, dynamic.jl:32-35 — always row 1 of the buffer */
         if (!dynamic) return;
         (void)row;
         for (int i = 0; i < N; i++) {
-            const double psi = site.psi_e[i] * std::pow(sat[i] / theta[i], site.bb[i]);
-            io.put_node(o.soil_humidity, 0, i, jclamp(std::exp(0.01801528 * psi / (m.fluid.gas_constant * Tn[i])), 0.0, 1.0));
+            const double psi = site.psi_e[i] * mcm::pow(sat[i] / theta[i], site.bb[i]);
+            io.put_node(o.soil_humidity, 0, i, jclamp(mcm::exp(0.01801528 * psi / (m.fluid.gas_constant * Tn[i])), 0.0, 1.0));
         }
     };
     EnvInstant env;
@@ -1271,12 +1272,12 @@ void mco_surface_profile(const mc_model_desc* m, double z0, double T_ref, double
     const double z = m->reference_height_m, h = m->local_height_m, kappa = m->karman_constant;
     double v;
     if (T_ref >= T_surf || zenith >= 90.0) {
-        const double ustar = mco::jmax(kappa * wind / std::log(z / z0), 1e-6);
-        v = h < z0 ? 0.0 : (ustar / kappa) * std::log(h / z0 + 0.0);
+        const double ustar = mco::jmax(kappa * wind / mcm::log(z / z0), 1e-6);
+        v = h < z0 ? 0.0 : (ustar / kappa) * mcm::log(h / z0 + 0.0);
     } else {
         mco::ObukhovOut o = mco::calc_obukhov(T_ref, T_surf, wind, z0, z, kappa, T_ref - T_surf, mco::calc_rho_cp((T_surf + T_ref) / 2.0), 16.0, 30, 1e-2, L_prev);
         const double x = mco::calc_phi_m(h, m->dyer_constant, o.L);
-        v = h < z0 ? 0.0 : (o.ustar / kappa) * mco::jmax(std::log(h / z0) - mco::calc_psi_m(x), 1e-6);
+        v = h < z0 ? 0.0 : (o.ustar / kappa) * mco::jmax(mcm::log(h / z0) - mco::calc_psi_m(x), 1e-6);
     }
     out4[0] = T_loc; out4[1] = v; out4[2] = Qc; out4[3] = L;
 }

@@ -1,0 +1,124 @@
+/*
+ * hostemu.cpp — DEVELOPMENT/TEST HARNESS, not product code and not a fallback.
+ *
+ * Compiles the product's per-site kernel body (microclimate.jl_b200/csrc/mc_device.cuh) with g++ and
+ * runs it site by site on the CPU, so the logic the CUDA kernel executes can be checked against the
+ * oracle in the CPU-only test tier (`pytest -m "not gpu"`), where no GPU exists.  Nothing in the
+ * product loads this library: libmicroclimate_b200.so has no CPU path and fails without a CUDA device.
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../microclimate.jl_b200/csrc/mc_device.cuh"
+
+namespace {
+struct Emu {
+    mc_model_desc model; int64_t S; int N; int64_t days_done;
+    std::vector<double> site[4], node[8], init_T, init_theta, T, theta, sum_phase, fsal, pool, wet, L_ode, L_prof, tdeep;
+    std::vector<int32_t> flags; bool has_init_T;
+    unsigned long long counters[8];
+};
+}
+
+extern "C" {
+
+void* he_create(const mc_model_desc* m, int64_t S)
+{
+    if (!m || m->n_snow != 0) return nullptr;
+    Emu* e = new Emu(); e->model = *m; e->S = S; e->N = m->n_soil; e->days_done = 0; std::memset(e->counters, 0, sizeof(e->counters));
+    return e;
+}
+void he_destroy(void* h) { delete (Emu*)h; }
+
+int he_set_sites(void* h, const mc_sites_soa* s, const mc_initial_soa* init)
+{
+    Emu* e = (Emu*)h; const size_t S = e->S, N = e->N;
+    const double* ss[4] = {s->roughness_height, s->slope, s->sky_view_fraction, s->albedo};
+    const double* ns[8] = {s->bulk_density, s->mineral_density, s->mineral_conductivity, s->mineral_heat_capacity, s->air_entry_water_potential,
+                           s->saturated_hydraulic_conductivity, s->campbell_b_parameter, s->root_density};
+    for (int k = 0; k < 4; k++) e->site[k].assign(ss[k], ss[k] + S);
+    for (int k = 0; k < 8; k++) e->node[k].assign(ns[k], ns[k] + N * S);
+    e->has_init_T = init->initial_soil_temperature != nullptr;
+    const double qnan = std::numeric_limits<double>::quiet_NaN();
+    e->init_T.assign(N * S, qnan);
+    if (e->has_init_T) e->init_T.assign(init->initial_soil_temperature, init->initial_soil_temperature + N * S);
+    e->init_theta.assign(init->initial_soil_moisture, init->initial_soil_moisture + N * S);
+    e->T = e->init_T; e->theta = e->init_theta; e->sum_phase.assign(N * S, 0.0); e->fsal.assign(N * S, qnan);
+    e->pool.assign(S, 0.0); e->wet.assign(S, 0.0); e->L_ode.assign(S, -0.3); e->L_prof.assign(S, -0.3); e->tdeep.assign(S, qnan);
+    e->flags.assign(S, 0); e->days_done = 0; std::memset(e->counters, 0, sizeof(e->counters));
+    return 0;
+}
+
+int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    Emu* e = (Emu*)h;
+    if (day0 != e->days_done) return -2;
+    mcd::build_dev_model(e->model, mcd::g_model_h);
+    mcd::KArgs a; std::memset(&a, 0, sizeof(a));
+    a.S = e->S; a.day0 = day0; a.ndays = ndays; a.has_init_T = e->has_init_T;
+    a.has_albedo_daily = f->albedo_daily != nullptr; a.has_lw = f->longwave_radiation != nullptr; a.has_presc = f->prescribed_soil_moisture != nullptr;
+    a.z0 = e->site[0].data(); a.slope = e->site[1].data(); a.svf = e->site[2].data(); a.albedo = e->site[3].data();
+    a.bd = e->node[0].data(); a.md = e->node[1].data(); a.lam_m = e->node[2].data(); a.c_m = e->node[3].data(); a.psi_e = e->node[4].data();
+    a.ks = e->node[5].data(); a.bb = e->node[6].data(); a.rootd = e->node[7].data(); a.init_T = e->init_T.data(); a.init_theta = e->init_theta.data();
+    a.T = e->T.data(); a.theta = e->theta.data(); a.sum_phase = e->sum_phase.data(); a.pool = e->pool.data(); a.wetness = e->wet.data();
+    a.L_ode = e->L_ode.data(); a.L_prof = e->L_prof.data(); a.tdeep_prev = e->tdeep.data(); a.fsal = e->fsal.data(); a.flags = e->flags.data();
+    a.f_P = f->pressure; a.f_T = f->reference_temperature; a.f_wind = f->reference_wind_speed; a.f_rh = f->reference_humidity;
+    a.f_cloud = f->cloud_cover; a.f_solar = f->global_radiation; a.f_diffuse = f->diffuse_fraction; a.f_zen = f->zenith_angle;
+    a.f_szen = f->zenith_slope_angle; a.f_rain = f->rainfall_hourly; a.f_lw = f->longwave_radiation;
+    a.d_lai = f->leaf_area_index; a.d_shade = f->shade; a.d_eps = f->surface_emissivity; a.d_epsc = f->cloud_emissivity; a.d_wet = f->soil_wetness;
+    a.d_tdeep = f->deep_soil_temperature; a.d_rain = f->rainfall_daily; a.d_albedo = f->albedo_daily; a.presc = f->prescribed_soil_moisture;
+    a.o_T = o->soil_temperature; a.o_theta = o->soil_moisture; a.o_psi = o->soil_water_potential; a.o_h = o->soil_humidity;
+    a.o_lam = o->soil_thermal_conductivity; a.o_cp = o->soil_heat_capacity; a.o_rho = o->soil_bulk_density; a.o_pool = o->surface_water; a.o_sky = o->sky_temperature;
+    int nbad = 0;
+    for (int64_t s = 0; s < e->S; s++) {
+        mcd::Counters cn = {};
+        if (e->N <= 10) mcd::solve_site<10>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES>(a, s, cn);
+        e->counters[0] += cn.n_rhs; e->counters[1] += cn.n_accept; e->counters[2] += cn.n_reject; e->counters[3] += cn.n_obukhov;
+        e->counters[4] += cn.n_newton; e->counters[5] += cn.n_infil; e->counters[6] += cn.n_day_passes;
+        if (o->status) o->status[s] = e->flags[s];
+        if (e->flags[s]) nbad++;
+    }
+    e->days_done += ndays;
+    return nbad;
+}
+
+int he_get_counters(void* h, mc_counters* c)
+{
+    Emu* e = (Emu*)h; std::memset(c, 0, sizeof(*c));
+    c->n_rhs = e->counters[0]; c->n_accept = e->counters[1]; c->n_reject = e->counters[2]; c->n_obukhov_iter = e->counters[3];
+    c->n_newton_iter = e->counters[4]; c->n_infil_steps = e->counters[5]; c->n_day_passes = e->counters[6]; c->n_site_days = (uint64_t)(e->days_done * e->S);
+    return 0;
+}
+
+int he_get_state(void* h, mc_state_soa* st)
+{
+    Emu* e = (Emu*)h; const size_t S = e->S, N = e->N;
+    auto cp = [](double* dst, const std::vector<double>& v, size_t n) { if (dst) std::memcpy(dst, v.data(), n * sizeof(double)); };
+    cp(st->soil_temperature, e->T, N * S); cp(st->soil_moisture, e->theta, N * S); cp(st->sum_phase, e->sum_phase, N * S); cp(st->fsal, e->fsal, N * S);
+    cp(st->pool, e->pool, S); cp(st->soil_wetness, e->wet, S); cp(st->obukhov_ode, e->L_ode, S); cp(st->obukhov_profile, e->L_prof, S);
+    cp(st->deep_temperature_prev, e->tdeep, S);
+    if (st->days_done) st->days_done[0] = e->days_done;
+    return 0;
+}
+
+}
+
+/* leaf functions for white-box comparison with the oracle */
+extern "C" void he_soil_properties(const mc_model_desc* m, double P, double T, double theta, double bd, double md, double lam_m, double c_m, double* out3)
+{
+    mcd::build_dev_model(*m, mcd::g_model_h);
+    mcd::soil_properties_full(T, P, theta, bd, md, lam_m, c_m, out3[0], out3[1], out3[2]);
+}
+extern "C" double he_goff_gratch(double T) { return mcd::goff_gratch(T); }
+extern "C" double he_fastpow(double x, double y) { return mcd::fastpow(x, y); }
+
+extern "C" int he_set_state(void* h, const mc_state_soa* st)
+{
+    Emu* e = (Emu*)h; const size_t S = e->S, N = e->N;
+    auto cp = [](std::vector<double>& v, const double* src, size_t n) { if (src) std::memcpy(v.data(), src, n * sizeof(double)); };
+    cp(e->T, st->soil_temperature, N * S); cp(e->theta, st->soil_moisture, N * S); cp(e->sum_phase, st->sum_phase, N * S); cp(e->fsal, st->fsal, N * S);
+    cp(e->pool, st->pool, S); cp(e->wet, st->soil_wetness, S); cp(e->L_ode, st->obukhov_ode, S); cp(e->L_prof, st->obukhov_profile, S);
+    cp(e->tdeep, st->deep_temperature_prev, S);
+    if (st->days_done) e->days_done = st->days_done[0];
+    return 0;
+}

@@ -1,0 +1,127 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA engine, called through the C ABI
+(include/microclimate_b200.h), against the CPU oracle on the same marshalled buffers.
+
+Bar: the north-star tolerance (<= 1e-3 K, <= 1e-5 m3/m3) on EVERY entry.  Because both sides evaluate the same
+IEEE operation sequence with the shared bit-reproducible math kernel (include/mc_math.h), the observed difference is
+exactly zero and the tests additionally assert bit-identity — which is what makes parity checkable at all for a path
+this ill-conditioned (tests/test_conditioning.py).
+"""
+import numpy as np
+import pytest
+
+import configs
+import parity
+from microclimate_jl_b200 import marshal as M
+from microclimate_jl_b200 import synthetic as syn
+from oracle.oracle import OracleEngine
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def SoilEngine():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from microclimate_jl_b200.simulation import SoilEngine as E
+    return E
+
+
+def _problem_buffers(problem):
+    desc = M.model_desc(problem.model, problem.time_mode, inputs0=problem.inputs)
+    sites = M.SitesBatch.from_inputs(problem.model, [problem.inputs])
+    forcing = M.ForcingBatch.from_inputs(problem.model, [problem.inputs], problem.days)
+    return desc, sites, forcing
+
+
+@pytest.mark.parametrize("mk", [configs.config1_monthly, configs.config2_daily], ids=["config1_monthly", "config2_daily"])
+def test_reference_configs_match_oracle(SoilEngine, mk):
+    """BASELINE.json configs 1 and 2 (the reference's own CI cases): every output field, every hour."""
+    p, _ = mk()
+    desc, sites, forcing = _problem_buffers(p)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    out, eg = parity.run(SoilEngine, desc, sites, forcing)
+    parity.assert_within_north_star(out, ref)
+    parity.assert_bit_identical(out, ref)
+    co, cg = eo.counters(), eg.counters()
+    for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps", "n_day_passes"):
+        assert co[k] == cg[k], k
+    assert cg["n_kernel_launches"] == 1
+
+
+def test_reference_goldens_through_cuda(SoilEngine):
+    """The reference's own assertions (test/micro_testrun_monthly.jl:172-182, micro_testrun_daily.jl:206-209) on the CUDA output."""
+    p, g1 = configs.config1_monthly()
+    out, _ = configs.run_engine(SoilEngine, p)
+    T = out.soil_temperature[:, :, 0]
+    assert np.abs(T / g1["soil_nmr"] - 1).max() < 1e-1 and np.abs(T - g1["soil_nmr"]).max() < 1.5
+    assert np.abs(out.sky_temperature[:, 0] / g1["TSKYC"] - 1).max() < 2e-3
+    p, g2 = configs.config2_daily()
+    out, _ = configs.run_engine(SoilEngine, p)
+    ci = np.arange(0, 19, 2)
+    T, th = out.soil_temperature[:, ci, 0], out.soil_moisture[:, ci, 0]
+    assert np.abs(T[:, :3] / g2["soil_nmr"][:, :3] - 1).max() < 1e-1
+    assert np.sqrt(((th - g2["soilmoist_nmr"]) ** 2).mean()) < 0.03
+    assert np.all(out.soil_moisture[1:, 18, 0] == 1.0 - 1.3 / 2.56)
+
+
+@pytest.fixture(scope="module")
+def synth():
+    S, nd = 512, 3
+    model = syn.synthetic_model()
+    desc = M.model_desc(model, syn.synthetic_time_mode())
+    return desc, syn.make_sites(0, S, S, with_sand=True), syn.make_forcing(0, S, S, 0, nd)
+
+
+def test_synthetic_grid_matches_oracle(SoilEngine, synth):
+    """512 synthetic sites (all texture classes incl. the non-converging dry-sand regime) x 3 days."""
+    desc, sites, forcing = synth
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing)
+    out, _ = parity.run(SoilEngine, desc, sites, forcing)
+    parity.assert_within_north_star(out, ref)
+    parity.assert_bit_identical(out, ref)
+
+
+def test_time_chunking_and_site_sharding_are_invariant(SoilEngine, synth):
+    desc, sites, forcing = synth
+    whole, _ = parity.run(SoilEngine, desc, sites, forcing, fields=("soil_temperature", "soil_moisture", "surface_water"))
+    chunked, _ = parity.run(SoilEngine, desc, sites, forcing, fields=("soil_temperature", "soil_moisture", "surface_water"), chunks=[1, 2])
+    parity.assert_bit_identical(chunked, whole, ("soil_temperature", "soil_moisture", "surface_water"))
+    lo, hi = 100, 357          # a ragged shard: not a multiple of the block or warp size
+    part, _ = parity.run(SoilEngine, desc, sites.slice(lo, hi), forcing.site_slice(lo, hi), fields=("soil_temperature", "soil_moisture"))
+    assert np.array_equal(part.soil_temperature, whole.soil_temperature[:, :, lo:hi])
+    assert np.array_equal(part.soil_moisture, whole.soil_moisture[:, :, lo:hi])
+
+
+def test_state_checkpoint_roundtrip(SoilEngine, synth):
+    desc, sites, forcing = synth
+    f = ("soil_temperature", "soil_moisture")
+    a = SoilEngine(desc, sites.S); a.set_sites(sites)
+    o1 = M.OutputBatch(1, desc.n_soil, sites.S, f); a.step_days(0, forcing.day_slice(0, 1), o1)
+    st = a.get_state()
+    assert st.days_done[0] == 1
+    b = SoilEngine(desc, sites.S); b.set_sites(sites); b.set_state(st)
+    oa = M.OutputBatch(1, desc.n_soil, sites.S, f); ob = M.OutputBatch(1, desc.n_soil, sites.S, f)
+    a.step_days(1, forcing.day_slice(1, 2), oa); b.step_days(1, forcing.day_slice(1, 2), ob)
+    parity.assert_bit_identical(oa, ob, f)
+
+
+def test_error_behaviour(SoilEngine, synth):
+    desc, sites, forcing = synth
+    e = SoilEngine(desc, sites.S)
+    out = M.OutputBatch(1, desc.n_soil, sites.S, ("soil_temperature",))
+    with pytest.raises(RuntimeError, match="mc_set_sites"):
+        e.step_days(0, forcing.day_slice(0, 1), out)
+    e.set_sites(sites)
+    with pytest.raises(RuntimeError, match="day0"):
+        e.step_days(3, forcing.day_slice(0, 1), out)
+    import copy
+    bad = copy.copy(desc); bad.n_soil = 2
+    with pytest.raises(RuntimeError, match="n_soil"):
+        SoilEngine(bad, 4)
+
+
+def test_fp64_peak_is_measured(SoilEngine, synth):
+    desc, sites, _ = synth
+    e = SoilEngine(desc, sites.S)
+    tf = e.measure_fp64_peak()
+    assert 10.0 < tf < 60.0     # B200: 148 SM x 64 FP64 lanes x 2 x ~1.9 GHz ~ 36-37 TFLOP/s

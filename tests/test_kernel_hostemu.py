@@ -1,0 +1,107 @@
+"""CPU tier: the product's per-site kernel body (microclimate.jl_b200/csrc/mc_device.cuh), compiled for the host by the
+tests/hostemu harness, against the oracle.  This is what lets the no-GPU tier check the code the CUDA kernel executes;
+the GPU tier (test_gpu_parity.py) repeats the same comparisons on the device through the C ABI."""
+import copy
+
+import numpy as np
+import pytest
+
+import configs
+import parity
+import microclimate_jl_b200 as mc
+from hostemu_engine import HostEmuEngine
+from microclimate_jl_b200 import marshal as M
+from microclimate_jl_b200 import synthetic as syn
+from oracle.oracle import OracleEngine
+
+
+def _buffers(problem):
+    desc = M.model_desc(problem.model, problem.time_mode, inputs0=problem.inputs)
+    return desc, M.SitesBatch.from_inputs(problem.model, [problem.inputs]), M.ForcingBatch.from_inputs(problem.model, [problem.inputs], problem.days)
+
+
+@pytest.mark.parametrize("mk", [configs.config1_monthly, configs.config2_daily], ids=["config1_monthly", "config2_daily"])
+def test_reference_configs_bit_identical(mk):
+    p, _ = mk()
+    desc, sites, forcing = _buffers(p)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    out, ee = parity.run(HostEmuEngine, desc, sites, forcing)
+    parity.assert_within_north_star(out, ref)
+    parity.assert_bit_identical(out, ref)
+    co, ce = eo.counters(), ee.counters()
+    assert all(co[k] == ce[k] for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps", "n_day_passes"))
+
+
+@pytest.fixture(scope="module")
+def synth():
+    S, nd = 48, 3
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    return desc, syn.make_sites(0, S, S, with_sand=True), syn.make_forcing(0, S, S, 0, nd)
+
+
+def test_synthetic_with_sand_bit_identical(synth):
+    desc, sites, forcing = synth
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing)
+    out, _ = parity.run(HostEmuEngine, desc, sites, forcing)
+    parity.assert_bit_identical(out, ref)
+    assert np.all((out.soil_moisture >= 0) & (out.soil_moisture <= 1)) and np.all(np.isfinite(out.soil_temperature))
+
+
+def test_chunking_and_sharding_invariance(synth):
+    desc, sites, forcing = synth
+    f = ("soil_temperature", "soil_moisture", "surface_water", "soil_water_potential")
+    whole, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+    chunked, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f, chunks=[2, 1])
+    parity.assert_bit_identical(chunked, whole, f)
+    ref_chunked, _ = parity.run(OracleEngine, desc, sites, forcing, fields=f, chunks=[2, 1])
+    parity.assert_bit_identical(chunked, ref_chunked, f)
+    part, _ = parity.run(HostEmuEngine, desc, sites.slice(7, 29), forcing.site_slice(7, 29), fields=f)
+    assert np.array_equal(part.soil_temperature, whole.soil_temperature[:, :, 7:29])
+    assert np.array_equal(part.soil_moisture, whole.soil_moisture[:, :, 7:29])
+
+
+def _variant(problem, **cfg):
+    p = copy.deepcopy(problem)
+    for k, v in cfg.items():
+        if k == "time_mode":
+            p.time_mode = v
+        elif k == "hydraulics":
+            p.model.soil_hydraulic_model = v
+        else:
+            setattr(p.model.config, k, v)
+    return p
+
+
+def test_strategy_variants_bit_identical():
+    """Every strategy object on the path: tolerance convergence, spin-up first day, flux-potential infiltration, Swinbank."""
+    p1, _ = configs.config1_monthly()
+    p2, _ = configs.config2_daily(4)
+    variants = [
+        _variant(p1, convergence=mc.SoilTemperatureConvergenceTolerance(tolerance=0.5, max_iterations_per_day=6),
+                 time_mode=mc.NonConsecutiveDayMode(iterations_per_day=6)),
+        _variant(p2, time_mode=mc.ConsecutiveDayMode(spinup_first_day=True), convergence=mc.FixedSoilTemperatureIterations(3)),
+        _variant(p2, hydraulics=mc.CampbellSoilHydraulics(infiltration_algorithm=mc.MatricFluxPotentialAlgorithm())),
+    ]
+    p_sw = copy.deepcopy(p1)
+    p_sw.model.radiation = mc.RadiationModel(longwave_model=mc.ViewFactorLongwave(atmospheric_radiation_model=mc.SwinbankAtmosphericRadiation()))
+    variants.append(p_sw)
+    for p in variants:
+        desc, sites, forcing = _buffers(p)
+        ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+        out, ee = parity.run(HostEmuEngine, desc, sites, forcing)
+        parity.assert_bit_identical(out, ref)
+        assert eo.counters()["n_day_passes"] == ee.counters()["n_day_passes"]
+
+
+def test_sloped_site_bit_identical():
+    p, _ = configs.config1_monthly()
+    p = copy.deepcopy(p)
+    p.inputs.site.slope = 20.0
+    p.inputs.site.sky_view_fraction = 0.8
+    h = p.inputs.environment_hourly
+    h.diffuse_fraction = np.full(len(h.zenith_angle), 0.3)
+    h.zenith_slope_angle = np.minimum(np.asarray(h.zenith_angle) + 10.0, 90.0)
+    desc, sites, forcing = _buffers(p)
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing)
+    out, _ = parity.run(HostEmuEngine, desc, sites, forcing)
+    parity.assert_bit_identical(out, ref)
