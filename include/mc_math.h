@@ -25,8 +25,12 @@
 
 #if defined(__CUDACC__)
 #define MCM_FN __host__ __device__ __forceinline__
+/* the big kernels (exp, log, atan) are real functions on the device: ONE copy each in the instruction cache instead of
+ * one per call site (the soil right-hand side alone has ~20 call sites) */
+#define MCM_HEAVY __host__ __device__ __noinline__
 #else
 #define MCM_FN static inline
+#define MCM_HEAVY static inline
 #endif
 
 namespace mcm {
@@ -45,7 +49,7 @@ MCM_FN uint32_t lo_word(double x) { return (uint32_t)(d2u(x) & 0xffffffffu); }
 MCM_FN double with_hi(double x, int32_t hi) { return u2d(((uint64_t)(uint32_t)hi << 32) | (d2u(x) & 0xffffffffu)); }
 
 /* ---- exp ---------------------------------------------------------------------------------- */
-MCM_FN double exp(double x)
+MCM_HEAVY double exp(double x)
 {
     const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
     const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
@@ -76,7 +80,7 @@ MCM_FN double exp(double x)
 }
 
 /* ---- log ---------------------------------------------------------------------------------- */
-MCM_FN double log(double x)
+MCM_HEAVY double log(double x)
 {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
@@ -150,7 +154,7 @@ MCM_FN double pow(double x, double y)
 }
 
 /* ---- atan ---------------------------------------------------------------------------------- */
-MCM_FN double atan(double x)
+MCM_HEAVY double atan(double x)
 {
     const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01, aT2 = 1.42857142725034663711e-01,
                  aT3 = -1.11111104054623557880e-01, aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,

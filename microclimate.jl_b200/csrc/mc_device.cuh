@@ -109,7 +109,7 @@ MC_DEV double jclamp(double x, double lo, double hi) { return x > hi ? hi : (x <
  * FluidProperties.jl psychrometrics (un-vendored; constants are data, see mc_fluid_constants)
  * ------------------------------------------------------------------------------------------ */
 /* vapour_pressure(GoffGratch(), T) [Pa] */
-MC_DEV double goff_gratch(double T)
+MC_DEV_NOINLINE double goff_gratch(double T)
 {
     const double Tp = T + 0.01;
     double loge;
@@ -153,7 +153,7 @@ MC_DEV double atmospheric_radiation(double e_Pa, double T_air)
 }
 
 /* precompute_longwave_sky -> sky temperature (view_factor.jl:23-67) */
-MC_DEV double sky_temperature(double svf, double /*P*/, double rh, double T_ref, double eps_cloud, double cloud, double shade,
+MC_DEV_NOINLINE double sky_temperature(double svf, double /*P*/, double rh, double T_ref, double eps_cloud, double cloud, double shade,
                               bool has_lw, double supplied_lw)
 {
     const DevModel& m = MC_CONST_MODEL;
@@ -182,7 +182,7 @@ MC_DEV double calc_psi_h(double x) { return 2.0 * mcm::log((1.0 + x * x) / 2.0);
 struct Obukhov { double L, Sts, Stb, ustar, psi_h, Q; int iters; };
 
 /* calc_Obukhov_length fixed point (monin_obukhov.jl:527-577): <=30 iterations, 1 % relative change */
-MC_DEV Obukhov calc_obukhov(double v_ref, double z0, double z, double lz, double dT, double rho_cp, double L0)
+MC_DEV_NOINLINE Obukhov calc_obukhov(double v_ref, double z0, double z, double lz, double dT, double rho_cp, double L0)
 {
     const DevModel& m = MC_CONST_MODEL;
     Obukhov o; o.L = L0; o.Q = 0.0; o.Stb = 0.0; o.Sts = 0.0; o.psi_h = 0.0; o.ustar = 0.0;
@@ -235,7 +235,7 @@ MC_DEV double devries_weight(double lam_c, double lam_f, double ga, double gc)
     const double r1 = lam_c / lam_f - 1.0;
     return 2.0 / (3.0 * (1.0 + ga * r1)) + 1.0 / (3.0 * (1.0 + gc * r1));
 }
-MC_DEV double soil_conductivity(double T, double P, double theta, double phim, double phig, double fw, double lam_m)
+MC_DEV_NOINLINE double soil_conductivity(double T, double P, double theta, double phim, double phig, double fw, double lam_m)
 {
     const DevModel& m = MC_CONST_MODEL;
     const double Tc = T - T0C;
@@ -507,7 +507,7 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
 /* ------------------------------------------------------------------------------------------
  * phase_transition!(::PhaseTransitionLatentHeat), latent_heat.jl:21-112 (sequential over nodes)
  * ------------------------------------------------------------------------------------------ */
-MC_DEV void phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
+MC_DEV_NOINLINE void phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
 {
     const double tol = 1.0e-4;
     for (int i = 0; i < N; i++) {
@@ -809,6 +809,50 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     return jclamp(jmax(0.0, io.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
 }
 
+
+/* theta-only soil property terms for the coming ODE hour (theta is constant while the ODE advances) */
+template <int NA>
+MC_DEV_NOINLINE void hoist_soil(const SiteRef& r, const double* theta, HourSoil<NA>& hs)
+{
+    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
+    for (int i = 0; i < m.N; i++) {
+        const double bd = r.node(a.bd, i), md = r.node(a.md, i);
+        const double th = theta[i];
+        const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
+        const double rho = th * WATER_RHO + bd;
+        hs.cap[i] = (rho * cp) * m.dzc[i] / 2.0;
+        hs.theta[i] = th; hs.phim[i] = bd / md; hs.phig[i] = jmax(0.0, 1.0 - th - bd / md);
+        hs.fw[i] = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
+    }
+}
+MC_DEV_NOINLINE void put_potential_row(const SiteRef& r, int row, const double* theta)
+{
+    const KArgs& a = *r.a;
+    if (!a.o_psi) return;
+    for (int i = 0; i < MC_CONST_MODEL.N; i++)
+        r.put_node(a.o_psi, row, i, r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i)));
+}
+/* initialise_soil_humidity!, dynamic.jl:32-35: always row 1 of the buffer */
+MC_DEV_NOINLINE void init_humidity(const SiteRef& r, const double* theta, const double* Tn)
+{
+    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
+    if (!m.dynamic || !a.o_h) return;
+    for (int i = 0; i < m.N; i++) {
+        const double psi = r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i));
+        r.put_node(a.o_h, 0, i, jclamp(mcm::exp(MW_INFIL * psi / (m.R * Tn[i])), 0.0, 1.0));
+    }
+}
+MC_DEV_NOINLINE void write_props(const SiteRef& r, int row, const double* Tn, const double* theta, double P)
+{
+    const KArgs& a = *r.a;
+    if (!a.o_lam && !a.o_cp && !a.o_rho) return;
+    for (int i = 0; i < MC_CONST_MODEL.N; i++) {
+        double lam, cp, rho;
+        soil_properties_full(Tn[i], P, theta[i], r.node(a.bd, i), r.node(a.md, i), r.node(a.lam_m, i), r.node(a.c_m, i), lam, cp, rho);
+        r.put_node(a.o_lam, row, i, lam); r.put_node(a.o_cp, row, i, cp); r.put_node(a.o_rho, row, i, rho);
+    }
+}
+
 MC_DEV bool is_converged(int iter, int niter, const double* T0, const double* T0_prev, int N)
 {
     const DevModel& m = MC_CONST_MODEL;
@@ -848,37 +892,7 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
         hp.fP = a.f_P + off; hp.fT = a.f_T + off; hp.fwind = a.f_wind + off; hp.frh = a.f_rh + off; hp.fcloud = a.f_cloud + off;
         hp.fsolar = a.f_solar + off; hp.fdiff = a.f_diffuse + off; hp.fzen = a.f_zen + off; hp.fszen = a.f_szen + off;
     };
-    auto hoist_soil = [&]() {      /* theta-only soil property terms for the coming ODE hour */
-        for (int i = 0; i < N; i++) {
-            const double bd = r.node(a.bd, i), md = r.node(a.md, i);
-            const double th = theta[i];
-            const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
-            const double rho = th * WATER_RHO + bd;
-            hs.cap[i] = (rho * cp) * m.dzc[i] / 2.0;
-            hs.theta[i] = th; hs.phim[i] = bd / md; hs.phig[i] = jmax(0.0, 1.0 - th - bd / md);
-            hs.fw[i] = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
-        }
-    };
     auto tins_mean = [&](int jl) { double ssum = 0.0; for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
-    auto put_potential_row = [&](int row) {
-        if (!a.o_psi) return;
-        for (int i = 0; i < N; i++) r.put_node(a.o_psi, row, i, r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i)));
-    };
-    auto init_humidity = [&](const double* Tn) {      /* initialise_soil_humidity!, dynamic.jl:32-35: always row 1 of the buffer */
-        if (!dynamic || !a.o_h) return;
-        for (int i = 0; i < N; i++) {
-            const double psi = r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i));
-            r.put_node(a.o_h, 0, i, jclamp(mcm::exp(MW_INFIL * psi / (m.R * Tn[i])), 0.0, 1.0));
-        }
-    };
-    auto write_props = [&](int row, const double* Tn, double P) {
-        if (!a.o_lam && !a.o_cp && !a.o_rho) return;
-        for (int i = 0; i < N; i++) {
-            double lam, cp, rho;
-            soil_properties_full(Tn[i], P, theta[i], r.node(a.bd, i), r.node(a.md, i), hs.lam_m[i], r.node(a.c_m, i), lam, cp, rho);
-            r.put_node(a.o_lam, row, i, lam); r.put_node(a.o_cp, row, i, cp); r.put_node(a.o_rho, row, i, rho);
-        }
-    };
     double sky_T = 0.0;
     auto set_hour_params = [&](const EnvInstant& e) {
         hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud; hp.albedo = e.albedo;
@@ -892,17 +906,17 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
         set_day_forcing(0);
         env = get_instant(r, 0, 0, site_albedo);
         for (int i = 0; i < N; i++) I.tmp[i] = a.has_init_T ? T0[i] : 280.0;
-        hoist_soil();
+        hoist_soil<NA>(r, theta, hs);
         hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
         Counters scratch = {};
         soil_rhs<NA>(hs, hp, I.tmp, 0.0, I.k1, scratch);
         /* solve_soil! pre-loop (simulation.jl:395-452) */
         if (!a.has_init_T) { const double t_init = tins_mean(0); for (int i = 0; i < N; i++) T0[i] = t_init; }
         for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-        write_props(0, T0, 101325.0);
-        put_potential_row(0);
+        write_props(r, 0, T0, theta, 101325.0);
+        put_potential_row(r, 0, theta);
         for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
-        init_humidity(T0);
+        init_humidity(r, theta, T0);
         tdeep_stale = env.T_deep;
         pool = 0.0;
     }
@@ -934,17 +948,17 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
             if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
                 for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
                 r.put_scalar(a.o_pool, day_row, pool);
-                put_potential_row(day_row);
-                init_humidity(T0);
+                put_potential_row(r, day_row, theta);
+                init_humidity(r, theta, T0);
                 const EnvInstant e0 = get_instant(r, jl, day_row, site_albedo);
                 r.put_scalar(a.o_sky, day_row, sky_temperature(hp.svf, e0.P, e0.rh, e0.T_ref, e0.eps_cloud, e0.cloud, e0.shade, a.has_lw != 0, e0.lw));
-                write_props(day_row, T0, e0.P);
+                write_props(r, day_row, T0, theta, e0.P);
             }
             env = get_instant(r, jl, day_row, site_albedo);
             T0[N - 1] = env.T_deep;
             set_hour_params(env);
             hp.L_prev = L_ode;
-            hoist_soil();
+            hoist_soil<NA>(r, theta, hs);
             /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
             for (int i = 0; i < N; i++) { I.u[i] = T0[i]; I.uprev[i] = T0[i]; }
             I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
@@ -952,7 +966,7 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
             for (int i = 0; i < 24; i++) {
                 const int step = jl * 24 + i;
                 for (int k = 0; k < N; k++) T0_before[k] = T0[k];
-                if (i > 0) hoist_soil();
+                if (i > 0) hoist_soil<NA>(r, theta, hs);
                 hp.L_prev = L_ode;
                 /* step_to_hour! (simulation.jl:888-903) */
                 const double target = (i + 1) * 60.0;
@@ -1003,7 +1017,7 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
                     for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
                     r.put_scalar(a.o_sky, out_row, sky_T);
                     if (have_infil) for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); }
-                    write_props(out_row, T0, r.hourly(a.f_P, out_row));
+                    write_props(r, out_row, T0, theta, r.hourly(a.f_P, out_row));
                 }
             }
         }

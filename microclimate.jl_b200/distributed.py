@@ -1,0 +1,70 @@
+"""Multi-GPU orchestration: one process per GPU, sites sharded contiguously, NO data-path collective.
+
+Sites are independent (reference: one MicroCache per site, `reinit!` per inputs, src/simulation.jl:266-277), so rank r
+integrates sites [lo_r, hi_r) on its own GPU and the only communication is a host-side gather of the selected output
+rows to rank 0 (gloo, CPU tensors) after the integration.  Results are independent of the number of ranks.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _abi as A
+from . import marshal as M
+from .simulation import site_shards
+
+
+def run_shard(engine_factory: Callable, desc, sites: M.SitesBatch, forcing: M.ForcingBatch, rank: int, world: int,
+              fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS, chunk_days: Optional[int] = None):
+    """Integrate this rank's contiguous shard of a batch that every rank can see (or regenerate)."""
+    lo, hi = site_shards(sites.S, world)[rank]
+    out = M.OutputBatch(forcing.ndays, desc.n_soil, hi - lo, fields, desc.n_snow)
+    if hi == lo:
+        return out, (lo, hi)
+    eng = engine_factory(desc, hi - lo)
+    eng.set_sites(sites.slice(lo, hi))
+    f = forcing.site_slice(lo, hi)
+    if not chunk_days:
+        eng.step_days(0, f, out)
+    else:
+        d0 = 0
+        while d0 < forcing.ndays:
+            d1 = min(forcing.ndays, d0 + chunk_days)
+            part = M.OutputBatch(d1 - d0, desc.n_soil, hi - lo, fields, desc.n_snow)
+            eng.step_days(d0, f.day_slice(d0, d1), part)
+            out.assign_rows(24 * d0, part)
+            d0 = d1
+    return out, (lo, hi)
+
+
+def gather_outputs(local: M.OutputBatch, n_sites_total: int, group=None, dst: int = 0) -> Optional[M.OutputBatch]:
+    """Host gather of per-rank output shards into one OutputBatch on `dst` (None elsewhere).  `group` must be a
+    CPU-capable (gloo) process group; with an nccl default group create one with `dist.new_group(backend="gloo")`."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    shards = site_shards(n_sites_total, world)
+    width = max(hi - lo for lo, hi in shards)
+    fields = [f for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS if getattr(local, f) is not None]
+    full = M.OutputBatch(local.ndays, local.N, n_sites_total, fields) if rank == dst else None
+
+    def padded(a):
+        t = torch.zeros(a.shape[:-1] + (width,), dtype=torch.float64)
+        t[..., :a.shape[-1]] = torch.from_numpy(np.ascontiguousarray(a))
+        return t
+    for f in fields:
+        t = padded(getattr(local, f))
+        bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, bufs, dst=dst, group=group)
+        if rank == dst:
+            for (lo, hi), b in zip(shards, bufs):
+                getattr(full, f)[..., lo:hi] = b[..., :hi - lo].numpy()
+    st = torch.zeros(width, dtype=torch.int32)
+    st[:local.S] = torch.from_numpy(local.status)
+    bufs = [torch.empty_like(st) for _ in range(world)] if rank == dst else None
+    dist.gather(st, bufs, dst=dst, group=group)
+    if rank == dst:
+        for (lo, hi), b in zip(shards, bufs):
+            full.status[lo:hi] = b[:hi - lo].numpy()
+    return full

@@ -1,0 +1,60 @@
+"""N>1 host path on CPU: world_size-2 gloo, contiguous site shards, no data-path collective, host gather to rank 0.
+The per-rank engine here is the host-emulated kernel body (tests/hostemu) because this tier has no GPU; the orchestration
+code under test (microclimate.jl_b200/distributed.py) is exactly what runs one-process-per-GPU with SoilEngine."""
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, S, nd, path):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    from hostemu_engine import HostEmuEngine
+    from microclimate_jl_b200 import distributed as D, marshal as M, synthetic as syn
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    sites, forcing = syn.make_sites(0, S, S), syn.make_forcing(0, S, S, 0, nd, threads=1)
+    f = ("soil_temperature", "soil_moisture", "surface_water")
+    local, (lo, hi) = D.run_shard(HostEmuEngine, desc, sites, forcing, rank, world, fields=f, chunk_days=1)
+    full = D.gather_outputs(local, S)
+    if rank == 0:
+        np.savez(path, T=full.soil_temperature, th=full.soil_moisture, pool=full.surface_water, status=full.status)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_run_equals_single_process():
+    from hostemu_engine import HostEmuEngine
+    import parity
+    from microclimate_jl_b200 import marshal as M, synthetic as syn
+    from microclimate_jl_b200.simulation import site_shards
+    S, nd = 13, 2          # ragged: 7 + 6 sites
+    assert site_shards(S, 2) == [(0, 7), (7, 13)] and site_shards(5, 8)[-1] == (5, 5)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.npz")
+        mp.spawn(_worker, args=(2, _free_port(), S, nd, path), nprocs=2, join=True)
+        got = np.load(path)
+        desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+        ref, _ = parity.run(HostEmuEngine, desc, syn.make_sites(0, S, S), syn.make_forcing(0, S, S, 0, nd, threads=1),
+                            fields=("soil_temperature", "soil_moisture", "surface_water"))
+        assert np.array_equal(got["T"], ref.soil_temperature)
+        assert np.array_equal(got["th"], ref.soil_moisture)
+        assert np.array_equal(got["pool"], ref.surface_water)
+        assert np.array_equal(got["status"], ref.status)
