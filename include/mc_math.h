@@ -48,8 +48,36 @@ MCM_FN int32_t hi_word(double x) { return (int32_t)(d2u(x) >> 32); }
 MCM_FN uint32_t lo_word(double x) { return (uint32_t)(d2u(x) & 0xffffffffu); }
 MCM_FN double with_hi(double x, int32_t hi) { return u2d(((uint64_t)(uint32_t)hi << 32) | (d2u(x) & 0xffffffffu)); }
 
+/* coefficient table: on the device it lives in constant memory so DFMA reads c[bank][offset] operands directly
+ * instead of materialising 64-bit immediates (two UMOVs per constant per use) */
+#if defined(__CUDA_ARCH__)
+#define MCM_TAB mcm_tab_c
+#else
+#define MCM_TAB mcm_tab_h
+#endif
+#define MCM_TAB_INIT { \
+    /* 0..11: 1/n!, n = 2..13 */ \
+    0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03, 1.3888888888888889e-03, 1.9841269841269841e-04, \
+    2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07, 2.5052108385441720e-08, 2.0876756987868100e-09, 1.6059043836821613e-10, \
+    /* 12..14: ln2_hi, ln2_lo, 1/ln2 */ \
+    6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00, \
+    /* 15..21: Lg1..Lg7 */ \
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01, \
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01 }
+#if defined(__CUDACC__)
+__constant__ double mcm_tab_c[22] = MCM_TAB_INIT;
+#endif
+static const double mcm_tab_h[22] = MCM_TAB_INIT;
+
+#if defined(__CUDA_ARCH__)
+MCM_FN double rne(double x) { return rint(x); }
+#else
+MCM_FN double rne(double x) { return __builtin_nearbyint(x); }
+#endif
+
 /* ---- exp ---------------------------------------------------------------------------------- */
-MCM_HEAVY double exp(double x)
+/* rare arguments (|x| >= 690, NaN): the classic fdlibm e_exp.c evaluation incl. overflow / gradual underflow */
+MCM_HEAVY double exp_slow(double x)
 {
     const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
     const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
@@ -57,21 +85,13 @@ MCM_HEAVY double exp(double x)
     if (x != x) return x;
     if (x > 7.09782712893383973096e+02) return u2d(0x7ff0000000000000ULL);
     if (x < -7.45133219101941108420e+02) return 0.0;
-    double hi = 0.0, lo = 0.0; int k = 0;
-    const double ax = x < 0.0 ? -x : x;
-    if (ax > 0.34657359027997264) {                 /* |x| > 0.5 ln2 */
-        k = (int)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
-        hi = x - (double)k * ln2HI;
-        lo = (double)k * ln2LO;
-        x = hi - lo;
-    } else if (ax < 3.725290298461914e-09) {        /* |x| < 2^-28 */
-        return 1.0 + x;
-    }
+    const int k = (int)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+    const double hi = x - (double)k * ln2HI;
+    const double lo = (double)k * ln2LO;
+    x = hi - lo;
     const double t = x * x;
     const double c = x - t * ffma(t, ffma(t, ffma(t, ffma(t, P5, P4), P3), P2), P1);
-    double y;
-    if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
-    y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+    const double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
     if (k >= -1021) {
         if (k == 1024) return y * 2.0 * 8.98846567431158e307;   /* 2^1023 */
         return u2d(d2u(y) + ((uint64_t)(int64_t)k << 52));
@@ -79,50 +99,81 @@ MCM_HEAVY double exp(double x)
     return u2d(d2u(y) + ((uint64_t)(int64_t)(k + 1000) << 52)) * 9.33263618503218878990e-302;   /* 2^-1000 */
 }
 
-/* ---- log ---------------------------------------------------------------------------------- */
-MCM_HEAVY double log(double x)
+/* exp(x) = 2^k * exp(r), r = x - k ln2, |r| <= 0.347: degree-13 Taylor polynomial evaluated Estrin-style (division-free,
+ * branch-free, short dependency chain); truncation 4e-18, total error < 1 ulp */
+MCM_FN bool exp_fast_ok(double x) { return fabs(x) < 690.0; }
+MCM_FN double exp_core(double x)
 {
-    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
-                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-                 Lg7 = 1.479819860511658591e-01;
-    int32_t hx = hi_word(x); const uint32_t lx = lo_word(x);
-    int k = 0;
-    if (hx < 0x00100000) {                          /* x < 2^-1022 */
-        if (((hx & 0x7fffffff) | lx) == 0) return -u2d(0x7ff0000000000000ULL);   /* log(+-0) = -inf */
-        if (hx < 0) return u2d(0x7ff8000000000000ULL);                            /* log(-#) = NaN */
-        k -= 54; x *= 1.80143985094819840000e+16; hx = hi_word(x);                /* subnormal: scale by 2^54 */
-    }
-    if (hx >= 0x7ff00000) return x + x;
-    k += (hx >> 20) - 1023;
+    const double kd = rne(x * MCM_TAB[14]);
+    const double hi = x - kd * MCM_TAB[12];          /* exact: ln2_hi has 21 trailing zero bits, |k| < 2^10 */
+    const double lo = kd * MCM_TAB[13];
+    const double r = hi - lo;
+    const double r2 = r * r;
+    const double r4 = r2 * r2;
+    const double q01 = ffma(r, MCM_TAB[1], MCM_TAB[0]);
+    const double q23 = ffma(r, MCM_TAB[3], MCM_TAB[2]);
+    const double q45 = ffma(r, MCM_TAB[5], MCM_TAB[4]);
+    const double q67 = ffma(r, MCM_TAB[7], MCM_TAB[6]);
+    const double q89 = ffma(r, MCM_TAB[9], MCM_TAB[8]);
+    const double qab = ffma(r, MCM_TAB[11], MCM_TAB[10]);
+    const double a = ffma(r2, q23, q01);
+    const double b = ffma(r2, q67, q45);
+    const double c = ffma(r2, qab, q89);
+    const double q = ffma(r4, ffma(r4, c, b), a);
+    const double y = 1.0 + ffma(r2, q, r);
+    return u2d(d2u(y) + ((uint64_t)(int64_t)kd << 52));
+}
+MCM_HEAVY double exp(double x)
+{
+    if (!exp_fast_ok(x)) return exp_slow(x);
+    return exp_core(x);
+}
+
+/* ---- log ---------------------------------------------------------------------------------- */
+/* rare arguments (zero, negative, subnormal, inf, NaN) */
+MCM_HEAVY double log_slow(double x)
+{
+    if (x != x) return x + x;
+    if (x == 0.0) return -u2d(0x7ff0000000000000ULL);
+    if (x < 0.0) return u2d(0x7ff8000000000000ULL);
+    if (x == u2d(0x7ff0000000000000ULL)) return x;
+    /* positive subnormal: scale by 2^54 and correct */
+    const double xs = x * 1.80143985094819840000e+16;
+    int32_t hx = hi_word(xs);
+    int k = (hx >> 20) - 1023 - 54;
     hx &= 0x000fffff;
     const int32_t i0 = (hx + 0x95f64) & 0x100000;
-    x = with_hi(x, hx | (i0 ^ 0x3ff00000));         /* normalise x or x/2 */
+    const double m = with_hi(xs, hx | (i0 ^ 0x3ff00000));
     k += (i0 >> 20);
-    const double f = x - 1.0;
-    const double dk = (double)k;
-    if ((0x000fffff & (2 + hx)) < 3) {              /* |f| < 2^-20 */
-        if (f == 0.0) { if (k == 0) return 0.0; return dk * ln2_hi + dk * ln2_lo; }
-        const double R = f * f * (0.5 - 0.33333333333333333 * f);
-        if (k == 0) return f - R;
-        return dk * ln2_hi - ((R - dk * ln2_lo) - f);
-    }
-    const double s = f / (2.0 + f);
-    const double z = s * s;
-    int32_t i = hx - 0x6147a;
-    const double w = z * z;
-    const int32_t j = 0x6b851 - hx;
-    const double t1 = w * ffma(w, ffma(w, Lg6, Lg4), Lg2);
-    const double t2 = z * ffma(w, ffma(w, ffma(w, Lg7, Lg5), Lg3), Lg1);
-    i |= j;
-    const double R = t2 + t1;
-    if (i > 0) {
-        const double hfsq = 0.5 * f * f;
-        if (k == 0) return f - (hfsq - s * (hfsq + R));
-        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
-    }
-    if (k == 0) return f - s * (f - R);
-    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+    const double f = m - 1.0, dk = (double)k;
+    const double s = f / (2.0 + f), z = s * s, w = z * z;
+    const double t1 = w * ffma(w, ffma(w, MCM_TAB[20], MCM_TAB[18]), MCM_TAB[16]);
+    const double t2 = z * ffma(w, ffma(w, ffma(w, MCM_TAB[21], MCM_TAB[19]), MCM_TAB[17]), MCM_TAB[15]);
+    const double R = t2 + t1, hfsq = 0.5 * f * f;
+    return dk * MCM_TAB[12] - ((hfsq - (s * (hfsq + R) + dk * MCM_TAB[13])) - f);
+}
+
+/* fdlibm e_log.c kernel (the always-hfsq form of the later k_log.h), branch-free for normal positive x */
+MCM_FN bool log_fast_ok(double x) { return x >= 2.2250738585072014e-308 && x < u2d(0x7ff0000000000000ULL); }
+MCM_FN double log_core(double x)
+{
+    int32_t hx = hi_word(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int32_t i0 = (hx + 0x95f64) & 0x100000;
+    const double m = with_hi(x, hx | (i0 ^ 0x3ff00000));      /* m in [sqrt(2)/2, sqrt(2)) */
+    k += (i0 >> 20);
+    const double f = m - 1.0, dk = (double)k;
+    const double s = f / (2.0 + f), z = s * s, w = z * z;
+    const double t1 = w * ffma(w, ffma(w, MCM_TAB[20], MCM_TAB[18]), MCM_TAB[16]);
+    const double t2 = z * ffma(w, ffma(w, ffma(w, MCM_TAB[21], MCM_TAB[19]), MCM_TAB[17]), MCM_TAB[15]);
+    const double R = t2 + t1, hfsq = 0.5 * f * f;
+    return dk * MCM_TAB[12] - ((hfsq - (s * (hfsq + R) + dk * MCM_TAB[13])) - f);
+}
+MCM_HEAVY double log(double x)
+{
+    if (!log_fast_ok(x)) return log_slow(x);
+    return log_core(x);
 }
 
 MCM_FN double log10(double x) { return log(x) * 4.34294481903251816668e-01; }
@@ -136,6 +187,10 @@ MCM_FN double exp_prod(double a, double b, double b_lo)
     return ffma(r, e, r);
 }
 MCM_FN double exp10(double x) { return exp_prod(x, 2.302585092994046, -2.1707562233822494e-16); }
+/* the pieces of exp10 for callers that evaluate several independent arguments side by side (instruction-level parallelism):
+ * exp10(x) == exp10_finish(exp(exp10_arg(x)), x, exp10_arg(x)) with exactly the operations of exp10 above */
+MCM_FN double exp10_arg(double x) { return x * 2.302585092994046; }
+MCM_FN double exp10_finish(double r, double x, double p) { const double e = ffma(x, 2.302585092994046, -p) + x * -2.1707562233822494e-16; return ffma(r, e, r); }
 MCM_FN double exp2(double x) { return exp_prod(x, 0.6931471805599453, 2.3190468138462996e-17); }
 
 /* pow for the cases the soil path uses: x > 0 (any y), x == 0, and x < 0 with integer-valued y */

@@ -1,0 +1,167 @@
+# MicroclimateB200.jl — Julia side of the drop-in: `solve_soil!` for MANY sites on B200s through the C ABI
+# (include/microclimate_b200.h).  The host stays Julia, keeps Microclimate.jl's own types, strips units, lays the data out
+# site-fastest SoA and `ccall`s libmicroclimate_b200.so.
+#
+# NOT RUN in the build container (no Julia there); it is the binding INTEGRATION.md describes.  The Python mirror
+# (microclimate.jl_b200/marshal.py + simulation.py) performs the same marshalling and is what the tests drive.
+module MicroclimateB200
+
+using Microclimate
+using Unitful
+import Microclimate: MicroModel, MicroInputs, MicroProblem, MicroCache, NoSnow, SnowModel,
+    NonConsecutiveDayMode, ConsecutiveDayMode, FixedSoilTemperatureIterations, SoilTemperatureConvergenceTolerance,
+    DailyRainfall, HourlyRainfall, PrescribedSoilMoisture, DynamicSoilMoisture, MatricFluxPotentialAlgorithm
+
+const LIB = get(ENV, "MICROCLIMATE_B200_LIB", joinpath(@__DIR__, "..", "microclimate.jl_b200", "csrc", "libmicroclimate_b200.so"))
+const MC_MAX_SOIL_NODES = 24
+const MC_SNOW_NODES = 8
+
+# ---- POD mirrors of include/microclimate_b200.h (field order and types must match the header) -----------------
+struct McFluid
+    molar_mass_water::Cdouble; molar_mass_air::Cdouble; ideal_gas_departure::Cdouble; cp_dry_air::Cdouble
+    cp_water_vapour::Cdouble; gas_constant::Cdouble; stefan_boltzmann::Cdouble; standard_gravity::Cdouble
+    standard_pressure::Cdouble; latent_heat_a::Cdouble; latent_heat_b::Cdouble; molar_latent_heat_a::Cdouble
+    molar_latent_heat_b::Cdouble
+end
+struct McSnow
+    snow_temperature_threshold_C::Cdouble; snow_density::Cdouble; snow_melt_factor::Cdouble; undercatch::Cdouble
+    rain_multiplier::Cdouble; rain_melt_factor::Cdouble; density_function::NTuple{4,Cdouble}; snow_conductivity::Cdouble
+    canopy_interception::Cdouble; min_snow_depth_cm::Cdouble; node_thresholds_cm::NTuple{MC_SNOW_NODES,Cdouble}
+    melt_threshold_C::Cdouble; ahc_kind::Cint
+    ahc_T_low_C::Cdouble; ahc_T_high_C::Cdouble; ahc_window_K::Cdouble; ahc_smoothing_K::Cdouble
+    ahc_T_melt_C::Cdouble; ahc_width_K::Cdouble
+    initial_snow_depth_cm::Cdouble; initial_snow_temperature_K::Cdouble; initial_snow_density::Cdouble
+end
+struct McModel
+    n_soil::Cint; n_snow::Cint
+    depths_m::NTuple{MC_MAX_SOIL_NODES,Cdouble}
+    reference_height_m::Cdouble; local_height_m::Cdouble
+    reltol::Cdouble; abstol::Cdouble; maximum_surface_temperature_K::Cdouble
+    de_vries_shape_factor::Cdouble; recirculation_power::Cdouble; return_flow_threshold::Cdouble
+    root_resistance::Cdouble; stomatal_closure_potential::Cdouble; leaf_resistance::Cdouble
+    stomatal_stability_parameter::Cdouble; root_radius::Cdouble
+    infiltration_algorithm::Cint
+    karman_constant::Cdouble; dyer_constant::Cdouble
+    time_mode::Cint; iterations_per_day::Cint; spinup_first_day::Cint
+    convergence_kind::Cint; convergence_iterations::Cint
+    convergence_tolerance_K::Cdouble
+    rainfall_schedule::Cint; moisture_strategy::Cint
+    moisture_tolerance::Cdouble; moisture_max_iterations::Cint; moisture_timestep_s::Cdouble
+    max_surface_pool::Cdouble
+    atmospheric_radiation::Cint; _pad0::Cint
+    fluid::McFluid; snow::McSnow
+end
+struct McSites;   p::NTuple{12,Ptr{Cdouble}}; end           # roughness … root_density (header order)
+struct McInitial; T::Ptr{Cdouble}; theta::Ptr{Cdouble}; end
+struct McForcing; hourly::NTuple{11,Ptr{Cdouble}}; daily::NTuple{8,Ptr{Cdouble}}; prescribed::Ptr{Cdouble}; doy::Ptr{Cint}; end
+struct McOutput;  node::NTuple{7,Ptr{Cdouble}}; scalar::NTuple{5,Ptr{Cdouble}}; snow_T::Ptr{Cdouble}; status::Ptr{Cint}; end
+
+check(h, rc, what) = rc < 0 ? error("$what failed (rc=$rc): " * unsafe_string(ccall((:mc_last_error, LIB), Cstring, (Ptr{Cvoid},), h))) : rc
+
+si(x, u) = Float64(ustrip(u, x))
+
+"Flatten MicroModel + MicroConfig + time mode into mc_model_desc (reference src/types.jl:71-120)."
+function model_desc(model::MicroModel, time_mode)
+    d = Ref{McModel}()
+    ccall((:mc_default_model, LIB), Cvoid, (Ref{McModel},), d)
+    m = d[]
+    N = length(model.depths)
+    depths = ntuple(i -> i <= N ? si(model.depths[i], u"m") : 0.0, MC_MAX_SOIL_NODES)
+    sem, sp, sh, cfg = model.soil_energy_model, model.soil_properties_model, model.soil_hydraulic_model, model.config
+    tm, ipd, spin = time_mode isa NonConsecutiveDayMode ? (0, time_mode.iterations_per_day, 0) : (1, 1, Int(time_mode.spinup_first_day))
+    cv = cfg.convergence
+    ck, ci, ct = cv isa FixedSoilTemperatureIterations ? (0, cv.iterations_per_day, 0.0) : (1, cv.max_iterations_per_day, si(cv.tolerance, u"K"))
+    sm = cfg.soil_moisture_strategy
+    dyn = sm isa DynamicSoilMoisture
+    McModel(N, model.snow_model isa NoSnow ? 0 : MC_SNOW_NODES, depths,
+        si(last(model.heights), u"m"), si(first(model.heights), u"m"),
+        ustrip(sem.ode_kwargs.reltol), si(sem.ode_kwargs.abstol, u"K"), si(u"K"(sem.maximum_surface_temperature), u"K"),
+        sp.de_vries_shape_factor, sp.recirculation_power, sp.return_flow_threshold,
+        si(sh.root_resistance, u"m^3/kg/s"), si(sh.stomatal_closure_potential, u"J/kg"), si(sh.leaf_resistance, u"m^4/kg/s"),
+        sh.stomatal_stability_parameter, si(sh.root_radius, u"m"),
+        sh.infiltration_algorithm isa MatricFluxPotentialAlgorithm ? 1 : 0,
+        model.boundary_layer_model.karman_constant, model.boundary_layer_model.dyer_constant,
+        tm, ipd, spin, ck, ci, ct,
+        cfg.rainfall_schedule isa HourlyRainfall ? 1 : 0, dyn ? 1 : 0,
+        dyn ? si(sm.moisture_tolerance, u"kg/m^2/s") : 1e-6, dyn ? sm.moisture_max_iterations : 500, dyn ? si(sm.moisture_timestep, u"s") : 360.0,
+        si(cfg.max_surface_pool, u"kg/m^2"), 0, 0, m.fluid, m.snow)
+end
+
+"""
+    solve_soil_batched!(caches::Vector{<:MicroCache}; device=0, chunk_days=nothing)
+
+Batched replacement of `Microclimate.solve_soil!(cache)` (src/simulation.jl:355-819): all caches share one `MicroModel`
+(the reference's own many-sites idiom, src/types.jl:143-144) and have had `solve_solar!` + `populate_weather!` run, so
+`cache.output` holds the hourly weather the path reads (src/simulation.jl:1006-1021,1051-1070).  Fills
+`cache.output.{soil_temperature, soil_moisture, soil_water_potential, soil_humidity, soil_thermal_conductivity,
+soil_heat_capacity, soil_bulk_density, surface_water, sky_temperature}` of every cache, so `solve_air!` runs unchanged.
+"""
+function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integer=0, chunk_days=nothing)
+    mp = first(caches).problem
+    model, S, N, D = mp.model, length(caches), length(mp.model.depths), length(mp.days)
+    H = 24D
+    desc = Ref(model_desc(model, mp.time_mode))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:mc_create, LIB), Cint, (Ref{McModel}, Int64, Cint, Ref{Ptr{Cvoid}}), desc, S, device, h), "mc_create")
+    try
+        inp(c) = c.problem.inputs
+        # ---- sites: [S] and [N][S] (site fastest) ------------------------------------------------------------
+        sitev(f) = Float64[f(inp(c)) for c in caches]
+        nodev(f) = Float64[f(inp(c), i) for c in caches, i in 1:N]            # S×N column-major == [N][S] row-major
+        site_arrays = (sitev(x -> si(x.site.roughness_height, u"m")), sitev(x -> si(x.site.slope, u"°")),
+                       sitev(x -> x.site.sky_view_fraction), sitev(x -> x.site.albedo),
+                       nodev((x, i) -> si(x.soil_profile.bulk_density[i], u"kg/m^3")), nodev((x, i) -> si(x.soil_profile.mineral_density[i], u"kg/m^3")),
+                       nodev((x, i) -> si(x.soil_profile.mineral_conductivity[i], u"W/m/K")), nodev((x, i) -> si(x.soil_profile.mineral_heat_capacity[i], u"J/kg/K")),
+                       nodev((x, i) -> si(x.soil_profile.hydraulics.air_entry_water_potential[i], u"J/kg")),
+                       nodev((x, i) -> si(x.soil_profile.hydraulics.saturated_hydraulic_conductivity[i], u"kg*s/m^3")),
+                       nodev((x, i) -> x.soil_profile.hydraulics.campbell_b_parameter[i]), nodev((x, i) -> si(x.soil_profile.hydraulics.root_density[i], u"m/m^3")))
+        has_T = !isnothing(inp(first(caches)).initial_soil_temperature)
+        T_init = has_T ? nodev((x, i) -> si(u"K"(x.initial_soil_temperature[i]), u"K")) : Float64[]
+        th_init = nodev((x, i) -> x.initial_soil_moisture[i])
+        # ---- forcing: hourly [H][S], daily [D][S] ----------------------------------------------------------------
+        hourly(f) = Float64[f(c, t) for c in caches, t in 1:H]
+        daily(f) = Float64[f(inp(c).environment_daily, d) for c in caches, d in 1:D]
+        o(c) = c.output
+        so(c) = c.buffers.solar_out
+        hrain = model.config.rainfall_schedule isa HourlyRainfall
+        hourly_arrays = (hourly((c, t) -> si(o(c).pressure[t], u"Pa")), hourly((c, t) -> si(u"K"(o(c).reference_temperature[t]), u"K")),
+                         hourly((c, t) -> si(o(c).reference_wind_speed[t], u"m/s")), hourly((c, t) -> o(c).reference_humidity[t]),
+                         hourly((c, t) -> o(c).cloud_cover[t]), hourly((c, t) -> si(o(c).global_radiation[t], u"W/m^2")),
+                         hourly((c, t) -> o(c).diffuse_fraction[t]), hourly((c, t) -> min(si(so(c).zenith_angle[t], u"°"), 90.0)),
+                         hourly((c, t) -> min(si(so(c).zenith_slope_angle[t], u"°"), 90.0)),
+                         hrain ? hourly((c, t) -> si(inp(c).environment_hourly.rainfall[t], u"kg/m^2")) : Float64[], Float64[])
+        daily_arrays = (daily((e, d) -> ustrip(e.leaf_area_index[d])), daily((e, d) -> e.shade[d]), daily((e, d) -> e.surface_emissivity[d]),
+                        daily((e, d) -> e.cloud_emissivity[d]), daily((e, d) -> e.soil_wetness[d]),
+                        daily((e, d) -> si(u"K"(e.deep_soil_temperature[d]), u"K")), daily((e, d) -> si(e.rainfall[d], u"kg/m^2")), Float64[])
+        doy = Cint.(mp.days)
+        # ---- outputs: [H][N][S] and [H][S] --------------------------------------------------------------------------
+        node_out = ntuple(_ -> zeros(S, N, H), 7)
+        scal_out = (zeros(S, H), zeros(S, H))
+        status = zeros(Cint, S)
+        ptr(a) = isempty(a) ? Ptr{Cdouble}(C_NULL) : pointer(a)
+        GC.@preserve site_arrays T_init th_init hourly_arrays daily_arrays doy node_out scal_out status begin
+            sites = Ref(McSites(map(ptr, site_arrays)))
+            init = Ref(McInitial(ptr(T_init), ptr(th_init)))
+            check(h[], ccall((:mc_set_sites, LIB), Cint, (Ptr{Cvoid}, Ref{McSites}, Ref{McInitial}), h[], sites, init), "mc_set_sites")
+            forcing = Ref(McForcing(map(ptr, hourly_arrays), map(ptr, daily_arrays), Ptr{Cdouble}(C_NULL), pointer(doy)))
+            out = Ref(McOutput(map(pointer, node_out), (pointer(scal_out[1]), pointer(scal_out[2]), Ptr{Cdouble}(C_NULL), Ptr{Cdouble}(C_NULL), Ptr{Cdouble}(C_NULL)),
+                               Ptr{Cdouble}(C_NULL), pointer(status)))
+            check(h[], ccall((:mc_step_days, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ref{McForcing}, Ref{McOutput}), h[], 0, D, forcing, out), "mc_step_days")
+        end
+        # ---- un-marshal into each cache's MicroResult (nsteps × N, unit-tagged) so solve_air! runs unchanged ----------
+        fields = (:soil_temperature => u"K", :soil_moisture => 1, :soil_water_potential => u"J/kg", :soil_humidity => 1,
+                  :soil_thermal_conductivity => u"W/m/K", :soil_heat_capacity => u"J/kg/K", :soil_bulk_density => u"kg/m^3")
+        for (s, c) in enumerate(caches), (k, (f, unit)) in enumerate(fields), i in 1:N, t in 1:H
+            getproperty(c.output, f)[t, i] = node_out[k][s, i, t] * unit
+        end
+        for (s, c) in enumerate(caches), t in 1:H
+            c.output.surface_water[t] = scal_out[1][s, t] * u"kg/m^2"
+            c.output.sky_temperature[t] = scal_out[2][s, t] * u"K"
+        end
+        return status
+    finally
+        ccall((:mc_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
+end # module

@@ -13,7 +13,7 @@ from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO = os.path.join(CSRC, "libmicroclimate_b200.so")
+SO = os.environ.get("MC_LIB") or os.path.join(CSRC, "libmicroclimate_b200.so")   # MC_LIB: development override (tuning variants)
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "microclimate_b200.h")
 SOURCES = [os.path.join(CSRC, "mc_api.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "mc_device.cuh"), INCLUDE, os.path.join(os.path.dirname(INCLUDE), "mc_math.h")]

@@ -30,13 +30,19 @@ thread_local std::string g_create_error;
         }                                                                                                      \
     } while (0)
 
-constexpr int BLOCK = 128;
+#ifndef MC_BLOCK
+#define MC_BLOCK 128
+#endif
+#ifndef MC_MIN_BLOCKS
+#define MC_MIN_BLOCKS 3
+#endif
+constexpr int BLOCK = MC_BLOCK;
 
 }  // namespace
 
 /* ---------------------------------------------------------------- kernels ---- */
 template <int NA>
-__global__ void __launch_bounds__(BLOCK) soil_chunk_kernel(const mcd::KArgs a)
+__global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const mcd::KArgs a)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
@@ -121,7 +127,13 @@ template <int NA>
 static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
 {
     const int grid = (int)((a.S + BLOCK - 1) / BLOCK);
-    soil_chunk_kernel<NA><<<grid, BLOCK, 0, st>>>(a);
+    static int pad = -1;                 /* development knob: dynamic shared-memory padding limits resident blocks per SM */
+    if (pad < 0) {
+        const char* e = getenv("MC_SMEM_PAD");
+        pad = e ? atoi(e) : 0;
+        if (pad > 48 * 1024) cudaFuncSetAttribute(soil_chunk_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
+    soil_chunk_kernel<NA><<<grid, BLOCK, pad, st>>>(a);
     return cudaGetLastError();
 }
 

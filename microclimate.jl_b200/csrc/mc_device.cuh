@@ -33,6 +33,7 @@
 #define MC_MEMBER __device__ __forceinline__
 #define MC_DEV_NOINLINE __device__ __noinline__
 #define MC_LDG(p) __ldg(p)
+#define MC_ROLLED _Pragma("unroll 1")
 #define MC_CONST_MODEL g_model_c
 #else
 #include <cmath>
@@ -40,7 +41,12 @@
 #define MC_MEMBER inline
 #define MC_DEV_NOINLINE static __attribute__((noinline))
 #define MC_LDG(p) (*(p))
+#define MC_ROLLED
 #define MC_CONST_MODEL g_model_h
+#endif
+
+#ifndef MC_USE_GG3
+#define MC_USE_GG3 0
 #endif
 
 namespace mcd {
@@ -123,6 +129,37 @@ MC_DEV_NOINLINE double goff_gratch(double T)
              + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314 /* mcm::log10(1013.246) */;
     }
     return 100.0 * mcm::exp10(loge);
+}
+
+/* goff_gratch at T-1, T, T+1 (the central difference of campbell_devries.jl:117-122) evaluated side by side: the three
+ * evaluations are independent, so interleaving them triples the instruction-level parallelism of the hottest code in the
+ * path.  Every element goes through exactly the operations of goff_gratch() above (bit-identical results). */
+struct GG3 { double em, e0, ep; };
+MC_DEV_NOINLINE GG3 goff_gratch3(double T)
+{
+    GG3 o;
+    const double t0 = (T - 1.0) + 0.01, t1 = T + 0.01, t2 = (T + 1.0) + 0.01;
+    if (t0 > 273.16 && t2 < 400.0) {                       /* all three on the over-water branch (t0 < t1 < t2) */
+        const double r0 = 373.16 / t0, r1 = 373.16 / t1, r2 = 373.16 / t2;
+        const double a0 = 11.344 * (1.0 - t0 / 373.16), a1 = 11.344 * (1.0 - t1 / 373.16), a2 = 11.344 * (1.0 - t2 / 373.16);
+        const double b0 = -3.49149 * (r0 - 1.0), b1 = -3.49149 * (r1 - 1.0), b2 = -3.49149 * (r2 - 1.0);
+        const double pa0 = mcm::exp10_arg(a0), pa1 = mcm::exp10_arg(a1), pa2 = mcm::exp10_arg(a2);
+        const double pb0 = mcm::exp10_arg(b0), pb1 = mcm::exp10_arg(b1), pb2 = mcm::exp10_arg(b2);
+        /* arguments are O(1) for 273 K < T < 400 K: always inside the fast range of exp / log */
+        const double ea0 = mcm::exp10_finish(mcm::exp_core(pa0), a0, pa0), ea1 = mcm::exp10_finish(mcm::exp_core(pa1), a1, pa1), ea2 = mcm::exp10_finish(mcm::exp_core(pa2), a2, pa2);
+        const double eb0 = mcm::exp10_finish(mcm::exp_core(pb0), b0, pb0), eb1 = mcm::exp10_finish(mcm::exp_core(pb1), b1, pb1), eb2 = mcm::exp10_finish(mcm::exp_core(pb2), b2, pb2);
+        const double l0 = mcm::log_core(r0) * 4.34294481903251816668e-01, l1 = mcm::log_core(r1) * 4.34294481903251816668e-01, l2 = mcm::log_core(r2) * 4.34294481903251816668e-01;
+        const double g0 = -7.90298 * (r0 - 1.0) + 5.02808 * l0 - 1.3816e-7 * (ea0 - 1.0) + 8.1328e-3 * (eb0 - 1.0) + 3.0057148979490314;
+        const double g1 = -7.90298 * (r1 - 1.0) + 5.02808 * l1 - 1.3816e-7 * (ea1 - 1.0) + 8.1328e-3 * (eb1 - 1.0) + 3.0057148979490314;
+        const double g2 = -7.90298 * (r2 - 1.0) + 5.02808 * l2 - 1.3816e-7 * (ea2 - 1.0) + 8.1328e-3 * (eb2 - 1.0) + 3.0057148979490314;
+        const double p0 = mcm::exp10_arg(g0), p1 = mcm::exp10_arg(g1), p2 = mcm::exp10_arg(g2);
+        o.em = 100.0 * mcm::exp10_finish(mcm::exp_core(p0), g0, p0);
+        o.e0 = 100.0 * mcm::exp10_finish(mcm::exp_core(p1), g1, p1);
+        o.ep = 100.0 * mcm::exp10_finish(mcm::exp_core(p2), g2, p2);
+    } else {
+        o.em = goff_gratch(T - 1.0); o.e0 = goff_gratch(T); o.ep = goff_gratch(T + 1.0);
+    }
+    return o;
 }
 
 struct WetAir { double vapour_pressure, vapour_density, specific_heat, density; };
@@ -244,9 +281,16 @@ MC_DEV_NOINLINE double soil_conductivity(double T, double P, double theta, doubl
     const double Dv = 2.12e-5 * (m.P0 / P) * mcm::pow(T / 273.15, 1.75);      /* campbell_devries.jl:109 */
     const double rho_hat = 44.65 * (P / m.P0) * (273.15 / T);                   /* :111 */
     const double Hv = m.Hv_a - m.Hv_b * (T - T0C);
+#if MC_USE_GG3
+    const GG3 gg = goff_gratch3(T);
+    const double e0 = gg.e0 * 0.99;
+    const double em = gg.em * 0.99;
+    const double ep = gg.ep * 0.99;
+#else
     const double e0 = goff_gratch(T) * 0.99;
     const double em = goff_gratch(T - 1.0) * 0.99;
     const double ep = goff_gratch(T + 1.0) * 0.99;
+#endif
     const double dedT = (ep - em) / 2.0;
     const double lam_g = lam_a + Hv * dedT * fw * rho_hat * Dv / (P - e0);
     const double lam_f = lam_g + fw * (lam_w - lam_g);
@@ -299,8 +343,7 @@ MC_DEV_NOINLINE void soil_rhs(const HourSoil<NA>& hs, const HourPar& hp, const d
     double G_up = soil_conductivity(T_up, P, hs.theta[0], hs.phim[0], hs.phig[0], hs.fw[0], hs.lam_m[0]) / m.dzg[0];
     double T_i = jclamp(u[1], T_LO, m.T_hi);
     const double Q_cond = G_up * (T_i - Ts_node);
-#pragma unroll 1
-    for (int i = 1; i < N - 1; i++) {
+    MC_ROLLED for (int i = 1; i < N - 1; i++) {
         const double T_dn = jclamp(u[i + 1], T_LO, m.T_hi);
         const double G_i = soil_conductivity(T_i, P, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]) / m.dzg[i];
         du[i] = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / hs.cap[i];
@@ -400,7 +443,7 @@ struct Integ {
     int iter, flags; bool accept, u_modified;
 };
 
-MC_DEV double rms_scaled(const double* x, const double* sk, int n) { double s = 0.0; for (int i = 0; i < n; i++) { const double q = x[i] / sk[i]; s += q * q; } return sqrt(s / n); }
+MC_DEV double rms_scaled(const double* x, const double* sk, int n) { double s = 0.0; MC_ROLLED for (int i = 0; i < n; i++) { const double q = x[i] / sk[i]; s += q * q; } return sqrt(s / n); }
 
 /* Hairer-Wanner automatic initial step (OrdinaryDiffEqCore initdt.jl), order 5 */
 template <int NA>
@@ -409,19 +452,19 @@ MC_DEV_NOINLINE double determine_initdt(Integ<NA>& I, const HourSoil<NA>& hs, co
     const DevModel& m = MC_CONST_MODEL; const int N = m.N;
     double* sk = I.tmp; double* f0 = I.k2; double* f1 = I.k3; double* u1 = I.k4;
     double s0 = 0.0;
-    for (int i = 0; i < N; i++) { sk[i] = m.abstol + fabs(I.u[i]) * m.reltol; const double q = I.u[i] / sk[i]; s0 += q * q; }
+    MC_ROLLED for (int i = 0; i < N; i++) { sk[i] = m.abstol + fabs(I.u[i]) * m.reltol; const double q = I.u[i] / sk[i]; s0 += q * q; }
     const double d0 = sqrt(s0 / N);
     soil_rhs<NA>(hs, hp, I.u, I.t, f0, cn);
     bool finite = true;
-    for (int i = 0; i < N; i++) if (!isfinite(f0[i])) finite = false;
+    MC_ROLLED for (int i = 0; i < N; i++) if (!isfinite(f0[i])) finite = false;
     if (!finite) return 1e-12;
     const double d1 = rms_scaled(f0, sk, N);
     double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
     dt0 = fmin(dt0, 1440.0);
-    for (int i = 0; i < N; i++) u1[i] = I.u[i] + dt0 * f0[i];
+    MC_ROLLED for (int i = 0; i < N; i++) u1[i] = I.u[i] + dt0 * f0[i];
     soil_rhs<NA>(hs, hp, u1, I.t + dt0, f1, cn);
     double s2 = 0.0;
-    for (int i = 0; i < N; i++) { const double q = (f1[i] - f0[i]) / sk[i]; s2 += q * q; }
+    MC_ROLLED for (int i = 0; i < N; i++) { const double q = (f1[i] - f0[i]) / sk[i]; s2 += q * q; }
     const double d2 = sqrt(s2 / N) / dt0;
     const double md = fmax(d1, d2);
     double dt1;
@@ -442,13 +485,13 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
             if (!I.accept) {
                 I.dt = I.dt / fmin(5.0, I.q11 / 0.9);
             } else {
-                for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
+                MC_ROLLED for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
                 I.dt = I.dtpropose;
                 if (I.u_modified) soil_rhs<NA>(hs, hp, I.u, I.t, I.k1, cn);
-                else for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
+                else MC_ROLLED for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
             }
         } else if (I.u_modified) {
-            for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
+            MC_ROLLED for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
         }
         I.iter++;
         I.dt = fmin(1440.0, I.dt);
@@ -456,24 +499,24 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
         if (!(I.dt > 1e-12) || ++guard > 100000) {
             I.flags |= (I.dt != I.dt) ? MC_STATUS_NAN : (guard > 100000 ? MC_STATUS_STEP_LIMIT : MC_STATUS_DT_UNDERFLOW);
             I.t = I.tstop; I.accept = true; I.dtpropose = 1.0;
-            for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
+            MC_ROLLED for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
             return;
         }
         const double t = I.t, dt = I.dt;
-        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
         soil_rhs<NA>(hs, hp, I.tmp, t + c1 * dt, I.k2, cn);
-        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
         soil_rhs<NA>(hs, hp, I.tmp, t + c2 * dt, I.k3, cn);
-        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
         soil_rhs<NA>(hs, hp, I.tmp, t + c3 * dt, I.k4, cn);
-        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
         soil_rhs<NA>(hs, hp, I.tmp, t + c4 * dt, I.k5, cn);
-        for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
         soil_rhs<NA>(hs, hp, I.tmp, t + dt, I.k6, cn);
-        for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
+        MC_ROLLED for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
         soil_rhs<NA>(hs, hp, I.u, t + dt, I.k7, cn);
         double ss = 0.0;
-        for (int i = 0; i < N; i++) {
+        MC_ROLLED for (int i = 0; i < N; i++) {
             const double ut = dt * (bt1 * I.k1[i] + bt2 * I.k2[i] + bt3 * I.k3[i] + bt4 * I.k4[i] + bt5 * I.k5[i] + bt6 * I.k6[i] + bt7 * I.k7[i]);
             const double q = ut / (m.abstol + fmax(fabs(I.uprev[i]), fabs(I.u[i])) * m.reltol);
             ss += q * q;
@@ -500,7 +543,7 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
             return;
         }
         cn.n_reject++;
-        for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
+        MC_ROLLED for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
     }
 }
 
@@ -510,7 +553,7 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
 MC_DEV_NOINLINE void phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
 {
     const double tol = 1.0e-4;
-    for (int i = 0; i < N; i++) {
+    MC_ROLLED for (int i = 0; i < N; i++) {
         double mean, mean_past;
         if (i < N - 1) { mean = 0.5 * (T[i] + T[i + 1]); mean_past = 0.5 * (Tpast[i] + Tpast[i + 1]); }
         else { mean = T[i]; mean_past = Tpast[i]; }
@@ -560,9 +603,9 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
     const int L = m.N;
     const double g = m.g, dt = m.moist_dt;
     const bool flux_alg = m.flux_alg != 0;
-    for (int i = 2; i <= L; i++) { B.wcn[i] = theta[i - 2]; B.wc[i] = theta[i - 2]; }
+    MC_ROLLED for (int i = 2; i <= L; i++) { B.wcn[i] = theta[i - 2]; B.wc[i] = theta[i - 2]; }
     /* initial_state_from_water_content! */
-    for (int i = 2; i <= L; i++) {
+    MC_ROLLED for (int i = 2; i <= L; i++) {
         B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
         if (!flux_alg) B.K[i] = hm.ks[i] * mcm::pow(hm.psi_e[i] / B.psi[i], hm.nexp[i]);
         else {
@@ -580,7 +623,7 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
     const double EP = mcm::exp(-0.82 * lai) * ET;
     const double TP = ET - EP;
     double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
-    for (int i = 2; i <= L; i++) {
+    MC_ROLLED for (int i = 2; i <= L; i++) {
         B.soilR[i] = hm.rootZ[i] / B.K[i];
         const double rt = B.soilR[i] + hm.rootR[i];
         psum += B.psi[i] / rt;
@@ -599,26 +642,26 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
         if (fabs(resid) <= 10.0) break;
     }
     const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
-    for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
+    MC_ROLLED for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
 
     InfilOut out; out.hit_max = true;
     counter = 0;
     while (counter < m.moist_max_it) {                                       /* Newton loop, campbell.jl:293-336 */
         double err = 0.0;
         counter++; cn.n_newton++;
-        for (int i = 2; i <= L; i++) {
+        MC_ROLLED for (int i = 2; i <= L; i++) {
             if (!flux_alg) B.K[i] = hm.ks[i] * mcm::pow(hm.psi_e[i] / B.psi[i], hm.nexp[i]);
             else B.K[i] = hm.ks[i] * mcm::pow(B.phi[i] / hm.phi_e[i], hm.fexp[i]);
         }
-        if (flux_alg) { for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]); B.psi[L + 1] = hm.psi_e[L]; }
+        if (flux_alg) { MC_ROLLED for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]); B.psi[L + 1] = hm.psi_e[L]; }
         B.jv[1] = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc);
         B.djv[1] = EP * MW_INFIL * B.h[2] / (hm.rts1 * (1.0 - rh_loc));
-        for (int i = 2; i <= L; i++) {
+        MC_ROLLED for (int i = 2; i <= L; i++) {
             const double kv = hm.kvc[i] * (hm.sat[i] - (B.wcn[i] + B.wcn[i + 1]) / 2.0) / hm.dz[i];
             B.jv[i] = kv * (B.h[i + 1] - B.h[i]);
             B.djv[i] = MW_INFIL * B.h[i] * kv / hm.rts[i];
         }
-        for (int i = 2; i <= L; i++) {
+        MC_ROLLED for (int i = 2; i <= L; i++) {
             if (!flux_alg) {
                 const double cap = -1.0 * hm.mass[i] * B.wcn[i] / (hm.bb[i] * B.psi[i] * dt);
                 B.sub[i] = -1.0 * B.K[i - 1] / hm.dz[i - 1] + g * hm.nexp[i] * B.K[i - 1] / B.psi[i - 1];
@@ -638,7 +681,7 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
             }
             err += fabs(B.F[i]);
         }
-        for (int i = 2; i <= L - 1; i++) {                                   /* thomas_forward_elimination! */
+        MC_ROLLED for (int i = 2; i <= L - 1; i++) {                                   /* thomas_forward_elimination! */
             B.cc[i] = B.sup[i] / B.dia[i];
             if (fabs(B.cc[i]) < 1e-8) B.cc[i] = 0.0;
             B.rr[i] = B.F[i] / B.dia[i];
@@ -648,12 +691,12 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
         if (!flux_alg) {
             double dpsi = B.F[L] / B.dia[L];                                 /* lower boundary clamp */
             B.psi[L] = jmin(B.psi[L] - dpsi, hm.psi_e[L]);
-            for (int i = L - 1; i >= 2; i--) {                               /* interior back-substitution + saturation averaging clamp */
+            MC_ROLLED for (int i = L - 1; i >= 2; i--) {                               /* interior back-substitution + saturation averaging clamp */
                 dpsi = B.rr[i] - B.cc[i] * dpsi;
                 B.psi[i] -= dpsi;
                 if (B.psi[i] > hm.psi_e[i]) B.psi[i] = (B.psi[i] + dpsi + hm.psi_e[i]) / 2.0;
             }
-            for (int i = 2; i <= L; i++) {                                   /* recover_water_content! */
+            MC_ROLLED for (int i = 2; i <= L; i++) {                                   /* recover_water_content! */
                 B.wcn[i] = jmax(hm.sat[i] * mcm::pow(hm.psi_e[i] / B.psi[i], 1.0 / hm.bb[i]), 1e-7);
                 B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
             }
@@ -661,21 +704,21 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
             double dphi = B.F[L] / B.dia[L];
             B.phi[L] -= dphi;
             if (B.phi[L] < 0.0) B.phi[L] = 1e-6; else if (B.phi[L] > hm.phi_e[L]) B.phi[L] = hm.phi_e[L];
-            for (int i = L - 1; i >= 2; i--) {
+            MC_ROLLED for (int i = L - 1; i >= 2; i--) {
                 dphi = B.rr[i] - B.cc[i] * dphi;
                 B.phi[i] -= dphi;
                 if (B.phi[i] < 0.0) B.phi[i] = 1e-6; else if (B.phi[i] > hm.phi_e[i]) B.phi[i] = hm.phi_e[i];
             }
-            for (int i = 2; i <= L; i++) B.wcn[i] = jmax(hm.sat[i] * mcm::pow(B.phi[i] / hm.phi_e[i], 1.0 / (hm.bb[i] + 3.0)), 1e-7);
-            for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
+            MC_ROLLED for (int i = 2; i <= L; i++) B.wcn[i] = jmax(hm.sat[i] * mcm::pow(B.phi[i] / hm.phi_e[i], 1.0 / (hm.bb[i] + 3.0)), 1e-7);
+            MC_ROLLED for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
             B.psi[L + 1] = hm.psi_e[L];
         }
-        for (int i = 2; i <= L; i++) B.h[i] = mcm::exp(MW_INFIL * B.psi[i] / hm.rts[i]);
+        MC_ROLLED for (int i = 2; i <= L; i++) B.h[i] = mcm::exp(MW_INFIL * B.psi[i] / hm.rts[i]);
         B.h[L + 1] = B.h[L];
         if (err <= m.moist_tol) { out.hit_max = false; break; }
     }
     out.surface_water_flux = ((B.psi[2] * B.K[2] - B.psi[3] * B.K[3]) / ((1.0 - hm.nexp[2]) * hm.dz[2]) + g * B.K[2] + TR) * dt;
-    for (int i = 2; i <= L + 1; i++) theta[i - 2] = B.wcn[i];
+    MC_ROLLED for (int i = 2; i <= L + 1; i++) theta[i - 2] = B.wcn[i];
     out.evaporation = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc) * dt;
     return out;
 }
@@ -766,7 +809,7 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
 
     /* per-hour constants of the implicit solve */
     HourMoist<NA> hm;
-    for (int i = 1; i <= L; i++) {
+    MC_ROLLED for (int i = 1; i <= L; i++) {
         const double b = r.node(a.bb, i - 1), pe = -fabs(r.node(a.psi_e, i - 1)), ksat = r.node(a.ks, i - 1);
         hm.psi_e[i] = pe; hm.bb[i] = b; hm.ks[i] = ksat;
         hm.sat[i] = 1.0 - r.node(a.bd, i - 1) / r.node(a.md, i - 1);
@@ -779,8 +822,8 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     /* depth[1] = -1e10, depth[2] = 0, depth[i+1] = depths[i-1], depth[L+1] = 1e20 */
     auto depth_final = [&](int i) -> double { return i == 1 ? -1e10 : (i == 2 ? 0.0 : (i == L + 1 ? 1e20 : m.depths[i - 2])); };
     auto depth_mass = [&](int i) -> double { return i <= 2 ? 0.0 : m.depths[i - 2]; };     /* as it stands when layer_water_mass is formed (campbell.jl:228-230) */
-    for (int i = 1; i <= L; i++) hm.dz[i] = depth_final(i + 1) - depth_final(i);
-    for (int i = 2; i <= L; i++) {
+    MC_ROLLED for (int i = 1; i <= L; i++) hm.dz[i] = depth_final(i + 1) - depth_final(i);
+    MC_ROLLED for (int i = 2; i <= L; i++) {
         hm.mass[i] = WATER_RHO * (depth_mass(i + 1) - depth_mass(i - 1)) / 2.0;
         const double rd = r.node(a.rootd, i - 1);
         const double thick = depth_final(i + 1) - depth_final(i - 1);
@@ -799,13 +842,13 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     pool = wet_surface_node(theta, pool, sat0, half);
     InfilWork<NA> B;
     InfilOut io; io.evaporation = 0.0; io.surface_water_flux = 0.0; io.hit_max = false;
-    for (int k = 0; k < m.niter_moist; k++) {
+    MC_ROLLED for (int k = 0; k < m.niter_moist; k++) {
         io = infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn);
         if (io.hit_max) flags |= MC_STATUS_NEWTON_MAXITER;
         pool = jclamp(pool - jmax(0.0, io.surface_water_flux) - jmax(0.0, io.evaporation), 0.0, m.max_pool);
         pool = wet_surface_node(theta, pool, sat0, half);
     }
-    for (int i = 0; i < N; i++) { psi_out[i] = B.psi[i + 2]; h_out[i] = B.h[i + 2]; }
+    MC_ROLLED for (int i = 0; i < N; i++) { psi_out[i] = B.psi[i + 2]; h_out[i] = B.h[i + 2]; }
     return jclamp(jmax(0.0, io.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
 }
 
@@ -815,7 +858,7 @@ template <int NA>
 MC_DEV_NOINLINE void hoist_soil(const SiteRef& r, const double* theta, HourSoil<NA>& hs)
 {
     const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
-    for (int i = 0; i < m.N; i++) {
+    MC_ROLLED for (int i = 0; i < m.N; i++) {
         const double bd = r.node(a.bd, i), md = r.node(a.md, i);
         const double th = theta[i];
         const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
@@ -829,7 +872,7 @@ MC_DEV_NOINLINE void put_potential_row(const SiteRef& r, int row, const double* 
 {
     const KArgs& a = *r.a;
     if (!a.o_psi) return;
-    for (int i = 0; i < MC_CONST_MODEL.N; i++)
+    MC_ROLLED for (int i = 0; i < MC_CONST_MODEL.N; i++)
         r.put_node(a.o_psi, row, i, r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i)));
 }
 /* initialise_soil_humidity!, dynamic.jl:32-35: always row 1 of the buffer */
@@ -837,7 +880,7 @@ MC_DEV_NOINLINE void init_humidity(const SiteRef& r, const double* theta, const 
 {
     const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
     if (!m.dynamic || !a.o_h) return;
-    for (int i = 0; i < m.N; i++) {
+    MC_ROLLED for (int i = 0; i < m.N; i++) {
         const double psi = r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i));
         r.put_node(a.o_h, 0, i, jclamp(mcm::exp(MW_INFIL * psi / (m.R * Tn[i])), 0.0, 1.0));
     }
@@ -846,7 +889,7 @@ MC_DEV_NOINLINE void write_props(const SiteRef& r, int row, const double* Tn, co
 {
     const KArgs& a = *r.a;
     if (!a.o_lam && !a.o_cp && !a.o_rho) return;
-    for (int i = 0; i < MC_CONST_MODEL.N; i++) {
+    MC_ROLLED for (int i = 0; i < MC_CONST_MODEL.N; i++) {
         double lam, cp, rho;
         soil_properties_full(Tn[i], P, theta[i], r.node(a.bd, i), r.node(a.md, i), r.node(a.lam_m, i), r.node(a.c_m, i), lam, cp, rho);
         r.put_node(a.o_lam, row, i, lam); r.put_node(a.o_cp, row, i, cp); r.put_node(a.o_rho, row, i, rho);
@@ -859,7 +902,7 @@ MC_DEV bool is_converged(int iter, int niter, const double* T0, const double* T0
     if (m.conv_kind == MC_CONV_FIXED) return iter >= niter;
     if (iter >= niter) return true;
     if (iter <= 1) return niter <= 1;
-    double mx = 0.0; for (int i = 0; i < N; i++) mx = fmax(mx, fabs(T0[i] - T0_prev[i]));
+    double mx = 0.0; MC_ROLLED for (int i = 0; i < N; i++) mx = fmax(mx, fabs(T0[i] - T0_prev[i]));
     return mx < m.conv_tol;
 }
 
@@ -879,20 +922,20 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
     HourSoil<NA> hs; HourPar hp; Integ<NA> I;
     double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_prev_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
     double psi_out[NA], h_out[NA];
-    for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; hs.lam_m[i] = r.node(a.lam_m, i); }
+    MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; hs.lam_m[i] = r.node(a.lam_m, i); }
     double pool = a.pool[s], wet_dyn = a.wetness[s], L_ode = a.L_ode[s], L_prof = a.L_prof[s], tdeep_stale = a.tdeep_prev[s];
     int flags = a.flags[s];
     const double site_albedo = MC_LDG(a.albedo + s);
     hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
     I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
-    for (int i = 0; i < N; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
+    MC_ROLLED for (int i = 0; i < N; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
 
     auto set_day_forcing = [&](int jl) {
         const int64_t off = (int64_t)jl * 24 * S + s;
         hp.fP = a.f_P + off; hp.fT = a.f_T + off; hp.fwind = a.f_wind + off; hp.frh = a.f_rh + off; hp.fcloud = a.f_cloud + off;
         hp.fsolar = a.f_solar + off; hp.fdiff = a.f_diffuse + off; hp.fzen = a.f_zen + off; hp.fszen = a.f_szen + off;
     };
-    auto tins_mean = [&](int jl) { double ssum = 0.0; for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
+    auto tins_mean = [&](int jl) { double ssum = 0.0; MC_ROLLED for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
     double sky_T = 0.0;
     auto set_hour_params = [&](const EnvInstant& e) {
         hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud; hp.albedo = e.albedo;
@@ -905,17 +948,17 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
         /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:224-238,853-860) */
         set_day_forcing(0);
         env = get_instant(r, 0, 0, site_albedo);
-        for (int i = 0; i < N; i++) I.tmp[i] = a.has_init_T ? T0[i] : 280.0;
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = a.has_init_T ? T0[i] : 280.0;
         hoist_soil<NA>(r, theta, hs);
         hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
         Counters scratch = {};
         soil_rhs<NA>(hs, hp, I.tmp, 0.0, I.k1, scratch);
         /* solve_soil! pre-loop (simulation.jl:395-452) */
-        if (!a.has_init_T) { const double t_init = tins_mean(0); for (int i = 0; i < N; i++) T0[i] = t_init; }
-        for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
+        if (!a.has_init_T) { const double t_init = tins_mean(0); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_init; }
+        MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
         write_props(r, 0, T0, theta, 101325.0);
         put_potential_row(r, 0, theta);
-        for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
+        MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
         init_humidity(r, theta, T0);
         tdeep_stale = env.T_deep;
         pool = 0.0;
@@ -926,27 +969,27 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
         set_day_forcing(jl);
         const int niter = nonconsec ? m.iters_per_day : ((m.spinup && j == 0) ? m.conv_iters : 1);
         int noon_i = 0; double best = r.hourly(a.f_zen, jl * 24);
-        for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
+        MC_ROLLED for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
         const int midnight_i = (noon_i + 12) % 24;
         if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516) */
-            for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-            if (!dynamic && a.has_presc) { for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
-            else for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i);
-            if (!a.has_init_T) { const double t_reset = tins_mean(jl); for (int i = 0; i < N; i++) T0[i] = t_reset; }
-            else for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i);
+            MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
+            if (!dynamic && a.has_presc) { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
+            else MC_ROLLED for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i);
+            if (!a.has_init_T) { const double t_reset = tins_mean(jl); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_reset; }
+            else MC_ROLLED for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i);
         }
         T0[N - 1] = tdeep_stale;
         int iter = 0; bool is_last = false;
-        for (int i = 0; i < N; i++) { T0_prev_start[i] = T0[i]; T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
+        MC_ROLLED for (int i = 0; i < N; i++) { T0_prev_start[i] = T0[i]; T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
         while (!is_last) {                                                    /* outer fixed point over day passes (simulation.jl:530) */
             iter++; cn.n_day_passes++;
             is_last = is_converged(iter, niter, T0, T0_prev_start, N);
-            for (int i = 0; i < N; i++) T0_prev_start[i] = T0[i];
-            if (!nonconsec) for (int i = 0; i < N; i++) T0[i] = T0_day_start[i];
-            for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
+            MC_ROLLED for (int i = 0; i < N; i++) T0_prev_start[i] = T0[i];
+            if (!nonconsec) MC_ROLLED for (int i = 0; i < N; i++) T0[i] = T0_day_start[i];
+            MC_ROLLED for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
             const int day_row = jl * 24;
             if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
-                for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
+                MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
                 r.put_scalar(a.o_pool, day_row, pool);
                 put_potential_row(r, day_row, theta);
                 init_humidity(r, theta, T0);
@@ -960,12 +1003,12 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
             hp.L_prev = L_ode;
             hoist_soil<NA>(r, theta, hs);
             /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
-            for (int i = 0; i < N; i++) { I.u[i] = T0[i]; I.uprev[i] = T0[i]; }
+            MC_ROLLED for (int i = 0; i < N; i++) { I.u[i] = T0[i]; I.uprev[i] = T0[i]; }
             I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
             I.dt = determine_initdt<NA>(I, hs, hp, cn);
-            for (int i = 0; i < 24; i++) {
+            MC_ROLLED for (int i = 0; i < 24; i++) {
                 const int step = jl * 24 + i;
-                for (int k = 0; k < N; k++) T0_before[k] = T0[k];
+                MC_ROLLED for (int k = 0; k < N; k++) T0_before[k] = T0[k];
                 if (i > 0) hoist_soil<NA>(r, theta, hs);
                 hp.L_prev = L_ode;
                 /* step_to_hour! (simulation.jl:888-903) */
@@ -974,20 +1017,20 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
                 while (I.t < target - 1e-10) {
                     tsit5_step<NA>(I, hs, hp, cn);
                     bool changed = false;
-                    for (int k = 0; k < N; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
-                    if (changed) { for (int k = 0; k < N; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
+                    MC_ROLLED for (int k = 0; k < N; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
+                    if (changed) { MC_ROLLED for (int k = 0; k < N; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
                 }
-                for (int k = 0; k < N; k++) T0[k] = I.u[k];
+                MC_ROLLED for (int k = 0; k < N; k++) T0[k] = I.u[k];
                 if (is_last) {
                     phase_transition(N, m.depths, T0, T0_before, sum_phase, theta);
-                    for (int k = 0; k < N; k++) T0_output[k] = T0[k];
+                    MC_ROLLED for (int k = 0; k < N; k++) T0_output[k] = T0[k];
                 }
                 if (i < 23) {
                     env = get_instant(r, jl, step + 1, site_albedo);
                     T0[N - 1] = env.T_deep;
                     set_hour_params(env);
                 }
-                for (int k = 0; k < N; k++) I.u[k] = T0[k];
+                MC_ROLLED for (int k = 0; k < N; k++) I.u[k] = T0[k];
                 I.u_modified = true;
                 {   /* init_surface_fluxes! (monin_obukhov.jl:247-264): hourly warm start of the Obukhov length */
                     const double T_air = MC_LDG(hp.fT + (int64_t)i * S);
@@ -1014,16 +1057,16 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
                 const int out_row = step + 1;
                 if (is_last && out_row < nrows && !(i == 23 && nonconsec)) {
                     r.put_scalar(a.o_pool, out_row, pool);
-                    for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
+                    MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
                     r.put_scalar(a.o_sky, out_row, sky_T);
-                    if (have_infil) for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); }
+                    if (have_infil) MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); }
                     write_props(r, out_row, T0, theta, r.hourly(a.f_P, out_row));
                 }
             }
         }
         tdeep_stale = env.T_deep;
     }
-    for (int i = 0; i < N; i++) {
+    MC_ROLLED for (int i = 0; i < N; i++) {
         a.T[(int64_t)i * S + s] = T0[i]; a.theta[(int64_t)i * S + s] = theta[i]; a.sum_phase[(int64_t)i * S + s] = sum_phase[i];
         a.fsal[(int64_t)i * S + s] = I.k1[i];
         if (!(isfinite(T0[i]) && isfinite(theta[i]))) flags |= MC_STATUS_NAN;
@@ -1047,9 +1090,9 @@ static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
     d.niter_moist = (int)(3600.0 / md.moisture_timestep_s);
     const int N = md.n_soil;
     double ld[MC_MAX_SOIL_NODES + 1];
-    for (int i = 0; i < N; i++) { d.depths[i] = md.depths_m[i]; ld[i] = md.depths_m[i]; }
+    MC_ROLLED for (int i = 0; i < N; i++) { d.depths[i] = md.depths_m[i]; ld[i] = md.depths_m[i]; }
     ld[N] = 0.0;                                          /* zero sentinel (heat_transport_1d.jl:127,173) */
-    for (int i = 0; i < N; i++) {
+    MC_ROLLED for (int i = 0; i < N; i++) {
         d.dzc[i] = i == 0 ? ld[1] : ld[i + 1] - ld[i - 1];
         d.dzg[i] = ld[i + 1] - ld[i];
     }
