@@ -41,13 +41,13 @@ constexpr int BLOCK = MC_BLOCK;
 }  // namespace
 
 /* ---------------------------------------------------------------- kernels ---- */
-template <int NA>
+template <int NA, int NS>
 __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const mcd::KArgs a)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
     mcd::Counters cn = {};
-    mcd::solve_site<NA>(a, s, cn);
+    mcd::solve_site<NA, NS>(a, s, cn);
     if (a.counters) {
         atomicAdd(a.counters + 0, (unsigned long long)cn.n_rhs);
         atomicAdd(a.counters + 1, (unsigned long long)cn.n_accept);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
 }
 
 /* fresh state == what init() + the top of solve_soil! establish (reference src/simulation.jl:141-243,383-452) */
-__global__ void init_state_kernel(mcd::KArgs a, int N)
+__global__ void init_state_kernel(mcd::KArgs a, int N, int n_snow, mc_snow_desc sm)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
@@ -70,7 +70,15 @@ __global__ void init_state_kernel(mcd::KArgs a, int N)
         a.T[k] = a.has_init_T ? a.init_T[k] : qnan;
         a.theta[k] = a.init_theta[k];
         a.sum_phase[k] = 0.0;
-        a.fsal[k] = qnan;
+    }
+    for (int i = 0; i < N + n_snow; i++) a.fsal[(int64_t)i * a.S + s] = qnan;
+    if (n_snow > 0) {              /* init_snow_temperatures + initial_snow_state(model, depth, density) + reset_snow_scratch! */
+        for (int i = 0; i < n_snow; i++) { a.snow_T[(int64_t)i * a.S + s] = sm.initial_snow_temperature_K; a.snow_nd[(int64_t)i * a.S + s] = 0.0; }
+        const double dflt = sm.density_function[0] > 0.0 ? sm.density_function[1] : sm.snow_density;
+        const double d = sm.initial_snow_density > 0.0 ? sm.initial_snow_density : dflt;
+        const double v[MC_SNOW_STATE_FIELDS] = {sm.initial_snow_depth_cm, 0.0, 0.3, d, d, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < MC_SNOW_STATE_FIELDS; k++) a.snow_state[(int64_t)k * a.S + s] = v[k];
+        a.q_freeze[s] = 0.0;
     }
     a.pool[s] = 0.0; a.wetness[s] = 0.0; a.L_ode[s] = -0.3; a.L_prof[s] = -0.3; a.tdeep_prev[s] = qnan; a.flags[s] = 0;
 }
@@ -101,6 +109,8 @@ struct mc_handle {
     double* arena = nullptr; size_t arena_doubles = 0;
     double *z0, *slope, *svf, *albedo, *bd, *md, *lam_m, *c_m, *psi_e, *ks, *bb, *rootd, *init_T, *init_theta;
     double *T, *theta, *sum_phase, *pool, *wetness, *L_ode, *L_prof, *tdeep_prev, *fsal;
+    double *snow_T = nullptr, *snow_state = nullptr, *snow_nd = nullptr, *q_freeze = nullptr;
+    int32_t* doy_dev = nullptr; size_t doy_cap = 0;
     int32_t* flags = nullptr;
     unsigned long long* counters = nullptr;
     bool has_init_T = false, sites_set = false;
@@ -117,13 +127,13 @@ static int validate_model(const mc_model_desc* m, std::string& err)
 {
     if (!m) { err = "model is NULL"; return -1; }
     if (m->n_soil < 3 || m->n_soil > MC_MAX_SOIL_NODES) { err = "n_soil must be in 3.." + std::to_string(MC_MAX_SOIL_NODES); return -1; }
-    if (m->n_snow != 0) { err = "SnowModel (n_snow=8) is not implemented on the CUDA path yet"; return -3; }
+    if (m->n_snow != 0 && m->n_snow != MC_SNOW_NODES) { err = "n_snow must be 0 (NoSnow) or 8 (SnowModel)"; return -3; }
     if (!(m->moisture_timestep_s > 0.0) || m->moisture_timestep_s > 3600.0) { err = "moisture_timestep_s must be in (0, 3600]"; return -1; }
     for (int i = 1; i < m->n_soil; i++) if (!(m->depths_m[i] > m->depths_m[i - 1])) { err = "depths must be strictly increasing"; return -1; }
     return 0;
 }
 
-template <int NA>
+template <int NA, int NS>
 static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
 {
     const int grid = (int)((a.S + BLOCK - 1) / BLOCK);
@@ -131,9 +141,9 @@ static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
     if (pad < 0) {
         const char* e = getenv("MC_SMEM_PAD");
         pad = e ? atoi(e) : 0;
-        if (pad > 48 * 1024) cudaFuncSetAttribute(soil_chunk_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        if (pad > 48 * 1024) cudaFuncSetAttribute(soil_chunk_kernel<NA, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
     }
-    soil_chunk_kernel<NA><<<grid, BLOCK, pad, st>>>(a);
+    soil_chunk_kernel<NA, NS><<<grid, BLOCK, pad, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -145,6 +155,7 @@ static void fill_site_state_args(mc_handle* h, mcd::KArgs& a)
     a.psi_e = h->psi_e; a.ks = h->ks; a.bb = h->bb; a.rootd = h->rootd; a.init_T = h->init_T; a.init_theta = h->init_theta;
     a.T = h->T; a.theta = h->theta; a.sum_phase = h->sum_phase; a.pool = h->pool; a.wetness = h->wetness; a.L_ode = h->L_ode;
     a.L_prof = h->L_prof; a.tdeep_prev = h->tdeep_prev; a.fsal = h->fsal; a.flags = h->flags; a.counters = h->counters;
+    a.snow_T = h->snow_T; a.snow_state = h->snow_state; a.snow_nd = h->snow_nd; a.q_freeze = h->q_freeze;
 }
 
 /* ---------------------------------------------------------------- C ABI ---- */
@@ -207,8 +218,9 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
     const size_t S = (size_t)n_sites, N = (size_t)h->N;
+    const size_t NSn = (size_t)model->n_snow;
     const size_t per_site = 4 + 5, per_node = 8 + 2 + 4;
-    h->arena_doubles = S * (per_site + per_node * N);
+    h->arena_doubles = S * (per_site + per_node * N + (NSn ? NSn * 3 + MC_SNOW_STATE_FIELDS + 1 : 0));
     if ((e = cudaMalloc(&h->arena, h->arena_doubles * sizeof(double))) != cudaSuccess) return fail("cudaMalloc(state arena)", e);
     double* p = h->arena;
     auto take = [&](size_t n) { double* q = p; p += n; return q; };
@@ -216,7 +228,8 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     h->bd = take(N * S); h->md = take(N * S); h->lam_m = take(N * S); h->c_m = take(N * S);
     h->psi_e = take(N * S); h->ks = take(N * S); h->bb = take(N * S); h->rootd = take(N * S);
     h->init_T = take(N * S); h->init_theta = take(N * S);
-    h->T = take(N * S); h->theta = take(N * S); h->sum_phase = take(N * S); h->fsal = take(N * S);
+    h->T = take(N * S); h->theta = take(N * S); h->sum_phase = take(N * S); h->fsal = take((N + NSn) * S);
+    if (NSn) { h->snow_T = take(NSn * S); h->snow_nd = take(NSn * S); h->snow_state = take(MC_SNOW_STATE_FIELDS * S); h->q_freeze = take(S); }
     h->pool = take(S); h->wetness = take(S); h->L_ode = take(S); h->L_prof = take(S); h->tdeep_prev = take(S);
     if ((e = cudaMalloc(&h->flags, S * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
     if ((e = cudaMalloc(&h->counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
@@ -230,7 +243,7 @@ void mc_destroy(mc_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->arena); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out);
+    cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -254,7 +267,7 @@ int mc_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init
     if (h->has_init_T) MC_CUDA(h, cudaMemcpyAsync(h->init_T, init->initial_soil_temperature, bNS, cudaMemcpyHostToDevice, h->stream));
     MC_CUDA(h, cudaMemcpyAsync(h->init_theta, init->initial_soil_moisture, bNS, cudaMemcpyHostToDevice, h->stream));
     mcd::KArgs a; fill_site_state_args(h, a);
-    init_state_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(a, h->N);
+    init_state_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(a, h->N, h->model.n_snow, h->model.snow);
     MC_CUDA(h, cudaGetLastError());
     MC_CUDA(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), h->stream));
     MC_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -265,13 +278,15 @@ int mc_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init
 static int copy_state(mc_handle* h, const mc_state_soa* st, bool to_host)
 {
     MC_CUDA(h, cudaSetDevice(h->device));
-    const size_t S = (size_t)h->S, N = (size_t)h->N, bS = S * sizeof(double), bNS = N * bS;
+    const size_t S = (size_t)h->S, N = (size_t)h->N, NSn = (size_t)h->model.n_snow, bS = S * sizeof(double), bNS = N * bS;
     struct Item { double* host; double* dev; size_t bytes; };
-    const Item items[] = {{st->soil_temperature, h->T, bNS}, {st->soil_moisture, h->theta, bNS}, {st->sum_phase, h->sum_phase, bNS}, {st->fsal, h->fsal, bNS},
+    const Item items[] = {{st->soil_temperature, h->T, bNS}, {st->soil_moisture, h->theta, bNS}, {st->sum_phase, h->sum_phase, bNS}, {st->fsal, h->fsal, (N + NSn) * bS},
                           {st->pool, h->pool, bS}, {st->soil_wetness, h->wetness, bS}, {st->obukhov_ode, h->L_ode, bS}, {st->obukhov_profile, h->L_prof, bS},
-                          {st->deep_temperature_prev, h->tdeep_prev, bS}};
+                          {st->deep_temperature_prev, h->tdeep_prev, bS},
+                          {st->snow_temperature, h->snow_T, NSn * bS}, {st->snow_state, h->snow_state, MC_SNOW_STATE_FIELDS * bS},
+                          {st->snow_node_depths, h->snow_nd, NSn * bS}, {st->q_freeze, h->q_freeze, bS}};
     for (const Item& it : items) {
-        if (!it.host) continue;
+        if (!it.host || !it.dev) continue;
         if (to_host) MC_CUDA(h, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
         else MC_CUDA(h, cudaMemcpyAsync(it.dev, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
     }
@@ -310,10 +325,18 @@ int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forc
     a.d_tdeep = f->deep_soil_temperature; a.d_rain = f->rainfall_daily; a.d_albedo = f->albedo_daily; a.presc = f->prescribed_soil_moisture;
     a.o_T = o->soil_temperature; a.o_theta = o->soil_moisture; a.o_psi = o->soil_water_potential; a.o_h = o->soil_humidity;
     a.o_lam = o->soil_thermal_conductivity; a.o_cp = o->soil_heat_capacity; a.o_rho = o->soil_bulk_density; a.o_pool = o->surface_water; a.o_sky = o->sky_temperature;
+    a.o_snow_fall = o->snow_fall; a.o_snow_depth = o->snow_depth; a.o_snow_dens = o->snow_density; a.o_snow_T = o->snow_temperature;
+    if (f->day_of_year) {                /* MicroProblem.days: always a HOST pointer, staged here (used by the snow melt-factor / Q_freeze guards) */
+        if (h->doy_cap < (size_t)ndays) { if (h->doy_dev) MC_CUDA(h, cudaFree(h->doy_dev)); MC_CUDA(h, cudaMalloc(&h->doy_dev, (size_t)ndays * sizeof(int32_t))); h->doy_cap = (size_t)ndays; }
+        MC_CUDA(h, cudaMemcpyAsync(h->doy_dev, f->day_of_year, (size_t)ndays * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        a.doy = h->doy_dev;
+    }
     MC_CUDA(h, cudaMemcpyToSymbolAsync(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice, h->stream));
     MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     const int na = pick_na(h->N);
-    cudaError_t e = na == 10 ? launch_chunk<10>(a, h->stream) : (na == 19 ? launch_chunk<19>(a, h->stream) : launch_chunk<MC_MAX_SOIL_NODES>(a, h->stream));
+    cudaError_t e;
+    if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, h->stream) : (na == 19 ? launch_chunk<19, 0>(a, h->stream) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, h->stream));
+    else e = na == 10 ? launch_chunk<10, MC_SNOW_NODES>(a, h->stream) : (na == 19 ? launch_chunk<19, MC_SNOW_NODES>(a, h->stream) : launch_chunk<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, h->stream));
     MC_CUDA(h, e);
     MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->last_launches = 1;
@@ -369,23 +392,28 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     fd.day_of_year = f->day_of_year;
     /* stage outputs */
     double* node_host[7] = {o->soil_temperature, o->soil_moisture, o->soil_water_potential, o->soil_humidity, o->soil_thermal_conductivity, o->soil_heat_capacity, o->soil_bulk_density};
-    double* scal_host[2] = {o->surface_water, o->sky_temperature};
+    const size_t NSn = (size_t)h->model.n_snow;
+    double* scal_host[5] = {o->surface_water, o->sky_temperature, NSn ? o->snow_fall : nullptr, NSn ? o->snow_depth : nullptr, NSn ? o->snow_density : nullptr};
+    double* snowT_host = NSn ? o->snow_temperature : nullptr;
     size_t need_out = 0;
     for (double* q : node_host) if (q) need_out += H * N * S;
     for (double* q : scal_host) if (q) need_out += H * S;
+    if (snowT_host) need_out += H * NSn * S;
     if (int rc = ensure_stage(h, &h->stage_out, &h->stage_out_doubles, need_out ? need_out : 1)) return rc;
     mc_output_soa od; std::memset(&od, 0, sizeof(od));
     double** node_dev[7] = {&od.soil_temperature, &od.soil_moisture, &od.soil_water_potential, &od.soil_humidity, &od.soil_thermal_conductivity, &od.soil_heat_capacity, &od.soil_bulk_density};
-    double** scal_dev[2] = {&od.surface_water, &od.sky_temperature};
+    double** scal_dev[5] = {&od.surface_water, &od.sky_temperature, &od.snow_fall, &od.snow_depth, &od.snow_density};
     double* q = h->stage_out;
     for (int k = 0; k < 7; k++) if (node_host[k]) { *node_dev[k] = q; q += H * N * S; }
-    for (int k = 0; k < 2; k++) if (scal_host[k]) { *scal_dev[k] = q; q += H * S; }
+    for (int k = 0; k < 5; k++) if (scal_host[k]) { *scal_dev[k] = q; q += H * S; }
+    if (snowT_host) { od.snow_temperature = q; q += H * NSn * S; }
     /* cells the path never writes (e.g. water potential rows under PrescribedSoilMoisture) read back as zero */
     if (need_out) MC_CUDA(h, cudaMemsetAsync(h->stage_out, 0, need_out * sizeof(double), h->stream));
     int rc = mc_step_days_device(h, day0, ndays, &fd, &od);
     if (rc < 0) return rc;
     for (int k = 0; k < 7; k++) if (node_host[k]) MC_CUDA(h, cudaMemcpyAsync(node_host[k], *node_dev[k], H * N * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    for (int k = 0; k < 2; k++) if (scal_host[k]) MC_CUDA(h, cudaMemcpyAsync(scal_host[k], *scal_dev[k], H * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    for (int k = 0; k < 5; k++) if (scal_host[k]) MC_CUDA(h, cudaMemcpyAsync(scal_host[k], *scal_dev[k], H * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (snowT_host) MC_CUDA(h, cudaMemcpyAsync(snowT_host, od.snow_temperature, H * NSn * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     std::vector<int32_t> status_tmp;
     int32_t* status_host = o->status;
     if (!status_host) { status_tmp.resize(S); status_host = status_tmp.data(); }

@@ -76,6 +76,7 @@ struct DevModel {
     /* FluidProperties constants */
     double Mw, eps, dep, cpa, cpv, R, sigma, g, P0, Lv_a, Lv_b, Hv_a, Hv_b, Ma_over_R;
     double schmidt_factor;  /* (0.71/0.60)^0.666, monin_obukhov.jl:406-407 */
+    mc_snow_desc snow;      /* SnowModel (n_snow = 8) */
 };
 
 #if defined(__CUDACC__)
@@ -97,11 +98,14 @@ struct KArgs {
     /* carried state */
     double *T, *theta, *sum_phase, *pool, *wetness, *L_ode, *L_prof, *tdeep_prev, *fsal;
     int32_t* flags;
+    double *snow_T, *snow_state, *snow_nd, *q_freeze;     /* SnowModel: [8][S], [MC_SNOW_STATE_FIELDS][S], [8][S], [S] */
+    const int32_t* doy;                                   /* [ndays] day of year (device) */
     /* forcing (chunk-relative rows) */
     const double *f_P, *f_T, *f_wind, *f_rh, *f_cloud, *f_solar, *f_diffuse, *f_zen, *f_szen, *f_rain, *f_lw;
     const double *d_lai, *d_shade, *d_eps, *d_epsc, *d_wet, *d_tdeep, *d_rain, *d_albedo, *presc;
     /* outputs (NULL = deselected) */
     double *o_T, *o_theta, *o_psi, *o_h, *o_lam, *o_cp, *o_rho, *o_pool, *o_sky;
+    double *o_snow_fall, *o_snow_depth, *o_snow_dens, *o_snow_T;
     unsigned long long* counters;   /* [8]: rhs, accept, reject, obukhov, newton, infil, day_passes, spare */
 };
 
@@ -258,6 +262,7 @@ struct HourPar {            /* SoilEnergyInputs scalars (heat_transport_1d.jl:41
     double z0, lz, slope, svf;          /* lz = mcm::log(zref/z0) */
     const double *fP, *fT, *fwind, *frh, *fcloud, *fsolar, *fdiff, *fzen, *fszen;   /* this site's day: base[k*S] is knot k */
     int64_t S;
+    const struct SnowCtx* sn;           /* SnowModel context (NULL without snow) */
 };
 
 MC_DEV double knot_lerp(const double* base, int64_t S, int i, double d)
@@ -394,6 +399,367 @@ MC_DEV_NOINLINE void soil_rhs(const HourSoil<NA>& hs, const HourPar& hp, const d
     du[0] = 60.0 * (Q_solar + Q_ir + Q_cond + Qc + 0.0 /* Q_freeze: snow only */ - Qe) / hs.cap[0];
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Snow: SnowModel{8} (src/snow/snow_model.jl) + apparent-heat-capacity closures (src/apparent_heat_capacity/*.jl).
+ * Depths in cm, densities in g/cm3, as upstream.  The reference's snow_depth_hourly[nsteps] scratch array is only read
+ * at [step] and [step-1]; it is carried as two scalars (sd_cur, sd_prev).
+ * ------------------------------------------------------------------------------------------ */
+constexpr int NSN = MC_SNOW_NODES;
+struct SnowState { double depth, age, days_since, density, prev_density, cum_melt, extra, sum_phase; int active; };
+struct SnowScratch { double node_depths[NSN]; double sd_prev, sd_cur; double meanT[NSN], meanTpast[NSN]; };
+struct SnowCtx { SnowState st; SnowScratch sc; double depths[MC_MAX_ODE_NODES + 1]; double Q_freeze; const SnowState* rhs_state; };
+
+MC_DEV double mc_tanh(double x) { const double e = mcm::exp(2.0 * x); return x > 20.0 ? 1.0 : (x < -20.0 ? -1.0 : (e - 1.0) / (e + 1.0)); }
+MC_DEV_NOINLINE double apparent_heat_capacity(double T, double cp_base)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    const double Tc = T - T0C, Lf = LATENT_FUSION;
+    switch (sm.ahc_kind) {
+    case MC_AHC_TANH: {
+        const double lo = (Tc - sm.ahc_T_low_C) / sm.ahc_smoothing_K, hi = (Tc - sm.ahc_T_high_C) / sm.ahc_smoothing_K;
+        return cp_base + (Lf / sm.ahc_window_K) * (0.5 * (mc_tanh(lo) - mc_tanh(hi)));
+    }
+    case MC_AHC_GAUSSIAN: {
+        const double x = (Tc - sm.ahc_T_melt_C) / sm.ahc_width_K;
+        return cp_base + (Lf / (sm.ahc_width_K * sqrt(2.0 * PI_D))) * mcm::exp(-0.5 * x * x);
+    }
+    case MC_AHC_WESTERMANN: {
+        const double x = (Tc - sm.ahc_T_melt_C) / sm.ahc_width_K, th = mc_tanh(x);
+        return cp_base + (Lf / (2.0 * sm.ahc_width_K)) * (1.0 - th * th);
+    }
+    default:
+        if (Tc > sm.ahc_T_low_C && Tc <= sm.ahc_T_high_C) return cp_base + Lf / sm.ahc_window_K;
+        return cp_base;
+    }
+}
+MC_DEV SnowState initial_snow_state(double depth, double density_or_neg)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    const double dflt = sm.density_function[0] > 0.0 ? sm.density_function[1] : sm.snow_density;
+    const double d = density_or_neg > 0.0 ? density_or_neg : dflt;
+    SnowState st; st.depth = depth; st.age = 0.0; st.days_since = 0.3; st.density = d; st.prev_density = d;
+    st.cum_melt = 0.0; st.extra = 0.0; st.active = 0; st.sum_phase = 0.0;
+    return st;
+}
+MC_DEV double evolve_snow_density(const SnowState& st)
+{
+    const double* df = MC_CONST_MODEL.snow.density_function;
+    if (!(df[0] > 0.0)) return st.density;
+    if (df[2] > 0.0) return (df[0] - df[1]) * (1.0 - mcm::exp(-df[2] * st.depth - df[3] * st.age)) + df[1];
+    return jmin(0.9167, df[0] * st.age + df[1]);
+}
+MC_DEV double snow_albedo(double days_since) { return (-9.874 * mcm::log(jmax(days_since, 0.3)) + 78.3434) / 100.0; }
+MC_DEV double snow_specific_heat(double dens, double P)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const double e = goff_gratch(273.15) * 1.0;
+    const double mr = (m.eps * m.dep * e) / (P - m.dep * e);
+    return 2100.0 * dens + (1005.0 + 1820.0 * (mr / 1.0 + mr)) * (1.0 - dens);
+}
+MC_DEV_NOINLINE void activate_snow_nodes(SnowState& st, SnowScratch& sc, double& sd)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    const double cursnow = sd;
+    int active = st.active;
+    if (cursnow > 300.0) active = 0;
+    if (cursnow < sm.min_snow_depth_cm) {
+        MC_ROLLED for (int i = 0; i < NSN; i++) sc.node_depths[i] = 0.0;
+        sd = 0.0; st.active = 0; st.depth = 0.0;
+        return;
+    }
+    int maxsnode = 0;
+    MC_ROLLED for (int i = 1; i <= NSN; i++) if (cursnow > sm.node_thresholds_cm[i - 1]) maxsnode = i;
+    maxsnode = maxsnode < NSN - 1 ? maxsnode : NSN - 1;
+    MC_ROLLED for (int i = 1; i <= maxsnode; i++) sc.node_depths[i + (NSN - maxsnode) - 1] = sm.node_thresholds_cm[i - 1];
+    if (maxsnode < active) { MC_ROLLED for (int i = 1; i <= NSN - maxsnode; i++) sc.node_depths[i - 1] = 0.0; }
+    st.depth = cursnow; st.active = maxsnode;
+}
+MC_DEV void compute_effective_depths(const SnowState& st, const SnowScratch& sc, double* out)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const double off = st.depth >= m.snow.min_snow_depth_cm ? st.depth : 0.0;
+    MC_ROLLED for (int i = 0; i < NSN; i++) out[i] = sc.node_depths[i] / 100.0;
+    MC_ROLLED for (int i = 0; i < m.N; i++) out[NSN + i] = m.depths[i] + off / 100.0;
+}
+MC_DEV void snow_layer_geometry(const SnowState& st, const SnowScratch& sc, int layer_index, int& node_index, double& thickness)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    const int maxsnode = st.active;
+    int ni = layer_index + NSN - 1 - maxsnode; ni = ni > NSN ? NSN : ni; ni = ni < 1 ? 1 : ni;
+    if (layer_index != maxsnode + 1) {
+        int upper = layer_index + NSN - maxsnode; upper = upper < 1 ? 1 : upper;
+        thickness = sc.node_depths[upper - 1] - sc.node_depths[ni - 1];
+    } else {
+        thickness = jmax(0.0, st.depth - sm.node_thresholds_cm[(maxsnode > 1 ? maxsnode : 1) - 1]);
+    }
+    node_index = ni - 1;
+}
+MC_DEV_NOINLINE double snow_thermal_melt(const SnowState& st, SnowScratch& sc, const double* Ts, const double* Ts_before, double P, double T_soil, double T_soil_before)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    MC_ROLLED for (int i = 0; i < NSN; i++) {
+        const double below = i < NSN - 1 ? Ts[i + 1] : T_soil, below_past = i < NSN - 1 ? Ts_before[i + 1] : T_soil_before;
+        sc.meanT[i] = (Ts[i] + below) / 2.0 - T0C;
+        sc.meanTpast[i] = (Ts_before[i] + below_past) / 2.0 - T0C;
+    }
+    const double cp = snow_specific_heat(st.density, P);
+    double total = 0.0;
+    MC_ROLLED for (int j = 1; j <= st.active + 1; j++) {
+        int ni; double thick; snow_layer_geometry(st, sc, j, ni, thick);
+        const double mass = thick * st.density * 10.0;
+        if (sc.meanT[ni] > sm.melt_threshold_C) {
+            const double dT = sc.meanT[ni] - sm.melt_threshold_C;
+            const double sensible = dT * cp * mass, latent = LATENT_FUSION * mass;
+            total += (sensible + latent) / LATENT_FUSION;
+        }
+    }
+    return total / 10.0;
+}
+MC_DEV_NOINLINE void snow_phase_transition(SnowState& st, SnowScratch& sc, double* Ts, double P, double& T_soil_surface)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    if (st.depth >= 200.0) return;
+    if (st.depth < sm.min_snow_depth_cm) return;
+    const double cp = snow_specific_heat(st.density, P);
+    bool clamp_soil = false; bool clamp[NSN]; double phase_heat[NSN], layer_mass[NSN];
+    MC_ROLLED for (int i = 0; i < NSN; i++) { clamp[i] = false; phase_heat[i] = 0.0; layer_mass[i] = 0.0; }
+    MC_ROLLED for (int j = 1; j <= st.active + 1; j++) {
+        if (j > NSN) continue;
+        int ni; double thick; snow_layer_geometry(st, sc, j, ni, thick);
+        if (!(sc.node_depths[ni] > 0.0)) continue;
+        const double mass = thick * st.density * 10.0;
+        if (sc.meanTpast[ni] >= 0.0 && sc.meanT[ni] <= 0.0) {
+            layer_mass[ni] = jmax(0.0, mass);
+            phase_heat[ni] = (sc.meanTpast[ni] - sc.meanT[ni]) * cp * layer_mass[ni];
+            clamp[ni] = true;
+            if (ni == NSN - 1) clamp_soil = true; else clamp[ni + 1] = true;
+        }
+    }
+    double sp = 0.0, total_mass = 0.0;
+    MC_ROLLED for (int i = 0; i < NSN; i++) sp += phase_heat[i];
+    double new_sum = st.sum_phase + sp;
+    MC_ROLLED for (int i = 0; i < NSN; i++) total_mass += layer_mass[i];
+    if (total_mass > 0.0 && new_sum > LATENT_FUSION * total_mass) {
+        bool over[NSN]; MC_ROLLED for (int i = 0; i < NSN; i++) over[i] = false;
+        MC_ROLLED for (int i = 0; i < NSN; i++) if (clamp[i] && phase_heat[i] > 0.0) { over[i] = true; phase_heat[i] = 0.0; if (i < NSN - 1) over[i + 1] = true; }
+        MC_ROLLED for (int i = 0; i < NSN; i++) if (over[i]) Ts[i] = T0C - 0.5;
+        if (clamp_soil) T_soil_surface = T0C - 0.5;
+        new_sum = 0.0;
+    } else {
+        MC_ROLLED for (int i = 0; i < NSN; i++) if (clamp[i]) Ts[i] = T0C;
+        if (clamp_soil) T_soil_surface = T0C;
+    }
+    st.sum_phase = new_sum;
+}
+struct SnowUpdateOut { double snowfall, thermal_melt, rain_melt; };
+MC_DEV_NOINLINE SnowUpdateOut update_snow(SnowState& st, SnowScratch& sc, const double* Ts, const double* Ts_before, double T_air, double rainfall, double P,
+                                          int64_t step, double T_soil, double T_soil_before, double Q_evap, bool hourly, double shade, int day_of_year)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    const bool first = step == 1, midnight = ((step - 1) % 24) == 0;
+    const double prev_dens = st.density;
+    const double new_dens = evolve_snow_density(st);
+    const double ratio = new_dens / prev_dens;
+    if (step > 1 && ratio != 0.0 && isfinite(ratio)) sc.sd_prev /= ratio;
+    double snowfall = 0.0, days_since = st.days_since;
+    if (T_air - T0C <= sm.snow_temperature_threshold_C && rainfall > 0.0) {
+        if (midnight || hourly) {
+            snowfall = rainfall * sm.rain_multiplier * sm.undercatch / new_dens / 10.0;
+            if (shade > 0.0) snowfall *= (1.0 - sm.canopy_interception);
+            days_since = 0.3;
+        } else days_since += 1.0 / 25.0;
+    } else days_since += 1.0 / 25.0;
+    days_since = jmax(days_since, 0.3);
+    double sublimation = 0.0;
+    if (T_soil - T0C > 0.0 && Q_evap > 0.0) {
+        const double gw = Q_evap / latent_heat(T_soil);
+        sublimation = gw * 3600.0 / new_dens / 10.0;
+    }
+    const double previous_depth = step > 1 ? sc.sd_prev : st.depth;
+    double rain_melt = 0.0;
+    if (T_air - T0C >= sm.snow_temperature_threshold_C && rainfall > 0.0 && previous_depth >= sm.min_snow_depth_cm) {
+        if (midnight || hourly) {
+            const double water_depth = rainfall / WATER_RHO * 100.0;
+            rain_melt = sm.rain_melt_factor * water_depth * (T_air - T0C) * 24.0 / new_dens;
+            if (hourly) rain_melt /= 24.0;
+            rain_melt = jmax(0.0, rain_melt);
+        }
+    }
+    SnowState for_melt = st; for_melt.density = new_dens;
+    double thermal_melt;
+    if (first || previous_depth < sm.min_snow_depth_cm) {
+        snow_thermal_melt(for_melt, sc, Ts, Ts_before, P, T_soil, T_soil_before);
+        thermal_melt = 0.0;
+    } else {
+        const double raw = snow_thermal_melt(for_melt, sc, Ts, Ts_before, P, T_soil, T_soil_before);
+        thermal_melt = day_of_year > 1 ? raw * sm.snow_melt_factor : raw;
+    }
+    double cum_melt = st.cum_melt + thermal_melt;
+    if (step % 24 == 0) cum_melt = 0.0;
+    const double carried = st.extra / new_dens / 10.0;
+    const double net_acc = jmax(0.0, snowfall - sublimation) + carried;
+    double extra = 0.0;
+    double new_depth = jmax(0.0, previous_depth + net_acc - rain_melt - thermal_melt);
+    if (new_depth < sm.min_snow_depth_cm && (step <= 1 || sc.sd_prev < 1e-8)) { extra = new_depth * new_dens * 10.0; new_depth = 0.0; }
+    sc.sd_cur = new_depth;
+    double age;
+    if (first) age = 0.0;
+    else if (sc.sd_cur > 0.0 && sc.sd_prev > 0.0) age = st.age + 1.0 / 25.0;
+    else age = 0.0;
+    st.depth = new_depth; st.age = age; st.days_since = days_since; st.density = new_dens; st.prev_density = new_dens;
+    st.cum_melt = cum_melt; st.extra = extra;
+    SnowUpdateOut o; o.snowfall = snowfall; o.thermal_melt = thermal_melt; o.rain_melt = rain_melt;
+    return o;
+}
+MC_DEV_NOINLINE void adjust_snow_near_nodes(SnowState& st, SnowScratch& sc, int64_t step)
+{
+    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
+    double snowout = sc.sd_cur;
+    double threshold = sm.node_thresholds_cm[(st.active > 1 ? st.active : 1) - 1];
+    double extra = st.extra;
+    if (step > 1 && snowout > 0.0) {
+        if ((snowout - threshold < 0.5) && (snowout <= sc.sd_prev)) {
+            extra += (snowout - threshold) * st.density * 10.0;
+            sc.sd_cur = jmax(0.0, threshold - 0.1);
+        }
+    }
+    st.extra = extra;
+    activate_snow_nodes(st, sc, sc.sd_cur);
+    snowout = sc.sd_cur;
+    if (snowout > 0.0) {
+        threshold = sm.node_thresholds_cm[(st.active > 1 ? st.active : 1) - 1];
+        if (snowout < sm.min_snow_depth_cm + 0.5 || snowout < threshold + 0.5) {
+            extra = 0.5 * st.density * 10.0;
+            sc.sd_cur = threshold + 0.5;
+        }
+    }
+    st.extra = extra; st.depth = sc.sd_cur;
+}
+/* surface_convection_evaporation with its default zenith of 90 degrees (neutral branch), as the snow block calls it (simulation.jl:660-671) */
+MC_DEV_NOINLINE double neutral_surface_evaporation(double T_surf, double T_air, double wind, double rh, double P, double z0, double lz, double wetness)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const double dT = T_air - T_surf;
+    const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
+    const double ustar = jmax(m.kappa * wind / lz, 1.0e-6);
+    const double Qc = convective_flux(rho_cp, dT, ustar, 0.64 / lz, sublayer_stanton(z0, ustar));
+    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
+    const WetAir wa = wet_air(T_air, rh, P);
+    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
+    const double Tsc = T_surf < T_LO ? T_LO : T_surf;
+    return (wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
+}
+
+/* soil_energy_balance in its general form (snow nodes on top, first active node j, co-located nodes), heat_transport_1d.jl:137-302.
+ * hs.cap holds rho*c of the soil nodes (volumetric); depths change hourly with the snowpack. */
+template <int NA>
+MC_DEV_NOINLINE void soil_rhs_snow(const HourSoil<NA>& hs, const HourPar& hp, const double* __restrict__ u, double t, double* __restrict__ du, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL; const SnowCtx& sn = *hp.sn; const mc_snow_desc& sm = m.snow;
+    constexpr int ns = NSN; const int N = m.N; const int M = N + ns;
+    cn.n_rhs++;
+    const double xk = t / 60.0;
+    int ik = (int)floor(xk);
+    ik = ik < 0 ? 0 : (ik > 23 ? 23 : ik);
+    const double dk = xk - (double)ik;
+    const double P = knot_lerp(hp.fP, hp.S, ik, dk);
+    const double T_air = knot_lerp(hp.fT, hp.S, ik, dk);
+    const double wind = jmax(knot_lerp(hp.fwind, hp.S, ik, dk), 0.1);
+    const double zen = jmin(90.0, nearbyint(knot_lerp(hp.fzen, hp.S, ik, dk) * 1000.0) / 1000.0);
+    const double solar = jmax(0.0, knot_lerp(hp.fsolar, hp.S, ik, dk));
+    const double cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
+    const double rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
+    double T[NA + NSN], lam[NA + NSN], vhc[NA + NSN], C[NA + NSN], G[NA + NSN];
+    MC_ROLLED for (int i = 0; i < M; i++) T[i] = jclamp(u[i], T_LO, m.T_hi);
+    MC_ROLLED for (int i = 0; i < N; i++) {
+        lam[ns + i] = soil_conductivity(T[ns + i], P, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]);
+        vhc[ns + i] = hs.cap[i];
+    }
+    {   /* write_snow_properties!, snow_model.jl:171-208 */
+        const SnowState& st = *sn.rhs_state;
+        const double snowdens = evolve_snow_density(st);
+        if (st.depth >= sm.min_snow_depth_cm) {
+            const double cps = snow_specific_heat(snowdens, P);
+            double k;
+            if (sm.snow_conductivity > 0.0) k = sm.snow_conductivity;
+            else { const double r = snowdens * 1000.0; k = 0.00395 + 0.00084 * r - 1.7756e-6 * (r * r) + 3.80635e-9 * (r * r * r); }
+            MC_ROLLED for (int i = 0; i < ns; i++) {
+                lam[i] = k;
+                const double cpi = apparent_heat_capacity(T[i], cps);
+                const int nx = i + 1 < ns - 1 ? i + 1 : ns - 1;
+                const bool active = sn.sc.node_depths[i] > 0.0 || (i < ns - 1 && sn.sc.node_depths[nx] > 0.0);
+                vhc[i] = (active ? snowdens * 1000.0 : 0.0) * cpi;
+            }
+        } else {
+            /* snow nodes take the first soil node's conductivity and specific heat with zero density: rho*c = 0 */
+            MC_ROLLED for (int i = 0; i < ns; i++) { lam[i] = lam[ns]; vhc[i] = 0.0; }
+        }
+    }
+    const double* ld = sn.depths;                     /* ld[M] = 0 sentinel */
+    MC_ROLLED for (int i = 0; i < M; i++) {
+        if (i == 0) {
+            const double d2 = ld[1];
+            C[0] = vhc[0] * d2 / 2.0;
+            G[0] = d2 == 0.0 ? 0.0 : lam[0] / d2;
+        } else {
+            const double dd = ld[i + 1] - ld[i];
+            if (i < ns && ld[i] == 0.0 && ld[i + 1] != 0.0) C[i] = vhc[i] * ld[i + 1];
+            else C[i] = vhc[i] * (ld[i + 1] - ld[i - 1]) / 2.0;
+            const double pdd = ld[i] - ld[i - 1];
+            G[i] = dd == 0.0 ? (pdd == 0.0 ? 0.0 : lam[i] / pdd) : lam[i] / dd;
+        }
+    }
+    int j = 0; while (j < M - 1 && C[j] == 0.0) j++;
+    double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
+    if (hp.slope > 0.0 && zen < 90.0) {
+        const double szen = jmin(90.0, knot_lerp(hp.fszen, hp.S, ik, dk));
+        const double fd = jclamp(knot_lerp(hp.fdiff, hp.S, ik, dk), 0.0, 1.0);
+        const double cz = mcm::cos(zen * PI_D / 180.0), csz = mcm::cos(szen * PI_D / 180.0);
+        Q_solar = jmax(0.0, (((1.0 - fd) * Q_solar) / cz) * csz) + (fd * Q_solar) * hp.svf;
+    }
+    const WetAir wa = wet_air(T_air, rh, P);
+    const double atm = atmospheric_radiation(wa.vapour_pressure, T_air);
+    const double cloud_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air - 2.0);
+    const double hill_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air);
+    const double lw_sky = (atm * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - hp.shade);
+    const double incoming = (lw_sky + hp.shade * hill_rad) * hp.svf + hill_rad * (1.0 - hp.svf);
+    const double Q_ir = incoming - ((1.0 - hp.shade) * m.sigma * hp.eps_surf) * mcm::pow4(T[j]) - hp.shade * hill_rad;
+    const double cond_ref = (t == 0.0 && j > 0) ? T[0] : T[j];
+    const double Q_cond = j < M - 1 ? G[j] * (T[j + 1] - cond_ref) : 0.0;
+    double Ts = T[j];
+    if (fabs(Ts - T0C) > 100.0) Ts = T_air + 1.0;
+    if (Ts == T_air) Ts = Ts + 0.1;
+    const double dT = T_air - Ts;
+    const double rho_cp = calc_rho_cp((Ts + T_air) / 2.0);
+    double Qc;
+    if (T_air >= Ts || zen >= 90.0) {
+        const double ustar = jmax(m.kappa * wind / hp.lz, 1.0e-6);
+        Qc = convective_flux(rho_cp, dT, ustar, 0.64 / hp.lz, sublayer_stanton(hp.z0, ustar));
+    } else {
+        const Obukhov o = calc_obukhov(wind, hp.z0, m.zref, hp.lz, dT, rho_cp, hp.L_prev >= 0.0 ? -0.3 : hp.L_prev);
+        cn.n_obukhov += o.iters;
+        Qc = o.Q;
+    }
+    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
+    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
+    const double Tsc = Ts < T_LO ? T_LO : Ts;
+    const double Qe = (hp.soil_wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
+    const double surf = 60.0 * (Q_solar + Q_ir + Q_cond + Qc + sn.Q_freeze - Qe) / C[j];
+    MC_ROLLED for (int i = 0; i < M; i++) {
+        if (i <= j) du[i] = surf;
+        else if (i == M - 1) du[i] = 0.0;
+        else du[i] = C[i] == 0.0 ? 0.0 : 60.0 * (G[i - 1] * (T[i - 1] - T[i]) + G[i] * (T[i + 1] - T[i])) / C[i];
+    }
+}
+
+template <int NA, int NS>
+MC_DEV void rhs_dispatch(const HourSoil<NA>& hs, const HourPar& hp, const double* u, double t, double* du, Counters& cn)
+{
+    if (NS == 0) soil_rhs<NA>(hs, hp, u, t, du, cn);
+    else soil_rhs_snow<NA>(hs, hp, u, t, du, cn);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Adaptive Tsit5 with OrdinaryDiffEq's PI controller (third-party arithmetic restated; see the
  * oracle header for provenance).  Integrator state lives in thread-local arrays.
@@ -446,15 +812,15 @@ struct Integ {
 MC_DEV double rms_scaled(const double* x, const double* sk, int n) { double s = 0.0; MC_ROLLED for (int i = 0; i < n; i++) { const double q = x[i] / sk[i]; s += q * q; } return sqrt(s / n); }
 
 /* Hairer-Wanner automatic initial step (OrdinaryDiffEqCore initdt.jl), order 5 */
-template <int NA>
-MC_DEV_NOINLINE double determine_initdt(Integ<NA>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
+template <int NA, int NS>
+MC_DEV_NOINLINE double determine_initdt(Integ<NA + NS>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
 {
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N;
+    const DevModel& m = MC_CONST_MODEL; const int N = m.N + NS;       /* ODE size */
     double* sk = I.tmp; double* f0 = I.k2; double* f1 = I.k3; double* u1 = I.k4;
     double s0 = 0.0;
     MC_ROLLED for (int i = 0; i < N; i++) { sk[i] = m.abstol + fabs(I.u[i]) * m.reltol; const double q = I.u[i] / sk[i]; s0 += q * q; }
     const double d0 = sqrt(s0 / N);
-    soil_rhs<NA>(hs, hp, I.u, I.t, f0, cn);
+    rhs_dispatch<NA, NS>(hs, hp, I.u, I.t, f0, cn);
     bool finite = true;
     MC_ROLLED for (int i = 0; i < N; i++) if (!isfinite(f0[i])) finite = false;
     if (!finite) return 1e-12;
@@ -462,7 +828,7 @@ MC_DEV_NOINLINE double determine_initdt(Integ<NA>& I, const HourSoil<NA>& hs, co
     double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
     dt0 = fmin(dt0, 1440.0);
     MC_ROLLED for (int i = 0; i < N; i++) u1[i] = I.u[i] + dt0 * f0[i];
-    soil_rhs<NA>(hs, hp, u1, I.t + dt0, f1, cn);
+    rhs_dispatch<NA, NS>(hs, hp, u1, I.t + dt0, f1, cn);
     double s2 = 0.0;
     MC_ROLLED for (int i = 0; i < N; i++) { const double q = (f1[i] - f0[i]) / sk[i]; s2 += q * q; }
     const double d2 = sqrt(s2 / N) / dt0;
@@ -474,11 +840,11 @@ MC_DEV_NOINLINE double determine_initdt(Integ<NA>& I, const HourSoil<NA>& hs, co
 }
 
 /* one accepted step: loopheader!/perform_step!/loopfooter! until accepted */
-template <int NA>
-MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
+template <int NA, int NS>
+MC_DEV_NOINLINE void tsit5_step(Integ<NA + NS>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
 {
     using namespace tsit5;
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N;
+    const DevModel& m = MC_CONST_MODEL; const int N = m.N + NS;       /* ODE size */
     int guard = 0;
     for (;;) {
         if (I.iter > 0) {
@@ -487,7 +853,7 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
             } else {
                 MC_ROLLED for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
                 I.dt = I.dtpropose;
-                if (I.u_modified) soil_rhs<NA>(hs, hp, I.u, I.t, I.k1, cn);
+                if (I.u_modified) rhs_dispatch<NA, NS>(hs, hp, I.u, I.t, I.k1, cn);
                 else MC_ROLLED for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
             }
         } else if (I.u_modified) {
@@ -504,17 +870,17 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA>& I, const HourSoil<NA>& hs, const Hour
         }
         const double t = I.t, dt = I.dt;
         MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
-        soil_rhs<NA>(hs, hp, I.tmp, t + c1 * dt, I.k2, cn);
+        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c1 * dt, I.k2, cn);
         MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
-        soil_rhs<NA>(hs, hp, I.tmp, t + c2 * dt, I.k3, cn);
+        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c2 * dt, I.k3, cn);
         MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
-        soil_rhs<NA>(hs, hp, I.tmp, t + c3 * dt, I.k4, cn);
+        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c3 * dt, I.k4, cn);
         MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
-        soil_rhs<NA>(hs, hp, I.tmp, t + c4 * dt, I.k5, cn);
+        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c4 * dt, I.k5, cn);
         MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
-        soil_rhs<NA>(hs, hp, I.tmp, t + dt, I.k6, cn);
+        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + dt, I.k6, cn);
         MC_ROLLED for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
-        soil_rhs<NA>(hs, hp, I.u, t + dt, I.k7, cn);
+        rhs_dispatch<NA, NS>(hs, hp, I.u, t + dt, I.k7, cn);
         double ss = 0.0;
         MC_ROLLED for (int i = 0; i < N; i++) {
             const double ut = dt * (bt1 * I.k1[i] + bt2 * I.k2[i] + bt3 * I.k3[i] + bt4 * I.k4[i] + bt5 * I.k5[i] + bt6 * I.k6[i] + bt7 * I.k7[i]);
@@ -762,7 +1128,7 @@ MC_DEV EnvInstant get_instant(const SiteRef& r, int day, int row, double site_al
 template <int NA>
 MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, const double* T0, double* theta, double& pool,
                                        double soil_wetness, double z0, double& L_prof, double* psi_out, double* h_out,
-                                       int& flags, Counters& cn)
+                                       int& flags, Counters& cn, bool snow_present)
 {
     const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
     const int N = m.N, L = N;
@@ -804,7 +1170,8 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
     const double Tsc = T_surf < T_LO ? T_LO : T_surf;
     const double Qe = (hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);      /* saturated=true */
-    const double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
+    double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
+    if (snow_present) EPot = 1e-7;                                              /* campbell.jl:437-440 */
     (void)soil_wetness;
 
     /* per-hour constants of the implicit solve */
@@ -854,7 +1221,7 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
 
 
 /* theta-only soil property terms for the coming ODE hour (theta is constant while the ODE advances) */
-template <int NA>
+template <int NA, int NS>
 MC_DEV_NOINLINE void hoist_soil(const SiteRef& r, const double* theta, HourSoil<NA>& hs)
 {
     const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
@@ -863,7 +1230,7 @@ MC_DEV_NOINLINE void hoist_soil(const SiteRef& r, const double* theta, HourSoil<
         const double th = theta[i];
         const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
         const double rho = th * WATER_RHO + bd;
-        hs.cap[i] = (rho * cp) * m.dzc[i] / 2.0;
+        hs.cap[i] = NS == 0 ? (rho * cp) * m.dzc[i] / 2.0 : rho * cp;      /* with snow the node geometry changes hourly: keep rho*c */
         hs.theta[i] = th; hs.phim[i] = bd / md; hs.phig[i] = jmax(0.0, 1.0 - th - bd / md);
         hs.fw[i] = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
     }
@@ -907,28 +1274,44 @@ MC_DEV bool is_converged(int iter, int niter, const double* T0, const double* T0
 }
 
 /* ------------------------------------------------------------------------------------------
- * solve_soil! for days [day0, day0+ndays) of site s (simulation.jl:355-819)
+ * solve_soil! for days [day0, day0+ndays) of site s (simulation.jl:355-819).  NS = 0 (NoSnow) or 8 (SnowModel):
+ * with snow the ODE state is [T_snow(8); T_soil(N)] over hourly-changing effective depths.
  * ------------------------------------------------------------------------------------------ */
-template <int NA>
+template <int NA, int NS>
 MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
 {
     const DevModel& m = MC_CONST_MODEL;
     const int N = m.N;
+    constexpr int ns = NS;
+    constexpr bool snow = NS > 0;
     const int nrows = a.ndays * 24;
     const bool dynamic = m.dynamic != 0, nonconsec = m.nonconsec != 0;
     SiteRef r; r.a = &a; r.s = s;
     const int64_t S = a.S;
 
-    HourSoil<NA> hs; HourPar hp; Integ<NA> I;
+    HourSoil<NA> hs; HourPar hp; Integ<NA + NS> I; SnowCtx sn;
     double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_prev_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
     double psi_out[NA], h_out[NA];
+    double Ts[NSN], Ts_before[NSN], Ts_day_start[NSN];
     MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; hs.lam_m[i] = r.node(a.lam_m, i); }
     double pool = a.pool[s], wet_dyn = a.wetness[s], L_ode = a.L_ode[s], L_prof = a.L_prof[s], tdeep_stale = a.tdeep_prev[s];
     int flags = a.flags[s];
     const double site_albedo = MC_LDG(a.albedo + s);
     hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
+    hp.sn = snow ? &sn : nullptr;
     I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
-    MC_ROLLED for (int i = 0; i < N; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
+    MC_ROLLED for (int i = 0; i < N + ns; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
+    double sd_last = 0.0;
+    SnowState proto_state;
+    if (snow) {
+        MC_ROLLED for (int i = 0; i < NSN; i++) { Ts[i] = a.snow_T[(int64_t)i * S + s]; sn.sc.node_depths[i] = a.snow_nd[(int64_t)i * S + s]; sn.sc.meanT[i] = 0.0; sn.sc.meanTpast[i] = 0.0; }
+        const double* q = a.snow_state + s;
+        sn.st.depth = q[0]; sn.st.age = q[S]; sn.st.days_since = q[2 * S]; sn.st.density = q[3 * S]; sn.st.prev_density = q[4 * S];
+        sn.st.cum_melt = q[5 * S]; sn.st.extra = q[6 * S]; sn.st.active = (int)q[7 * S]; sn.st.sum_phase = q[8 * S]; sd_last = q[9 * S];
+        sn.sc.sd_prev = 0.0; sn.sc.sd_cur = 0.0;
+        sn.Q_freeze = a.q_freeze[s]; sn.rhs_state = &sn.st;
+        MC_ROLLED for (int i = 0; i <= N + ns; i++) sn.depths[i] = 0.0;
+    }
 
     auto set_day_forcing = [&](int jl) {
         const int64_t off = (int64_t)jl * 24 * S + s;
@@ -937,22 +1320,39 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
     };
     auto tins_mean = [&](int jl) { double ssum = 0.0; MC_ROLLED for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
     double sky_T = 0.0;
-    auto set_hour_params = [&](const EnvInstant& e) {
-        hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud; hp.albedo = e.albedo;
-        hp.soil_wetness = dynamic ? wet_dyn : e.wet_daily;
+    bool is_last = false;
+    /* apply_snow_overrides (simulation.jl:46-81) + per-hour parameter update */
+    auto set_hour_params = [&](const EnvInstant& e, int64_t gstep, double depth_prev_hour) {
+        hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud;
+        const bool snow_active = snow && is_last && ((gstep > 1 ? depth_prev_hour : sn.st.depth) > 0.0);
+        if (snow_active) { hp.albedo = snow_albedo(sn.st.days_since); hp.soil_wetness = 1.0; }
+        else { hp.albedo = e.albedo; hp.soil_wetness = dynamic ? wet_dyn : e.wet_daily; }
         sky_T = sky_temperature(hp.svf, e.P, e.rh, e.T_ref, e.eps_cloud, e.cloud, e.shade, a.has_lw != 0, e.lw);
     };
+    auto combine = [&](double* u) { MC_ROLLED for (int i = 0; i < ns; i++) u[i] = Ts[i]; MC_ROLLED for (int i = 0; i < N; i++) u[ns + i] = T0[i]; };
+    auto sync_inactive = [&]() { const double sy = Ts[0]; MC_ROLLED for (int k = 0; k < ns; k++) if (!(sn.sc.node_depths[k] > 0.0)) Ts[k] = sy; };
 
     EnvInstant env;
     if (a.day0 == 0) {
-        /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:224-238,853-860) */
+        /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:196-238,853-860) */
         set_day_forcing(0);
         env = get_instant(r, 0, 0, site_albedo);
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = a.has_init_T ? T0[i] : 280.0;
-        hoist_soil<NA>(r, theta, hs);
+        MC_ROLLED for (int i = 0; i < ns; i++) I.tmp[i] = m.snow.initial_snow_temperature_K;
+        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[ns + i] = a.has_init_T ? T0[i] : 280.0;
+        hoist_soil<NA, NS>(r, theta, hs);
         hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
-        Counters scratch = {};
-        soil_rhs<NA>(hs, hp, I.tmp, 0.0, I.k1, scratch);
+        if (snow) {           /* depths_proto = combined_depths(initial snow state) but p.snow_state = initial_snow_state(model) */
+            proto_state = initial_snow_state(0.0, -1.0);
+            compute_effective_depths(sn.st, sn.sc, sn.depths);
+            sn.rhs_state = &proto_state;
+            const double qf = sn.Q_freeze; sn.Q_freeze = 0.0;
+            Counters scratch = {};
+            rhs_dispatch<NA, NS>(hs, hp, I.tmp, 0.0, I.k1, scratch);
+            sn.rhs_state = &sn.st; sn.Q_freeze = qf;
+        } else {
+            Counters scratch = {};
+            rhs_dispatch<NA, NS>(hs, hp, I.tmp, 0.0, I.k1, scratch);
+        }
         /* solve_soil! pre-loop (simulation.jl:395-452) */
         if (!a.has_init_T) { const double t_init = tins_mean(0); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_init; }
         MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
@@ -962,31 +1362,38 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
         init_humidity(r, theta, T0);
         tdeep_stale = env.T_deep;
         pool = 0.0;
+        if (snow) sn.Q_freeze = 0.0;
     }
 
     for (int jl = 0; jl < a.ndays; jl++) {
         const int64_t j = a.day0 + jl;
+        const int doy = a.doy ? (int)MC_LDG(a.doy + jl) : (int)(j + 1);
         set_day_forcing(jl);
         const int niter = nonconsec ? m.iters_per_day : ((m.spinup && j == 0) ? m.conv_iters : 1);
         int noon_i = 0; double best = r.hourly(a.f_zen, jl * 24);
         MC_ROLLED for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
         const int midnight_i = (noon_i + 12) % 24;
-        if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516) */
+        if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516); the snowpack is NOT reset */
             MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
+            if (snow) sn.st.sum_phase = 0.0;
             if (!dynamic && a.has_presc) { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
-            else MC_ROLLED for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i);
-            if (!a.has_init_T) { const double t_reset = tins_mean(jl); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_reset; }
-            else MC_ROLLED for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i);
+            else { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i); }
+            const double t_reset = tins_mean(jl);
+            if (!a.has_init_T) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_reset; }
+            else { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i); }
+            MC_ROLLED for (int i = 0; i < ns; i++) Ts[i] = t_reset;
         }
         T0[N - 1] = tdeep_stale;
-        int iter = 0; bool is_last = false;
+        int iter = 0; is_last = false;
         MC_ROLLED for (int i = 0; i < N; i++) { T0_prev_start[i] = T0[i]; T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
+        MC_ROLLED for (int i = 0; i < ns; i++) Ts_day_start[i] = Ts[i];
         while (!is_last) {                                                    /* outer fixed point over day passes (simulation.jl:530) */
             iter++; cn.n_day_passes++;
             is_last = is_converged(iter, niter, T0, T0_prev_start, N);
             MC_ROLLED for (int i = 0; i < N; i++) T0_prev_start[i] = T0[i];
-            if (!nonconsec) MC_ROLLED for (int i = 0; i < N; i++) T0[i] = T0_day_start[i];
+            if (!nonconsec) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = T0_day_start[i]; MC_ROLLED for (int i = 0; i < ns; i++) Ts[i] = Ts_day_start[i]; }
             MC_ROLLED for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
+            if (snow && nonconsec) sn.st.sum_phase = 0.0;
             const int day_row = jl * 24;
             if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
                 MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
@@ -999,46 +1406,83 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
             }
             env = get_instant(r, jl, day_row, site_albedo);
             T0[N - 1] = env.T_deep;
-            set_hour_params(env);
+            set_hour_params(env, a.day0 * 24 + day_row + 1, sd_last);
+            if (snow) {
+                if (!is_last) { double tmp = sn.st.depth; activate_snow_nodes(sn.st, sn.sc, tmp); }
+                compute_effective_depths(sn.st, sn.sc, sn.depths);
+                int fa = -1; MC_ROLLED for (int k = ns - 1; k >= 0; k--) if (sn.sc.node_depths[k] > 0.0) fa = k;
+                const double sync_temp = fa < 0 ? T0[0] : Ts[fa];
+                MC_ROLLED for (int k = 0; k < ns; k++) if (fa < 0 || k < fa) Ts[k] = sync_temp;       /* _sync_snow_to_active */
+            }
             hp.L_prev = L_ode;
-            hoist_soil<NA>(r, theta, hs);
+            hoist_soil<NA, NS>(r, theta, hs);
             /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
-            MC_ROLLED for (int i = 0; i < N; i++) { I.u[i] = T0[i]; I.uprev[i] = T0[i]; }
+            combine(I.u);
+            MC_ROLLED for (int i = 0; i < N + ns; i++) I.uprev[i] = I.u[i];
             I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
-            I.dt = determine_initdt<NA>(I, hs, hp, cn);
-            MC_ROLLED for (int i = 0; i < 24; i++) {
+            I.dt = determine_initdt<NA, NS>(I, hs, hp, cn);
+            for (int i = 0; i < 24; i++) {
                 const int step = jl * 24 + i;
+                const int64_t gstep = a.day0 * 24 + step + 1;
                 MC_ROLLED for (int k = 0; k < N; k++) T0_before[k] = T0[k];
-                if (i > 0) hoist_soil<NA>(r, theta, hs);
+                MC_ROLLED for (int k = 0; k < ns; k++) Ts_before[k] = Ts[k];
+                if (i > 0) hoist_soil<NA, NS>(r, theta, hs);
                 hp.L_prev = L_ode;
                 /* step_to_hour! (simulation.jl:888-903) */
                 const double target = (i + 1) * 60.0;
                 I.tstop = target;
                 while (I.t < target - 1e-10) {
-                    tsit5_step<NA>(I, hs, hp, cn);
+                    tsit5_step<NA, NS>(I, hs, hp, cn);
                     bool changed = false;
-                    MC_ROLLED for (int k = 0; k < N; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
-                    if (changed) { MC_ROLLED for (int k = 0; k < N; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
+                    MC_ROLLED for (int k = 0; k < N + ns; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
+                    if (changed) { MC_ROLLED for (int k = 0; k < N + ns; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
                 }
-                MC_ROLLED for (int k = 0; k < N; k++) T0[k] = I.u[k];
+                MC_ROLLED for (int k = 0; k < ns; k++) Ts[k] = I.u[k];
+                MC_ROLLED for (int k = 0; k < N; k++) T0[k] = I.u[ns + k];
                 if (is_last) {
                     phase_transition(N, m.depths, T0, T0_before, sum_phase, theta);
                     MC_ROLLED for (int k = 0; k < N; k++) T0_output[k] = T0[k];
                 }
+                double snowfall_hour = 0.0, thermal_melt = 0.0, rain_melt_snow = 0.0;
+                if (snow && is_last) {                                        /* snow post-ODE block (simulation.jl:656-708) */
+                    sn.sc.sd_prev = sd_last;
+                    const double Qe = neutral_surface_evaporation(T0[0], env.T_ref, env.wind, env.rh, env.P, hp.z0, hp.lz, hp.soil_wetness);
+                    const SnowUpdateOut so = update_snow(sn.st, sn.sc, Ts, Ts_before, env.T_ref, env.rain_daily, env.P, gstep, T0[0], T0_before[0], Qe,
+                                                         m.rain_hourly != 0, env.shade, doy);
+                    snowfall_hour = so.snowfall; thermal_melt = so.thermal_melt; rain_melt_snow = so.rain_melt;
+                    if (doy > 1 && m.snow.snow_melt_factor <= 1.0) sn.Q_freeze = thermal_melt * 10.0 * LATENT_FUSION / 3600.0 * (1.0 - m.snow.snow_melt_factor);
+                    else sn.Q_freeze = 0.0;
+                    int prev_active = sn.st.active;
+                    activate_snow_nodes(sn.st, sn.sc, sn.sc.sd_cur);
+                    if (sn.st.active < prev_active) sync_inactive();
+                    double soil_surf = T0[0];
+                    snow_phase_transition(sn.st, sn.sc, Ts, env.P, soil_surf);      /* soil-surface clamp deliberately not applied upstream */
+                    MC_ROLLED for (int k = 0; k < ns; k++) if (sn.sc.node_depths[k] > 0.0 && Ts[k] > T0C) Ts[k] = T0C;     /* clamp_snow_temperatures */
+                    /* freeze_new_snow selects an empty index range upstream: no-op */
+                    adjust_snow_near_nodes(sn.st, sn.sc, gstep);
+                    prev_active = sn.st.active;
+                    activate_snow_nodes(sn.st, sn.sc, sn.sc.sd_cur);
+                    if (sn.st.active < prev_active) sync_inactive();
+                    sd_last = sn.sc.sd_cur;
+                }
                 if (i < 23) {
                     env = get_instant(r, jl, step + 1, site_albedo);
                     T0[N - 1] = env.T_deep;
-                    set_hour_params(env);
+                    set_hour_params(env, gstep + 1, sd_last);
+                    if (snow) {
+                        if (!is_last) { double tmp = sn.st.depth; activate_snow_nodes(sn.st, sn.sc, tmp); }
+                        compute_effective_depths(sn.st, sn.sc, sn.depths);
+                    }
                 }
-                MC_ROLLED for (int k = 0; k < N; k++) I.u[k] = T0[k];
+                combine(I.u);
                 I.u_modified = true;
                 {   /* init_surface_fluxes! (monin_obukhov.jl:247-264): hourly warm start of the Obukhov length */
                     const double T_air = MC_LDG(hp.fT + (int64_t)i * S);
                     const double wind = jmax(MC_LDG(hp.fwind + (int64_t)i * S), 0.1);
                     const double zen = jmin(90.0, nearbyint(MC_LDG(hp.fzen + (int64_t)i * S) * 1000.0) / 1000.0);
-                    const double Ts = T0[0];
-                    if (T_air < Ts && zen < 90.0) {
-                        const Obukhov ob = calc_obukhov(wind, hp.z0, m.zref, hp.lz, T_air - Ts, calc_rho_cp((Ts + T_air) / 2.0), L_ode >= 0.0 ? -0.3 : L_ode);
+                    const double Tsf = T0[0];
+                    if (T_air < Tsf && zen < 90.0) {
+                        const Obukhov ob = calc_obukhov(wind, hp.z0, m.zref, hp.lz, T_air - Tsf, calc_rho_cp((Tsf + T_air) / 2.0), L_ode >= 0.0 ? -0.3 : L_ode);
                         cn.n_obukhov += ob.iters;
                         L_ode = ob.L;
                     }
@@ -1048,9 +1492,18 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
                     double rain;
                     if (m.rain_hourly) rain = r.hourly(a.f_rain, step);
                     else rain = (i == midnight_i) ? env.rain_daily : 0.0;
-                    pool = jclamp(pool + rain, 0.0, m.max_pool);
+                    bool snow_present = false;
+                    if (snow) {
+                        rain = rain * m.snow.rain_multiplier;
+                        snow_present = sn.sc.sd_cur > 0.0;
+                        const double melted_water = thermal_melt * 10.0, rain_melt_water = rain_melt_snow * sn.st.density * 10.0;
+                        if (snow_present && env.T_ref - T0C < m.snow.snow_temperature_threshold_C) pool = jclamp(pool + melted_water, 0.0, m.max_pool);
+                        else pool = jclamp(pool + rain + rain_melt_water + melted_water, 0.0, m.max_pool);
+                    } else {
+                        pool = jclamp(pool + rain, 0.0, m.max_pool);
+                    }
                     if (dynamic) {
-                        wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn);
+                        wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn, snow_present);
                         have_infil = true;
                     }
                 }
@@ -1059,8 +1512,14 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
                     r.put_scalar(a.o_pool, out_row, pool);
                     MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
                     r.put_scalar(a.o_sky, out_row, sky_T);
-                    if (have_infil) MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); }
+                    if (have_infil) { MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); } }
                     write_props(r, out_row, T0, theta, r.hourly(a.f_P, out_row));
+                }
+                if (is_last && snow) {                                        /* snow outputs are recorded at `step` (simulation.jl:803-813) */
+                    r.put_scalar(a.o_snow_fall, step, snowfall_hour);
+                    r.put_scalar(a.o_snow_depth, step, sn.sc.sd_cur);
+                    r.put_scalar(a.o_snow_dens, step, evolve_snow_density(sn.st));
+                    if (a.o_snow_T) { MC_ROLLED for (int k = 0; k < ns; k++) a.o_snow_T[((int64_t)step * ns + k) * S + s] = Ts[k]; }
                 }
             }
         }
@@ -1068,11 +1527,18 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
     }
     MC_ROLLED for (int i = 0; i < N; i++) {
         a.T[(int64_t)i * S + s] = T0[i]; a.theta[(int64_t)i * S + s] = theta[i]; a.sum_phase[(int64_t)i * S + s] = sum_phase[i];
-        a.fsal[(int64_t)i * S + s] = I.k1[i];
         if (!(isfinite(T0[i]) && isfinite(theta[i]))) flags |= MC_STATUS_NAN;
     }
+    MC_ROLLED for (int i = 0; i < N + ns; i++) a.fsal[(int64_t)i * S + s] = I.k1[i];
     a.pool[s] = pool; a.wetness[s] = wet_dyn; a.L_ode[s] = L_ode; a.L_prof[s] = L_prof; a.tdeep_prev[s] = tdeep_stale;
     a.flags[s] = flags | I.flags;
+    if (snow) {
+        MC_ROLLED for (int i = 0; i < NSN; i++) { a.snow_T[(int64_t)i * S + s] = Ts[i]; a.snow_nd[(int64_t)i * S + s] = sn.sc.node_depths[i]; }
+        double* q = a.snow_state + s;
+        q[0] = sn.st.depth; q[S] = sn.st.age; q[2 * S] = sn.st.days_since; q[3 * S] = sn.st.density; q[4 * S] = sn.st.prev_density;
+        q[5 * S] = sn.st.cum_melt; q[6 * S] = sn.st.extra; q[7 * S] = (double)sn.st.active; q[8 * S] = sn.st.sum_phase; q[9 * S] = sd_last;
+        a.q_freeze[s] = sn.Q_freeze;
+    }
 }
 
 /* host side: flatten mc_model_desc into DevModel (run once per handle) */
@@ -1109,6 +1575,7 @@ static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
     d.P0 = f.standard_pressure; d.Lv_a = f.latent_heat_a; d.Lv_b = f.latent_heat_b; d.Hv_a = f.molar_latent_heat_a; d.Hv_b = f.molar_latent_heat_b;
     d.Ma_over_R = f.molar_mass_air / f.gas_constant;
     d.schmidt_factor = mcm::pow(0.71 / 0.60, 0.666);
+    d.snow = md.snow;
 }
 
 

@@ -292,6 +292,246 @@ static double sky_temperature(const mc_model_desc& m, double svf, double P, doub
     return mcm::pow(incoming / sigma, 0.25);
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Snow: SnowModel{8} (src/snow/snow_model.jl) and the apparent-heat-capacity closures
+ * (src/apparent_heat_capacity/*.jl).  Depths in cm, densities in g/cm3, as upstream.
+ * The reference's `snow_depth_hourly[nsteps]` scratch array is only ever read at [step] and
+ * [step-1]; it is carried as two scalars (sd_cur, sd_prev).
+ * ------------------------------------------------------------------------------------------ */
+static const int NSN = MC_SNOW_NODES;
+struct SnowState { double depth, age, days_since, density, prev_density, cum_melt, extra, sum_phase; int active; };
+struct SnowScratch { double node_depths[NSN]; double sd_prev, sd_cur; double meanT[NSN], meanTpast[NSN]; };
+
+/* apparent_heat_capacity(::BonacinaStep / TanhSmoothed / Gaussian / WestermannSigmoid, T, cp_base, L_fusion) */
+static inline double mc_tanh(double x) { const double e = mcm::exp(2.0 * x); return x > 20.0 ? 1.0 : (x < -20.0 ? -1.0 : (e - 1.0) / (e + 1.0)); }
+static double apparent_heat_capacity(const mc_snow_desc& sm, double T, double cp_base)
+{
+    const double Tc = T - T0C, Lf = LATENT_HEAT_FUSION;
+    switch (sm.ahc_kind) {
+    case MC_AHC_TANH: {                                                         /* tanh.jl:40-49 */
+        const double lo = (Tc - sm.ahc_T_low_C) / sm.ahc_smoothing_K, hi = (Tc - sm.ahc_T_high_C) / sm.ahc_smoothing_K;
+        return cp_base + (Lf / sm.ahc_window_K) * (0.5 * (mc_tanh(lo) - mc_tanh(hi)));
+    }
+    case MC_AHC_GAUSSIAN: {                                                     /* gaussian.jl:31-38 */
+        const double x = (Tc - sm.ahc_T_melt_C) / sm.ahc_width_K;
+        return cp_base + (Lf / (sm.ahc_width_K * std::sqrt(2.0 * M_PI))) * mcm::exp(-0.5 * x * x);
+    }
+    case MC_AHC_WESTERMANN: {                                                   /* westermann.jl:35-43 */
+        const double x = (Tc - sm.ahc_T_melt_C) / sm.ahc_width_K, th = mc_tanh(x);
+        return cp_base + (Lf / (2.0 * sm.ahc_width_K)) * (1.0 - th * th);
+    }
+    default:                                                                    /* bonacina.jl:30-36 */
+        if (Tc > sm.ahc_T_low_C && Tc <= sm.ahc_T_high_C) return cp_base + Lf / sm.ahc_window_K;
+        return cp_base;
+    }
+}
+
+static SnowState initial_snow_state(const mc_snow_desc& sm, double depth, double density_or_neg)     /* snow_model.jl:63-74 */
+{
+    const double dflt = sm.density_function[0] > 0.0 ? sm.density_function[1] : sm.snow_density;
+    const double d = density_or_neg > 0.0 ? density_or_neg : dflt;
+    SnowState st; st.depth = depth; st.age = 0.0; st.days_since = 0.3; st.density = d; st.prev_density = d;
+    st.cum_melt = 0.0; st.extra = 0.0; st.active = 0; st.sum_phase = 0.0;
+    return st;
+}
+static double evolve_snow_density(const mc_snow_desc& sm, const SnowState& st)                        /* :277-288 */
+{
+    const double* df = sm.density_function;
+    if (!(df[0] > 0.0)) return st.density;
+    if (df[2] > 0.0) return (df[0] - df[1]) * (1.0 - mcm::exp(-df[2] * st.depth - df[3] * st.age)) + df[1];
+    return jmin(0.9167, df[0] * st.age + df[1]);
+}
+static inline double snow_albedo(double days_since) { return (-9.874 * mcm::log(jmax(days_since, 0.3)) + 78.3434) / 100.0; }   /* :268-270 */
+static double snow_specific_heat(const mc_fluid_constants& fc, double dens, double P)                 /* :323-329 */
+{
+    const double mr = wet_air(fc, 273.15, 1.0, P).mixing_ratio;
+    return 2100.0 * dens + (1005.0 + 1820.0 * (mr / 1.0 + mr)) * (1.0 - dens);
+}
+/* activate_snow_nodes!, :108-142.  `sd` is snow_depth_hourly[step]. */
+static void activate_snow_nodes(const mc_snow_desc& sm, SnowState& st, SnowScratch& sc, double& sd)
+{
+    const double cursnow = sd;
+    int active = st.active;
+    if (cursnow > 300.0) active = 0;
+    if (cursnow < sm.min_snow_depth_cm) {
+        for (int i = 0; i < NSN; i++) sc.node_depths[i] = 0.0;
+        sd = 0.0; st.active = 0; st.depth = 0.0;
+        return;
+    }
+    int maxsnode = 0;
+    for (int i = 1; i <= NSN; i++) if (cursnow > sm.node_thresholds_cm[i - 1]) maxsnode = i;
+    maxsnode = std::min(maxsnode, NSN - 1);
+    for (int i = 1; i <= maxsnode; i++) sc.node_depths[i + (NSN - maxsnode) - 1] = sm.node_thresholds_cm[i - 1];
+    if (maxsnode < active) for (int i = 1; i <= NSN - maxsnode; i++) sc.node_depths[i - 1] = 0.0;
+    st.depth = cursnow; st.active = maxsnode;
+}
+/* compute_effective_depths!, :155-167 (metres) */
+static void compute_effective_depths(const mc_snow_desc& sm, const SnowState& st, const SnowScratch& sc, const double* soil_depths, int N, double* out)
+{
+    const double off = st.depth >= sm.min_snow_depth_cm ? st.depth : 0.0;
+    for (int i = 0; i < NSN; i++) out[i] = sc.node_depths[i] / 100.0;
+    for (int i = 0; i < N; i++) out[NSN + i] = soil_depths[i] + off / 100.0;
+}
+/* snow_layer_geometry, :304-317 (1-based layer_index; returns 0-based node index) */
+static void snow_layer_geometry(const mc_snow_desc& sm, const SnowState& st, const SnowScratch& sc, int layer_index, int& node_index, double& thickness)
+{
+    const int maxsnode = st.active;
+    const int ni = std::max(1, std::min(NSN, layer_index + NSN - 1 - maxsnode));
+    if (layer_index != maxsnode + 1) {
+        const int upper = std::max(1, layer_index + NSN - maxsnode);
+        thickness = sc.node_depths[upper - 1] - sc.node_depths[ni - 1];
+    } else {
+        thickness = jmax(0.0, st.depth - sm.node_thresholds_cm[std::max(1, maxsnode) - 1]);
+    }
+    node_index = ni - 1;
+}
+/* snow_thermal_melt!, :333-365 -> cm of water; fills meanT / meanTpast (degC) */
+static double snow_thermal_melt(const mc_model_desc& m, const SnowState& st, SnowScratch& sc, const double* Ts, const double* Ts_before,
+                                double P, double T_soil, double T_soil_before)
+{
+    const mc_snow_desc& sm = m.snow;
+    for (int i = 0; i < NSN; i++) {
+        const double below = i < NSN - 1 ? Ts[i + 1] : T_soil, below_past = i < NSN - 1 ? Ts_before[i + 1] : T_soil_before;
+        sc.meanT[i] = (Ts[i] + below) / 2.0 - T0C;
+        sc.meanTpast[i] = (Ts_before[i] + below_past) / 2.0 - T0C;
+    }
+    const double cp = snow_specific_heat(m.fluid, st.density, P);
+    double total = 0.0;                                                       /* kg/m2 */
+    for (int j = 1; j <= st.active + 1; j++) {
+        int ni; double thick; snow_layer_geometry(sm, st, sc, j, ni, thick);
+        const double mass = thick * st.density * 10.0;                        /* cm * g/cm3 -> kg/m2 */
+        if (sc.meanT[ni] > sm.melt_threshold_C) {
+            const double dT = sc.meanT[ni] - sm.melt_threshold_C;
+            const double sensible = dT * cp * mass, latent = LATENT_HEAT_FUSION * mass;
+            total += (sensible + latent) / LATENT_HEAT_FUSION;
+        }
+    }
+    return total / 10.0;                                                      /* kg/m2 of water / (1 g/cm3) -> cm */
+}
+/* snow_phase_transition, :369-467 */
+static void snow_phase_transition(const mc_model_desc& m, SnowState& st, SnowScratch& sc, double* Ts, double P, double& T_soil_surface)
+{
+    const mc_snow_desc& sm = m.snow;
+    if (st.depth >= 200.0) return;
+    if (st.depth < sm.min_snow_depth_cm) return;
+    const double cp = snow_specific_heat(m.fluid, st.density, P);
+    bool clamp_soil = false; bool clamp[NSN]; double phase_heat[NSN], layer_mass[NSN];
+    for (int i = 0; i < NSN; i++) { clamp[i] = false; phase_heat[i] = 0.0; layer_mass[i] = 0.0; }
+    for (int j = 1; j <= st.active + 1; j++) {
+        if (j > NSN) continue;
+        int ni; double thick; snow_layer_geometry(sm, st, sc, j, ni, thick);
+        if (!(sc.node_depths[ni] > 0.0)) continue;
+        const double mass = thick * st.density * 10.0;
+        if (sc.meanTpast[ni] >= 0.0 && sc.meanT[ni] <= 0.0) {
+            layer_mass[ni] = jmax(0.0, mass);
+            phase_heat[ni] = (sc.meanTpast[ni] - sc.meanT[ni]) * cp * layer_mass[ni];
+            clamp[ni] = true;
+            if (ni == NSN - 1) clamp_soil = true; else clamp[ni + 1] = true;
+        }
+    }
+    double new_sum = st.sum_phase, total_mass = 0.0;
+    { double sp = 0.0; for (int i = 0; i < NSN; i++) sp += phase_heat[i]; new_sum = st.sum_phase + sp; }
+    for (int i = 0; i < NSN; i++) total_mass += layer_mass[i];
+    if (total_mass > 0.0 && new_sum > LATENT_HEAT_FUSION * total_mass) {
+        bool over[NSN]; for (int i = 0; i < NSN; i++) over[i] = false;
+        for (int i = 0; i < NSN; i++) if (clamp[i] && phase_heat[i] > 0.0) { over[i] = true; phase_heat[i] = 0.0; if (i < NSN - 1) over[i + 1] = true; }
+        for (int i = 0; i < NSN; i++) if (over[i]) Ts[i] = T0C - 0.5;
+        if (clamp_soil) T_soil_surface = T0C - 0.5;
+        new_sum = 0.0;
+    } else {
+        for (int i = 0; i < NSN; i++) if (clamp[i]) Ts[i] = T0C;
+        if (clamp_soil) T_soil_surface = T0C;
+    }
+    st.sum_phase = new_sum;
+}
+struct SnowUpdateOut { double snowfall, thermal_melt, rain_melt; };
+/* update_snow!, :471-594.  `step` is the 1-based global hour index. */
+static SnowUpdateOut update_snow(const mc_model_desc& m, SnowState& st, SnowScratch& sc, const double* Ts, const double* Ts_before,
+                                 double T_air, double rainfall, double P, int64_t step, double T_soil, double T_soil_before, double Q_evap,
+                                 bool hourly, double shade, int day_of_year)
+{
+    const mc_snow_desc& sm = m.snow;
+    const bool first = step == 1, midnight = ((step - 1) % 24) == 0;
+    const double prev_dens = st.density;
+    const double new_dens = evolve_snow_density(sm, st);
+    const double ratio = new_dens / prev_dens;
+    if (step > 1 && ratio != 0.0 && std::isfinite(ratio)) sc.sd_prev /= ratio;
+    double snowfall = 0.0, days_since = st.days_since;
+    if (T_air - T0C <= sm.snow_temperature_threshold_C && rainfall > 0.0) {
+        if (midnight || hourly) {
+            snowfall = rainfall * sm.rain_multiplier * sm.undercatch / new_dens / 10.0;        /* kg/m2 / (g/cm3) -> cm */
+            if (shade > 0.0) snowfall *= (1.0 - sm.canopy_interception);
+            days_since = 0.3;
+        } else days_since += 1.0 / 25.0;
+    } else days_since += 1.0 / 25.0;
+    days_since = jmax(days_since, 0.3);
+    double sublimation = 0.0;
+    if (T_soil - T0C > 0.0 && Q_evap > 0.0) {
+        const double gw = Q_evap / enthalpy_of_vaporisation(m.fluid, T_soil);                   /* kg/s/m2 */
+        sublimation = gw * 3600.0 / new_dens / 10.0;
+    }
+    const double previous_depth = step > 1 ? sc.sd_prev : st.depth;
+    double rain_melt = 0.0;
+    if (T_air - T0C >= sm.snow_temperature_threshold_C && rainfall > 0.0 && previous_depth >= sm.min_snow_depth_cm) {
+        if (midnight || hourly) {
+            const double water_depth = rainfall / WATER_DENSITY * 100.0;                         /* cm */
+            rain_melt = sm.rain_melt_factor * water_depth * (T_air - T0C) * 24.0 / new_dens;
+            if (hourly) rain_melt /= 24.0;
+            rain_melt = jmax(0.0, rain_melt);
+        }
+    }
+    SnowState for_melt = st; for_melt.density = new_dens;
+    double thermal_melt;
+    if (first || previous_depth < sm.min_snow_depth_cm) {
+        snow_thermal_melt(m, for_melt, sc, Ts, Ts_before, P, T_soil, T_soil_before);
+        thermal_melt = 0.0;
+    } else {
+        const double raw = snow_thermal_melt(m, for_melt, sc, Ts, Ts_before, P, T_soil, T_soil_before);
+        thermal_melt = day_of_year > 1 ? raw * sm.snow_melt_factor : raw;
+    }
+    double cum_melt = st.cum_melt + thermal_melt;
+    if (step % 24 == 0) cum_melt = 0.0;
+    const double carried = st.extra / new_dens / 10.0;
+    const double net_acc = jmax(0.0, snowfall - sublimation) + carried;
+    double extra = 0.0;
+    double new_depth = jmax(0.0, previous_depth + net_acc - rain_melt - thermal_melt);
+    if (new_depth < sm.min_snow_depth_cm && (step <= 1 || sc.sd_prev < 1e-8)) { extra = new_depth * new_dens * 10.0; new_depth = 0.0; }
+    sc.sd_cur = new_depth;
+    double age;
+    if (first) age = 0.0;
+    else if (sc.sd_cur > 0.0 && sc.sd_prev > 0.0) age = st.age + 1.0 / 25.0;
+    else age = 0.0;
+    st.depth = new_depth; st.age = age; st.days_since = days_since; st.density = new_dens; st.prev_density = new_dens;
+    st.cum_melt = cum_melt; st.extra = extra;
+    SnowUpdateOut o; o.snowfall = snowfall; o.thermal_melt = thermal_melt; o.rain_melt = rain_melt;
+    return o;
+}
+/* adjust_snow_near_nodes!, :598-629 */
+static void adjust_snow_near_nodes(const mc_snow_desc& sm, SnowState& st, SnowScratch& sc, int64_t step)
+{
+    double snowout = sc.sd_cur;
+    double threshold = sm.node_thresholds_cm[std::max(1, st.active) - 1];
+    double extra = st.extra;
+    if (step > 1 && snowout > 0.0) {
+        if ((snowout - threshold < 0.5) && (snowout <= sc.sd_prev)) {
+            extra += (snowout - threshold) * st.density * 10.0;
+            sc.sd_cur = jmax(0.0, threshold - 0.1);
+        }
+    }
+    st.extra = extra;
+    activate_snow_nodes(sm, st, sc, sc.sd_cur);
+    snowout = sc.sd_cur;
+    if (snowout > 0.0) {
+        threshold = sm.node_thresholds_cm[std::max(1, st.active) - 1];
+        if (snowout < sm.min_snow_depth_cm + 0.5 || snowout < threshold + 0.5) {
+            extra = 0.5 * st.density * 10.0;
+            sc.sd_cur = threshold + 0.5;
+        }
+    }
+    st.extra = extra; st.depth = sc.sd_cur;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Per-site problem data gathered from the SoA buffers
  * ------------------------------------------------------------------------------------------ */
@@ -315,6 +555,7 @@ struct RhsParams {
     double soil_wetness, albedo, Q_freeze;
     double L_prev;                /* buffers.soil_energy_balance.obukhov_length_prev */
     int M, n_snow;
+    const SnowState* snow; const SnowScratch* snow_scratch;   /* p.snow_state, buffers.snow (n_snow > 0) */
 };
 
 /* soil_energy_balance, heat_transport_1d.jl:137-302.  u, du in K and K/min. */
@@ -331,7 +572,24 @@ static void soil_energy_balance(const double* u, const RhsParams& p, double t, d
         SoilProps sp = soil_properties(m, f.pressure, T[ns + i], p.theta[i], s.bd[i], s.md[i], s.lam_m[i], s.c_m[i]);
         lam[ns + i] = sp.conductivity; cp[ns + i] = sp.heat_capacity; rho[ns + i] = sp.density;
     }
-    /* (snow node properties are filled here when n_snow > 0 — second wave) */
+    if (ns > 0) {                                                                          /* write_snow_properties!, snow_model.jl:171-208 */
+        const mc_snow_desc& sm = m.snow; const SnowState& st = *p.snow; const SnowScratch& sc = *p.snow_scratch;
+        const double snowdens = evolve_snow_density(sm, st);
+        if (st.depth >= sm.min_snow_depth_cm) {
+            const double cps = snow_specific_heat(m.fluid, snowdens, f.pressure);
+            double k;
+            if (sm.snow_conductivity > 0.0) k = sm.snow_conductivity;
+            else { const double r = snowdens * 1000.0; k = 0.00395 + 0.00084 * r - 1.7756e-6 * (r * r) + 3.80635e-9 * (r * r * r); }
+            for (int i = 0; i < ns; i++) {
+                lam[i] = k;
+                cp[i] = apparent_heat_capacity(sm, T[i], cps);
+                const bool active = sc.node_depths[i] > 0.0 || (i < ns - 1 && sc.node_depths[std::min(ns - 1, i + 1)] > 0.0);
+                rho[i] = active ? snowdens * 1000.0 : 0.0;
+            }
+        } else {
+            for (int i = 0; i < ns; i++) { lam[i] = lam[ns]; cp[i] = cp[ns]; rho[i] = 0.0; }
+        }
+    }
     for (int i = 0; i < M; i++) ld[i] = p.depths[i];
     ld[M] = 0.0;                                                                           /* :127,173 sentinel */
     for (int i = 0; i < M; i++) {                                                          /* :175-210 */
@@ -864,6 +1122,8 @@ struct SiteState {
     double fsal[MAXM];
     int flags;
     InfilBuffers infil;
+    /* SnowModel only */
+    double Ts[NSN]; SnowState snow; SnowScratch snow_scratch; double sd_last, Q_freeze;
 };
 
 struct SiteIO {
@@ -952,72 +1212,89 @@ static void init_site_state(SiteState& st, const mc_model_desc& m, const Site& s
     st.tdeep_prev = std::numeric_limits<double>::quiet_NaN();
     for (int i = 0; i < MAXM; i++) st.fsal[i] = std::numeric_limits<double>::quiet_NaN();
     st.flags = 0;
+    for (int i = 0; i < NSN; i++) { st.Ts[i] = m.snow.initial_snow_temperature_K; st.snow_scratch.node_depths[i] = 0.0; st.snow_scratch.meanT[i] = 0.0; st.snow_scratch.meanTpast[i] = 0.0; }
+    st.snow = initial_snow_state(m.snow, m.snow.initial_snow_depth_cm, m.snow.initial_snow_density);
+    st.snow_scratch.sd_prev = 0.0; st.snow_scratch.sd_cur = 0.0; st.sd_last = 0.0; st.Q_freeze = 0.0;
     (void)site;
 }
 
 /*
- * solve_soil! for days [day0, day0+ndays) of one site.  `first` = this is global day 1 (day0 == 0):
- * runs the pre-loop block (src/simulation.jl:395-452) and the prototype RHS evaluation that
- * SciMLBase.init performs to seed fsalfirst (src/simulation.jl:224-238, 853-860).
+ * solve_soil! for days [day0, day0+ndays) of one site.  day0 == 0 runs the pre-loop block (src/simulation.jl:395-452) and the
+ * prototype RHS evaluation that SciMLBase.init performs to seed fsalfirst (src/simulation.jl:224-238, 853-860).
+ * With SnowModel the ODE state is [T_snow(8); T_soil(N)] over hourly-changing effective depths (src/simulation.jl:595-741).
  */
 static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_initial_soa& init, SiteState& st,
                             SiteIO& io, int64_t day0, Counters& cn)
 {
-    const int N = m.n_soil; const int ns = 0; const int M = N + ns;
+    const int N = m.n_soil; const int ns = m.n_snow; const int M = N + ns;
+    const bool snow = ns > 0; const mc_snow_desc& sm = m.snow;
     const int ndays = io.ndays; const int nrows = ndays * 24;
     const bool dynamic = m.moisture_strategy == MC_MOIST_DYNAMIC;
     const bool nonconsec = m.time_mode == MC_TIME_NONCONSECUTIVE;
+    const bool hourly_rain = m.rainfall_schedule == MC_RAIN_HOURLY;
     const mc_forcing_soa& f = *io.f; mc_output_soa& o = *io.o;
     const bool has_init_T = init.initial_soil_temperature != nullptr;
     double T0[MAXN]; for (int i = 0; i < N; i++) T0[i] = st.T[i];
     double* theta = st.theta; double* sum_phase = st.sum_phase;
+    double* Ts = st.Ts; SnowState& sst = st.snow; SnowScratch& ssc = st.snow_scratch;
     double sum_phase_day_start[MAXN], sat[MAXN];
     for (int i = 0; i < N; i++) sat[i] = 1.0 - site.bd[i] / site.md[i];
-    double pool = st.pool, Q_freeze = 0.0;
+    double pool = st.pool, Q_freeze = st.Q_freeze;
     DayForcing F;
-    RhsParams p; p.m = &m; p.site = &site; p.forcing = &F; p.M = M; p.n_snow = ns;
-    for (int i = 0; i < N; i++) p.depths[i] = m.depths_m[i];
+    RhsParams p; p.m = &m; p.site = &site; p.forcing = &F; p.M = M; p.n_snow = ns; p.snow = &sst; p.snow_scratch = &ssc;
+    for (int i = 0; i < N; i++) p.depths[ns + i] = m.depths_m[i];
+    for (int i = 0; i < ns; i++) p.depths[i] = 0.0;
     Integrator I; I.M = M; I.reltol = m.reltol; I.abstol = m.abstol; I.flags = 0; I.iter = 0; I.accept_step = false; I.u_modified = false;
     I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.EEst = 1; I.tstop_next = 1440.0;
     for (int i = 0; i < M; i++) { I.fsalfirst[i] = st.fsal[i]; I.fsallast[i] = st.fsal[i]; }
     auto put_water_potential_row = [&](int row) {
         for (int i = 0; i < N; i++) io.put_node(o.soil_water_potential, row, i, site.psi_e[i] * mcm::pow(sat[i] / theta[i], site.bb[i]));
     };
-    auto init_soil_humidity = [&](int row, const double* Tn) {   /* initialise_soil_humidity!, dynamic.jl:32-35 — always row 1 of the buffer */
+    auto init_soil_humidity = [&](const double* Tn) {   /* initialise_soil_humidity!, dynamic.jl:32-35 — always row 1 of the buffer */
         if (!dynamic) return;
-        (void)row;
         for (int i = 0; i < N; i++) {
             const double psi = site.psi_e[i] * mcm::pow(sat[i] / theta[i], site.bb[i]);
             io.put_node(o.soil_humidity, 0, i, jclamp(mcm::exp(0.01801528 * psi / (m.fluid.gas_constant * Tn[i])), 0.0, 1.0));
         }
     };
+    auto combine = [&](double* u) { for (int i = 0; i < ns; i++) u[i] = Ts[i]; for (int i = 0; i < N; i++) u[ns + i] = T0[i]; };
+    auto sync_inactive = [&]() { const double sy = Ts[0]; for (int k = 0; k < ns; k++) if (!(ssc.node_depths[k] > 0.0)) Ts[k] = sy; };   /* simulation.jl:93-98 */
     EnvInstant env;
     if (day0 == 0) {
-        /* init(): prototype RHS evaluation seeds fsalfirst (SciMLBase.init -> initialize!) */
+        /* init(): prototype RHS evaluation seeds fsalfirst (SciMLBase.init -> initialize!), src/simulation.jl:196-238 */
         update_forcing_day(F, io, 0);
         env = get_instant(io, 0, 0, site);
-        double Tproto[MAXN];
-        for (int i = 0; i < N; i++) { Tproto[i] = has_init_T ? st.T[i] : 280.0; p.theta[i] = theta[i]; }
+        double Tproto[MAXM];
+        for (int i = 0; i < ns; i++) Tproto[i] = sm.initial_snow_temperature_K;
+        for (int i = 0; i < N; i++) { Tproto[ns + i] = has_init_T ? st.T[i] : 280.0; p.theta[i] = theta[i]; }
         p.shade = env.shade; p.eps_surf = env.eps_surf; p.eps_cloud = env.eps_cloud;
         p.soil_wetness = 0.0; p.albedo = site.albedo; p.Q_freeze = 0.0; p.L_prev = st.L_ode;
+        SnowState proto_state = initial_snow_state(sm, 0.0, -1.0);
+        if (snow) {                                            /* depths_proto = combined_depths(initial snow state) but p.snow_state = initial_snow_state(model) */
+            compute_effective_depths(sm, sst, ssc, m.depths_m, N, p.depths);
+            p.snow = &proto_state;
+        }
         Counters scratch;
         soil_energy_balance(Tproto, p, 0.0, I.fsalfirst, scratch);
+        p.snow = &sst;
         /* solve_soil! pre-loop, :395-452 */
         if (!has_init_T) { const double t_init = tins_mean(io, 0); for (int i = 0; i < N; i++) T0[i] = t_init; }
         for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
         write_soil_properties(io, m, site, N, 0, T0, theta, 101325.0);
         put_water_potential_row(0);
         for (int i = 0; i < N; i++) { io.put_node(o.soil_temperature, 0, i, T0[i]); io.put_node(o.soil_moisture, 0, i, theta[i]); }
-        init_soil_humidity(0, T0);
+        init_soil_humidity(T0);
         st.tdeep_prev = env.T_deep;
-        pool = 0.0;
+        pool = 0.0; Q_freeze = 0.0;
     }
     double tdeep_stale = st.tdeep_prev;
     double soil_wetness_dyn = st.soil_wetness;
     double sky_T = 0.0;
+    double sd_last = st.sd_last;      /* snow_depth_hourly[last processed step] */
 
     for (int jl = 0; jl < ndays; jl++) {
         const int64_t j = day0 + jl;   /* 0-based global day */
+        const int doy = f.day_of_year ? f.day_of_year[jl] : (int)(j + 1);
         update_forcing_day(F, io, jl);
         int niter;
         if (nonconsec) niter = m.iterations_per_day;                                         /* non_consecutive.jl:46-47 */
@@ -1027,72 +1304,119 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
         const int midnight_i = (noon_i + 12) % 24;   /* 0-based hour index */
         if (nonconsec) {                                                                     /* :480-516 */
             for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
+            if (snow) sst.sum_phase = 0.0;
             if (!dynamic && f.prescribed_soil_moisture) { for (int i = 0; i < N; i++) theta[i] = f.prescribed_soil_moisture[((int64_t)jl * N + i) * io.S + io.s]; }
             else for (int i = 0; i < N; i++) theta[i] = init.initial_soil_moisture[(int64_t)i * io.S + io.s];
+            /* reset_snow_per_day is false in BOTH time modes (non_consecutive.jl:40): the snowpack persists from one output day to the next */
             const double t_reset = tins_mean(io, jl);
             if (!has_init_T) for (int i = 0; i < N; i++) T0[i] = t_reset;
             else for (int i = 0; i < N; i++) T0[i] = init.initial_soil_temperature[(int64_t)i * io.S + io.s];
+            for (int i = 0; i < ns; i++) Ts[i] = t_reset;
         }
         T0[N - 1] = tdeep_stale;                                                             /* :517 */
         int iter = 0; bool is_last = false;
         double T0_prev_start[MAXN], T0_day_start[MAXN], T0_iter_start[MAXN], T0_before[MAXN], T0_output[MAXN];
+        double Ts_day_start[NSN], Ts_before[NSN];
         for (int i = 0; i < N; i++) { T0_prev_start[i] = T0[i]; T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
+        for (int i = 0; i < ns; i++) Ts_day_start[i] = Ts[i];
         while (!is_last) {                                                                   /* :530 */
             iter++; cn.n_day_passes++;
             for (int i = 0; i < N; i++) T0_iter_start[i] = T0[i];
             is_last = is_converged(m, iter, niter, T0, T0_prev_start, N);
             for (int i = 0; i < N; i++) T0_prev_start[i] = T0_iter_start[i];
-            if (!nonconsec) for (int i = 0; i < N; i++) T0[i] = T0_day_start[i];             /* iter_resets_T */
+            if (!nonconsec) { for (int i = 0; i < N; i++) T0[i] = T0_day_start[i]; for (int i = 0; i < ns; i++) Ts[i] = Ts_day_start[i]; }   /* iter_resets_T */
             for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
+            if (snow && nonconsec) sst.sum_phase = 0.0;
             const int day_row = jl * 24;
             if (is_last) {                                                                   /* :557-592 */
                 for (int i = 0; i < N; i++) { io.put_node(o.soil_temperature, day_row, i, T0[i]); io.put_node(o.soil_moisture, day_row, i, theta[i]); }
                 io.put_scalar(o.surface_water, day_row, pool);
                 put_water_potential_row(day_row);
-                init_soil_humidity(day_row, T0);
+                init_soil_humidity(T0);
                 EnvInstant e0 = get_instant(io, jl, day_row, site);
                 io.put_scalar(o.sky_temperature, day_row, sky_temperature(m, site.svf, e0.P, e0.rh, e0.T_ref, e0.eps_cloud, e0.cloud, e0.shade, e0.has_lw, e0.lw));
                 write_soil_properties(io, m, site, N, day_row, T0, theta, e0.P);
             }
-            int step = jl * 24;                                                              /* :595-633 */
+            int step = jl * 24;                                                              /* chunk-relative 0-based; global 1-based = day0*24 + step + 1 */
             env = get_instant(io, jl, step, site);
             T0[N - 1] = env.T_deep;
-            auto set_hour_params = [&](const EnvInstant& e) {
+            /* apply_snow_overrides (simulation.jl:46-81) + per-hour parameter update */
+            auto set_hour_params = [&](const EnvInstant& e, int64_t gstep /*1-based global*/, double depth_prev_hour) {
                 p.shade = e.shade; p.eps_surf = e.eps_surf; p.eps_cloud = e.eps_cloud;
-                p.albedo = e.has_albedo ? e.albedo_daily : site.albedo;
-                p.soil_wetness = dynamic ? soil_wetness_dyn : e.soil_wetness_daily;
+                const bool snow_active = snow && is_last && ((gstep > 1 ? depth_prev_hour : sst.depth) > 0.0);
+                if (snow_active) { p.albedo = snow_albedo(sst.days_since); p.soil_wetness = 1.0; }
+                else { p.albedo = e.has_albedo ? e.albedo_daily : site.albedo; p.soil_wetness = dynamic ? soil_wetness_dyn : e.soil_wetness_daily; }
                 p.Q_freeze = Q_freeze;
                 sky_T = sky_temperature(m, site.svf, e.P, e.rh, e.T_ref, e.eps_cloud, e.cloud, e.shade, e.has_lw, e.lw);
             };
-            set_hour_params(env);
+            const int64_t g0 = day0 * 24 + step + 1;
+            set_hour_params(env, g0, sd_last);
+            if (snow) {
+                if (!is_last) { double tmp = sst.depth; activate_snow_nodes(sm, sst, ssc, tmp); }
+                compute_effective_depths(sm, sst, ssc, m.depths_m, N, p.depths);
+                int fa = -1; for (int k = 0; k < ns; k++) if (ssc.node_depths[k] > 0.0) { fa = k; break; }
+                const double sync_temp = fa < 0 ? T0[0] : Ts[fa];
+                for (int k = 0; k < ns; k++) if (fa < 0 || k < fa) Ts[k] = sync_temp;     /* _sync_snow_to_active */
+            }
             p.L_prev = st.L_ode;
             for (int i = 0; i < N; i++) p.theta[i] = theta[i];
-            reinit(I, T0, p, cn);
+            double u0[MAXM]; combine(u0);
+            reinit(I, u0, p, cn);
             for (int i = 0; i < 24; i++) {                                                   /* :635 */
                 step = jl * 24 + i;
+                const int64_t gstep = day0 * 24 + step + 1;
                 for (int k = 0; k < N; k++) { T0_before[k] = T0[k]; p.theta[k] = theta[k]; }
+                for (int k = 0; k < ns; k++) Ts_before[k] = Ts[k];
                 p.L_prev = st.L_ode;
                 step_to_hour(I, i + 1, p, cn);
-                for (int k = 0; k < N; k++) T0[k] = I.u[k];
+                for (int k = 0; k < ns; k++) Ts[k] = I.u[k];
+                for (int k = 0; k < N; k++) T0[k] = I.u[ns + k];
                 if (is_last) {                                                               /* :645-650 */
                     phase_transition(N, m.depths_m, T0, T0_before, sum_phase, theta);
                     for (int k = 0; k < N; k++) T0_output[k] = T0[k];
                 }
+                double snowfall_hour = 0.0, thermal_melt = 0.0, rain_melt_snow = 0.0;
+                if (snow && is_last) {                                                       /* :656-708 */
+                    ssc.sd_prev = sd_last;
+                    double Qe, Qc;                                                           /* zenith defaults to 90 deg: neutral branch */
+                    surface_convection_evaporation(m, T0[0], env.T_ref, env.wind, env.rh, env.P, site.z0, m.reference_height_m, 90.0, p.soil_wetness, -0.3, Qe, Qc, cn);
+                    const double rain_for_snow = env.rain_daily;                             /* environment_instant.rainfall is the DAILY total (simulation.jl:1031) */
+                    SnowUpdateOut so = update_snow(m, sst, ssc, Ts, Ts_before, env.T_ref, rain_for_snow, env.P, gstep, T0[0], T0_before[0], Qe, hourly_rain, env.shade, doy);
+                    snowfall_hour = so.snowfall; thermal_melt = so.thermal_melt; rain_melt_snow = so.rain_melt;
+                    if (doy > 1 && sm.snow_melt_factor <= 1.0) Q_freeze = thermal_melt * 10.0 * LATENT_HEAT_FUSION / 3600.0 * (1.0 - sm.snow_melt_factor);
+                    else Q_freeze = 0.0;
+                    int prev_active = sst.active;
+                    activate_snow_nodes(sm, sst, ssc, ssc.sd_cur);
+                    if (sst.active < prev_active) sync_inactive();
+                    double soil_surf = T0[0];
+                    snow_phase_transition(m, sst, ssc, Ts, env.P, soil_surf);               /* soil-surface clamp deliberately NOT applied (simulation.jl:689-702) */
+                    for (int k = 0; k < ns; k++) if (ssc.node_depths[k] > 0.0 && Ts[k] > T0C) Ts[k] = T0C;   /* clamp_snow_temperatures */
+                    /* freeze_new_snow (snow_model.jl:235-264) selects the index range (N+1-m):(N-m), which is empty: a no-op upstream */
+                    adjust_snow_near_nodes(sm, sst, ssc, gstep);
+                    prev_active = sst.active;
+                    activate_snow_nodes(sm, sst, ssc, ssc.sd_cur);
+                    if (sst.active < prev_active) sync_inactive();
+                    sd_last = ssc.sd_cur;
+                }
                 if (i < 23) {                                                                /* :712-735 */
                     env = get_instant(io, jl, step + 1, site);
                     T0[N - 1] = env.T_deep;
-                    set_hour_params(env);
+                    set_hour_params(env, gstep + 1, sd_last);
+                    if (snow) {
+                        if (!is_last) { double tmp = sst.depth; activate_snow_nodes(sm, sst, ssc, tmp); }
+                        compute_effective_depths(sm, sst, ssc, m.depths_m, N, p.depths);
+                    }
                 }
-                for (int k = 0; k < N; k++) I.u[k] = T0[k];                                  /* :736-741 */
+                combine(I.u);                                                                /* :736-741 */
                 I.u_modified = true;
                 {                                                                            /* init_surface_fluxes!, monin_obukhov.jl:247-264 */
                     const Instant9 fi = interpolate_forcings(F, (double)(i * 60));
-                    const double Ts = T0[0];
-                    if (fi.air_temperature < Ts && fi.zenith < 90.0) {
-                        const double dT = fi.air_temperature - Ts;
-                        const double rho_cp = calc_rho_cp((Ts + fi.air_temperature) / 2.0);
+                    const double Tsurf = T0[0];
+                    if (fi.air_temperature < Tsurf && fi.zenith < 90.0) {
+                        const double dT = fi.air_temperature - Tsurf;
+                        const double rho_cp = calc_rho_cp((Tsurf + fi.air_temperature) / 2.0);
                         const double L0 = st.L_ode >= 0.0 ? -0.3 : st.L_ode;
-                        ObukhovOut ob = calc_obukhov(fi.air_temperature, Ts, fi.wind_speed, site.z0, m.reference_height_m, m.karman_constant, dT, rho_cp, 16.0, 30, 1e-2, L0);
+                        ObukhovOut ob = calc_obukhov(fi.air_temperature, Tsurf, fi.wind_speed, site.z0, m.reference_height_m, m.karman_constant, dT, rho_cp, 16.0, 30, 1e-2, L0);
                         cn.n_obukhov += ob.iters;
                         st.L_ode = ob.L;
                     }
@@ -1100,11 +1424,20 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
                 bool have_infil = false;
                 if (is_last) {                                                               /* :745-777 */
                     double rain;
-                    if (m.rainfall_schedule == MC_RAIN_HOURLY) rain = io.hourly(f.rainfall_hourly, step);
+                    if (hourly_rain) rain = io.hourly(f.rainfall_hourly, step);
                     else rain = (i == midnight_i) ? env.rain_daily : 0.0;
-                    pool = jclamp(pool + rain + 0.0 + 0.0, 0.0, m.max_surface_pool);
+                    bool snow_present = false;
+                    if (snow) {
+                        rain = rain * sm.rain_multiplier;
+                        snow_present = ssc.sd_cur > 0.0;
+                        const double melted_water = thermal_melt * 10.0, rain_melt_water = rain_melt_snow * sst.density * 10.0;
+                        if (snow_present && env.T_ref - T0C < sm.snow_temperature_threshold_C) pool = jclamp(pool + melted_water, 0.0, m.max_surface_pool);
+                        else pool = jclamp(pool + rain + rain_melt_water + melted_water, 0.0, m.max_surface_pool);
+                    } else {
+                        pool = jclamp(pool + rain + 0.0 + 0.0, 0.0, m.max_surface_pool);
+                    }
                     if (dynamic) {
-                        WaterOut w = soil_water_balance(st.infil, m, site, N, env, T0, pool, soil_wetness_dyn, theta, st.L_prof, false, st.flags, cn);
+                        WaterOut w = soil_water_balance(st.infil, m, site, N, env, T0, pool, soil_wetness_dyn, theta, st.L_prof, snow_present, st.flags, cn);
                         soil_wetness_dyn = w.soil_wetness; pool = w.pool; have_infil = true;
                     }
                 }
@@ -1120,12 +1453,18 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
                     const double P_out = io.hourly(f.pressure, out_row);
                     write_soil_properties(io, m, site, N, out_row, T0, theta, P_out);
                 }
+                if (is_last && snow) {                                                       /* snow outputs are recorded at `step`, :803-813 */
+                    io.put_scalar(o.snow_fall, step, snowfall_hour);
+                    io.put_scalar(o.snow_depth, step, ssc.sd_cur);
+                    io.put_scalar(o.snow_density, step, evolve_snow_density(sm, sst));
+                    if (o.snow_temperature) for (int k = 0; k < ns; k++) o.snow_temperature[((int64_t)step * ns + k) * io.S + io.s] = Ts[k];
+                }
             }
         }
         tdeep_stale = env.T_deep;
     }
     for (int i = 0; i < N; i++) st.T[i] = T0[i];
-    st.pool = pool; st.soil_wetness = soil_wetness_dyn; st.tdeep_prev = tdeep_stale;
+    st.pool = pool; st.soil_wetness = soil_wetness_dyn; st.tdeep_prev = tdeep_stale; st.sd_last = sd_last; st.Q_freeze = Q_freeze;
     for (int i = 0; i < M; i++) st.fsal[i] = I.fsalfirst[i];
     st.flags |= I.flags;
     for (int i = 0; i < N; i++) if (!(std::isfinite(st.T[i]) && std::isfinite(st.theta[i]))) st.flags |= MC_STATUS_NAN;
@@ -1160,7 +1499,7 @@ extern "C" {
 
 void* mco_create(const mc_model_desc* model, int64_t n_sites)
 {
-    if (!model || n_sites <= 0 || model->n_soil < 3 || model->n_soil > MC_MAX_SOIL_NODES || model->n_snow != 0) return nullptr;
+    if (!model || n_sites <= 0 || model->n_soil < 3 || model->n_soil > MC_MAX_SOIL_NODES || (model->n_snow != 0 && model->n_snow != MC_SNOW_NODES)) return nullptr;
     mco::Oracle* o = new mco::Oracle();
     o->model = *model; o->S = n_sites; o->sites.resize(n_sites); o->states.resize(n_sites); o->days_done = 0; o->has_init_T = false;
     return o;
@@ -1241,6 +1580,19 @@ int mco_get_state(void* h, mc_state_soa* out)
         if (out->obukhov_ode) out->obukhov_ode[s] = st.L_ode;
         if (out->obukhov_profile) out->obukhov_profile[s] = st.L_prof;
         if (out->deep_temperature_prev) out->deep_temperature_prev[s] = st.tdeep_prev;
+        if (o->model.n_snow > 0) {
+            for (int i = 0; i < o->model.n_snow; i++) {
+                if (out->snow_temperature) out->snow_temperature[(int64_t)i * S + s] = st.Ts[i];
+                if (out->snow_node_depths) out->snow_node_depths[(int64_t)i * S + s] = st.snow_scratch.node_depths[i];
+                if (out->fsal) out->fsal[(int64_t)(N + i) * S + s] = st.fsal[N + i];
+            }
+            if (out->snow_state) {
+                const double v[MC_SNOW_STATE_FIELDS] = {st.snow.depth, st.snow.age, st.snow.days_since, st.snow.density, st.snow.prev_density, st.snow.cum_melt,
+                                                        st.snow.extra, (double)st.snow.active, st.snow.sum_phase, st.sd_last};
+                for (int k = 0; k < MC_SNOW_STATE_FIELDS; k++) out->snow_state[(int64_t)k * S + s] = v[k];
+            }
+            if (out->q_freeze) out->q_freeze[s] = st.Q_freeze;
+        }
     }
     if (out->days_done) out->days_done[0] = o->days_done;
     return 0;

@@ -15,6 +15,7 @@ namespace {
 struct Emu {
     mc_model_desc model; int64_t S; int N; int64_t days_done;
     std::vector<double> site[4], node[8], init_T, init_theta, T, theta, sum_phase, fsal, pool, wet, L_ode, L_prof, tdeep;
+    std::vector<double> snow_T, snow_state, snow_nd, q_freeze;
     std::vector<int32_t> flags; bool has_init_T;
     unsigned long long counters[8];
 };
@@ -24,7 +25,7 @@ extern "C" {
 
 void* he_create(const mc_model_desc* m, int64_t S)
 {
-    if (!m || m->n_snow != 0) return nullptr;
+    if (!m || (m->n_snow != 0 && m->n_snow != MC_SNOW_NODES)) return nullptr;
     Emu* e = new Emu(); e->model = *m; e->S = S; e->N = m->n_soil; e->days_done = 0; std::memset(e->counters, 0, sizeof(e->counters));
     return e;
 }
@@ -43,7 +44,16 @@ int he_set_sites(void* h, const mc_sites_soa* s, const mc_initial_soa* init)
     e->init_T.assign(N * S, qnan);
     if (e->has_init_T) e->init_T.assign(init->initial_soil_temperature, init->initial_soil_temperature + N * S);
     e->init_theta.assign(init->initial_soil_moisture, init->initial_soil_moisture + N * S);
-    e->T = e->init_T; e->theta = e->init_theta; e->sum_phase.assign(N * S, 0.0); e->fsal.assign(N * S, qnan);
+    e->T = e->init_T; e->theta = e->init_theta; e->sum_phase.assign(N * S, 0.0); e->fsal.assign((N + e->model.n_snow) * S, qnan);
+    if (e->model.n_snow) {
+        const mc_snow_desc& sm = e->model.snow; const size_t NS = e->model.n_snow;
+        e->snow_T.assign(NS * S, sm.initial_snow_temperature_K); e->snow_nd.assign(NS * S, 0.0); e->q_freeze.assign(S, 0.0);
+        const double dflt = sm.density_function[0] > 0.0 ? sm.density_function[1] : sm.snow_density;
+        const double d = sm.initial_snow_density > 0.0 ? sm.initial_snow_density : dflt;
+        const double v[MC_SNOW_STATE_FIELDS] = {sm.initial_snow_depth_cm, 0.0, 0.3, d, d, 0.0, 0.0, 0.0, 0.0, 0.0};
+        e->snow_state.assign(MC_SNOW_STATE_FIELDS * S, 0.0);
+        for (int k = 0; k < MC_SNOW_STATE_FIELDS; k++) for (size_t q = 0; q < S; q++) e->snow_state[k * S + q] = v[k];
+    }
     e->pool.assign(S, 0.0); e->wet.assign(S, 0.0); e->L_ode.assign(S, -0.3); e->L_prof.assign(S, -0.3); e->tdeep.assign(S, qnan);
     e->flags.assign(S, 0); e->days_done = 0; std::memset(e->counters, 0, sizeof(e->counters));
     return 0;
@@ -62,6 +72,8 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     a.ks = e->node[5].data(); a.bb = e->node[6].data(); a.rootd = e->node[7].data(); a.init_T = e->init_T.data(); a.init_theta = e->init_theta.data();
     a.T = e->T.data(); a.theta = e->theta.data(); a.sum_phase = e->sum_phase.data(); a.pool = e->pool.data(); a.wetness = e->wet.data();
     a.L_ode = e->L_ode.data(); a.L_prof = e->L_prof.data(); a.tdeep_prev = e->tdeep.data(); a.fsal = e->fsal.data(); a.flags = e->flags.data();
+    if (e->model.n_snow) { a.snow_T = e->snow_T.data(); a.snow_state = e->snow_state.data(); a.snow_nd = e->snow_nd.data(); a.q_freeze = e->q_freeze.data(); }
+    a.doy = f->day_of_year;
     a.f_P = f->pressure; a.f_T = f->reference_temperature; a.f_wind = f->reference_wind_speed; a.f_rh = f->reference_humidity;
     a.f_cloud = f->cloud_cover; a.f_solar = f->global_radiation; a.f_diffuse = f->diffuse_fraction; a.f_zen = f->zenith_angle;
     a.f_szen = f->zenith_slope_angle; a.f_rain = f->rainfall_hourly; a.f_lw = f->longwave_radiation;
@@ -69,10 +81,12 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     a.d_tdeep = f->deep_soil_temperature; a.d_rain = f->rainfall_daily; a.d_albedo = f->albedo_daily; a.presc = f->prescribed_soil_moisture;
     a.o_T = o->soil_temperature; a.o_theta = o->soil_moisture; a.o_psi = o->soil_water_potential; a.o_h = o->soil_humidity;
     a.o_lam = o->soil_thermal_conductivity; a.o_cp = o->soil_heat_capacity; a.o_rho = o->soil_bulk_density; a.o_pool = o->surface_water; a.o_sky = o->sky_temperature;
+    a.o_snow_fall = o->snow_fall; a.o_snow_depth = o->snow_depth; a.o_snow_dens = o->snow_density; a.o_snow_T = o->snow_temperature;
     int nbad = 0;
     for (int64_t s = 0; s < e->S; s++) {
         mcd::Counters cn = {};
-        if (e->N <= 10) mcd::solve_site<10>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES>(a, s, cn);
+        if (e->model.n_snow == 0) { if (e->N <= 10) mcd::solve_site<10, 0>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, 0>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, 0>(a, s, cn); }
+        else { if (e->N <= 10) mcd::solve_site<10, MC_SNOW_NODES>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, MC_SNOW_NODES>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, s, cn); }
         e->counters[0] += cn.n_rhs; e->counters[1] += cn.n_accept; e->counters[2] += cn.n_reject; e->counters[3] += cn.n_obukhov;
         e->counters[4] += cn.n_newton; e->counters[5] += cn.n_infil; e->counters[6] += cn.n_day_passes;
         if (o->status) o->status[s] = e->flags[s];

@@ -73,8 +73,8 @@ def test_fails_loudly_without_a_gpu_and_on_bad_models(L):
     d.n_soil = 2
     assert L.mc_create(C.byref(d), 8, 0, C.byref(h)) == -1 and b"n_soil" in L.mc_last_error(None)
     d.n_soil = 19
-    d.n_snow = 8
-    assert L.mc_create(C.byref(d), 8, 0, C.byref(h)) == -3 and b"SnowModel" in L.mc_last_error(None)
+    d.n_snow = 3
+    assert L.mc_create(C.byref(d), 8, 0, C.byref(h)) == -3 and b"n_snow" in L.mc_last_error(None)
     assert L.mc_step_days(None, 0, 1, None, None) == -1
 
 

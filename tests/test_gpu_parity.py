@@ -125,3 +125,42 @@ def test_fp64_peak_is_measured(SoilEngine, synth):
     e = SoilEngine(desc, sites.S)
     tf = e.measure_fp64_peak()
     assert 10.0 < tf < 60.0     # B200: 148 SM x 64 FP64 lanes x 2 x ~1.9 GHz ~ 36-37 TFLOP/s
+
+
+def test_snow_model_matches_oracle(SoilEngine):
+    """BASELINE config 3: SnowModel (8 snow nodes on top of the soil column) + each apparent_heat_capacity closure, and a
+    config-4-shaped problem (consecutive days, dynamic moisture, snow).  Every output incl. the snow fields, bit for bit."""
+    import copy
+    import dataclasses
+    import microclimate_jl_b200 as mc
+    f = parity.ALL_FIELDS + ("snow_fall", "snow_depth", "snow_density", "snow_temperature")
+    p, g = configs.config1_monthly(snow=True)
+    for ahc in (mc.BonacinaStep(), mc.TanhSmoothed(), mc.Gaussian(), mc.WestermannSigmoid()):
+        q = copy.deepcopy(p)
+        q.model.snow_model = dataclasses.replace(q.model.snow_model, apparent_heat_capacity=ahc)
+        desc, sites, forcing = _problem_buffers(q)
+        ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+        out, eg = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+        parity.assert_within_north_star(out, ref, f)
+        parity.assert_bit_identical(out, ref, f)
+        assert eo.counters()["n_rhs"] == eg.counters()["n_rhs"]
+        if isinstance(ahc, mc.BonacinaStep):        # the reference's own assertions on the CUDA output (micro_testrun_monthly_snow.jl:194-196)
+            assert np.allclose(out.snow_fall[:, 0], g["SNOWFALL"], rtol=1e-3, atol=1e-9)
+            assert np.allclose(out.snow_depth[:72, 0], g["SNOWDEP"][:72], rtol=1e-2)
+            assert np.allclose(out.snow_density[:72, 0], g["SNOWDENS"][:72], rtol=1e-2)
+    p2, _ = configs.config2_daily(6)
+    p2 = copy.deepcopy(p2)
+    p2.model.snow_model = mc.SnowModel(density_function=(0.5979, 0.2178, 0.001, 0.0038))
+    h = p2.inputs.environment_hourly
+    h.reference_temperature = np.asarray(h.reference_temperature) - 12.0
+    p2.inputs.environment_daily.rainfall = np.asarray(p2.inputs.environment_daily.rainfall) + 4.0
+    desc, sites, forcing = _problem_buffers(p2)
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    out, _ = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(out, ref, f)
+    st = SoilEngine(desc, 1)
+    st.set_sites(sites)
+    o1 = M.OutputBatch(2, desc.n_soil, 1, f, desc.n_snow)
+    st.step_days(0, forcing.day_slice(0, 2), o1)
+    state = st.get_state()
+    assert state.snow_state is not None and state.snow_state[0, 0] == o1.snow_depth[-1, 0]      # current depth is carried

@@ -2,6 +2,7 @@
 tests/hostemu harness, against the oracle.  This is what lets the no-GPU tier check the code the CUDA kernel executes;
 the GPU tier (test_gpu_parity.py) repeats the same comparisons on the device through the C ABI."""
 import copy
+import dataclasses
 
 import numpy as np
 import pytest
@@ -105,3 +106,48 @@ def test_sloped_site_bit_identical():
     ref, _ = parity.run(OracleEngine, desc, sites, forcing)
     out, _ = parity.run(HostEmuEngine, desc, sites, forcing)
     parity.assert_bit_identical(out, ref)
+
+
+def test_snow_model_and_apparent_heat_capacity_variants_bit_identical():
+    """SnowModel (config 3) with each apparent_heat_capacity closure (src/apparent_heat_capacity/*.jl), plus a chunked run
+    (the snowpack state is part of the carried state)."""
+    p, _ = configs.config1_monthly(snow=True)
+    f = parity.ALL_FIELDS + ("snow_fall", "snow_depth", "snow_density", "snow_temperature")
+    for ahc in (mc.BonacinaStep(), mc.TanhSmoothed(), mc.Gaussian(), mc.WestermannSigmoid()):
+        q = copy.deepcopy(p)
+        q.model.snow_model = dataclasses.replace(q.model.snow_model, apparent_heat_capacity=ahc)
+        desc, sites, forcing = _buffers(q)
+        assert desc.n_snow == 8
+        ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+        out, ee = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+        parity.assert_bit_identical(out, ref, f)
+        assert eo.counters()["n_rhs"] == ee.counters()["n_rhs"]
+        assert ref.snow_depth.max() > 10.0
+    desc, sites, forcing = _buffers(p)
+    whole, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+    chunked, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f, chunks=[5, 4, 3])
+    parity.assert_bit_identical(chunked, whole, f)
+    ref_chunked, _ = parity.run(OracleEngine, desc, sites, forcing, fields=f, chunks=[5, 4, 3])
+    parity.assert_bit_identical(chunked, ref_chunked, f)
+
+
+def test_snow_with_dynamic_moisture_consecutive_days_bit_identical():
+    """Config-4-shaped problem (consecutive days, dynamic moisture, snow): config 2's site with a SnowModel and cold forcing."""
+    p, _ = configs.config2_daily(6)
+    p = copy.deepcopy(p)
+    p.model.snow_model = mc.SnowModel(density_function=(0.5979, 0.2178, 0.001, 0.0038))
+    h = p.inputs.environment_hourly
+    h.reference_temperature = np.asarray(h.reference_temperature) - 12.0        # push the desert winter below freezing
+    p.inputs.environment_daily.rainfall = np.asarray(p.inputs.environment_daily.rainfall) + 4.0
+    desc, sites, forcing = _buffers(p)
+    f = parity.ALL_FIELDS + ("snow_fall", "snow_depth", "snow_density", "snow_temperature")
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    out, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(out, ref, f)
+    # chunked == whole for everything except soil_humidity's first row per chunk (upstream writes initialise_soil_humidity! to
+    # row 1 of the output buffer only, src/soil_moisture/dynamic.jl:32-35; a chunk's buffer starts at its own row 1)
+    g = tuple(x for x in f if x != "soil_humidity")
+    chunked, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f, chunks=[2, 4])
+    parity.assert_bit_identical(chunked, ref, g)
+    assert np.array_equal(np.delete(chunked.soil_humidity, 48, axis=0), np.delete(ref.soil_humidity, 48, axis=0))
+    assert ref.snow_depth.max() > 2.0 and np.all(np.isfinite(ref.soil_temperature))

@@ -205,3 +205,24 @@ def test_phase_transition_freeze_thaw(L):
     L.mco_phase_transition(N, p(depths), p(T2), p(Tpast2), p(S), p(theta))
     assert S[0] == pytest.approx(max(0.0, S0 - 2.0 * mass * 4184.0))
     assert (T2[0] == 273.15) == (S[0] > 0)
+
+
+def test_config3_monthly_snow_vs_nichemapr():
+    """Config 3 (SnowModel, 8 snow nodes, BonacinaStep apparent heat capacity): the reference's own assertions
+    (test/micro_testrun_monthly_snow.jl:194-196) — snowfall rtol 1e-3, snow depth and density over the first 72 h rtol 1e-2."""
+    g = configs.load("config1_monthly_snow.npz")
+    p, _ = configs.config1_monthly(snow=True)
+    fields = M.DEFAULT_OUTPUT_FIELDS + ("snow_fall", "snow_depth", "snow_density", "snow_temperature")
+    out, eng = configs.run_engine(OracleEngine, p, fields=fields)
+    assert out.status[0] == 0
+    sf, sd, dens = out.snow_fall[:, 0], out.snow_depth[:, 0], out.snow_density[:, 0]
+    assert np.allclose(sf, g["SNOWFALL"], rtol=1e-3, atol=1e-9)
+    assert np.allclose(sd[:72], g["SNOWDEP"][:72], rtol=1e-2)
+    assert np.allclose(dens[:72], g["SNOWDENS"][:72], rtol=1e-2)
+    # the pack builds over the winter days, is gone in summer and rebuilds in autumn, like NicheMapR's
+    assert sd[24 * 2] > 40.0 and np.all(sd[24 * 5:24 * 9] == 0.0) and sd[-1] > 50.0
+    assert np.abs(sd - g["SNOWDEP"]).max() < 15.0
+    T = out.soil_temperature[:, :, 0]
+    assert np.all(np.isfinite(T)) and np.abs(T / g["soil_nmr"] - 1).max() < 1e-1
+    assert np.all(out.snow_temperature[sd > 0][:, -1] <= 273.15 + 1e-9)     # active snow nodes never above freezing
+    assert np.abs(out.sky_temperature[:, 0] / g["TSKYC"] - 1).max() < 2e-3
