@@ -30,11 +30,12 @@ thread_local std::string g_create_error;
         }                                                                                                      \
     } while (0)
 
+/* 64-thread blocks, 8 resident per SM (128 registers/thread, 16 warps/SM): measured best on B200 (profiles/README.md) */
 #ifndef MC_BLOCK
-#define MC_BLOCK 128
+#define MC_BLOCK 64
 #endif
 #ifndef MC_MIN_BLOCKS
-#define MC_MIN_BLOCKS 3
+#define MC_MIN_BLOCKS 8
 #endif
 constexpr int BLOCK = MC_BLOCK;
 
@@ -44,10 +45,10 @@ constexpr int BLOCK = MC_BLOCK;
 template <int NA, int NS>
 __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const mcd::KArgs a)
 {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.S) return;
     mcd::Counters cn = {};
-    mcd::solve_site<NA, NS>(a, s, cn);
+    /* grid-stride over sites: the grid may be sized to the machine (blocks per SM x SM count) instead of to the problem */
+    for (int64_t s = a.s_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.s_end; s += (int64_t)gridDim.x * blockDim.x)
+        mcd::solve_site<NA, NS>(a, s, cn);
     if (a.counters) {
         atomicAdd(a.counters + 0, (unsigned long long)cn.n_rhs);
         atomicAdd(a.counters + 1, (unsigned long long)cn.n_accept);
@@ -103,6 +104,9 @@ struct mc_handle {
     int device = 0;
     int N = 0;
     cudaStream_t stream = nullptr;
+    static constexpr int MAX_SLICES = 4;
+    cudaStream_t slice_stream[MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_ready = nullptr, ev_slice[MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr}, ev_kernel[MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     /* device arrays (all one arena) */
@@ -136,7 +140,14 @@ static int validate_model(const mc_model_desc* m, std::string& err)
 template <int NA, int NS>
 static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
 {
-    const int grid = (int)((a.S + BLOCK - 1) / BLOCK);
+    int grid = (int)((a.s_end - a.s_begin + BLOCK - 1) / BLOCK);
+    static int per_sm = -1, n_sm = 0;    /* development knob: MC_BLOCKS_PER_SM caps resident blocks by sizing the grid (persistent, grid-stride) */
+    if (per_sm < 0) {
+        const char* e = getenv("MC_BLOCKS_PER_SM");
+        per_sm = e ? atoi(e) : 0;
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (per_sm > 0 && grid > per_sm * n_sm) grid = per_sm * n_sm;
     static int pad = -1;                 /* development knob: dynamic shared-memory padding limits resident blocks per SM */
     if (pad < 0) {
         const char* e = getenv("MC_SMEM_PAD");
@@ -150,7 +161,7 @@ static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
 static void fill_site_state_args(mc_handle* h, mcd::KArgs& a)
 {
     std::memset(&a, 0, sizeof(a));
-    a.S = h->S; a.has_init_T = h->has_init_T;
+    a.S = h->S; a.s_begin = 0; a.s_end = h->S; a.has_init_T = h->has_init_T;
     a.z0 = h->z0; a.slope = h->slope; a.svf = h->svf; a.albedo = h->albedo; a.bd = h->bd; a.md = h->md; a.lam_m = h->lam_m; a.c_m = h->c_m;
     a.psi_e = h->psi_e; a.ks = h->ks; a.bb = h->bb; a.rootd = h->rootd; a.init_T = h->init_T; a.init_theta = h->init_theta;
     a.T = h->T; a.theta = h->theta; a.sum_phase = h->sum_phase; a.pool = h->pool; a.wetness = h->wetness; a.L_ode = h->L_ode;
@@ -217,6 +228,12 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    for (int k = 0; k < mc_handle::MAX_SLICES; k++) {
+        if ((e = cudaStreamCreateWithFlags(&h->slice_stream[k], cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_slice[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    }
     const size_t S = (size_t)n_sites, N = (size_t)h->N;
     const size_t NSn = (size_t)model->n_snow;
     const size_t per_site = 4 + 5, per_node = 8 + 2 + 4;
@@ -246,6 +263,8 @@ void mc_destroy(mc_handle* h)
     cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+    for (int k = 0; k < mc_handle::MAX_SLICES; k++) { if (h->ev_slice[k]) cudaEventDestroy(h->ev_slice[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->slice_stream[k]) cudaStreamDestroy(h->slice_stream[k]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -307,15 +326,16 @@ static int check_forcing(mc_handle* h, const mc_forcing_soa* f)
     return 0;
 }
 
-int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+/* argument validation + KArgs for a chunk whose forcing/output pointers are DEVICE pointers; uploads the model constants and the
+ * day-of-year vector on the handle's main stream */
+static int prepare_chunk(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o, mcd::KArgs& a)
 {
-    if (!h) return -1;
     if (!h->sites_set) { h->err = "mc_set_sites has not been called"; return -1; }
     if (!f || !o || ndays <= 0) { h->err = "forcing/out must be non-NULL and ndays positive"; return -1; }
     if (day0 != h->days_done) { h->err = "day0 must equal the number of days already integrated"; return -2; }
     if (check_forcing(h, f)) return -1;
     MC_CUDA(h, cudaSetDevice(h->device));
-    mcd::KArgs a; fill_site_state_args(h, a);
+    fill_site_state_args(h, a);
     a.day0 = day0; a.ndays = ndays;
     a.has_albedo_daily = f->albedo_daily != nullptr; a.has_lw = f->longwave_radiation != nullptr; a.has_presc = f->prescribed_soil_moisture != nullptr;
     a.f_P = f->pressure; a.f_T = f->reference_temperature; a.f_wind = f->reference_wind_speed; a.f_rh = f->reference_humidity;
@@ -332,12 +352,27 @@ int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forc
         a.doy = h->doy_dev;
     }
     MC_CUDA(h, cudaMemcpyToSymbolAsync(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice, h->stream));
-    MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    return 0;
+}
+
+static int launch_range(mc_handle* h, mcd::KArgs a, int64_t lo, int64_t hi, cudaStream_t st)
+{
+    a.s_begin = lo; a.s_end = hi;
     const int na = pick_na(h->N);
     cudaError_t e;
-    if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, h->stream) : (na == 19 ? launch_chunk<19, 0>(a, h->stream) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, h->stream));
-    else e = na == 10 ? launch_chunk<10, MC_SNOW_NODES>(a, h->stream) : (na == 19 ? launch_chunk<19, MC_SNOW_NODES>(a, h->stream) : launch_chunk<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, h->stream));
+    if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, st) : (na == 19 ? launch_chunk<19, 0>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, st));
+    else e = na == 10 ? launch_chunk<10, MC_SNOW_NODES>(a, st) : (na == 19 ? launch_chunk<19, MC_SNOW_NODES>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, st));
     MC_CUDA(h, e);
+    return 0;
+}
+
+int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!h) return -1;
+    mcd::KArgs a;
+    if (int rc = prepare_chunk(h, day0, ndays, f, o, a)) return rc;
+    MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    if (int rc = launch_range(h, a, 0, h->S, h->stream)) return rc;
     MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->last_launches = 1;
     h->days_done += ndays;
@@ -363,6 +398,10 @@ static int ensure_stage(mc_handle* h, double** buf, size_t* have, size_t need)
     return 0;
 }
 
+/* Host-buffer entry point.  The site range can be cut into up to 4 contiguous slices (MC_SLICES), each on its own stream:
+ *     H2D(slice k forcing)  ->  soil_chunk_kernel(slice k)  ->  D2H(slice k outputs)
+ * so the PCIe copies of one slice overlap the kernel of another (site-fastest SoA makes a slice a strided block per row:
+ * cudaMemcpy2DAsync with pitch S*8).  Results do not depend on the slicing (sites are independent). */
 int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
 {
     if (!h) return -1;
@@ -370,6 +409,9 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     if (check_forcing(h, f)) return -1;
     MC_CUDA(h, cudaSetDevice(h->device));
     const size_t S = (size_t)h->S, N = (size_t)h->N, H = 24 * (size_t)ndays, D = (size_t)ndays;
+    const size_t NSn = (size_t)h->model.n_snow;
+    struct Plane { const double* host_in; double* host_out; double* dev; size_t rows; };   /* [rows][S] planes */
+    std::vector<Plane> in_planes, out_planes;
     /* stage forcing */
     const double* hourly_src[11] = {f->pressure, f->reference_temperature, f->reference_wind_speed, f->reference_humidity, f->cloud_cover,
                                     f->global_radiation, f->diffuse_fraction, f->zenith_angle, f->zenith_slope_angle, f->rainfall_hourly, f->longwave_radiation};
@@ -386,13 +428,12 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     const double** daily_dst[8] = {&fd.leaf_area_index, &fd.shade, &fd.surface_emissivity, &fd.cloud_emissivity, &fd.soil_wetness, &fd.deep_soil_temperature,
                                    &fd.rainfall_daily, &fd.albedo_daily};
     double* p = h->stage_in;
-    for (int k = 0; k < 11; k++) if (hourly_src[k]) { MC_CUDA(h, cudaMemcpyAsync(p, hourly_src[k], H * S * sizeof(double), cudaMemcpyHostToDevice, h->stream)); *hourly_dst[k] = p; p += H * S; }
-    for (int k = 0; k < 8; k++) if (daily_src[k]) { MC_CUDA(h, cudaMemcpyAsync(p, daily_src[k], D * S * sizeof(double), cudaMemcpyHostToDevice, h->stream)); *daily_dst[k] = p; p += D * S; }
-    if (f->prescribed_soil_moisture) { MC_CUDA(h, cudaMemcpyAsync(p, f->prescribed_soil_moisture, D * N * S * sizeof(double), cudaMemcpyHostToDevice, h->stream)); fd.prescribed_soil_moisture = p; p += D * N * S; }
+    for (int k = 0; k < 11; k++) if (hourly_src[k]) { in_planes.push_back({hourly_src[k], nullptr, p, H}); *hourly_dst[k] = p; p += H * S; }
+    for (int k = 0; k < 8; k++) if (daily_src[k]) { in_planes.push_back({daily_src[k], nullptr, p, D}); *daily_dst[k] = p; p += D * S; }
+    if (f->prescribed_soil_moisture) { in_planes.push_back({f->prescribed_soil_moisture, nullptr, p, D * N}); fd.prescribed_soil_moisture = p; p += D * N * S; }
     fd.day_of_year = f->day_of_year;
     /* stage outputs */
     double* node_host[7] = {o->soil_temperature, o->soil_moisture, o->soil_water_potential, o->soil_humidity, o->soil_thermal_conductivity, o->soil_heat_capacity, o->soil_bulk_density};
-    const size_t NSn = (size_t)h->model.n_snow;
     double* scal_host[5] = {o->surface_water, o->sky_temperature, NSn ? o->snow_fall : nullptr, NSn ? o->snow_depth : nullptr, NSn ? o->snow_density : nullptr};
     double* snowT_host = NSn ? o->snow_temperature : nullptr;
     size_t need_out = 0;
@@ -404,21 +445,49 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     double** node_dev[7] = {&od.soil_temperature, &od.soil_moisture, &od.soil_water_potential, &od.soil_humidity, &od.soil_thermal_conductivity, &od.soil_heat_capacity, &od.soil_bulk_density};
     double** scal_dev[5] = {&od.surface_water, &od.sky_temperature, &od.snow_fall, &od.snow_depth, &od.snow_density};
     double* q = h->stage_out;
-    for (int k = 0; k < 7; k++) if (node_host[k]) { *node_dev[k] = q; q += H * N * S; }
-    for (int k = 0; k < 5; k++) if (scal_host[k]) { *scal_dev[k] = q; q += H * S; }
-    if (snowT_host) { od.snow_temperature = q; q += H * NSn * S; }
+    for (int k = 0; k < 7; k++) if (node_host[k]) { out_planes.push_back({nullptr, node_host[k], q, H * N}); *node_dev[k] = q; q += H * N * S; }
+    for (int k = 0; k < 5; k++) if (scal_host[k]) { out_planes.push_back({nullptr, scal_host[k], q, H}); *scal_dev[k] = q; q += H * S; }
+    if (snowT_host) { out_planes.push_back({nullptr, snowT_host, q, H * NSn}); od.snow_temperature = q; q += H * NSn * S; }
+
+    mcd::KArgs a;
+    if (int rc = prepare_chunk(h, day0, ndays, &fd, &od, a)) return rc;
     /* cells the path never writes (e.g. water potential rows under PrescribedSoilMoisture) read back as zero */
     if (need_out) MC_CUDA(h, cudaMemsetAsync(h->stage_out, 0, need_out * sizeof(double), h->stream));
-    int rc = mc_step_days_device(h, day0, ndays, &fd, &od);
-    if (rc < 0) return rc;
-    for (int k = 0; k < 7; k++) if (node_host[k]) MC_CUDA(h, cudaMemcpyAsync(node_host[k], *node_dev[k], H * N * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    for (int k = 0; k < 5; k++) if (scal_host[k]) MC_CUDA(h, cudaMemcpyAsync(scal_host[k], *scal_dev[k], H * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (snowT_host) MC_CUDA(h, cudaMemcpyAsync(snowT_host, od.snow_temperature, H * NSn * S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    MC_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));          /* model constants, day-of-year and the zeroed outputs are in place */
+    const char* want_env = getenv("MC_SLICES");                  /* development/test knob: force the number of slices */
+    const int want = want_env ? atoi(want_env) : 0;
+    /* default ONE slice: on B200 + PCIe Gen5 the pinned copies are ~3 % of a step, while splitting the launch costs more in
+     * per-slice tail (measured 1/2/4 slices at 1 Mi sites: 92.8 k / 91.5 k / 84.7 k site-days/s end to end) */
+    int n_slices = want > 0 ? want : 1;
+    if (n_slices > mc_handle::MAX_SLICES) n_slices = mc_handle::MAX_SLICES;
     std::vector<int32_t> status_tmp;
     int32_t* status_host = o->status;
     if (!status_host) { status_tmp.resize(S); status_host = status_tmp.data(); }
-    MC_CUDA(h, cudaMemcpyAsync(status_host, h->flags, S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    if ((rc = mc_synchronize(h)) < 0) return rc;
+    int prev_kernel = -1;
+    for (int k = 0; k < n_slices; k++) {
+        const size_t lo = S * (size_t)k / (size_t)n_slices, hi = S * (size_t)(k + 1) / (size_t)n_slices;
+        if (hi == lo) continue;
+        cudaStream_t st = h->slice_stream[k];
+        const size_t w = (hi - lo) * sizeof(double), pitch = S * sizeof(double);
+        MC_CUDA(h, cudaStreamWaitEvent(st, h->ev_ready, 0));
+        for (const Plane& pl : in_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.dev + lo, pitch, pl.host_in + lo, pitch, w, pl.rows, cudaMemcpyHostToDevice, st));
+        /* kernels run one after another (slice k+1 waits for slice k) so that the D2H of slice k overlaps the kernel of slice k+1;
+         * concurrent slice kernels would all finish together and leave every D2H at the end */
+        if (prev_kernel >= 0) MC_CUDA(h, cudaStreamWaitEvent(st, h->ev_kernel[prev_kernel], 0));
+        if (int rc = launch_range(h, a, (int64_t)lo, (int64_t)hi, st)) return rc;
+        MC_CUDA(h, cudaEventRecord(h->ev_kernel[k], st));
+        prev_kernel = k;
+        for (const Plane& pl : out_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.host_out + lo, pitch, pl.dev + lo, pitch, w, pl.rows, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(h, cudaMemcpyAsync(status_host + lo, h->flags + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MC_CUDA(h, cudaEventRecord(h->ev_slice[k], st));
+        MC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_slice[k], 0));
+    }
+    MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    h->last_launches = (unsigned long long)n_slices;
+    h->days_done += ndays;
+    int rc = mc_synchronize(h);
+    if (rc < 0) return rc;
     int nbad = 0;
     for (size_t i = 0; i < S; i++) if (status_host[i]) nbad++;
     return nbad;

@@ -34,6 +34,7 @@
 #define MC_DEV_NOINLINE __device__ __noinline__
 #define MC_LDG(p) __ldg(p)
 #define MC_ROLLED _Pragma("unroll 1")
+#define MC_UNROLL4 _Pragma("unroll 4")
 #define MC_CONST_MODEL g_model_c
 #else
 #include <cmath>
@@ -42,6 +43,7 @@
 #define MC_DEV_NOINLINE static __attribute__((noinline))
 #define MC_LDG(p) (*(p))
 #define MC_ROLLED
+#define MC_UNROLL4
 #define MC_CONST_MODEL g_model_h
 #endif
 
@@ -87,7 +89,8 @@ static DevModel g_model_h;
 
 /* ---- kernel arguments: every array is site-fastest SoA (x[node][site], f[hour][site]) ---- */
 struct KArgs {
-    int64_t S;        /* sites in this launch */
+    int64_t S;        /* sites of the handle = stride of every SoA array */
+    int64_t s_begin, s_end;   /* site range [s_begin, s_end) this launch integrates (pipelined site slices) */
     int64_t day0;     /* global index of the first day of the chunk */
     int32_t ndays;    /* days in the chunk */
     int32_t has_init_T, has_albedo_daily, has_lw, has_presc;
@@ -277,14 +280,14 @@ MC_DEV double devries_weight(double lam_c, double lam_f, double ga, double gc)
     const double r1 = lam_c / lam_f - 1.0;
     return 2.0 / (3.0 * (1.0 + ga * r1)) + 1.0 / (3.0 * (1.0 + gc * r1));
 }
-MC_DEV_NOINLINE double soil_conductivity(double T, double P, double theta, double phim, double phig, double fw, double lam_m)
+MC_DEV_NOINLINE double soil_conductivity(double T, double P, double p0_over_p, double p_over_p0, double theta, double phim, double phig, double fw, double lam_m)
 {
     const DevModel& m = MC_CONST_MODEL;
     const double Tc = T - T0C;
     const double lam_w = 0.554 + 2.24e-3 * Tc - 9.87e-6 * Tc * Tc;
     const double lam_a = 0.024 + 7.73e-5 * Tc - 2.6e-8 * Tc * Tc;
-    const double Dv = 2.12e-5 * (m.P0 / P) * mcm::pow(T / 273.15, 1.75);      /* campbell_devries.jl:109 */
-    const double rho_hat = 44.65 * (P / m.P0) * (273.15 / T);                   /* :111 */
+    const double Dv = 2.12e-5 * p0_over_p * mcm::pow(T / 273.15, 1.75);       /* campbell_devries.jl:109; p0_over_p = P0/P hoisted by the caller */
+    const double rho_hat = 44.65 * p_over_p0 * (273.15 / T);                    /* :111 */
     const double Hv = m.Hv_a - m.Hv_b * (T - T0C);
 #if MC_USE_GG3
     const GG3 gg = goff_gratch3(T);
@@ -315,7 +318,7 @@ MC_DEV void soil_properties_full(double T, double P, double theta, double bd, do
     const double phim = bd / md;
     const double phig = jmax(0.0, 1.0 - theta - phim);
     const double fw = 1.0 / (1.0 + mcm::pow(theta / m.theta0, -m.recirc_pow));
-    lam = soil_conductivity(T, P, theta, phim, phig, fw, lam_m);
+    lam = soil_conductivity(T, P, m.P0 / P, P / m.P0, theta, phim, phig, fw, lam_m);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -342,17 +345,23 @@ MC_DEV_NOINLINE void soil_rhs(const HourSoil<NA>& hs, const HourPar& hp, const d
     const double cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
     const double rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
 
-    /* conduction: node conductance G_i = lambda_i(T_i) / dz_i, built on the fly so only two live at a time */
+    /* conduction: node conductance G_i = lambda_i(T_i) / dz_i, built on the fly so only two live at a time; the next node's
+     * hoisted terms are loaded BEFORE the long conductivity call so their latency hides behind it */
     const double Ts_node = jclamp(u[0], T_LO, m.T_hi);
     double T_up = Ts_node;
-    double G_up = soil_conductivity(T_up, P, hs.theta[0], hs.phim[0], hs.phig[0], hs.fw[0], hs.lam_m[0]) / m.dzg[0];
+    double th = hs.theta[1], pm = hs.phim[1], pg = hs.phig[1], fw = hs.fw[1], lm = hs.lam_m[1], cap = hs.cap[1];
     double T_i = jclamp(u[1], T_LO, m.T_hi);
+    const double p0p = m.P0 / P, pp0 = P / m.P0;
+    double G_up = soil_conductivity(T_up, P, p0p, pp0, hs.theta[0], hs.phim[0], hs.phig[0], hs.fw[0], hs.lam_m[0]) / m.dzg[0];
     const double Q_cond = G_up * (T_i - Ts_node);
     MC_ROLLED for (int i = 1; i < N - 1; i++) {
+        const int in = i + 1 < N - 1 ? i + 1 : i;
         const double T_dn = jclamp(u[i + 1], T_LO, m.T_hi);
-        const double G_i = soil_conductivity(T_i, P, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]) / m.dzg[i];
-        du[i] = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / hs.cap[i];
+        const double nth = hs.theta[in], npm = hs.phim[in], npg = hs.phig[in], nfw = hs.fw[in], nlm = hs.lam_m[in], ncap = hs.cap[in];
+        const double G_i = soil_conductivity(T_i, P, p0p, pp0, th, pm, pg, fw, lm) / m.dzg[i];
+        du[i] = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / cap;
         T_up = T_i; T_i = T_dn; G_up = G_i;
+        th = nth; pm = npm; pg = npg; fw = nfw; lm = nlm; cap = ncap;
     }
     du[N - 1] = 0.0;                                         /* Dirichlet bottom node (:291-293) */
 
@@ -672,8 +681,9 @@ MC_DEV_NOINLINE void soil_rhs_snow(const HourSoil<NA>& hs, const HourPar& hp, co
     const double rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
     double T[NA + NSN], lam[NA + NSN], vhc[NA + NSN], C[NA + NSN], G[NA + NSN];
     MC_ROLLED for (int i = 0; i < M; i++) T[i] = jclamp(u[i], T_LO, m.T_hi);
+    const double p0p = m.P0 / P, pp0 = P / m.P0;
     MC_ROLLED for (int i = 0; i < N; i++) {
-        lam[ns + i] = soil_conductivity(T[ns + i], P, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]);
+        lam[ns + i] = soil_conductivity(T[ns + i], P, p0p, pp0, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]);
         vhc[ns + i] = hs.cap[i];
     }
     {   /* write_snow_properties!, snow_model.jl:171-208 */
@@ -851,13 +861,13 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA + NS>& I, const HourSoil<NA>& hs, const
             if (!I.accept) {
                 I.dt = I.dt / fmin(5.0, I.q11 / 0.9);
             } else {
-                MC_ROLLED for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
+                MC_UNROLL4 for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
                 I.dt = I.dtpropose;
                 if (I.u_modified) rhs_dispatch<NA, NS>(hs, hp, I.u, I.t, I.k1, cn);
-                else MC_ROLLED for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
+                else MC_UNROLL4 for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
             }
         } else if (I.u_modified) {
-            MC_ROLLED for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
+            MC_UNROLL4 for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
         }
         I.iter++;
         I.dt = fmin(1440.0, I.dt);
@@ -865,24 +875,24 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA + NS>& I, const HourSoil<NA>& hs, const
         if (!(I.dt > 1e-12) || ++guard > 100000) {
             I.flags |= (I.dt != I.dt) ? MC_STATUS_NAN : (guard > 100000 ? MC_STATUS_STEP_LIMIT : MC_STATUS_DT_UNDERFLOW);
             I.t = I.tstop; I.accept = true; I.dtpropose = 1.0;
-            MC_ROLLED for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
+            MC_UNROLL4 for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
             return;
         }
         const double t = I.t, dt = I.dt;
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
         rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c1 * dt, I.k2, cn);
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
         rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c2 * dt, I.k3, cn);
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
         rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c3 * dt, I.k4, cn);
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
         rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c4 * dt, I.k5, cn);
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
         rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + dt, I.k6, cn);
-        MC_ROLLED for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
         rhs_dispatch<NA, NS>(hs, hp, I.u, t + dt, I.k7, cn);
         double ss = 0.0;
-        MC_ROLLED for (int i = 0; i < N; i++) {
+        MC_UNROLL4 for (int i = 0; i < N; i++) {
             const double ut = dt * (bt1 * I.k1[i] + bt2 * I.k2[i] + bt3 * I.k3[i] + bt4 * I.k4[i] + bt5 * I.k5[i] + bt6 * I.k6[i] + bt7 * I.k7[i]);
             const double q = ut / (m.abstol + fmax(fabs(I.uprev[i]), fabs(I.u[i])) * m.reltol);
             ss += q * q;
@@ -909,7 +919,7 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA + NS>& I, const HourSoil<NA>& hs, const
             return;
         }
         cn.n_reject++;
-        MC_ROLLED for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
+        MC_UNROLL4 for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
     }
 }
 
@@ -1089,6 +1099,114 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
     return out;
 }
 
+
+/* infiltration_step! for the matric-potential algorithm (the default), restructured for a GPU thread: the reference's seven
+ * separate passes over the node arrays per Newton iteration (conductivity, vapour flux, assembly, Thomas forward elimination,
+ * back-substitution, water-content recovery, humidity) are fused into ONE forward and ONE backward sweep that carry the
+ * neighbour values in registers, so the thread-local arrays shrink from 16 to 6 and each is read/written once per sweep.
+ * Every floating-point operation is the reference's, in the reference's order per node (results are bit-identical to the
+ * unfused form, which the oracle keeps). */
+template <int NA>
+MC_DEV_NOINLINE InfilOut infiltration_step_psi(const HourMoist<NA>& hm, InfilWork<NA>& B, double* theta, double rh_loc, double lai, double ET, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    cn.n_infil++;
+    const int L = m.N;
+    const double g = m.g, dt = m.moist_dt;
+    const double EP = mcm::exp(-0.82 * lai) * ET;
+    const double TP = ET - EP;
+    /* initial state from water content + root/soil resistances (campbell.jl:215-267) */
+    double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
+    MC_ROLLED for (int i = 2; i <= L; i++) {
+        const double wcn = theta[i - 2];
+        const double psi = hm.psi_e[i] * mcm::pow(hm.sat[i] / wcn, hm.bb[i]);
+        const double K = hm.ks[i] * mcm::pow(hm.psi_e[i] / psi, hm.nexp[i]);
+        B.wcn[i] = wcn; B.psi[i] = psi;
+        B.h[i] = mcm::exp(MW_INFIL * psi / hm.rts[i]);
+        const double soilR = hm.rootZ[i] / K;
+        B.soilR[i] = soilR;
+        const double rt = soilR + hm.rootR[i];
+        psum += psi / rt;
+        rsum += 1.0 / rt;
+    }
+    B.psi[L + 1] = hm.psi_e[L]; B.h[L + 1] = 1.0; B.wcn[L + 1] = hm.sat[L + 1];
+    const double psi1 = B.psi[2];                                           /* water_potential[1] = water_potential[2], never updated again */
+    const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
+    const double RL = m.RL, PC = m.PC, SP = m.SP;
+    int counter = 0;
+    while (counter < m.moist_max_it) {                                       /* stomatal Newton, campbell.jl:270-284 */
+        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
+        const double xp = mcm::pow(psi_leaf / PC, SP);
+        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
+        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
+        psi_leaf = psi_leaf - resid / slope;
+        counter++;
+        if (fabs(resid) <= 10.0) break;
+    }
+    const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
+    MC_ROLLED for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
+
+    InfilOut out; out.hit_max = true;
+    double K2 = 0.0, K3 = 0.0;
+    counter = 0;
+    while (counter < m.moist_max_it) {                                       /* Newton loop, campbell.jl:293-336 */
+        double err = 0.0;
+        counter++; cn.n_newton++;
+        /* ---- forward sweep: conductivity, vapour flux, assembly, Thomas elimination ---- */
+        double Km = 0.0, psim = psi1;                                        /* K[1] = 0, psi[1] */
+        double jvm = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc);
+        double djvm = EP * MW_INFIL * B.h[2] / (hm.rts1 * (1.0 - rh_loc));
+        double psic = B.psi[2], wcnc = B.wcn[2], hc = B.h[2];
+        double Kc = hm.ks[2] * mcm::pow(hm.psi_e[2] / psic, hm.nexp[2]);
+        double ccm = 0.0, rrm = 0.0, diaL = 0.0, FL = 0.0;
+        MC_ROLLED for (int i = 2; i <= L; i++) {
+            const double psip = B.psi[i + 1], wcnp = B.wcn[i + 1], hp = B.h[i + 1];
+            const double Kp = i + 1 <= L ? hm.ks[i + 1] * mcm::pow(hm.psi_e[i + 1] / psip, hm.nexp[i + 1]) : hm.ks[L];
+            if (i == 2) { K2 = Kc; K3 = Kp; }
+            const double kv = hm.kvc[i] * (hm.sat[i] - (wcnc + wcnp) / 2.0) / hm.dz[i];
+            const double jvi = kv * (hp - hc);
+            const double djvi = MW_INFIL * hc * kv / hm.rts[i];
+            const double cap = -1.0 * hm.mass[i] * wcnc / (hm.bb[i] * psic * dt);
+            const double sub = -1.0 * Km / hm.dz[i - 1] + g * hm.nexp[i] * Km / psim;
+            const double sup = -1.0 * Kp / hm.dz[i];
+            double dia = Kc / hm.dz[i - 1] + Kc / hm.dz[i] + cap - g * hm.nexp[i] * Kc / psic + djvm + djvi;
+            double F = ((psic * Kc - psim * Km) / hm.dz[i - 1] - (psip * Kp - psic * Kc) / hm.dz[i]) / (1.0 - hm.nexp[i])
+                     + hm.mass[i] * (wcnc - theta[i - 2]) / dt - g * (Km - Kc) + jvm - jvi + B.uptake[i];
+            err += fabs(F);
+            if (i >= 3) { dia -= sub * ccm; F -= sub * rrm; }               /* elimination step owed by row i-1 */
+            if (i <= L - 1) {
+                double cc = sup / dia;
+                if (fabs(cc) < 1e-8) cc = 0.0;
+                const double rr = F / dia;
+                B.cc[i] = cc; B.rr[i] = rr; ccm = cc; rrm = rr;
+            } else { diaL = dia; FL = F; }
+            Km = Kc; psim = psic; jvm = jvi; djvm = djvi;
+            Kc = Kp; psic = psip; wcnc = wcnp; hc = hp;
+        }
+        /* ---- backward sweep: back-substitution with the saturation clamps, water content, humidity ---- */
+        double dpsi = FL / diaL;
+        MC_ROLLED for (int i = L; i >= 2; i--) {
+            double psi = B.psi[i];
+            if (i == L) psi = jmin(psi - dpsi, hm.psi_e[L]);
+            else {
+                dpsi = B.rr[i] - B.cc[i] * dpsi;
+                psi -= dpsi;
+                if (psi > hm.psi_e[i]) psi = (psi + dpsi + hm.psi_e[i]) / 2.0;
+            }
+            const double wcn = jmax(hm.sat[i] * mcm::pow(hm.psi_e[i] / psi, 1.0 / hm.bb[i]), 1e-7);
+            psi = hm.psi_e[i] * mcm::pow(hm.sat[i] / wcn, hm.bb[i]);
+            B.wcn[i] = wcn; B.psi[i] = psi;
+            B.h[i] = mcm::exp(MW_INFIL * psi / hm.rts[i]);
+        }
+        B.h[L + 1] = B.h[L];
+        if (err <= m.moist_tol) { out.hit_max = false; break; }
+    }
+    out.surface_water_flux = ((B.psi[2] * K2 - B.psi[3] * K3) / ((1.0 - hm.nexp[2]) * hm.dz[2]) + g * K2 + TR) * dt;
+    MC_ROLLED for (int i = 2; i <= L + 1; i++) theta[i - 2] = B.wcn[i];
+    out.evaporation = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc) * dt;
+    return out;
+}
+
 MC_DEV double wet_surface_node(double* theta, double pool, double sat, double half_thickness)
 {
     if (pool <= 0.0) return pool;
@@ -1210,7 +1328,7 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     InfilWork<NA> B;
     InfilOut io; io.evaporation = 0.0; io.surface_water_flux = 0.0; io.hit_max = false;
     MC_ROLLED for (int k = 0; k < m.niter_moist; k++) {
-        io = infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn);
+        io = m.flux_alg ? infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn) : infiltration_step_psi<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn);
         if (io.hit_max) flags |= MC_STATUS_NEWTON_MAXITER;
         pool = jclamp(pool - jmax(0.0, io.surface_water_flux) - jmax(0.0, io.evaporation), 0.0, m.max_pool);
         pool = wet_surface_node(theta, pool, sat0, half);

@@ -1126,6 +1126,8 @@ struct SiteState {
     double Ts[NSN]; SnowState snow; SnowScratch snow_scratch; double sd_last, Q_freeze;
 };
 
+static int32_t* g_trace_attempts = nullptr; static int32_t* g_trace_newton = nullptr; static int64_t g_trace_rows = 0;
+
 struct SiteIO {
     /* inputs for the chunk, per-site gathered views (strided access through lambdas below) */
     int64_t S, s; int ndays;
@@ -1368,7 +1370,9 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
                 for (int k = 0; k < N; k++) { T0_before[k] = T0[k]; p.theta[k] = theta[k]; }
                 for (int k = 0; k < ns; k++) Ts_before[k] = Ts[k];
                 p.L_prev = st.L_ode;
+                const uint64_t att0 = cn.n_accept + cn.n_reject, new0 = cn.n_newton;
                 step_to_hour(I, i + 1, p, cn);
+                if (g_trace_attempts && step < g_trace_rows) g_trace_attempts[io.s * g_trace_rows + step] += (int32_t)(cn.n_accept + cn.n_reject - att0);
                 for (int k = 0; k < ns; k++) Ts[k] = I.u[k];
                 for (int k = 0; k < N; k++) T0[k] = I.u[ns + k];
                 if (is_last) {                                                               /* :645-650 */
@@ -1441,6 +1445,7 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
                         soil_wetness_dyn = w.soil_wetness; pool = w.pool; have_infil = true;
                     }
                 }
+                if (g_trace_newton && step < g_trace_rows) g_trace_newton[io.s * g_trace_rows + step] += (int32_t)(cn.n_newton - new0);
                 const int out_row = step + 1;                                                /* :782-798 */
                 const bool in_bounds = out_row < nrows;   /* rows past the chunk belong to the next chunk's day pre-fill */
                 const bool crosses_day = (i == 23);
@@ -1643,6 +1648,8 @@ int mco_infiltration_steps(const mc_model_desc* m, const mc_sites_soa* site1, do
     return iters;
 }
 double mco_fastpow(double x, double y) { return mco::fastpow(x, y); }
+/* analysis hook: per-site per-hour RK attempts / Newton iterations of the NEXT mco_step_days call ([S][rows] int32, zero-initialised by the caller) */
+void mco_set_trace(int32_t* attempts, int32_t* newton, int64_t rows) { mco::g_trace_attempts = attempts; mco::g_trace_newton = newton; mco::g_trace_rows = rows; }
 /* phase_transition! white box */
 void mco_phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
 {

@@ -164,3 +164,19 @@ def test_snow_model_matches_oracle(SoilEngine):
     st.step_days(0, forcing.day_slice(0, 2), o1)
     state = st.get_state()
     assert state.snow_state is not None and state.snow_state[0, 0] == o1.snow_depth[-1, 0]      # current depth is carried
+
+
+def test_pipelined_site_slices_do_not_change_results(SoilEngine, synth, monkeypatch):
+    """mc_step_days cuts the site range into slices on separate streams (H2D / kernel / D2H overlap); forcing 3 ragged slices on
+    512 sites must give the single-launch result bit for bit."""
+    desc, sites, forcing = synth
+    f = ("soil_temperature", "soil_moisture", "surface_water", "sky_temperature")
+    monkeypatch.setenv("MC_SLICES", "1")
+    one, _ = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    monkeypatch.setenv("MC_SLICES", "3")
+    three, e3 = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
+    assert e3.counters()["n_kernel_launches"] == 3
+    for name in f:
+        a, b = getattr(one, name), getattr(three, name)
+        assert np.array_equal(a[..., :509], b), name
+    assert np.array_equal(one.status[:509], three.status)
