@@ -19,6 +19,9 @@
  */
 #ifndef MC_MATH_H
 #define MC_MATH_H
+#ifndef MCM_DIV_NOINLINE
+#define MCM_DIV_NOINLINE 0
+#endif
 
 #include <stdint.h>
 #include <math.h>
@@ -34,6 +37,13 @@
 #endif
 
 namespace mcm {
+
+#if defined(__CUDA_ARCH__) && MCM_DIV_NOINLINE
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+#define MCM_DIV(a, b) mcm::ddiv((a), (b))
+#else
+#define MCM_DIV(a, b) ((a) / (b))
+#endif
 
 #if defined(__CUDA_ARCH__)
 MCM_FN uint64_t d2u(double x) { return (uint64_t)__double_as_longlong(x); }
@@ -146,7 +156,7 @@ MCM_HEAVY double log_slow(double x)
     const double m = with_hi(xs, hx | (i0 ^ 0x3ff00000));
     k += (i0 >> 20);
     const double f = m - 1.0, dk = (double)k;
-    const double s = f / (2.0 + f), z = s * s, w = z * z;
+    const double s = MCM_DIV(f, 2.0 + f), z = s * s, w = z * z;
     const double t1 = w * ffma(w, ffma(w, MCM_TAB[20], MCM_TAB[18]), MCM_TAB[16]);
     const double t2 = z * ffma(w, ffma(w, ffma(w, MCM_TAB[21], MCM_TAB[19]), MCM_TAB[17]), MCM_TAB[15]);
     const double R = t2 + t1, hfsq = 0.5 * f * f;
@@ -164,7 +174,7 @@ MCM_FN double log_core(double x)
     const double m = with_hi(x, hx | (i0 ^ 0x3ff00000));      /* m in [sqrt(2)/2, sqrt(2)) */
     k += (i0 >> 20);
     const double f = m - 1.0, dk = (double)k;
-    const double s = f / (2.0 + f), z = s * s, w = z * z;
+    const double s = MCM_DIV(f, 2.0 + f), z = s * s, w = z * z;
     const double t1 = w * ffma(w, ffma(w, MCM_TAB[20], MCM_TAB[18]), MCM_TAB[16]);
     const double t2 = z * ffma(w, ffma(w, ffma(w, MCM_TAB[21], MCM_TAB[19]), MCM_TAB[17]), MCM_TAB[15]);
     const double R = t2 + t1, hfsq = 0.5 * f * f;

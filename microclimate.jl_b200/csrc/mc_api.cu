@@ -30,12 +30,13 @@ thread_local std::string g_create_error;
         }                                                                                                      \
     } while (0)
 
-/* 64-thread blocks, 8 resident per SM (128 registers/thread, 16 warps/SM): measured best on B200 (profiles/README.md) */
+/* 64-thread blocks, 16 resident per SM = 32 warps/SM at 64 registers/thread: the measured optimum on B200 (occupancy sweep in
+ * profiles/README.md: 16 / 20 / 24 / 32 / 40 / 48 / 64 warps per SM -> 92 / 90 / 94 / 105 / 103 / 99 / 93 k site-days/s) */
 #ifndef MC_BLOCK
 #define MC_BLOCK 64
 #endif
 #ifndef MC_MIN_BLOCKS
-#define MC_MIN_BLOCKS 8
+#define MC_MIN_BLOCKS 16
 #endif
 constexpr int BLOCK = MC_BLOCK;
 

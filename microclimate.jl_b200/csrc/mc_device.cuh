@@ -34,7 +34,14 @@
 #define MC_DEV_NOINLINE __device__ __noinline__
 #define MC_LDG(p) __ldg(p)
 #define MC_ROLLED _Pragma("unroll 1")
+#ifndef MC_TSIT5_ROLLED
+#define MC_TSIT5_ROLLED 0
+#endif
+#if MC_TSIT5_ROLLED
+#define MC_UNROLL4 _Pragma("unroll 1")
+#else
 #define MC_UNROLL4 _Pragma("unroll 4")
+#endif
 #define MC_CONST_MODEL g_model_c
 #else
 #include <cmath>
@@ -127,12 +134,12 @@ MC_DEV_NOINLINE double goff_gratch(double T)
     const double Tp = T + 0.01;
     double loge;
     if (Tp <= 273.16) {
-        const double r = 273.16 / Tp;
-        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - Tp / 273.16) + 0.7858350313586662 /* mcm::log10(6.1071) */;
+        const double r = MCM_DIV(273.16, Tp);
+        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - MCM_DIV(Tp, 273.16)) + 0.7858350313586662 /* mcm::log10(6.1071) */;
     } else {
-        const double r = 373.16 / Tp;
+        const double r = MCM_DIV(373.16, Tp);
         loge = -7.90298 * (r - 1.0) + 5.02808 * mcm::log10(r)
-             - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - Tp / 373.16)) - 1.0)
+             - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - MCM_DIV(Tp, 373.16))) - 1.0)
              + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314 /* mcm::log10(1013.246) */;
     }
     return 100.0 * mcm::exp10(loge);
@@ -275,10 +282,18 @@ MC_DEV double knot_lerp(const double* base, int64_t S, int i, double d)
 }
 
 /* Campbell-de Vries bulk conductivity of one node (campbell_devries.jl:79-142), T-dependent part only */
-MC_DEV double devries_weight(double lam_c, double lam_f, double ga, double gc)
+#ifndef MC_WEIGHT_NOINLINE
+#define MC_WEIGHT_NOINLINE 0
+#endif
+#if MC_WEIGHT_NOINLINE
+MC_DEV_NOINLINE
+#else
+MC_DEV
+#endif
+double devries_weight(double lam_c, double lam_f, double ga, double gc)
 {
-    const double r1 = lam_c / lam_f - 1.0;
-    return 2.0 / (3.0 * (1.0 + ga * r1)) + 1.0 / (3.0 * (1.0 + gc * r1));
+    const double r1 = MCM_DIV(lam_c, lam_f) - 1.0;
+    return MCM_DIV(2.0, 3.0 * (1.0 + ga * r1)) + MCM_DIV(1.0, 3.0 * (1.0 + gc * r1));
 }
 MC_DEV_NOINLINE double soil_conductivity(double T, double P, double p0_over_p, double p_over_p0, double theta, double phim, double phig, double fw, double lam_m)
 {
@@ -286,8 +301,8 @@ MC_DEV_NOINLINE double soil_conductivity(double T, double P, double p0_over_p, d
     const double Tc = T - T0C;
     const double lam_w = 0.554 + 2.24e-3 * Tc - 9.87e-6 * Tc * Tc;
     const double lam_a = 0.024 + 7.73e-5 * Tc - 2.6e-8 * Tc * Tc;
-    const double Dv = 2.12e-5 * p0_over_p * mcm::pow(T / 273.15, 1.75);       /* campbell_devries.jl:109; p0_over_p = P0/P hoisted by the caller */
-    const double rho_hat = 44.65 * p_over_p0 * (273.15 / T);                    /* :111 */
+    const double Dv = 2.12e-5 * p0_over_p * mcm::pow(MCM_DIV(T, 273.15), 1.75);       /* campbell_devries.jl:109; p0_over_p = P0/P hoisted by the caller */
+    const double rho_hat = 44.65 * p_over_p0 * MCM_DIV(273.15, T);                    /* :111 */
     const double Hv = m.Hv_a - m.Hv_b * (T - T0C);
 #if MC_USE_GG3
     const GG3 gg = goff_gratch3(T);
@@ -300,12 +315,12 @@ MC_DEV_NOINLINE double soil_conductivity(double T, double P, double p0_over_p, d
     const double ep = goff_gratch(T + 1.0) * 0.99;
 #endif
     const double dedT = (ep - em) / 2.0;
-    const double lam_g = lam_a + Hv * dedT * fw * rho_hat * Dv / (P - e0);
+    const double lam_g = lam_a + MCM_DIV(Hv * dedT * fw * rho_hat * Dv, P - e0);
     const double lam_f = lam_g + fw * (lam_w - lam_g);
     const double ww = devries_weight(lam_w, lam_f, m.ga, m.gc);
     const double wm = devries_weight(lam_m, lam_f, m.ga, m.gc);
     const double wg = devries_weight(lam_g, lam_f, m.ga, m.gc);
-    return (theta * ww * lam_w + phim * wm * lam_m + phig * wg * lam_g) / (theta * ww + phim * wm + phig * wg);
+    return MCM_DIV(theta * ww * lam_w + phim * wm * lam_m + phig * wg * lam_g, theta * ww + phim * wm + phig * wg);
 }
 
 /* full soil_properties for the output rows (update_soil_properties!, simulation.jl:905-913) */
