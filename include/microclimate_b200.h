@@ -35,6 +35,7 @@ extern "C" {
 #define MC_SNOW_NODES 8
 #define MC_MAX_ODE_NODES (MC_MAX_SOIL_NODES + MC_SNOW_NODES)
 #define MC_HOURS_PER_DAY 24
+#define MC_MAX_HEIGHTS 16
 
 /* enums mirror the reference's strategy singletons */
 enum { MC_TIME_NONCONSECUTIVE = 0, MC_TIME_CONSECUTIVE = 1 };   /* src/time_mode/{non_consecutive,consecutive}.jl */
@@ -108,6 +109,9 @@ typedef struct mc_model_desc {
     double  depths_m[MC_MAX_SOIL_NODES];    /* MicroModel.depths, metres */
     double  reference_height_m;             /* last(heights) */
     double  local_height_m;                 /* first(heights) */
+    int32_t n_heights;                      /* length(MicroModel.heights): air nodes of solve_air! (src/simulation.jl:822-851) */
+    int32_t _pad1;
+    double  heights_m[MC_MAX_HEIGHTS];      /* MicroModel.heights, metres; the last one is the reference height */
     /* SoilHeatTransport1D */
     double  reltol, abstol;                 /* 1e-6, 1e-3 (K) */
     double  maximum_surface_temperature_K;  /* 85 degC = 358.15 */
@@ -190,6 +194,7 @@ typedef struct mc_state_soa {
     double* snow_state;         /* [MC_SNOW_STATE_FIELDS][S] (n_snow>0) or NULL */
     double* snow_node_depths;   /* [8][S] cm (n_snow>0) or NULL */
     double* q_freeze;           /* [S] W/m2 (n_snow>0) or NULL */
+    double* obukhov_air;        /* [S] m   buffers.air_profile.obukhov_length_prev (solve_air!) */
     int64_t* days_done;         /* [1] days integrated so far (global day index of the next day) */
 } mc_state_soa;
 #define MC_SNOW_STATE_FIELDS 10 /* depth, age, days_since_snow, density, prev_density, cum_melt, extra_snow, active_nodes, sum_phase, prev_hour_depth */
@@ -245,6 +250,13 @@ typedef struct mc_output_soa {
     double* snow_depth;                /* [H][S] cm */
     double* snow_density;              /* [H][S] g/cm3 */
     double* snow_temperature;          /* [H][8][S] K */
+    /* solve_air! (src/simulation.jl:822-851): MOST profiles from the final surface temperature; needs soil_temperature (and, with
+     * snow, snow_depth + snow_temperature) selected as well.  NULL = do not run solve_air! */
+    double* air_temperature;           /* [H][n_heights][S] K */
+    double* wind_speed;                /* [H][n_heights][S] m/s */
+    double* relative_humidity;         /* [H][n_heights][S] */
+    double* convective_heat_flux;      /* [H][S] W/m2 */
+    double* friction_velocity;         /* [H][S] m/s */
     int32_t* status;                   /* [S] MC_STATUS_* bits, or NULL */
 } mc_output_soa;
 

@@ -15,6 +15,7 @@ import Microclimate: MicroModel, MicroInputs, MicroProblem, MicroCache, NoSnow, 
 const LIB = get(ENV, "MICROCLIMATE_B200_LIB", joinpath(@__DIR__, "..", "microclimate.jl_b200", "csrc", "libmicroclimate_b200.so"))
 const MC_MAX_SOIL_NODES = 24
 const MC_SNOW_NODES = 8
+const MC_MAX_HEIGHTS = 16
 
 # ---- POD mirrors of include/microclimate_b200.h (field order and types must match the header) -----------------
 struct McFluid
@@ -36,6 +37,8 @@ struct McModel
     n_soil::Cint; n_snow::Cint
     depths_m::NTuple{MC_MAX_SOIL_NODES,Cdouble}
     reference_height_m::Cdouble; local_height_m::Cdouble
+    n_heights::Cint; _pad1::Cint
+    heights_m::NTuple{MC_MAX_HEIGHTS,Cdouble}
     reltol::Cdouble; abstol::Cdouble; maximum_surface_temperature_K::Cdouble
     de_vries_shape_factor::Cdouble; recirculation_power::Cdouble; return_flow_threshold::Cdouble
     root_resistance::Cdouble; stomatal_closure_potential::Cdouble; leaf_resistance::Cdouble
@@ -54,7 +57,8 @@ end
 struct McSites;   p::NTuple{12,Ptr{Cdouble}}; end           # roughness … root_density (header order)
 struct McInitial; T::Ptr{Cdouble}; theta::Ptr{Cdouble}; end
 struct McForcing; hourly::NTuple{11,Ptr{Cdouble}}; daily::NTuple{8,Ptr{Cdouble}}; prescribed::Ptr{Cdouble}; doy::Ptr{Cint}; end
-struct McOutput;  node::NTuple{7,Ptr{Cdouble}}; scalar::NTuple{5,Ptr{Cdouble}}; snow_T::Ptr{Cdouble}; status::Ptr{Cint}; end
+struct McOutput;  node::NTuple{7,Ptr{Cdouble}}; scalar::NTuple{5,Ptr{Cdouble}}; snow_T::Ptr{Cdouble}
+                  profile::NTuple{3,Ptr{Cdouble}}; profile_scalar::NTuple{2,Ptr{Cdouble}}; status::Ptr{Cint}; end   # profile = solve_air! outputs (NULL = skip)
 
 check(h, rc, what) = rc < 0 ? error("$what failed (rc=$rc): " * unsafe_string(ccall((:mc_last_error, LIB), Cstring, (Ptr{Cvoid},), h))) : rc
 
@@ -75,6 +79,7 @@ function model_desc(model::MicroModel, time_mode)
     dyn = sm isa DynamicSoilMoisture
     McModel(N, model.snow_model isa NoSnow ? 0 : MC_SNOW_NODES, depths,
         si(last(model.heights), u"m"), si(first(model.heights), u"m"),
+        length(model.heights), 0, ntuple(i -> i <= length(model.heights) ? si(model.heights[i], u"m") : 0.0, MC_MAX_HEIGHTS),
         ustrip(sem.ode_kwargs.reltol), si(sem.ode_kwargs.abstol, u"K"), si(u"K"(sem.maximum_surface_temperature), u"K"),
         sp.de_vries_shape_factor, sp.recirculation_power, sp.return_flow_threshold,
         si(sh.root_resistance, u"m^3/kg/s"), si(sh.stomatal_closure_potential, u"J/kg"), si(sh.leaf_resistance, u"m^4/kg/s"),
@@ -145,7 +150,7 @@ function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integ
             check(h[], ccall((:mc_set_sites, LIB), Cint, (Ptr{Cvoid}, Ref{McSites}, Ref{McInitial}), h[], sites, init), "mc_set_sites")
             forcing = Ref(McForcing(map(ptr, hourly_arrays), map(ptr, daily_arrays), Ptr{Cdouble}(C_NULL), pointer(doy)))
             out = Ref(McOutput(map(pointer, node_out), (pointer(scal_out[1]), pointer(scal_out[2]), Ptr{Cdouble}(C_NULL), Ptr{Cdouble}(C_NULL), Ptr{Cdouble}(C_NULL)),
-                               Ptr{Cdouble}(C_NULL), pointer(status)))
+                               Ptr{Cdouble}(C_NULL), ntuple(_ -> Ptr{Cdouble}(C_NULL), 3), ntuple(_ -> Ptr{Cdouble}(C_NULL), 2), pointer(status)))   # pass profile buffers here to run solve_air! on the GPU too
             check(h[], ccall((:mc_step_days, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ref{McForcing}, Ref{McOutput}), h[], 0, D, forcing, out), "mc_step_days")
         end
         # ---- un-marshal into each cache's MicroResult (nsteps × N, unit-tagged) so solve_air! runs unchanged ----------

@@ -9,6 +9,7 @@ MC_MAX_SOIL_NODES = 24
 MC_SNOW_NODES = 8
 MC_MAX_ODE_NODES = MC_MAX_SOIL_NODES + MC_SNOW_NODES
 MC_SNOW_STATE_FIELDS = 10
+MC_MAX_HEIGHTS = 16
 
 MC_TIME_NONCONSECUTIVE, MC_TIME_CONSECUTIVE = 0, 1
 MC_CONV_FIXED, MC_CONV_TOLERANCE = 0, 1
@@ -50,6 +51,7 @@ class ModelDesc(C.Structure):
         ("n_soil", _i32), ("n_snow", _i32),
         ("depths_m", _d * MC_MAX_SOIL_NODES),
         ("reference_height_m", _d), ("local_height_m", _d),
+        ("n_heights", _i32), ("_pad1", _i32), ("heights_m", _d * MC_MAX_HEIGHTS),
         ("reltol", _d), ("abstol", _d), ("maximum_surface_temperature_K", _d),
         ("de_vries_shape_factor", _d), ("recirculation_power", _d), ("return_flow_threshold", _d),
         ("root_resistance", _d), ("stomatal_closure_potential", _d), ("leaf_resistance", _d),
@@ -82,7 +84,7 @@ class StateSoA(C.Structure):
     _fields_ = [(n, _pd) for n in (
         "soil_temperature", "soil_moisture", "sum_phase", "pool", "soil_wetness", "obukhov_ode",
         "obukhov_profile", "deep_temperature_prev", "fsal", "snow_temperature", "snow_state",
-        "snow_node_depths", "q_freeze")] + [("days_done", C.POINTER(C.c_int64))]
+        "snow_node_depths", "q_freeze", "obukhov_air")] + [("days_done", C.POINTER(C.c_int64))]
 
 
 FORCING_HOURLY = ("pressure", "reference_temperature", "reference_wind_speed", "reference_humidity",
@@ -100,11 +102,14 @@ class ForcingSoA(C.Structure):
 OUTPUT_NODE_FIELDS = ("soil_temperature", "soil_moisture", "soil_water_potential", "soil_humidity",
                       "soil_thermal_conductivity", "soil_heat_capacity", "soil_bulk_density")
 OUTPUT_SCALAR_FIELDS = ("surface_water", "sky_temperature", "snow_fall", "snow_depth", "snow_density")
+OUTPUT_PROFILE_FIELDS = ("air_temperature", "wind_speed", "relative_humidity")          # [H][n_heights][S]
+OUTPUT_PROFILE_SCALARS = ("convective_heat_flux", "friction_velocity")                  # [H][S]
 
 
 class OutputSoA(C.Structure):
     _fields_ = ([(n, _pd) for n in OUTPUT_NODE_FIELDS] + [(n, _pd) for n in OUTPUT_SCALAR_FIELDS]
-                + [("snow_temperature", _pd), ("status", C.POINTER(_i32))])
+                + [("snow_temperature", _pd)] + [(n, _pd) for n in OUTPUT_PROFILE_FIELDS + OUTPUT_PROFILE_SCALARS]
+                + [("status", C.POINTER(_i32))])
 
 
 class Counters(C.Structure):

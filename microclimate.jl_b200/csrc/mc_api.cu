@@ -61,6 +61,15 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
     }
 }
 
+/* solve_air! for the rows of the chunk the soil kernel just wrote (reference src/simulation.jl:822-851) */
+__global__ void __launch_bounds__(128) air_profile_kernel(const mcd::KArgs a)
+{
+    mcd::Counters cn = {};
+    for (int64_t s = a.s_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.s_end; s += (int64_t)gridDim.x * blockDim.x)
+        mcd::solve_air_site(a, s, cn);
+    if (a.counters && cn.n_obukhov) atomicAdd(a.counters + 3, (unsigned long long)cn.n_obukhov);
+}
+
 /* fresh state == what init() + the top of solve_soil! establish (reference src/simulation.jl:141-243,383-452) */
 __global__ void init_state_kernel(mcd::KArgs a, int N, int n_snow, mc_snow_desc sm)
 {
@@ -82,7 +91,7 @@ __global__ void init_state_kernel(mcd::KArgs a, int N, int n_snow, mc_snow_desc 
         for (int k = 0; k < MC_SNOW_STATE_FIELDS; k++) a.snow_state[(int64_t)k * a.S + s] = v[k];
         a.q_freeze[s] = 0.0;
     }
-    a.pool[s] = 0.0; a.wetness[s] = 0.0; a.L_ode[s] = -0.3; a.L_prof[s] = -0.3; a.tdeep_prev[s] = qnan; a.flags[s] = 0;
+    a.pool[s] = 0.0; a.wetness[s] = 0.0; a.L_ode[s] = -0.3; a.L_prof[s] = -0.3; a.L_air[s] = -0.3; a.tdeep_prev[s] = qnan; a.flags[s] = 0;
 }
 
 /* DFMA throughput micro-benchmark: 8 independent FMA chains per thread */
@@ -114,7 +123,7 @@ struct mc_handle {
     double* arena = nullptr; size_t arena_doubles = 0;
     double *z0, *slope, *svf, *albedo, *bd, *md, *lam_m, *c_m, *psi_e, *ks, *bb, *rootd, *init_T, *init_theta;
     double *T, *theta, *sum_phase, *pool, *wetness, *L_ode, *L_prof, *tdeep_prev, *fsal;
-    double *snow_T = nullptr, *snow_state = nullptr, *snow_nd = nullptr, *q_freeze = nullptr;
+    double *snow_T = nullptr, *snow_state = nullptr, *snow_nd = nullptr, *q_freeze = nullptr, *L_air = nullptr;
     int32_t* doy_dev = nullptr; size_t doy_cap = 0;
     int32_t* flags = nullptr;
     unsigned long long* counters = nullptr;
@@ -134,6 +143,7 @@ static int validate_model(const mc_model_desc* m, std::string& err)
     if (m->n_soil < 3 || m->n_soil > MC_MAX_SOIL_NODES) { err = "n_soil must be in 3.." + std::to_string(MC_MAX_SOIL_NODES); return -1; }
     if (m->n_snow != 0 && m->n_snow != MC_SNOW_NODES) { err = "n_snow must be 0 (NoSnow) or 8 (SnowModel)"; return -3; }
     if (!(m->moisture_timestep_s > 0.0) || m->moisture_timestep_s > 3600.0) { err = "moisture_timestep_s must be in (0, 3600]"; return -1; }
+    if (m->n_heights < 0 || m->n_heights > MC_MAX_HEIGHTS) { err = "n_heights must be in 0.." + std::to_string(MC_MAX_HEIGHTS); return -1; }
     for (int i = 1; i < m->n_soil; i++) if (!(m->depths_m[i] > m->depths_m[i - 1])) { err = "depths must be strictly increasing"; return -1; }
     return 0;
 }
@@ -168,6 +178,7 @@ static void fill_site_state_args(mc_handle* h, mcd::KArgs& a)
     a.T = h->T; a.theta = h->theta; a.sum_phase = h->sum_phase; a.pool = h->pool; a.wetness = h->wetness; a.L_ode = h->L_ode;
     a.L_prof = h->L_prof; a.tdeep_prev = h->tdeep_prev; a.fsal = h->fsal; a.flags = h->flags; a.counters = h->counters;
     a.snow_T = h->snow_T; a.snow_state = h->snow_state; a.snow_nd = h->snow_nd; a.q_freeze = h->q_freeze;
+    a.L_air = h->L_air; a.n_snow = h->model.n_snow;
 }
 
 /* ---------------------------------------------------------------- C ABI ---- */
@@ -237,7 +248,7 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     }
     const size_t S = (size_t)n_sites, N = (size_t)h->N;
     const size_t NSn = (size_t)model->n_snow;
-    const size_t per_site = 4 + 5, per_node = 8 + 2 + 4;
+    const size_t per_site = 4 + 5 + 1, per_node = 8 + 2 + 4;
     h->arena_doubles = S * (per_site + per_node * N + (NSn ? NSn * 3 + MC_SNOW_STATE_FIELDS + 1 : 0));
     if ((e = cudaMalloc(&h->arena, h->arena_doubles * sizeof(double))) != cudaSuccess) return fail("cudaMalloc(state arena)", e);
     double* p = h->arena;
@@ -248,7 +259,7 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     h->init_T = take(N * S); h->init_theta = take(N * S);
     h->T = take(N * S); h->theta = take(N * S); h->sum_phase = take(N * S); h->fsal = take((N + NSn) * S);
     if (NSn) { h->snow_T = take(NSn * S); h->snow_nd = take(NSn * S); h->snow_state = take(MC_SNOW_STATE_FIELDS * S); h->q_freeze = take(S); }
-    h->pool = take(S); h->wetness = take(S); h->L_ode = take(S); h->L_prof = take(S); h->tdeep_prev = take(S);
+    h->pool = take(S); h->wetness = take(S); h->L_ode = take(S); h->L_prof = take(S); h->tdeep_prev = take(S); h->L_air = take(S);
     if ((e = cudaMalloc(&h->flags, S * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
     if ((e = cudaMalloc(&h->counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
     if ((e = cudaMemset(h->counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
@@ -304,7 +315,7 @@ static int copy_state(mc_handle* h, const mc_state_soa* st, bool to_host)
                           {st->pool, h->pool, bS}, {st->soil_wetness, h->wetness, bS}, {st->obukhov_ode, h->L_ode, bS}, {st->obukhov_profile, h->L_prof, bS},
                           {st->deep_temperature_prev, h->tdeep_prev, bS},
                           {st->snow_temperature, h->snow_T, NSn * bS}, {st->snow_state, h->snow_state, MC_SNOW_STATE_FIELDS * bS},
-                          {st->snow_node_depths, h->snow_nd, NSn * bS}, {st->q_freeze, h->q_freeze, bS}};
+                          {st->snow_node_depths, h->snow_nd, NSn * bS}, {st->q_freeze, h->q_freeze, bS}, {st->obukhov_air, h->L_air, bS}};
     for (const Item& it : items) {
         if (!it.host || !it.dev) continue;
         if (to_host) MC_CUDA(h, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -347,6 +358,11 @@ static int prepare_chunk(mc_handle* h, int64_t day0, int32_t ndays, const mc_for
     a.o_T = o->soil_temperature; a.o_theta = o->soil_moisture; a.o_psi = o->soil_water_potential; a.o_h = o->soil_humidity;
     a.o_lam = o->soil_thermal_conductivity; a.o_cp = o->soil_heat_capacity; a.o_rho = o->soil_bulk_density; a.o_pool = o->surface_water; a.o_sky = o->sky_temperature;
     a.o_snow_fall = o->snow_fall; a.o_snow_depth = o->snow_depth; a.o_snow_dens = o->snow_density; a.o_snow_T = o->snow_temperature;
+    a.o_air_T = o->air_temperature; a.o_wind = o->wind_speed; a.o_rh = o->relative_humidity; a.o_qc = o->convective_heat_flux; a.o_ustar = o->friction_velocity;
+    if (a.o_air_T || a.o_wind || a.o_rh || a.o_qc || a.o_ustar) {
+        if (h->model.n_heights < 1) { h->err = "solve_air! outputs requested but the model has no heights"; return -1; }
+        if (!a.o_T || (h->model.n_snow > 0 && (!a.o_snow_depth || !a.o_snow_T))) { h->err = "solve_air! outputs need soil_temperature (and snow_depth + snow_temperature with SnowModel) selected"; return -1; }
+    }
     if (f->day_of_year) {                /* MicroProblem.days: always a HOST pointer, staged here (used by the snow melt-factor / Q_freeze guards) */
         if (h->doy_cap < (size_t)ndays) { if (h->doy_dev) MC_CUDA(h, cudaFree(h->doy_dev)); MC_CUDA(h, cudaMalloc(&h->doy_dev, (size_t)ndays * sizeof(int32_t))); h->doy_cap = (size_t)ndays; }
         MC_CUDA(h, cudaMemcpyAsync(h->doy_dev, f->day_of_year, (size_t)ndays * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -364,6 +380,11 @@ static int launch_range(mc_handle* h, mcd::KArgs a, int64_t lo, int64_t hi, cuda
     if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, st) : (na == 19 ? launch_chunk<19, 0>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, st));
     else e = na == 10 ? launch_chunk<10, MC_SNOW_NODES>(a, st) : (na == 19 ? launch_chunk<19, MC_SNOW_NODES>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, st));
     MC_CUDA(h, e);
+    if (a.o_air_T || a.o_wind || a.o_rh || a.o_qc || a.o_ustar) {
+        const int grid = (int)((hi - lo + 127) / 128);
+        air_profile_kernel<<<grid, 128, 0, st>>>(a);
+        MC_CUDA(h, cudaGetLastError());
+    }
     return 0;
 }
 
@@ -441,14 +462,23 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     for (double* q : node_host) if (q) need_out += H * N * S;
     for (double* q : scal_host) if (q) need_out += H * S;
     if (snowT_host) need_out += H * NSn * S;
+    const size_t NH = (size_t)h->model.n_heights;
+    double* prof_host[3] = {o->air_temperature, o->wind_speed, o->relative_humidity};
+    double* profs_host[2] = {o->convective_heat_flux, o->friction_velocity};
+    for (double* q2 : prof_host) if (q2) need_out += H * NH * S;
+    for (double* q2 : profs_host) if (q2) need_out += H * S;
     if (int rc = ensure_stage(h, &h->stage_out, &h->stage_out_doubles, need_out ? need_out : 1)) return rc;
     mc_output_soa od; std::memset(&od, 0, sizeof(od));
     double** node_dev[7] = {&od.soil_temperature, &od.soil_moisture, &od.soil_water_potential, &od.soil_humidity, &od.soil_thermal_conductivity, &od.soil_heat_capacity, &od.soil_bulk_density};
     double** scal_dev[5] = {&od.surface_water, &od.sky_temperature, &od.snow_fall, &od.snow_depth, &od.snow_density};
+    double** prof_dev[3] = {&od.air_temperature, &od.wind_speed, &od.relative_humidity};
+    double** profs_dev[2] = {&od.convective_heat_flux, &od.friction_velocity};
     double* q = h->stage_out;
     for (int k = 0; k < 7; k++) if (node_host[k]) { out_planes.push_back({nullptr, node_host[k], q, H * N}); *node_dev[k] = q; q += H * N * S; }
     for (int k = 0; k < 5; k++) if (scal_host[k]) { out_planes.push_back({nullptr, scal_host[k], q, H}); *scal_dev[k] = q; q += H * S; }
     if (snowT_host) { out_planes.push_back({nullptr, snowT_host, q, H * NSn}); od.snow_temperature = q; q += H * NSn * S; }
+    for (int k = 0; k < 3; k++) if (prof_host[k]) { out_planes.push_back({nullptr, prof_host[k], q, H * NH}); *prof_dev[k] = q; q += H * NH * S; }
+    for (int k = 0; k < 2; k++) if (profs_host[k]) { out_planes.push_back({nullptr, profs_host[k], q, H}); *profs_dev[k] = q; q += H * S; }
 
     mcd::KArgs a;
     if (int rc = prepare_chunk(h, day0, ndays, &fd, &od, a)) return rc;

@@ -86,6 +86,7 @@ struct DevModel {
     double Mw, eps, dep, cpa, cpv, R, sigma, g, P0, Lv_a, Lv_b, Hv_a, Hv_b, Ma_over_R;
     double schmidt_factor;  /* (0.71/0.60)^0.666, monin_obukhov.jl:406-407 */
     mc_snow_desc snow;      /* SnowModel (n_snow = 8) */
+    int n_heights; double heights[MC_MAX_HEIGHTS];      /* MicroModel.heights (solve_air!) */
 };
 
 #if defined(__CUDACC__)
@@ -116,6 +117,9 @@ struct KArgs {
     /* outputs (NULL = deselected) */
     double *o_T, *o_theta, *o_psi, *o_h, *o_lam, *o_cp, *o_rho, *o_pool, *o_sky;
     double *o_snow_fall, *o_snow_depth, *o_snow_dens, *o_snow_T;
+    double *o_air_T, *o_wind, *o_rh, *o_qc, *o_ustar;     /* solve_air! profiles [H][n_heights][S] and scalars [H][S] */
+    double *L_air;                                        /* [S] Obukhov warm start of the air-profile buffer */
+    int32_t n_snow;
     unsigned long long* counters;   /* [8]: rhs, accept, reject, obukhov, newton, infil, day_passes, spare */
 };
 
@@ -1674,6 +1678,70 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * solve_air! (src/simulation.jl:822-851) for the rows of one chunk of site s: atmospheric_surface_profile! (monin_obukhov.jl:85-206)
+ * at every height from the row's final surface temperature.  Runs as its own small kernel after the soil kernel of the chunk.
+ * ------------------------------------------------------------------------------------------ */
+MC_DEV void solve_air_site(const KArgs& a, int64_t s, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const int N = m.N, ns = a.n_snow, nh = m.n_heights, H = a.ndays * 24;
+    const int64_t S = a.S;
+    const double z = m.zref, z0 = MC_LDG(a.z0 + s), kappa = m.kappa, gamma = m.gamma;
+    const double lzr = mcm::log(z / z0);
+    int ref_idx = -1; for (int k = nh - 1; k >= 0; k--) if (m.heights[k] == z) ref_idx = k;
+    double L_air = a.L_air[s];
+    for (int row = 0; row < H; row++) {
+        const bool has_snow = ns > 0 && a.o_snow_depth && a.o_snow_depth[(int64_t)row * S + s] > 0.0;
+        const double T_surf = has_snow ? a.o_snow_T[((int64_t)row * ns + 0) * S + s] : a.o_T[((int64_t)row * N + 0) * S + s];
+        const double T_ref = MC_LDG(a.f_T + (int64_t)row * S + s), wind = MC_LDG(a.f_wind + (int64_t)row * S + s);
+        const double rh = MC_LDG(a.f_rh + (int64_t)row * S + s), zen = MC_LDG(a.f_zen + (int64_t)row * S + s);
+        const double dT = T_ref - T_surf;
+        const double rho_cp = calc_rho_cp((T_surf + T_ref) / 2.0);
+        double Tair[MC_MAX_HEIGHTS], Qc, ustar;
+        if (T_ref >= T_surf || zen >= 90.0) {
+            ustar = jmax(kappa * wind / lzr, 1.0e-6);
+            const double Stb = 0.64 / lzr, Sts = sublayer_stanton(z0, ustar);
+            Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
+            const double Tz0 = (T_ref * Stb + T_surf * Sts) / (Stb + Sts);
+            for (int k = 0; k < nh; k++) {
+                const double h = m.heights[k]; double v;
+                if (h < z0) { v = 0.0; Tair[k] = T_surf + (Tz0 - T_surf) * (h / z0); }
+                else if (k == ref_idx) { v = wind; Tair[k] = T_ref; }
+                else { v = (ustar / kappa) * mcm::log(h / z0 + 0.0); Tair[k] = Tz0 + (T_ref - Tz0) * mcm::log(h / z0) / lzr; }
+                if (a.o_wind) a.o_wind[((int64_t)row * nh + k) * S + s] = v;
+            }
+        } else {
+            const Obukhov ob = calc_obukhov(wind, z0, z, lzr, dT, rho_cp, L_air);
+            cn.n_obukhov += ob.iters;
+            L_air = ob.L; Qc = ob.Q; ustar = ob.ustar;
+            const double Tz0 = (T_ref * ob.Stb + T_surf * ob.Sts) / (ob.Stb + ob.Sts);
+            for (int k = 0; k < nh; k++) {
+                const double h = m.heights[k]; double v;
+                if (h < z0) { v = 0.0; Tair[k] = T_surf + (Tz0 - T_surf) * (h / z0); }
+                else if (k == ref_idx) { v = wind; Tair[k] = T_ref; }
+                else {
+                    const double x = calc_phi_m(h, gamma, ob.L);
+                    const double psi_m1 = calc_psi_m(x), psi_h2 = calc_psi_h(x);
+                    const double hr = h / z0;
+                    v = (ob.ustar / kappa) * jmax(mcm::log(hr) - psi_m1, 1e-6);
+                    Tair[k] = Tz0 + (T_ref - Tz0) * jmax(mcm::log(hr) - psi_h2, 1e-6) / (mcm::log(z / z0) - ob.psi_h);
+                }
+                if (a.o_wind) a.o_wind[((int64_t)row * nh + k) * S + s] = v;
+            }
+        }
+        const double e_ref = goff_gratch(T_ref) * rh;
+        for (int k = 0; k < nh; k++) {
+            if (a.o_air_T) a.o_air_T[((int64_t)row * nh + k) * S + s] = Tair[k];
+            if (a.o_rh) a.o_rh[((int64_t)row * nh + k) * S + s] = jclamp(e_ref / goff_gratch(Tair[k]) * 1.0, 0.0, 1.0);
+        }
+        if (a.o_qc) a.o_qc[(int64_t)row * S + s] = Qc;
+        if (a.o_ustar) a.o_ustar[(int64_t)row * S + s] = ustar;
+    }
+    a.L_air[s] = L_air;
+}
+
 /* host side: flatten mc_model_desc into DevModel (run once per handle) */
 static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
 {
@@ -1709,6 +1777,8 @@ static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
     d.Ma_over_R = f.molar_mass_air / f.gas_constant;
     d.schmidt_factor = mcm::pow(0.71 / 0.60, 0.666);
     d.snow = md.snow;
+    d.n_heights = md.n_heights;
+    for (int i = 0; i < MC_MAX_HEIGHTS; i++) d.heights[i] = i < md.n_heights ? md.heights_m[i] : 0.0;
 }
 
 

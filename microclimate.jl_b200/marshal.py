@@ -34,6 +34,11 @@ def model_desc(model: T.MicroModel, time_mode, *, inputs0: Optional[T.MicroInput
     heights = np.asarray(model.heights, float)
     m.reference_height_m = heights[-1]
     m.local_height_m = heights[0]
+    if len(heights) > A.MC_MAX_HEIGHTS:
+        raise ValueError(f"at most {A.MC_MAX_HEIGHTS} heights")
+    m.n_heights = len(heights)
+    for i, hgt in enumerate(heights):
+        m.heights_m[i] = hgt
     sem = model.soil_energy_model
     m.reltol, m.abstol, m.maximum_surface_temperature_K = sem.reltol, sem.abstol, sem.maximum_surface_temperature
     sp = model.soil_properties_model
@@ -286,9 +291,14 @@ DEFAULT_OUTPUT_FIELDS = A.OUTPUT_NODE_FIELDS + ("surface_water", "sky_temperatur
 class OutputBatch:
     """mc_output_soa for a chunk: node fields [24*ndays][N][S], scalars [24*ndays][S].  Unselected = None."""
 
-    def __init__(self, ndays: int, n_soil: int, n_sites: int, fields: Sequence[str] = DEFAULT_OUTPUT_FIELDS, n_snow: int = 0):
+    def __init__(self, ndays: int, n_soil: int, n_sites: int, fields: Sequence[str] = DEFAULT_OUTPUT_FIELDS, n_snow: int = 0,
+                 n_heights: int = 0):
         self.ndays, self.N, self.S = ndays, n_soil, n_sites
         H = 24 * ndays
+        for f in A.OUTPUT_PROFILE_FIELDS:
+            setattr(self, f, np.zeros((H, n_heights, n_sites)) if (n_heights and f in fields) else None)
+        for f in A.OUTPUT_PROFILE_SCALARS:
+            setattr(self, f, np.zeros((H, n_sites)) if (n_heights and f in fields) else None)
         for f in A.OUTPUT_NODE_FIELDS:
             setattr(self, f, np.zeros((H, n_soil, n_sites)) if f in fields else None)
         for f in A.OUTPUT_SCALAR_FIELDS:
@@ -301,14 +311,16 @@ class OutputBatch:
         for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS:
             setattr(c, f, _ptr(getattr(self, f)))
         c.snow_temperature = _ptr(self.snow_temperature)
+        for f in A.OUTPUT_PROFILE_FIELDS + A.OUTPUT_PROFILE_SCALARS:
+            setattr(c, f, _ptr(getattr(self, f, None)))
         c.status = self.status.ctypes.data_as(C.POINTER(C.c_int32))
         return c
 
     def assign_rows(self, row0: int, part: "OutputBatch"):
         """Copy a day-chunk's rows into this batch at row offset `row0` (time-chunked runs)."""
         H = 24 * part.ndays
-        for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS + ("snow_temperature",):
-            dst, src = getattr(self, f), getattr(part, f)
+        for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS + ("snow_temperature",) + A.OUTPUT_PROFILE_FIELDS + A.OUTPUT_PROFILE_SCALARS:
+            dst, src = getattr(self, f, None), getattr(part, f, None)
             if dst is not None and src is not None:
                 dst[row0:row0 + H] = src
         self.status |= part.status
@@ -323,6 +335,12 @@ class OutputBatch:
             a = getattr(self, f)
             setattr(r, f, None if a is None else np.ascontiguousarray(a[:, s]))
         r.snow_temperature = None if self.snow_temperature is None else np.ascontiguousarray(self.snow_temperature[:, :, s])
+        for f in A.OUTPUT_PROFILE_FIELDS:
+            a = getattr(self, f, None)
+            setattr(r, f, None if a is None else np.ascontiguousarray(a[:, :, s]))
+        for f in A.OUTPUT_PROFILE_SCALARS:
+            a = getattr(self, f, None)
+            setattr(r, f, None if a is None else np.ascontiguousarray(a[:, s]))
         r.status = int(self.status[s])
         return r
 
@@ -345,6 +363,7 @@ class StateBatch:
         self.snow_state = np.zeros((A.MC_SNOW_STATE_FIELDS, n_sites)) if n_snow else None
         self.snow_node_depths = np.zeros((n_snow, n_sites)) if n_snow else None
         self.q_freeze = np.zeros(n_sites) if n_snow else None
+        self.obukhov_air = np.zeros(n_sites)
         self.days_done = np.zeros(1, dtype=np.int64)
 
     def c_struct(self) -> A.StateSoA:

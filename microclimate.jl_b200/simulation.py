@@ -127,8 +127,9 @@ def site_shards(n_sites: int, n_shards: int):
 def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, days: Sequence[int],
                        time_mode=None, fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS,
                        chunk_days: Optional[int] = None, device: int = 0) -> M.OutputBatch:
-    """Batched `solve_soil!`: one model, many inputs -> one OutputBatch (site-fastest); `site_result(s)`
-    un-marshals a site into the reference's (nsteps, N) MicroResult layout.
+    """Batched `solve_soil!` (+ `solve_air!` when any of the profile fields air_temperature / wind_speed / relative_humidity /
+    convective_heat_flux / friction_velocity is selected): one model, many inputs -> one OutputBatch (site-fastest);
+    `site_result(s)` un-marshals a site into the reference's (nsteps, N) MicroResult layout.
 
     `chunk_days` streams time in chunks with the carried state resident on the GPU (results are identical
     to a single chunk: the state carried between chunks is exactly what the reference carries between days)."""
@@ -139,7 +140,7 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
     sites = M.SitesBatch.from_inputs(model, inputs)
     forcing = M.ForcingBatch.from_inputs(model, inputs, days)
     ndays, S = len(days), len(inputs)
-    out = M.OutputBatch(ndays, desc.n_soil, S, fields, desc.n_snow)
+    out = M.OutputBatch(ndays, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
     with SoilEngine(desc, S, device) as eng:
         eng.set_sites(sites)
         if not chunk_days or chunk_days >= ndays:
@@ -148,7 +149,7 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
             d0 = 0
             while d0 < ndays:
                 d1 = min(ndays, d0 + chunk_days)
-                part = M.OutputBatch(d1 - d0, desc.n_soil, S, fields, desc.n_snow)
+                part = M.OutputBatch(d1 - d0, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
                 eng.step_days(d0, forcing.day_slice(d0, d1), part)
                 out.assign_rows(24 * d0, part)
                 d0 = d1

@@ -318,6 +318,12 @@ class MicroResult:
     snow_depth: Optional[np.ndarray] = None
     snow_density: Optional[np.ndarray] = None
     snow_temperature: Optional[np.ndarray] = None
+    # AtmosphericProfile (src/outputs.jl:1-16), filled by solve_air!
+    air_temperature: Optional[np.ndarray] = None
+    wind_speed: Optional[np.ndarray] = None
+    relative_humidity: Optional[np.ndarray] = None
+    convective_heat_flux: Optional[np.ndarray] = None
+    friction_velocity: Optional[np.ndarray] = None
     status: int = 0
 
 

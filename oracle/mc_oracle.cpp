@@ -1124,6 +1124,7 @@ struct SiteState {
     InfilBuffers infil;
     /* SnowModel only */
     double Ts[NSN]; SnowState snow; SnowScratch snow_scratch; double sd_last, Q_freeze;
+    double L_air;        /* buffers.air_profile.obukhov_length_prev (solve_air!) */
 };
 
 static int32_t* g_trace_attempts = nullptr; static int32_t* g_trace_newton = nullptr; static int64_t g_trace_rows = 0;
@@ -1217,6 +1218,7 @@ static void init_site_state(SiteState& st, const mc_model_desc& m, const Site& s
     for (int i = 0; i < NSN; i++) { st.Ts[i] = m.snow.initial_snow_temperature_K; st.snow_scratch.node_depths[i] = 0.0; st.snow_scratch.meanT[i] = 0.0; st.snow_scratch.meanTpast[i] = 0.0; }
     st.snow = initial_snow_state(m.snow, m.snow.initial_snow_depth_cm, m.snow.initial_snow_density);
     st.snow_scratch.sd_prev = 0.0; st.snow_scratch.sd_cur = 0.0; st.sd_last = 0.0; st.Q_freeze = 0.0;
+    st.L_air = -0.3;
     (void)site;
 }
 
@@ -1475,6 +1477,67 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
     for (int i = 0; i < N; i++) if (!(std::isfinite(st.T[i]) && std::isfinite(st.theta[i]))) st.flags |= MC_STATUS_NAN;
 }
 
+
+/* solve_air! (src/simulation.jl:822-851): per output row, atmospheric_surface_profile! (monin_obukhov.jl:85-206) at every height of
+ * MicroModel.heights from the row's final surface temperature (top snow node when snow covers the ground).  Rows are processed in
+ * order: the Obukhov warm start of the air-profile buffer carries from row to row. */
+static void solve_air_site(const mc_model_desc& m, const Site& site, SiteState& st, const SiteIO& io, Counters& cn)
+{
+    const mc_forcing_soa& f = *io.f; const mc_output_soa& o = *io.o;
+    if (!o.air_temperature && !o.wind_speed && !o.relative_humidity && !o.convective_heat_flux && !o.friction_velocity) return;
+    const int N = m.n_soil, ns = m.n_snow, nh = m.n_heights, H = io.ndays * 24;
+    const double z = m.reference_height_m, z0 = site.z0, kappa = m.karman_constant, gamma = m.dyer_constant;
+    const double lzr = mcm::log(z / z0);
+    int ref_idx = -1; for (int k = 0; k < nh; k++) if (m.heights_m[k] == z) { ref_idx = k; break; }
+    auto put_h = [&](double* a, int row, int k, double v) { if (a) a[((int64_t)row * nh + k) * io.S + io.s] = v; };
+    for (int row = 0; row < H; row++) {
+        const bool has_snow = ns > 0 && o.snow_depth && o.snow_depth[(int64_t)row * io.S + io.s] > 0.0;
+        const double T_surf = has_snow ? o.snow_temperature[((int64_t)row * ns + 0) * io.S + io.s] : o.soil_temperature[((int64_t)row * N + 0) * io.S + io.s];
+        const double T_ref = io.hourly(f.reference_temperature, row), wind = io.hourly(f.reference_wind_speed, row);
+        const double rh = io.hourly(f.reference_humidity, row), zen = io.hourly(f.zenith_angle, row);
+        const double dT = T_ref - T_surf;
+        const double rho_cp = calc_rho_cp((T_surf + T_ref) / 2.0);
+        double Tair[MC_MAX_HEIGHTS], Qc, ustar;
+        if (T_ref >= T_surf || zen >= 90.0) {
+            ustar = jmax(kappa * wind / lzr, 1.0e-6);
+            const double Stb = bulk_stanton(lzr), Sts = sublayer_stanton(z0, ustar);
+            Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
+            const double Tz0 = (T_ref * Stb + T_surf * Sts) / (Stb + Sts);
+            for (int k = 0; k < nh; k++) {
+                const double h = m.heights_m[k]; double v;
+                if (h < z0) { v = 0.0; Tair[k] = T_surf + (Tz0 - T_surf) * (h / z0); }
+                else if (k == ref_idx) { v = wind; Tair[k] = T_ref; }
+                else { v = (ustar / kappa) * mcm::log(h / z0 + 0.0); Tair[k] = Tz0 + (T_ref - Tz0) * mcm::log(h / z0) / lzr; }
+                put_h(o.wind_speed, row, k, v);
+            }
+        } else {
+            ObukhovOut ob = calc_obukhov(T_ref, T_surf, wind, z0, z, kappa, dT, rho_cp, 16.0, 30, 1e-2, st.L_air);
+            cn.n_obukhov += ob.iters;
+            st.L_air = ob.L; Qc = ob.Q; ustar = ob.ustar;
+            for (int k = 0; k < nh; k++) {
+                const double h = m.heights_m[k]; double v;
+                if (h < z0) { v = 0.0; Tair[k] = T_surf + (ob.T_z0 - T_surf) * (h / z0); }
+                else if (k == ref_idx) { v = wind; Tair[k] = T_ref; }
+                else {
+                    const double x = calc_phi_m(h, gamma, ob.L);
+                    const double psi_m1 = calc_psi_m(x), psi_h2 = calc_psi_h(x);
+                    const double hr = h / z0;
+                    v = (ob.ustar / kappa) * jmax(mcm::log(hr) - psi_m1, 1e-6);
+                    Tair[k] = ob.T_z0 + (T_ref - ob.T_z0) * jmax(mcm::log(hr) - psi_h2, 1e-6) / (mcm::log(z / z0) - ob.psi_h);
+                }
+                put_h(o.wind_speed, row, k, v);
+            }
+        }
+        const double e_ref = goff_gratch(T_ref) * rh;
+        for (int k = 0; k < nh; k++) {
+            put_h(o.air_temperature, row, k, Tair[k]);
+            put_h(o.relative_humidity, row, k, jclamp(e_ref / goff_gratch(Tair[k]) * 1.0, 0.0, 1.0));
+        }
+        io.put_scalar(o.convective_heat_flux, row, Qc);
+        io.put_scalar(o.friction_velocity, row, ustar);
+    }
+}
+
 static void gather_site(Site& site, const mc_model_desc& m, const mc_sites_soa& ss, int64_t S, int64_t s)
 {
     const int N = m.n_soil;
@@ -1543,6 +1606,7 @@ int mco_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* fo
         for (int64_t s = 0; s < S; s++) {
             mco::SiteIO io; io.S = S; io.s = s; io.ndays = ndays; io.f = forcing; io.o = out; io.N = o->model.n_soil;
             mco::solve_soil_site(o->model, o->sites[s], ii, o->states[s], io, day0, cn);
+            mco::solve_air_site(o->model, o->sites[s], o->states[s], io, cn);
             if (out->status) out->status[s] = o->states[s].flags;
             if (o->states[s].flags) bad++;
         }
@@ -1585,6 +1649,7 @@ int mco_get_state(void* h, mc_state_soa* out)
         if (out->obukhov_ode) out->obukhov_ode[s] = st.L_ode;
         if (out->obukhov_profile) out->obukhov_profile[s] = st.L_prof;
         if (out->deep_temperature_prev) out->deep_temperature_prev[s] = st.tdeep_prev;
+        if (out->obukhov_air) out->obukhov_air[s] = st.L_air;
         if (o->model.n_snow > 0) {
             for (int i = 0; i < o->model.n_snow; i++) {
                 if (out->snow_temperature) out->snow_temperature[(int64_t)i * S + s] = st.Ts[i];

@@ -94,7 +94,7 @@ def run_engine(engine_cls, problem, inputs_list=None, fields=None, **kw):
     desc = M.model_desc(problem.model, problem.time_mode, inputs0=inputs_list[0])
     sites = M.SitesBatch.from_inputs(problem.model, inputs_list)
     forcing = M.ForcingBatch.from_inputs(problem.model, inputs_list, problem.days)
-    out = M.OutputBatch(len(problem.days), desc.n_soil, len(inputs_list), fields or M.DEFAULT_OUTPUT_FIELDS, desc.n_snow)
+    out = M.OutputBatch(len(problem.days), desc.n_soil, len(inputs_list), fields or M.DEFAULT_OUTPUT_FIELDS, desc.n_snow, desc.n_heights)
     eng = engine_cls(desc, len(inputs_list), **kw)
     eng.set_sites(sites)
     eng.step_days(0, forcing, out)

@@ -15,7 +15,7 @@ namespace {
 struct Emu {
     mc_model_desc model; int64_t S; int N; int64_t days_done;
     std::vector<double> site[4], node[8], init_T, init_theta, T, theta, sum_phase, fsal, pool, wet, L_ode, L_prof, tdeep;
-    std::vector<double> snow_T, snow_state, snow_nd, q_freeze;
+    std::vector<double> snow_T, snow_state, snow_nd, q_freeze, L_air;
     std::vector<int32_t> flags; bool has_init_T;
     unsigned long long counters[8];
 };
@@ -55,6 +55,7 @@ int he_set_sites(void* h, const mc_sites_soa* s, const mc_initial_soa* init)
         for (int k = 0; k < MC_SNOW_STATE_FIELDS; k++) for (size_t q = 0; q < S; q++) e->snow_state[k * S + q] = v[k];
     }
     e->pool.assign(S, 0.0); e->wet.assign(S, 0.0); e->L_ode.assign(S, -0.3); e->L_prof.assign(S, -0.3); e->tdeep.assign(S, qnan);
+    e->L_air.assign(S, -0.3);
     e->flags.assign(S, 0); e->days_done = 0; std::memset(e->counters, 0, sizeof(e->counters));
     return 0;
 }
@@ -82,11 +83,15 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     a.o_T = o->soil_temperature; a.o_theta = o->soil_moisture; a.o_psi = o->soil_water_potential; a.o_h = o->soil_humidity;
     a.o_lam = o->soil_thermal_conductivity; a.o_cp = o->soil_heat_capacity; a.o_rho = o->soil_bulk_density; a.o_pool = o->surface_water; a.o_sky = o->sky_temperature;
     a.o_snow_fall = o->snow_fall; a.o_snow_depth = o->snow_depth; a.o_snow_dens = o->snow_density; a.o_snow_T = o->snow_temperature;
+    a.o_air_T = o->air_temperature; a.o_wind = o->wind_speed; a.o_rh = o->relative_humidity; a.o_qc = o->convective_heat_flux; a.o_ustar = o->friction_velocity;
+    a.L_air = e->L_air.data(); a.n_snow = e->model.n_snow; a.s_begin = 0; a.s_end = e->S;
+    const bool want_air = a.o_air_T || a.o_wind || a.o_rh || a.o_qc || a.o_ustar;
     int nbad = 0;
     for (int64_t s = 0; s < e->S; s++) {
         mcd::Counters cn = {};
         if (e->model.n_snow == 0) { if (e->N <= 10) mcd::solve_site<10, 0>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, 0>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, 0>(a, s, cn); }
         else { if (e->N <= 10) mcd::solve_site<10, MC_SNOW_NODES>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, MC_SNOW_NODES>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, s, cn); }
+        if (want_air) mcd::solve_air_site(a, s, cn);
         e->counters[0] += cn.n_rhs; e->counters[1] += cn.n_accept; e->counters[2] += cn.n_reject; e->counters[3] += cn.n_obukhov;
         e->counters[4] += cn.n_newton; e->counters[5] += cn.n_infil; e->counters[6] += cn.n_day_passes;
         if (o->status) o->status[s] = e->flags[s];
@@ -110,7 +115,7 @@ int he_get_state(void* h, mc_state_soa* st)
     auto cp = [](double* dst, const std::vector<double>& v, size_t n) { if (dst) std::memcpy(dst, v.data(), n * sizeof(double)); };
     cp(st->soil_temperature, e->T, N * S); cp(st->soil_moisture, e->theta, N * S); cp(st->sum_phase, e->sum_phase, N * S); cp(st->fsal, e->fsal, N * S);
     cp(st->pool, e->pool, S); cp(st->soil_wetness, e->wet, S); cp(st->obukhov_ode, e->L_ode, S); cp(st->obukhov_profile, e->L_prof, S);
-    cp(st->deep_temperature_prev, e->tdeep, S);
+    cp(st->deep_temperature_prev, e->tdeep, S); cp(st->obukhov_air, e->L_air, S);
     if (st->days_done) st->days_done[0] = e->days_done;
     return 0;
 }
@@ -132,7 +137,7 @@ extern "C" int he_set_state(void* h, const mc_state_soa* st)
     auto cp = [](std::vector<double>& v, const double* src, size_t n) { if (src) std::memcpy(v.data(), src, n * sizeof(double)); };
     cp(e->T, st->soil_temperature, N * S); cp(e->theta, st->soil_moisture, N * S); cp(e->sum_phase, st->sum_phase, N * S); cp(e->fsal, st->fsal, N * S);
     cp(e->pool, st->pool, S); cp(e->wet, st->soil_wetness, S); cp(e->L_ode, st->obukhov_ode, S); cp(e->L_prof, st->obukhov_profile, S);
-    cp(e->tdeep, st->deep_temperature_prev, S);
+    cp(e->tdeep, st->deep_temperature_prev, S); cp(e->L_air, st->obukhov_air, S);
     if (st->days_done) e->days_done = st->days_done[0];
     return 0;
 }

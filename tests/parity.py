@@ -5,6 +5,8 @@ from microclimate_jl_b200 import _abi as A
 from microclimate_jl_b200 import marshal as M
 
 ALL_FIELDS = A.OUTPUT_NODE_FIELDS + ("surface_water", "sky_temperature")
+AIR_FIELDS = A.OUTPUT_PROFILE_FIELDS + A.OUTPUT_PROFILE_SCALARS
+SNOW_FIELDS = ("snow_fall", "snow_depth", "snow_density", "snow_temperature")
 
 # north_star tolerances (BASELINE.json): <= 1e-3 K on hourly soil temperature, <= 1e-5 m3/m3 on moisture.
 TOL_T_K = 1e-3
@@ -14,7 +16,7 @@ TOL_THETA = 1e-5
 def run(engine_cls, desc, sites, forcing, fields=ALL_FIELDS, chunks=None, **kw):
     """Integrate `forcing` on `engine_cls`; `chunks` = list of day counts to split the run into."""
     S, nd = sites.S, forcing.ndays
-    out = M.OutputBatch(nd, desc.n_soil, S, fields, desc.n_snow)
+    out = M.OutputBatch(nd, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
     eng = engine_cls(desc, S, **kw)
     eng.set_sites(sites)
     if not chunks:
@@ -23,7 +25,7 @@ def run(engine_cls, desc, sites, forcing, fields=ALL_FIELDS, chunks=None, **kw):
         assert sum(chunks) == nd
         d0 = 0
         for c in chunks:
-            part = M.OutputBatch(c, desc.n_soil, S, fields, desc.n_snow)
+            part = M.OutputBatch(c, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
             eng.step_days(d0, forcing.day_slice(d0, d0 + c), part)
             out.assign_rows(24 * d0, part)
             d0 += c
@@ -50,7 +52,7 @@ def assert_within_north_star(a, b, fields=ALL_FIELDS):
 
 def assert_bit_identical(a, b, fields=ALL_FIELDS):
     for f in fields:
-        x, y = getattr(a, f), getattr(b, f)
+        x, y = getattr(a, f, None), getattr(b, f, None)
         if x is None or y is None:
             continue
         assert np.array_equal(x, y, equal_nan=True), (f, float(np.nanmax(np.abs(x - y))))

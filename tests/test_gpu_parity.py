@@ -180,3 +180,23 @@ def test_pipelined_site_slices_do_not_change_results(SoilEngine, synth, monkeypa
         a, b = getattr(one, name), getattr(three, name)
         assert np.array_equal(a[..., :509], b), name
     assert np.array_equal(one.status[:509], three.status)
+
+
+def test_solve_air_matches_oracle(SoilEngine):
+    """solve_air! (the first "next" row of the scope table): MOST profiles from the final surface temperature, snow surface included."""
+    import copy
+    p, g = configs.config1_monthly(snow=True)
+    p = copy.deepcopy(p)
+    p.model.heights = np.array([0.002, 0.01, 0.5, 2.0])
+    f = parity.ALL_FIELDS + parity.SNOW_FIELDS + parity.AIR_FIELDS
+    desc, sites, forcing = _problem_buffers(p)
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    out, _ = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(out, ref, f)
+    chunked, _ = parity.run(SoilEngine, desc, sites, forcing, fields=f, chunks=[7, 5])
+    parity.assert_bit_identical(chunked, ref, parity.AIR_FIELDS)
+    # without soil_temperature selected the call must refuse rather than read garbage
+    bad = M.OutputBatch(12, desc.n_soil, 1, parity.AIR_FIELDS, desc.n_snow, desc.n_heights)
+    e = SoilEngine(desc, 1); e.set_sites(sites)
+    with pytest.raises(RuntimeError, match="solve_air"):
+        e.step_days(0, forcing, bad)

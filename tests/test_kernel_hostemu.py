@@ -151,3 +151,19 @@ def test_snow_with_dynamic_moisture_consecutive_days_bit_identical():
     parity.assert_bit_identical(chunked, ref, g)
     assert np.array_equal(np.delete(chunked.soil_humidity, 48, axis=0), np.delete(ref.soil_humidity, 48, axis=0))
     assert ref.snow_depth.max() > 2.0 and np.all(np.isfinite(ref.soil_temperature))
+
+
+def test_solve_air_bit_identical_incl_snow_surface_and_chunking():
+    """solve_air! rows (air temperature / wind / humidity profiles at several heights, convective flux, friction velocity)."""
+    p, _ = configs.config1_monthly(snow=True)
+    p = copy.deepcopy(p)
+    p.model.heights = np.array([0.002, 0.01, 0.5, 2.0])          # one height below the roughness length, one interior, the reference height
+    f = parity.ALL_FIELDS + parity.SNOW_FIELDS + parity.AIR_FIELDS
+    desc, sites, forcing = _buffers(p)
+    assert desc.n_heights == 4
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    out, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(out, ref, f)
+    assert np.all(out.wind_speed[:, 0, 0] == 0.0) and np.array_equal(out.air_temperature[:, 3, 0], forcing.reference_temperature[:, 0])
+    chunked, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f, chunks=[7, 5])
+    parity.assert_bit_identical(chunked, ref, parity.AIR_FIELDS)
