@@ -204,7 +204,15 @@ MCM_FN double exp10_finish(double r, double x, double p) { const double e = ffma
 MCM_FN double exp2(double x) { return exp_prod(x, 0.6931471805599453, 2.3190468138462996e-17); }
 
 /* pow for the cases the soil path uses: x > 0 (any y), x == 0, and x < 0 with integer-valued y */
-MCM_FN double pow(double x, double y)
+#ifndef MCM_POW_NOINLINE
+#define MCM_POW_NOINLINE 1      /* one shared copy on the device: at 32 warps/SM instruction fetch is the top stall, code size matters */
+#endif
+#if MCM_POW_NOINLINE
+MCM_HEAVY
+#else
+MCM_FN
+#endif
+double pow(double x, double y)
 {
     if (y == 0.0) return 1.0;
     if (x != x || y != y) return x + y;
