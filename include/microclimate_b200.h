@@ -316,6 +316,10 @@ int  mc_get_status(mc_handle* h, int32_t* status_host /* [S] */);
  * MEASURED_PEAKS.json has no FP64 figure). */
 int  mc_measure_fp64_peak(mc_handle* h, double* tflops);
 
+/* development probe (not part of the drop-in): rate of the hottest device function over independent (site, node) items —
+ * the headroom of a node-parallel formulation, see DESIGN.md */
+int  mc_bench_conductivity(mc_handle* h, int64_t n_items, int reps, double* evals_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ("mc_abi_version", "mc_backend_name", "mc_default_fluid", "mc_default_model", "mc_create", "mc_destroy",
            "mc_last_error", "mc_set_sites", "mc_get_state", "mc_set_state", "mc_step_days", "mc_step_days_device",
-           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak")
+           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity")
 
 
 def _nvcc():
@@ -78,5 +78,6 @@ def lib():
     L.mc_reset_counters.argtypes = [H]
     L.mc_get_status.argtypes = [H, C.POINTER(C.c_int32)]
     L.mc_measure_fp64_peak.argtypes = [H, C.POINTER(C.c_double)]
+    L.mc_bench_conductivity.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L

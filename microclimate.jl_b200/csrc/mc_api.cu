@@ -106,6 +106,23 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters)
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+/* Headroom probe (not on the product path): the hottest function of the soil right-hand side, soil_conductivity, evaluated over a flat
+ * array of independent (site, node) items — full lanes, no divergence, a tiny instruction window.  Its rate against the rate the same
+ * function achieves inside soil_chunk_kernel quantifies what a block-cooperative, node-parallel formulation could gain. */
+__global__ void __launch_bounds__(256) conductivity_items_kernel(const double* __restrict__ T, const double* __restrict__ theta, double* __restrict__ out, int64_t n, int reps)
+{
+    const mcd::DevModel& m = mcd::g_model_c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double th = theta[i], phim = 0.5, phig = mcd::jmax(0.0, 1.0 - th - phim), fw = 0.5, lam_m = 2.5;
+        double Ti = T[i], acc = 0.0;
+        for (int r = 0; r < reps; r++) {
+            acc += mcd::soil_conductivity(Ti, 101325.0, 1.0, 1.0, th, phim, phig, fw, lam_m);
+            Ti += 1e-3;
+        }
+        out[i] = acc + m.ga * 0.0;
+    }
+}
+
 /* ---------------------------------------------------------------- handle ---- */
 struct mc_handle {
     mc_model_desc model;
@@ -553,6 +570,31 @@ int mc_get_status(mc_handle* h, int32_t* status_host)
     MC_CUDA(h, cudaSetDevice(h->device));
     MC_CUDA(h, cudaMemcpyAsync(status_host, h->flags, (size_t)h->S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* development probe: evaluations per second of soil_conductivity over independent items (see conductivity_items_kernel) */
+int mc_bench_conductivity(mc_handle* h, int64_t n_items, int reps, double* evals_per_s)
+{
+    if (!h || !evals_per_s || n_items <= 0 || reps <= 0) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<double> T((size_t)n_items), th((size_t)n_items);
+    for (int64_t i = 0; i < n_items; i++) { T[(size_t)i] = 275.0 + (double)(i % 5000) * 0.01; th[(size_t)i] = 0.05 + (double)(i % 3000) * 1e-4; }
+    double *dT = nullptr, *dth = nullptr, *dout = nullptr;
+    MC_CUDA(h, cudaMalloc(&dT, (size_t)n_items * 8)); MC_CUDA(h, cudaMalloc(&dth, (size_t)n_items * 8)); MC_CUDA(h, cudaMalloc(&dout, (size_t)n_items * 8));
+    MC_CUDA(h, cudaMemcpyAsync(dT, T.data(), (size_t)n_items * 8, cudaMemcpyHostToDevice, h->stream));
+    MC_CUDA(h, cudaMemcpyAsync(dth, th.data(), (size_t)n_items * 8, cudaMemcpyHostToDevice, h->stream));
+    MC_CUDA(h, cudaMemcpyToSymbolAsync(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice, h->stream));
+    cudaDeviceProp prop; MC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8;
+    conductivity_items_kernel<<<blocks, 256, 0, h->stream>>>(dT, dth, dout, n_items, 1);
+    MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    conductivity_items_kernel<<<blocks, 256, 0, h->stream>>>(dT, dth, dout, n_items, reps);
+    MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f; MC_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *evals_per_s = (double)n_items * reps / (ms * 1e-3);
+    cudaFree(dT); cudaFree(dth); cudaFree(dout);
     return 0;
 }
 

@@ -189,6 +189,8 @@ def make_forcing(s0: int, s1: int, S_total: int, day0: int, ndays: int, *, threa
     S = s1 - s0
     if out is None:
         out = M.ForcingBatch(ndays, S, hourly_rain=True, day_of_year=[(d % 365) + 1 for d in range(day0, day0 + ndays)])
+    else:
+        out.day_of_year[:] = [(d % 365) + 1 for d in range(day0, day0 + ndays)]
     jobs = [(a, min(s1, a + block)) for a in range(s0, s1, block)]
     threads = threads or min(len(jobs), os.cpu_count() or 1)
     if threads <= 1:

@@ -295,7 +295,7 @@ static double sky_temperature(const mc_model_desc& m, double svf, double P, doub
 
 /* ------------------------------------------------------------------------------------------
  * Snow: SnowModel{8} (src/snow/snow_model.jl) and the apparent-heat-capacity closures
- * (src/apparent_heat_capacity/*.jl).  Depths in cm, densities in g/cm3, as upstream.
+ * (src/apparent_heat_capacity/ *.jl).  Depths in cm, densities in g/cm3, as upstream.
  * The reference's `snow_depth_hourly[nsteps]` scratch array is only ever read at [step] and
  * [step-1]; it is carried as two scalars (sd_cur, sd_prev).
  * ------------------------------------------------------------------------------------------ */
