@@ -61,6 +61,40 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
     }
 }
 
+/* Block-cooperative variant (NoSnow, fixed day-pass counts): a block owns blockDim.x sites; the conductivity of every RHS evaluation is
+ * served by the whole block over (requesting site, node) items (mc_device.cuh, "Block-cooperative ODE phase").  Threads past the end of
+ * the range mirror the last site (same values to the same addresses) so that every thread of a block reaches every barrier. */
+#ifndef MC_COOP_MIN_BLOCKS
+#define MC_COOP_MIN_BLOCKS 8
+#endif
+template <int NA>
+__global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_coop_kernel(const mcd::KArgs a)
+{
+    __shared__ mcd::CoopShared sh;
+    mcd::Counters cn = {};
+    double* scr = a.coop_scr + (size_t)blockIdx.x * ((size_t)mcd::SCR_ARRAYS * NA * mcd::COOP_TB);
+    for (int64_t base = a.s_begin + (int64_t)blockIdx.x * blockDim.x; base < a.s_end; base += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = base + threadIdx.x;
+        const bool valid = s < a.s_end;
+        if (!valid) s = a.s_end - 1;
+        mcd::Counters c1 = {};
+        mcd::solve_site_coop<NA>(a, s, c1, sh, scr);
+        if (valid) {
+            cn.n_rhs += c1.n_rhs; cn.n_accept += c1.n_accept; cn.n_reject += c1.n_reject; cn.n_obukhov += c1.n_obukhov;
+            cn.n_newton += c1.n_newton; cn.n_infil += c1.n_infil; cn.n_day_passes += c1.n_day_passes;
+        }
+    }
+    if (a.counters) {
+        atomicAdd(a.counters + 0, (unsigned long long)cn.n_rhs);
+        atomicAdd(a.counters + 1, (unsigned long long)cn.n_accept);
+        atomicAdd(a.counters + 2, (unsigned long long)cn.n_reject);
+        atomicAdd(a.counters + 3, (unsigned long long)cn.n_obukhov);
+        atomicAdd(a.counters + 4, (unsigned long long)cn.n_newton);
+        atomicAdd(a.counters + 5, (unsigned long long)cn.n_infil);
+        atomicAdd(a.counters + 6, (unsigned long long)cn.n_day_passes);
+    }
+}
+
 /* solve_air! for the rows of the chunk the soil kernel just wrote (reference src/simulation.jl:822-851) */
 __global__ void __launch_bounds__(128) air_profile_kernel(const mcd::KArgs a)
 {
@@ -149,6 +183,7 @@ struct mc_handle {
     /* chunk staging (grown on demand) */
     double* stage_in = nullptr; size_t stage_in_doubles = 0;
     double* stage_out = nullptr; size_t stage_out_doubles = 0;
+    double* coop_scr = nullptr; size_t coop_scr_doubles = 0;      /* per-block scratch of the block-cooperative kernel */
     double last_ms = 0.0; unsigned long long last_launches = 0;
 };
 
@@ -184,6 +219,40 @@ static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
     }
     soil_chunk_kernel<NA, NS><<<grid, BLOCK, pad, st>>>(a);
     return cudaGetLastError();
+}
+
+/* the block-cooperative kernel serves NoSnow models whose day-pass count is the same for every site (FixedIterations) */
+static bool coop_enabled(const mc_handle* h)
+{
+    static int legacy = -1;
+    if (legacy < 0) { const char* e = getenv("MC_KERNEL"); legacy = (e && std::strcmp(e, "legacy") == 0) ? 1 : 0; }
+    return !legacy && h->model.n_snow == 0 && h->dm.conv_kind == MC_CONV_FIXED;
+}
+
+template <int NA>
+static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
+{
+    constexpr int TB = mcd::COOP_TB;
+    int grid = (int)((a.s_end - a.s_begin + TB - 1) / TB);
+    static int per_sm = -1, n_sm = 0;
+    if (per_sm < 0) {
+        const char* e = getenv("MC_BLOCKS_PER_SM");
+        per_sm = e ? atoi(e) : 0;
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (per_sm > 0 && grid > per_sm * n_sm) grid = per_sm * n_sm;
+    const size_t need = (size_t)grid * mcd::SCR_ARRAYS * NA * TB;
+    if (h->coop_scr_doubles < need) {
+        MC_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < mc_handle::MAX_SLICES; k++) if (h->slice_stream[k]) MC_CUDA(h, cudaStreamSynchronize(h->slice_stream[k]));
+        if (h->coop_scr) { MC_CUDA(h, cudaFree(h->coop_scr)); h->coop_scr = nullptr; h->coop_scr_doubles = 0; }
+        MC_CUDA(h, cudaMalloc(&h->coop_scr, need * sizeof(double)));
+        h->coop_scr_doubles = need;
+    }
+    a.coop_scr = h->coop_scr;
+    soil_chunk_coop_kernel<NA><<<grid, TB, 0, st>>>(a);
+    MC_CUDA(h, cudaGetLastError());
+    return 0;
 }
 
 static void fill_site_state_args(mc_handle* h, mcd::KArgs& a)
@@ -289,7 +358,7 @@ void mc_destroy(mc_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out);
+    cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out); cudaFree(h->coop_scr);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
@@ -393,8 +462,11 @@ static int launch_range(mc_handle* h, mcd::KArgs a, int64_t lo, int64_t hi, cuda
 {
     a.s_begin = lo; a.s_end = hi;
     const int na = pick_na(h->N);
-    cudaError_t e;
-    if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, st) : (na == 19 ? launch_chunk<19, 0>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, st));
+    cudaError_t e = cudaSuccess;
+    if (coop_enabled(h)) {
+        if (int rc = na == 10 ? launch_chunk_coop<10>(h, a, st) : (na == 19 ? launch_chunk_coop<19>(h, a, st) : launch_chunk_coop<MC_MAX_SOIL_NODES>(h, a, st))) return rc;
+    }
+    else if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, st) : (na == 19 ? launch_chunk<19, 0>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, st));
     else e = na == 10 ? launch_chunk<10, MC_SNOW_NODES>(a, st) : (na == 19 ? launch_chunk<19, MC_SNOW_NODES>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, st));
     MC_CUDA(h, e);
     if (a.o_air_T || a.o_wind || a.o_rh || a.o_qc || a.o_ustar) {

@@ -8,6 +8,7 @@
  */
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include "../../microclimate.jl_b200/csrc/mc_device.cuh"
 
@@ -87,9 +88,15 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     a.L_air = e->L_air.data(); a.n_snow = e->model.n_snow; a.s_begin = 0; a.s_end = e->S;
     const bool want_air = a.o_air_T || a.o_wind || a.o_rh || a.o_qc || a.o_ustar;
     int nbad = 0;
+    /* same kernel selection as launch_range(): the block-cooperative path (here a "block" of one thread) for NoSnow + FixedIterations */
+    const char* kenv = getenv("MC_KERNEL");
+    const bool coop = !(kenv && std::strcmp(kenv, "legacy") == 0) && e->model.n_snow == 0 && mcd::g_model_h.conv_kind == MC_CONV_FIXED;
+    std::vector<double> scr((size_t)mcd::SCR_ARRAYS * MC_MAX_SOIL_NODES);
+    mcd::CoopShared sh;
     for (int64_t s = 0; s < e->S; s++) {
         mcd::Counters cn = {};
-        if (e->model.n_snow == 0) { if (e->N <= 10) mcd::solve_site<10, 0>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, 0>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, 0>(a, s, cn); }
+        if (coop) { if (e->N <= 10) mcd::solve_site_coop<10>(a, s, cn, sh, scr.data()); else if (e->N <= 19) mcd::solve_site_coop<19>(a, s, cn, sh, scr.data()); else mcd::solve_site_coop<MC_MAX_SOIL_NODES>(a, s, cn, sh, scr.data()); }
+        else if (e->model.n_snow == 0) { if (e->N <= 10) mcd::solve_site<10, 0>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, 0>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, 0>(a, s, cn); }
         else { if (e->N <= 10) mcd::solve_site<10, MC_SNOW_NODES>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, MC_SNOW_NODES>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, s, cn); }
         if (want_air) mcd::solve_air_site(a, s, cn);
         e->counters[0] += cn.n_rhs; e->counters[1] += cn.n_accept; e->counters[2] += cn.n_reject; e->counters[3] += cn.n_obukhov;
