@@ -65,20 +65,38 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
  * served by the whole block over (requesting site, node) items (mc_device.cuh, "Block-cooperative ODE phase").  Threads past the end of
  * the range mirror the last site (same values to the same addresses) so that every thread of a block reaches every barrier. */
 #ifndef MC_COOP_MIN_BLOCKS
-#define MC_COOP_MIN_BLOCKS 8
+#define MC_COOP_MIN_BLOCKS 1
+#endif
+#ifndef MC_COOP_V
+#define MC_COOP_V 2            /* 1: integrator vectors thread-local, conductivity served by the block; 2: every ODE node loop is an item pass */
+#endif
+#if MC_COOP_V == 2
+#define MC_COOP_ARRAYS mcd::P_ARRAYS
+#else
+#define MC_COOP_ARRAYS mcd::SCR_ARRAYS
 #endif
 template <int NA>
 __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_coop_kernel(const mcd::KArgs a)
 {
+#if MC_COOP_V == 2
+    __shared__ mcd::Coop2Shared sh;
+    if (threadIdx.x == 0) { sh.count[0] = 0; sh.count[1] = 0; }
+    __syncthreads();
+#else
     __shared__ mcd::CoopShared sh;
+#endif
     mcd::Counters cn = {};
-    double* scr = a.coop_scr + (size_t)blockIdx.x * ((size_t)mcd::SCR_ARRAYS * NA * mcd::COOP_TB);
+    double* scr = a.coop_scr + (size_t)blockIdx.x * ((size_t)MC_COOP_ARRAYS * NA * mcd::COOP_TB);
     for (int64_t base = a.s_begin + (int64_t)blockIdx.x * blockDim.x; base < a.s_end; base += (int64_t)gridDim.x * blockDim.x) {
         int64_t s = base + threadIdx.x;
         const bool valid = s < a.s_end;
         if (!valid) s = a.s_end - 1;
         mcd::Counters c1 = {};
+#if MC_COOP_V == 2
+        mcd::solve_site_coop2<NA>(a, s, c1, sh, scr);
+#else
         mcd::solve_site_coop<NA>(a, s, c1, sh, scr);
+#endif
         if (valid) {
             cn.n_rhs += c1.n_rhs; cn.n_accept += c1.n_accept; cn.n_reject += c1.n_reject; cn.n_obukhov += c1.n_obukhov;
             cn.n_newton += c1.n_newton; cn.n_infil += c1.n_infil; cn.n_day_passes += c1.n_day_passes;
@@ -241,7 +259,7 @@ static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
     if (per_sm > 0 && grid > per_sm * n_sm) grid = per_sm * n_sm;
-    const size_t need = (size_t)grid * mcd::SCR_ARRAYS * NA * TB;
+    const size_t need = (size_t)grid * MC_COOP_ARRAYS * NA * TB;
     if (h->coop_scr_doubles < need) {
         MC_CUDA(h, cudaStreamSynchronize(h->stream));
         for (int k = 0; k < mc_handle::MAX_SLICES; k++) if (h->slice_stream[k]) MC_CUDA(h, cudaStreamSynchronize(h->slice_stream[k]));
