@@ -14,6 +14,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "mc_device.cuh"
 
@@ -71,29 +72,30 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
 #define MC_COOP_V 2            /* 1: integrator vectors thread-local, conductivity served by the block; 2: every ODE node loop is an item pass */
 #endif
 #if MC_COOP_V == 2
-#define MC_COOP_ARRAYS mcd::P_ARRAYS
+#define MC_COOP_ROWS(NA) mcd::Coop2Rows<NA>::value
 #else
-#define MC_COOP_ARRAYS mcd::SCR_ARRAYS
+#define MC_COOP_ROWS(NA) ((size_t)mcd::SCR_ARRAYS * (NA))
 #endif
 template <int NA>
 __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_coop_kernel(const mcd::KArgs a)
 {
 #if MC_COOP_V == 2
     __shared__ mcd::Coop2Shared sh;
-    if (threadIdx.x == 0) { sh.count[0] = 0; sh.count[1] = 0; }
+    __shared__ mcd::MoistShared ms;
+    if (threadIdx.x == 0) { sh.count[0] = 0; sh.count[1] = 0; ms.countU[0] = ms.countU[1] = ms.countF[0] = ms.countF[1] = ms.alive[0] = ms.alive[1] = 0; }
     __syncthreads();
 #else
     __shared__ mcd::CoopShared sh;
 #endif
     mcd::Counters cn = {};
-    double* scr = a.coop_scr + (size_t)blockIdx.x * ((size_t)MC_COOP_ARRAYS * NA * mcd::COOP_TB);
+    double* scr = a.coop_scr + (size_t)blockIdx.x * (MC_COOP_ROWS(NA) * blockDim.x);
     for (int64_t base = a.s_begin + (int64_t)blockIdx.x * blockDim.x; base < a.s_end; base += (int64_t)gridDim.x * blockDim.x) {
         int64_t s = base + threadIdx.x;
         const bool valid = s < a.s_end;
         if (!valid) s = a.s_end - 1;
         mcd::Counters c1 = {};
 #if MC_COOP_V == 2
-        mcd::solve_site_coop2<NA>(a, s, c1, sh, scr);
+        mcd::solve_site_coop2<NA>(a, s, c1, sh, ms, scr);
 #else
         mcd::solve_site_coop<NA>(a, s, c1, sh, scr);
 #endif
@@ -250,16 +252,24 @@ static bool coop_enabled(const mc_handle* h)
 template <int NA>
 static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
 {
-    constexpr int TB = mcd::COOP_TB;
-    int grid = (int)((a.s_end - a.s_begin + TB - 1) / TB);
     static int per_sm = -1, n_sm = 0;
     if (per_sm < 0) {
         const char* e = getenv("MC_BLOCKS_PER_SM");
         per_sm = e ? atoi(e) : 0;
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    if (per_sm > 0 && grid > per_sm * n_sm) grid = per_sm * n_sm;
-    const size_t need = (size_t)grid * MC_COOP_ARRAYS * NA * TB;
+    /* block size: COOP_TB threads (one block per SM) when the range fills the machine, else the range spread over all SMs */
+    const int64_t n = a.s_end - a.s_begin;
+    int TB = mcd::COOP_TB;
+    if (n < (int64_t)n_sm * TB) {
+        const int64_t per = (n + n_sm - 1) / n_sm;
+        TB = (int)std::min<int64_t>(mcd::COOP_TB, std::max<int64_t>(128, (per + 31) / 32 * 32));
+    }
+    int grid = (int)((n + TB - 1) / TB);
+    /* more blocks than 8 per SM run as a grid-stride loop over batches of TB sites: bounds the scratch (2.8 MB per block at N = 19) */
+    const int cap = (per_sm > 0 ? per_sm : 8) * n_sm;
+    if (grid > cap) grid = cap;
+    const size_t need = (size_t)grid * MC_COOP_ROWS(NA) * TB;
     if (h->coop_scr_doubles < need) {
         MC_CUDA(h, cudaStreamSynchronize(h->stream));
         for (int k = 0; k < mc_handle::MAX_SLICES; k++) if (h->slice_stream[k]) MC_CUDA(h, cudaStreamSynchronize(h->slice_stream[k]));

@@ -28,6 +28,9 @@
 #include "../../include/microclimate_b200.h"
 #include "../../include/mc_math.h"
 
+#ifndef MC_COOP_MOIST
+#define MC_COOP_MOIST 0            /* 1: block-cooperative soil water balance (experimental: bit-identical but ~15 % slower than the per-site form, profiles/README.md) */
+#endif
 #if defined(__CUDACC__)
 #define MC_DEV __device__ __forceinline__
 #define MC_MEMBER __device__ __forceinline__
@@ -43,6 +46,10 @@
 #define MC_PRAGMA_STR(x) _Pragma(#x)
 #define MC_PRAGMA(x) MC_PRAGMA_STR(x)
 #define MC_CU MC_PRAGMA(unroll MC_COOP_UNROLL)
+#ifndef MC_THOMAS_UNROLL_N
+#define MC_THOMAS_UNROLL_N 3       /* owner-side Thomas sweeps: loads of the next rows issue under the divisions of the current one */
+#endif
+#define MC_THOMAS_UNROLL MC_PRAGMA(unroll MC_THOMAS_UNROLL_N)
 #if MC_TSIT5_ROLLED
 #define MC_UNROLL4 _Pragma("unroll 1")
 #else
@@ -61,6 +68,7 @@
 #define MC_ROLLED
 #define MC_UNROLL4
 #define MC_CU
+#define MC_THOMAS_UNROLL
 #define MC_CONST_MODEL g_model_h
 #define MC_TID 0
 #define MC_TB 1
@@ -97,6 +105,7 @@ struct DevModel {
     double depths[MAXN];
     double dzc[MAXN];       /* ld[i+1]-ld[i-1] (i>=1), ld[1] for i=0, with the zero sentinel at ld[N]   (heat_transport_1d.jl:175-210) */
     double dzg[MAXN];       /* ld[i+1]-ld[i] */
+    double mdz[MAXN + 2], mmass[MAXN + 2];   /* infiltration grid: depth[i+1]-depth[i] and layer water mass (campbell.jl:228-230), index i = 1..L */
     double zref, zloc, reltol, abstol, T_hi;
     double ga, gc, recirc_pow, theta0;
     double root_res, PC, RL, SP, root_radius;
@@ -1355,7 +1364,7 @@ MC_DEV void coop2_item_stage(const Coop2Shared& sh, Coop2Shared& shw, double* sc
     MC_SCR(P_T, i, o) = Tc;
     if (i < m.N - 1)
         MC_SCR(P_LAM, i, o) = soil_conductivity(Tc, sh.P[o], sh.p0p[o], sh.pp0[o], MC_SCR(P_TH, i, o), MC_SCR(P_PM, i, o), MC_SCR(P_PG, i, o),
-                                                MC_SCR(P_FW, i, o), MC_SCR(P_LM, i, o));
+                                                MC_SCR(P_FW, i, o), MC_SCR(P_LM, i, o)) / m.dzg[i];      /* the conductance lambda / dz of the layer below node i */
 }
 
 /* the error-estimate term of one node (stage 7), given its fresh k7 */
@@ -1382,8 +1391,8 @@ MC_DEV void coop2_item_conduct(const Coop2Shared& sh, double* scr, int o, int i)
     double du = 0.0;
     if (i < m.N - 1) {
         const double T_up = MC_SCR(P_T, i - 1, o), T_i = MC_SCR(P_T, i, o), T_dn = MC_SCR(P_T, i + 1, o);
-        const double G_up = MC_SCR(P_LAM, i - 1, o) / m.dzg[i - 1];
-        const double G_i = MC_SCR(P_LAM, i, o) / m.dzg[i];
+        const double G_up = MC_SCR(P_LAM, i - 1, o);
+        const double G_i = MC_SCR(P_LAM, i, o);
         du = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / MC_SCR(P_CAP, i, o);
     }
     MC_SCR(stage_out_array(stage, (code >> 4) & 1), i, o) = du;
@@ -1420,7 +1429,7 @@ MC_DEV_NOINLINE double coop2_surface(const HourPar& hp, const RhsCtx& R, const d
     const DevModel& m = MC_CONST_MODEL; const int tid = MC_TID;
     const double P = R.P, T_air = R.T_air, wind = R.wind, zen = R.zen, solar = R.solar, cloud = R.cloud, rh = R.rh;
     const double Ts_node = MC_SCR(P_T, 0, tid);
-    const double G_up = MC_SCR(P_LAM, 0, tid) / m.dzg[0];
+    const double G_up = MC_SCR(P_LAM, 0, tid);
     const double Q_cond = G_up * (MC_SCR(P_T, 1, tid) - Ts_node);
     double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
     if (hp.slope > 0.0 && zen < 90.0) {
@@ -1531,7 +1540,11 @@ MC_DEV_NOINLINE bool coop2_advance(Own2& I, Coop2Shared& sh, double* scr, Counte
                 {
                     double ss = 0.0;
                     ss += I.q0 * I.q0;
-                    MC_ROLLED for (int i = 1; i < N; i++) { const double q = MC_SCR(P_Q, i, tid); ss += q * q; }
+                    MC_ROLLED for (int i0 = 1; i0 < N; i0 += 6) {      /* in-order sum; the loads of a batch are issued together */
+                        double qv[6];
+                        _Pragma("unroll") for (int k = 0; k < 6; k++) qv[k] = i0 + k < N ? MC_SCR(P_Q, i0 + k, tid) : 0.0;
+                        _Pragma("unroll") for (int k = 0; k < 6; k++) if (i0 + k < N) ss += qv[k] * qv[k];
+                    }
                     const double EEst = sqrt(ss / N);
                     I.u_modified = false;
                     double q;
@@ -1604,14 +1617,16 @@ MC_DEV void coop2_rounds(Own2& I, bool pending, const HourPar& hp, Coop2Shared& 
         sh.list[0] = tid;
 #endif
         if (A == 0) break;                        /* parity stays: count[par] is still zero for the next call */
+        /* item j = node * A + (index into the list); j / A by multiplication (exact for j < 2^20, A <= 1024) */
+        const unsigned long long magic = (0x100000000ull + (unsigned)A - 1ull) / (unsigned)A;
         {   /* pass 1: stage vector, clamp, conductivity */
             const int total = A * N;
-            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = j / A; coop2_item_stage<NA>(sh, sh, scr, sh.list[j - node * A], node); }
+            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); coop2_item_stage<NA>(sh, sh, scr, sh.list[j - node * A], node); }
         }
         MC_BLOCK_SYNC();
         {   /* pass 2: conduction of nodes 1..N-1 */
             const int total = A * (N - 1);
-            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = j / A; coop2_item_conduct<NA>(sh, scr, sh.list[j - node * A], node + 1); }
+            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); coop2_item_conduct<NA>(sh, scr, sh.list[j - node * A], node + 1); }
         }
         if (pending) {
             cn.n_rhs++;
@@ -1810,7 +1825,7 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
  * Every floating-point operation is the reference's, in the reference's order per node (results are bit-identical to the
  * unfused form, which the oracle keeps). */
 template <int NA>
-MC_DEV_NOINLINE InfilOut infiltration_step_psi(const HourMoist<NA>& hm, InfilWork<NA>& B, double* theta, double rh_loc, double lai, double ET, Counters& cn)
+MC_DEV_NOINLINE InfilOut infiltration_step_psi(const HourMoist<NA>& hm, InfilWork<NA>& B, double* theta, double rh_loc, double lai, double ET, Counters& cn, bool warm)
 {
     const DevModel& m = MC_CONST_MODEL;
     cn.n_infil++;
@@ -1820,12 +1835,19 @@ MC_DEV_NOINLINE InfilOut infiltration_step_psi(const HourMoist<NA>& hm, InfilWor
     const double TP = ET - EP;
     /* initial state from water content + root/soil resistances (campbell.jl:215-267) */
     double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
+    /* warm: B still holds the previous sub-step of this hour.  Its final state IS this sub-step's initial state (water content copied to
+     * theta, potential and humidity the same functions of it), so only a row whose theta was changed since (the wetted surface node)
+     * is rebuilt; the reference recomputes all rows to the same bits (the oracle keeps that form). */
     MC_ROLLED for (int i = 2; i <= L; i++) {
         const double wcn = theta[i - 2];
-        const double psi = hm.psi_e[i] * mcm::pow(hm.sat[i] / wcn, hm.bb[i]);
+        double psi;
+        if (warm && wcn == B.wcn[i]) psi = B.psi[i];
+        else {
+            psi = hm.psi_e[i] * mcm::pow(hm.sat[i] / wcn, hm.bb[i]);
+            B.wcn[i] = wcn; B.psi[i] = psi;
+            B.h[i] = mcm::exp(MW_INFIL * psi / hm.rts[i]);
+        }
         const double K = hm.ks[i] * mcm::pow(hm.psi_e[i] / psi, hm.nexp[i]);
-        B.wcn[i] = wcn; B.psi[i] = psi;
-        B.h[i] = mcm::exp(MW_INFIL * psi / hm.rts[i]);
         const double soilR = hm.rootZ[i] / K;
         B.soilR[i] = soilR;
         const double rt = soilR + hm.rootR[i];
@@ -2031,7 +2053,7 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     InfilWork<NA> B;
     InfilOut io; io.evaporation = 0.0; io.surface_water_flux = 0.0; io.hit_max = false;
     MC_ROLLED for (int k = 0; k < m.niter_moist; k++) {
-        io = m.flux_alg ? infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn) : infiltration_step_psi<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn);
+        io = m.flux_alg ? infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn) : infiltration_step_psi<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn, k > 0);
         if (io.hit_max) flags |= MC_STATUS_NEWTON_MAXITER;
         pool = jclamp(pool - jmax(0.0, io.surface_water_flux) - jmax(0.0, io.evaporation), 0.0, m.max_pool);
         pool = wet_surface_node(theta, pool, sat0, half);
@@ -2040,6 +2062,332 @@ MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, co
     return jclamp(jmax(0.0, io.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
 }
 
+
+/* ==========================================================================================================================
+ * Block-cooperative soil water balance (soil_water_balance!, campbell.jl:378-495, water-potential form).  The Newton iterations of
+ * the implicit infiltration step are where sites of a warp diverge most (2 to 500 iterations per sub-step), and one iteration is
+ * almost entirely per-node work (3 pow + 1 exp per node).  Every site runs its own (sub-step, iteration) sequence; each round the
+ * block serves, for the sites that need them,
+ *
+ *     U-pass : per node, new water content / potential / humidity / conductivity from the back-substituted potential     | barrier
+ *     F-pass : per node, the mass-balance residual and the tridiagonal row (vapour flux, capacity, gravity terms)          | barrier
+ *     owners : in-order residual sum, Thomas elimination and back-substitution, convergence, sub-step bookkeeping          | barrier
+ *
+ * so a site that needs 500 iterations costs 500 short rounds instead of stalling its warp for 500 serial sweeps of the profile.
+ * Arithmetic and operation order are those of infiltration_step_psi / soil_water_hour above.
+ * ========================================================================================================================== */
+enum { M_PSIE = 0, M_SAT, M_BB, M_KS, M_NEXP, M_ROOTR, M_ROOTZ, M_KVC, M_RTS, M_PSI, M_K, M_H, M_WCN, M_TH0, M_SUB, M_DIA, M_SUP, M_F, M_UPT, M_CC, M_RR, M_Q1, M_Q2, M_RT, M_ARRAYS };
+#define MC_MSCR(arr, i, t) scr[((size_t)(P_ARRAYS * NA + (arr) * (NA + 2) + (i))) * MC_TB + (t)]
+enum { MF_FIRST = 1, MF_S0 = 2, MF_FINAL = 4 };
+template <int NA> struct Coop2Rows { static constexpr size_t value = (size_t)P_ARRAYS * NA + (MC_COOP_MOIST ? (size_t)M_ARRAYS * (NA + 2) : 0); };
+
+struct MoistShared { int listF[COOP_TB]; int countU[2], countF[2], alive[2]; };
+
+/* U-pass item: node i (2..L) of site o */
+template <int NA>
+MC_DEV void moist_item_update(const Coop2Shared& sh, double* scr, int o, int i)
+{
+    const int fl = sh.code[o];
+    const double psi_e = MC_MSCR(M_PSIE, i, o), sat = MC_MSCR(M_SAT, i, o), bb = MC_MSCR(M_BB, i, o);
+    double wcn;
+    if (fl & MF_S0) wcn = MC_MSCR(M_TH0, i, o);
+    else wcn = jmax(sat * mcm::pow(psi_e / MC_MSCR(M_PSI, i, o), 1.0 / bb), 1e-7);
+    const double psi = psi_e * mcm::pow(sat / wcn, bb);
+    MC_MSCR(M_WCN, i, o) = wcn; MC_MSCR(M_PSI, i, o) = psi;
+    MC_MSCR(M_H, i, o) = mcm::exp(MW_INFIL * psi / MC_MSCR(M_RTS, i, o));
+    const double K = MC_MSCR(M_KS, i, o) * mcm::pow(psi_e / psi, MC_MSCR(M_NEXP, i, o));
+    MC_MSCR(M_K, i, o) = K;
+    if (fl & MF_FINAL) MC_MSCR(M_TH0, i, o) = wcn;
+    if (fl & (MF_FINAL | MF_S0)) {          /* this state starts the next sub-step: root + soil resistance terms of its stomatal balance (campbell.jl:253-267) */
+        const double rt = MC_MSCR(M_ROOTZ, i, o) / K + MC_MSCR(M_ROOTR, i, o);
+        MC_MSCR(M_RT, i, o) = rt; MC_MSCR(M_Q1, i, o) = psi / rt; MC_MSCR(M_Q2, i, o) = 1.0 / rt;
+    }
+}
+
+/* F-pass item: residual and tridiagonal row of node i (2..L) of site o (root uptake is formed in a sub-step's first iteration).
+ * sh.P = EP, sh.p0p = rh_loc, sh.pp0 = R * Ts[1], sh.dt = psi[1] of the sub-step. */
+template <int NA>
+MC_DEV void moist_item_assemble(const Coop2Shared& sh, double* scr, int o, int i)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const int L = m.N;
+    const double g = m.g, dt = m.moist_dt;
+    const bool first = (sh.code[o] & MF_FIRST) != 0;
+    const double psic = MC_MSCR(M_PSI, i, o), Kc = MC_MSCR(M_K, i, o), wcnc = MC_MSCR(M_WCN, i, o), hc = MC_MSCR(M_H, i, o);
+    const double nexp = MC_MSCR(M_NEXP, i, o), sat = MC_MSCR(M_SAT, i, o);
+    double psim, Km, jvm, djvm;
+    if (i == 2) {
+        const double EP = sh.P[o], rh_loc = sh.p0p[o];
+        psim = first ? psic : sh.dt[o]; Km = 0.0;
+        jvm = EP * (hc - rh_loc) / (1.0 - rh_loc);
+        djvm = EP * MW_INFIL * hc / (sh.pp0[o] * (1.0 - rh_loc));
+    } else {
+        psim = MC_MSCR(M_PSI, i - 1, o); Km = MC_MSCR(M_K, i - 1, o);
+        const double wcnm = MC_MSCR(M_WCN, i - 1, o), hm1 = MC_MSCR(M_H, i - 1, o);
+        const double kvm = MC_MSCR(M_KVC, i - 1, o) * (MC_MSCR(M_SAT, i - 1, o) - (wcnm + wcnc) / 2.0) / m.mdz[i - 1];
+        jvm = kvm * (hc - hm1);
+        djvm = MW_INFIL * hm1 * kvm / MC_MSCR(M_RTS, i - 1, o);
+    }
+    double psip, Kp, wcnp, hp;
+    if (i + 1 <= L) { psip = MC_MSCR(M_PSI, i + 1, o); Kp = MC_MSCR(M_K, i + 1, o); wcnp = MC_MSCR(M_WCN, i + 1, o); hp = MC_MSCR(M_H, i + 1, o); }
+    else { psip = MC_MSCR(M_PSIE, L, o); Kp = MC_MSCR(M_KS, L, o); wcnp = MC_MSCR(M_SAT, L, o); hp = first ? 1.0 : hc; }   /* row L+1: psi_e[L], ks[L], sat[L+1] = sat[L], h = 1 then h[L] */
+    const double kv = MC_MSCR(M_KVC, i, o) * (sat - (wcnc + wcnp) / 2.0) / m.mdz[i];
+    const double jvi = kv * (hp - hc);
+    const double djvi = MW_INFIL * hc * kv / MC_MSCR(M_RTS, i, o);
+    const double cap = -1.0 * m.mmass[i] * wcnc / (MC_MSCR(M_BB, i, o) * psic * dt);
+    const double sub = -1.0 * Km / m.mdz[i - 1] + g * nexp * Km / psim;
+    const double sup = -1.0 * Kp / m.mdz[i];
+    const double dia = Kc / m.mdz[i - 1] + Kc / m.mdz[i] + cap - g * nexp * Kc / psic + djvm + djvi;
+    double uptake;
+    if (first) { uptake = (psic - MC_MSCR(M_UPT, 0, o) - MC_MSCR(M_UPT, 1, o)) / MC_MSCR(M_RT, i, o); MC_MSCR(M_UPT, i, o) = uptake; }   /* rows 0, 1: psi_leaf, RL * TR */
+    else uptake = MC_MSCR(M_UPT, i, o);
+    const double F = ((psic * Kc - psim * Km) / m.mdz[i - 1] - (psip * Kp - psic * Kc) / m.mdz[i]) / (1.0 - nexp)
+                   + m.mmass[i] * (wcnc - MC_MSCR(M_TH0, i, o)) / dt - g * (Km - Kc) + jvm - jvi + uptake;
+    MC_MSCR(M_SUB, i, o) = sub; MC_MSCR(M_DIA, i, o) = dia; MC_MSCR(M_SUP, i, o) = sup; MC_MSCR(M_F, i, o) = F;
+}
+
+struct MoistOwn {
+    double EP, TP, rh_loc, K2, K3, TR, evaporation, surface_water_flux, pool, sat0, half;
+    int k, counter, state;         /* state: 0 = done, 1 = sub-step start owed, 2 = Newton iteration owed */
+    bool hit_any;
+};
+
+/* owner: start of sub-step k (the part of infiltration_step! before the Newton loop): root/soil resistances, stomatal Newton, uptake */
+template <int NA>
+MC_DEV_NOINLINE void moist_substep_start(MoistOwn& W, Coop2Shared& sh, double* scr, Counters& cn)
+{
+    const DevModel& m = MC_CONST_MODEL; const int L = m.N; const int tid = MC_TID;
+    cn.n_infil++;
+    double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
+    MC_ROLLED for (int i0 = 2; i0 <= L; i0 += 4) {                           /* in-order sums of the per-node quotients the U-pass left */
+        double q1[4], q2[4];
+        _Pragma("unroll") for (int k = 0; k < 4; k++) { q1[k] = i0 + k <= L ? MC_MSCR(M_Q1, i0 + k, tid) : 0.0; q2[k] = i0 + k <= L ? MC_MSCR(M_Q2, i0 + k, tid) : 0.0; }
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (i0 + k <= L) { psum += q1[k]; rsum += q2[k]; }
+    }
+    sh.dt[tid] = MC_MSCR(M_PSI, 2, tid);                                     /* water_potential[1] = water_potential[2], never updated again */
+    const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
+    const double RL = m.RL, PC = m.PC, SP = m.SP, TP = W.TP;
+    int counter = 0;
+    while (counter < m.moist_max_it) {                                       /* stomatal Newton, campbell.jl:270-284 */
+        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
+        const double xp = mcm::pow(psi_leaf / PC, SP);
+        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
+        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
+        psi_leaf = psi_leaf - resid / slope;
+        counter++;
+        if (fabs(resid) <= 10.0) break;
+    }
+    W.TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
+    MC_MSCR(M_UPT, 0, tid) = psi_leaf; MC_MSCR(M_UPT, 1, tid) = RL * W.TR;    /* the first F-pass forms uptake[i] = (psi[i] - psi_leaf - RL TR) / (rootR[i] + soilR[i]) */
+    W.counter = 0;
+}
+
+/* owner: one Newton iteration's serial part: residual sum, Thomas elimination, back-substitution with the saturation clamps.
+ * Returns true when this was the sub-step's last iteration (converged or iteration cap). */
+template <int NA>
+MC_DEV_NOINLINE bool moist_thomas(MoistOwn& W, double* scr, Counters& cn, int& flags)
+{
+    const DevModel& m = MC_CONST_MODEL; const int L = m.N; const int tid = MC_TID;
+    W.counter++; cn.n_newton++;
+    W.K2 = MC_MSCR(M_K, 2, tid);
+    W.K3 = 3 <= L ? MC_MSCR(M_K, 3, tid) : MC_MSCR(M_KS, L, tid);
+    double err = 0.0, ccm = 0.0, rrm = 0.0, diaL = 0.0, FL = 0.0;
+    MC_THOMAS_UNROLL for (int i = 2; i <= L; i++) {
+        const double sub = MC_MSCR(M_SUB, i, tid), sup = MC_MSCR(M_SUP, i, tid);
+        double dia = MC_MSCR(M_DIA, i, tid);
+        double F = MC_MSCR(M_F, i, tid);
+        err += fabs(F);
+        if (i >= 3) { dia -= sub * ccm; F -= sub * rrm; }
+        if (i <= L - 1) {
+            double cc = sup / dia;
+            if (fabs(cc) < 1e-8) cc = 0.0;
+            const double rr = F / dia;
+            MC_MSCR(M_CC, i, tid) = cc; MC_MSCR(M_RR, i, tid) = rr; ccm = cc; rrm = rr;
+        } else { diaL = dia; FL = F; }
+    }
+    double dpsi = FL / diaL;
+    MC_THOMAS_UNROLL for (int i = L; i >= 2; i--) {
+        double psi = MC_MSCR(M_PSI, i, tid);
+        const double psi_e = MC_MSCR(M_PSIE, i, tid);
+        if (i == L) psi = jmin(psi - dpsi, psi_e);
+        else {
+            dpsi = MC_MSCR(M_RR, i, tid) - MC_MSCR(M_CC, i, tid) * dpsi;
+            psi -= dpsi;
+            if (psi > psi_e) psi = (psi + dpsi + psi_e) / 2.0;
+        }
+        MC_MSCR(M_PSI, i, tid) = psi;                                         /* raw potential: the U-pass turns it into the new state */
+    }
+    const bool converged = err <= m.moist_tol;
+    const bool last = converged || W.counter >= m.moist_max_it;
+    if (last && !converged) { flags |= MC_STATUS_NEWTON_MAXITER; }
+    return last;
+}
+
+/* soil_water_balance! for the hour, cooperatively.  Same interface as soil_water_hour (water-potential form, no snow). */
+template <int NA>
+MC_DEV double soil_water_hour_coop(const SiteRef& r, const EnvInstant& e, const double* T0, double* theta, double& pool,
+                                   double z0, double& L_prof, double* psi_out, double* h_out, int& flags, Counters& cn,
+                                   Coop2Shared& sh, MoistShared& ms, double* scr, int& par_io)
+{
+    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
+    const int N = m.N, L = N; const int tid = MC_TID, TB = MC_TB;
+    const double T_surf = T0[0], T_air = e.T_ref, P = e.P, rh = e.rh;
+    /* atmospheric_surface_profile! restricted to what is consumed here (monin_obukhov.jl:85-206) */
+    const double z = m.zref, hloc = m.zloc;
+    const double lz = mcm::log(z / z0);
+    const double dT = T_air - T_surf;
+    const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
+    double T_loc, Qc;
+    if (T_air >= T_surf || e.zenith >= 90.0) {
+        const double ustar = jmax(m.kappa * e.wind / lz, 1.0e-6);
+        const double Stb = 0.64 / lz, Sts = sublayer_stanton(z0, ustar);
+        Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
+        const double Tz0 = (T_air * Stb + T_surf * Sts) / (Stb + Sts);
+        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
+        else if (hloc == z) T_loc = T_air;
+        else T_loc = Tz0 + (T_air - Tz0) * mcm::log(hloc / z0) / lz;
+    } else {
+        const Obukhov o = calc_obukhov(e.wind, z0, z, lz, dT, rho_cp, L_prof);
+        cn.n_obukhov += o.iters;
+        L_prof = o.L; Qc = o.Q;
+        const double Tz0 = (T_air * o.Stb + T_surf * o.Sts) / (o.Stb + o.Sts);
+        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
+        else if (hloc == z) T_loc = T_air;
+        else {
+            const double x = calc_phi_m(hloc, m.gamma, o.L);
+            const double tl = jmax(mcm::log(hloc / z0) - calc_psi_h(x), 1e-6);
+            T_loc = Tz0 + (T_air - Tz0) * tl / (lz - o.psi_h);
+        }
+    }
+    /* local relative humidity and potential evaporation (campbell.jl:416-440) */
+    const double es_air = goff_gratch(T_air);
+    const double e_ref = es_air * rh;
+    const double rh_ref_prof = jclamp(e_ref / es_air, 0.0, 1.0);
+    const double rh_loc = jclamp((es_air * rh_ref_prof) / goff_gratch(T_loc), 0.0, 0.99);
+    const double hc = jmax(fabs(Qc / (T_surf - T_air)), 0.5);
+    const WetAir wa = wet_air(T_air, rh, P);
+    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
+    const double Tsc = T_surf < T_LO ? T_LO : T_surf;
+    const double Qe = (hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);      /* saturated=true */
+    const double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
+
+    /* per-hour constants of the implicit solve, into the block's scratch (rows 1..L of the reference's 1-based profile) */
+    MC_ROLLED for (int i = 1; i <= L; i++) {
+        const double b = r.node(a.bb, i - 1), pe = -fabs(r.node(a.psi_e, i - 1)), ksat = r.node(a.ks, i - 1);
+        const double nexp = 2.0 + 3.0 / b;
+        MC_MSCR(M_PSIE, i, tid) = pe; MC_MSCR(M_BB, i, tid) = b; MC_MSCR(M_KS, i, tid) = ksat;
+        MC_MSCR(M_SAT, i, tid) = 1.0 - r.node(a.bd, i - 1) / r.node(a.md, i - 1);
+        MC_MSCR(M_NEXP, i, tid) = nexp;
+        if (i >= 2) {
+            const double rd = r.node(a.rootd, i - 1);
+            const double thick = (i == L ? 1e20 : m.depths[i - 1]) - (i == 2 ? -1e10 : (i == 3 ? 0.0 : m.depths[i - 3]));      /* depth[i+1] - depth[i-1] */
+            if (rd > 0.0) {
+                MC_MSCR(M_ROOTR, i, tid) = m.root_res / (rd * thick / 2.0);
+                MC_MSCR(M_ROOTZ, i, tid) = (1.0 - nexp) * mcm::log(PI_D * m.root_radius * m.root_radius * rd) / (4.0 * PI_D * rd * thick / 2.0);
+            } else { MC_MSCR(M_ROOTR, i, tid) = 1e20; MC_MSCR(M_ROOTZ, i, tid) = 0.0; }
+            MC_MSCR(M_KVC, i, tid) = 0.66 * DV_INFIL * vapour_density_sat(T0[i - 1]);
+            MC_MSCR(M_RTS, i, tid) = m.R * T0[i - 2];
+        }
+    }
+    MoistOwn W;
+    W.sat0 = 1.0 - r.node(a.bd, 0) / r.node(a.md, 0);
+    W.half = (m.depths[1] - m.depths[0]) / 2.0;
+    pool = wet_surface_node(theta, pool, W.sat0, W.half);
+    MC_ROLLED for (int i = 2; i <= L; i++) MC_MSCR(M_TH0, i, tid) = theta[i - 2];
+    W.EP = mcm::exp(-0.82 * e.lai) * EPot; W.TP = EPot - W.EP; W.rh_loc = rh_loc; W.pool = pool;
+    W.k = 0; W.counter = 0; W.state = m.niter_moist > 0 ? 1 : 0; W.hit_any = false; W.evaporation = 0.0; W.surface_water_flux = 0.0; W.TR = 0.0; W.K2 = 0.0; W.K3 = 0.0;
+    sh.P[tid] = W.EP; sh.p0p[tid] = rh_loc; sh.pp0[tid] = m.R * T0[0];
+
+    /* rounds.  needU / needF say which passes this site takes part in next round. */
+    bool needU = W.state != 0, needF = false;
+    sh.code[tid] = (unsigned char)(MF_S0);
+    int par = par_io;
+    for (;;) {
+        const bool alive = W.state != 0;
+#if defined(__CUDACC__)
+        {
+            const unsigned bu = __ballot_sync(0xffffffffu, needU), bf = __ballot_sync(0xffffffffu, needF), ba = __ballot_sync(0xffffffffu, alive);
+            const int lane = tid & 31;
+            int baseU = 0, baseF = 0;
+            if (lane == 0) {
+                if (bu) baseU = atomicAdd(&ms.countU[par], __popc(bu));
+                if (bf) baseF = atomicAdd(&ms.countF[par], __popc(bf));
+                if (ba) atomicAdd(&ms.alive[par], __popc(ba));
+            }
+            baseU = __shfl_sync(0xffffffffu, baseU, 0); baseF = __shfl_sync(0xffffffffu, baseF, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (needU) sh.list[baseU + __popc(bu & lt)] = tid;
+            if (needF) ms.listF[baseF + __popc(bf & lt)] = tid;
+        }
+        __syncthreads();
+        const int AU = ms.countU[par], AF = ms.countF[par], AL = ms.alive[par];
+        if (tid == 0) { ms.countU[par ^ 1] = 0; ms.countF[par ^ 1] = 0; ms.alive[par ^ 1] = 0; }
+#else
+        const int AU = needU ? 1 : 0, AF = needF ? 1 : 0, AL = alive ? 1 : 0;
+        sh.list[0] = tid; ms.listF[0] = tid;
+#endif
+        if (AL == 0) break;
+        if (AU > 0) {
+            const unsigned long long magic = (0x100000000ull + (unsigned)AU - 1ull) / (unsigned)AU;
+            const int total = AU * (L - 1);
+            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); moist_item_update<NA>(sh, scr, sh.list[j - node * AU], node + 2); }
+        }
+        MC_BLOCK_SYNC();
+        if (AF > 0) {
+            const unsigned long long magic = (0x100000000ull + (unsigned)AF - 1ull) / (unsigned)AF;
+            const int total = AF * (L - 1);
+            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); moist_item_assemble<NA>(sh, scr, ms.listF[j - node * AF], node + 2); }
+        }
+        MC_BLOCK_SYNC();
+        /* owner slot */
+        if (needF) {                                                          /* a Newton iteration was assembled: solve it */
+            const bool last = moist_thomas<NA>(W, scr, cn, flags);
+            needU = true; needF = !last;
+            sh.code[tid] = (unsigned char)(last ? MF_FINAL : 0);
+            if (last) W.state = 1;                                            /* next owner slot: sub-step bookkeeping */
+        } else if (W.state == 1) {
+            if (W.counter > 0) {                                              /* end of sub-step k (after its last update): infiltration_step!'s outputs + pool */
+                const double psi2 = MC_MSCR(M_PSI, 2, tid), psi3 = 3 <= L ? MC_MSCR(M_PSI, 3, tid) : MC_MSCR(M_PSIE, L, tid);
+                W.surface_water_flux = ((psi2 * W.K2 - psi3 * W.K3) / ((1.0 - MC_MSCR(M_NEXP, 2, tid)) * m.mdz[2]) + m.g * W.K2 + W.TR) * m.moist_dt;
+                W.evaporation = W.EP * (MC_MSCR(M_H, 2, tid) - W.rh_loc) / (1.0 - W.rh_loc) * m.moist_dt;
+                W.pool = jclamp(W.pool - jmax(0.0, W.surface_water_flux) - jmax(0.0, W.evaporation), 0.0, m.max_pool);
+                if (W.pool > 0.0) {                                           /* wet_surface_node on theta[0] = row 2 */
+                    double th0 = MC_MSCR(M_TH0, 2, tid);
+                    const double before = th0;
+                    W.pool = wet_surface_node(&th0, W.pool, W.sat0, W.half);
+                    if (th0 != before) MC_MSCR(M_TH0, 2, tid) = th0;
+                    if (th0 != before && W.k + 1 < m.niter_moist) {           /* the next sub-step's start recomputes the state of row 2 from the wetted water content */
+                        const double psi_e = MC_MSCR(M_PSIE, 2, tid);
+                        const double psi = psi_e * mcm::pow(MC_MSCR(M_SAT, 2, tid) / th0, MC_MSCR(M_BB, 2, tid));
+                        MC_MSCR(M_WCN, 2, tid) = th0; MC_MSCR(M_PSI, 2, tid) = psi;
+                        MC_MSCR(M_H, 2, tid) = mcm::exp(MW_INFIL * psi / MC_MSCR(M_RTS, 2, tid));
+                        const double K = MC_MSCR(M_KS, 2, tid) * mcm::pow(psi_e / psi, MC_MSCR(M_NEXP, 2, tid));
+                        MC_MSCR(M_K, 2, tid) = K;
+                        const double rt = MC_MSCR(M_ROOTZ, 2, tid) / K + MC_MSCR(M_ROOTR, 2, tid);
+                        MC_MSCR(M_RT, 2, tid) = rt; MC_MSCR(M_Q1, 2, tid) = psi / rt; MC_MSCR(M_Q2, 2, tid) = 1.0 / rt;
+                    }
+                }
+                W.k++;
+            }
+            if (W.k < m.niter_moist) {
+                moist_substep_start<NA>(W, sh, scr, cn);
+                sh.code[tid] = (unsigned char)MF_FIRST;
+                needU = false; needF = true; W.state = 2;
+            } else { needU = false; needF = false; W.state = 0; }
+        }
+        MC_BLOCK_SYNC();
+        par ^= 1;
+    }
+    par_io = par;
+    pool = W.pool;
+    if (m.niter_moist > 0) {
+        MC_ROLLED for (int i = 2; i <= L; i++) theta[i - 2] = MC_MSCR(M_TH0, i, tid);
+        theta[L - 1] = MC_MSCR(M_SAT, L, tid);                               /* water_content[L+1] = saturation of the last row */
+    }
+    MC_ROLLED for (int i = 0; i < N - 1; i++) { psi_out[i] = MC_MSCR(M_PSI, i + 2, tid); h_out[i] = MC_MSCR(M_H, i + 2, tid); }
+    psi_out[N - 1] = MC_MSCR(M_PSIE, L, tid); h_out[N - 1] = MC_MSCR(M_H, L, tid);      /* row L+1: psi_e[L], h[L+1] = h[L] */
+    return jclamp(jmax(0.0, W.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
+}
 
 /* theta-only soil property terms for the coming ODE hour (theta is constant while the ODE advances) */
 template <int NA, int NS>
@@ -2545,7 +2893,7 @@ MC_DEV void solve_site_coop(const KArgs& a, int64_t s, Counters& cn, CoopShared&
 
 /* solve_soil! for one site with the block-cooperative ODE phase in its second form (integrator vectors in the block's scratch) */
 template <int NA>
-MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Shared& sh, double* scr)
+MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Shared& sh, MoistShared& ms, double* scr)
 {
     const DevModel& m = MC_CONST_MODEL;
     const int N = m.N;
@@ -2556,6 +2904,8 @@ MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Share
     const int tid = MC_TID;
 
     HourPar hp; Own2 I;
+    const bool coop_moist = MC_COOP_MOIST && !m.flux_alg && m.niter_moist >= 1 && m.moist_max_it >= 1;      /* water-potential form of infiltration_step! */
+    int mpar = 0; (void)mpar; (void)coop_moist; (void)ms;
     double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
     double psi_out[NA], h_out[NA];
     MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; MC_SCR(P_LM, i, tid) = r.node(a.lam_m, i); }
@@ -2698,6 +3048,10 @@ MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Share
                     else rain = (i == midnight_i) ? env.rain_daily : 0.0;
                     pool = jclamp(pool + rain, 0.0, m.max_pool);
                     if (dynamic) {
+#if MC_COOP_MOIST
+                        if (coop_moist) wet_dyn = soil_water_hour_coop<NA>(r, env, T0, theta, pool, hp.z0, L_prof, psi_out, h_out, flags, cn, sh, ms, scr, mpar);
+                        else
+#endif
                         wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn, false);
                         have_infil = true;
                     }
@@ -2807,6 +3161,14 @@ static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
     MC_ROLLED for (int i = 0; i < N; i++) {
         d.dzc[i] = i == 0 ? ld[1] : ld[i + 1] - ld[i - 1];
         d.dzg[i] = ld[i + 1] - ld[i];
+    }
+    {   /* same expressions as soil_water_hour: depth[1] = -1e10, depth[2] = 0, depth[i+1] = depths[i-1], depth[L+1] = 1e20 */
+        const int L = N;
+        auto depth_final = [&](int i) -> double { return i == 1 ? -1e10 : (i == 2 ? 0.0 : (i == L + 1 ? 1e20 : d.depths[i - 2])); };
+        auto depth_mass = [&](int i) -> double { return i <= 2 ? 0.0 : d.depths[i - 2]; };
+        for (int i = 0; i < MAXN + 2; i++) { d.mdz[i] = 0.0; d.mmass[i] = 0.0; }
+        for (int i = 1; i <= L; i++) d.mdz[i] = depth_final(i + 1) - depth_final(i);
+        for (int i = 2; i <= L; i++) d.mmass[i] = WATER_RHO * (depth_mass(i + 1) - depth_mass(i - 1)) / 2.0;
     }
     d.zref = md.reference_height_m; d.zloc = md.local_height_m; d.reltol = md.reltol; d.abstol = md.abstol;
     d.T_hi = md.maximum_surface_temperature_K;

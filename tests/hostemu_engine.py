@@ -15,14 +15,35 @@ _DEPS = [os.path.join(_HERE, "hostemu.cpp"), os.path.join(_ROOT, "microclimate.j
          os.path.join(_ROOT, "include", "microclimate_b200.h")]
 
 
-def build(force=False):
-    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(d) for d in _DEPS):
-        return _SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-mfma", "-o", _SO, os.path.join(_HERE, "hostemu.cpp")])
-    return _SO
+def build(force=False, so=_SO, defs=()):
+    if not force and os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(d) for d in _DEPS):
+        return so
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-mfma", *defs, "-o", so, os.path.join(_HERE, "hostemu.cpp")])
+    return so
 
 
 _lib = None
+_variants = {}
+
+
+def _bind(L):
+    L.he_create.restype = C.c_void_p
+    L.he_create.argtypes = [C.POINTER(A.ModelDesc), C.c_int64]
+    L.he_destroy.argtypes = [C.c_void_p]
+    L.he_set_sites.argtypes = [C.c_void_p, C.POINTER(A.SitesSoA), C.POINTER(A.InitialSoA)]
+    L.he_step_days.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
+    L.he_get_counters.argtypes = [C.c_void_p, C.POINTER(A.Counters)]
+    L.he_get_state.argtypes = [C.c_void_p, C.POINTER(A.StateSoA)]
+    L.he_set_state.argtypes = [C.c_void_p, C.POINTER(A.StateSoA)]
+    return L
+
+
+def variant(name, defs):
+    """The same harness compiled with extra -D switches (compile-time kernel options such as MC_COOP_MOIST=1)."""
+    if name not in _variants:
+        so = os.path.join(_HERE, f"libmc_hostemu_{name}.so")
+        _variants[name] = _bind(C.CDLL(build(so=so, defs=tuple(defs))))
+    return _variants[name]
 
 
 def lib():
@@ -43,41 +64,44 @@ def lib():
 
 
 class HostEmuEngine:
+    LIB = None          # subclasses bind a variant() library here
+
     def __init__(self, desc, n_sites):
         self.desc, self.S = desc, n_sites
-        self.h = lib().he_create(C.byref(desc), n_sites)
+        self._L = self.LIB if self.LIB is not None else lib()
+        self.h = self._L.he_create(C.byref(desc), n_sites)
         if not self.h:
             raise RuntimeError("he_create failed")
 
     def close(self):
         if self.h:
-            lib().he_destroy(self.h)
+            self._L.he_destroy(self.h)
             self.h = None
 
     __del__ = close
 
     def set_sites(self, sites):
         cs, ci = sites.c_sites(), sites.c_initial()
-        assert lib().he_set_sites(self.h, C.byref(cs), C.byref(ci)) == 0
+        assert self._L.he_set_sites(self.h, C.byref(cs), C.byref(ci)) == 0
 
     def step_days(self, day0, forcing, out):
         cf, co = forcing.c_struct(), out.c_struct()
-        rc = lib().he_step_days(self.h, day0, forcing.ndays, C.byref(cf), C.byref(co))
+        rc = self._L.he_step_days(self.h, day0, forcing.ndays, C.byref(cf), C.byref(co))
         if rc < 0:
             raise RuntimeError(f"he_step_days rc={rc}")
         return rc
 
     def counters(self):
         c = A.Counters()
-        lib().he_get_counters(self.h, C.byref(c))
+        self._L.he_get_counters(self.h, C.byref(c))
         return c.as_dict()
 
     def get_state(self):
         st = M.StateBatch(self.desc.n_soil, self.desc.n_snow, self.S)
         cs = st.c_struct()
-        lib().he_get_state(self.h, C.byref(cs))
+        self._L.he_get_state(self.h, C.byref(cs))
         return st
 
     def set_state(self, st):
         cs = st.c_struct()
-        assert lib().he_set_state(self.h, C.byref(cs)) == 0
+        assert self._L.he_set_state(self.h, C.byref(cs)) == 0

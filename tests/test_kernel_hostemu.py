@@ -61,6 +61,27 @@ def test_chunking_and_sharding_invariance(synth):
     assert np.array_equal(part.soil_moisture, whole.soil_moisture[:, :, 7:29])
 
 
+def test_cooperative_moisture_option_bit_identical(synth):
+    """MC_COOP_MOIST=1 (block-cooperative soil water balance; compiled out by default because it is slower on B200) must stay
+    bit-identical: it relies on a sub-step's initial state being the previous sub-step's final state."""
+    import hostemu_engine
+
+    class CoopMoistEngine(HostEmuEngine):
+        LIB = hostemu_engine.variant("coopmoist", ["-DMC_COOP_MOIST=1"])
+
+    p, _ = configs.config2_daily(3)
+    desc, sites, forcing = _buffers(p)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    out, ee = parity.run(CoopMoistEngine, desc, sites, forcing)
+    parity.assert_bit_identical(out, ref)
+    co, ce = eo.counters(), ee.counters()
+    assert all(co[k] == ce[k] for k in ("n_rhs", "n_accept", "n_reject", "n_newton_iter", "n_infil_steps"))
+    desc, sites, forcing = synth
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing)
+    out, _ = parity.run(CoopMoistEngine, desc, sites, forcing)
+    parity.assert_bit_identical(out, ref)
+
+
 def _variant(problem, **cfg):
     p = copy.deepcopy(problem)
     for k, v in cfg.items():
