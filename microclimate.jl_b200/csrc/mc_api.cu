@@ -244,8 +244,8 @@ static cudaError_t launch_chunk(const mcd::KArgs& a, cudaStream_t st)
 /* the block-cooperative kernel serves NoSnow models whose day-pass count is the same for every site (FixedIterations) */
 static bool coop_enabled(const mc_handle* h)
 {
-    static int legacy = -1;
-    if (legacy < 0) { const char* e = getenv("MC_KERNEL"); legacy = (e && std::strcmp(e, "legacy") == 0) ? 1 : 0; }
+    const char* e = getenv("MC_KERNEL");                           /* MC_KERNEL=legacy: per-site kernel for every model (A/B and test knob) */
+    const bool legacy = e && std::strcmp(e, "legacy") == 0;
     return !legacy && h->model.n_snow == 0 && h->dm.conv_kind == MC_CONV_FIXED;
 }
 
@@ -265,10 +265,12 @@ static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
         const int64_t per = (n + n_sm - 1) / n_sm;
         TB = (int)std::min<int64_t>(mcd::COOP_TB, std::max<int64_t>(128, (per + 31) / 32 * 32));
     }
+    if (const char* e = getenv("MC_COOP_BLOCK")) TB = std::min(mcd::COOP_TB, std::max(32, atoi(e) / 32 * 32));      /* test knob: force the block size */
     int grid = (int)((n + TB - 1) / TB);
     /* more blocks than 8 per SM run as a grid-stride loop over batches of TB sites: bounds the scratch (2.8 MB per block at N = 19) */
     const int cap = (per_sm > 0 ? per_sm : 8) * n_sm;
     if (grid > cap) grid = cap;
+    if (const char* e = getenv("MC_COOP_GRID")) grid = std::max(1, std::min(grid, atoi(e)));                          /* test knob: force the grid-stride loop */
     const size_t need = (size_t)grid * MC_COOP_ROWS(NA) * TB;
     if (h->coop_scr_doubles < need) {
         MC_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -182,6 +182,28 @@ def test_pipelined_site_slices_do_not_change_results(SoilEngine, synth, monkeypa
     assert np.array_equal(one.status[:509], three.status)
 
 
+def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
+    """The block-cooperative kernel must not depend on how sites fall into blocks: full-machine blocks of 1024 threads with a ragged last
+    block, a grid-stride loop over several batches per block, and the legacy per-site kernel all give the oracle's bits."""
+    desc, sites, forcing = synth
+    f = ("soil_temperature", "soil_moisture", "surface_water", "soil_water_potential")
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    monkeypatch.setenv("MC_COOP_BLOCK", "1024")                 # one ragged block: 512 sites + 512 mirror threads
+    a, ea = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(a, ref, f)
+    assert ea.counters()["n_rhs"] == eo.counters()["n_rhs"] and ea.counters()["n_newton_iter"] == eo.counters()["n_newton_iter"]
+    monkeypatch.setenv("MC_COOP_BLOCK", "96")                   # 6 batches ...
+    monkeypatch.setenv("MC_COOP_GRID", "2")                     # ... over 2 blocks: grid-stride reuse of the block scratch, ragged tail
+    b, eb = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
+    for name in f:
+        assert np.array_equal(getattr(b, name), getattr(ref, name)[..., :509]), name
+    monkeypatch.delenv("MC_COOP_BLOCK"); monkeypatch.delenv("MC_COOP_GRID")
+    monkeypatch.setenv("MC_KERNEL", "legacy")                   # the per-site kernel (what snow / tolerance-convergence models run)
+    c, ec = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(c, ref, f)
+    monkeypatch.delenv("MC_KERNEL")
+
+
 def test_solve_air_matches_oracle(SoilEngine):
     """solve_air! (the first "next" row of the scope table): MOST profiles from the final surface temperature, snow surface included."""
     import copy
