@@ -122,7 +122,7 @@ def main():
     S_total = S * max(world, args.gpus)
     cores = os.cpu_count() or 1
     config = {"workload": "synthetic site grid (BASELINE config 5): %d sites/GPU x 1 day per step, N=19 soil nodes, ConsecutiveDayMode, "
-                          "DynamicSoilMoisture(1e-6,500,360 s), HourlyRainfall, no snow, hourly T+theta profiles out" % S,
+                          "DynamicSoilMoisture(1e-6,500,360 s), HourlyRainfall, no snow, hourly T+theta profiles out; every GPU's shard is one full latitude sweep" % S,
               "sites_per_gpu": S, "total_sites": S_total, "days_per_step": 1, "n_soil": 19, "seed": syn.SEED,
               "l2": "inputs_larger_than_L2 (%.2f GB forcing + %.2f GB outputs per step)" % (S * 247 * 8 / 1e9, S * 38 * 24 * 8 / 1e9)}
 
@@ -130,14 +130,14 @@ def main():
         if rank != 0:
             return
         n = args.cpu_sites or max(64, min(S, 768 * cores))
-        times = cpu_run(desc, S_total, 0, n, 0, args.warmup + args.steps, threads=cores)
+        times = cpu_run(desc, n, 0, n, 0, args.warmup + args.steps, threads=cores)      # n sites spanning the whole latitude sweep: same mix as a GPU shard
         tt = times[args.warmup:]
         v = n * len(tt) / sum(tt)
         line = {"impl": "reference", "metric": "site-days/sec (hourly soil T+moisture)", "value": v, "unit": "site-days/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(tt) / len(tt), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "site-days/s", "cores": cores, "kind": "port",
-                                 "sample": "%d sites x 1 day per step (first sites of the grid), OpenMP over sites; Julia reference not installable here" % n},
+                                 "sample": "%d sites (one full latitude sweep of the synthetic grid) x 1 day per step, OpenMP over sites; Julia reference not installable here" % n},
                 "e2e": {"value": v, "unit": "site-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=real_stdout, flush=True)
         return
@@ -153,13 +153,13 @@ def main():
     ndays = args.warmup + args.steps
     s0 = rank * S
     t_gen = time.perf_counter()
-    sites = syn.make_sites(s0, s0 + S, S_total)
+    sites = syn.make_sites(s0, s0 + S, S)            # every rank's shard is one full latitude sweep of S sites (site ids rank*S ..): identical workload mix per GPU
     eng = SoilEngine(desc, S, device=local_rank)
     peak_tf = eng.measure_fp64_peak()
     eng.set_sites(sites)
     # forcing for all warm-up + timed days: pinned host copy (e2e leg) and device-resident copy (value leg)
     from microclimate_jl_b200 import _abi as A
-    host_days = [_pin_forcing(syn.make_forcing(s0, s0 + S, S_total, d, 1)) for d in range(ndays)]
+    host_days = [_pin_forcing(syn.make_forcing(s0, s0 + S, S, d, 1)) for d in range(ndays)]
     t_gen = time.perf_counter() - t_gen
     out_host = M.OutputBatch(1, desc.n_soil, S, ())
     for f in FIELDS:
@@ -248,9 +248,9 @@ def main():
             "gpu_launches": args.steps, "roofline": roof, "flagged_sites": status_bad, "wall_value_s": wall_value, "setup_s": t_gen, "checksum": checksum}
     if world == 1 and not args.no_cpu_baseline:
         n = args.cpu_sites or max(64, min(S, 768 * cores))
-        times = cpu_run(desc, S_total, 0, n, 0, 2, threads=cores)
+        times = cpu_run(desc, n, 0, n, 0, 2, threads=cores)
         line["cpu_baseline"] = {"value": n / times[1], "unit": "site-days/s", "cores": cores, "kind": "port",
-                                "sample": "%d sites x 1 day (day 1 after a 1-day warm-up), OpenMP over sites, %.1f s; C++ restatement of the reference (Julia not installable here)" % (n, times[1])}
+                                "sample": "%d sites (one full latitude sweep) x 1 day (day 1 after a 1-day warm-up), OpenMP over sites, %.1f s; C++ restatement of the reference (Julia not installable here)" % (n, times[1])}
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()

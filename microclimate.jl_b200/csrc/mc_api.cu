@@ -63,30 +63,20 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
 }
 
 /* Block-cooperative variant (NoSnow, fixed day-pass counts): a block owns blockDim.x sites; the conductivity of every RHS evaluation is
- * served by the whole block over (requesting site, node) items (mc_device.cuh, "Block-cooperative ODE phase").  Threads past the end of
+ * and every other node loop of the ODE hour are served by the whole block over (requesting site, node) items (mc_device.cuh,
+ * "Block-cooperative ODE phase").  Threads past the end of
  * the range mirror the last site (same values to the same addresses) so that every thread of a block reaches every barrier. */
 #ifndef MC_COOP_MIN_BLOCKS
 #define MC_COOP_MIN_BLOCKS 1
 #endif
-#ifndef MC_COOP_V
-#define MC_COOP_V 2            /* 1: integrator vectors thread-local, conductivity served by the block; 2: every ODE node loop is an item pass */
-#endif
-#if MC_COOP_V == 2
 #define MC_COOP_ROWS(NA) mcd::Coop2Rows<NA>::value
-#else
-#define MC_COOP_ROWS(NA) ((size_t)mcd::SCR_ARRAYS * (NA))
-#endif
 template <int NA>
 __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_coop_kernel(const mcd::KArgs a)
 {
-#if MC_COOP_V == 2
     __shared__ mcd::Coop2Shared sh;
     __shared__ mcd::MoistShared ms;
     if (threadIdx.x == 0) { sh.count[0] = 0; sh.count[1] = 0; ms.countU[0] = ms.countU[1] = ms.countF[0] = ms.countF[1] = ms.alive[0] = ms.alive[1] = 0; }
     __syncthreads();
-#else
-    __shared__ mcd::CoopShared sh;
-#endif
     mcd::Counters cn = {};
     double* scr = a.coop_scr + (size_t)blockIdx.x * (MC_COOP_ROWS(NA) * blockDim.x);
     for (int64_t base = a.s_begin + (int64_t)blockIdx.x * blockDim.x; base < a.s_end; base += (int64_t)gridDim.x * blockDim.x) {
@@ -94,11 +84,7 @@ __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_c
         const bool valid = s < a.s_end;
         if (!valid) s = a.s_end - 1;
         mcd::Counters c1 = {};
-#if MC_COOP_V == 2
         mcd::solve_site_coop2<NA>(a, s, c1, sh, ms, scr);
-#else
-        mcd::solve_site_coop<NA>(a, s, c1, sh, scr);
-#endif
         if (valid) {
             cn.n_rhs += c1.n_rhs; cn.n_accept += c1.n_accept; cn.n_reject += c1.n_reject; cn.n_obukhov += c1.n_obukhov;
             cn.n_newton += c1.n_newton; cn.n_infil += c1.n_infil; cn.n_day_passes += c1.n_day_passes;

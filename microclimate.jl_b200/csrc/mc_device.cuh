@@ -40,12 +40,8 @@
 #ifndef MC_TSIT5_ROLLED
 #define MC_TSIT5_ROLLED 1       /* rolled stage loops: 2.2 k -> 0.9 k instructions, +5 % at 32 warps/SM (instruction-fetch bound) */
 #endif
-#ifndef MC_COOP_UNROLL
-#define MC_COOP_UNROLL 1        /* unroll factor of the owner-phase node loops of the block-cooperative kernel */
-#endif
 #define MC_PRAGMA_STR(x) _Pragma(#x)
 #define MC_PRAGMA(x) MC_PRAGMA_STR(x)
-#define MC_CU MC_PRAGMA(unroll MC_COOP_UNROLL)
 #ifndef MC_THOMAS_UNROLL_N
 #define MC_THOMAS_UNROLL_N 3       /* owner-side Thomas sweeps: loads of the next rows issue under the divisions of the current one */
 #endif
@@ -67,7 +63,6 @@
 #define MC_LDG(p) (*(p))
 #define MC_ROLLED
 #define MC_UNROLL4
-#define MC_CU
 #define MC_THOMAS_UNROLL
 #define MC_CONST_MODEL g_model_h
 #define MC_TID 0
@@ -1001,289 +996,24 @@ MC_DEV_NOINLINE void tsit5_step(Integ<NA + NS>& I, const HourSoil<NA>& hs, const
 
 
 /* ==========================================================================================================================
- * Block-cooperative ODE phase (NoSnow).  Every thread still owns one site, but the dominant cost of the right-hand side — the
- * Campbell-de Vries conductivity of every node (3 Goff-Gratch evaluations + pow + de Vries weights, ~1.5 k instructions) — is
- * served by the WHOLE BLOCK over a flat list of (site, node) items of the sites that currently need an RHS evaluation:
- *
- *     owners:  run their adaptive Tsit5 state machine up to the next RHS request, publish the clamped stage vector      (pre)
- *     block :  ballot the requesting sites, then ALL threads evaluate soil_conductivity over  requesting sites x nodes   (service)
- *     owners:  finish the RHS (conduction, surface energy balance) and resume the state machine                          (post)
- *
- * Sites that have already reached the hour boundary (or whose step was accepted early) no longer idle their lanes: they serve
- * items of the sites still stepping, so the service phase runs at full lane occupancy with a ~1 k-instruction window shared by
- * every warp of the block (the per-site kernel ran it at ~20/32 lanes with every warp at a different PC).  The integrator is the
- * SAME arithmetic as tsit5_step / determine_initdt above, written as a resumable state machine (protothread style): each
- * MC_YIELD publishes an RHS request and returns; the next call resumes right after it.
+ * Block-cooperative ODE phase (NoSnow).  Every thread still OWNS one site, but the node loops of the ODE hour — above all the
+ * Campbell-de Vries conductivity of every node at every RHS evaluation (3 Goff-Gratch evaluations + pow + de Vries weights,
+ * ~1.5 k instructions) — are served by the WHOLE BLOCK over a flat list of (site, node) items of the sites that currently need an
+ * RHS evaluation.  Sites that have already reached the hour boundary no longer idle their lanes: they serve items of the sites
+ * still stepping, and every warp of the block shares one short instruction window.  The integrator is the SAME arithmetic as
+ * tsit5_step / determine_initdt above, written as a resumable state machine (protothread style): each yield publishes an RHS request
+ * and returns; the next call resumes right after it.
  * ========================================================================================================================== */
 #ifndef MC_COOP_TB
 #define MC_COOP_TB 1024     /* one block per SM: every warp of the SM is in the same phase (measured 128 / 256 / 512 / 1024 threads: 135 / 148 / 156 / 163 k site-days/s) */
 #endif
 constexpr int COOP_TB = MC_COOP_TB;
-enum { SCR_T = 0, SCR_LAM, SCR_TH, SCR_PM, SCR_PG, SCR_FW, SCR_LM, SCR_ARRAYS };
-
-struct CoopShared { int list[COOP_TB]; int warp_count[COOP_TB / 32 + 1]; int total; double P[COOP_TB], p0p[COOP_TB], pp0[COOP_TB]; };
-
-template <int NA>
-struct CoopInteg : Integ<NA> {
-    int st, guard; bool need_initdt;
-    const double* req_u; double req_t; double* req_out;      /* the pending RHS request */
-    double target, w0, w1, w2, st_t, st_dt;                    /* hour boundary; init-dt temporaries; t and dt of the step in flight */
-};
 
 struct RhsCtx { double P, T_air, wind, zen, solar, cloud, rh, szen, fd; };
 
-template <int NA>
-MC_DEV double* scr_at(double* scr, int arr, int node, int tid) { return scr + ((size_t)(arr * NA + node) * MC_TB + tid); }
-
-/* RHS, part 1 (owner): interpolate the forcing at t, publish pressure terms and the clamped temperatures of nodes 0..N-2 */
-template <int NA>
-MC_DEV void rhs_pre(const HourPar& hp, const double* u, double t, RhsCtx& R, CoopShared& sh, double* scr)
-{
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N; const int tid = MC_TID;
-    const double xk = t / 60.0;
-    int ik = (int)floor(xk);
-    ik = ik < 0 ? 0 : (ik > 23 ? 23 : ik);
-    const double dk = xk - (double)ik;
-    R.P = knot_lerp(hp.fP, hp.S, ik, dk);
-    R.T_air = knot_lerp(hp.fT, hp.S, ik, dk);
-    R.wind = jmax(knot_lerp(hp.fwind, hp.S, ik, dk), 0.1);
-    R.zen = jmin(90.0, nearbyint(knot_lerp(hp.fzen, hp.S, ik, dk) * 1000.0) / 1000.0);
-    R.solar = jmax(0.0, knot_lerp(hp.fsolar, hp.S, ik, dk));
-    R.cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
-    R.rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
-    R.szen = 0.0; R.fd = 0.0;
-    if (hp.slope > 0.0 && R.zen < 90.0) {
-        R.szen = jmin(90.0, knot_lerp(hp.fszen, hp.S, ik, dk));
-        R.fd = jclamp(knot_lerp(hp.fdiff, hp.S, ik, dk), 0.0, 1.0);
-    }
-    sh.P[tid] = R.P; sh.p0p[tid] = m.P0 / R.P; sh.pp0[tid] = R.P / m.P0;
-    MC_CU for (int i = 0; i < N - 1; i++) *scr_at<NA>(scr, SCR_T, i, tid) = jclamp(u[i], T_LO, m.T_hi);
-}
-
-/* RHS, part 2 (whole block): conductivity of every (requesting site, node) item */
-template <int NA>
-MC_DEV void rhs_service(int A, const CoopShared& sh, double* scr)
-{
-    const DevModel& m = MC_CONST_MODEL; const int NI = m.N - 1; const int tid = MC_TID, TB = MC_TB;
-    const int total = A * NI;
-    MC_ROLLED for (int j = tid; j < total; j += TB) {
-        const int node = j / A;
-        const int o = sh.list[j - node * A];
-        const double lam = soil_conductivity(*scr_at<NA>(scr, SCR_T, node, o), sh.P[o], sh.p0p[o], sh.pp0[o],
-                                             *scr_at<NA>(scr, SCR_TH, node, o), *scr_at<NA>(scr, SCR_PM, node, o), *scr_at<NA>(scr, SCR_PG, node, o),
-                                             *scr_at<NA>(scr, SCR_FW, node, o), *scr_at<NA>(scr, SCR_LM, node, o));
-        *scr_at<NA>(scr, SCR_LAM, node, o) = lam;
-    }
-}
-
-/* RHS, part 3 (owner): conduction + surface energy balance, exactly soil_rhs's arithmetic (heat_transport_1d.jl:137-302) */
-template <int NA>
-MC_DEV_NOINLINE void rhs_post(const HourSoil<NA>& hs, const HourPar& hp, const RhsCtx& R, const double* __restrict__ u, double* __restrict__ du,
-                              double* scr, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N; const int tid = MC_TID;
-    cn.n_rhs++;
-    const double P = R.P, T_air = R.T_air, wind = R.wind, zen = R.zen, solar = R.solar, cloud = R.cloud, rh = R.rh;
-    const double Ts_node = jclamp(u[0], T_LO, m.T_hi);
-    double T_up = Ts_node;
-    double G_up = *scr_at<NA>(scr, SCR_LAM, 0, tid) / m.dzg[0];
-    double T_i = jclamp(u[1], T_LO, m.T_hi);
-    const double Q_cond = G_up * (T_i - Ts_node);
-    MC_CU for (int i = 1; i < N - 1; i++) {
-        const double T_dn = jclamp(u[i + 1], T_LO, m.T_hi);
-        const double G_i = *scr_at<NA>(scr, SCR_LAM, i, tid) / m.dzg[i];
-        du[i] = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / hs.cap[i];
-        T_up = T_i; T_i = T_dn; G_up = G_i;
-    }
-    du[N - 1] = 0.0;
-    double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
-    if (hp.slope > 0.0 && zen < 90.0) {
-        const double cz = mcm::cos(zen * PI_D / 180.0), csz = mcm::cos(R.szen * PI_D / 180.0);
-        Q_solar = jmax(0.0, (((1.0 - R.fd) * Q_solar) / cz) * csz) + (R.fd * Q_solar) * hp.svf;
-    }
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double atm = atmospheric_radiation(wa.vapour_pressure, T_air);
-    const double cloud_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air - 2.0);
-    const double hill_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air);
-    const double lw_sky = (atm * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - hp.shade);
-    const double incoming = (lw_sky + hp.shade * hill_rad) * hp.svf + hill_rad * (1.0 - hp.svf);
-    const double Q_ir = incoming - ((1.0 - hp.shade) * m.sigma * hp.eps_surf) * mcm::pow4(Ts_node) - hp.shade * hill_rad;
-    double Ts = Ts_node;
-    if (fabs(Ts - T0C) > 100.0) Ts = T_air + 1.0;
-    if (Ts == T_air) Ts = Ts + 0.1;
-    const double dT = T_air - Ts;
-    const double rho_cp = calc_rho_cp((Ts + T_air) / 2.0);
-    double Qc;
-    if (T_air >= Ts || zen >= 90.0) {
-        const double ustar = jmax(m.kappa * wind / hp.lz, 1.0e-6);
-        Qc = convective_flux(rho_cp, dT, ustar, 0.64 / hp.lz, sublayer_stanton(hp.z0, ustar));
-    } else {
-        const Obukhov o = calc_obukhov(wind, hp.z0, m.zref, hp.lz, dT, rho_cp, hp.L_prev >= 0.0 ? -0.3 : hp.L_prev);
-        cn.n_obukhov += o.iters;
-        Qc = o.Q;
-    }
-    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = Ts < T_LO ? T_LO : Ts;
-    const double Qe = (hp.soil_wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
-    du[0] = 60.0 * (Q_solar + Q_ir + Q_cond + Qc + 0.0 - Qe) / hs.cap[0];
-}
-
-#define MC_YIELD(label, uvec, tt, outk) do { I.st = (label); I.req_u = (uvec); I.req_t = (tt); I.req_out = (outk); return true; case (label):; } while (0)
-
-/* Resumable adaptive integration to I.target: returns true with an RHS request published in (req_u, req_t, req_out), false when the
- * hour boundary is reached.  Same operations as determine_initdt / tsit5_step / the step_to_hour! clamp loop. */
-template <int NA>
-MC_DEV_NOINLINE bool coop_advance(CoopInteg<NA>& I, Counters& cn)
-{
-    using namespace tsit5;
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N;
-    switch (I.st) {
-    case 0:
-        if (I.need_initdt) {                                             /* Hairer-Wanner initial step: two RHS evaluations */
-            I.need_initdt = false;
-            { double s0 = 0.0;
-              MC_CU for (int i = 0; i < N; i++) { I.tmp[i] = m.abstol + fabs(I.u[i]) * m.reltol; const double q = I.u[i] / I.tmp[i]; s0 += q * q; }
-              I.w0 = sqrt(s0 / N); }
-            MC_YIELD(1, I.u, I.t, I.k2);
-            { bool finite = true;
-              MC_CU for (int i = 0; i < N; i++) if (!isfinite(I.k2[i])) finite = false;
-              if (!finite) { I.dt = 1e-12; goto initdt_done; } }
-            I.w1 = rms_scaled(I.k2, I.tmp, N);
-            I.w2 = (I.w0 < 1e-5 || I.w1 < 1e-5) ? 1e-6 : (I.w0 / I.w1) / 100.0;
-            I.w2 = fmin(I.w2, 1440.0);
-            MC_CU for (int i = 0; i < N; i++) I.k4[i] = I.u[i] + I.w2 * I.k2[i];
-            MC_YIELD(2, I.k4, I.t + I.w2, I.k3);
-            { double s2 = 0.0;
-              MC_CU for (int i = 0; i < N; i++) { const double q = (I.k3[i] - I.k2[i]) / I.tmp[i]; s2 += q * q; }
-              const double d2 = sqrt(s2 / N) / I.w2;
-              const double md = fmax(I.w1, d2);
-              double dt1;
-              if (md <= 1e-15) dt1 = fmax(1e-6, I.w2 * 1e-3);
-              else dt1 = mcm::exp10(-(2.0 + mcm::log10(md)) / 5.0);
-              I.dt = fmin(fmin(100.0 * I.w2, dt1), 1440.0); }
-        initdt_done:;
-        }
-        while (I.t < I.target - 1e-10) {                                 /* step_to_hour! */
-            I.guard = 0;
-            for (;;) {                                                   /* one accepted step */
-                if (I.iter > 0) {
-                    if (!I.accept) {
-                        I.dt = I.dt / fmin(5.0, I.q11 / 0.9);
-                    } else {
-                        MC_CU for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
-                        I.dt = I.dtpropose;
-                        if (I.u_modified) { MC_YIELD(3, I.u, I.t, I.k1); }
-                        else { MC_CU for (int i = 0; i < N; i++) I.k1[i] = I.k7[i]; }
-                    }
-                } else if (I.u_modified) {
-                    MC_CU for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
-                }
-                I.iter++;
-                I.dt = fmin(1440.0, I.dt);
-                I.dt = fmin(I.dt, I.tstop - I.t);
-                if (!(I.dt > 1e-12) || ++I.guard > 100000) {
-                    I.flags |= (I.dt != I.dt) ? MC_STATUS_NAN : (I.guard > 100000 ? MC_STATUS_STEP_LIMIT : MC_STATUS_DT_UNDERFLOW);
-                    I.t = I.tstop; I.accept = true; I.dtpropose = 1.0;
-                    MC_CU for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
-                    break;
-                }
-                I.st_t = I.t; I.st_dt = I.dt;
-                MC_CU for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + I.st_dt * a21 * I.k1[i];
-                MC_YIELD(4, I.tmp, I.st_t + c1 * I.st_dt, I.k2);
-                MC_CU for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + I.st_dt * (a31 * I.k1[i] + a32 * I.k2[i]);
-                MC_YIELD(5, I.tmp, I.st_t + c2 * I.st_dt, I.k3);
-                MC_CU for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + I.st_dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
-                MC_YIELD(6, I.tmp, I.st_t + c3 * I.st_dt, I.k4);
-                MC_CU for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + I.st_dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
-                MC_YIELD(7, I.tmp, I.st_t + c4 * I.st_dt, I.k5);
-                MC_CU for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + I.st_dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
-                MC_YIELD(8, I.tmp, I.st_t + I.st_dt, I.k6);
-                MC_CU for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + I.st_dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
-                MC_YIELD(9, I.u, I.st_t + I.st_dt, I.k7);
-                {
-                    double ss = 0.0;
-                    MC_CU for (int i = 0; i < N; i++) {
-                        const double ut = I.st_dt * (bt1 * I.k1[i] + bt2 * I.k2[i] + bt3 * I.k3[i] + bt4 * I.k4[i] + bt5 * I.k5[i] + bt6 * I.k6[i] + bt7 * I.k7[i]);
-                        const double q = ut / (m.abstol + fmax(fabs(I.uprev[i]), fabs(I.u[i])) * m.reltol);
-                        ss += q * q;
-                    }
-                    const double EEst = sqrt(ss / N);
-                    I.u_modified = false;
-                    double q;
-                    if (EEst == 0.0) q = 0.1;
-                    else {
-                        I.q11 = fastpow(EEst, 7.0 / 50.0);
-                        q = I.q11 / fastpow(I.qold, 2.0 / 25.0);
-                        q = fmax(0.1, fmin(5.0, q / 0.9));
-                    }
-                    I.accept = EEst <= 1.0;
-                    if (EEst != EEst) { I.flags |= MC_STATUS_NAN; I.accept = true; q = 1.0; }
-                    if (I.accept) {
-                        cn.n_accept++;
-                        I.qold = fmax(EEst, 1e-4);
-                        const double dtnew = I.dt / q;
-                        double ttmp = I.t + I.dt;
-                        if (fabs(ttmp - I.tstop) < 100.0 * 2.220446049250313e-16 * fmax(I.t, I.tstop)) ttmp = I.tstop;
-                        I.t = ttmp;
-                        I.dtpropose = fmin(1440.0, dtnew);
-                        break;
-                    }
-                    cn.n_reject++;
-                    MC_CU for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
-                }
-            }
-            {   /* re-clamp the state after every internal step (simulation.jl:891-900) */
-                bool changed = false;
-                MC_CU for (int k = 0; k < N; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
-                if (changed) { MC_CU for (int k = 0; k < N; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
-            }
-        }
-        I.st = 0;
-        return false;
-    case 10:                                                             /* one-shot RHS (prototype evaluation of init()) */
-        I.st = 0;
-        return false;
-    }
-    return false;
-}
-
-/* Drive every site of the block to its next hour boundary (or through a one-shot RHS): rounds of pre / ballot / service / post. */
-template <int NA>
-MC_DEV void coop_rounds(CoopInteg<NA>& I, bool pending, const HourSoil<NA>& hs, const HourPar& hp, CoopShared& sh, double* scr, Counters& cn)
-{
-    RhsCtx R;
-    const int tid = MC_TID;
-    for (;;) {
-        if (pending) rhs_pre<NA>(hp, I.req_u, I.req_t, R, sh, scr);
-#if defined(__CUDACC__)
-        const unsigned bal = __ballot_sync(0xffffffffu, pending);
-        const int lane = tid & 31, w = tid >> 5, nw = (MC_TB + 31) >> 5;
-        if (lane == 0) sh.warp_count[w] = __popc(bal);
-        __syncthreads();
-        int off = 0, A = 0;
-        for (int k = 0; k < nw; k++) { const int c = sh.warp_count[k]; if (k < w) off += c; A += c; }
-        if (A == 0) break;
-        if (pending) sh.list[off + __popc(bal & ((1u << lane) - 1u))] = tid;
-        __syncthreads();
-#else
-        const int A = pending ? 1 : 0;
-        if (A == 0) break;
-        sh.list[0] = tid;
-#endif
-        rhs_service<NA>(A, sh, scr);
-        MC_BLOCK_SYNC();
-        if (pending) {
-            rhs_post<NA>(hs, hp, R, I.req_u, I.req_out, scr, cn);
-            pending = coop_advance<NA>(I, cn);
-        }
-    }
-}
-
-
 /* ==========================================================================================================================
- * Block-cooperative ODE phase, second form: the integrator's vectors (k1..k7, u, uprev) live in the block's scratch instead of
- * thread-local memory and EVERY node loop of the ODE hour is an item pass over (requesting site, node):
+ * The integrator's vectors (k1..k7, u, uprev) live in the block's scratch instead of thread-local memory and EVERY node loop of
+ * the ODE hour is an item pass over (requesting site, node):
  *
  *     owners : resume the Tsit5 state machine -> publish (stage, dt, pressure terms)                                   | barrier
  *     pass 1 : stage vector x = uprev + dt * sum(a_sj k_j)  ->  clamped T  ->  Campbell-de Vries conductivity          | barrier
@@ -2713,185 +2443,9 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
 
 
 /* ------------------------------------------------------------------------------------------
- * solve_soil! for one site, block-cooperative ODE phase (NoSnow, fixed day-pass counts so that every site of the block makes the
- * same sequence of coop_rounds calls).  Everything outside the ODE hour is solve_site<NA,0> verbatim.
+ * solve_soil! for one site with the block-cooperative ODE phase (NoSnow, fixed day-pass counts so that every site of the block makes
+ * the same sequence of coop2_rounds calls).  Everything outside the ODE hour is solve_site<NA,0> verbatim.
  * ------------------------------------------------------------------------------------------ */
-template <int NA>
-MC_DEV void solve_site_coop(const KArgs& a, int64_t s, Counters& cn, CoopShared& sh, double* scr)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int N = m.N;
-    const int nrows = a.ndays * 24;
-    const bool dynamic = m.dynamic != 0, nonconsec = m.nonconsec != 0;
-    SiteRef r; r.a = &a; r.s = s;
-    const int64_t S = a.S;
-    const int tid = MC_TID;
-
-    HourSoil<NA> hs; HourPar hp; CoopInteg<NA> I;
-    double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
-    double psi_out[NA], h_out[NA];
-    MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; hs.lam_m[i] = r.node(a.lam_m, i); }
-    double pool = a.pool[s], wet_dyn = a.wetness[s], L_ode = a.L_ode[s], L_prof = a.L_prof[s], tdeep_stale = a.tdeep_prev[s];
-    int flags = a.flags[s];
-    const double site_albedo = MC_LDG(a.albedo + s);
-    hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
-    hp.sn = nullptr;
-    I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
-    I.st = 0; I.guard = 0; I.need_initdt = false;
-    MC_ROLLED for (int i = 0; i < N; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
-
-    auto set_day_forcing = [&](int jl) {
-        const int64_t off = (int64_t)jl * 24 * S + s;
-        hp.fP = a.f_P + off; hp.fT = a.f_T + off; hp.fwind = a.f_wind + off; hp.frh = a.f_rh + off; hp.fcloud = a.f_cloud + off;
-        hp.fsolar = a.f_solar + off; hp.fdiff = a.f_diffuse + off; hp.fzen = a.f_zen + off; hp.fszen = a.f_szen + off;
-    };
-    auto tins_mean = [&](int jl) { double ssum = 0.0; MC_ROLLED for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
-    double sky_T = 0.0;
-    auto set_hour_params = [&](const EnvInstant& e) {
-        hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud;
-        hp.albedo = e.albedo; hp.soil_wetness = dynamic ? wet_dyn : e.wet_daily;
-        sky_T = sky_temperature(hp.svf, e.P, e.rh, e.T_ref, e.eps_cloud, e.cloud, e.shade, a.has_lw != 0, e.lw);
-    };
-    /* theta-only terms of the hour: heat capacities stay with the owner, the conductivity inputs go to the block's scratch */
-    auto hoist_publish = [&]() {
-        hoist_soil<NA, 0>(r, theta, hs);
-        MC_ROLLED for (int i = 0; i < N - 1; i++) {
-            *scr_at<NA>(scr, SCR_TH, i, tid) = hs.theta[i]; *scr_at<NA>(scr, SCR_PM, i, tid) = hs.phim[i]; *scr_at<NA>(scr, SCR_PG, i, tid) = hs.phig[i];
-            *scr_at<NA>(scr, SCR_FW, i, tid) = hs.fw[i]; *scr_at<NA>(scr, SCR_LM, i, tid) = hs.lam_m[i];
-        }
-    };
-
-    EnvInstant env;
-    if (a.day0 == 0) {
-        /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:196-238,853-860) */
-        set_day_forcing(0);
-        env = get_instant(r, 0, 0, site_albedo);
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[i] = a.has_init_T ? T0[i] : 280.0;
-        hoist_publish();
-        hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
-        {
-            Counters scratch = {};
-            I.st = 10; I.req_u = I.tmp; I.req_t = 0.0; I.req_out = I.k1;
-            coop_rounds<NA>(I, true, hs, hp, sh, scr, scratch);
-        }
-        /* solve_soil! pre-loop (simulation.jl:395-452) */
-        if (!a.has_init_T) { const double t_init = tins_mean(0); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_init; }
-        MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-        write_props(r, 0, T0, theta, 101325.0);
-        put_potential_row(r, 0, theta);
-        MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
-        init_humidity(r, theta, T0);
-        tdeep_stale = env.T_deep;
-        pool = 0.0;
-    }
-
-    for (int jl = 0; jl < a.ndays; jl++) {
-        const int64_t j = a.day0 + jl;
-        set_day_forcing(jl);
-        const int niter = nonconsec ? m.iters_per_day : ((m.spinup && j == 0) ? m.conv_iters : 1);
-        int noon_i = 0; double best = r.hourly(a.f_zen, jl * 24);
-        MC_ROLLED for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
-        const int midnight_i = (noon_i + 12) % 24;
-        if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516) */
-            MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-            if (!dynamic && a.has_presc) { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
-            else { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i); }
-            const double t_reset = tins_mean(jl);
-            if (!a.has_init_T) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_reset; }
-            else { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i); }
-        }
-        T0[N - 1] = tdeep_stale;
-        MC_ROLLED for (int i = 0; i < N; i++) { T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
-        for (int iter = 1; iter <= niter; iter++) {                           /* fixed day-pass count (block-uniform) */
-            cn.n_day_passes++;
-            const bool is_last = iter >= niter;
-            if (!nonconsec) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = T0_day_start[i]; }
-            MC_ROLLED for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
-            const int day_row = jl * 24;
-            if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
-                MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
-                r.put_scalar(a.o_pool, day_row, pool);
-                put_potential_row(r, day_row, theta);
-                init_humidity(r, theta, T0);
-                const EnvInstant e0 = get_instant(r, jl, day_row, site_albedo);
-                r.put_scalar(a.o_sky, day_row, sky_temperature(hp.svf, e0.P, e0.rh, e0.T_ref, e0.eps_cloud, e0.cloud, e0.shade, a.has_lw != 0, e0.lw));
-                write_props(r, day_row, T0, theta, e0.P);
-            }
-            env = get_instant(r, jl, day_row, site_albedo);
-            T0[N - 1] = env.T_deep;
-            set_hour_params(env);
-            /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
-            MC_ROLLED for (int i = 0; i < N; i++) { I.u[i] = T0[i]; I.uprev[i] = T0[i]; }
-            I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
-            I.need_initdt = true;                                             /* the two init-dt RHS calls join hour 0's rounds */
-            for (int i = 0; i < 24; i++) {
-                const int step = jl * 24 + i;
-                MC_ROLLED for (int k = 0; k < N; k++) T0_before[k] = T0[k];
-                hoist_publish();
-                hp.L_prev = L_ode;
-                /* step_to_hour! (simulation.jl:888-903), cooperatively */
-                I.target = (i + 1) * 60.0; I.tstop = I.target; I.st = 0;
-                {
-                    const bool pend = coop_advance<NA>(I, cn);
-                    coop_rounds<NA>(I, pend, hs, hp, sh, scr, cn);
-                }
-                MC_ROLLED for (int k = 0; k < N; k++) T0[k] = I.u[k];
-                if (is_last) {
-                    phase_transition(N, m.depths, T0, T0_before, sum_phase, theta);
-                    MC_ROLLED for (int k = 0; k < N; k++) T0_output[k] = T0[k];
-                }
-                if (i < 23) {
-                    env = get_instant(r, jl, step + 1, site_albedo);
-                    T0[N - 1] = env.T_deep;
-                    set_hour_params(env);
-                }
-                MC_ROLLED for (int k = 0; k < N; k++) I.u[k] = T0[k];
-                I.u_modified = true;
-                {   /* init_surface_fluxes! (monin_obukhov.jl:247-264): hourly warm start of the Obukhov length */
-                    const double T_air = MC_LDG(hp.fT + (int64_t)i * S);
-                    const double wind = jmax(MC_LDG(hp.fwind + (int64_t)i * S), 0.1);
-                    const double zen = jmin(90.0, nearbyint(MC_LDG(hp.fzen + (int64_t)i * S) * 1000.0) / 1000.0);
-                    const double Tsf = T0[0];
-                    if (T_air < Tsf && zen < 90.0) {
-                        const Obukhov ob = calc_obukhov(wind, hp.z0, m.zref, hp.lz, T_air - Tsf, calc_rho_cp((Tsf + T_air) / 2.0), L_ode >= 0.0 ? -0.3 : L_ode);
-                        cn.n_obukhov += ob.iters;
-                        L_ode = ob.L;
-                    }
-                }
-                bool have_infil = false;
-                if (is_last) {
-                    double rain;
-                    if (m.rain_hourly) rain = r.hourly(a.f_rain, step);
-                    else rain = (i == midnight_i) ? env.rain_daily : 0.0;
-                    pool = jclamp(pool + rain, 0.0, m.max_pool);
-                    if (dynamic) {
-                        wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn, false);
-                        have_infil = true;
-                    }
-                }
-                const int out_row = step + 1;
-                if (is_last && out_row < nrows && !(i == 23 && nonconsec)) {
-                    r.put_scalar(a.o_pool, out_row, pool);
-                    MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
-                    r.put_scalar(a.o_sky, out_row, sky_T);
-                    if (have_infil) { MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); } }
-                    write_props(r, out_row, T0, theta, r.hourly(a.f_P, out_row));
-                }
-            }
-        }
-        tdeep_stale = env.T_deep;
-    }
-    MC_ROLLED for (int i = 0; i < N; i++) {
-        a.T[(int64_t)i * S + s] = T0[i]; a.theta[(int64_t)i * S + s] = theta[i]; a.sum_phase[(int64_t)i * S + s] = sum_phase[i];
-        if (!(isfinite(T0[i]) && isfinite(theta[i]))) flags |= MC_STATUS_NAN;
-    }
-    MC_ROLLED for (int i = 0; i < N; i++) a.fsal[(int64_t)i * S + s] = I.k1[i];
-    a.pool[s] = pool; a.wetness[s] = wet_dyn; a.L_ode[s] = L_ode; a.L_prof[s] = L_prof; a.tdeep_prev[s] = tdeep_stale;
-    a.flags[s] = flags | I.flags;
-}
-
-
-/* solve_soil! for one site with the block-cooperative ODE phase in its second form (integrator vectors in the block's scratch) */
 template <int NA>
 MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Shared& sh, MoistShared& ms, double* scr)
 {

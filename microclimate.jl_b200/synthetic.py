@@ -79,7 +79,9 @@ def synthetic_time_mode():
 
 def _site_scalars(s0: int, s1: int, S_total: int):
     s = np.arange(s0, s1, dtype=np.int64)
-    lat = -60.0 + 130.0 * (s + u01(ST_LAT, s)) / S_total              # monotone in s: warps are latitude-coherent
+    # monotone in s within one sweep of S_total sites (warps are latitude-coherent); site ids beyond S_total start another sweep with fresh
+    # random streams, so N shards of S_total sites each are statistically identical workloads (bench.py's weak scaling)
+    lat = -60.0 + 130.0 * ((s % S_total) + u01(ST_LAT, s)) / S_total
     t_mean = 27.0 - 0.55 * np.abs(lat) + 3.0 * ndtri(u01(ST_TMEAN, s))  # degC
     a_ann = 2.0 + 0.25 * np.abs(lat)
     a_diu = 4.0 + 10.0 * u01(ST_ADIU, s)

@@ -87,6 +87,24 @@ def config2_daily(ndays=30):
     return problem, g
 
 
+def regrid(problem, depths):
+    """The same problem on another depth grid (per-node soil parameters / initial state taken from the nearest old node)."""
+    import copy
+    p = copy.deepcopy(problem)
+    old, new = np.asarray(p.model.depths, float), np.asarray(depths, float)
+    idx = np.abs(old[None, :] - new[:, None]).argmin(axis=1)
+    take = lambda a: None if a is None else np.asarray(a)[idx].copy()
+    p.model.depths = new
+    sp, hy = p.inputs.soil_profile, p.inputs.soil_profile.hydraulics
+    for o, names in ((sp, ("bulk_density", "mineral_density", "mineral_conductivity", "mineral_heat_capacity")),
+                     (hy, ("air_entry_water_potential", "saturated_hydraulic_conductivity", "campbell_b_parameter", "root_density"))):
+        for nme in names:
+            object.__setattr__(o, nme, take(getattr(o, nme)))
+    p.inputs.initial_soil_temperature = take(p.inputs.initial_soil_temperature)
+    p.inputs.initial_soil_moisture = take(p.inputs.initial_soil_moisture)
+    return p
+
+
 def run_engine(engine_cls, problem, inputs_list=None, fields=None, **kw):
     """Run a whole problem in one chunk on `engine_cls` (SoilEngine or OracleEngine). Returns OutputBatch."""
     from microclimate_jl_b200 import marshal as M

@@ -91,14 +91,12 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     /* same kernel selection as launch_range(): the block-cooperative path (here a "block" of one thread) for NoSnow + FixedIterations */
     const char* kenv = getenv("MC_KERNEL");
     const bool coop = !(kenv && std::strcmp(kenv, "legacy") == 0) && e->model.n_snow == 0 && mcd::g_model_h.conv_kind == MC_CONV_FIXED;
-    const bool coop1 = kenv && std::strcmp(kenv, "coop1") == 0;        /* first form of the cooperative path (thread-local integrator vectors) */
     std::vector<double> scr(mcd::Coop2Rows<MC_MAX_SOIL_NODES>::value);
     static mcd::MoistShared ms; std::memset(&ms, 0, sizeof(ms));
-    static mcd::CoopShared sh; static mcd::Coop2Shared sh2; sh2.count[0] = sh2.count[1] = 0;
+    static mcd::Coop2Shared sh2; sh2.count[0] = sh2.count[1] = 0;
     for (int64_t s = 0; s < e->S; s++) {
         mcd::Counters cn = {};
-        if (coop && !coop1) { if (e->N <= 10) mcd::solve_site_coop2<10>(a, s, cn, sh2, ms, scr.data()); else if (e->N <= 19) mcd::solve_site_coop2<19>(a, s, cn, sh2, ms, scr.data()); else mcd::solve_site_coop2<MC_MAX_SOIL_NODES>(a, s, cn, sh2, ms, scr.data()); }
-        else if (coop) { if (e->N <= 10) mcd::solve_site_coop<10>(a, s, cn, sh, scr.data()); else if (e->N <= 19) mcd::solve_site_coop<19>(a, s, cn, sh, scr.data()); else mcd::solve_site_coop<MC_MAX_SOIL_NODES>(a, s, cn, sh, scr.data()); }
+        if (coop) { if (e->N <= 10) mcd::solve_site_coop2<10>(a, s, cn, sh2, ms, scr.data()); else if (e->N <= 19) mcd::solve_site_coop2<19>(a, s, cn, sh2, ms, scr.data()); else mcd::solve_site_coop2<MC_MAX_SOIL_NODES>(a, s, cn, sh2, ms, scr.data()); }
         else if (e->model.n_snow == 0) { if (e->N <= 10) mcd::solve_site<10, 0>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, 0>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, 0>(a, s, cn); }
         else { if (e->N <= 10) mcd::solve_site<10, MC_SNOW_NODES>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, MC_SNOW_NODES>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, s, cn); }
         if (want_air) mcd::solve_air_site(a, s, cn);

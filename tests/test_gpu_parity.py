@@ -182,6 +182,18 @@ def test_pipelined_site_slices_do_not_change_results(SoilEngine, synth, monkeypa
     assert np.array_equal(one.status[:509], three.status)
 
 
+@pytest.mark.parametrize("n_nodes", [7, 24], ids=["N7", "N24"])
+def test_other_node_counts_match_oracle(SoilEngine, n_nodes):
+    """Node counts below / between the kernels' compile-time array bounds (NA = 10 / 19 / 24)."""
+    p, _ = configs.config2_daily(3)
+    depths = np.concatenate([[0.0], np.geomspace(0.01, 2.0, n_nodes - 1)])
+    desc, sites, forcing = _problem_buffers(configs.regrid(p, depths))
+    ref, _ = parity.run(OracleEngine, desc, sites, forcing)
+    out, _ = parity.run(SoilEngine, desc, sites, forcing)
+    parity.assert_within_north_star(out, ref)
+    parity.assert_bit_identical(out, ref)
+
+
 def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     """The block-cooperative kernel must not depend on how sites fall into blocks: full-machine blocks of 1024 threads with a ragged last
     block, a grid-stride loop over several batches per block, and the legacy per-site kernel all give the oracle's bits."""

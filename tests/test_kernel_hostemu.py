@@ -82,6 +82,19 @@ def test_cooperative_moisture_option_bit_identical(synth):
     parity.assert_bit_identical(out, ref)
 
 
+@pytest.mark.parametrize("n_nodes", [7, 22, 24], ids=["N7", "N22", "N24"])
+def test_other_node_counts_bit_identical(n_nodes):
+    """Node counts that are not an array bound of the kernel templates (NA = 10 / 19 / 24): ragged rows of the block scratch."""
+    p, _ = configs.config2_daily(3)
+    depths = np.concatenate([[0.0], np.geomspace(0.01, 2.0, n_nodes - 1)])
+    desc, sites, forcing = _buffers(configs.regrid(p, depths))
+    assert desc.n_soil == n_nodes
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    out, ee = parity.run(HostEmuEngine, desc, sites, forcing)
+    parity.assert_bit_identical(out, ref)
+    assert eo.counters()["n_rhs"] == ee.counters()["n_rhs"]
+
+
 def _variant(problem, **cfg):
     p = copy.deepcopy(problem)
     for k, v in cfg.items():
