@@ -1401,6 +1401,40 @@ MC_DEV_NOINLINE void phase_transition(int N, const double* depths, double* T, co
  * Campbell (1985) water balance.  Arrays use the reference's 1-based buffer indices
  * (buffer node i <-> soil node i-1; entry 0 unused), campbell.jl:129-361.
  * ------------------------------------------------------------------------------------------ */
+/* Stomatal Newton for the leaf water potential (campbell.jl:270-284): iterate until |residual| <= 10 J/kg or moisture_max_iterations.
+ * The update is a function of psi_leaf alone (everything else is constant within the sub-step), so as soon as a value repeats, the
+ * remaining iterations are periodic and the value after the last one follows from the period.  On the benchmark grid 10 % of the
+ * sub-steps never meet the exit test and the reference runs all 500 iterations; 99.97 % of those orbits have period 1 or 2 (compared
+ * directly) or a longer period found by Brent's cycle detection within a few iterations.  The skipped iterations are exactly the ones
+ * that would reproduce already-visited values, so the result is bit-identical to running them (the oracle does run them). */
+MC_DEV_NOINLINE double stomatal_newton(double psi_leaf, double psi_bar, double R_bar, double TP)
+{
+    const DevModel& m = MC_CONST_MODEL;
+    const double RL = m.RL, PC = m.PC, SP = m.SP;
+    const double qnan = (double)NAN;                                       /* never equal to anything */
+    double prev1 = qnan, prev2 = qnan, tort = qnan;
+    int counter = 0, lam = 0, power = 1;
+    bool detect = true;
+    while (counter < m.moist_max_it) {
+        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
+        const double xp = mcm::pow(psi_leaf / PC, SP);
+        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
+        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
+        psi_leaf = psi_leaf - resid / slope;
+        counter++;
+        if (fabs(resid) <= 10.0) break;
+        if (detect) {
+            int period = 0;
+            if (psi_leaf == prev1) period = 1;
+            else if (psi_leaf == prev2) period = 2;
+            else if (psi_leaf == tort) period = lam + 1;
+            if (period) { counter = m.moist_max_it - (m.moist_max_it - counter) % period; detect = false; }     /* skip whole periods */
+            else { prev2 = prev1; prev1 = psi_leaf; if (++lam == power) { tort = psi_leaf; power <<= 1; lam = 0; } }
+        }
+    }
+    return psi_leaf;
+}
+
 template <int NA>
 struct HourMoist {              /* per-hour constants of infiltration_step! (soil T and site parameters are fixed within the hour) */
     double psi_e[NA + 2], sat[NA + 2], bb[NA + 2], ks[NA + 2], nexp[NA + 2], mass[NA + 2], rootR[NA + 2], rootZ[NA + 2];
@@ -1455,16 +1489,8 @@ MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA
     }
     const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
     const double RL = m.RL, PC = m.PC, SP = m.SP;
+    psi_leaf = stomatal_newton(psi_leaf, psi_bar, R_bar, TP);                /* campbell.jl:270-284 */
     int counter = 0;
-    while (counter < m.moist_max_it) {                                       /* stomatal Newton, campbell.jl:270-284 */
-        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
-        const double xp = mcm::pow(psi_leaf / PC, SP);
-        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
-        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
-        psi_leaf = psi_leaf - resid / slope;
-        counter++;
-        if (fabs(resid) <= 10.0) break;
-    }
     const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
     MC_ROLLED for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
 
@@ -1588,16 +1614,8 @@ MC_DEV_NOINLINE InfilOut infiltration_step_psi(const HourMoist<NA>& hm, InfilWor
     const double psi1 = B.psi[2];                                           /* water_potential[1] = water_potential[2], never updated again */
     const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
     const double RL = m.RL, PC = m.PC, SP = m.SP;
+    psi_leaf = stomatal_newton(psi_leaf, psi_bar, R_bar, TP);                /* campbell.jl:270-284 */
     int counter = 0;
-    while (counter < m.moist_max_it) {                                       /* stomatal Newton, campbell.jl:270-284 */
-        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
-        const double xp = mcm::pow(psi_leaf / PC, SP);
-        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
-        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
-        psi_leaf = psi_leaf - resid / slope;
-        counter++;
-        if (fabs(resid) <= 10.0) break;
-    }
     const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
     MC_ROLLED for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
 
@@ -1897,16 +1915,7 @@ MC_DEV_NOINLINE void moist_substep_start(MoistOwn& W, Coop2Shared& sh, double* s
     sh.dt[tid] = MC_MSCR(M_PSI, 2, tid);                                     /* water_potential[1] = water_potential[2], never updated again */
     const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
     const double RL = m.RL, PC = m.PC, SP = m.SP, TP = W.TP;
-    int counter = 0;
-    while (counter < m.moist_max_it) {                                       /* stomatal Newton, campbell.jl:270-284 */
-        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
-        const double xp = mcm::pow(psi_leaf / PC, SP);
-        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
-        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
-        psi_leaf = psi_leaf - resid / slope;
-        counter++;
-        if (fabs(resid) <= 10.0) break;
-    }
+    psi_leaf = stomatal_newton(psi_leaf, psi_bar, R_bar, TP);                /* campbell.jl:270-284 */
     W.TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
     MC_MSCR(M_UPT, 0, tid) = psi_leaf; MC_MSCR(M_UPT, 1, tid) = RL * W.TR;    /* the first F-pass forms uptake[i] = (psi[i] - psi_leaf - RL TR) / (rootR[i] + soilR[i]) */
     W.counter = 0;

@@ -213,6 +213,8 @@ static ObukhovOut calc_obukhov(double T_ref, double T_surf, double v_ref, double
     return o;
 }
 
+/* analysis hook (tools only): Newton iterations per (site, hour, sub-step) */
+static int32_t* g_trace_sub = nullptr; static thread_local int64_t tl_trace_row = -1;
 struct Counters { uint64_t n_rhs = 0, n_accept = 0, n_reject = 0, n_obukhov = 0, n_newton = 0, n_infil = 0, n_day_passes = 0; };
 
 /* surface_fluxes, :208-245 -> (Q_conv, dT) */
@@ -1099,7 +1101,9 @@ static WaterOut soil_water_balance(InfilBuffers& B, const mc_model_desc& m, cons
     const int niter = (int)(3600.0 / m.moisture_timestep_s);
     InfilOut io{};
     for (int k = 0; k < niter; k++) {                                                        /* :449-484 */
+        const uint64_t nw0 = cn.n_newton;
         io = infiltration_step(B, m, s, N, m.depths_m, P, theta, rh_loc, e.lai, EP, T0, cn);
+        if (g_trace_sub && tl_trace_row >= 0 && k < 10) g_trace_sub[tl_trace_row * 10 + k] += (int32_t)(cn.n_newton - nw0);
         if (io.hit_max) flags |= MC_STATUS_NEWTON_MAXITER;
         const double surf_evap = jmax(0.0, io.evaporation);
         const double wflux = jmax(0.0, io.surface_water_flux);
@@ -1373,6 +1377,7 @@ static void solve_soil_site(const mc_model_desc& m, const Site& site, const mc_i
                 for (int k = 0; k < ns; k++) Ts_before[k] = Ts[k];
                 p.L_prev = st.L_ode;
                 const uint64_t att0 = cn.n_accept + cn.n_reject, new0 = cn.n_newton;
+                tl_trace_row = (g_trace_sub && step < g_trace_rows) ? io.s * g_trace_rows + step : -1;
                 step_to_hour(I, i + 1, p, cn);
                 if (g_trace_attempts && step < g_trace_rows) g_trace_attempts[io.s * g_trace_rows + step] += (int32_t)(cn.n_accept + cn.n_reject - att0);
                 for (int k = 0; k < ns; k++) Ts[k] = I.u[k];
@@ -1714,6 +1719,7 @@ int mco_infiltration_steps(const mc_model_desc* m, const mc_sites_soa* site1, do
 }
 double mco_fastpow(double x, double y) { return mco::fastpow(x, y); }
 /* analysis hook: per-site per-hour RK attempts / Newton iterations of the NEXT mco_step_days call ([S][rows] int32, zero-initialised by the caller) */
+void mco_set_trace_sub(int32_t* sub) { mco::g_trace_sub = sub; }
 void mco_set_trace(int32_t* attempts, int32_t* newton, int64_t rows) { mco::g_trace_attempts = attempts; mco::g_trace_newton = newton; mco::g_trace_rows = rows; }
 /* phase_transition! white box */
 void mco_phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
