@@ -28,6 +28,9 @@ FIELDS = ("soil_temperature", "soil_moisture")
 # executed FP64 flop per site-day of the benchmark grid (DADD + DMUL + 2 DFMA), calibrated with ncu: profiles/README.md
 FLOP_PER_SITE_DAY = 41.1e6
 ALG_BYTES_PER_SITE_DAY = (10 * 24 + 7) * 8 + 2 * 19 * 24 * 8     # hourly+daily forcing read, hourly T+theta written
+# dram__bytes_read.sum + dram__bytes_write.sum of the soil kernel per site-day (one ncu capture, profiles/r1_v10_metrics.csv: 1.271 TB + 0.338 TB over
+# 151 552 site-days): block scratch and thread-local arrays of 1024 resident sites per SM overflow L2 - the traffic is ~1100x the algorithmic bytes
+DRAM_BYTES_PER_SITE_DAY = (1.270695e12 + 337.769864e9) / 151552
 
 
 def _pinned(shape):
@@ -237,9 +240,10 @@ def main():
     per_gpu = value / world
     roof = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf, "peak_how": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
             "achieved": (flop_sd * per_gpu / 1e12) if flop_sd else None, "frac": (flop_sd * per_gpu / 1e12 / peak_tf) if flop_sd else None,
-            "flop_per_site_day": flop_sd, "traffic": None,
+            "flop_per_site_day": flop_sd, "traffic": DRAM_BYTES_PER_SITE_DAY * S,
+            "traffic_how": "DRAM bytes per launch (one launch = one step of %d site-days per GPU) scaled from one ncu capture of the same kernel; not re-measured in this run" % S,
             "hbm": {"achieved": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9, "peak": 6536.0, "unit": "GB/s", "frac": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9 / 6536.0,
-                    "alg_bytes_per_site_day": ALG_BYTES_PER_SITE_DAY},
+                    "alg_bytes_per_site_day": ALG_BYTES_PER_SITE_DAY, "dram_traffic_GBps": DRAM_BYTES_PER_SITE_DAY * per_gpu / 1e9},
             "work_per_site_day": {k: counters[k] / max(1, counters["n_site_days"] - S * args.warmup) for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter")}}
     line = {"metric": "site-days/sec (hourly soil T+moisture)", "value": value, "unit": "site-days/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_time / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -139,6 +139,31 @@ extern "C" void he_soil_properties(const mc_model_desc* m, double P, double T, d
 extern "C" double he_goff_gratch(double T) { return mcd::goff_gratch(T); }
 extern "C" double he_fastpow(double x, double y) { return mcd::fastpow(x, y); }
 
+/* stomatal Newton (campbell.jl:270-284): the kernel's cycle-resolving form against the plain loop the reference runs */
+extern "C" double he_stomatal_newton(const mc_model_desc* m, double psi_bar, double R_bar, double TP)
+{
+    mcd::build_dev_model(*m, mcd::g_model_h);
+    return mcd::stomatal_newton(0.0, psi_bar, R_bar, TP);
+}
+extern "C" double he_stomatal_newton_plain(const mc_model_desc* m, double psi_bar, double R_bar, double TP, int* iterations)
+{
+    mcd::build_dev_model(*m, mcd::g_model_h);
+    const mcd::DevModel& d = mcd::g_model_h;
+    const double RL = d.RL, PC = d.PC, SP = d.SP;
+    double psi_leaf = 0.0; int counter = 0;
+    while (counter < d.moist_max_it) {
+        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
+        const double xp = mcm::pow(psi_leaf / PC, SP);
+        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
+        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
+        psi_leaf = psi_leaf - resid / slope;
+        counter++;
+        if (std::fabs(resid) <= 10.0) break;
+    }
+    if (iterations) *iterations = counter;
+    return psi_leaf;
+}
+
 extern "C" int he_set_state(void* h, const mc_state_soa* st)
 {
     Emu* e = (Emu*)h; const size_t S = e->S, N = e->N;

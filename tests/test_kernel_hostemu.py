@@ -95,6 +95,31 @@ def test_other_node_counts_bit_identical(n_nodes):
     assert eo.counters()["n_rhs"] == ee.counters()["n_rhs"]
 
 
+def test_stomatal_cycle_shortcut_equals_plain_loop():
+    """The kernel resolves a stomatal Newton iteration that never meets |residual| <= 10 from its cycle instead of running all
+    moisture_max_iterations; the value after the last iteration must be the plain loop's, bit for bit, whatever the orbit."""
+    import ctypes as C
+    import hostemu_engine
+    L = hostemu_engine.lib()
+    L.he_stomatal_newton.restype = C.c_double
+    L.he_stomatal_newton.argtypes = [C.c_void_p] + [C.c_double] * 3
+    L.he_stomatal_newton_plain.restype = C.c_double
+    L.he_stomatal_newton_plain.argtypes = [C.c_void_p] + [C.c_double] * 3 + [C.POINTER(C.c_int)]
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    rng = np.random.default_rng(7)
+    n, capped = 20000, 0
+    psi_bar = -np.exp(rng.uniform(np.log(0.5), np.log(3000.0), n))          # J/kg
+    R_bar = np.exp(rng.uniform(np.log(1e5), np.log(1e12), n))               # m4/kg/s
+    TP = np.exp(rng.uniform(np.log(1e-12), np.log(2e-4), n))                # kg/m2/s
+    for a, b, c in zip(psi_bar, R_bar, TP):
+        it = C.c_int(0)
+        plain = L.he_stomatal_newton_plain(C.byref(desc), a, b, c, C.byref(it))
+        fast = L.he_stomatal_newton(C.byref(desc), a, b, c)
+        capped += it.value >= desc.moisture_max_iterations
+        assert (plain == fast) or (plain != plain and fast != fast), (a, b, c, plain, fast, it.value)
+    assert capped > 100          # the sample must exercise non-terminating orbits
+
+
 def _variant(problem, **cfg):
     p = copy.deepcopy(problem)
     for k, v in cfg.items():
