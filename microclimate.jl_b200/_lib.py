@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SO = os.environ.get("MC_LIB") or os.path.join(CSRC, "libmicroclimate_b200.so")   # MC_LIB: development override (tuning variants)
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "microclimate_b200.h")
 SOURCES = [os.path.join(CSRC, "mc_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "mc_device.cuh"), INCLUDE, os.path.join(os.path.dirname(INCLUDE), "mc_math.h")]
+DEPS = SOURCES + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + [INCLUDE, os.path.join(os.path.dirname(INCLUDE), "mc_math.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "--shared", "-Xcompiler", "-fPIC"]
 

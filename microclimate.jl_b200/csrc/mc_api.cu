@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(BLOCK, MC_MIN_BLOCKS) soil_chunk_kernel(const 
 }
 
 /* Block-cooperative variant (NoSnow, fixed day-pass counts): a block owns blockDim.x sites; the conductivity of every RHS evaluation is
- * and every other node loop of the ODE hour are served by the whole block over (requesting site, node) items (mc_device.cuh,
+ * and every other node loop of the ODE hour are served by the whole block over (requesting site, node) items (mc_coop_ode.cuh,
  * "Block-cooperative ODE phase").  Threads past the end of
  * the range mirror the last site (same values to the same addresses) so that every thread of a block reaches every barrier. */
 #ifndef MC_COOP_MIN_BLOCKS

@@ -1,25 +1,31 @@
 /*
- * mc_device.cuh — per-site soil heat + moisture integration, one GPU thread per site (sm_100a).
+ * mc_device.cuh — device code of the batched-sites soil heat + moisture integration (sm_100a).
  *
- * B200-native restatement of Microclimate.jl's solve_soil! hot path
- * (reference src/simulation.jl:355-819 and everything below it).  This is NOT a translation of
- * the Julia control flow: the per-site algorithm is re-organised around what a thread can keep
- * on chip —
- *   - theta is constant during an ODE hour, so every theta-only term of the Campbell-de Vries
- *     soil properties (areal heat capacity, volume fractions, recirculation factor) is hoisted
- *     out of the right-hand side into a per-hour table;
- *   - soil temperature is constant during the moisture hour, so the infiltration setup block
- *     (reference campbell.jl:180-248, recomputed 10x per hour upstream) and the per-node vapour
- *     densities inside the Newton loop are computed once per hour;
- *   - forcing is read straight from the site-fastest SoA arrays (a warp reads 32 consecutive
- *     doubles per knot: one 256 B coalesced request), never copied into per-site buffers;
- *   - all powers with fixed exponents are strength-reduced (x^4, x^1.75, x^0.75).
- * Results are the reference algorithm's to within floating-point reassociation (tests compare
- * against the CPU oracle at 1e-3 K / 1e-5 m3/m3, observed ~1e-9).
+ * B200-native restatement of Microclimate.jl's solve_soil! hot path (reference src/simulation.jl:355-819 and everything
+ * below it).  This is NOT a translation of the Julia control flow:
+ *   - theta is constant during an ODE hour, so every theta-only term of the Campbell-de Vries soil properties (areal heat
+ *     capacity, volume fractions, recirculation factor) is hoisted out of the right-hand side into a per-hour table;
+ *   - soil temperature is constant during the moisture hour, so the infiltration setup block (reference campbell.jl:180-248,
+ *     recomputed 10x per hour upstream) and the per-node vapour densities inside the Newton loop are computed once per hour;
+ *   - forcing is read straight from the site-fastest SoA arrays (a warp reads 32 consecutive doubles per knot: one 256 B
+ *     coalesced request), never copied into per-site buffers;
+ *   - in the block-cooperative kernel the node loops of the ODE hour are item passes of the whole block over (site, node)
+ *     pairs and the integrator is a resumable state machine (mc_coop_ode.cuh).
+ * Only results of whole sub-expressions are hoisted, never re-associated: every floating-point operation of the reference
+ * algorithm is executed in the reference's order with the shared bit-reproducible math kernel (include/mc_math.h), so the
+ * outputs are bit-identical to the CPU oracle (tests/).
  *
- * The functions are written against a tiny platform shim so the very same per-site code can be
- * compiled by g++ for tests/hostemu (a development harness that runs the kernel body on the
- * CPU where no GPU exists).  The shipped library (mc_api.cu) only ever launches the CUDA kernel.
+ * Layout of the device code (all in namespace mcd, included below in this order):
+ *   mc_physics.cuh   psychrometrics, longwave, Monin-Obukhov, soil properties, no-snow RHS
+ *   mc_snow.cuh      SnowModel{8} and the snow-aware RHS
+ *   mc_tsit5.cuh     adaptive Tsit5 + PI controller, per-site form
+ *   mc_coop_ode.cuh  block-cooperative ODE phase
+ *   mc_moisture.cuh  freeze/thaw, Campbell (1985) soil water balance
+ *   mc_site.cuh      solve_soil! / solve_air! per site, host-side model flattening
+ *
+ * The functions are written against a tiny platform shim so the very same code can be compiled by g++ for tests/hostemu (a
+ * development harness that runs the kernel body on the CPU where no GPU exists).  The shipped library (mc_api.cu) only ever
+ * launches the CUDA kernels.
  */
 #pragma once
 #include <stdint.h>
@@ -153,2603 +159,11 @@ MC_DEV double jmax(double a, double b) { return (a != a || b != b) ? (a + b) : (
 MC_DEV double jmin(double a, double b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
 MC_DEV double jclamp(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
 
-/* ------------------------------------------------------------------------------------------
- * FluidProperties.jl psychrometrics (un-vendored; constants are data, see mc_fluid_constants)
- * ------------------------------------------------------------------------------------------ */
-/* vapour_pressure(GoffGratch(), T) [Pa] */
-MC_DEV_NOINLINE double goff_gratch(double T)
-{
-    const double Tp = T + 0.01;
-    double loge;
-    if (Tp <= 273.16) {
-        const double r = MCM_DIV(273.16, Tp);
-        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - MCM_DIV(Tp, 273.16)) + 0.7858350313586662 /* mcm::log10(6.1071) */;
-    } else {
-        const double r = MCM_DIV(373.16, Tp);
-        loge = -7.90298 * (r - 1.0) + 5.02808 * mcm::log10(r)
-             - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - MCM_DIV(Tp, 373.16))) - 1.0)
-             + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314 /* mcm::log10(1013.246) */;
-    }
-    return 100.0 * mcm::exp10(loge);
-}
-
-/* goff_gratch at T-1, T, T+1 (the central difference of campbell_devries.jl:117-122) evaluated side by side: the three
- * evaluations are independent, so interleaving them triples the instruction-level parallelism of the hottest code in the
- * path.  Every element goes through exactly the operations of goff_gratch() above (bit-identical results). */
-struct GG3 { double em, e0, ep; };
-MC_DEV_NOINLINE GG3 goff_gratch3(double T)
-{
-    GG3 o;
-    const double t0 = (T - 1.0) + 0.01, t1 = T + 0.01, t2 = (T + 1.0) + 0.01;
-    if (t0 > 273.16 && t2 < 400.0) {                       /* all three on the over-water branch (t0 < t1 < t2) */
-        const double r0 = 373.16 / t0, r1 = 373.16 / t1, r2 = 373.16 / t2;
-        const double a0 = 11.344 * (1.0 - t0 / 373.16), a1 = 11.344 * (1.0 - t1 / 373.16), a2 = 11.344 * (1.0 - t2 / 373.16);
-        const double b0 = -3.49149 * (r0 - 1.0), b1 = -3.49149 * (r1 - 1.0), b2 = -3.49149 * (r2 - 1.0);
-        const double pa0 = mcm::exp10_arg(a0), pa1 = mcm::exp10_arg(a1), pa2 = mcm::exp10_arg(a2);
-        const double pb0 = mcm::exp10_arg(b0), pb1 = mcm::exp10_arg(b1), pb2 = mcm::exp10_arg(b2);
-        /* arguments are O(1) for 273 K < T < 400 K: always inside the fast range of exp / log */
-        const double ea0 = mcm::exp10_finish(mcm::exp_core(pa0), a0, pa0), ea1 = mcm::exp10_finish(mcm::exp_core(pa1), a1, pa1), ea2 = mcm::exp10_finish(mcm::exp_core(pa2), a2, pa2);
-        const double eb0 = mcm::exp10_finish(mcm::exp_core(pb0), b0, pb0), eb1 = mcm::exp10_finish(mcm::exp_core(pb1), b1, pb1), eb2 = mcm::exp10_finish(mcm::exp_core(pb2), b2, pb2);
-        const double l0 = mcm::log_core(r0) * 4.34294481903251816668e-01, l1 = mcm::log_core(r1) * 4.34294481903251816668e-01, l2 = mcm::log_core(r2) * 4.34294481903251816668e-01;
-        const double g0 = -7.90298 * (r0 - 1.0) + 5.02808 * l0 - 1.3816e-7 * (ea0 - 1.0) + 8.1328e-3 * (eb0 - 1.0) + 3.0057148979490314;
-        const double g1 = -7.90298 * (r1 - 1.0) + 5.02808 * l1 - 1.3816e-7 * (ea1 - 1.0) + 8.1328e-3 * (eb1 - 1.0) + 3.0057148979490314;
-        const double g2 = -7.90298 * (r2 - 1.0) + 5.02808 * l2 - 1.3816e-7 * (ea2 - 1.0) + 8.1328e-3 * (eb2 - 1.0) + 3.0057148979490314;
-        const double p0 = mcm::exp10_arg(g0), p1 = mcm::exp10_arg(g1), p2 = mcm::exp10_arg(g2);
-        o.em = 100.0 * mcm::exp10_finish(mcm::exp_core(p0), g0, p0);
-        o.e0 = 100.0 * mcm::exp10_finish(mcm::exp_core(p1), g1, p1);
-        o.ep = 100.0 * mcm::exp10_finish(mcm::exp_core(p2), g2, p2);
-    } else {
-        o.em = goff_gratch(T - 1.0); o.e0 = goff_gratch(T); o.ep = goff_gratch(T + 1.0);
-    }
-    return o;
-}
-
-struct WetAir { double vapour_pressure, vapour_density, specific_heat, density; };
-
-#if MC_WETAIR_NOINLINE
-MC_DEV_NOINLINE
-#else
-MC_DEV
-#endif
-WetAir wet_air(double T, double rh, double P)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    WetAir w;
-    const double e = goff_gratch(T) * rh;
-    w.vapour_pressure = e;
-    const double mr = (m.eps * m.dep * e) / (P - m.dep * e);
-    w.vapour_density = e * m.Mw / (0.998 * m.R * T);
-    const double T_vir = T * ((1.0 + mr / m.eps) / (1.0 + mr));
-    w.density = m.Ma_over_R * P / (0.999 * T_vir);
-    w.specific_heat = (m.cpa + mr * m.cpv) / (1.0 + mr);
-    return w;
-}
-MC_DEV double vapour_density_sat(double T) { const DevModel& m = MC_CONST_MODEL; return goff_gratch(T) * m.Mw / (0.998 * m.R * T); }
-MC_DEV double latent_heat(double T) { const DevModel& m = MC_CONST_MODEL; return m.Lv_a - m.Lv_b * (T - T0C); }
-
-/* atmospheric_radiation (Campbell-Norman / Swinbank), src/radiation/atmospheric */
-MC_DEV double atmospheric_radiation(double e_Pa, double T_air)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    if (m.swinbank) return (9.2e-6 * T_air * T_air) * m.sigma * mcm::pow4(T_air);
-    const double Tp = T_air + 0.01;
-    return (1.72 * mcm::pow((e_Pa / 1000.0) / Tp, 1.0 / 7.0)) * m.sigma * mcm::pow4(Tp);
-}
-
-/* precompute_longwave_sky -> sky temperature (view_factor.jl:23-67) */
-MC_DEV_NOINLINE double sky_temperature(double svf, double /*P*/, double rh, double T_ref, double eps_cloud, double cloud, double shade,
-                              bool has_lw, double supplied_lw)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const double cloud_rad = m.sigma * eps_cloud * mcm::pow4(T_ref - 2.0);
-    const double hill_rad = m.sigma * eps_cloud * mcm::pow4(T_ref);
-    double lw_sky;
-    if (has_lw) lw_sky = supplied_lw * (1.0 - shade);
-    else {
-        const double e = goff_gratch(T_ref) * rh;
-        lw_sky = (atmospheric_radiation(e, T_ref) * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - shade);
-    }
-    const double incoming = (lw_sky + shade * hill_rad) * svf + hill_rad * (1.0 - svf);
-    return mcm::pow(incoming / m.sigma, 0.25);
-}
-
-/* ------------------------------------------------------------------------------------------
- * Monin-Obukhov (src/boundary_layer/monin_obukhov.jl)
- * ------------------------------------------------------------------------------------------ */
-MC_DEV double calc_rho_cp(double Tmean) { return (0.08472 / Tmean) * 4.184e6; }
-MC_DEV double sublayer_stanton(double z0, double ustar) { return 0.62 / mcm::pow(z0 * 100.0 * (ustar * 6000.0) / 12.0, 0.45); }
-MC_DEV double convective_flux(double rho_cp, double dT, double ustar, double Stb, double Sts) { return rho_cp * dT * ustar * Stb / (1.0 + Stb / Sts); }
-MC_DEV double calc_phi_m(double z, double gamma, double L) { return sqrt(sqrt(1.0 - gamma * z / L)); }
-MC_DEV double calc_psi_m(double x) { return 2.0 * mcm::log((1.0 + x) / 2.0) + mcm::log((1.0 + x * x) / 2.0) - 2.0 * mcm::atan(x) + PI_D / 2.0; }
-MC_DEV double calc_psi_h(double x) { return 2.0 * mcm::log((1.0 + x * x) / 2.0); }
-
-struct Obukhov { double L, Sts, Stb, ustar, psi_h, Q; int iters; };
-
-/* calc_Obukhov_length fixed point (monin_obukhov.jl:527-577): <=30 iterations, 1 % relative change */
-MC_DEV_NOINLINE Obukhov calc_obukhov(double v_ref, double z0, double z, double lz, double dT, double rho_cp, double L0)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    Obukhov o; o.L = L0; o.Q = 0.0; o.Stb = 0.0; o.Sts = 0.0; o.psi_h = 0.0; o.ustar = 0.0;
-    double rel = 1.0; int count = 0;
-    while (rel > 1.0e-2 && count < 30) {
-        count++;
-        const double x = calc_phi_m(z, 16.0, o.L);
-        const double psi_m = calc_psi_m(x);
-        o.psi_h = calc_psi_h(x);
-        double lrc = lz - psi_m;
-        if (lrc <= 0.0) lrc = 1.0e-6;
-        o.ustar = m.kappa * v_ref / lrc;
-        if (o.ustar < 1.0e-6) o.ustar = 1.0e-6;
-        o.Sts = sublayer_stanton(z0, o.ustar);
-        o.Stb = (0.64 / lrc) * (1.0 - 0.1 * z / o.L);
-        o.Q = convective_flux(rho_cp, dT, o.ustar, o.Stb, o.Sts);
-        const double Lnew = RHOCPTKG * o.ustar * o.ustar * o.ustar / o.Q;
-        rel = fabs((Lnew - o.L) / o.L);
-        o.L = Lnew;
-    }
-    o.iters = count;
-    return o;
-}
-
-/* ------------------------------------------------------------------------------------------
- * Per-site context: what a thread keeps for its site across the whole chunk
- * ------------------------------------------------------------------------------------------ */
-template <int NA>
-struct HourSoil {           /* theta-only soil property terms, rebuilt once per hour (theta is constant within the ODE hour) */
-    double cap[NA];         /* areal heat capacity of the node's control volume, J/m2/K            (heat_transport_1d.jl:175-190) */
-    double theta[NA], phim[NA], phig[NA], fw[NA], lam_m[NA];
-};
-
-struct HourPar {            /* SoilEnergyInputs scalars (heat_transport_1d.jl:41-63) */
-    double shade, eps_surf, eps_cloud, soil_wetness, albedo, L_prev;
-    double z0, lz, slope, svf;          /* lz = mcm::log(zref/z0) */
-    const double *fP, *fT, *fwind, *frh, *fcloud, *fsolar, *fdiff, *fzen, *fszen;   /* this site's day: base[k*S] is knot k */
-    const double* ftab[7];              /* {P, T, wind, zen, solar, cloud, rh}: the seven always-used interpolants, for a rolled loop */
-    int64_t S;
-    const struct SnowCtx* sn;           /* SnowModel context (NULL without snow) */
-};
-
-MC_DEV double knot_lerp(const double* base, int64_t S, int i, double d)
-{
-    const int i1 = i + 1 > 23 ? 23 : i + 1;      /* 25th knot repeats hour 24 (simulation.jl:990) */
-    return (1.0 - d) * MC_LDG(base + (int64_t)i * S) + d * MC_LDG(base + (int64_t)i1 * S);
-}
-
-/* Campbell-de Vries bulk conductivity of one node (campbell_devries.jl:79-142), T-dependent part only */
-#ifndef MC_WEIGHT_NOINLINE
-#define MC_WEIGHT_NOINLINE 0
-#endif
-#if MC_WEIGHT_NOINLINE
-MC_DEV_NOINLINE
-#else
-MC_DEV
-#endif
-double devries_weight(double lam_c, double lam_f, double ga, double gc)
-{
-    const double r1 = MCM_DIV(lam_c, lam_f) - 1.0;
-    return MCM_DIV(2.0, 3.0 * (1.0 + ga * r1)) + MCM_DIV(1.0, 3.0 * (1.0 + gc * r1));
-}
-MC_DEV_NOINLINE double soil_conductivity(double T, double P, double p0_over_p, double p_over_p0, double theta, double phim, double phig, double fw, double lam_m)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const double Tc = T - T0C;
-    const double lam_w = 0.554 + 2.24e-3 * Tc - 9.87e-6 * Tc * Tc;
-    const double lam_a = 0.024 + 7.73e-5 * Tc - 2.6e-8 * Tc * Tc;
-    const double Dv = 2.12e-5 * p0_over_p * mcm::pow(MCM_DIV(T, 273.15), 1.75);       /* campbell_devries.jl:109; p0_over_p = P0/P hoisted by the caller */
-    const double rho_hat = 44.65 * p_over_p0 * MCM_DIV(273.15, T);                    /* :111 */
-    const double Hv = m.Hv_a - m.Hv_b * (T - T0C);
-#if MC_USE_GG3
-    const GG3 gg = goff_gratch3(T);
-    const double e0 = gg.e0 * 0.99;
-    const double em = gg.em * 0.99;
-    const double ep = gg.ep * 0.99;
-#else
-    const double e0 = goff_gratch(T) * 0.99;
-    const double em = goff_gratch(T - 1.0) * 0.99;
-    const double ep = goff_gratch(T + 1.0) * 0.99;
-#endif
-    const double dedT = (ep - em) / 2.0;
-    const double lam_g = lam_a + MCM_DIV(Hv * dedT * fw * rho_hat * Dv, P - e0);
-    const double lam_f = lam_g + fw * (lam_w - lam_g);
-    const double ww = devries_weight(lam_w, lam_f, m.ga, m.gc);
-    const double wm = devries_weight(lam_m, lam_f, m.ga, m.gc);
-    const double wg = devries_weight(lam_g, lam_f, m.ga, m.gc);
-    return MCM_DIV(theta * ww * lam_w + phim * wm * lam_m + phig * wg * lam_g, theta * ww + phim * wm + phig * wg);
-}
-
-/* full soil_properties for the output rows (update_soil_properties!, simulation.jl:905-913) */
-MC_DEV void soil_properties_full(double T, double P, double theta, double bd, double md, double lam_m, double c_m,
-                                 double& lam, double& cp, double& rho)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    cp = bd / md * c_m + theta * WATER_CP;
-    rho = theta * WATER_RHO + bd;
-    const double phim = bd / md;
-    const double phig = jmax(0.0, 1.0 - theta - phim);
-    const double fw = 1.0 / (1.0 + mcm::pow(theta / m.theta0, -m.recirc_pow));
-    lam = soil_conductivity(T, P, m.P0 / P, P / m.P0, theta, phim, phig, fw, lam_m);
-}
-
-/* ------------------------------------------------------------------------------------------
- * soil_energy_balance (heat_transport_1d.jl:137-302), no-snow form: the surface is node 0.
- * u, du in K and K/min.
- * ------------------------------------------------------------------------------------------ */
-template <int NA>
-MC_DEV_NOINLINE void soil_rhs(const HourSoil<NA>& hs, const HourPar& hp, const double* __restrict__ u, double t,
-                              double* __restrict__ du, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int N = m.N;
-    cn.n_rhs++;
-    /* interpolate_forcings (forcing.jl:24-37) */
-    const double xk = t / 60.0;
-    int ik = (int)floor(xk);
-    ik = ik < 0 ? 0 : (ik > 23 ? 23 : ik);
-    const double dk = xk - (double)ik;
-#if MC_LERP_LOOP
-    double fv[7];
-    MC_ROLLED for (int k = 0; k < 7; k++) fv[k] = knot_lerp(hp.ftab[k], hp.S, ik, dk);
-    const double P = fv[0], T_air = fv[1];
-    const double wind = jmax(fv[2], 0.1);
-    const double zen = jmin(90.0, nearbyint(fv[3] * 1000.0) / 1000.0);
-    const double solar = jmax(0.0, fv[4]);
-    const double cloud = jclamp(fv[5], 0.0, 1.0);
-    const double rh = jclamp(fv[6], 0.0, 1.0);
-#else
-    const double P = knot_lerp(hp.fP, hp.S, ik, dk);
-    const double T_air = knot_lerp(hp.fT, hp.S, ik, dk);
-    const double wind = jmax(knot_lerp(hp.fwind, hp.S, ik, dk), 0.1);
-    const double zen = jmin(90.0, nearbyint(knot_lerp(hp.fzen, hp.S, ik, dk) * 1000.0) / 1000.0);
-    const double solar = jmax(0.0, knot_lerp(hp.fsolar, hp.S, ik, dk));
-    const double cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
-    const double rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
-#endif
-
-    /* conduction: node conductance G_i = lambda_i(T_i) / dz_i, built on the fly so only two live at a time; the next node's
-     * hoisted terms are loaded BEFORE the long conductivity call so their latency hides behind it */
-    const double Ts_node = jclamp(u[0], T_LO, m.T_hi);
-    double T_up = Ts_node;
-    double th = hs.theta[1], pm = hs.phim[1], pg = hs.phig[1], fw = hs.fw[1], lm = hs.lam_m[1], cap = hs.cap[1];
-    double T_i = jclamp(u[1], T_LO, m.T_hi);
-    const double p0p = m.P0 / P, pp0 = P / m.P0;
-    double G_up = soil_conductivity(T_up, P, p0p, pp0, hs.theta[0], hs.phim[0], hs.phig[0], hs.fw[0], hs.lam_m[0]) / m.dzg[0];
-    const double Q_cond = G_up * (T_i - Ts_node);
-    MC_ROLLED for (int i = 1; i < N - 1; i++) {
-        const int in = i + 1 < N - 1 ? i + 1 : i;
-        const double T_dn = jclamp(u[i + 1], T_LO, m.T_hi);
-        const double nth = hs.theta[in], npm = hs.phim[in], npg = hs.phig[in], nfw = hs.fw[in], nlm = hs.lam_m[in], ncap = hs.cap[in];
-        const double G_i = soil_conductivity(T_i, P, p0p, pp0, th, pm, pg, fw, lm) / m.dzg[i];
-        du[i] = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / cap;
-        T_up = T_i; T_i = T_dn; G_up = G_i;
-        th = nth; pm = npm; pg = npg; fw = nfw; lm = nlm; cap = ncap;
-    }
-    du[N - 1] = 0.0;                                         /* Dirichlet bottom node (:291-293) */
-
-    /* shortwave (:223-232) */
-    double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
-    if (hp.slope > 0.0 && zen < 90.0) {
-        const double szen = jmin(90.0, knot_lerp(hp.fszen, hp.S, ik, dk));
-        const double fd = jclamp(knot_lerp(hp.fdiff, hp.S, ik, dk), 0.0, 1.0);
-        const double cz = mcm::cos(zen * PI_D / 180.0), csz = mcm::cos(szen * PI_D / 180.0);
-        Q_solar = jmax(0.0, (((1.0 - fd) * Q_solar) / cz) * csz) + (fd * Q_solar) * hp.svf;
-    }
-    /* longwave (:237-250) */
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double atm = atmospheric_radiation(wa.vapour_pressure, T_air);
-    const double cloud_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air - 2.0);
-    const double hill_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air);
-    const double lw_sky = (atm * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - hp.shade);
-    const double incoming = (lw_sky + hp.shade * hill_rad) * hp.svf + hill_rad * (1.0 - hp.svf);
-    const double Q_ir = incoming - ((1.0 - hp.shade) * m.sigma * hp.eps_surf) * mcm::pow4(Ts_node) - hp.shade * hill_rad;
-
-    /* surface temperature guards (:260-266) */
-    double Ts = Ts_node;
-    if (fabs(Ts - T0C) > 100.0) Ts = T_air + 1.0;
-    if (Ts == T_air) Ts = Ts + 0.1;
-
-    /* surface_fluxes (monin_obukhov.jl:208-245) */
-    const double dT = T_air - Ts;
-    const double rho_cp = calc_rho_cp((Ts + T_air) / 2.0);
-    double Qc;
-    if (T_air >= Ts || zen >= 90.0) {
-        const double ustar = jmax(m.kappa * wind / hp.lz, 1.0e-6);
-        Qc = convective_flux(rho_cp, dT, ustar, 0.64 / hp.lz, sublayer_stanton(hp.z0, ustar));
-    } else {
-        const Obukhov o = calc_obukhov(wind, hp.z0, m.zref, hp.lz, dT, rho_cp, hp.L_prev >= 0.0 ? -0.3 : hp.L_prev);
-        cn.n_obukhov += o.iters;
-        Qc = o.Q;
-    }
-    /* surface_convection_evaporation + evaporation (bulk_transfer.jl:11-81) */
-    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = Ts < T_LO ? T_LO : Ts;
-    const double Qe = (hp.soil_wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
-
-    du[0] = 60.0 * (Q_solar + Q_ir + Q_cond + Qc + 0.0 /* Q_freeze: snow only */ - Qe) / hs.cap[0];
-}
-
-
-/* ------------------------------------------------------------------------------------------
- * Snow: SnowModel{8} (src/snow/snow_model.jl) + apparent-heat-capacity closures (src/apparent_heat_capacity/*.jl).
- * Depths in cm, densities in g/cm3, as upstream.  The reference's snow_depth_hourly[nsteps] scratch array is only read
- * at [step] and [step-1]; it is carried as two scalars (sd_cur, sd_prev).
- * ------------------------------------------------------------------------------------------ */
-constexpr int NSN = MC_SNOW_NODES;
-struct SnowState { double depth, age, days_since, density, prev_density, cum_melt, extra, sum_phase; int active; };
-struct SnowScratch { double node_depths[NSN]; double sd_prev, sd_cur; double meanT[NSN], meanTpast[NSN]; };
-struct SnowCtx { SnowState st; SnowScratch sc; double depths[MC_MAX_ODE_NODES + 1]; double Q_freeze; const SnowState* rhs_state; };
-
-MC_DEV double mc_tanh(double x) { const double e = mcm::exp(2.0 * x); return x > 20.0 ? 1.0 : (x < -20.0 ? -1.0 : (e - 1.0) / (e + 1.0)); }
-MC_DEV_NOINLINE double apparent_heat_capacity(double T, double cp_base)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    const double Tc = T - T0C, Lf = LATENT_FUSION;
-    switch (sm.ahc_kind) {
-    case MC_AHC_TANH: {
-        const double lo = (Tc - sm.ahc_T_low_C) / sm.ahc_smoothing_K, hi = (Tc - sm.ahc_T_high_C) / sm.ahc_smoothing_K;
-        return cp_base + (Lf / sm.ahc_window_K) * (0.5 * (mc_tanh(lo) - mc_tanh(hi)));
-    }
-    case MC_AHC_GAUSSIAN: {
-        const double x = (Tc - sm.ahc_T_melt_C) / sm.ahc_width_K;
-        return cp_base + (Lf / (sm.ahc_width_K * sqrt(2.0 * PI_D))) * mcm::exp(-0.5 * x * x);
-    }
-    case MC_AHC_WESTERMANN: {
-        const double x = (Tc - sm.ahc_T_melt_C) / sm.ahc_width_K, th = mc_tanh(x);
-        return cp_base + (Lf / (2.0 * sm.ahc_width_K)) * (1.0 - th * th);
-    }
-    default:
-        if (Tc > sm.ahc_T_low_C && Tc <= sm.ahc_T_high_C) return cp_base + Lf / sm.ahc_window_K;
-        return cp_base;
-    }
-}
-MC_DEV SnowState initial_snow_state(double depth, double density_or_neg)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    const double dflt = sm.density_function[0] > 0.0 ? sm.density_function[1] : sm.snow_density;
-    const double d = density_or_neg > 0.0 ? density_or_neg : dflt;
-    SnowState st; st.depth = depth; st.age = 0.0; st.days_since = 0.3; st.density = d; st.prev_density = d;
-    st.cum_melt = 0.0; st.extra = 0.0; st.active = 0; st.sum_phase = 0.0;
-    return st;
-}
-MC_DEV double evolve_snow_density(const SnowState& st)
-{
-    const double* df = MC_CONST_MODEL.snow.density_function;
-    if (!(df[0] > 0.0)) return st.density;
-    if (df[2] > 0.0) return (df[0] - df[1]) * (1.0 - mcm::exp(-df[2] * st.depth - df[3] * st.age)) + df[1];
-    return jmin(0.9167, df[0] * st.age + df[1]);
-}
-MC_DEV double snow_albedo(double days_since) { return (-9.874 * mcm::log(jmax(days_since, 0.3)) + 78.3434) / 100.0; }
-MC_DEV double snow_specific_heat(double dens, double P)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const double e = goff_gratch(273.15) * 1.0;
-    const double mr = (m.eps * m.dep * e) / (P - m.dep * e);
-    return 2100.0 * dens + (1005.0 + 1820.0 * (mr / 1.0 + mr)) * (1.0 - dens);
-}
-MC_DEV_NOINLINE void activate_snow_nodes(SnowState& st, SnowScratch& sc, double& sd)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    const double cursnow = sd;
-    int active = st.active;
-    if (cursnow > 300.0) active = 0;
-    if (cursnow < sm.min_snow_depth_cm) {
-        MC_ROLLED for (int i = 0; i < NSN; i++) sc.node_depths[i] = 0.0;
-        sd = 0.0; st.active = 0; st.depth = 0.0;
-        return;
-    }
-    int maxsnode = 0;
-    MC_ROLLED for (int i = 1; i <= NSN; i++) if (cursnow > sm.node_thresholds_cm[i - 1]) maxsnode = i;
-    maxsnode = maxsnode < NSN - 1 ? maxsnode : NSN - 1;
-    MC_ROLLED for (int i = 1; i <= maxsnode; i++) sc.node_depths[i + (NSN - maxsnode) - 1] = sm.node_thresholds_cm[i - 1];
-    if (maxsnode < active) { MC_ROLLED for (int i = 1; i <= NSN - maxsnode; i++) sc.node_depths[i - 1] = 0.0; }
-    st.depth = cursnow; st.active = maxsnode;
-}
-MC_DEV void compute_effective_depths(const SnowState& st, const SnowScratch& sc, double* out)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const double off = st.depth >= m.snow.min_snow_depth_cm ? st.depth : 0.0;
-    MC_ROLLED for (int i = 0; i < NSN; i++) out[i] = sc.node_depths[i] / 100.0;
-    MC_ROLLED for (int i = 0; i < m.N; i++) out[NSN + i] = m.depths[i] + off / 100.0;
-}
-MC_DEV void snow_layer_geometry(const SnowState& st, const SnowScratch& sc, int layer_index, int& node_index, double& thickness)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    const int maxsnode = st.active;
-    int ni = layer_index + NSN - 1 - maxsnode; ni = ni > NSN ? NSN : ni; ni = ni < 1 ? 1 : ni;
-    if (layer_index != maxsnode + 1) {
-        int upper = layer_index + NSN - maxsnode; upper = upper < 1 ? 1 : upper;
-        thickness = sc.node_depths[upper - 1] - sc.node_depths[ni - 1];
-    } else {
-        thickness = jmax(0.0, st.depth - sm.node_thresholds_cm[(maxsnode > 1 ? maxsnode : 1) - 1]);
-    }
-    node_index = ni - 1;
-}
-MC_DEV_NOINLINE double snow_thermal_melt(const SnowState& st, SnowScratch& sc, const double* Ts, const double* Ts_before, double P, double T_soil, double T_soil_before)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    MC_ROLLED for (int i = 0; i < NSN; i++) {
-        const double below = i < NSN - 1 ? Ts[i + 1] : T_soil, below_past = i < NSN - 1 ? Ts_before[i + 1] : T_soil_before;
-        sc.meanT[i] = (Ts[i] + below) / 2.0 - T0C;
-        sc.meanTpast[i] = (Ts_before[i] + below_past) / 2.0 - T0C;
-    }
-    const double cp = snow_specific_heat(st.density, P);
-    double total = 0.0;
-    MC_ROLLED for (int j = 1; j <= st.active + 1; j++) {
-        int ni; double thick; snow_layer_geometry(st, sc, j, ni, thick);
-        const double mass = thick * st.density * 10.0;
-        if (sc.meanT[ni] > sm.melt_threshold_C) {
-            const double dT = sc.meanT[ni] - sm.melt_threshold_C;
-            const double sensible = dT * cp * mass, latent = LATENT_FUSION * mass;
-            total += (sensible + latent) / LATENT_FUSION;
-        }
-    }
-    return total / 10.0;
-}
-MC_DEV_NOINLINE void snow_phase_transition(SnowState& st, SnowScratch& sc, double* Ts, double P, double& T_soil_surface)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    if (st.depth >= 200.0) return;
-    if (st.depth < sm.min_snow_depth_cm) return;
-    const double cp = snow_specific_heat(st.density, P);
-    bool clamp_soil = false; bool clamp[NSN]; double phase_heat[NSN], layer_mass[NSN];
-    MC_ROLLED for (int i = 0; i < NSN; i++) { clamp[i] = false; phase_heat[i] = 0.0; layer_mass[i] = 0.0; }
-    MC_ROLLED for (int j = 1; j <= st.active + 1; j++) {
-        if (j > NSN) continue;
-        int ni; double thick; snow_layer_geometry(st, sc, j, ni, thick);
-        if (!(sc.node_depths[ni] > 0.0)) continue;
-        const double mass = thick * st.density * 10.0;
-        if (sc.meanTpast[ni] >= 0.0 && sc.meanT[ni] <= 0.0) {
-            layer_mass[ni] = jmax(0.0, mass);
-            phase_heat[ni] = (sc.meanTpast[ni] - sc.meanT[ni]) * cp * layer_mass[ni];
-            clamp[ni] = true;
-            if (ni == NSN - 1) clamp_soil = true; else clamp[ni + 1] = true;
-        }
-    }
-    double sp = 0.0, total_mass = 0.0;
-    MC_ROLLED for (int i = 0; i < NSN; i++) sp += phase_heat[i];
-    double new_sum = st.sum_phase + sp;
-    MC_ROLLED for (int i = 0; i < NSN; i++) total_mass += layer_mass[i];
-    if (total_mass > 0.0 && new_sum > LATENT_FUSION * total_mass) {
-        bool over[NSN]; MC_ROLLED for (int i = 0; i < NSN; i++) over[i] = false;
-        MC_ROLLED for (int i = 0; i < NSN; i++) if (clamp[i] && phase_heat[i] > 0.0) { over[i] = true; phase_heat[i] = 0.0; if (i < NSN - 1) over[i + 1] = true; }
-        MC_ROLLED for (int i = 0; i < NSN; i++) if (over[i]) Ts[i] = T0C - 0.5;
-        if (clamp_soil) T_soil_surface = T0C - 0.5;
-        new_sum = 0.0;
-    } else {
-        MC_ROLLED for (int i = 0; i < NSN; i++) if (clamp[i]) Ts[i] = T0C;
-        if (clamp_soil) T_soil_surface = T0C;
-    }
-    st.sum_phase = new_sum;
-}
-struct SnowUpdateOut { double snowfall, thermal_melt, rain_melt; };
-MC_DEV_NOINLINE SnowUpdateOut update_snow(SnowState& st, SnowScratch& sc, const double* Ts, const double* Ts_before, double T_air, double rainfall, double P,
-                                          int64_t step, double T_soil, double T_soil_before, double Q_evap, bool hourly, double shade, int day_of_year)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    const bool first = step == 1, midnight = ((step - 1) % 24) == 0;
-    const double prev_dens = st.density;
-    const double new_dens = evolve_snow_density(st);
-    const double ratio = new_dens / prev_dens;
-    if (step > 1 && ratio != 0.0 && isfinite(ratio)) sc.sd_prev /= ratio;
-    double snowfall = 0.0, days_since = st.days_since;
-    if (T_air - T0C <= sm.snow_temperature_threshold_C && rainfall > 0.0) {
-        if (midnight || hourly) {
-            snowfall = rainfall * sm.rain_multiplier * sm.undercatch / new_dens / 10.0;
-            if (shade > 0.0) snowfall *= (1.0 - sm.canopy_interception);
-            days_since = 0.3;
-        } else days_since += 1.0 / 25.0;
-    } else days_since += 1.0 / 25.0;
-    days_since = jmax(days_since, 0.3);
-    double sublimation = 0.0;
-    if (T_soil - T0C > 0.0 && Q_evap > 0.0) {
-        const double gw = Q_evap / latent_heat(T_soil);
-        sublimation = gw * 3600.0 / new_dens / 10.0;
-    }
-    const double previous_depth = step > 1 ? sc.sd_prev : st.depth;
-    double rain_melt = 0.0;
-    if (T_air - T0C >= sm.snow_temperature_threshold_C && rainfall > 0.0 && previous_depth >= sm.min_snow_depth_cm) {
-        if (midnight || hourly) {
-            const double water_depth = rainfall / WATER_RHO * 100.0;
-            rain_melt = sm.rain_melt_factor * water_depth * (T_air - T0C) * 24.0 / new_dens;
-            if (hourly) rain_melt /= 24.0;
-            rain_melt = jmax(0.0, rain_melt);
-        }
-    }
-    SnowState for_melt = st; for_melt.density = new_dens;
-    double thermal_melt;
-    if (first || previous_depth < sm.min_snow_depth_cm) {
-        snow_thermal_melt(for_melt, sc, Ts, Ts_before, P, T_soil, T_soil_before);
-        thermal_melt = 0.0;
-    } else {
-        const double raw = snow_thermal_melt(for_melt, sc, Ts, Ts_before, P, T_soil, T_soil_before);
-        thermal_melt = day_of_year > 1 ? raw * sm.snow_melt_factor : raw;
-    }
-    double cum_melt = st.cum_melt + thermal_melt;
-    if (step % 24 == 0) cum_melt = 0.0;
-    const double carried = st.extra / new_dens / 10.0;
-    const double net_acc = jmax(0.0, snowfall - sublimation) + carried;
-    double extra = 0.0;
-    double new_depth = jmax(0.0, previous_depth + net_acc - rain_melt - thermal_melt);
-    if (new_depth < sm.min_snow_depth_cm && (step <= 1 || sc.sd_prev < 1e-8)) { extra = new_depth * new_dens * 10.0; new_depth = 0.0; }
-    sc.sd_cur = new_depth;
-    double age;
-    if (first) age = 0.0;
-    else if (sc.sd_cur > 0.0 && sc.sd_prev > 0.0) age = st.age + 1.0 / 25.0;
-    else age = 0.0;
-    st.depth = new_depth; st.age = age; st.days_since = days_since; st.density = new_dens; st.prev_density = new_dens;
-    st.cum_melt = cum_melt; st.extra = extra;
-    SnowUpdateOut o; o.snowfall = snowfall; o.thermal_melt = thermal_melt; o.rain_melt = rain_melt;
-    return o;
-}
-MC_DEV_NOINLINE void adjust_snow_near_nodes(SnowState& st, SnowScratch& sc, int64_t step)
-{
-    const mc_snow_desc& sm = MC_CONST_MODEL.snow;
-    double snowout = sc.sd_cur;
-    double threshold = sm.node_thresholds_cm[(st.active > 1 ? st.active : 1) - 1];
-    double extra = st.extra;
-    if (step > 1 && snowout > 0.0) {
-        if ((snowout - threshold < 0.5) && (snowout <= sc.sd_prev)) {
-            extra += (snowout - threshold) * st.density * 10.0;
-            sc.sd_cur = jmax(0.0, threshold - 0.1);
-        }
-    }
-    st.extra = extra;
-    activate_snow_nodes(st, sc, sc.sd_cur);
-    snowout = sc.sd_cur;
-    if (snowout > 0.0) {
-        threshold = sm.node_thresholds_cm[(st.active > 1 ? st.active : 1) - 1];
-        if (snowout < sm.min_snow_depth_cm + 0.5 || snowout < threshold + 0.5) {
-            extra = 0.5 * st.density * 10.0;
-            sc.sd_cur = threshold + 0.5;
-        }
-    }
-    st.extra = extra; st.depth = sc.sd_cur;
-}
-/* surface_convection_evaporation with its default zenith of 90 degrees (neutral branch), as the snow block calls it (simulation.jl:660-671) */
-MC_DEV_NOINLINE double neutral_surface_evaporation(double T_surf, double T_air, double wind, double rh, double P, double z0, double lz, double wetness)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const double dT = T_air - T_surf;
-    const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
-    const double ustar = jmax(m.kappa * wind / lz, 1.0e-6);
-    const double Qc = convective_flux(rho_cp, dT, ustar, 0.64 / lz, sublayer_stanton(z0, ustar));
-    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = T_surf < T_LO ? T_LO : T_surf;
-    return (wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
-}
-
-/* soil_energy_balance in its general form (snow nodes on top, first active node j, co-located nodes), heat_transport_1d.jl:137-302.
- * hs.cap holds rho*c of the soil nodes (volumetric); depths change hourly with the snowpack. */
-template <int NA>
-MC_DEV_NOINLINE void soil_rhs_snow(const HourSoil<NA>& hs, const HourPar& hp, const double* __restrict__ u, double t, double* __restrict__ du, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL; const SnowCtx& sn = *hp.sn; const mc_snow_desc& sm = m.snow;
-    constexpr int ns = NSN; const int N = m.N; const int M = N + ns;
-    cn.n_rhs++;
-    const double xk = t / 60.0;
-    int ik = (int)floor(xk);
-    ik = ik < 0 ? 0 : (ik > 23 ? 23 : ik);
-    const double dk = xk - (double)ik;
-#if MC_LERP_LOOP
-    double fv[7];
-    MC_ROLLED for (int k = 0; k < 7; k++) fv[k] = knot_lerp(hp.ftab[k], hp.S, ik, dk);
-    const double P = fv[0], T_air = fv[1];
-    const double wind = jmax(fv[2], 0.1);
-    const double zen = jmin(90.0, nearbyint(fv[3] * 1000.0) / 1000.0);
-    const double solar = jmax(0.0, fv[4]);
-    const double cloud = jclamp(fv[5], 0.0, 1.0);
-    const double rh = jclamp(fv[6], 0.0, 1.0);
-#else
-    const double P = knot_lerp(hp.fP, hp.S, ik, dk);
-    const double T_air = knot_lerp(hp.fT, hp.S, ik, dk);
-    const double wind = jmax(knot_lerp(hp.fwind, hp.S, ik, dk), 0.1);
-    const double zen = jmin(90.0, nearbyint(knot_lerp(hp.fzen, hp.S, ik, dk) * 1000.0) / 1000.0);
-    const double solar = jmax(0.0, knot_lerp(hp.fsolar, hp.S, ik, dk));
-    const double cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
-    const double rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
-#endif
-    double T[NA + NSN], lam[NA + NSN], vhc[NA + NSN], C[NA + NSN], G[NA + NSN];
-    MC_ROLLED for (int i = 0; i < M; i++) T[i] = jclamp(u[i], T_LO, m.T_hi);
-    const double p0p = m.P0 / P, pp0 = P / m.P0;
-    MC_ROLLED for (int i = 0; i < N; i++) {
-        lam[ns + i] = soil_conductivity(T[ns + i], P, p0p, pp0, hs.theta[i], hs.phim[i], hs.phig[i], hs.fw[i], hs.lam_m[i]);
-        vhc[ns + i] = hs.cap[i];
-    }
-    {   /* write_snow_properties!, snow_model.jl:171-208 */
-        const SnowState& st = *sn.rhs_state;
-        const double snowdens = evolve_snow_density(st);
-        if (st.depth >= sm.min_snow_depth_cm) {
-            const double cps = snow_specific_heat(snowdens, P);
-            double k;
-            if (sm.snow_conductivity > 0.0) k = sm.snow_conductivity;
-            else { const double r = snowdens * 1000.0; k = 0.00395 + 0.00084 * r - 1.7756e-6 * (r * r) + 3.80635e-9 * (r * r * r); }
-            MC_ROLLED for (int i = 0; i < ns; i++) {
-                lam[i] = k;
-                const double cpi = apparent_heat_capacity(T[i], cps);
-                const int nx = i + 1 < ns - 1 ? i + 1 : ns - 1;
-                const bool active = sn.sc.node_depths[i] > 0.0 || (i < ns - 1 && sn.sc.node_depths[nx] > 0.0);
-                vhc[i] = (active ? snowdens * 1000.0 : 0.0) * cpi;
-            }
-        } else {
-            /* snow nodes take the first soil node's conductivity and specific heat with zero density: rho*c = 0 */
-            MC_ROLLED for (int i = 0; i < ns; i++) { lam[i] = lam[ns]; vhc[i] = 0.0; }
-        }
-    }
-    const double* ld = sn.depths;                     /* ld[M] = 0 sentinel */
-    MC_ROLLED for (int i = 0; i < M; i++) {
-        if (i == 0) {
-            const double d2 = ld[1];
-            C[0] = vhc[0] * d2 / 2.0;
-            G[0] = d2 == 0.0 ? 0.0 : lam[0] / d2;
-        } else {
-            const double dd = ld[i + 1] - ld[i];
-            if (i < ns && ld[i] == 0.0 && ld[i + 1] != 0.0) C[i] = vhc[i] * ld[i + 1];
-            else C[i] = vhc[i] * (ld[i + 1] - ld[i - 1]) / 2.0;
-            const double pdd = ld[i] - ld[i - 1];
-            G[i] = dd == 0.0 ? (pdd == 0.0 ? 0.0 : lam[i] / pdd) : lam[i] / dd;
-        }
-    }
-    int j = 0; while (j < M - 1 && C[j] == 0.0) j++;
-    double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
-    if (hp.slope > 0.0 && zen < 90.0) {
-        const double szen = jmin(90.0, knot_lerp(hp.fszen, hp.S, ik, dk));
-        const double fd = jclamp(knot_lerp(hp.fdiff, hp.S, ik, dk), 0.0, 1.0);
-        const double cz = mcm::cos(zen * PI_D / 180.0), csz = mcm::cos(szen * PI_D / 180.0);
-        Q_solar = jmax(0.0, (((1.0 - fd) * Q_solar) / cz) * csz) + (fd * Q_solar) * hp.svf;
-    }
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double atm = atmospheric_radiation(wa.vapour_pressure, T_air);
-    const double cloud_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air - 2.0);
-    const double hill_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air);
-    const double lw_sky = (atm * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - hp.shade);
-    const double incoming = (lw_sky + hp.shade * hill_rad) * hp.svf + hill_rad * (1.0 - hp.svf);
-    const double Q_ir = incoming - ((1.0 - hp.shade) * m.sigma * hp.eps_surf) * mcm::pow4(T[j]) - hp.shade * hill_rad;
-    const double cond_ref = (t == 0.0 && j > 0) ? T[0] : T[j];
-    const double Q_cond = j < M - 1 ? G[j] * (T[j + 1] - cond_ref) : 0.0;
-    double Ts = T[j];
-    if (fabs(Ts - T0C) > 100.0) Ts = T_air + 1.0;
-    if (Ts == T_air) Ts = Ts + 0.1;
-    const double dT = T_air - Ts;
-    const double rho_cp = calc_rho_cp((Ts + T_air) / 2.0);
-    double Qc;
-    if (T_air >= Ts || zen >= 90.0) {
-        const double ustar = jmax(m.kappa * wind / hp.lz, 1.0e-6);
-        Qc = convective_flux(rho_cp, dT, ustar, 0.64 / hp.lz, sublayer_stanton(hp.z0, ustar));
-    } else {
-        const Obukhov o = calc_obukhov(wind, hp.z0, m.zref, hp.lz, dT, rho_cp, hp.L_prev >= 0.0 ? -0.3 : hp.L_prev);
-        cn.n_obukhov += o.iters;
-        Qc = o.Q;
-    }
-    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = Ts < T_LO ? T_LO : Ts;
-    const double Qe = (hp.soil_wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
-    const double surf = 60.0 * (Q_solar + Q_ir + Q_cond + Qc + sn.Q_freeze - Qe) / C[j];
-    MC_ROLLED for (int i = 0; i < M; i++) {
-        if (i <= j) du[i] = surf;
-        else if (i == M - 1) du[i] = 0.0;
-        else du[i] = C[i] == 0.0 ? 0.0 : 60.0 * (G[i - 1] * (T[i - 1] - T[i]) + G[i] * (T[i + 1] - T[i])) / C[i];
-    }
-}
-
-template <int NA, int NS>
-MC_DEV void rhs_dispatch(const HourSoil<NA>& hs, const HourPar& hp, const double* u, double t, double* du, Counters& cn)
-{
-    if (NS == 0) soil_rhs<NA>(hs, hp, u, t, du, cn);
-    else soil_rhs_snow<NA>(hs, hp, u, t, du, cn);
-}
-
-/* ------------------------------------------------------------------------------------------
- * Adaptive Tsit5 with OrdinaryDiffEq's PI controller (third-party arithmetic restated; see the
- * oracle header for provenance).  Integrator state lives in thread-local arrays.
- * ------------------------------------------------------------------------------------------ */
-namespace tsit5 {
-constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
-constexpr double a21 = 0.161;
-constexpr double a31 = -0.008480655492356989, a32 = 0.335480655492357;
-constexpr double a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815;
-constexpr double a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365, a54 = -0.09249506636175525;
-constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.159367898576159, a64 = -0.071584973281401, a65 = -0.028269050394068383;
-constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996, a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
-constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469, bt3 = 0.007880878010261995,
-                 bt4 = -0.1447110071732629, bt5 = 0.5823571654525552, bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
-}
-
-/* FastPower.fastpower(x, y): Float32 log2 rational fit + exp2, as the PI controller uses it */
-MC_DEV float fastlog2f(float x)
-{
-    union { float f; uint32_t u; } v; v.f = x;
-    const uint32_t ux = v.u;
-    const uint32_t ex = (ux & 0x7F800000u) >> 23;
-    float signif, fexp;
-    if (ux & 0x00400000u) { v.u = (ux & 0x007FFFFFu) | 0x3f000000u; signif = v.f; fexp = (float)ex - 126.0f; }
-    else                  { v.u = (ux & 0x007FFFFFu) | 0x3f800000u; signif = v.f; fexp = (float)ex - 127.0f; }
-    signif = signif - 1.0f;
-#if defined(__CUDACC__)
-    return __fadd_rn(fexp, __fdiv_rn(__fmul_rn(signif, __fadd_rn(__fmul_rn(0.338953f, signif), 2.198599f)), __fadd_rn(signif, 1.523692f)));
-#else
-    return fexp + signif * (0.338953f * signif + 2.198599f) / (signif + 1.523692f);
-#endif
-}
-MC_DEV double fastpow(double x, double y)
-{
-#if defined(__CUDACC__)
-    const float l = __fmul_rn(fastlog2f((float)x), (float)y);
-#else
-    const float l = fastlog2f((float)x) * (float)y;
-#endif
-    return (double)(float)mcm::exp2((double)l);
-}
-
-template <int NA>
-struct Integ {
-    double u[NA], uprev[NA], k1[NA], k2[NA], k3[NA], k4[NA], k5[NA], k6[NA], k7[NA], tmp[NA];
-    double t, dt, dtpropose, qold, q11, tstop;
-    int iter, flags; bool accept, u_modified;
-};
-
-MC_DEV double rms_scaled(const double* x, const double* sk, int n) { double s = 0.0; MC_ROLLED for (int i = 0; i < n; i++) { const double q = x[i] / sk[i]; s += q * q; } return sqrt(s / n); }
-
-/* Hairer-Wanner automatic initial step (OrdinaryDiffEqCore initdt.jl), order 5 */
-template <int NA, int NS>
-MC_DEV_NOINLINE double determine_initdt(Integ<NA + NS>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N + NS;       /* ODE size */
-    double* sk = I.tmp; double* f0 = I.k2; double* f1 = I.k3; double* u1 = I.k4;
-    double s0 = 0.0;
-    MC_ROLLED for (int i = 0; i < N; i++) { sk[i] = m.abstol + fabs(I.u[i]) * m.reltol; const double q = I.u[i] / sk[i]; s0 += q * q; }
-    const double d0 = sqrt(s0 / N);
-    rhs_dispatch<NA, NS>(hs, hp, I.u, I.t, f0, cn);
-    bool finite = true;
-    MC_ROLLED for (int i = 0; i < N; i++) if (!isfinite(f0[i])) finite = false;
-    if (!finite) return 1e-12;
-    const double d1 = rms_scaled(f0, sk, N);
-    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
-    dt0 = fmin(dt0, 1440.0);
-    MC_ROLLED for (int i = 0; i < N; i++) u1[i] = I.u[i] + dt0 * f0[i];
-    rhs_dispatch<NA, NS>(hs, hp, u1, I.t + dt0, f1, cn);
-    double s2 = 0.0;
-    MC_ROLLED for (int i = 0; i < N; i++) { const double q = (f1[i] - f0[i]) / sk[i]; s2 += q * q; }
-    const double d2 = sqrt(s2 / N) / dt0;
-    const double md = fmax(d1, d2);
-    double dt1;
-    if (md <= 1e-15) dt1 = fmax(1e-6, dt0 * 1e-3);
-    else dt1 = mcm::exp10(-(2.0 + mcm::log10(md)) / 5.0);
-    return fmin(fmin(100.0 * dt0, dt1), 1440.0);
-}
-
-/* one accepted step: loopheader!/perform_step!/loopfooter! until accepted */
-template <int NA, int NS>
-MC_DEV_NOINLINE void tsit5_step(Integ<NA + NS>& I, const HourSoil<NA>& hs, const HourPar& hp, Counters& cn)
-{
-    using namespace tsit5;
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N + NS;       /* ODE size */
-    int guard = 0;
-    for (;;) {
-        if (I.iter > 0) {
-            if (!I.accept) {
-                I.dt = I.dt / fmin(5.0, I.q11 / 0.9);
-            } else {
-                MC_UNROLL4 for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
-                I.dt = I.dtpropose;
-                if (I.u_modified) rhs_dispatch<NA, NS>(hs, hp, I.u, I.t, I.k1, cn);
-                else MC_UNROLL4 for (int i = 0; i < N; i++) I.k1[i] = I.k7[i];
-            }
-        } else if (I.u_modified) {
-            MC_UNROLL4 for (int i = 0; i < N; i++) I.uprev[i] = I.u[i];
-        }
-        I.iter++;
-        I.dt = fmin(1440.0, I.dt);
-        I.dt = fmin(I.dt, I.tstop - I.t);
-        if (!(I.dt > 1e-12) || ++guard > 100000) {
-            I.flags |= (I.dt != I.dt) ? MC_STATUS_NAN : (guard > 100000 ? MC_STATUS_STEP_LIMIT : MC_STATUS_DT_UNDERFLOW);
-            I.t = I.tstop; I.accept = true; I.dtpropose = 1.0;
-            MC_UNROLL4 for (int i = 0; i < N; i++) I.k7[i] = I.k1[i];
-            return;
-        }
-        const double t = I.t, dt = I.dt;
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * a21 * I.k1[i];
-        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c1 * dt, I.k2, cn);
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a31 * I.k1[i] + a32 * I.k2[i]);
-        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c2 * dt, I.k3, cn);
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a41 * I.k1[i] + a42 * I.k2[i] + a43 * I.k3[i]);
-        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c3 * dt, I.k4, cn);
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a51 * I.k1[i] + a52 * I.k2[i] + a53 * I.k3[i] + a54 * I.k4[i]);
-        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + c4 * dt, I.k5, cn);
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.tmp[i] = I.uprev[i] + dt * (a61 * I.k1[i] + a62 * I.k2[i] + a63 * I.k3[i] + a64 * I.k4[i] + a65 * I.k5[i]);
-        rhs_dispatch<NA, NS>(hs, hp, I.tmp, t + dt, I.k6, cn);
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.u[i] = I.uprev[i] + dt * (a71 * I.k1[i] + a72 * I.k2[i] + a73 * I.k3[i] + a74 * I.k4[i] + a75 * I.k5[i] + a76 * I.k6[i]);
-        rhs_dispatch<NA, NS>(hs, hp, I.u, t + dt, I.k7, cn);
-        double ss = 0.0;
-        MC_UNROLL4 for (int i = 0; i < N; i++) {
-            const double ut = dt * (bt1 * I.k1[i] + bt2 * I.k2[i] + bt3 * I.k3[i] + bt4 * I.k4[i] + bt5 * I.k5[i] + bt6 * I.k6[i] + bt7 * I.k7[i]);
-            const double q = ut / (m.abstol + fmax(fabs(I.uprev[i]), fabs(I.u[i])) * m.reltol);
-            ss += q * q;
-        }
-        const double EEst = sqrt(ss / N);
-        I.u_modified = false;
-        double q;
-        if (EEst == 0.0) q = 0.1;
-        else {
-            I.q11 = fastpow(EEst, 7.0 / 50.0);
-            q = I.q11 / fastpow(I.qold, 2.0 / 25.0);
-            q = fmax(0.1, fmin(5.0, q / 0.9));
-        }
-        I.accept = EEst <= 1.0;
-        if (EEst != EEst) { I.flags |= MC_STATUS_NAN; I.accept = true; q = 1.0; }
-        if (I.accept) {
-            cn.n_accept++;
-            I.qold = fmax(EEst, 1e-4);
-            const double dtnew = I.dt / q;
-            double ttmp = I.t + I.dt;
-            if (fabs(ttmp - I.tstop) < 100.0 * 2.220446049250313e-16 * fmax(I.t, I.tstop)) ttmp = I.tstop;
-            I.t = ttmp;
-            I.dtpropose = fmin(1440.0, dtnew);
-            return;
-        }
-        cn.n_reject++;
-        MC_UNROLL4 for (int i = 0; i < N; i++) I.u[i] = I.uprev[i];
-    }
-}
-
-
-/* ==========================================================================================================================
- * Block-cooperative ODE phase (NoSnow).  Every thread still OWNS one site, but the node loops of the ODE hour — above all the
- * Campbell-de Vries conductivity of every node at every RHS evaluation (3 Goff-Gratch evaluations + pow + de Vries weights,
- * ~1.5 k instructions) — are served by the WHOLE BLOCK over a flat list of (site, node) items of the sites that currently need an
- * RHS evaluation.  Sites that have already reached the hour boundary no longer idle their lanes: they serve items of the sites
- * still stepping, and every warp of the block shares one short instruction window.  The integrator is the SAME arithmetic as
- * tsit5_step / determine_initdt above, written as a resumable state machine (protothread style): each yield publishes an RHS request
- * and returns; the next call resumes right after it.
- * ========================================================================================================================== */
-#ifndef MC_COOP_TB
-#define MC_COOP_TB 1024     /* one block per SM: every warp of the SM is in the same phase (measured 128 / 256 / 512 / 1024 threads: 135 / 148 / 156 / 163 k site-days/s) */
-#endif
-constexpr int COOP_TB = MC_COOP_TB;
-
-struct RhsCtx { double P, T_air, wind, zen, solar, cloud, rh, szen, fd; };
-
-/* ==========================================================================================================================
- * The integrator's vectors (k1..k7, u, uprev) live in the block's scratch instead of thread-local memory and EVERY node loop of
- * the ODE hour is an item pass over (requesting site, node):
- *
- *     owners : resume the Tsit5 state machine -> publish (stage, dt, pressure terms)                                   | barrier
- *     pass 1 : stage vector x = uprev + dt * sum(a_sj k_j)  ->  clamped T  ->  Campbell-de Vries conductivity          | barrier
- *     pass 2 : conduction du_i of nodes 1..N-1 (+ the error-estimate term of stage 7); owners: surface energy balance   | barrier
- *
- * Only scalar control (step-size controller, in-order error sum) and the surface energy balance remain per-site work.  The copies
- * uprev <- u and k1 <- k7 of an accepted step become role swaps of two pairs of physical arrays (uswap / kswap), done lazily at
- * the next loop header exactly where OrdinaryDiffEq copies.  Every floating-point operation and every summation order is that of
- * tsit5_step / determine_initdt / soil_rhs above.
- * ========================================================================================================================== */
-enum { PK_A = 0, PK_2, PK_3, PK_4, PK_5, PK_6, PK_B, PU_A, PU_B, P_T, P_LAM, P_Q, P_TH, P_PM, P_PG, P_FW, P_LM, P_CAP, P_ARRAYS };
-enum { ST_NONE = 0, ST_INIT_F0, ST_INIT_F1, ST_REFRESH, ST_2, ST_3, ST_4, ST_5, ST_6, ST_7 };
-
-struct Coop2Shared {
-    int list[COOP_TB]; int count[2]; int clampflag[COOP_TB];
-    double P[COOP_TB], p0p[COOP_TB], pp0[COOP_TB], dt[COOP_TB];
-    unsigned char code[COOP_TB];        /* stage | kswap << 4 | uswap << 5 */
-};
-
-struct Own2 {                           /* what the owner keeps of its integrator */
-    double t, dt, dtpropose, qold, q11, tstop, target, w0, w1, w2, st_t, st_dt, req_t, q0;
-    int st, guard, iter, flags, stage, par;
-    bool accept, u_modified, need_initdt, u_stale, kswap, uswap;
-    MC_MEMBER int k1arr() const { return kswap ? PK_B : PK_A; }
-    MC_MEMBER int k7arr() const { return kswap ? PK_A : PK_B; }
-    MC_MEMBER int uarr() const { return uswap ? PU_B : PU_A; }
-    MC_MEMBER int uparr() const { return uswap ? PU_A : PU_B; }
-};
-
-MC_DEV int stage_out_array(int stage, bool kswap)
-{
-    switch (stage) {
-    case ST_INIT_F0: case ST_2: return PK_2;
-    case ST_INIT_F1: case ST_3: return PK_3;
-    case ST_4: return PK_4;
-    case ST_5: return PK_5;
-    case ST_6: return PK_6;
-    case ST_7: return kswap ? PK_A : PK_B;
-    default: return kswap ? PK_B : PK_A;          /* ST_REFRESH -> k1 */
-    }
-}
-
-#define MC_SCR(arr, node, t) scr[((size_t)((arr) * NA + (node))) * MC_TB + (t)]
-
-/* pass 1, one (site o, node i) item */
-template <int NA>
-MC_DEV void coop2_item_stage(const Coop2Shared& sh, Coop2Shared& shw, double* scr, int o, int i)
-{
-    using namespace tsit5;
-    const DevModel& m = MC_CONST_MODEL;
-    const int code = sh.code[o], stage = code & 15;
-    const bool kswap = (code >> 4) & 1, uswap = (code >> 5) & 1;
-    const int K1 = kswap ? PK_B : PK_A, U = uswap ? PU_B : PU_A, UP = uswap ? PU_A : PU_B;
-    const double dt = sh.dt[o];
-    const double up = MC_SCR(UP, i, o);
-    double x;
-    switch (stage) {
-    case ST_INIT_F1: x = up + dt * MC_SCR(PK_2, i, o); break;
-    case ST_2: x = up + dt * a21 * MC_SCR(K1, i, o); break;
-    case ST_3: x = up + dt * (a31 * MC_SCR(K1, i, o) + a32 * MC_SCR(PK_2, i, o)); break;
-    case ST_4: x = up + dt * (a41 * MC_SCR(K1, i, o) + a42 * MC_SCR(PK_2, i, o) + a43 * MC_SCR(PK_3, i, o)); break;
-    case ST_5: x = up + dt * (a51 * MC_SCR(K1, i, o) + a52 * MC_SCR(PK_2, i, o) + a53 * MC_SCR(PK_3, i, o) + a54 * MC_SCR(PK_4, i, o)); break;
-    case ST_6: x = up + dt * (a61 * MC_SCR(K1, i, o) + a62 * MC_SCR(PK_2, i, o) + a63 * MC_SCR(PK_3, i, o) + a64 * MC_SCR(PK_4, i, o) + a65 * MC_SCR(PK_5, i, o)); break;
-    case ST_7:
-        x = up + dt * (a71 * MC_SCR(K1, i, o) + a72 * MC_SCR(PK_2, i, o) + a73 * MC_SCR(PK_3, i, o) + a74 * MC_SCR(PK_4, i, o) + a75 * MC_SCR(PK_5, i, o) + a76 * MC_SCR(PK_6, i, o));
-        MC_SCR(U, i, o) = x;
-        break;
-    default: x = up; break;                       /* ST_INIT_F0, ST_REFRESH: the RHS at the current state (u == uprev there) */
-    }
-    const double Tc = jclamp(x, T_LO, m.T_hi);
-    if (stage == ST_7 && Tc != x) {
-#if defined(__CUDACC__)
-        atomicOr(&shw.clampflag[o], 1);
-#else
-        shw.clampflag[o] |= 1;
-#endif
-    }
-    MC_SCR(P_T, i, o) = Tc;
-    if (i < m.N - 1)
-        MC_SCR(P_LAM, i, o) = soil_conductivity(Tc, sh.P[o], sh.p0p[o], sh.pp0[o], MC_SCR(P_TH, i, o), MC_SCR(P_PM, i, o), MC_SCR(P_PG, i, o),
-                                                MC_SCR(P_FW, i, o), MC_SCR(P_LM, i, o)) / m.dzg[i];      /* the conductance lambda / dz of the layer below node i */
-}
-
-/* the error-estimate term of one node (stage 7), given its fresh k7 */
-template <int NA>
-MC_DEV double coop2_error_term(const Coop2Shared& sh, double* scr, int o, int i, double k7)
-{
-    using namespace tsit5;
-    const DevModel& m = MC_CONST_MODEL;
-    const int code = sh.code[o];
-    const bool kswap = (code >> 4) & 1, uswap = (code >> 5) & 1;
-    const int K1 = kswap ? PK_B : PK_A, U = uswap ? PU_B : PU_A, UP = uswap ? PU_A : PU_B;
-    const double dt = sh.dt[o];
-    const double ut = dt * (bt1 * MC_SCR(K1, i, o) + bt2 * MC_SCR(PK_2, i, o) + bt3 * MC_SCR(PK_3, i, o) + bt4 * MC_SCR(PK_4, i, o) + bt5 * MC_SCR(PK_5, i, o)
-                            + bt6 * MC_SCR(PK_6, i, o) + bt7 * k7);
-    return ut / (m.abstol + fmax(fabs(MC_SCR(UP, i, o)), fabs(MC_SCR(U, i, o))) * m.reltol);
-}
-
-/* pass 2, one (site o, node i >= 1) item: conduction (heat_transport_1d.jl:192-210) */
-template <int NA>
-MC_DEV void coop2_item_conduct(const Coop2Shared& sh, double* scr, int o, int i)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int code = sh.code[o], stage = code & 15;
-    double du = 0.0;
-    if (i < m.N - 1) {
-        const double T_up = MC_SCR(P_T, i - 1, o), T_i = MC_SCR(P_T, i, o), T_dn = MC_SCR(P_T, i + 1, o);
-        const double G_up = MC_SCR(P_LAM, i - 1, o);
-        const double G_i = MC_SCR(P_LAM, i, o);
-        du = 60.0 * (G_up * (T_up - T_i) + G_i * (T_dn - T_i)) / MC_SCR(P_CAP, i, o);
-    }
-    MC_SCR(stage_out_array(stage, (code >> 4) & 1), i, o) = du;
-    if (stage == ST_7) MC_SCR(P_Q, i, o) = coop2_error_term<NA>(sh, scr, o, i, du);
-}
-
-/* owner: forcing at the stage time + pressure terms for pass 1 */
-MC_DEV void coop2_pre(const HourPar& hp, double t, RhsCtx& R, Coop2Shared& sh)
-{
-    const DevModel& m = MC_CONST_MODEL; const int tid = MC_TID;
-    const double xk = t / 60.0;
-    int ik = (int)floor(xk);
-    ik = ik < 0 ? 0 : (ik > 23 ? 23 : ik);
-    const double dk = xk - (double)ik;
-    R.P = knot_lerp(hp.fP, hp.S, ik, dk);
-    R.T_air = knot_lerp(hp.fT, hp.S, ik, dk);
-    R.wind = jmax(knot_lerp(hp.fwind, hp.S, ik, dk), 0.1);
-    R.zen = jmin(90.0, nearbyint(knot_lerp(hp.fzen, hp.S, ik, dk) * 1000.0) / 1000.0);
-    R.solar = jmax(0.0, knot_lerp(hp.fsolar, hp.S, ik, dk));
-    R.cloud = jclamp(knot_lerp(hp.fcloud, hp.S, ik, dk), 0.0, 1.0);
-    R.rh = jclamp(knot_lerp(hp.frh, hp.S, ik, dk), 0.0, 1.0);
-    R.szen = 0.0; R.fd = 0.0;
-    if (hp.slope > 0.0 && R.zen < 90.0) {
-        R.szen = jmin(90.0, knot_lerp(hp.fszen, hp.S, ik, dk));
-        R.fd = jclamp(knot_lerp(hp.fdiff, hp.S, ik, dk), 0.0, 1.0);
-    }
-    sh.P[tid] = R.P; sh.p0p[tid] = m.P0 / R.P; sh.pp0[tid] = R.P / m.P0;
-}
-
-/* owner: surface energy balance of node 0 (heat_transport_1d.jl:212-302), same arithmetic as soil_rhs */
-template <int NA>
-MC_DEV_NOINLINE double coop2_surface(const HourPar& hp, const RhsCtx& R, const double* scr, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL; const int tid = MC_TID;
-    const double P = R.P, T_air = R.T_air, wind = R.wind, zen = R.zen, solar = R.solar, cloud = R.cloud, rh = R.rh;
-    const double Ts_node = MC_SCR(P_T, 0, tid);
-    const double G_up = MC_SCR(P_LAM, 0, tid);
-    const double Q_cond = G_up * (MC_SCR(P_T, 1, tid) - Ts_node);
-    double Q_solar = (1.0 - hp.albedo) * solar * (1.0 - hp.shade);
-    if (hp.slope > 0.0 && zen < 90.0) {
-        const double cz = mcm::cos(zen * PI_D / 180.0), csz = mcm::cos(R.szen * PI_D / 180.0);
-        Q_solar = jmax(0.0, (((1.0 - R.fd) * Q_solar) / cz) * csz) + (R.fd * Q_solar) * hp.svf;
-    }
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double atm = atmospheric_radiation(wa.vapour_pressure, T_air);
-    const double cloud_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air - 2.0);
-    const double hill_rad = m.sigma * hp.eps_cloud * mcm::pow4(T_air);
-    const double lw_sky = (atm * (1.0 - cloud) + cloud_rad * cloud) * (1.0 - hp.shade);
-    const double incoming = (lw_sky + hp.shade * hill_rad) * hp.svf + hill_rad * (1.0 - hp.svf);
-    const double Q_ir = incoming - ((1.0 - hp.shade) * m.sigma * hp.eps_surf) * mcm::pow4(Ts_node) - hp.shade * hill_rad;
-    double Ts = Ts_node;
-    if (fabs(Ts - T0C) > 100.0) Ts = T_air + 1.0;
-    if (Ts == T_air) Ts = Ts + 0.1;
-    const double dT = T_air - Ts;
-    const double rho_cp = calc_rho_cp((Ts + T_air) / 2.0);
-    double Qc;
-    if (T_air >= Ts || zen >= 90.0) {
-        const double ustar = jmax(m.kappa * wind / hp.lz, 1.0e-6);
-        Qc = convective_flux(rho_cp, dT, ustar, 0.64 / hp.lz, sublayer_stanton(hp.z0, ustar));
-    } else {
-        const Obukhov o = calc_obukhov(wind, hp.z0, m.zref, hp.lz, dT, rho_cp, hp.L_prev >= 0.0 ? -0.3 : hp.L_prev);
-        cn.n_obukhov += o.iters;
-        Qc = o.Q;
-    }
-    const double hc = dT == 0.0 ? 0.5 : jmax(fabs(Qc / dT), 0.5);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = Ts < T_LO ? T_LO : Ts;
-    const double Qe = (hp.soil_wetness * hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);
-    return 60.0 * (Q_solar + Q_ir + Q_cond + Qc + 0.0 - Qe) / MC_SCR(P_CAP, 0, tid);
-}
-
-#define MC_YIELD2(label, stg, tt) do { I.st = (label); I.stage = (stg); I.req_t = (tt); return true; case (label):; } while (0)
-
-/* Resumable adaptive integration to I.target (see coop_advance): returns true with the next stage published in (stage, req_t). */
-template <int NA>
-MC_DEV_NOINLINE bool coop2_advance(Own2& I, Coop2Shared& sh, double* scr, Counters& cn)
-{
-    using namespace tsit5;
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N; const int tid = MC_TID;
-    switch (I.st) {
-    case 0:
-        if (I.need_initdt) {                                             /* Hairer-Wanner initial step: two RHS evaluations */
-            I.need_initdt = false;
-            { double s0 = 0.0; const int UP = I.uparr();
-              MC_ROLLED for (int i = 0; i < N; i++) { const double ui = MC_SCR(UP, i, tid); const double sk = m.abstol + fabs(ui) * m.reltol; const double q = ui / sk; s0 += q * q; }
-              I.w0 = sqrt(s0 / N); }
-            MC_YIELD2(1, ST_INIT_F0, I.t);
-            { bool finite = true;
-              MC_ROLLED for (int i = 0; i < N; i++) if (!isfinite(MC_SCR(PK_2, i, tid))) finite = false;
-              if (!finite) { I.dt = 1e-12; goto initdt_done; } }
-            { double s1 = 0.0; const int UP = I.uparr();
-              MC_ROLLED for (int i = 0; i < N; i++) { const double sk = m.abstol + fabs(MC_SCR(UP, i, tid)) * m.reltol; const double q = MC_SCR(PK_2, i, tid) / sk; s1 += q * q; }
-              I.w1 = sqrt(s1 / N); }
-            I.w2 = (I.w0 < 1e-5 || I.w1 < 1e-5) ? 1e-6 : (I.w0 / I.w1) / 100.0;
-            I.w2 = fmin(I.w2, 1440.0);
-            sh.dt[tid] = I.w2;
-            MC_YIELD2(2, ST_INIT_F1, I.t + I.w2);
-            { double s2 = 0.0; const int UP = I.uparr();
-              MC_ROLLED for (int i = 0; i < N; i++) { const double sk = m.abstol + fabs(MC_SCR(UP, i, tid)) * m.reltol; const double q = (MC_SCR(PK_3, i, tid) - MC_SCR(PK_2, i, tid)) / sk; s2 += q * q; }
-              const double d2 = sqrt(s2 / N) / I.w2;
-              const double md = fmax(I.w1, d2);
-              double dt1;
-              if (md <= 1e-15) dt1 = fmax(1e-6, I.w2 * 1e-3);
-              else dt1 = mcm::exp10(-(2.0 + mcm::log10(md)) / 5.0);
-              I.dt = fmin(fmin(100.0 * I.w2, dt1), 1440.0); }
-        initdt_done:;
-        }
-        while (I.t < I.target - 1e-10) {                                 /* step_to_hour! */
-            I.guard = 0;
-            for (;;) {                                                   /* one accepted step */
-                if (I.iter > 0) {
-                    if (!I.accept) {
-                        I.dt = I.dt / fmin(5.0, I.q11 / 0.9);
-                    } else {
-                        I.uswap = !I.uswap; I.u_stale = true;            /* uprev <- u */
-                        I.dt = I.dtpropose;
-                        if (I.u_modified) { MC_YIELD2(3, ST_REFRESH, I.t); }
-                        else I.kswap = !I.kswap;                          /* k1 <- k7 (FSAL) */
-                    }
-                } else if (I.u_modified) {
-                    const int U = I.uarr(), UP = I.uparr();
-                    MC_ROLLED for (int i = 0; i < N; i++) MC_SCR(UP, i, tid) = MC_SCR(U, i, tid);
-                }
-                I.iter++;
-                I.dt = fmin(1440.0, I.dt);
-                I.dt = fmin(I.dt, I.tstop - I.t);
-                if (!(I.dt > 1e-12) || ++I.guard > 100000) {
-                    I.flags |= (I.dt != I.dt) ? MC_STATUS_NAN : (I.guard > 100000 ? MC_STATUS_STEP_LIMIT : MC_STATUS_DT_UNDERFLOW);
-                    I.t = I.tstop; I.accept = true; I.dtpropose = 1.0;
-                    const int K1 = I.k1arr(), K7 = I.k7arr(), U = I.uarr(), UP = I.uparr();
-                    MC_ROLLED for (int i = 0; i < N; i++) MC_SCR(K7, i, tid) = MC_SCR(K1, i, tid);
-                    if (I.u_stale) { MC_ROLLED for (int i = 0; i < N; i++) MC_SCR(U, i, tid) = MC_SCR(UP, i, tid); I.u_stale = false; }
-                    sh.clampflag[tid] = 1;                               /* force the exact check below */
-                    break;
-                }
-                I.st_t = I.t; I.st_dt = I.dt;
-                sh.dt[tid] = I.st_dt;
-                MC_YIELD2(4, ST_2, I.st_t + c1 * I.st_dt);
-                MC_YIELD2(5, ST_3, I.st_t + c2 * I.st_dt);
-                MC_YIELD2(6, ST_4, I.st_t + c3 * I.st_dt);
-                MC_YIELD2(7, ST_5, I.st_t + c4 * I.st_dt);
-                MC_YIELD2(8, ST_6, I.st_t + I.st_dt);
-                sh.clampflag[tid] = 0;
-                MC_YIELD2(9, ST_7, I.st_t + I.st_dt);
-                {
-                    double ss = 0.0;
-                    ss += I.q0 * I.q0;
-                    MC_ROLLED for (int i0 = 1; i0 < N; i0 += 6) {      /* in-order sum; the loads of a batch are issued together */
-                        double qv[6];
-                        _Pragma("unroll") for (int k = 0; k < 6; k++) qv[k] = i0 + k < N ? MC_SCR(P_Q, i0 + k, tid) : 0.0;
-                        _Pragma("unroll") for (int k = 0; k < 6; k++) if (i0 + k < N) ss += qv[k] * qv[k];
-                    }
-                    const double EEst = sqrt(ss / N);
-                    I.u_modified = false;
-                    double q;
-                    if (EEst == 0.0) q = 0.1;
-                    else {
-                        I.q11 = fastpow(EEst, 7.0 / 50.0);
-                        q = I.q11 / fastpow(I.qold, 2.0 / 25.0);
-                        q = fmax(0.1, fmin(5.0, q / 0.9));
-                    }
-                    I.accept = EEst <= 1.0;
-                    if (EEst != EEst) { I.flags |= MC_STATUS_NAN; I.accept = true; q = 1.0; }
-                    if (I.accept) {
-                        cn.n_accept++;
-                        I.qold = fmax(EEst, 1e-4);
-                        const double dtnew = I.dt / q;
-                        double ttmp = I.t + I.dt;
-                        if (fabs(ttmp - I.tstop) < 100.0 * 2.220446049250313e-16 * fmax(I.t, I.tstop)) ttmp = I.tstop;
-                        I.t = ttmp;
-                        I.dtpropose = fmin(1440.0, dtnew);
-                        I.u_stale = false;
-                        break;
-                    }
-                    cn.n_reject++;
-                    I.u_stale = true;                                     /* u <- uprev: the array of u now holds the rejected proposal */
-                }
-            }
-            if (sh.clampflag[tid]) {   /* re-clamp the state after every internal step (simulation.jl:891-900); pass 1 flags candidates */
-                const int U = I.uarr(), UP = I.uparr();
-                bool changed = false;
-                MC_ROLLED for (int k = 0; k < N; k++) { const double v = MC_SCR(U, k, tid); const double c = jclamp(v, T_LO, m.T_hi); if (c != v) { MC_SCR(U, k, tid) = c; changed = true; } }
-                if (changed) { MC_ROLLED for (int k = 0; k < N; k++) MC_SCR(UP, k, tid) = MC_SCR(U, k, tid); I.u_modified = true; }
-            }
-        }
-        I.st = 0; I.stage = ST_NONE;
-        return false;
-    case 10:                                                             /* one-shot RHS (prototype evaluation of init()) */
-        I.st = 0; I.stage = ST_NONE;
-        return false;
-    }
-    return false;
-}
-
-/* Drive every site of the block through the RHS evaluations its state machine requests until all have reached their target. */
-template <int NA>
-MC_DEV void coop2_rounds(Own2& I, bool pending, const HourPar& hp, Coop2Shared& sh, double* scr, Counters& cn)
-{
-    RhsCtx R;
-    const DevModel& m = MC_CONST_MODEL; const int N = m.N;
-    const int tid = MC_TID, TB = MC_TB;
-    int par = I.par;     /* list-counter parity: block-uniform, carried across calls (the counter a round leaves non-zero is cleared by the next) */
-    for (;;) {
-        if (pending) {
-            coop2_pre(hp, I.req_t, R, sh);
-            sh.code[tid] = (unsigned char)(I.stage | (I.kswap ? 16 : 0) | (I.uswap ? 32 : 0));
-        }
-#if defined(__CUDACC__)
-        {   /* append the requesting sites to the round's list: one shared atomic per warp */
-            const unsigned bal = __ballot_sync(0xffffffffu, pending);
-            const int lane = tid & 31;
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&sh.count[par], __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pending) sh.list[base + __popc(bal & ((1u << lane) - 1u))] = tid;
-        }
-        __syncthreads();
-        const int A = sh.count[par];
-        if (tid == 0) sh.count[par ^ 1] = 0;
-#else
-        const int A = pending ? 1 : 0;
-        sh.list[0] = tid;
-#endif
-        if (A == 0) break;                        /* parity stays: count[par] is still zero for the next call */
-        /* item j = node * A + (index into the list); j / A by multiplication (exact for j < 2^20, A <= 1024) */
-        const unsigned long long magic = (0x100000000ull + (unsigned)A - 1ull) / (unsigned)A;
-        {   /* pass 1: stage vector, clamp, conductivity */
-            const int total = A * N;
-            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); coop2_item_stage<NA>(sh, sh, scr, sh.list[j - node * A], node); }
-        }
-        MC_BLOCK_SYNC();
-        {   /* pass 2: conduction of nodes 1..N-1 */
-            const int total = A * (N - 1);
-            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); coop2_item_conduct<NA>(sh, scr, sh.list[j - node * A], node + 1); }
-        }
-        if (pending) {
-            cn.n_rhs++;
-            const double du0 = coop2_surface<NA>(hp, R, scr, cn);
-            MC_SCR(stage_out_array(I.stage, I.kswap), 0, tid) = du0;
-            if (I.stage == ST_7) I.q0 = coop2_error_term<NA>(sh, scr, tid, 0, du0);
-        }
-        MC_BLOCK_SYNC();
-        if (pending) pending = coop2_advance<NA>(I, sh, scr, cn);
-        par ^= 1;
-    }
-    I.par = par;
-}
-
-/* ------------------------------------------------------------------------------------------
- * phase_transition!(::PhaseTransitionLatentHeat), latent_heat.jl:21-112 (sequential over nodes)
- * ------------------------------------------------------------------------------------------ */
-MC_DEV_NOINLINE void phase_transition(int N, const double* depths, double* T, const double* Tpast, double* sum_phase, const double* theta)
-{
-    const double tol = 1.0e-4;
-    MC_ROLLED for (int i = 0; i < N; i++) {
-        double mean, mean_past;
-        if (i < N - 1) { mean = 0.5 * (T[i] + T[i + 1]); mean_past = 0.5 * (Tpast[i] + Tpast[i + 1]); }
-        else { mean = T[i]; mean_past = Tpast[i]; }
-        double mass = 0.0;
-        if (theta[i] > 0.0) mass = (i < N - 1 ? (depths[i + 1] - depths[i]) : ((depths[i] + 1.0) - depths[i])) * 1000.0 * theta[i];
-        if (theta[i] <= 0.0 || mass <= 0.0) { sum_phase[i] = 0.0; continue; }
-        const double max_latent = LATENT_FUSION * mass;
-        if ((mean_past - T0C > tol) && (mean - T0C <= -tol)) {
-            sum_phase[i] += (mean_past - mean) * mass * WATER_CP;
-            if (sum_phase[i] >= max_latent) sum_phase[i] = max_latent;
-            T[i] = T0C; if (i < N - 1) T[i + 1] = T0C;
-        } else if ((mean_past - T0C < -tol) && (mean - T0C >= tol)) {
-            sum_phase[i] -= (mean - mean_past) * mass * WATER_CP;
-            if (sum_phase[i] <= 0.0) sum_phase[i] = 0.0;
-            else { T[i] = T0C; if (i < N - 1) T[i + 1] = T0C; }
-        }
-    }
-}
-
-/* ------------------------------------------------------------------------------------------
- * Campbell (1985) water balance.  Arrays use the reference's 1-based buffer indices
- * (buffer node i <-> soil node i-1; entry 0 unused), campbell.jl:129-361.
- * ------------------------------------------------------------------------------------------ */
-/* Stomatal Newton for the leaf water potential (campbell.jl:270-284): iterate until |residual| <= 10 J/kg or moisture_max_iterations.
- * The update is a function of psi_leaf alone (everything else is constant within the sub-step), so as soon as a value repeats, the
- * remaining iterations are periodic and the value after the last one follows from the period.  On the benchmark grid 10 % of the
- * sub-steps never meet the exit test and the reference runs all 500 iterations; 99.97 % of those orbits have period 1 or 2 (compared
- * directly) or a longer period found by Brent's cycle detection within a few iterations.  The skipped iterations are exactly the ones
- * that would reproduce already-visited values, so the result is bit-identical to running them (the oracle does run them). */
-MC_DEV_NOINLINE double stomatal_newton(double psi_leaf, double psi_bar, double R_bar, double TP)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const double RL = m.RL, PC = m.PC, SP = m.SP;
-    const double qnan = (double)NAN;                                       /* never equal to anything */
-    double prev1 = qnan, prev2 = qnan, tort = qnan;
-    int counter = 0, lam = 0, power = 1;
-    bool detect = true;
-    while (counter < m.moist_max_it) {
-        if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
-        const double xp = mcm::pow(psi_leaf / PC, SP);
-        const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
-        const double resid = psi_bar - psi_leaf - TP * (R_bar + RL) / (1.0 + xp);
-        psi_leaf = psi_leaf - resid / slope;
-        counter++;
-        if (fabs(resid) <= 10.0) break;
-        if (detect) {
-            int period = 0;
-            if (psi_leaf == prev1) period = 1;
-            else if (psi_leaf == prev2) period = 2;
-            else if (psi_leaf == tort) period = lam + 1;
-            if (period) { counter = m.moist_max_it - (m.moist_max_it - counter) % period; detect = false; }     /* skip whole periods */
-            else { prev2 = prev1; prev1 = psi_leaf; if (++lam == power) { tort = psi_leaf; power <<= 1; lam = 0; } }
-        }
-    }
-    return psi_leaf;
-}
-
-template <int NA>
-struct HourMoist {              /* per-hour constants of infiltration_step! (soil T and site parameters are fixed within the hour) */
-    double psi_e[NA + 2], sat[NA + 2], bb[NA + 2], ks[NA + 2], nexp[NA + 2], mass[NA + 2], rootR[NA + 2], rootZ[NA + 2];
-    double dz[NA + 2];          /* depth[i+1]-depth[i] with depth[1]=-1e10, depth[L+1]=1e20 */
-    double kvc[NA + 2];         /* 0.66 * Dv * rho_v,sat(T_i)                                   (campbell.jl:307-309) */
-    double rts[NA + 2];         /* R * T_{i-1}                                                  (campbell.jl:224,311,330) */
-    double phi_e[NA + 2], fexp[NA + 2];   /* matric flux potential form only */
-    double rts1;                /* R * Ts[1] */
-};
-
-template <int NA>
-struct InfilWork {
-    double psi[NA + 2], K[NA + 2], h[NA + 2], wc[NA + 2], wcn[NA + 2], phi[NA + 2];
-    double jv[NA + 2], djv[NA + 2], sub[NA + 2], dia[NA + 2], sup[NA + 2], F[NA + 2], cc[NA + 2], rr[NA + 2], uptake[NA + 2], soilR[NA + 2];
-};
-
-struct InfilOut { double evaporation, surface_water_flux; bool hit_max; };
-
-template <int NA>
-MC_DEV_NOINLINE InfilOut infiltration_step(const HourMoist<NA>& hm, InfilWork<NA>& B, double* theta, double rh_loc, double lai, double ET, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    cn.n_infil++;
-    const int L = m.N;
-    const double g = m.g, dt = m.moist_dt;
-    const bool flux_alg = m.flux_alg != 0;
-    MC_ROLLED for (int i = 2; i <= L; i++) { B.wcn[i] = theta[i - 2]; B.wc[i] = theta[i - 2]; }
-    /* initial_state_from_water_content! */
-    MC_ROLLED for (int i = 2; i <= L; i++) {
-        B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
-        if (!flux_alg) B.K[i] = hm.ks[i] * mcm::pow(hm.psi_e[i] / B.psi[i], hm.nexp[i]);
-        else {
-            B.phi[i] = hm.phi_e[i] * mcm::pow(B.wcn[i] / hm.sat[i], hm.bb[i] + 3.0);
-            B.K[i] = hm.ks[i] * mcm::pow(B.phi[i] / hm.phi_e[i], hm.fexp[i]);
-        }
-        B.h[i] = mcm::exp(MW_INFIL * B.psi[i] / hm.rts[i]);
-    }
-    B.psi[L + 1] = hm.psi_e[L];
-    if (flux_alg) B.phi[L + 1] = hm.phi_e[L];
-    B.h[L + 1] = 1.0; B.wc[L + 1] = hm.sat[L + 1]; B.wcn[L + 1] = hm.sat[L + 1];
-    B.K[L + 1] = hm.ks[L];
-    B.psi[1] = B.psi[2]; B.K[1] = 0.0;
-    if (flux_alg) B.phi[1] = 0.0;     /* never written upstream: the zero-initialised buffer value */
-    const double EP = mcm::exp(-0.82 * lai) * ET;
-    const double TP = ET - EP;
-    double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
-    MC_ROLLED for (int i = 2; i <= L; i++) {
-        B.soilR[i] = hm.rootZ[i] / B.K[i];
-        const double rt = B.soilR[i] + hm.rootR[i];
-        psum += B.psi[i] / rt;
-        rsum += 1.0 / rt;
-    }
-    const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
-    const double RL = m.RL, PC = m.PC, SP = m.SP;
-    psi_leaf = stomatal_newton(psi_leaf, psi_bar, R_bar, TP);                /* campbell.jl:270-284 */
-    int counter = 0;
-    const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
-    MC_ROLLED for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
-
-    InfilOut out; out.hit_max = true;
-    counter = 0;
-    while (counter < m.moist_max_it) {                                       /* Newton loop, campbell.jl:293-336 */
-        double err = 0.0;
-        counter++; cn.n_newton++;
-        MC_ROLLED for (int i = 2; i <= L; i++) {
-            if (!flux_alg) B.K[i] = hm.ks[i] * mcm::pow(hm.psi_e[i] / B.psi[i], hm.nexp[i]);
-            else B.K[i] = hm.ks[i] * mcm::pow(B.phi[i] / hm.phi_e[i], hm.fexp[i]);
-        }
-        if (flux_alg) { MC_ROLLED for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]); B.psi[L + 1] = hm.psi_e[L]; }
-        B.jv[1] = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc);
-        B.djv[1] = EP * MW_INFIL * B.h[2] / (hm.rts1 * (1.0 - rh_loc));
-        MC_ROLLED for (int i = 2; i <= L; i++) {
-            const double kv = hm.kvc[i] * (hm.sat[i] - (B.wcn[i] + B.wcn[i + 1]) / 2.0) / hm.dz[i];
-            B.jv[i] = kv * (B.h[i + 1] - B.h[i]);
-            B.djv[i] = MW_INFIL * B.h[i] * kv / hm.rts[i];
-        }
-        MC_ROLLED for (int i = 2; i <= L; i++) {
-            if (!flux_alg) {
-                const double cap = -1.0 * hm.mass[i] * B.wcn[i] / (hm.bb[i] * B.psi[i] * dt);
-                B.sub[i] = -1.0 * B.K[i - 1] / hm.dz[i - 1] + g * hm.nexp[i] * B.K[i - 1] / B.psi[i - 1];
-                B.sup[i] = -1.0 * B.K[i + 1] / hm.dz[i];
-                B.dia[i] = B.K[i] / hm.dz[i - 1] + B.K[i] / hm.dz[i] + cap - g * hm.nexp[i] * B.K[i] / B.psi[i] + B.djv[i - 1] + B.djv[i];
-                B.F[i] = ((B.psi[i] * B.K[i] - B.psi[i - 1] * B.K[i - 1]) / hm.dz[i - 1]
-                        - (B.psi[i + 1] * B.K[i + 1] - B.psi[i] * B.K[i]) / hm.dz[i]) / (1.0 - hm.nexp[i])
-                       + hm.mass[i] * (B.wcn[i] - B.wc[i]) / dt - g * (B.K[i - 1] - B.K[i]) + B.jv[i - 1] - B.jv[i] + B.uptake[i];
-            } else {
-                const double b3 = hm.fexp[i];
-                const double cap = hm.mass[i] * B.wcn[i] / ((hm.bb[i] + 3.0) * B.phi[i] * dt);
-                B.sub[i] = -1.0 / hm.dz[i - 1] - g * b3 * B.K[i - 1] / B.phi[i - 1];
-                B.sup[i] = -1.0 / hm.dz[i];
-                B.dia[i] = 1.0 / hm.dz[i - 1] + 1.0 / hm.dz[i] + cap + g * b3 * B.K[i] / B.phi[i];
-                B.F[i] = (B.phi[i] - B.phi[i - 1]) / hm.dz[i - 1] - (B.phi[i + 1] - B.phi[i]) / hm.dz[i]
-                       + hm.mass[i] * (B.wcn[i] - B.wc[i]) / dt - g * (B.K[i - 1] - B.K[i]) + B.jv[i - 1] - B.jv[i] + B.uptake[i];
-            }
-            err += fabs(B.F[i]);
-        }
-        MC_ROLLED for (int i = 2; i <= L - 1; i++) {                                   /* thomas_forward_elimination! */
-            B.cc[i] = B.sup[i] / B.dia[i];
-            if (fabs(B.cc[i]) < 1e-8) B.cc[i] = 0.0;
-            B.rr[i] = B.F[i] / B.dia[i];
-            B.dia[i + 1] -= B.sub[i + 1] * B.cc[i];
-            B.F[i + 1] -= B.sub[i + 1] * B.rr[i];
-        }
-        if (!flux_alg) {
-            double dpsi = B.F[L] / B.dia[L];                                 /* lower boundary clamp */
-            B.psi[L] = jmin(B.psi[L] - dpsi, hm.psi_e[L]);
-            MC_ROLLED for (int i = L - 1; i >= 2; i--) {                               /* interior back-substitution + saturation averaging clamp */
-                dpsi = B.rr[i] - B.cc[i] * dpsi;
-                B.psi[i] -= dpsi;
-                if (B.psi[i] > hm.psi_e[i]) B.psi[i] = (B.psi[i] + dpsi + hm.psi_e[i]) / 2.0;
-            }
-            MC_ROLLED for (int i = 2; i <= L; i++) {                                   /* recover_water_content! */
-                B.wcn[i] = jmax(hm.sat[i] * mcm::pow(hm.psi_e[i] / B.psi[i], 1.0 / hm.bb[i]), 1e-7);
-                B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
-            }
-        } else {
-            double dphi = B.F[L] / B.dia[L];
-            B.phi[L] -= dphi;
-            if (B.phi[L] < 0.0) B.phi[L] = 1e-6; else if (B.phi[L] > hm.phi_e[L]) B.phi[L] = hm.phi_e[L];
-            MC_ROLLED for (int i = L - 1; i >= 2; i--) {
-                dphi = B.rr[i] - B.cc[i] * dphi;
-                B.phi[i] -= dphi;
-                if (B.phi[i] < 0.0) B.phi[i] = 1e-6; else if (B.phi[i] > hm.phi_e[i]) B.phi[i] = hm.phi_e[i];
-            }
-            MC_ROLLED for (int i = 2; i <= L; i++) B.wcn[i] = jmax(hm.sat[i] * mcm::pow(B.phi[i] / hm.phi_e[i], 1.0 / (hm.bb[i] + 3.0)), 1e-7);
-            MC_ROLLED for (int i = 2; i <= L; i++) B.psi[i] = hm.psi_e[i] * mcm::pow(hm.sat[i] / B.wcn[i], hm.bb[i]);
-            B.psi[L + 1] = hm.psi_e[L];
-        }
-        MC_ROLLED for (int i = 2; i <= L; i++) B.h[i] = mcm::exp(MW_INFIL * B.psi[i] / hm.rts[i]);
-        B.h[L + 1] = B.h[L];
-        if (err <= m.moist_tol) { out.hit_max = false; break; }
-    }
-    out.surface_water_flux = ((B.psi[2] * B.K[2] - B.psi[3] * B.K[3]) / ((1.0 - hm.nexp[2]) * hm.dz[2]) + g * B.K[2] + TR) * dt;
-    MC_ROLLED for (int i = 2; i <= L + 1; i++) theta[i - 2] = B.wcn[i];
-    out.evaporation = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc) * dt;
-    return out;
-}
-
-
-/* infiltration_step! for the matric-potential algorithm (the default), restructured for a GPU thread: the reference's seven
- * separate passes over the node arrays per Newton iteration (conductivity, vapour flux, assembly, Thomas forward elimination,
- * back-substitution, water-content recovery, humidity) are fused into ONE forward and ONE backward sweep that carry the
- * neighbour values in registers, so the thread-local arrays shrink from 16 to 6 and each is read/written once per sweep.
- * Every floating-point operation is the reference's, in the reference's order per node (results are bit-identical to the
- * unfused form, which the oracle keeps). */
-template <int NA>
-MC_DEV_NOINLINE InfilOut infiltration_step_psi(const HourMoist<NA>& hm, InfilWork<NA>& B, double* theta, double rh_loc, double lai, double ET, Counters& cn, bool warm)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    cn.n_infil++;
-    const int L = m.N;
-    const double g = m.g, dt = m.moist_dt;
-    const double EP = mcm::exp(-0.82 * lai) * ET;
-    const double TP = ET - EP;
-    /* initial state from water content + root/soil resistances (campbell.jl:215-267) */
-    double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
-    /* warm: B still holds the previous sub-step of this hour.  Its final state IS this sub-step's initial state (water content copied to
-     * theta, potential and humidity the same functions of it), so only a row whose theta was changed since (the wetted surface node)
-     * is rebuilt; the reference recomputes all rows to the same bits (the oracle keeps that form). */
-    MC_ROLLED for (int i = 2; i <= L; i++) {
-        const double wcn = theta[i - 2];
-        double psi;
-        if (warm && wcn == B.wcn[i]) psi = B.psi[i];
-        else {
-            psi = hm.psi_e[i] * mcm::pow(hm.sat[i] / wcn, hm.bb[i]);
-            B.wcn[i] = wcn; B.psi[i] = psi;
-            B.h[i] = mcm::exp(MW_INFIL * psi / hm.rts[i]);
-        }
-        const double K = hm.ks[i] * mcm::pow(hm.psi_e[i] / psi, hm.nexp[i]);
-        const double soilR = hm.rootZ[i] / K;
-        B.soilR[i] = soilR;
-        const double rt = soilR + hm.rootR[i];
-        psum += psi / rt;
-        rsum += 1.0 / rt;
-    }
-    B.psi[L + 1] = hm.psi_e[L]; B.h[L + 1] = 1.0; B.wcn[L + 1] = hm.sat[L + 1];
-    const double psi1 = B.psi[2];                                           /* water_potential[1] = water_potential[2], never updated again */
-    const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
-    const double RL = m.RL, PC = m.PC, SP = m.SP;
-    psi_leaf = stomatal_newton(psi_leaf, psi_bar, R_bar, TP);                /* campbell.jl:270-284 */
-    int counter = 0;
-    const double TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
-    MC_ROLLED for (int i = 2; i <= L; i++) B.uptake[i] = (B.psi[i] - psi_leaf - RL * TR) / (hm.rootR[i] + B.soilR[i]);
-
-    InfilOut out; out.hit_max = true;
-    double K2 = 0.0, K3 = 0.0;
-    counter = 0;
-    while (counter < m.moist_max_it) {                                       /* Newton loop, campbell.jl:293-336 */
-        double err = 0.0;
-        counter++; cn.n_newton++;
-        /* ---- forward sweep: conductivity, vapour flux, assembly, Thomas elimination ---- */
-        double Km = 0.0, psim = psi1;                                        /* K[1] = 0, psi[1] */
-        double jvm = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc);
-        double djvm = EP * MW_INFIL * B.h[2] / (hm.rts1 * (1.0 - rh_loc));
-        double psic = B.psi[2], wcnc = B.wcn[2], hc = B.h[2];
-        double Kc = hm.ks[2] * mcm::pow(hm.psi_e[2] / psic, hm.nexp[2]);
-        double ccm = 0.0, rrm = 0.0, diaL = 0.0, FL = 0.0;
-        MC_ROLLED for (int i = 2; i <= L; i++) {
-            const double psip = B.psi[i + 1], wcnp = B.wcn[i + 1], hp = B.h[i + 1];
-            const double Kp = i + 1 <= L ? hm.ks[i + 1] * mcm::pow(hm.psi_e[i + 1] / psip, hm.nexp[i + 1]) : hm.ks[L];
-            if (i == 2) { K2 = Kc; K3 = Kp; }
-            const double kv = hm.kvc[i] * (hm.sat[i] - (wcnc + wcnp) / 2.0) / hm.dz[i];
-            const double jvi = kv * (hp - hc);
-            const double djvi = MW_INFIL * hc * kv / hm.rts[i];
-            const double cap = -1.0 * hm.mass[i] * wcnc / (hm.bb[i] * psic * dt);
-            const double sub = -1.0 * Km / hm.dz[i - 1] + g * hm.nexp[i] * Km / psim;
-            const double sup = -1.0 * Kp / hm.dz[i];
-            double dia = Kc / hm.dz[i - 1] + Kc / hm.dz[i] + cap - g * hm.nexp[i] * Kc / psic + djvm + djvi;
-            double F = ((psic * Kc - psim * Km) / hm.dz[i - 1] - (psip * Kp - psic * Kc) / hm.dz[i]) / (1.0 - hm.nexp[i])
-                     + hm.mass[i] * (wcnc - theta[i - 2]) / dt - g * (Km - Kc) + jvm - jvi + B.uptake[i];
-            err += fabs(F);
-            if (i >= 3) { dia -= sub * ccm; F -= sub * rrm; }               /* elimination step owed by row i-1 */
-            if (i <= L - 1) {
-                double cc = sup / dia;
-                if (fabs(cc) < 1e-8) cc = 0.0;
-                const double rr = F / dia;
-                B.cc[i] = cc; B.rr[i] = rr; ccm = cc; rrm = rr;
-            } else { diaL = dia; FL = F; }
-            Km = Kc; psim = psic; jvm = jvi; djvm = djvi;
-            Kc = Kp; psic = psip; wcnc = wcnp; hc = hp;
-        }
-        /* ---- backward sweep: back-substitution with the saturation clamps, water content, humidity ---- */
-        double dpsi = FL / diaL;
-        MC_ROLLED for (int i = L; i >= 2; i--) {
-            double psi = B.psi[i];
-            if (i == L) psi = jmin(psi - dpsi, hm.psi_e[L]);
-            else {
-                dpsi = B.rr[i] - B.cc[i] * dpsi;
-                psi -= dpsi;
-                if (psi > hm.psi_e[i]) psi = (psi + dpsi + hm.psi_e[i]) / 2.0;
-            }
-            const double wcn = jmax(hm.sat[i] * mcm::pow(hm.psi_e[i] / psi, 1.0 / hm.bb[i]), 1e-7);
-            psi = hm.psi_e[i] * mcm::pow(hm.sat[i] / wcn, hm.bb[i]);
-            B.wcn[i] = wcn; B.psi[i] = psi;
-            B.h[i] = mcm::exp(MW_INFIL * psi / hm.rts[i]);
-        }
-        B.h[L + 1] = B.h[L];
-        if (err <= m.moist_tol) { out.hit_max = false; break; }
-    }
-    out.surface_water_flux = ((B.psi[2] * K2 - B.psi[3] * K3) / ((1.0 - hm.nexp[2]) * hm.dz[2]) + g * K2 + TR) * dt;
-    MC_ROLLED for (int i = 2; i <= L + 1; i++) theta[i - 2] = B.wcn[i];
-    out.evaporation = EP * (B.h[2] - rh_loc) / (1.0 - rh_loc) * dt;
-    return out;
-}
-
-MC_DEV double wet_surface_node(double* theta, double pool, double sat, double half_thickness)
-{
-    if (pool <= 0.0) return pool;
-    const double cap_node = half_thickness * 1000.0;
-    const double capacity = jmax(0.0, (sat - theta[0]) * cap_node);
-    const double delivered = jmin(pool, capacity);
-    theta[0] = jmin(sat, theta[0] + delivered / cap_node);
-    return pool - delivered;
-}
-
-/* per-site accessors over the SoA arrays */
-struct SiteRef {
-    const KArgs* a; int64_t s;
-    MC_MEMBER double node(const double* p, int i) const { return MC_LDG(p + (int64_t)i * a->S + s); }
-    MC_MEMBER double hourly(const double* p, int row) const { return MC_LDG(p + (int64_t)row * a->S + s); }
-    MC_MEMBER double daily(const double* p, int d) const { return MC_LDG(p + (int64_t)d * a->S + s); }
-    MC_MEMBER void put_node(double* p, int row, int node_i, double v) const { if (p) p[((int64_t)row * MC_CONST_MODEL.N + node_i) * a->S + s] = v; }
-    MC_MEMBER void put_scalar(double* p, int row, double v) const { if (p) p[(int64_t)row * a->S + s] = v; }
-};
-
-struct EnvInstant { double lai, shade, eps_surf, eps_cloud, wet_daily, T_deep, rain_daily, albedo, P, T_ref, wind, rh, zenith, cloud, lw; };
-
-MC_DEV EnvInstant get_instant(const SiteRef& r, int day, int row, double site_albedo)
-{
-    const KArgs& a = *r.a; EnvInstant e;
-    e.lai = r.daily(a.d_lai, day); e.shade = r.daily(a.d_shade, day); e.eps_surf = r.daily(a.d_eps, day); e.eps_cloud = r.daily(a.d_epsc, day);
-    e.wet_daily = r.daily(a.d_wet, day); e.T_deep = r.daily(a.d_tdeep, day); e.rain_daily = r.daily(a.d_rain, day);
-    e.albedo = a.has_albedo_daily ? r.daily(a.d_albedo, day) : site_albedo;
-    e.P = r.hourly(a.f_P, row); e.T_ref = r.hourly(a.f_T, row); e.wind = r.hourly(a.f_wind, row); e.rh = r.hourly(a.f_rh, row);
-    e.zenith = r.hourly(a.f_zen, row); e.cloud = r.hourly(a.f_cloud, row);
-    e.lw = a.has_lw ? r.hourly(a.f_lw, row) : 0.0;
-    return e;
-}
-
-/* soil_water_balance! (campbell.jl:378-495) for one hour: MOST profile -> potential evaporation -> pool wetting ->
- * niter_moist implicit sub-steps.  Returns the new soil_wetness; updates theta, pool, L_prof and the psi/h outputs. */
-template <int NA>
-MC_DEV_NOINLINE double soil_water_hour(const SiteRef& r, const EnvInstant& e, const double* T0, double* theta, double& pool,
-                                       double soil_wetness, double z0, double& L_prof, double* psi_out, double* h_out,
-                                       int& flags, Counters& cn, bool snow_present)
-{
-    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
-    const int N = m.N, L = N;
-    const double T_surf = T0[0], T_air = e.T_ref, P = e.P, rh = e.rh;
-    /* atmospheric_surface_profile! restricted to what is consumed here: air temperature at the local height + Q_conv (monin_obukhov.jl:85-206) */
-    const double z = m.zref, hloc = m.zloc;
-    const double lz = mcm::log(z / z0);
-    const double dT = T_air - T_surf;
-    const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
-    double T_loc, Qc;
-    if (T_air >= T_surf || e.zenith >= 90.0) {
-        const double ustar = jmax(m.kappa * e.wind / lz, 1.0e-6);
-        const double Stb = 0.64 / lz, Sts = sublayer_stanton(z0, ustar);
-        Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
-        const double Tz0 = (T_air * Stb + T_surf * Sts) / (Stb + Sts);
-        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
-        else if (hloc == z) T_loc = T_air;
-        else T_loc = Tz0 + (T_air - Tz0) * mcm::log(hloc / z0) / lz;
-    } else {
-        const Obukhov o = calc_obukhov(e.wind, z0, z, lz, dT, rho_cp, L_prof);
-        cn.n_obukhov += o.iters;
-        L_prof = o.L; Qc = o.Q;
-        const double Tz0 = (T_air * o.Stb + T_surf * o.Sts) / (o.Stb + o.Sts);
-        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
-        else if (hloc == z) T_loc = T_air;
-        else {
-            const double x = calc_phi_m(hloc, m.gamma, o.L);
-            const double tl = jmax(mcm::log(hloc / z0) - calc_psi_h(x), 1e-6);
-            T_loc = Tz0 + (T_air - Tz0) * tl / (lz - o.psi_h);
-        }
-    }
-    /* local relative humidity and potential evaporation (campbell.jl:416-440) */
-    const double es_air = goff_gratch(T_air);
-    const double e_ref = es_air * rh;
-    const double rh_ref_prof = jclamp(e_ref / es_air, 0.0, 1.0);
-    const double rh_loc = jclamp((es_air * rh_ref_prof) / goff_gratch(T_loc), 0.0, 0.99);
-    const double hc = jmax(fabs(Qc / (T_surf - T_air)), 0.5);
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = T_surf < T_LO ? T_LO : T_surf;
-    const double Qe = (hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);      /* saturated=true */
-    double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
-    if (snow_present) EPot = 1e-7;                                              /* campbell.jl:437-440 */
-    (void)soil_wetness;
-
-    /* per-hour constants of the implicit solve */
-    HourMoist<NA> hm;
-    MC_ROLLED for (int i = 1; i <= L; i++) {
-        const double b = r.node(a.bb, i - 1), pe = -fabs(r.node(a.psi_e, i - 1)), ksat = r.node(a.ks, i - 1);
-        hm.psi_e[i] = pe; hm.bb[i] = b; hm.ks[i] = ksat;
-        hm.sat[i] = 1.0 - r.node(a.bd, i - 1) / r.node(a.md, i - 1);
-        hm.nexp[i] = 2.0 + 3.0 / b;
-        hm.fexp[i] = (2.0 * b + 3.0) / (b + 3.0);
-        hm.phi_e[i] = -ksat * pe * b / (b + 3.0);
-    }
-    hm.psi_e[L + 1] = hm.psi_e[L]; hm.sat[L + 1] = hm.sat[L]; hm.bb[L + 1] = hm.bb[L]; hm.ks[L + 1] = hm.ks[L];
-    hm.nexp[L + 1] = hm.nexp[L]; hm.fexp[L + 1] = hm.fexp[L]; hm.phi_e[L + 1] = hm.phi_e[L];
-    /* depth[1] = -1e10, depth[2] = 0, depth[i+1] = depths[i-1], depth[L+1] = 1e20 */
-    auto depth_final = [&](int i) -> double { return i == 1 ? -1e10 : (i == 2 ? 0.0 : (i == L + 1 ? 1e20 : m.depths[i - 2])); };
-    auto depth_mass = [&](int i) -> double { return i <= 2 ? 0.0 : m.depths[i - 2]; };     /* as it stands when layer_water_mass is formed (campbell.jl:228-230) */
-    MC_ROLLED for (int i = 1; i <= L; i++) hm.dz[i] = depth_final(i + 1) - depth_final(i);
-    MC_ROLLED for (int i = 2; i <= L; i++) {
-        hm.mass[i] = WATER_RHO * (depth_mass(i + 1) - depth_mass(i - 1)) / 2.0;
-        const double rd = r.node(a.rootd, i - 1);
-        const double thick = depth_final(i + 1) - depth_final(i - 1);
-        if (rd > 0.0) {
-            hm.rootR[i] = m.root_res / (rd * thick / 2.0);
-            hm.rootZ[i] = (1.0 - hm.nexp[i]) * mcm::log(PI_D * m.root_radius * m.root_radius * rd) / (4.0 * PI_D * rd * thick / 2.0);
-        } else { hm.rootR[i] = 1e20; hm.rootZ[i] = 0.0; }
-        const double Ts_i = i <= L ? T0[i - 1] : T0[L - 1];        /* B.Ts[i] = T0[i-1] */
-        hm.kvc[i] = 0.66 * DV_INFIL * vapour_density_sat(Ts_i);
-        hm.rts[i] = m.R * T0[i - 2];                                /* R * B.Ts[i-1] */
-    }
-    hm.rts1 = m.R * T0[0];
-
-    const double sat0 = 1.0 - r.node(a.bd, 0) / r.node(a.md, 0);
-    const double half = (m.depths[1] - m.depths[0]) / 2.0;
-    pool = wet_surface_node(theta, pool, sat0, half);
-    InfilWork<NA> B;
-    InfilOut io; io.evaporation = 0.0; io.surface_water_flux = 0.0; io.hit_max = false;
-    MC_ROLLED for (int k = 0; k < m.niter_moist; k++) {
-        io = m.flux_alg ? infiltration_step<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn) : infiltration_step_psi<NA>(hm, B, theta, rh_loc, e.lai, EPot, cn, k > 0);
-        if (io.hit_max) flags |= MC_STATUS_NEWTON_MAXITER;
-        pool = jclamp(pool - jmax(0.0, io.surface_water_flux) - jmax(0.0, io.evaporation), 0.0, m.max_pool);
-        pool = wet_surface_node(theta, pool, sat0, half);
-    }
-    MC_ROLLED for (int i = 0; i < N; i++) { psi_out[i] = B.psi[i + 2]; h_out[i] = B.h[i + 2]; }
-    return jclamp(jmax(0.0, io.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
-}
-
-
-/* ==========================================================================================================================
- * Block-cooperative soil water balance (soil_water_balance!, campbell.jl:378-495, water-potential form).  The Newton iterations of
- * the implicit infiltration step are where sites of a warp diverge most (2 to 500 iterations per sub-step), and one iteration is
- * almost entirely per-node work (3 pow + 1 exp per node).  Every site runs its own (sub-step, iteration) sequence; each round the
- * block serves, for the sites that need them,
- *
- *     U-pass : per node, new water content / potential / humidity / conductivity from the back-substituted potential     | barrier
- *     F-pass : per node, the mass-balance residual and the tridiagonal row (vapour flux, capacity, gravity terms)          | barrier
- *     owners : in-order residual sum, Thomas elimination and back-substitution, convergence, sub-step bookkeeping          | barrier
- *
- * so a site that needs 500 iterations costs 500 short rounds instead of stalling its warp for 500 serial sweeps of the profile.
- * Arithmetic and operation order are those of infiltration_step_psi / soil_water_hour above.
- * ========================================================================================================================== */
-enum { M_PSIE = 0, M_SAT, M_BB, M_KS, M_NEXP, M_ROOTR, M_ROOTZ, M_KVC, M_RTS, M_PSI, M_K, M_H, M_WCN, M_TH0, M_SUB, M_DIA, M_SUP, M_F, M_UPT, M_CC, M_RR, M_Q1, M_Q2, M_RT, M_ARRAYS };
-#define MC_MSCR(arr, i, t) scr[((size_t)(P_ARRAYS * NA + (arr) * (NA + 2) + (i))) * MC_TB + (t)]
-enum { MF_FIRST = 1, MF_S0 = 2, MF_FINAL = 4 };
-template <int NA> struct Coop2Rows { static constexpr size_t value = (size_t)P_ARRAYS * NA + (MC_COOP_MOIST ? (size_t)M_ARRAYS * (NA + 2) : 0); };
-
-struct MoistShared { int listF[COOP_TB]; int countU[2], countF[2], alive[2]; };
-
-/* U-pass item: node i (2..L) of site o */
-template <int NA>
-MC_DEV void moist_item_update(const Coop2Shared& sh, double* scr, int o, int i)
-{
-    const int fl = sh.code[o];
-    const double psi_e = MC_MSCR(M_PSIE, i, o), sat = MC_MSCR(M_SAT, i, o), bb = MC_MSCR(M_BB, i, o);
-    double wcn;
-    if (fl & MF_S0) wcn = MC_MSCR(M_TH0, i, o);
-    else wcn = jmax(sat * mcm::pow(psi_e / MC_MSCR(M_PSI, i, o), 1.0 / bb), 1e-7);
-    const double psi = psi_e * mcm::pow(sat / wcn, bb);
-    MC_MSCR(M_WCN, i, o) = wcn; MC_MSCR(M_PSI, i, o) = psi;
-    MC_MSCR(M_H, i, o) = mcm::exp(MW_INFIL * psi / MC_MSCR(M_RTS, i, o));
-    const double K = MC_MSCR(M_KS, i, o) * mcm::pow(psi_e / psi, MC_MSCR(M_NEXP, i, o));
-    MC_MSCR(M_K, i, o) = K;
-    if (fl & MF_FINAL) MC_MSCR(M_TH0, i, o) = wcn;
-    if (fl & (MF_FINAL | MF_S0)) {          /* this state starts the next sub-step: root + soil resistance terms of its stomatal balance (campbell.jl:253-267) */
-        const double rt = MC_MSCR(M_ROOTZ, i, o) / K + MC_MSCR(M_ROOTR, i, o);
-        MC_MSCR(M_RT, i, o) = rt; MC_MSCR(M_Q1, i, o) = psi / rt; MC_MSCR(M_Q2, i, o) = 1.0 / rt;
-    }
-}
-
-/* F-pass item: residual and tridiagonal row of node i (2..L) of site o (root uptake is formed in a sub-step's first iteration).
- * sh.P = EP, sh.p0p = rh_loc, sh.pp0 = R * Ts[1], sh.dt = psi[1] of the sub-step. */
-template <int NA>
-MC_DEV void moist_item_assemble(const Coop2Shared& sh, double* scr, int o, int i)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int L = m.N;
-    const double g = m.g, dt = m.moist_dt;
-    const bool first = (sh.code[o] & MF_FIRST) != 0;
-    const double psic = MC_MSCR(M_PSI, i, o), Kc = MC_MSCR(M_K, i, o), wcnc = MC_MSCR(M_WCN, i, o), hc = MC_MSCR(M_H, i, o);
-    const double nexp = MC_MSCR(M_NEXP, i, o), sat = MC_MSCR(M_SAT, i, o);
-    double psim, Km, jvm, djvm;
-    if (i == 2) {
-        const double EP = sh.P[o], rh_loc = sh.p0p[o];
-        psim = first ? psic : sh.dt[o]; Km = 0.0;
-        jvm = EP * (hc - rh_loc) / (1.0 - rh_loc);
-        djvm = EP * MW_INFIL * hc / (sh.pp0[o] * (1.0 - rh_loc));
-    } else {
-        psim = MC_MSCR(M_PSI, i - 1, o); Km = MC_MSCR(M_K, i - 1, o);
-        const double wcnm = MC_MSCR(M_WCN, i - 1, o), hm1 = MC_MSCR(M_H, i - 1, o);
-        const double kvm = MC_MSCR(M_KVC, i - 1, o) * (MC_MSCR(M_SAT, i - 1, o) - (wcnm + wcnc) / 2.0) / m.mdz[i - 1];
-        jvm = kvm * (hc - hm1);
-        djvm = MW_INFIL * hm1 * kvm / MC_MSCR(M_RTS, i - 1, o);
-    }
-    double psip, Kp, wcnp, hp;
-    if (i + 1 <= L) { psip = MC_MSCR(M_PSI, i + 1, o); Kp = MC_MSCR(M_K, i + 1, o); wcnp = MC_MSCR(M_WCN, i + 1, o); hp = MC_MSCR(M_H, i + 1, o); }
-    else { psip = MC_MSCR(M_PSIE, L, o); Kp = MC_MSCR(M_KS, L, o); wcnp = MC_MSCR(M_SAT, L, o); hp = first ? 1.0 : hc; }   /* row L+1: psi_e[L], ks[L], sat[L+1] = sat[L], h = 1 then h[L] */
-    const double kv = MC_MSCR(M_KVC, i, o) * (sat - (wcnc + wcnp) / 2.0) / m.mdz[i];
-    const double jvi = kv * (hp - hc);
-    const double djvi = MW_INFIL * hc * kv / MC_MSCR(M_RTS, i, o);
-    const double cap = -1.0 * m.mmass[i] * wcnc / (MC_MSCR(M_BB, i, o) * psic * dt);
-    const double sub = -1.0 * Km / m.mdz[i - 1] + g * nexp * Km / psim;
-    const double sup = -1.0 * Kp / m.mdz[i];
-    const double dia = Kc / m.mdz[i - 1] + Kc / m.mdz[i] + cap - g * nexp * Kc / psic + djvm + djvi;
-    double uptake;
-    if (first) { uptake = (psic - MC_MSCR(M_UPT, 0, o) - MC_MSCR(M_UPT, 1, o)) / MC_MSCR(M_RT, i, o); MC_MSCR(M_UPT, i, o) = uptake; }   /* rows 0, 1: psi_leaf, RL * TR */
-    else uptake = MC_MSCR(M_UPT, i, o);
-    const double F = ((psic * Kc - psim * Km) / m.mdz[i - 1] - (psip * Kp - psic * Kc) / m.mdz[i]) / (1.0 - nexp)
-                   + m.mmass[i] * (wcnc - MC_MSCR(M_TH0, i, o)) / dt - g * (Km - Kc) + jvm - jvi + uptake;
-    MC_MSCR(M_SUB, i, o) = sub; MC_MSCR(M_DIA, i, o) = dia; MC_MSCR(M_SUP, i, o) = sup; MC_MSCR(M_F, i, o) = F;
-}
-
-struct MoistOwn {
-    double EP, TP, rh_loc, K2, K3, TR, evaporation, surface_water_flux, pool, sat0, half;
-    int k, counter, state;         /* state: 0 = done, 1 = sub-step start owed, 2 = Newton iteration owed */
-    bool hit_any;
-};
-
-/* owner: start of sub-step k (the part of infiltration_step! before the Newton loop): root/soil resistances, stomatal Newton, uptake */
-template <int NA>
-MC_DEV_NOINLINE void moist_substep_start(MoistOwn& W, Coop2Shared& sh, double* scr, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL; const int L = m.N; const int tid = MC_TID;
-    cn.n_infil++;
-    double psum = 0.0, rsum = 0.0, psi_leaf = 0.0;
-    MC_ROLLED for (int i0 = 2; i0 <= L; i0 += 4) {                           /* in-order sums of the per-node quotients the U-pass left */
-        double q1[4], q2[4];
-        _Pragma("unroll") for (int k = 0; k < 4; k++) { q1[k] = i0 + k <= L ? MC_MSCR(M_Q1, i0 + k, tid) : 0.0; q2[k] = i0 + k <= L ? MC_MSCR(M_Q2, i0 + k, tid) : 0.0; }
-        _Pragma("unroll") for (int k = 0; k < 4; k++) if (i0 + k <= L) { psum += q1[k]; rsum += q2[k]; }
-    }
-    sh.dt[tid] = MC_MSCR(M_PSI, 2, tid);                                     /* water_potential[1] = water_potential[2], never updated again */
-    const double psi_bar = psum / rsum, R_bar = 1.0 / rsum;
-    const double RL = m.RL, PC = m.PC, SP = m.SP, TP = W.TP;
-    psi_leaf = stomatal_newton(psi_leaf, psi_bar, R_bar, TP);                /* campbell.jl:270-284 */
-    W.TR = TP / (1.0 + mcm::pow(psi_leaf / PC, SP));
-    MC_MSCR(M_UPT, 0, tid) = psi_leaf; MC_MSCR(M_UPT, 1, tid) = RL * W.TR;    /* the first F-pass forms uptake[i] = (psi[i] - psi_leaf - RL TR) / (rootR[i] + soilR[i]) */
-    W.counter = 0;
-}
-
-/* owner: one Newton iteration's serial part: residual sum, Thomas elimination, back-substitution with the saturation clamps.
- * Returns true when this was the sub-step's last iteration (converged or iteration cap). */
-template <int NA>
-MC_DEV_NOINLINE bool moist_thomas(MoistOwn& W, double* scr, Counters& cn, int& flags)
-{
-    const DevModel& m = MC_CONST_MODEL; const int L = m.N; const int tid = MC_TID;
-    W.counter++; cn.n_newton++;
-    W.K2 = MC_MSCR(M_K, 2, tid);
-    W.K3 = 3 <= L ? MC_MSCR(M_K, 3, tid) : MC_MSCR(M_KS, L, tid);
-    double err = 0.0, ccm = 0.0, rrm = 0.0, diaL = 0.0, FL = 0.0;
-    MC_THOMAS_UNROLL for (int i = 2; i <= L; i++) {
-        const double sub = MC_MSCR(M_SUB, i, tid), sup = MC_MSCR(M_SUP, i, tid);
-        double dia = MC_MSCR(M_DIA, i, tid);
-        double F = MC_MSCR(M_F, i, tid);
-        err += fabs(F);
-        if (i >= 3) { dia -= sub * ccm; F -= sub * rrm; }
-        if (i <= L - 1) {
-            double cc = sup / dia;
-            if (fabs(cc) < 1e-8) cc = 0.0;
-            const double rr = F / dia;
-            MC_MSCR(M_CC, i, tid) = cc; MC_MSCR(M_RR, i, tid) = rr; ccm = cc; rrm = rr;
-        } else { diaL = dia; FL = F; }
-    }
-    double dpsi = FL / diaL;
-    MC_THOMAS_UNROLL for (int i = L; i >= 2; i--) {
-        double psi = MC_MSCR(M_PSI, i, tid);
-        const double psi_e = MC_MSCR(M_PSIE, i, tid);
-        if (i == L) psi = jmin(psi - dpsi, psi_e);
-        else {
-            dpsi = MC_MSCR(M_RR, i, tid) - MC_MSCR(M_CC, i, tid) * dpsi;
-            psi -= dpsi;
-            if (psi > psi_e) psi = (psi + dpsi + psi_e) / 2.0;
-        }
-        MC_MSCR(M_PSI, i, tid) = psi;                                         /* raw potential: the U-pass turns it into the new state */
-    }
-    const bool converged = err <= m.moist_tol;
-    const bool last = converged || W.counter >= m.moist_max_it;
-    if (last && !converged) { flags |= MC_STATUS_NEWTON_MAXITER; }
-    return last;
-}
-
-/* soil_water_balance! for the hour, cooperatively.  Same interface as soil_water_hour (water-potential form, no snow). */
-template <int NA>
-MC_DEV double soil_water_hour_coop(const SiteRef& r, const EnvInstant& e, const double* T0, double* theta, double& pool,
-                                   double z0, double& L_prof, double* psi_out, double* h_out, int& flags, Counters& cn,
-                                   Coop2Shared& sh, MoistShared& ms, double* scr, int& par_io)
-{
-    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
-    const int N = m.N, L = N; const int tid = MC_TID, TB = MC_TB;
-    const double T_surf = T0[0], T_air = e.T_ref, P = e.P, rh = e.rh;
-    /* atmospheric_surface_profile! restricted to what is consumed here (monin_obukhov.jl:85-206) */
-    const double z = m.zref, hloc = m.zloc;
-    const double lz = mcm::log(z / z0);
-    const double dT = T_air - T_surf;
-    const double rho_cp = calc_rho_cp((T_surf + T_air) / 2.0);
-    double T_loc, Qc;
-    if (T_air >= T_surf || e.zenith >= 90.0) {
-        const double ustar = jmax(m.kappa * e.wind / lz, 1.0e-6);
-        const double Stb = 0.64 / lz, Sts = sublayer_stanton(z0, ustar);
-        Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
-        const double Tz0 = (T_air * Stb + T_surf * Sts) / (Stb + Sts);
-        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
-        else if (hloc == z) T_loc = T_air;
-        else T_loc = Tz0 + (T_air - Tz0) * mcm::log(hloc / z0) / lz;
-    } else {
-        const Obukhov o = calc_obukhov(e.wind, z0, z, lz, dT, rho_cp, L_prof);
-        cn.n_obukhov += o.iters;
-        L_prof = o.L; Qc = o.Q;
-        const double Tz0 = (T_air * o.Stb + T_surf * o.Sts) / (o.Stb + o.Sts);
-        if (hloc < z0) T_loc = T_surf + (Tz0 - T_surf) * (hloc / z0);
-        else if (hloc == z) T_loc = T_air;
-        else {
-            const double x = calc_phi_m(hloc, m.gamma, o.L);
-            const double tl = jmax(mcm::log(hloc / z0) - calc_psi_h(x), 1e-6);
-            T_loc = Tz0 + (T_air - Tz0) * tl / (lz - o.psi_h);
-        }
-    }
-    /* local relative humidity and potential evaporation (campbell.jl:416-440) */
-    const double es_air = goff_gratch(T_air);
-    const double e_ref = es_air * rh;
-    const double rh_ref_prof = jclamp(e_ref / es_air, 0.0, 1.0);
-    const double rh_loc = jclamp((es_air * rh_ref_prof) / goff_gratch(T_loc), 0.0, 0.99);
-    const double hc = jmax(fabs(Qc / (T_surf - T_air)), 0.5);
-    const WetAir wa = wet_air(T_air, rh, P);
-    const double hd = (hc / (wa.specific_heat * wa.density)) * m.schmidt_factor;
-    const double Tsc = T_surf < T_LO ? T_LO : T_surf;
-    const double Qe = (hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);      /* saturated=true */
-    const double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
-
-    /* per-hour constants of the implicit solve, into the block's scratch (rows 1..L of the reference's 1-based profile) */
-    MC_ROLLED for (int i = 1; i <= L; i++) {
-        const double b = r.node(a.bb, i - 1), pe = -fabs(r.node(a.psi_e, i - 1)), ksat = r.node(a.ks, i - 1);
-        const double nexp = 2.0 + 3.0 / b;
-        MC_MSCR(M_PSIE, i, tid) = pe; MC_MSCR(M_BB, i, tid) = b; MC_MSCR(M_KS, i, tid) = ksat;
-        MC_MSCR(M_SAT, i, tid) = 1.0 - r.node(a.bd, i - 1) / r.node(a.md, i - 1);
-        MC_MSCR(M_NEXP, i, tid) = nexp;
-        if (i >= 2) {
-            const double rd = r.node(a.rootd, i - 1);
-            const double thick = (i == L ? 1e20 : m.depths[i - 1]) - (i == 2 ? -1e10 : (i == 3 ? 0.0 : m.depths[i - 3]));      /* depth[i+1] - depth[i-1] */
-            if (rd > 0.0) {
-                MC_MSCR(M_ROOTR, i, tid) = m.root_res / (rd * thick / 2.0);
-                MC_MSCR(M_ROOTZ, i, tid) = (1.0 - nexp) * mcm::log(PI_D * m.root_radius * m.root_radius * rd) / (4.0 * PI_D * rd * thick / 2.0);
-            } else { MC_MSCR(M_ROOTR, i, tid) = 1e20; MC_MSCR(M_ROOTZ, i, tid) = 0.0; }
-            MC_MSCR(M_KVC, i, tid) = 0.66 * DV_INFIL * vapour_density_sat(T0[i - 1]);
-            MC_MSCR(M_RTS, i, tid) = m.R * T0[i - 2];
-        }
-    }
-    MoistOwn W;
-    W.sat0 = 1.0 - r.node(a.bd, 0) / r.node(a.md, 0);
-    W.half = (m.depths[1] - m.depths[0]) / 2.0;
-    pool = wet_surface_node(theta, pool, W.sat0, W.half);
-    MC_ROLLED for (int i = 2; i <= L; i++) MC_MSCR(M_TH0, i, tid) = theta[i - 2];
-    W.EP = mcm::exp(-0.82 * e.lai) * EPot; W.TP = EPot - W.EP; W.rh_loc = rh_loc; W.pool = pool;
-    W.k = 0; W.counter = 0; W.state = m.niter_moist > 0 ? 1 : 0; W.hit_any = false; W.evaporation = 0.0; W.surface_water_flux = 0.0; W.TR = 0.0; W.K2 = 0.0; W.K3 = 0.0;
-    sh.P[tid] = W.EP; sh.p0p[tid] = rh_loc; sh.pp0[tid] = m.R * T0[0];
-
-    /* rounds.  needU / needF say which passes this site takes part in next round. */
-    bool needU = W.state != 0, needF = false;
-    sh.code[tid] = (unsigned char)(MF_S0);
-    int par = par_io;
-    for (;;) {
-        const bool alive = W.state != 0;
-#if defined(__CUDACC__)
-        {
-            const unsigned bu = __ballot_sync(0xffffffffu, needU), bf = __ballot_sync(0xffffffffu, needF), ba = __ballot_sync(0xffffffffu, alive);
-            const int lane = tid & 31;
-            int baseU = 0, baseF = 0;
-            if (lane == 0) {
-                if (bu) baseU = atomicAdd(&ms.countU[par], __popc(bu));
-                if (bf) baseF = atomicAdd(&ms.countF[par], __popc(bf));
-                if (ba) atomicAdd(&ms.alive[par], __popc(ba));
-            }
-            baseU = __shfl_sync(0xffffffffu, baseU, 0); baseF = __shfl_sync(0xffffffffu, baseF, 0);
-            const unsigned lt = (1u << lane) - 1u;
-            if (needU) sh.list[baseU + __popc(bu & lt)] = tid;
-            if (needF) ms.listF[baseF + __popc(bf & lt)] = tid;
-        }
-        __syncthreads();
-        const int AU = ms.countU[par], AF = ms.countF[par], AL = ms.alive[par];
-        if (tid == 0) { ms.countU[par ^ 1] = 0; ms.countF[par ^ 1] = 0; ms.alive[par ^ 1] = 0; }
-#else
-        const int AU = needU ? 1 : 0, AF = needF ? 1 : 0, AL = alive ? 1 : 0;
-        sh.list[0] = tid; ms.listF[0] = tid;
-#endif
-        if (AL == 0) break;
-        if (AU > 0) {
-            const unsigned long long magic = (0x100000000ull + (unsigned)AU - 1ull) / (unsigned)AU;
-            const int total = AU * (L - 1);
-            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); moist_item_update<NA>(sh, scr, sh.list[j - node * AU], node + 2); }
-        }
-        MC_BLOCK_SYNC();
-        if (AF > 0) {
-            const unsigned long long magic = (0x100000000ull + (unsigned)AF - 1ull) / (unsigned)AF;
-            const int total = AF * (L - 1);
-            MC_ROLLED for (int j = tid; j < total; j += TB) { const int node = (int)(((unsigned long long)j * magic) >> 32); moist_item_assemble<NA>(sh, scr, ms.listF[j - node * AF], node + 2); }
-        }
-        MC_BLOCK_SYNC();
-        /* owner slot */
-        if (needF) {                                                          /* a Newton iteration was assembled: solve it */
-            const bool last = moist_thomas<NA>(W, scr, cn, flags);
-            needU = true; needF = !last;
-            sh.code[tid] = (unsigned char)(last ? MF_FINAL : 0);
-            if (last) W.state = 1;                                            /* next owner slot: sub-step bookkeeping */
-        } else if (W.state == 1) {
-            if (W.counter > 0) {                                              /* end of sub-step k (after its last update): infiltration_step!'s outputs + pool */
-                const double psi2 = MC_MSCR(M_PSI, 2, tid), psi3 = 3 <= L ? MC_MSCR(M_PSI, 3, tid) : MC_MSCR(M_PSIE, L, tid);
-                W.surface_water_flux = ((psi2 * W.K2 - psi3 * W.K3) / ((1.0 - MC_MSCR(M_NEXP, 2, tid)) * m.mdz[2]) + m.g * W.K2 + W.TR) * m.moist_dt;
-                W.evaporation = W.EP * (MC_MSCR(M_H, 2, tid) - W.rh_loc) / (1.0 - W.rh_loc) * m.moist_dt;
-                W.pool = jclamp(W.pool - jmax(0.0, W.surface_water_flux) - jmax(0.0, W.evaporation), 0.0, m.max_pool);
-                if (W.pool > 0.0) {                                           /* wet_surface_node on theta[0] = row 2 */
-                    double th0 = MC_MSCR(M_TH0, 2, tid);
-                    const double before = th0;
-                    W.pool = wet_surface_node(&th0, W.pool, W.sat0, W.half);
-                    if (th0 != before) MC_MSCR(M_TH0, 2, tid) = th0;
-                    if (th0 != before && W.k + 1 < m.niter_moist) {           /* the next sub-step's start recomputes the state of row 2 from the wetted water content */
-                        const double psi_e = MC_MSCR(M_PSIE, 2, tid);
-                        const double psi = psi_e * mcm::pow(MC_MSCR(M_SAT, 2, tid) / th0, MC_MSCR(M_BB, 2, tid));
-                        MC_MSCR(M_WCN, 2, tid) = th0; MC_MSCR(M_PSI, 2, tid) = psi;
-                        MC_MSCR(M_H, 2, tid) = mcm::exp(MW_INFIL * psi / MC_MSCR(M_RTS, 2, tid));
-                        const double K = MC_MSCR(M_KS, 2, tid) * mcm::pow(psi_e / psi, MC_MSCR(M_NEXP, 2, tid));
-                        MC_MSCR(M_K, 2, tid) = K;
-                        const double rt = MC_MSCR(M_ROOTZ, 2, tid) / K + MC_MSCR(M_ROOTR, 2, tid);
-                        MC_MSCR(M_RT, 2, tid) = rt; MC_MSCR(M_Q1, 2, tid) = psi / rt; MC_MSCR(M_Q2, 2, tid) = 1.0 / rt;
-                    }
-                }
-                W.k++;
-            }
-            if (W.k < m.niter_moist) {
-                moist_substep_start<NA>(W, sh, scr, cn);
-                sh.code[tid] = (unsigned char)MF_FIRST;
-                needU = false; needF = true; W.state = 2;
-            } else { needU = false; needF = false; W.state = 0; }
-        }
-        MC_BLOCK_SYNC();
-        par ^= 1;
-    }
-    par_io = par;
-    pool = W.pool;
-    if (m.niter_moist > 0) {
-        MC_ROLLED for (int i = 2; i <= L; i++) theta[i - 2] = MC_MSCR(M_TH0, i, tid);
-        theta[L - 1] = MC_MSCR(M_SAT, L, tid);                               /* water_content[L+1] = saturation of the last row */
-    }
-    MC_ROLLED for (int i = 0; i < N - 1; i++) { psi_out[i] = MC_MSCR(M_PSI, i + 2, tid); h_out[i] = MC_MSCR(M_H, i + 2, tid); }
-    psi_out[N - 1] = MC_MSCR(M_PSIE, L, tid); h_out[N - 1] = MC_MSCR(M_H, L, tid);      /* row L+1: psi_e[L], h[L+1] = h[L] */
-    return jclamp(jmax(0.0, W.evaporation) / (EPot * m.moist_dt), 0.0, 1.0);
-}
-
-/* theta-only soil property terms for the coming ODE hour (theta is constant while the ODE advances) */
-template <int NA, int NS>
-MC_DEV_NOINLINE void hoist_soil(const SiteRef& r, const double* theta, HourSoil<NA>& hs)
-{
-    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
-    MC_ROLLED for (int i = 0; i < m.N; i++) {
-        const double bd = r.node(a.bd, i), md = r.node(a.md, i);
-        const double th = theta[i];
-        const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
-        const double rho = th * WATER_RHO + bd;
-        hs.cap[i] = NS == 0 ? (rho * cp) * m.dzc[i] / 2.0 : rho * cp;      /* with snow the node geometry changes hourly: keep rho*c */
-        hs.theta[i] = th; hs.phim[i] = bd / md; hs.phig[i] = jmax(0.0, 1.0 - th - bd / md);
-        hs.fw[i] = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
-    }
-}
-MC_DEV_NOINLINE void put_potential_row(const SiteRef& r, int row, const double* theta)
-{
-    const KArgs& a = *r.a;
-    if (!a.o_psi) return;
-    MC_ROLLED for (int i = 0; i < MC_CONST_MODEL.N; i++)
-        r.put_node(a.o_psi, row, i, r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i)));
-}
-/* initialise_soil_humidity!, dynamic.jl:32-35: always row 1 of the buffer */
-MC_DEV_NOINLINE void init_humidity(const SiteRef& r, const double* theta, const double* Tn)
-{
-    const DevModel& m = MC_CONST_MODEL; const KArgs& a = *r.a;
-    if (!m.dynamic || !a.o_h) return;
-    MC_ROLLED for (int i = 0; i < m.N; i++) {
-        const double psi = r.node(a.psi_e, i) * mcm::pow((1.0 - r.node(a.bd, i) / r.node(a.md, i)) / theta[i], r.node(a.bb, i));
-        r.put_node(a.o_h, 0, i, jclamp(mcm::exp(MW_INFIL * psi / (m.R * Tn[i])), 0.0, 1.0));
-    }
-}
-MC_DEV_NOINLINE void write_props(const SiteRef& r, int row, const double* Tn, const double* theta, double P)
-{
-    const KArgs& a = *r.a;
-    if (!a.o_lam && !a.o_cp && !a.o_rho) return;
-    MC_ROLLED for (int i = 0; i < MC_CONST_MODEL.N; i++) {
-        double lam, cp, rho;
-        soil_properties_full(Tn[i], P, theta[i], r.node(a.bd, i), r.node(a.md, i), r.node(a.lam_m, i), r.node(a.c_m, i), lam, cp, rho);
-        r.put_node(a.o_lam, row, i, lam); r.put_node(a.o_cp, row, i, cp); r.put_node(a.o_rho, row, i, rho);
-    }
-}
-
-MC_DEV bool is_converged(int iter, int niter, const double* T0, const double* T0_prev, int N)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    if (m.conv_kind == MC_CONV_FIXED) return iter >= niter;
-    if (iter >= niter) return true;
-    if (iter <= 1) return niter <= 1;
-    double mx = 0.0; MC_ROLLED for (int i = 0; i < N; i++) mx = fmax(mx, fabs(T0[i] - T0_prev[i]));
-    return mx < m.conv_tol;
-}
-
-/* ------------------------------------------------------------------------------------------
- * solve_soil! for days [day0, day0+ndays) of site s (simulation.jl:355-819).  NS = 0 (NoSnow) or 8 (SnowModel):
- * with snow the ODE state is [T_snow(8); T_soil(N)] over hourly-changing effective depths.
- * ------------------------------------------------------------------------------------------ */
-template <int NA, int NS>
-MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int N = m.N;
-    constexpr int ns = NS;
-    constexpr bool snow = NS > 0;
-    const int nrows = a.ndays * 24;
-    const bool dynamic = m.dynamic != 0, nonconsec = m.nonconsec != 0;
-    SiteRef r; r.a = &a; r.s = s;
-    const int64_t S = a.S;
-
-    HourSoil<NA> hs; HourPar hp; Integ<NA + NS> I; SnowCtx sn;
-    double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_prev_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
-    double psi_out[NA], h_out[NA];
-    double Ts[NSN], Ts_before[NSN], Ts_day_start[NSN];
-    MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; hs.lam_m[i] = r.node(a.lam_m, i); }
-    double pool = a.pool[s], wet_dyn = a.wetness[s], L_ode = a.L_ode[s], L_prof = a.L_prof[s], tdeep_stale = a.tdeep_prev[s];
-    int flags = a.flags[s];
-    const double site_albedo = MC_LDG(a.albedo + s);
-    hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
-    hp.sn = snow ? &sn : nullptr;
-    I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
-    MC_ROLLED for (int i = 0; i < N + ns; i++) { I.k1[i] = a.fsal[(int64_t)i * S + s]; I.k7[i] = I.k1[i]; }
-    double sd_last = 0.0;
-    SnowState proto_state;
-    if (snow) {
-        MC_ROLLED for (int i = 0; i < NSN; i++) { Ts[i] = a.snow_T[(int64_t)i * S + s]; sn.sc.node_depths[i] = a.snow_nd[(int64_t)i * S + s]; sn.sc.meanT[i] = 0.0; sn.sc.meanTpast[i] = 0.0; }
-        const double* q = a.snow_state + s;
-        sn.st.depth = q[0]; sn.st.age = q[S]; sn.st.days_since = q[2 * S]; sn.st.density = q[3 * S]; sn.st.prev_density = q[4 * S];
-        sn.st.cum_melt = q[5 * S]; sn.st.extra = q[6 * S]; sn.st.active = (int)q[7 * S]; sn.st.sum_phase = q[8 * S]; sd_last = q[9 * S];
-        sn.sc.sd_prev = 0.0; sn.sc.sd_cur = 0.0;
-        sn.Q_freeze = a.q_freeze[s]; sn.rhs_state = &sn.st;
-        MC_ROLLED for (int i = 0; i <= N + ns; i++) sn.depths[i] = 0.0;
-    }
-
-    auto set_day_forcing = [&](int jl) {
-        const int64_t off = (int64_t)jl * 24 * S + s;
-        hp.fP = a.f_P + off; hp.fT = a.f_T + off; hp.fwind = a.f_wind + off; hp.frh = a.f_rh + off; hp.fcloud = a.f_cloud + off;
-        hp.fsolar = a.f_solar + off; hp.fdiff = a.f_diffuse + off; hp.fzen = a.f_zen + off; hp.fszen = a.f_szen + off;
-        hp.ftab[0] = hp.fP; hp.ftab[1] = hp.fT; hp.ftab[2] = hp.fwind; hp.ftab[3] = hp.fzen; hp.ftab[4] = hp.fsolar; hp.ftab[5] = hp.fcloud; hp.ftab[6] = hp.frh;
-    };
-    auto tins_mean = [&](int jl) { double ssum = 0.0; MC_ROLLED for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
-    double sky_T = 0.0;
-    bool is_last = false;
-    /* apply_snow_overrides (simulation.jl:46-81) + per-hour parameter update */
-    auto set_hour_params = [&](const EnvInstant& e, int64_t gstep, double depth_prev_hour) {
-        hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud;
-        const bool snow_active = snow && is_last && ((gstep > 1 ? depth_prev_hour : sn.st.depth) > 0.0);
-        if (snow_active) { hp.albedo = snow_albedo(sn.st.days_since); hp.soil_wetness = 1.0; }
-        else { hp.albedo = e.albedo; hp.soil_wetness = dynamic ? wet_dyn : e.wet_daily; }
-        sky_T = sky_temperature(hp.svf, e.P, e.rh, e.T_ref, e.eps_cloud, e.cloud, e.shade, a.has_lw != 0, e.lw);
-    };
-    auto combine = [&](double* u) { MC_ROLLED for (int i = 0; i < ns; i++) u[i] = Ts[i]; MC_ROLLED for (int i = 0; i < N; i++) u[ns + i] = T0[i]; };
-    auto sync_inactive = [&]() { const double sy = Ts[0]; MC_ROLLED for (int k = 0; k < ns; k++) if (!(sn.sc.node_depths[k] > 0.0)) Ts[k] = sy; };
-
-    EnvInstant env;
-    if (a.day0 == 0) {
-        /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:196-238,853-860) */
-        set_day_forcing(0);
-        env = get_instant(r, 0, 0, site_albedo);
-        MC_ROLLED for (int i = 0; i < ns; i++) I.tmp[i] = m.snow.initial_snow_temperature_K;
-        MC_ROLLED for (int i = 0; i < N; i++) I.tmp[ns + i] = a.has_init_T ? T0[i] : 280.0;
-        hoist_soil<NA, NS>(r, theta, hs);
-        hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
-        if (snow) {           /* depths_proto = combined_depths(initial snow state) but p.snow_state = initial_snow_state(model) */
-            proto_state = initial_snow_state(0.0, -1.0);
-            compute_effective_depths(sn.st, sn.sc, sn.depths);
-            sn.rhs_state = &proto_state;
-            const double qf = sn.Q_freeze; sn.Q_freeze = 0.0;
-            Counters scratch = {};
-            rhs_dispatch<NA, NS>(hs, hp, I.tmp, 0.0, I.k1, scratch);
-            sn.rhs_state = &sn.st; sn.Q_freeze = qf;
-        } else {
-            Counters scratch = {};
-            rhs_dispatch<NA, NS>(hs, hp, I.tmp, 0.0, I.k1, scratch);
-        }
-        /* solve_soil! pre-loop (simulation.jl:395-452) */
-        if (!a.has_init_T) { const double t_init = tins_mean(0); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_init; }
-        MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-        write_props(r, 0, T0, theta, 101325.0);
-        put_potential_row(r, 0, theta);
-        MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
-        init_humidity(r, theta, T0);
-        tdeep_stale = env.T_deep;
-        pool = 0.0;
-        if (snow) sn.Q_freeze = 0.0;
-    }
-
-    for (int jl = 0; jl < a.ndays; jl++) {
-        const int64_t j = a.day0 + jl;
-        const int doy = a.doy ? (int)MC_LDG(a.doy + jl) : (int)(j + 1);
-        set_day_forcing(jl);
-        const int niter = nonconsec ? m.iters_per_day : ((m.spinup && j == 0) ? m.conv_iters : 1);
-        int noon_i = 0; double best = r.hourly(a.f_zen, jl * 24);
-        MC_ROLLED for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
-        const int midnight_i = (noon_i + 12) % 24;
-        if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516); the snowpack is NOT reset */
-            MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-            if (snow) sn.st.sum_phase = 0.0;
-            if (!dynamic && a.has_presc) { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
-            else { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i); }
-            const double t_reset = tins_mean(jl);
-            if (!a.has_init_T) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_reset; }
-            else { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i); }
-            MC_ROLLED for (int i = 0; i < ns; i++) Ts[i] = t_reset;
-        }
-        T0[N - 1] = tdeep_stale;
-        int iter = 0; is_last = false;
-        MC_ROLLED for (int i = 0; i < N; i++) { T0_prev_start[i] = T0[i]; T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
-        MC_ROLLED for (int i = 0; i < ns; i++) Ts_day_start[i] = Ts[i];
-        while (!is_last) {                                                    /* outer fixed point over day passes (simulation.jl:530) */
-            iter++; cn.n_day_passes++;
-            is_last = is_converged(iter, niter, T0, T0_prev_start, N);
-            MC_ROLLED for (int i = 0; i < N; i++) T0_prev_start[i] = T0[i];
-            if (!nonconsec) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = T0_day_start[i]; MC_ROLLED for (int i = 0; i < ns; i++) Ts[i] = Ts_day_start[i]; }
-            MC_ROLLED for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
-            if (snow && nonconsec) sn.st.sum_phase = 0.0;
-            const int day_row = jl * 24;
-            if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
-                MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
-                r.put_scalar(a.o_pool, day_row, pool);
-                put_potential_row(r, day_row, theta);
-                init_humidity(r, theta, T0);
-                const EnvInstant e0 = get_instant(r, jl, day_row, site_albedo);
-                r.put_scalar(a.o_sky, day_row, sky_temperature(hp.svf, e0.P, e0.rh, e0.T_ref, e0.eps_cloud, e0.cloud, e0.shade, a.has_lw != 0, e0.lw));
-                write_props(r, day_row, T0, theta, e0.P);
-            }
-            env = get_instant(r, jl, day_row, site_albedo);
-            T0[N - 1] = env.T_deep;
-            set_hour_params(env, a.day0 * 24 + day_row + 1, sd_last);
-            if (snow) {
-                if (!is_last) { double tmp = sn.st.depth; activate_snow_nodes(sn.st, sn.sc, tmp); }
-                compute_effective_depths(sn.st, sn.sc, sn.depths);
-                int fa = -1; MC_ROLLED for (int k = ns - 1; k >= 0; k--) if (sn.sc.node_depths[k] > 0.0) fa = k;
-                const double sync_temp = fa < 0 ? T0[0] : Ts[fa];
-                MC_ROLLED for (int k = 0; k < ns; k++) if (fa < 0 || k < fa) Ts[k] = sync_temp;       /* _sync_snow_to_active */
-            }
-            hp.L_prev = L_ode;
-            hoist_soil<NA, NS>(r, theta, hs);
-            /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
-            combine(I.u);
-            MC_ROLLED for (int i = 0; i < N + ns; i++) I.uprev[i] = I.u[i];
-            I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
-            I.dt = determine_initdt<NA, NS>(I, hs, hp, cn);
-            for (int i = 0; i < 24; i++) {
-                const int step = jl * 24 + i;
-                const int64_t gstep = a.day0 * 24 + step + 1;
-                MC_ROLLED for (int k = 0; k < N; k++) T0_before[k] = T0[k];
-                MC_ROLLED for (int k = 0; k < ns; k++) Ts_before[k] = Ts[k];
-                if (i > 0) hoist_soil<NA, NS>(r, theta, hs);
-                hp.L_prev = L_ode;
-                /* step_to_hour! (simulation.jl:888-903) */
-                const double target = (i + 1) * 60.0;
-                I.tstop = target;
-                while (I.t < target - 1e-10) {
-                    tsit5_step<NA, NS>(I, hs, hp, cn);
-                    bool changed = false;
-                    MC_ROLLED for (int k = 0; k < N + ns; k++) { const double c = jclamp(I.u[k], T_LO, m.T_hi); if (c != I.u[k]) { I.u[k] = c; changed = true; } }
-                    if (changed) { MC_ROLLED for (int k = 0; k < N + ns; k++) I.uprev[k] = I.u[k]; I.u_modified = true; }
-                }
-                MC_ROLLED for (int k = 0; k < ns; k++) Ts[k] = I.u[k];
-                MC_ROLLED for (int k = 0; k < N; k++) T0[k] = I.u[ns + k];
-                if (is_last) {
-                    phase_transition(N, m.depths, T0, T0_before, sum_phase, theta);
-                    MC_ROLLED for (int k = 0; k < N; k++) T0_output[k] = T0[k];
-                }
-                double snowfall_hour = 0.0, thermal_melt = 0.0, rain_melt_snow = 0.0;
-                if (snow && is_last) {                                        /* snow post-ODE block (simulation.jl:656-708) */
-                    sn.sc.sd_prev = sd_last;
-                    const double Qe = neutral_surface_evaporation(T0[0], env.T_ref, env.wind, env.rh, env.P, hp.z0, hp.lz, hp.soil_wetness);
-                    const SnowUpdateOut so = update_snow(sn.st, sn.sc, Ts, Ts_before, env.T_ref, env.rain_daily, env.P, gstep, T0[0], T0_before[0], Qe,
-                                                         m.rain_hourly != 0, env.shade, doy);
-                    snowfall_hour = so.snowfall; thermal_melt = so.thermal_melt; rain_melt_snow = so.rain_melt;
-                    if (doy > 1 && m.snow.snow_melt_factor <= 1.0) sn.Q_freeze = thermal_melt * 10.0 * LATENT_FUSION / 3600.0 * (1.0 - m.snow.snow_melt_factor);
-                    else sn.Q_freeze = 0.0;
-                    int prev_active = sn.st.active;
-                    activate_snow_nodes(sn.st, sn.sc, sn.sc.sd_cur);
-                    if (sn.st.active < prev_active) sync_inactive();
-                    double soil_surf = T0[0];
-                    snow_phase_transition(sn.st, sn.sc, Ts, env.P, soil_surf);      /* soil-surface clamp deliberately not applied upstream */
-                    MC_ROLLED for (int k = 0; k < ns; k++) if (sn.sc.node_depths[k] > 0.0 && Ts[k] > T0C) Ts[k] = T0C;     /* clamp_snow_temperatures */
-                    /* freeze_new_snow selects an empty index range upstream: no-op */
-                    adjust_snow_near_nodes(sn.st, sn.sc, gstep);
-                    prev_active = sn.st.active;
-                    activate_snow_nodes(sn.st, sn.sc, sn.sc.sd_cur);
-                    if (sn.st.active < prev_active) sync_inactive();
-                    sd_last = sn.sc.sd_cur;
-                }
-                if (i < 23) {
-                    env = get_instant(r, jl, step + 1, site_albedo);
-                    T0[N - 1] = env.T_deep;
-                    set_hour_params(env, gstep + 1, sd_last);
-                    if (snow) {
-                        if (!is_last) { double tmp = sn.st.depth; activate_snow_nodes(sn.st, sn.sc, tmp); }
-                        compute_effective_depths(sn.st, sn.sc, sn.depths);
-                    }
-                }
-                combine(I.u);
-                I.u_modified = true;
-                {   /* init_surface_fluxes! (monin_obukhov.jl:247-264): hourly warm start of the Obukhov length */
-                    const double T_air = MC_LDG(hp.fT + (int64_t)i * S);
-                    const double wind = jmax(MC_LDG(hp.fwind + (int64_t)i * S), 0.1);
-                    const double zen = jmin(90.0, nearbyint(MC_LDG(hp.fzen + (int64_t)i * S) * 1000.0) / 1000.0);
-                    const double Tsf = T0[0];
-                    if (T_air < Tsf && zen < 90.0) {
-                        const Obukhov ob = calc_obukhov(wind, hp.z0, m.zref, hp.lz, T_air - Tsf, calc_rho_cp((Tsf + T_air) / 2.0), L_ode >= 0.0 ? -0.3 : L_ode);
-                        cn.n_obukhov += ob.iters;
-                        L_ode = ob.L;
-                    }
-                }
-                bool have_infil = false;
-                if (is_last) {
-                    double rain;
-                    if (m.rain_hourly) rain = r.hourly(a.f_rain, step);
-                    else rain = (i == midnight_i) ? env.rain_daily : 0.0;
-                    bool snow_present = false;
-                    if (snow) {
-                        rain = rain * m.snow.rain_multiplier;
-                        snow_present = sn.sc.sd_cur > 0.0;
-                        const double melted_water = thermal_melt * 10.0, rain_melt_water = rain_melt_snow * sn.st.density * 10.0;
-                        if (snow_present && env.T_ref - T0C < m.snow.snow_temperature_threshold_C) pool = jclamp(pool + melted_water, 0.0, m.max_pool);
-                        else pool = jclamp(pool + rain + rain_melt_water + melted_water, 0.0, m.max_pool);
-                    } else {
-                        pool = jclamp(pool + rain, 0.0, m.max_pool);
-                    }
-                    if (dynamic) {
-                        wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn, snow_present);
-                        have_infil = true;
-                    }
-                }
-                const int out_row = step + 1;
-                if (is_last && out_row < nrows && !(i == 23 && nonconsec)) {
-                    r.put_scalar(a.o_pool, out_row, pool);
-                    MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
-                    r.put_scalar(a.o_sky, out_row, sky_T);
-                    if (have_infil) { MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); } }
-                    write_props(r, out_row, T0, theta, r.hourly(a.f_P, out_row));
-                }
-                if (is_last && snow) {                                        /* snow outputs are recorded at `step` (simulation.jl:803-813) */
-                    r.put_scalar(a.o_snow_fall, step, snowfall_hour);
-                    r.put_scalar(a.o_snow_depth, step, sn.sc.sd_cur);
-                    r.put_scalar(a.o_snow_dens, step, evolve_snow_density(sn.st));
-                    if (a.o_snow_T) { MC_ROLLED for (int k = 0; k < ns; k++) a.o_snow_T[((int64_t)step * ns + k) * S + s] = Ts[k]; }
-                }
-            }
-        }
-        tdeep_stale = env.T_deep;
-    }
-    MC_ROLLED for (int i = 0; i < N; i++) {
-        a.T[(int64_t)i * S + s] = T0[i]; a.theta[(int64_t)i * S + s] = theta[i]; a.sum_phase[(int64_t)i * S + s] = sum_phase[i];
-        if (!(isfinite(T0[i]) && isfinite(theta[i]))) flags |= MC_STATUS_NAN;
-    }
-    MC_ROLLED for (int i = 0; i < N + ns; i++) a.fsal[(int64_t)i * S + s] = I.k1[i];
-    a.pool[s] = pool; a.wetness[s] = wet_dyn; a.L_ode[s] = L_ode; a.L_prof[s] = L_prof; a.tdeep_prev[s] = tdeep_stale;
-    a.flags[s] = flags | I.flags;
-    if (snow) {
-        MC_ROLLED for (int i = 0; i < NSN; i++) { a.snow_T[(int64_t)i * S + s] = Ts[i]; a.snow_nd[(int64_t)i * S + s] = sn.sc.node_depths[i]; }
-        double* q = a.snow_state + s;
-        q[0] = sn.st.depth; q[S] = sn.st.age; q[2 * S] = sn.st.days_since; q[3 * S] = sn.st.density; q[4 * S] = sn.st.prev_density;
-        q[5 * S] = sn.st.cum_melt; q[6 * S] = sn.st.extra; q[7 * S] = (double)sn.st.active; q[8 * S] = sn.st.sum_phase; q[9 * S] = sd_last;
-        a.q_freeze[s] = sn.Q_freeze;
-    }
-}
-
-
-/* ------------------------------------------------------------------------------------------
- * solve_soil! for one site with the block-cooperative ODE phase (NoSnow, fixed day-pass counts so that every site of the block makes
- * the same sequence of coop2_rounds calls).  Everything outside the ODE hour is solve_site<NA,0> verbatim.
- * ------------------------------------------------------------------------------------------ */
-template <int NA>
-MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Shared& sh, MoistShared& ms, double* scr)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int N = m.N;
-    const int nrows = a.ndays * 24;
-    const bool dynamic = m.dynamic != 0, nonconsec = m.nonconsec != 0;
-    SiteRef r; r.a = &a; r.s = s;
-    const int64_t S = a.S;
-    const int tid = MC_TID;
-
-    HourPar hp; Own2 I;
-    const bool coop_moist = MC_COOP_MOIST && !m.flux_alg && m.niter_moist >= 1 && m.moist_max_it >= 1;      /* water-potential form of infiltration_step! */
-    int mpar = 0; (void)mpar; (void)coop_moist; (void)ms;
-    double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
-    double psi_out[NA], h_out[NA];
-    MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; MC_SCR(P_LM, i, tid) = r.node(a.lam_m, i); }
-    double pool = a.pool[s], wet_dyn = a.wetness[s], L_ode = a.L_ode[s], L_prof = a.L_prof[s], tdeep_stale = a.tdeep_prev[s];
-    int flags = a.flags[s];
-    const double site_albedo = MC_LDG(a.albedo + s);
-    hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
-    hp.sn = nullptr;
-    I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
-    I.st = 0; I.guard = 0; I.need_initdt = false; I.u_stale = false; I.kswap = false; I.uswap = false; I.stage = ST_NONE; I.q0 = 0.0; I.par = 0;
-    MC_ROLLED for (int i = 0; i < N; i++) { const double f = a.fsal[(int64_t)i * S + s]; MC_SCR(PK_A, i, tid) = f; MC_SCR(PK_B, i, tid) = f; }
-
-    auto set_day_forcing = [&](int jl) {
-        const int64_t off = (int64_t)jl * 24 * S + s;
-        hp.fP = a.f_P + off; hp.fT = a.f_T + off; hp.fwind = a.f_wind + off; hp.frh = a.f_rh + off; hp.fcloud = a.f_cloud + off;
-        hp.fsolar = a.f_solar + off; hp.fdiff = a.f_diffuse + off; hp.fzen = a.f_zen + off; hp.fszen = a.f_szen + off;
-    };
-    auto tins_mean = [&](int jl) { double ssum = 0.0; MC_ROLLED for (int h = 0; h < 24; h++) ssum += r.hourly(a.f_T, jl * 24 + h); ssum += r.hourly(a.f_T, jl * 24 + 23); return ssum / 25.0; };
-    double sky_T = 0.0;
-    auto set_hour_params = [&](const EnvInstant& e) {
-        hp.shade = e.shade; hp.eps_surf = e.eps_surf; hp.eps_cloud = e.eps_cloud;
-        hp.albedo = e.albedo; hp.soil_wetness = dynamic ? wet_dyn : e.wet_daily;
-        sky_T = sky_temperature(hp.svf, e.P, e.rh, e.T_ref, e.eps_cloud, e.cloud, e.shade, a.has_lw != 0, e.lw);
-    };
-    /* theta-only soil property terms of the coming ODE hour, straight into the block's scratch (hoist_soil) */
-    auto hoist_publish = [&]() {
-        MC_ROLLED for (int i = 0; i < N; i++) {
-            const double bd = r.node(a.bd, i), md = r.node(a.md, i);
-            const double th = theta[i];
-            const double cp = bd / md * r.node(a.c_m, i) + th * WATER_CP;
-            const double rho = th * WATER_RHO + bd;
-            MC_SCR(P_CAP, i, tid) = (rho * cp) * m.dzc[i] / 2.0;
-            MC_SCR(P_TH, i, tid) = th; MC_SCR(P_PM, i, tid) = bd / md; MC_SCR(P_PG, i, tid) = jmax(0.0, 1.0 - th - bd / md);
-            MC_SCR(P_FW, i, tid) = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
-        }
-    };
-
-    EnvInstant env;
-    if (a.day0 == 0) {
-        /* init(): SciMLBase.init evaluates the RHS once at prototype parameters to seed fsalfirst (simulation.jl:196-238,853-860) */
-        set_day_forcing(0);
-        env = get_instant(r, 0, 0, site_albedo);
-        MC_ROLLED for (int i = 0; i < N; i++) MC_SCR(I.uparr(), i, tid) = a.has_init_T ? T0[i] : 280.0;
-        hoist_publish();
-        hp.shade = env.shade; hp.eps_surf = env.eps_surf; hp.eps_cloud = env.eps_cloud; hp.soil_wetness = 0.0; hp.albedo = site_albedo; hp.L_prev = L_ode;
-        {
-            Counters scratch = {};
-            I.st = 10; I.stage = ST_REFRESH; I.req_t = 0.0;
-            coop2_rounds<NA>(I, true, hp, sh, scr, scratch);
-        }
-        /* solve_soil! pre-loop (simulation.jl:395-452) */
-        if (!a.has_init_T) { const double t_init = tins_mean(0); MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_init; }
-        MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-        write_props(r, 0, T0, theta, 101325.0);
-        put_potential_row(r, 0, theta);
-        MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, 0, i, T0[i]); r.put_node(a.o_theta, 0, i, theta[i]); }
-        init_humidity(r, theta, T0);
-        tdeep_stale = env.T_deep;
-        pool = 0.0;
-    }
-
-    for (int jl = 0; jl < a.ndays; jl++) {
-        const int64_t j = a.day0 + jl;
-        set_day_forcing(jl);
-        const int niter = nonconsec ? m.iters_per_day : ((m.spinup && j == 0) ? m.conv_iters : 1);
-        int noon_i = 0; double best = r.hourly(a.f_zen, jl * 24);
-        MC_ROLLED for (int i = 1; i < 24; i++) { const double zz = r.hourly(a.f_zen, jl * 24 + i); if (zz < best) { best = zz; noon_i = i; } }
-        const int midnight_i = (noon_i + 12) % 24;
-        if (nonconsec) {                                                      /* per-day resets (simulation.jl:480-516) */
-            MC_ROLLED for (int i = 0; i < N; i++) sum_phase[i] = 0.0;
-            if (!dynamic && a.has_presc) { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = MC_LDG(a.presc + ((int64_t)jl * N + i) * S + s); }
-            else { MC_ROLLED for (int i = 0; i < N; i++) theta[i] = r.node(a.init_theta, i); }
-            const double t_reset = tins_mean(jl);
-            if (!a.has_init_T) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = t_reset; }
-            else { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = r.node(a.init_T, i); }
-        }
-        T0[N - 1] = tdeep_stale;
-        MC_ROLLED for (int i = 0; i < N; i++) { T0_day_start[i] = T0[i]; sum_phase_day_start[i] = sum_phase[i]; }
-        for (int iter = 1; iter <= niter; iter++) {                           /* fixed day-pass count (block-uniform) */
-            cn.n_day_passes++;
-            const bool is_last = iter >= niter;
-            if (!nonconsec) { MC_ROLLED for (int i = 0; i < N; i++) T0[i] = T0_day_start[i]; }
-            MC_ROLLED for (int i = 0; i < N; i++) { sum_phase[i] = sum_phase_day_start[i]; T0_output[i] = T0[i]; }
-            const int day_row = jl * 24;
-            if (is_last) {                                                    /* day row 1 = state at the start of the output pass (:557-592) */
-                MC_ROLLED for (int i = 0; i < N; i++) { r.put_node(a.o_T, day_row, i, T0[i]); r.put_node(a.o_theta, day_row, i, theta[i]); }
-                r.put_scalar(a.o_pool, day_row, pool);
-                put_potential_row(r, day_row, theta);
-                init_humidity(r, theta, T0);
-                const EnvInstant e0 = get_instant(r, jl, day_row, site_albedo);
-                r.put_scalar(a.o_sky, day_row, sky_temperature(hp.svf, e0.P, e0.rh, e0.T_ref, e0.eps_cloud, e0.cloud, e0.shade, a.has_lw != 0, e0.lw));
-                write_props(r, day_row, T0, theta, e0.P);
-            }
-            env = get_instant(r, jl, day_row, site_albedo);
-            T0[N - 1] = env.T_deep;
-            set_hour_params(env);
-            /* reinit!(integrator, u0; t0=0, reset_dt=true, reinit_cache=false): k1 (fsalfirst) deliberately stays stale */
-            MC_ROLLED for (int i = 0; i < N; i++) { MC_SCR(PU_A, i, tid) = T0[i]; MC_SCR(PU_B, i, tid) = T0[i]; }
-            I.u_stale = false;
-            I.t = 0.0; I.iter = 0; I.u_modified = false; I.accept = false; I.qold = 1e-4; I.q11 = 1.0; I.tstop = 1440.0;
-            I.need_initdt = true;                                             /* the two init-dt RHS calls join hour 0's rounds */
-            for (int i = 0; i < 24; i++) {
-                const int step = jl * 24 + i;
-                MC_ROLLED for (int k = 0; k < N; k++) T0_before[k] = T0[k];
-                hoist_publish();
-                hp.L_prev = L_ode;
-                /* step_to_hour! (simulation.jl:888-903), cooperatively */
-                I.target = (i + 1) * 60.0; I.tstop = I.target; I.st = 0;
-                {
-                    const bool pend = coop2_advance<NA>(I, sh, scr, cn);
-                    coop2_rounds<NA>(I, pend, hp, sh, scr, cn);
-                }
-                { const int U = I.uarr(); MC_ROLLED for (int k = 0; k < N; k++) T0[k] = MC_SCR(U, k, tid); }
-                if (is_last) {
-                    phase_transition(N, m.depths, T0, T0_before, sum_phase, theta);
-                    MC_ROLLED for (int k = 0; k < N; k++) T0_output[k] = T0[k];
-                }
-                if (i < 23) {
-                    env = get_instant(r, jl, step + 1, site_albedo);
-                    T0[N - 1] = env.T_deep;
-                    set_hour_params(env);
-                }
-                { const int U = I.uarr(); MC_ROLLED for (int k = 0; k < N; k++) MC_SCR(U, k, tid) = T0[k]; }
-                I.u_modified = true;
-                {   /* init_surface_fluxes! (monin_obukhov.jl:247-264): hourly warm start of the Obukhov length */
-                    const double T_air = MC_LDG(hp.fT + (int64_t)i * S);
-                    const double wind = jmax(MC_LDG(hp.fwind + (int64_t)i * S), 0.1);
-                    const double zen = jmin(90.0, nearbyint(MC_LDG(hp.fzen + (int64_t)i * S) * 1000.0) / 1000.0);
-                    const double Tsf = T0[0];
-                    if (T_air < Tsf && zen < 90.0) {
-                        const Obukhov ob = calc_obukhov(wind, hp.z0, m.zref, hp.lz, T_air - Tsf, calc_rho_cp((Tsf + T_air) / 2.0), L_ode >= 0.0 ? -0.3 : L_ode);
-                        cn.n_obukhov += ob.iters;
-                        L_ode = ob.L;
-                    }
-                }
-                bool have_infil = false;
-                if (is_last) {
-                    double rain;
-                    if (m.rain_hourly) rain = r.hourly(a.f_rain, step);
-                    else rain = (i == midnight_i) ? env.rain_daily : 0.0;
-                    pool = jclamp(pool + rain, 0.0, m.max_pool);
-                    if (dynamic) {
-#if MC_COOP_MOIST
-                        if (coop_moist) wet_dyn = soil_water_hour_coop<NA>(r, env, T0, theta, pool, hp.z0, L_prof, psi_out, h_out, flags, cn, sh, ms, scr, mpar);
-                        else
-#endif
-                        wet_dyn = soil_water_hour<NA>(r, env, T0, theta, pool, wet_dyn, hp.z0, L_prof, psi_out, h_out, flags, cn, false);
-                        have_infil = true;
-                    }
-                }
-                const int out_row = step + 1;
-                if (is_last && out_row < nrows && !(i == 23 && nonconsec)) {
-                    r.put_scalar(a.o_pool, out_row, pool);
-                    MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_T, out_row, k, T0_output[k]); r.put_node(a.o_theta, out_row, k, theta[k]); }
-                    r.put_scalar(a.o_sky, out_row, sky_T);
-                    if (have_infil) { MC_ROLLED for (int k = 0; k < N; k++) { r.put_node(a.o_psi, out_row, k, psi_out[k]); r.put_node(a.o_h, out_row, k, h_out[k]); } }
-                    write_props(r, out_row, T0, theta, r.hourly(a.f_P, out_row));
-                }
-            }
-        }
-        tdeep_stale = env.T_deep;
-    }
-    MC_ROLLED for (int i = 0; i < N; i++) {
-        a.T[(int64_t)i * S + s] = T0[i]; a.theta[(int64_t)i * S + s] = theta[i]; a.sum_phase[(int64_t)i * S + s] = sum_phase[i];
-        if (!(isfinite(T0[i]) && isfinite(theta[i]))) flags |= MC_STATUS_NAN;
-    }
-    { const int K1 = I.k1arr(); MC_ROLLED for (int i = 0; i < N; i++) a.fsal[(int64_t)i * S + s] = MC_SCR(K1, i, tid); }
-    a.pool[s] = pool; a.wetness[s] = wet_dyn; a.L_ode[s] = L_ode; a.L_prof[s] = L_prof; a.tdeep_prev[s] = tdeep_stale;
-    a.flags[s] = flags | I.flags;
-}
-
-
-/* ------------------------------------------------------------------------------------------
- * solve_air! (src/simulation.jl:822-851) for the rows of one chunk of site s: atmospheric_surface_profile! (monin_obukhov.jl:85-206)
- * at every height from the row's final surface temperature.  Runs as its own small kernel after the soil kernel of the chunk.
- * ------------------------------------------------------------------------------------------ */
-MC_DEV void solve_air_site(const KArgs& a, int64_t s, Counters& cn)
-{
-    const DevModel& m = MC_CONST_MODEL;
-    const int N = m.N, ns = a.n_snow, nh = m.n_heights, H = a.ndays * 24;
-    const int64_t S = a.S;
-    const double z = m.zref, z0 = MC_LDG(a.z0 + s), kappa = m.kappa, gamma = m.gamma;
-    const double lzr = mcm::log(z / z0);
-    int ref_idx = -1; for (int k = nh - 1; k >= 0; k--) if (m.heights[k] == z) ref_idx = k;
-    double L_air = a.L_air[s];
-    for (int row = 0; row < H; row++) {
-        const bool has_snow = ns > 0 && a.o_snow_depth && a.o_snow_depth[(int64_t)row * S + s] > 0.0;
-        const double T_surf = has_snow ? a.o_snow_T[((int64_t)row * ns + 0) * S + s] : a.o_T[((int64_t)row * N + 0) * S + s];
-        const double T_ref = MC_LDG(a.f_T + (int64_t)row * S + s), wind = MC_LDG(a.f_wind + (int64_t)row * S + s);
-        const double rh = MC_LDG(a.f_rh + (int64_t)row * S + s), zen = MC_LDG(a.f_zen + (int64_t)row * S + s);
-        const double dT = T_ref - T_surf;
-        const double rho_cp = calc_rho_cp((T_surf + T_ref) / 2.0);
-        double Tair[MC_MAX_HEIGHTS], Qc, ustar;
-        if (T_ref >= T_surf || zen >= 90.0) {
-            ustar = jmax(kappa * wind / lzr, 1.0e-6);
-            const double Stb = 0.64 / lzr, Sts = sublayer_stanton(z0, ustar);
-            Qc = convective_flux(rho_cp, dT, ustar, Stb, Sts);
-            const double Tz0 = (T_ref * Stb + T_surf * Sts) / (Stb + Sts);
-            for (int k = 0; k < nh; k++) {
-                const double h = m.heights[k]; double v;
-                if (h < z0) { v = 0.0; Tair[k] = T_surf + (Tz0 - T_surf) * (h / z0); }
-                else if (k == ref_idx) { v = wind; Tair[k] = T_ref; }
-                else { v = (ustar / kappa) * mcm::log(h / z0 + 0.0); Tair[k] = Tz0 + (T_ref - Tz0) * mcm::log(h / z0) / lzr; }
-                if (a.o_wind) a.o_wind[((int64_t)row * nh + k) * S + s] = v;
-            }
-        } else {
-            const Obukhov ob = calc_obukhov(wind, z0, z, lzr, dT, rho_cp, L_air);
-            cn.n_obukhov += ob.iters;
-            L_air = ob.L; Qc = ob.Q; ustar = ob.ustar;
-            const double Tz0 = (T_ref * ob.Stb + T_surf * ob.Sts) / (ob.Stb + ob.Sts);
-            for (int k = 0; k < nh; k++) {
-                const double h = m.heights[k]; double v;
-                if (h < z0) { v = 0.0; Tair[k] = T_surf + (Tz0 - T_surf) * (h / z0); }
-                else if (k == ref_idx) { v = wind; Tair[k] = T_ref; }
-                else {
-                    const double x = calc_phi_m(h, gamma, ob.L);
-                    const double psi_m1 = calc_psi_m(x), psi_h2 = calc_psi_h(x);
-                    const double hr = h / z0;
-                    v = (ob.ustar / kappa) * jmax(mcm::log(hr) - psi_m1, 1e-6);
-                    Tair[k] = Tz0 + (T_ref - Tz0) * jmax(mcm::log(hr) - psi_h2, 1e-6) / (mcm::log(z / z0) - ob.psi_h);
-                }
-                if (a.o_wind) a.o_wind[((int64_t)row * nh + k) * S + s] = v;
-            }
-        }
-        const double e_ref = goff_gratch(T_ref) * rh;
-        for (int k = 0; k < nh; k++) {
-            if (a.o_air_T) a.o_air_T[((int64_t)row * nh + k) * S + s] = Tair[k];
-            if (a.o_rh) a.o_rh[((int64_t)row * nh + k) * S + s] = jclamp(e_ref / goff_gratch(Tair[k]) * 1.0, 0.0, 1.0);
-        }
-        if (a.o_qc) a.o_qc[(int64_t)row * S + s] = Qc;
-        if (a.o_ustar) a.o_ustar[(int64_t)row * S + s] = ustar;
-    }
-    a.L_air[s] = L_air;
-}
-
-/* host side: flatten mc_model_desc into DevModel (run once per handle) */
-static inline void build_dev_model(const mc_model_desc& md, DevModel& d)
-{
-    memset(&d, 0, sizeof(d));
-    d.N = md.n_soil;
-    d.dynamic = md.moisture_strategy == MC_MOIST_DYNAMIC;
-    d.nonconsec = md.time_mode == MC_TIME_NONCONSECUTIVE;
-    d.conv_kind = md.convergence_kind; d.conv_iters = md.convergence_iterations; d.iters_per_day = md.iterations_per_day;
-    d.spinup = md.spinup_first_day; d.rain_hourly = md.rainfall_schedule == MC_RAIN_HOURLY;
-    d.flux_alg = md.infiltration_algorithm == MC_INFIL_MATRIC_FLUX_POTENTIAL;
-    d.swinbank = md.atmospheric_radiation == MC_ATMRAD_SWINBANK;
-    d.moist_max_it = md.moisture_max_iterations;
-    d.niter_moist = (int)(3600.0 / md.moisture_timestep_s);
-    const int N = md.n_soil;
-    double ld[MC_MAX_SOIL_NODES + 1];
-    MC_ROLLED for (int i = 0; i < N; i++) { d.depths[i] = md.depths_m[i]; ld[i] = md.depths_m[i]; }
-    ld[N] = 0.0;                                          /* zero sentinel (heat_transport_1d.jl:127,173) */
-    MC_ROLLED for (int i = 0; i < N; i++) {
-        d.dzc[i] = i == 0 ? ld[1] : ld[i + 1] - ld[i - 1];
-        d.dzg[i] = ld[i + 1] - ld[i];
-    }
-    {   /* same expressions as soil_water_hour: depth[1] = -1e10, depth[2] = 0, depth[i+1] = depths[i-1], depth[L+1] = 1e20 */
-        const int L = N;
-        auto depth_final = [&](int i) -> double { return i == 1 ? -1e10 : (i == 2 ? 0.0 : (i == L + 1 ? 1e20 : d.depths[i - 2])); };
-        auto depth_mass = [&](int i) -> double { return i <= 2 ? 0.0 : d.depths[i - 2]; };
-        for (int i = 0; i < MAXN + 2; i++) { d.mdz[i] = 0.0; d.mmass[i] = 0.0; }
-        for (int i = 1; i <= L; i++) d.mdz[i] = depth_final(i + 1) - depth_final(i);
-        for (int i = 2; i <= L; i++) d.mmass[i] = WATER_RHO * (depth_mass(i + 1) - depth_mass(i - 1)) / 2.0;
-    }
-    d.zref = md.reference_height_m; d.zloc = md.local_height_m; d.reltol = md.reltol; d.abstol = md.abstol;
-    d.T_hi = md.maximum_surface_temperature_K;
-    d.ga = md.de_vries_shape_factor; d.gc = 1.0 - 2.0 * d.ga; d.recirc_pow = md.recirculation_power; d.theta0 = md.return_flow_threshold;
-    d.root_res = md.root_resistance; d.PC = md.stomatal_closure_potential; d.RL = md.leaf_resistance;
-    d.SP = md.stomatal_stability_parameter; d.root_radius = md.root_radius;
-    d.kappa = md.karman_constant; d.gamma = md.dyer_constant; d.conv_tol = md.convergence_tolerance_K;
-    d.moist_tol = md.moisture_tolerance; d.moist_dt = md.moisture_timestep_s; d.max_pool = md.max_surface_pool;
-    const mc_fluid_constants& f = md.fluid;
-    d.Mw = f.molar_mass_water; d.eps = f.molar_mass_water / f.molar_mass_air; d.dep = f.ideal_gas_departure;
-    d.cpa = f.cp_dry_air; d.cpv = f.cp_water_vapour; d.R = f.gas_constant; d.sigma = f.stefan_boltzmann; d.g = f.standard_gravity;
-    d.P0 = f.standard_pressure; d.Lv_a = f.latent_heat_a; d.Lv_b = f.latent_heat_b; d.Hv_a = f.molar_latent_heat_a; d.Hv_b = f.molar_latent_heat_b;
-    d.Ma_over_R = f.molar_mass_air / f.gas_constant;
-    d.schmidt_factor = mcm::pow(0.71 / 0.60, 0.666);
-    d.snow = md.snow;
-    d.n_heights = md.n_heights;
-    for (int i = 0; i < MC_MAX_HEIGHTS; i++) d.heights[i] = i < md.n_heights ? md.heights_m[i] : 0.0;
-}
-
+#include "mc_physics.cuh"
+#include "mc_snow.cuh"
+#include "mc_tsit5.cuh"
+#include "mc_coop_ode.cuh"
+#include "mc_moisture.cuh"
+#include "mc_site.cuh"
 
 } // namespace mcd

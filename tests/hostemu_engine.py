@@ -11,8 +11,9 @@ from microclimate_jl_b200 import marshal as M
 _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
 _SO = os.path.join(_HERE, "libmc_hostemu.so")
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
-_DEPS = [os.path.join(_HERE, "hostemu.cpp"), os.path.join(_ROOT, "microclimate.jl_b200", "csrc", "mc_device.cuh"), os.path.join(_ROOT, "include", "mc_math.h"),
-         os.path.join(_ROOT, "include", "microclimate_b200.h")]
+_CSRC = os.path.join(_ROOT, "microclimate.jl_b200", "csrc")
+_DEPS = [os.path.join(_HERE, "hostemu.cpp"), os.path.join(_ROOT, "include", "mc_math.h"), os.path.join(_ROOT, "include", "microclimate_b200.h")] + \
+        sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh"))
 
 
 def build(force=False, so=_SO, defs=()):
