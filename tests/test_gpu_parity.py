@@ -194,6 +194,20 @@ def test_other_node_counts_match_oracle(SoilEngine, n_nodes):
     parity.assert_bit_identical(out, ref)
 
 
+def test_capped_newton_solves_match_oracle(SoilEngine):
+    """Sandy sites whose moisture Newton solve runs to the 500-iteration cap (1260, 1331, 1353 of the 4096-site grid): the kernel skips whole
+    periods of exactly periodic orbits; outputs, status flags and iteration counts must be those of the oracle's full loop."""
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    sites = syn.make_sites(1256, 1360, 4096, with_sand=True)
+    forcing = syn.make_forcing(1256, 1360, 4096, 0, 3)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    out, eg = parity.run(SoilEngine, desc, sites, forcing)
+    assert (ref.status != 0).any()
+    parity.assert_bit_identical(out, ref)
+    assert np.array_equal(out.status, ref.status)
+    assert eo.counters()["n_newton_iter"] == eg.counters()["n_newton_iter"]
+
+
 def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     """The block-cooperative kernel must not depend on how sites fall into blocks: full-machine blocks of 1024 threads with a ragged last
     block, a grid-stride loop over several batches per block, and the legacy per-site kernel all give the oracle's bits."""
