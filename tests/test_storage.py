@@ -1,0 +1,105 @@
+"""On-disk containers (microclimate.jl_b200/storage.py): round trips, zero-copy chunk reads, site sharding, and a
+time-chunked run driven from files with a checkpoint in the middle — bit-identical to the in-memory run."""
+import numpy as np
+
+import parity
+from hostemu_engine import HostEmuEngine
+from microclimate_jl_b200 import _abi as A
+from microclimate_jl_b200 import marshal as M
+from microclimate_jl_b200 import storage as st
+from microclimate_jl_b200 import synthetic as syn
+
+S, ND = 40, 3
+
+
+def _problem():
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    return desc, syn.make_sites(0, S, S, with_sand=True), syn.make_forcing(0, S, S, 0, ND)
+
+
+def test_round_trips_and_zero_copy_reads(tmp_path):
+    desc, sites, forcing = _problem()
+    st.save_sites(tmp_path / "sites.mcb", sites, note="synthetic")
+    st.save_forcing(tmp_path / "forcing.mcb", forcing, day0=0)
+    s2 = st.load_sites(tmp_path / "sites.mcb")
+    for f in sites.SITE_FIELDS + sites.NODE_FIELDS + ("initial_soil_moisture", "initial_soil_temperature"):
+        assert np.array_equal(getattr(sites, f), getattr(s2, f)), f
+    c = st.Container(tmp_path / "forcing.mcb")
+    assert c.header["S"] == S and c.header["ndays"] == ND and all(e["offset"] % st.ALIGN == 0 for e in c.header["arrays"])
+    f2 = st.load_forcing(tmp_path / "forcing.mcb", 1, 3)                       # days 1..2, all sites: contiguous file ranges
+    assert isinstance(f2.reference_temperature, np.memmap) and f2.reference_temperature.flags.c_contiguous
+    assert f2.longwave_radiation is None and f2.albedo_daily is None           # unselected arrays stay absent
+    ref = forcing.day_slice(1, 3)
+    for f in A.FORCING_HOURLY + A.FORCING_DAILY:
+        a, b = getattr(ref, f), getattr(f2, f)
+        assert (a is None and b is None) or np.array_equal(a, b), f
+    assert np.array_equal(f2.day_of_year, ref.day_of_year)
+    f3 = st.load_forcing(tmp_path / "forcing.mcb", 0, 2, 7, 29)                # a ragged site shard
+    ref = forcing.day_slice(0, 2).site_slice(7, 29)
+    for f in A.FORCING_HOURLY + A.FORCING_DAILY:
+        a, b = getattr(ref, f), getattr(f3, f)
+        assert (a is None and b is None) or (np.array_equal(a, b) and b.flags.c_contiguous), f
+
+
+def test_file_driven_chunked_run_with_checkpoint_is_bit_identical(tmp_path):
+    desc, sites, forcing = _problem()
+    fields = ("soil_temperature", "soil_moisture", "surface_water", "soil_water_potential")
+    whole, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=fields)
+    st.save_sites(tmp_path / "sites.mcb", sites)
+    st.save_forcing(tmp_path / "forcing.mcb", forcing)
+
+    # leg 1: days 0-1 from the files, outputs and a state checkpoint to disk
+    e1 = HostEmuEngine(desc, S)
+    e1.set_sites(st.load_sites(tmp_path / "sites.mcb"))
+    o1 = M.OutputBatch(2, desc.n_soil, S, fields)
+    e1.step_days(0, st.load_forcing(tmp_path / "forcing.mcb", 0, 2), o1)
+    st.save_outputs(tmp_path / "out_000.mcb", o1, day0=0)
+    st.save_state(tmp_path / "state_002.mcb", e1.get_state())
+    e1.close()
+
+    # leg 2: a fresh engine resumes from the checkpoint and integrates day 2
+    ck = st.load_state(tmp_path / "state_002.mcb")
+    assert int(ck.days_done[0]) == 2
+    e2 = HostEmuEngine(desc, S)
+    e2.set_sites(st.load_sites(tmp_path / "sites.mcb"))
+    e2.set_state(ck)
+    o2 = M.OutputBatch(1, desc.n_soil, S, fields)
+    e2.step_days(2, st.load_forcing(tmp_path / "forcing.mcb", 2, 3), o2)
+    st.save_outputs(tmp_path / "out_002.mcb", o2, day0=2)
+
+    a, b = st.load_outputs(tmp_path / "out_000.mcb"), st.load_outputs(tmp_path / "out_002.mcb")
+    assert isinstance(a.soil_temperature, np.memmap)
+    for f in ("soil_temperature", "soil_moisture", "surface_water"):
+        assert np.array_equal(np.concatenate([getattr(a, f), getattr(b, f)]), getattr(whole, f)), f
+    # soil_water_potential: the first row of a chunk is the upstream quirk documented in tests/test_kernel_hostemu.py -> compare from row 1 on
+    assert np.array_equal(b.soil_water_potential[1:], whole.soil_water_potential[49:])
+    assert np.array_equal(a.status | b.status, whole.status)
+
+
+def test_site_shards_of_one_file_equal_the_whole(tmp_path):
+    desc, sites, forcing = _problem()
+    fields = ("soil_temperature", "soil_moisture")
+    whole, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=fields)
+    st.save_sites(tmp_path / "sites.mcb", sites)
+    st.save_forcing(tmp_path / "forcing.mcb", forcing)
+    for lo, hi in ((0, 17), (17, 40)):                                         # what two ranks would read
+        part, _ = parity.run(HostEmuEngine, desc, st.load_sites(tmp_path / "sites.mcb", lo, hi),
+                             st.load_forcing(tmp_path / "forcing.mcb", 0, ND, lo, hi), fields=fields)
+        assert np.array_equal(part.soil_temperature, whole.soil_temperature[:, :, lo:hi])
+        assert np.array_equal(part.soil_moisture, whole.soil_moisture[:, :, lo:hi])
+
+
+def test_dataset_cli_matches_in_memory_run(tmp_path):
+    """tools/dataset.py make + run (kernel body on the CPU through the test harness) == the in-memory run of the same grid."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = str(tmp_path / "ds")
+    subprocess.check_call([sys.executable, "tools/dataset.py", "make", d, "--sites", "16", "--days", "2", "--chunk", "1"], cwd=root)
+    subprocess.check_call([sys.executable, "tools/dataset.py", "run", d, "--engine", "hostemu"], cwd=root)
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    whole, _ = parity.run(HostEmuEngine, desc, syn.make_sites(0, 16, 16), syn.make_forcing(0, 16, 16, 0, 2), fields=("soil_temperature", "soil_moisture"))
+    got = np.concatenate([st.load_outputs(os.path.join(d, f"out_d{k:04d}_s0-16.mcb")).soil_temperature for k in (0, 1)])
+    assert np.array_equal(got, whole.soil_temperature)
+    assert int(st.load_state(os.path.join(d, "state_s0-16.mcb")).days_done[0]) == 2
