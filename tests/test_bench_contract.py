@@ -1,0 +1,37 @@
+"""bench.py's reference arm runs on CPU (the oracle on all host cores): check the one-JSON-line contract the driver parses, and that the
+product arm refuses to run without a CUDA device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--sites", "64", "--cpu-sites", "64", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines                                  # nothing but the JSON line on stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "site-days/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"] == "site-days/sec (hourly soil T+moisture)" and d["dtype"] == "f64" and d["scaling"] == "weak"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "site-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_only_rank_zero_works_under_torchrun_env():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    p = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--sites", "64", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=120, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_product_arm_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        return
+    p = subprocess.run([sys.executable, "bench.py", "--sites", "64", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and "no CPU path" in (p.stderr + p.stdout)
