@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_c
 {
     __shared__ mcd::Coop2Shared sh;
     __shared__ mcd::MoistShared ms;
-    if (threadIdx.x == 0) { sh.count[0] = 0; sh.count[1] = 0; ms.countU[0] = ms.countU[1] = ms.countF[0] = ms.countF[1] = ms.alive[0] = ms.alive[1] = 0; }
+    if (threadIdx.x == 0) { for (int k = 0; k < 3; k++) { sh.count[k] = 0; ms.countU[k] = 0; ms.countF[k] = 0; ms.alive[k] = 0; } }
+    int rot_ode = 0, rot_moist = 0;        /* rotation of the list counters: block-uniform, carried across site batches */
     __syncthreads();
     mcd::Counters cn = {};
     double* scr = a.coop_scr + (size_t)blockIdx.x * (MC_COOP_ROWS(NA) * blockDim.x);
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_c
         const bool valid = s < a.s_end;
         if (!valid) s = a.s_end - 1;
         mcd::Counters c1 = {};
-        mcd::solve_site_coop2<NA>(a, s, c1, sh, ms, scr);
+        mcd::solve_site_coop2<NA>(a, s, c1, sh, ms, scr, rot_ode, rot_moist);
         if (valid) {
             cn.n_rhs += c1.n_rhs; cn.n_accept += c1.n_accept; cn.n_reject += c1.n_reject; cn.n_obukhov += c1.n_obukhov;
             cn.n_newton += c1.n_newton; cn.n_infil += c1.n_infil; cn.n_day_passes += c1.n_day_passes;

@@ -19,6 +19,40 @@ constexpr int COOP_TB = MC_COOP_TB;
 
 struct RhsCtx { double P, T_air, wind, zen, solar, cloud, rh, szen, fd; };
 
+/* Block-level list building: every thread with `pred` appends its id to `list`, positions from `*counter` (shared memory).  On the GPU one
+ * shared-memory atomic per warp (ballot + popc); on the host (tests/hostemu, one or several OS threads per "block") a plain atomic. */
+MC_DEV void block_list_append(bool pred, int* list, int* counter, int tid)
+{
+#if defined(__CUDACC__)
+    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+    const int lane = tid & 31;
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) list[base + __popc(bal & ((1u << lane) - 1u))] = tid;
+#else
+    if (pred) list[__atomic_fetch_add(counter, 1, __ATOMIC_RELAXED)] = tid;
+#endif
+}
+MC_DEV void block_count_add(bool pred, int* counter, int tid)
+{
+#if defined(__CUDACC__)
+    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+    if ((tid & 31) == 0 && bal) atomicAdd(counter, __popc(bal));
+#else
+    (void)tid;
+    if (pred) __atomic_fetch_add(counter, 1, __ATOMIC_RELAXED);
+#endif
+}
+MC_DEV void block_flag_or(int* flag, int v)
+{
+#if defined(__CUDACC__)
+    atomicOr(flag, v);
+#else
+    __atomic_fetch_or(flag, v, __ATOMIC_RELAXED);
+#endif
+}
+
 /* ==========================================================================================================================
  * The integrator's vectors (k1..k7, u, uprev) live in the block's scratch instead of thread-local memory and EVERY node loop of
  * the ODE hour is an item pass over (requesting site, node):
@@ -36,7 +70,7 @@ enum { PK_A = 0, PK_2, PK_3, PK_4, PK_5, PK_6, PK_B, PU_A, PU_B, P_T, P_LAM, P_Q
 enum { ST_NONE = 0, ST_INIT_F0, ST_INIT_F1, ST_REFRESH, ST_2, ST_3, ST_4, ST_5, ST_6, ST_7 };
 
 struct Coop2Shared {
-    int list[COOP_TB]; int count[2]; int clampflag[COOP_TB];
+    int list[COOP_TB]; int count[3]; int clampflag[COOP_TB];      /* count: three rotating list counters (see coop2_rounds) */
     double P[COOP_TB], p0p[COOP_TB], pp0[COOP_TB], dt[COOP_TB];
     unsigned char code[COOP_TB];        /* stage | kswap << 4 | uswap << 5 */
 };
@@ -92,13 +126,7 @@ MC_DEV void coop2_item_stage(const Coop2Shared& sh, Coop2Shared& shw, double* sc
     default: x = up; break;                       /* ST_INIT_F0, ST_REFRESH: the RHS at the current state (u == uprev there) */
     }
     const double Tc = jclamp(x, T_LO, m.T_hi);
-    if (stage == ST_7 && Tc != x) {
-#if defined(__CUDACC__)
-        atomicOr(&shw.clampflag[o], 1);
-#else
-        shw.clampflag[o] |= 1;
-#endif
-    }
+    if (stage == ST_7 && Tc != x) block_flag_or(&shw.clampflag[o], 1);
     MC_SCR(P_T, i, o) = Tc;
     if (i < m.N - 1)
         MC_SCR(P_LAM, i, o) = soil_conductivity(Tc, sh.P[o], sh.p0p[o], sh.pp0[o], MC_SCR(P_TH, i, o), MC_SCR(P_PM, i, o), MC_SCR(P_PG, i, o),
@@ -332,29 +360,22 @@ MC_DEV void coop2_rounds(Own2& I, bool pending, const HourPar& hp, Coop2Shared& 
     RhsCtx R;
     const DevModel& m = MC_CONST_MODEL; const int N = m.N;
     const int tid = MC_TID, TB = MC_TB;
-    int par = I.par;     /* list-counter parity: block-uniform, carried across calls (the counter a round leaves non-zero is cleared by the next) */
+    /* The request list of round r is counted in sh.count[r % 3]; after the round's barrier thread 0 clears the counter of round r + 2.  Three
+     * counters, cleared two rounds ahead, make every access race-free without extra barriers: the counter a thread is still reading (round r)
+     * is not written before round r + 3's appends, and the counter of round r + 1 was cleared during round r - 1.  The rotation index is
+     * block-uniform and carried across calls and site batches (every thread of a block runs the same number of rounds). */
+    int par = I.par;
     for (;;) {
         if (pending) {
             coop2_pre(hp, I.req_t, R, sh);
             sh.code[tid] = (unsigned char)(I.stage | (I.kswap ? 16 : 0) | (I.uswap ? 32 : 0));
         }
-#if defined(__CUDACC__)
-        {   /* append the requesting sites to the round's list: one shared atomic per warp */
-            const unsigned bal = __ballot_sync(0xffffffffu, pending);
-            const int lane = tid & 31;
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&sh.count[par], __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pending) sh.list[base + __popc(bal & ((1u << lane) - 1u))] = tid;
-        }
-        __syncthreads();
+        block_list_append(pending, sh.list, &sh.count[par], tid);        /* the requesting sites of this round */
+        MC_BLOCK_SYNC();
         const int A = sh.count[par];
-        if (tid == 0) sh.count[par ^ 1] = 0;
-#else
-        const int A = pending ? 1 : 0;
-        sh.list[0] = tid;
-#endif
-        if (A == 0) break;                        /* parity stays: count[par] is still zero for the next call */
+        if (tid == 0) sh.count[par == 0 ? 2 : par - 1] = 0;      /* (par + 2) % 3 */
+        par = par == 2 ? 0 : par + 1;
+        if (A == 0) break;
         /* item j = node * A + (index into the list); j / A by multiplication (exact for j < 2^20, A <= 1024) */
         const unsigned long long magic = (0x100000000ull + (unsigned)A - 1ull) / (unsigned)A;
         {   /* pass 1: stage vector, clamp, conductivity */
@@ -374,7 +395,6 @@ MC_DEV void coop2_rounds(Own2& I, bool pending, const HourPar& hp, Coop2Shared& 
         }
         MC_BLOCK_SYNC();
         if (pending) pending = coop2_advance<NA>(I, sh, scr, cn);
-        par ^= 1;
     }
     I.par = par;
 }

@@ -71,9 +71,17 @@
 #define MC_UNROLL4
 #define MC_THOMAS_UNROLL
 #define MC_CONST_MODEL g_model_h
+#ifdef MC_HOST_THREADS          /* tests/hostemu threaded mode: a "block" of OS threads with a real barrier, to exercise the block protocol on the CPU */
+#include <barrier>
+namespace mcd_host { inline thread_local int tl_tid = 0; inline int g_tb = 1; inline std::barrier<>* g_barrier = nullptr; }
+#define MC_TID (mcd_host::tl_tid)
+#define MC_TB (mcd_host::g_tb)
+#define MC_BLOCK_SYNC() mcd_host::g_barrier->arrive_and_wait()
+#else
 #define MC_TID 0
 #define MC_TB 1
 #define MC_BLOCK_SYNC() ((void)0)
+#endif
 #endif
 
 #ifndef MC_USE_GG3

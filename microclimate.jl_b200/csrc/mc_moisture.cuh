@@ -481,7 +481,7 @@ enum { M_PSIE = 0, M_SAT, M_BB, M_KS, M_NEXP, M_ROOTR, M_ROOTZ, M_KVC, M_RTS, M_
 enum { MF_FIRST = 1, MF_S0 = 2, MF_FINAL = 4 };
 template <int NA> struct Coop2Rows { static constexpr size_t value = (size_t)P_ARRAYS * NA + (MC_COOP_MOIST ? (size_t)M_ARRAYS * (NA + 2) : 0); };
 
-struct MoistShared { int listF[COOP_TB]; int countU[2], countF[2], alive[2]; };
+struct MoistShared { int listF[COOP_TB]; int countU[3], countF[3], alive[3]; };      /* three rotating counter sets, as in coop2_rounds */
 
 /* U-pass item: node i (2..L) of site o */
 template <int NA>
@@ -695,28 +695,13 @@ MC_DEV double soil_water_hour_coop(const SiteRef& r, const EnvInstant& e, const 
     int par = par_io;
     for (;;) {
         const bool alive = W.state != 0;
-#if defined(__CUDACC__)
-        {
-            const unsigned bu = __ballot_sync(0xffffffffu, needU), bf = __ballot_sync(0xffffffffu, needF), ba = __ballot_sync(0xffffffffu, alive);
-            const int lane = tid & 31;
-            int baseU = 0, baseF = 0;
-            if (lane == 0) {
-                if (bu) baseU = atomicAdd(&ms.countU[par], __popc(bu));
-                if (bf) baseF = atomicAdd(&ms.countF[par], __popc(bf));
-                if (ba) atomicAdd(&ms.alive[par], __popc(ba));
-            }
-            baseU = __shfl_sync(0xffffffffu, baseU, 0); baseF = __shfl_sync(0xffffffffu, baseF, 0);
-            const unsigned lt = (1u << lane) - 1u;
-            if (needU) sh.list[baseU + __popc(bu & lt)] = tid;
-            if (needF) ms.listF[baseF + __popc(bf & lt)] = tid;
-        }
-        __syncthreads();
+        block_list_append(needU, sh.list, &ms.countU[par], tid);
+        block_list_append(needF, ms.listF, &ms.countF[par], tid);
+        block_count_add(alive, &ms.alive[par], tid);
+        MC_BLOCK_SYNC();
         const int AU = ms.countU[par], AF = ms.countF[par], AL = ms.alive[par];
-        if (tid == 0) { ms.countU[par ^ 1] = 0; ms.countF[par ^ 1] = 0; ms.alive[par ^ 1] = 0; }
-#else
-        const int AU = needU ? 1 : 0, AF = needF ? 1 : 0, AL = alive ? 1 : 0;
-        sh.list[0] = tid; ms.listF[0] = tid;
-#endif
+        if (tid == 0) { const int z = par == 0 ? 2 : par - 1; ms.countU[z] = 0; ms.countF[z] = 0; ms.alive[z] = 0; }      /* the set of round r + 2 */
+        par = par == 2 ? 0 : par + 1;
         if (AL == 0) break;
         if (AU > 0) {
             const unsigned long long magic = (0x100000000ull + (unsigned)AU - 1ull) / (unsigned)AU;
@@ -767,7 +752,6 @@ MC_DEV double soil_water_hour_coop(const SiteRef& r, const EnvInstant& e, const 
             } else { needU = false; needF = false; W.state = 0; }
         }
         MC_BLOCK_SYNC();
-        par ^= 1;
     }
     par_io = par;
     pool = W.pool;

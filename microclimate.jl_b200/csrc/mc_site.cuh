@@ -331,7 +331,7 @@ MC_DEV void solve_site(const KArgs& a, int64_t s, Counters& cn)
  * the same sequence of coop2_rounds calls).  Everything outside the ODE hour is solve_site<NA,0> verbatim.
  * ------------------------------------------------------------------------------------------ */
 template <int NA>
-MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Shared& sh, MoistShared& ms, double* scr)
+MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Shared& sh, MoistShared& ms, double* scr, int& rot_ode, int& rot_moist)
 {
     const DevModel& m = MC_CONST_MODEL;
     const int N = m.N;
@@ -343,7 +343,7 @@ MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Share
 
     HourPar hp; Own2 I;
     const bool coop_moist = MC_COOP_MOIST && !m.flux_alg && m.niter_moist >= 1 && m.moist_max_it >= 1;      /* water-potential form of infiltration_step! */
-    int mpar = 0; (void)mpar; (void)coop_moist; (void)ms;
+    int& mpar = rot_moist; (void)mpar; (void)coop_moist; (void)ms;
     double T0[NA], theta[NA], sum_phase[NA], sum_phase_day_start[NA], T0_day_start[NA], T0_before[NA], T0_output[NA];
     double psi_out[NA], h_out[NA];
     MC_ROLLED for (int i = 0; i < N; i++) { T0[i] = a.T[(int64_t)i * S + s]; theta[i] = a.theta[(int64_t)i * S + s]; sum_phase[i] = a.sum_phase[(int64_t)i * S + s]; MC_SCR(P_LM, i, tid) = r.node(a.lam_m, i); }
@@ -353,7 +353,7 @@ MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Share
     hp.z0 = MC_LDG(a.z0 + s); hp.slope = MC_LDG(a.slope + s); hp.svf = MC_LDG(a.svf + s); hp.lz = mcm::log(m.zref / hp.z0); hp.S = S;
     hp.sn = nullptr;
     I.flags = 0; I.iter = 0; I.accept = false; I.u_modified = false; I.t = 0; I.dt = 0; I.dtpropose = 0; I.qold = 1e-4; I.q11 = 1; I.tstop = 1440.0;
-    I.st = 0; I.guard = 0; I.need_initdt = false; I.u_stale = false; I.kswap = false; I.uswap = false; I.stage = ST_NONE; I.q0 = 0.0; I.par = 0;
+    I.st = 0; I.guard = 0; I.need_initdt = false; I.u_stale = false; I.kswap = false; I.uswap = false; I.stage = ST_NONE; I.q0 = 0.0; I.par = rot_ode;      /* rotation of the block's list counters continues across site batches */
     MC_ROLLED for (int i = 0; i < N; i++) { const double f = a.fsal[(int64_t)i * S + s]; MC_SCR(PK_A, i, tid) = f; MC_SCR(PK_B, i, tid) = f; }
 
     auto set_day_forcing = [&](int jl) {
@@ -513,6 +513,7 @@ MC_DEV void solve_site_coop2(const KArgs& a, int64_t s, Counters& cn, Coop2Share
     { const int K1 = I.k1arr(); MC_ROLLED for (int i = 0; i < N; i++) a.fsal[(int64_t)i * S + s] = MC_SCR(K1, i, tid); }
     a.pool[s] = pool; a.wetness[s] = wet_dyn; a.L_ode[s] = L_ode; a.L_prof[s] = L_prof; a.tdeep_prev[s] = tdeep_stale;
     a.flags[s] = flags | I.flags;
+    rot_ode = I.par;
 }
 
 

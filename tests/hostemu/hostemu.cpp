@@ -10,9 +10,50 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#ifdef MC_HOST_THREADS
+#include <mutex>
+#include <thread>
+#endif
 #include "../../microclimate.jl_b200/csrc/mc_device.cuh"
 
 namespace {
+#ifdef MC_HOST_THREADS
+/* Threaded mode: one "block" = HE_TB OS threads sharing Coop2Shared / MoistShared / the block scratch, with a real barrier behind
+ * MC_BLOCK_SYNC() — the block protocol of the cooperative kernel (request lists, counter parity, role swaps seen by other threads,
+ * mirror threads of a ragged last block) exercised on the CPU. */
+template <int NA>
+void run_blocks_threaded(const mcd::KArgs& a, int TB, int grid, unsigned long long* counters)
+{
+    const int64_t n = a.s_end - a.s_begin;
+    const int nbatch = (int)((n + TB - 1) / TB);
+    if (grid <= 0 || grid > nbatch) grid = nbatch;                 /* grid < nbatch: grid-stride loop over batches, as with MC_COOP_GRID */
+    std::vector<double> scr(mcd::Coop2Rows<NA>::value * (size_t)TB);
+    std::mutex mu;
+    for (int b = 0; b < grid; b++) {                               /* blocks one after the other (one barrier object) */
+        static mcd::Coop2Shared sh; static mcd::MoistShared ms;
+        std::memset(&sh, 0, sizeof(sh)); std::memset(&ms, 0, sizeof(ms));
+        std::barrier<> bar(TB);
+        mcd_host::g_tb = TB; mcd_host::g_barrier = &bar;
+        std::vector<std::thread> th;
+        for (int t = 0; t < TB; t++) th.emplace_back([&, t]() {
+            mcd_host::tl_tid = t;
+            int rot_ode = 0, rot_moist = 0;
+            mcd::Counters cn = {};
+            for (int64_t base = a.s_begin + (int64_t)b * TB; base < a.s_end; base += (int64_t)grid * TB) {
+                int64_t s = base + t; const bool valid = s < a.s_end; if (!valid) s = a.s_end - 1;      /* mirror threads, as in the kernel */
+                mcd::Counters c1 = {};
+                mcd::solve_site_coop2<NA>(a, s, c1, sh, ms, scr.data(), rot_ode, rot_moist);
+                if (valid) { cn.n_rhs += c1.n_rhs; cn.n_accept += c1.n_accept; cn.n_reject += c1.n_reject; cn.n_obukhov += c1.n_obukhov;
+                             cn.n_newton += c1.n_newton; cn.n_infil += c1.n_infil; cn.n_day_passes += c1.n_day_passes; }
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            counters[0] += cn.n_rhs; counters[1] += cn.n_accept; counters[2] += cn.n_reject; counters[3] += cn.n_obukhov;
+            counters[4] += cn.n_newton; counters[5] += cn.n_infil; counters[6] += cn.n_day_passes;
+        });
+        for (auto& x : th) x.join();
+    }
+}
+#endif
 struct Emu {
     mc_model_desc model; int64_t S; int N; int64_t days_done;
     std::vector<double> site[4], node[8], init_T, init_theta, T, theta, sum_phase, fsal, pool, wet, L_ode, L_prof, tdeep;
@@ -93,10 +134,24 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     const bool coop = !(kenv && std::strcmp(kenv, "legacy") == 0) && e->model.n_snow == 0 && mcd::g_model_h.conv_kind == MC_CONV_FIXED;
     std::vector<double> scr(mcd::Coop2Rows<MC_MAX_SOIL_NODES>::value);
     static mcd::MoistShared ms; std::memset(&ms, 0, sizeof(ms));
-    static mcd::Coop2Shared sh2; sh2.count[0] = sh2.count[1] = 0;
+    static mcd::Coop2Shared sh2; std::memset(&sh2, 0, sizeof(sh2)); int rot_ode = 0, rot_moist = 0;
+#ifdef MC_HOST_THREADS
+    if (coop) {
+        const char* tbe = getenv("HE_TB"); const int TB = tbe ? atoi(tbe) : 8;
+        const char* ge = getenv("HE_GRID"); const int grid = ge ? atoi(ge) : 0;
+        if (e->N <= 10) run_blocks_threaded<10>(a, TB, grid, e->counters); else if (e->N <= 19) run_blocks_threaded<19>(a, TB, grid, e->counters); else run_blocks_threaded<MC_MAX_SOIL_NODES>(a, TB, grid, e->counters);
+        for (int64_t s = 0; s < e->S; s++) {
+            if (want_air) { mcd::Counters cn = {}; mcd::solve_air_site(a, s, cn); e->counters[3] += cn.n_obukhov; }
+            if (o->status) o->status[s] = e->flags[s];
+            if (e->flags[s]) nbad++;
+        }
+        e->days_done += ndays;
+        return nbad;
+    }
+#endif
     for (int64_t s = 0; s < e->S; s++) {
         mcd::Counters cn = {};
-        if (coop) { if (e->N <= 10) mcd::solve_site_coop2<10>(a, s, cn, sh2, ms, scr.data()); else if (e->N <= 19) mcd::solve_site_coop2<19>(a, s, cn, sh2, ms, scr.data()); else mcd::solve_site_coop2<MC_MAX_SOIL_NODES>(a, s, cn, sh2, ms, scr.data()); }
+        if (coop) { if (e->N <= 10) mcd::solve_site_coop2<10>(a, s, cn, sh2, ms, scr.data(), rot_ode, rot_moist); else if (e->N <= 19) mcd::solve_site_coop2<19>(a, s, cn, sh2, ms, scr.data(), rot_ode, rot_moist); else mcd::solve_site_coop2<MC_MAX_SOIL_NODES>(a, s, cn, sh2, ms, scr.data(), rot_ode, rot_moist); }
         else if (e->model.n_snow == 0) { if (e->N <= 10) mcd::solve_site<10, 0>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, 0>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, 0>(a, s, cn); }
         else { if (e->N <= 10) mcd::solve_site<10, MC_SNOW_NODES>(a, s, cn); else if (e->N <= 19) mcd::solve_site<19, MC_SNOW_NODES>(a, s, cn); else mcd::solve_site<MC_MAX_SOIL_NODES, MC_SNOW_NODES>(a, s, cn); }
         if (want_air) mcd::solve_air_site(a, s, cn);

@@ -137,6 +137,27 @@ def test_stomatal_cycle_shortcut_equals_plain_loop():
     assert capped > 100          # the sample must exercise non-terminating orbits
 
 
+@pytest.mark.parametrize("defs", [(), ("-DMC_COOP_MOIST=1",)], ids=["default", "coop_moist"])
+def test_block_protocol_with_real_threads(defs, monkeypatch):
+    """The cooperative kernel's block protocol — request lists with counter parity, item passes over other threads' sites, role swaps,
+    barriers, mirror threads of a ragged last block — run with 8 OS threads per block and a real barrier (hostemu -DMC_HOST_THREADS)."""
+    import hostemu_engine
+
+    class ThreadedEngine(HostEmuEngine):
+        LIB = hostemu_engine.variant("threads" + ("_cm" if defs else ""), ["-DMC_HOST_THREADS", "-std=c++20", "-pthread", *defs])
+
+    monkeypatch.setenv("HE_TB", "8")
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    sites, forcing = syn.make_sites(0, 21, 21, with_sand=True), syn.make_forcing(0, 21, 21, 0, 2)      # 3 batches, the last one 5 sites + 3 mirrors
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    for grid in ("0", "1"):                      # one batch per block / one block striding over the three batches (counter rotation carried)
+        monkeypatch.setenv("HE_GRID", grid)
+        out, ee = parity.run(ThreadedEngine, desc, sites, forcing)
+        parity.assert_bit_identical(out, ref)
+        co, ce = eo.counters(), ee.counters()
+        assert all(co[k] == ce[k] for k in ("n_rhs", "n_accept", "n_reject", "n_newton_iter", "n_infil_steps"))
+
+
 def _variant(problem, **cfg):
     p = copy.deepcopy(problem)
     for k, v in cfg.items():
