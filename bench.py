@@ -25,8 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FIELDS = ("soil_temperature", "soil_moisture")
-# executed FP64 flop per site-day of the benchmark grid (DADD + DMUL + 2 DFMA), calibrated with ncu: profiles/README.md
-FLOP_PER_SITE_DAY = 41.1e6
+# FP64 flop per site-day of the benchmark grid (DADD + DMUL + 2 DFMA thread instructions, ncu SASS counts, profiles/README.md):
+#   EXECUTED by the current kernel (build v10, profiles/r1_v10_*): 38.55e6 - this is what roofline.achieved uses;
+#   the reference algorithm run literally (every stomatal / moisture Newton iteration executed, build v9): 41.6e6 - reported beside it.
+FLOP_PER_SITE_DAY = 38.55e6
+ALG_FLOP_PER_SITE_DAY = 41.6e6
 ALG_BYTES_PER_SITE_DAY = (10 * 24 + 7) * 8 + 2 * 19 * 24 * 8     # hourly+daily forcing read, hourly T+theta written
 # dram__bytes_read.sum + dram__bytes_write.sum of the soil kernel per site-day (one ncu capture, profiles/r1_v10_metrics.csv: 1.271 TB + 0.338 TB over
 # 151 552 site-days): block scratch and thread-local arrays of 1024 resident sites per SM overflow L2 - the traffic is ~1100x the algorithmic bytes
@@ -240,7 +243,8 @@ def main():
     per_gpu = value / world
     roof = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf, "peak_how": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
             "achieved": (flop_sd * per_gpu / 1e12) if flop_sd else None, "frac": (flop_sd * per_gpu / 1e12 / peak_tf) if flop_sd else None,
-            "flop_per_site_day": flop_sd, "traffic": DRAM_BYTES_PER_SITE_DAY * S,
+            "flop_per_site_day": flop_sd, "flop_per_site_day_reference_algorithm": ALG_FLOP_PER_SITE_DAY,
+            "achieved_reference_algorithm": ALG_FLOP_PER_SITE_DAY * per_gpu / 1e12, "traffic": DRAM_BYTES_PER_SITE_DAY * S,
             "traffic_how": "DRAM bytes per launch (one launch = one step of %d site-days per GPU) scaled from one ncu capture of the same kernel; not re-measured in this run" % S,
             "hbm": {"achieved": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9, "peak": 6536.0, "unit": "GB/s", "frac": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9 / 6536.0,
                     "alg_bytes_per_site_day": ALG_BYTES_PER_SITE_DAY, "dram_traffic_GBps": DRAM_BYTES_PER_SITE_DAY * per_gpu / 1e9},
