@@ -40,8 +40,18 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libmicroclimate_b200.so (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    # several processes may get here at once (one rank per GPU under torchrun): serialise on a lock file, compile to a private name, rename atomically
+    import fcntl
+    with open(SO + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if force or is_stale():
+                tmp = f"{SO}.{os.getpid()}.tmp"
+                cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+                subprocess.check_call(cmd, cwd=CSRC)
+                os.replace(tmp, SO)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     return SO
 
 
