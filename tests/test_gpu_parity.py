@@ -248,3 +248,98 @@ def test_solve_air_matches_oracle(SoilEngine):
     e = SoilEngine(desc, 1); e.set_sites(sites)
     with pytest.raises(RuntimeError, match="solve_air"):
         e.step_days(0, forcing, bad)
+
+
+# ---- strategy variants on the B200 (scope rows a8 / a12 / a14): the same cases the CPU tier runs through the host emulation ----
+def _variant(problem, **cfg):
+    import copy
+    p = copy.deepcopy(problem)
+    for k, v in cfg.items():
+        if k == "time_mode":
+            p.time_mode = v
+        elif k == "hydraulics":
+            p.model.soil_hydraulic_model = v
+        else:
+            setattr(p.model.config, k, v)
+    return p
+
+
+def _assert_gpu_equals_oracle(SoilEngine, p, fields=parity.ALL_FIELDS):
+    desc, sites, forcing = _problem_buffers(p)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=fields)
+    out, eg = parity.run(SoilEngine, desc, sites, forcing, fields=fields)
+    parity.assert_within_north_star(out, ref, fields)
+    parity.assert_bit_identical(out, ref, fields)
+    co, cg = eo.counters(), eg.counters()
+    for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps", "n_day_passes"):
+        assert co[k] == cg[k], k
+    return ref, out
+
+
+def test_tolerance_convergence_matches_oracle(SoilEngine):
+    """SoilTemperatureConvergenceTolerance (src/soil_temperature_convergence/tolerance.jl:8-22): the day-pass count differs per day
+    (and, in a batch, per site) - the per-lane `is_last` divergence of survey H-c."""
+    import microclimate_jl_b200 as mc
+    p1, _ = configs.config1_monthly()
+    p = _variant(p1, convergence=mc.SoilTemperatureConvergenceTolerance(tolerance=0.5, max_iterations_per_day=6),
+                 time_mode=mc.NonConsecutiveDayMode(iterations_per_day=6))
+    ref, _ = _assert_gpu_equals_oracle(SoilEngine, p)
+    desc, sites, forcing = _problem_buffers(p)
+    _, eo = parity.run(OracleEngine, desc, sites, forcing)
+    assert 12 < eo.counters()["n_day_passes"] < 72          # neither the minimum nor the cap on every day: the tolerance decides
+
+
+def test_spinup_first_day_matches_oracle(SoilEngine):
+    """ConsecutiveDayMode(spinup_first_day=true) (src/time_mode/consecutive.jl:9-23): day 1 repeats `iterations` passes."""
+    import microclimate_jl_b200 as mc
+    p2, _ = configs.config2_daily(4)
+    p = _variant(p2, time_mode=mc.ConsecutiveDayMode(spinup_first_day=True), convergence=mc.FixedSoilTemperatureIterations(3))
+    _assert_gpu_equals_oracle(SoilEngine, p)
+
+
+def test_matric_flux_potential_infiltration_matches_oracle(SoilEngine):
+    """MatricFluxPotentialAlgorithm (src/soil_hydraulics/infiltration_algorithm/matric_flux_potential.jl:19-101)."""
+    import microclimate_jl_b200 as mc
+    p2, _ = configs.config2_daily(4)
+    p = _variant(p2, hydraulics=mc.CampbellSoilHydraulics(infiltration_algorithm=mc.MatricFluxPotentialAlgorithm()))
+    _assert_gpu_equals_oracle(SoilEngine, p)
+
+
+def test_swinbank_and_supplied_longwave_match_oracle(SoilEngine):
+    """SwinbankAtmosphericRadiation (src/radiation/atmospheric/swinbank.jl:9-11) and user-supplied longwave
+    (src/radiation/longwave/view_factor.jl:23-67, `longwave_radiation` hourly forcing)."""
+    import copy
+    import microclimate_jl_b200 as mc
+    p1, _ = configs.config1_monthly()
+    p_sw = copy.deepcopy(p1)
+    p_sw.model.radiation = mc.RadiationModel(longwave_model=mc.ViewFactorLongwave(atmospheric_radiation_model=mc.SwinbankAtmosphericRadiation()))
+    ref_sw, _ = _assert_gpu_equals_oracle(SoilEngine, p_sw)
+    ref_cn, _ = _assert_gpu_equals_oracle(SoilEngine, p1)
+    assert not np.array_equal(ref_sw.soil_temperature, ref_cn.soil_temperature)       # the strategy really changes the answer
+    p_lw = copy.deepcopy(p1)
+    h = p_lw.inputs.environment_hourly
+    h.longwave_radiation = 300.0 + 40.0 * np.cos(np.arange(len(h.zenith_angle)) * (2 * np.pi / 24.0))
+    ref_lw, _ = _assert_gpu_equals_oracle(SoilEngine, p_lw)
+    assert not np.array_equal(ref_lw.sky_temperature, ref_cn.sky_temperature)
+
+
+def test_sloped_site_matches_oracle(SoilEngine):
+    """Sloped site with a reduced sky view (src/soil_balance/energy/heat_transport_1d.jl:223-232): slope-zenith and diffuse fraction forcing."""
+    import copy
+    p, _ = configs.config1_monthly()
+    p = copy.deepcopy(p)
+    p.inputs.site.slope = 20.0
+    p.inputs.site.sky_view_fraction = 0.8
+    h = p.inputs.environment_hourly
+    h.diffuse_fraction = np.full(len(h.zenith_angle), 0.3)
+    h.zenith_slope_angle = np.minimum(np.asarray(h.zenith_angle) + 10.0, 90.0)
+    _assert_gpu_equals_oracle(SoilEngine, p)
+    # and a dynamic-moisture, consecutive-day sloped site (the block-cooperative kernel's slope branch)
+    p2, _ = configs.config2_daily(3)
+    p2 = copy.deepcopy(p2)
+    p2.inputs.site.slope = 15.0
+    p2.inputs.site.sky_view_fraction = 0.9
+    h = p2.inputs.environment_hourly
+    h.diffuse_fraction = np.full(len(h.zenith_angle), 0.25)
+    h.zenith_slope_angle = np.minimum(np.asarray(h.zenith_angle) + 8.0, 90.0)
+    _assert_gpu_equals_oracle(SoilEngine, p2)
