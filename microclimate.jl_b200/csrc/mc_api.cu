@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 #include "mc_device.cuh"
 
@@ -40,6 +41,15 @@ thread_local std::string g_create_error;
 #define MC_MIN_BLOCKS 16
 #endif
 constexpr int BLOCK = MC_BLOCK;
+
+/* The flattened model lives in ONE __constant__ bank per device (mcd::g_model_c).  Handles with different models may share a device, and
+ * mc_step_days_device is asynchronous, so an upload must never land while another handle's kernel is still reading the bank: the resident
+ * model of every device is remembered here, uploads happen only when it differs from the launching handle's, after the device has drained,
+ * and the check + upload + launch of a chunk are one critical section per device (model_guard).  Same-model handles never upload or wait. */
+constexpr int MAX_DEVICES = 64;
+std::mutex g_model_mutex[MAX_DEVICES];
+mcd::DevModel g_model_resident[MAX_DEVICES];
+bool g_model_valid[MAX_DEVICES];
 
 }  // namespace
 
@@ -100,6 +110,22 @@ __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_c
         atomicAdd(a.counters + 5, (unsigned long long)cn.n_infil);
         atomicAdd(a.counters + 6, (unsigned long long)cn.n_day_passes);
     }
+}
+
+/* Asynchronous kernel (mc_async.cuh): one persistent block per SM keeps SLOTS sites resident in shared memory; its warps are generic workers that
+ * claim node items / single-lane tasks of whatever sites offer them.  Serves every NoSnow model with the water-potential infiltration form. */
+#ifndef MC_ASYNC_THREADS
+#define MC_ASYNC_THREADS 1024
+#endif
+template <int NA, int SLOTS>
+__global__ void __launch_bounds__(MC_ASYNC_THREADS, 1) soil_async_kernel(const __grid_constant__ mcd::KArgs a)
+{
+    extern __shared__ __align__(16) unsigned char mc_async_smem[];
+    mcd::AsyncBlock<NA, SLOTS>& B = *reinterpret_cast<mcd::AsyncBlock<NA, SLOTS>*>(mc_async_smem);
+    mcd::async_block_init<NA, SLOTS>(B, (int)threadIdx.x, (int)blockDim.x, a.async_slots);
+    __syncthreads();
+    double* ga = a.async_scr + (size_t)blockIdx.x * ((size_t)mcd::G_ARRAYS * NA * SLOTS);
+    mcd::async_worker<NA, SLOTS>(B, a, ga, (int)(threadIdx.x >> 5));
 }
 
 /* solve_air! for the rows of the chunk the soil kernel just wrote (reference src/simulation.jl:822-851) */
@@ -191,6 +217,7 @@ struct mc_handle {
     double* stage_in = nullptr; size_t stage_in_doubles = 0;
     double* stage_out = nullptr; size_t stage_out_doubles = 0;
     double* coop_scr = nullptr; size_t coop_scr_doubles = 0;      /* per-block scratch of the block-cooperative kernel */
+    double* async_scr = nullptr; size_t async_scr_doubles = 0;    /* per-block L2-resident scratch of the asynchronous kernel */
     double last_ms = 0.0; unsigned long long last_launches = 0;
 };
 
@@ -268,6 +295,47 @@ static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
     }
     a.coop_scr = h->coop_scr;
     soil_chunk_coop_kernel<NA><<<grid, TB, 0, st>>>(a);
+    MC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+/* the asynchronous kernel serves every NoSnow model whose infiltration step is the water-potential form (per-site pass counts are no constraint) */
+static bool async_enabled(const mc_handle* h)
+{
+    const char* e = getenv("MC_KERNEL");                           /* MC_KERNEL=coop / legacy: A/B and test knob */
+    if (e && (std::strcmp(e, "legacy") == 0 || std::strcmp(e, "coop") == 0)) return false;
+    return h->model.n_snow == 0 && !h->dm.flux_alg;
+}
+
+template <int NA, int SLOTS>
+static int launch_chunk_async(mc_handle* h, mcd::KArgs& a, cudaStream_t st, int slice)
+{
+    static int n_sm = 0; static bool attr_set = false;
+    constexpr size_t smem = sizeof(mcd::AsyncBlock<NA, SLOTS>);
+    if (!attr_set) {
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        MC_CUDA(h, cudaFuncSetAttribute(soil_async_kernel<NA, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t n = a.s_end - a.s_begin;
+    int grid = (int)std::min<int64_t>(n_sm, n);
+    if (const char* e = getenv("MC_ASYNC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));                           /* test knob */
+    int slots = (int)std::min<int64_t>(SLOTS, (n + grid - 1) / grid);                                                   /* small ranges: spread the sites over all SMs */
+    if (const char* e = getenv("MC_ASYNC_SLOTS")) slots = std::max(1, std::min((int)SLOTS, atoi(e)));                   /* test / tuning knob */
+    int threads = MC_ASYNC_THREADS;
+    if (const char* e = getenv("MC_ASYNC_THREADS")) threads = std::max(32, std::min(MC_ASYNC_THREADS, atoi(e) / 32 * 32));
+    const size_t need = (size_t)grid * mcd::G_ARRAYS * NA * SLOTS;
+    if (h->async_scr_doubles < need) {
+        MC_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < mc_handle::MAX_SLICES; k++) if (h->slice_stream[k]) MC_CUDA(h, cudaStreamSynchronize(h->slice_stream[k]));
+        if (h->async_scr) { MC_CUDA(h, cudaFree(h->async_scr)); h->async_scr = nullptr; h->async_scr_doubles = 0; }
+        MC_CUDA(h, cudaMalloc(&h->async_scr, need * sizeof(double)));
+        h->async_scr_doubles = need;
+    }
+    a.async_scr = h->async_scr; a.async_slots = slots;
+    a.next_site = h->counters + 8 + slice;
+    MC_CUDA(h, cudaMemsetAsync(a.next_site, 0, sizeof(unsigned long long), st));
+    soil_async_kernel<NA, SLOTS><<<grid, threads, smem, st>>>(a);
     MC_CUDA(h, cudaGetLastError());
     return 0;
 }
@@ -364,8 +432,8 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     if (NSn) { h->snow_T = take(NSn * S); h->snow_nd = take(NSn * S); h->snow_state = take(MC_SNOW_STATE_FIELDS * S); h->q_freeze = take(S); }
     h->pool = take(S); h->wetness = take(S); h->L_ode = take(S); h->L_prof = take(S); h->tdeep_prev = take(S); h->L_air = take(S);
     if ((e = cudaMalloc(&h->flags, S * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
-    if ((e = cudaMalloc(&h->counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
-    if ((e = cudaMemset(h->counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
+    if ((e = cudaMalloc(&h->counters, 16 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+    if ((e = cudaMemset(h->counters, 0, 16 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
     *out = h;
     return 0;
 }
@@ -375,7 +443,7 @@ void mc_destroy(mc_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out); cudaFree(h->coop_scr);
+    cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out); cudaFree(h->coop_scr); cudaFree(h->async_scr);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
@@ -471,16 +539,30 @@ static int prepare_chunk(mc_handle* h, int64_t day0, int32_t ndays, const mc_for
         MC_CUDA(h, cudaMemcpyAsync(h->doy_dev, f->day_of_year, (size_t)ndays * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         a.doy = h->doy_dev;
     }
-    MC_CUDA(h, cudaMemcpyToSymbolAsync(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
 
-static int launch_range(mc_handle* h, mcd::KArgs a, int64_t lo, int64_t hi, cudaStream_t st)
+/* must be called with g_model_mutex[h->device] held, immediately before the launches that read the constant bank */
+static int ensure_model_resident(mc_handle* h)
+{
+    const int d = h->device;
+    if (g_model_valid[d] && std::memcmp(&g_model_resident[d], &h->dm, sizeof(mcd::DevModel)) == 0) return 0;
+    MC_CUDA(h, cudaDeviceSynchronize());                                  /* kernels of other handles may still read the old model */
+    MC_CUDA(h, cudaMemcpyToSymbol(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice));
+    g_model_resident[d] = h->dm; g_model_valid[d] = true;
+    return 0;
+}
+
+static int launch_range(mc_handle* h, mcd::KArgs a, int64_t lo, int64_t hi, cudaStream_t st, int slice = 0)
 {
     a.s_begin = lo; a.s_end = hi;
     const int na = pick_na(h->N);
     cudaError_t e = cudaSuccess;
-    if (coop_enabled(h)) {
+    if (async_enabled(h)) {
+        /* slices of one async scratch would overlap: concurrent slices share h->async_scr only because slice kernels are serialised (mc_step_days) */
+        if (int rc = na == 10 ? launch_chunk_async<10, 64>(h, a, st, slice) : (na == 19 ? launch_chunk_async<19, 64>(h, a, st, slice) : launch_chunk_async<MC_MAX_SOIL_NODES, 48>(h, a, st, slice))) return rc;
+    }
+    else if (coop_enabled(h)) {
         if (int rc = na == 10 ? launch_chunk_coop<10>(h, a, st) : (na == 19 ? launch_chunk_coop<19>(h, a, st) : launch_chunk_coop<MC_MAX_SOIL_NODES>(h, a, st))) return rc;
     }
     else if (h->model.n_snow == 0) e = na == 10 ? launch_chunk<10, 0>(a, st) : (na == 19 ? launch_chunk<19, 0>(a, st) : launch_chunk<MC_MAX_SOIL_NODES, 0>(a, st));
@@ -499,6 +581,8 @@ int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forc
     if (!h) return -1;
     mcd::KArgs a;
     if (int rc = prepare_chunk(h, day0, ndays, f, o, a)) return rc;
+    std::lock_guard<std::mutex> model_guard(g_model_mutex[h->device % MAX_DEVICES]);
+    if (int rc = ensure_model_resident(h)) return rc;
     MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (int rc = launch_range(h, a, 0, h->S, h->stream)) return rc;
     MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -602,6 +686,8 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     int32_t* status_host = o->status;
     if (!status_host) { status_tmp.resize(S); status_host = status_tmp.data(); }
     int prev_kernel = -1;
+    std::unique_lock<std::mutex> model_guard(g_model_mutex[h->device % MAX_DEVICES]);
+    if (int rc = ensure_model_resident(h)) return rc;
     for (int k = 0; k < n_slices; k++) {
         const size_t lo = S * (size_t)k / (size_t)n_slices, hi = S * (size_t)(k + 1) / (size_t)n_slices;
         if (hi == lo) continue;
@@ -612,7 +698,7 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
         /* kernels run one after another (slice k+1 waits for slice k) so that the D2H of slice k overlaps the kernel of slice k+1;
          * concurrent slice kernels would all finish together and leave every D2H at the end */
         if (prev_kernel >= 0) MC_CUDA(h, cudaStreamWaitEvent(st, h->ev_kernel[prev_kernel], 0));
-        if (int rc = launch_range(h, a, (int64_t)lo, (int64_t)hi, st)) return rc;
+        if (int rc = launch_range(h, a, (int64_t)lo, (int64_t)hi, st, k)) return rc;
         MC_CUDA(h, cudaEventRecord(h->ev_kernel[k], st));
         prev_kernel = k;
         for (const Plane& pl : out_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.host_out + lo, pitch, pl.dev + lo, pitch, w, pl.rows, cudaMemcpyDeviceToHost, st));
@@ -621,6 +707,7 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
         MC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_slice[k], 0));
     }
     MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    model_guard.unlock();                                         /* everything that reads the constant bank is enqueued */
     h->last_launches = (unsigned long long)n_slices;
     h->days_done += ndays;
     int rc = mc_synchronize(h);
@@ -673,7 +760,8 @@ int mc_bench_conductivity(mc_handle* h, int64_t n_items, int reps, double* evals
     MC_CUDA(h, cudaMalloc(&dT, (size_t)n_items * 8)); MC_CUDA(h, cudaMalloc(&dth, (size_t)n_items * 8)); MC_CUDA(h, cudaMalloc(&dout, (size_t)n_items * 8));
     MC_CUDA(h, cudaMemcpyAsync(dT, T.data(), (size_t)n_items * 8, cudaMemcpyHostToDevice, h->stream));
     MC_CUDA(h, cudaMemcpyAsync(dth, th.data(), (size_t)n_items * 8, cudaMemcpyHostToDevice, h->stream));
-    MC_CUDA(h, cudaMemcpyToSymbolAsync(mcd::g_model_c, &h->dm, sizeof(mcd::DevModel), 0, cudaMemcpyHostToDevice, h->stream));
+    std::lock_guard<std::mutex> model_guard(g_model_mutex[h->device % MAX_DEVICES]);
+    if (int rc = ensure_model_resident(h)) return rc;
     cudaDeviceProp prop; MC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     const int blocks = prop.multiProcessorCount * 8;
     conductivity_items_kernel<<<blocks, 256, 0, h->stream>>>(dT, dth, dout, n_items, 1);

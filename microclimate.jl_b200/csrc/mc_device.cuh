@@ -22,6 +22,7 @@
  *   mc_coop_ode.cuh  block-cooperative ODE phase
  *   mc_moisture.cuh  freeze/thaw, Campbell (1985) soil water balance
  *   mc_site.cuh      solve_soil! / solve_air! per site, host-side model flattening
+ *   mc_async.cuh     asynchronous shared-memory-resident solve_soil! (the default NoSnow kernel)
  *
  * The functions are written against a tiny platform shim so the very same code can be compiled by g++ for tests/hostemu (a
  * development harness that runs the kernel body on the CPU where no GPU exists).  The shipped library (mc_api.cu) only ever
@@ -63,6 +64,7 @@
 #define MC_BLOCK_SYNC() __syncthreads()
 #else
 #include <cmath>
+#include <thread>
 #define MC_DEV static inline
 #define MC_MEMBER inline
 #define MC_DEV_NOINLINE static __attribute__((noinline))
@@ -159,6 +161,9 @@ struct KArgs {
     int32_t n_snow;
     unsigned long long* counters;   /* [8]: rhs, accept, reject, obukhov, newton, infil, day_passes, spare */
     double* coop_scr;               /* block-cooperative kernel: per-block scratch [block][SCR_ARRAYS][NA][block threads] */
+    double* async_scr;              /* asynchronous kernel: per-block L2-resident scratch [block][G_ARRAYS][NA][SLOTS] (site constants, hourly / daily copies) */
+    unsigned long long* next_site;  /* asynchronous kernel: the launch's site cursor (slots take their next site from it) */
+    int32_t async_slots;            /* asynchronous kernel: slots a block activates (fewer than its capacity when the range is small, so that every SM gets sites) */
 };
 
 struct Counters { unsigned int n_rhs, n_accept, n_reject, n_obukhov, n_newton, n_infil, n_day_passes; };
@@ -173,5 +178,6 @@ MC_DEV double jclamp(double x, double lo, double hi) { return x > hi ? hi : (x <
 #include "mc_coop_ode.cuh"
 #include "mc_moisture.cuh"
 #include "mc_site.cuh"
+#include "mc_async.cuh"
 
 } // namespace mcd

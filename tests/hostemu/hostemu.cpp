@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <limits>
 #ifdef MC_HOST_THREADS
 #include <mutex>
 #include <thread>
@@ -54,6 +55,38 @@ void run_blocks_threaded(const mcd::KArgs& a, int TB, int grid, unsigned long lo
     }
 }
 #endif
+#ifndef HE_SLOTS
+#define HE_SLOTS 6
+#endif
+/* The asynchronous kernel body (mc_async.cuh): `grid` blocks run concurrently, each with `nwarps` worker "warps".  A warp is one OS thread (with
+ * -DMC_HOST_THREADS; otherwise a single warp on the calling thread) that executes its MCA_LANES lanes one after the other; the request masks, cursor
+ * words and retire counters are real atomics, so the claim / retire protocol runs under arbitrary interleavings. */
+static long long g_async_runs = 0;
+template <int NA>
+void run_async(mcd::KArgs a, int nwarps, int grid, unsigned long long* counters)
+{
+    g_async_runs++;
+    using Blk = mcd::AsyncBlock<NA, HE_SLOTS>;
+    unsigned long long cursor = 0, cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    a.next_site = &cursor; a.counters = cnt;
+    std::vector<Blk*> blocks; std::vector<std::vector<double>> scr;
+    for (int b = 0; b < grid; b++) {
+        Blk* B = new Blk(); std::memset(B, 0, sizeof(Blk));
+        for (int t = 0; t < HE_SLOTS; t++) mcd::async_block_init<NA, HE_SLOTS>(*B, t, HE_SLOTS, a.async_slots);
+        blocks.push_back(B); scr.emplace_back((size_t)mcd::G_ARRAYS * NA * HE_SLOTS, 0.0);
+    }
+#ifdef MC_HOST_THREADS
+    std::vector<std::thread> th;
+    for (int b = 0; b < grid; b++) for (int w = 0; w < nwarps; w++)
+        th.emplace_back([&, b, w]() { mcd::async_worker<NA, HE_SLOTS>(*blocks[b], a, scr[b].data(), w); });
+    for (auto& x : th) x.join();
+#else
+    (void)nwarps;
+    for (int b = 0; b < grid; b++) mcd::async_worker<NA, HE_SLOTS>(*blocks[b], a, scr[b].data(), 0);
+#endif
+    for (auto* B : blocks) delete B;
+    for (int k = 0; k < 7; k++) counters[k] += cnt[k];
+}
 struct Emu {
     mc_model_desc model; int64_t S; int N; int64_t days_done;
     std::vector<double> site[4], node[8], init_T, init_theta, T, theta, sum_phase, fsal, pool, wet, L_ode, L_prof, tdeep;
@@ -131,7 +164,21 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     int nbad = 0;
     /* same kernel selection as launch_range(): the block-cooperative path (here a "block" of one thread) for NoSnow + FixedIterations */
     const char* kenv = getenv("MC_KERNEL");
-    const bool coop = !(kenv && std::strcmp(kenv, "legacy") == 0) && e->model.n_snow == 0 && mcd::g_model_h.conv_kind == MC_CONV_FIXED;
+    const bool legacy = kenv && std::strcmp(kenv, "legacy") == 0, force_coop = kenv && std::strcmp(kenv, "coop") == 0;
+    const bool coop = !legacy && e->model.n_snow == 0 && mcd::g_model_h.conv_kind == MC_CONV_FIXED;
+    /* same kernel selection as launch_range(): the asynchronous kernel for every NoSnow model with the water-potential infiltration form */
+    if (!legacy && !force_coop && e->model.n_snow == 0 && !mcd::g_model_h.flux_alg) {
+        const char* we = getenv("HE_WARPS"); const int nwarps = we ? atoi(we) : 3;
+        const char* ge = getenv("HE_GRID"); const int grid = ge && atoi(ge) > 0 ? atoi(ge) : 2;
+        if (e->N <= 10) run_async<10>(a, nwarps, grid, e->counters); else if (e->N <= 19) run_async<19>(a, nwarps, grid, e->counters); else run_async<MC_MAX_SOIL_NODES>(a, nwarps, grid, e->counters);
+        for (int64_t s = 0; s < e->S; s++) {
+            if (want_air) { mcd::Counters cn = {}; mcd::solve_air_site(a, s, cn); e->counters[3] += cn.n_obukhov; }
+            if (o->status) o->status[s] = e->flags[s];
+            if (e->flags[s]) nbad++;
+        }
+        e->days_done += ndays;
+        return nbad;
+    }
     std::vector<double> scr(mcd::Coop2Rows<MC_MAX_SOIL_NODES>::value);
     static mcd::MoistShared ms; std::memset(&ms, 0, sizeof(ms));
     static mcd::Coop2Shared sh2; std::memset(&sh2, 0, sizeof(sh2)); int rot_ode = 0, rot_moist = 0;
@@ -218,6 +265,8 @@ extern "C" double he_stomatal_newton_plain(const mc_model_desc* m, double psi_ba
     if (iterations) *iterations = counter;
     return psi_leaf;
 }
+
+extern "C" long long he_async_runs(void) { return g_async_runs; }      /* how many chunks went through the asynchronous kernel body */
 
 extern "C" int he_set_state(void* h, const mc_state_soa* st)
 {

@@ -147,6 +147,7 @@ def test_block_protocol_with_real_threads(defs, monkeypatch):
         LIB = hostemu_engine.variant("threads" + ("_cm" if defs else ""), ["-DMC_HOST_THREADS", "-std=c++20", "-pthread", *defs])
 
     monkeypatch.setenv("HE_TB", "8")
+    monkeypatch.setenv("MC_KERNEL", "coop")      # the block-synchronous cooperative kernel (the default is the asynchronous one, tested below)
     desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
     sites, forcing = syn.make_sites(0, 21, 21, with_sand=True), syn.make_forcing(0, 21, 21, 0, 2)      # 3 batches, the last one 5 sites + 3 mirrors
     ref, eo = parity.run(OracleEngine, desc, sites, forcing)
@@ -156,6 +157,40 @@ def test_block_protocol_with_real_threads(defs, monkeypatch):
         parity.assert_bit_identical(out, ref)
         co, ce = eo.counters(), ee.counters()
         assert all(co[k] == ce[k] for k in ("n_rhs", "n_accept", "n_reject", "n_newton_iter", "n_infil_steps"))
+
+
+@pytest.mark.parametrize("slots,lanes", [(6, 4), (3, 2), (64, 32)], ids=["6slots_4lanes", "3slots_2lanes", "64slots_32lanes"])
+def test_async_protocol_with_real_threads(slots, lanes, monkeypatch):
+    """The asynchronous kernel's claim / retire protocol (request masks, per-slot cursor words claimed by compare-and-swap, retire counters,
+    sites handed out from a shared cursor) with real threads: every worker "warp" is an OS thread, several blocks run concurrently, slots and
+    lanes are few so that passes are claimed in pieces by different warps.  Results and counters must be the oracle's whatever the interleaving."""
+    import ctypes as C
+    import hostemu_engine
+
+    class AsyncEngine(HostEmuEngine):
+        LIB = hostemu_engine.variant(f"async_{slots}_{lanes}", ["-DMC_HOST_THREADS", "-std=c++20", "-pthread", f"-DHE_SLOTS={slots}", f"-DMCA_LANES={lanes}"])
+
+    AsyncEngine.LIB.he_async_runs.restype = C.c_longlong
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    sites, forcing = syn.make_sites(0, 29, 29, with_sand=True), syn.make_forcing(0, 29, 29, 0, 2)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing, chunks=[1, 1])
+    before = AsyncEngine.LIB.he_async_runs()
+    for warps, grid in (("5", "2"), ("2", "3"), ("7", "1")):
+        monkeypatch.setenv("HE_WARPS", warps)
+        monkeypatch.setenv("HE_GRID", grid)
+        out, ee = parity.run(AsyncEngine, desc, sites, forcing, chunks=[1, 1])
+        parity.assert_bit_identical(out, ref)
+        co, ce = eo.counters(), ee.counters()
+        assert all(co[k] == ce[k] for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps", "n_day_passes"))
+    assert AsyncEngine.LIB.he_async_runs() - before == 6          # the asynchronous body really ran (2 chunks x 3 configurations)
+    # config 1: non-consecutive days, 3 passes per day, prescribed moisture; and the tolerance-based pass count (per-site, no block-uniform constraint)
+    p1, _ = configs.config1_monthly()
+    for p in (p1, _variant(p1, convergence=mc.SoilTemperatureConvergenceTolerance(tolerance=0.5, max_iterations_per_day=6), time_mode=mc.NonConsecutiveDayMode(iterations_per_day=6))):
+        d1, s1, f1 = _buffers(p)
+        ref1, eo1 = parity.run(OracleEngine, d1, s1, f1)
+        out1, ee1 = parity.run(AsyncEngine, d1, s1, f1)
+        parity.assert_bit_identical(out1, ref1)
+        assert eo1.counters()["n_day_passes"] == ee1.counters()["n_day_passes"] and eo1.counters()["n_rhs"] == ee1.counters()["n_rhs"]
 
 
 def _variant(problem, **cfg):
