@@ -343,3 +343,32 @@ def test_sloped_site_matches_oracle(SoilEngine):
     h.diffuse_fraction = np.full(len(h.zenith_angle), 0.25)
     h.zenith_slope_angle = np.minimum(np.asarray(h.zenith_angle) + 8.0, 90.0)
     _assert_gpu_equals_oracle(SoilEngine, p2)
+
+
+def test_file_driven_run_matches_in_memory(SoilEngine, tmp_path):
+    """On-disk formats (scope row f4): site / forcing containers memory-mapped into mc_step_days, chunked outputs and a state checkpoint written per
+    chunk (tools/dataset.py) - the file-driven run, interrupted after the first chunk and resumed from its checkpoint, must equal the in-memory run."""
+    import os
+    import subprocess
+    import sys
+    from microclimate_jl_b200 import storage as st
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    S, ND = 1536, 3
+    d = str(tmp_path)
+    subprocess.check_call([sys.executable, "tools/dataset.py", "make", d, "--sites", str(S), "--days", str(ND), "--chunk", "1"], cwd=root)
+    chunks = sorted(p for p in os.listdir(d) if p.startswith("forcing_d"))
+    assert len(chunks) == ND
+    hidden = [os.path.join(d, c) for c in chunks[1:]]
+    for p in hidden:                                   # first invocation only sees day 0 ...
+        os.rename(p, p + ".later")
+    subprocess.check_call([sys.executable, "tools/dataset.py", "run", d], cwd=root)
+    for p in hidden:                                   # ... the second resumes from the checkpoint for days 1-2
+        os.rename(p + ".later", p)
+    subprocess.check_call([sys.executable, "tools/dataset.py", "run", d, "--resume"], cwd=root)
+    desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
+    f = ("soil_temperature", "soil_moisture", "surface_water")
+    ref, _ = parity.run(SoilEngine, desc, syn.make_sites(0, S, S), syn.make_forcing(0, S, S, 0, ND), fields=f)
+    for name in f:
+        got = np.concatenate([getattr(st.load_outputs(os.path.join(d, f"out_d{k:04d}_s0-{S}.mcb")), name) for k in range(ND)])
+        assert np.array_equal(got, getattr(ref, name)), name
+    assert int(st.load_state(os.path.join(d, f"state_s0-{S}.mcb")).days_done[0]) == ND
