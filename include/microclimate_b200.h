@@ -301,6 +301,15 @@ int  mc_set_state(mc_handle* h, const mc_state_soa* in);
 int  mc_step_days(mc_handle* h, int64_t day0, int32_t ndays,
                   const mc_forcing_soa* forcing, mc_output_soa* out);
 
+/* Asynchronous form of mc_step_days: enqueues H2D(forcing) -> kernel -> D2H(outputs, status) on the handle's copy-in / compute / copy-out
+ * streams and returns.  Two staging sets alternate, so with the calls for chunk q+1 issued before mc_wait the H2D of chunk q+1 and the D2H of
+ * chunk q-1 overlap the kernel of chunk q (a third call waits for the oldest chunk).  Host buffers (pinned for real overlap) must stay valid
+ * until mc_wait, which returns the flagged-site count of the most recent chunk.  This is what a host loop over day chunks - and a single host
+ * thread driving several devices - uses; the reference's equivalent is the serial day loop of solve_soil! (src/simulation.jl:454-819). */
+int  mc_step_days_async(mc_handle* h, int64_t day0, int32_t ndays,
+                        const mc_forcing_soa* forcing, mc_output_soa* out);
+int  mc_wait(mc_handle* h);
+
 /* same, but every pointer inside `forcing` and `out` is a DEVICE pointer on the handle's
  * GPU (day_of_year stays a host pointer); no copies.  Asynchronous on the handle's stream
  * until mc_synchronize. */
@@ -311,6 +320,23 @@ int  mc_synchronize(mc_handle* h);
 int  mc_get_counters(mc_handle* h, mc_counters* out);
 int  mc_reset_counters(mc_handle* h);
 int  mc_get_status(mc_handle* h, int32_t* status_host /* [S] */);
+
+/* One host process, several GPUs (the reference idiom is one process sweeping sites with reinit!(cache, inputs); solve!(cache),
+ * src/simulation.jl:266-277).  A multi handle shards the n_sites columns of ONE set of host arrays contiguously over the listed devices (a device
+ * may be listed more than once); mc_multi_step_days* runs the asynchronous pipeline of every device on its column range, so all GPUs copy and
+ * integrate concurrently and write into disjoint column ranges of the caller's output arrays.  Same call order and error behaviour as the
+ * single-device entry points; mc_multi_wait returns the flagged-site count summed over devices. */
+typedef struct mc_multi mc_multi;
+int  mc_multi_create(const mc_model_desc* model, int64_t n_sites, const int* device_ids, int n_devices, mc_multi** out);
+void mc_multi_destroy(mc_multi* m);
+const char* mc_multi_last_error(const mc_multi* m);
+int  mc_multi_device_count(const mc_multi* m);
+mc_handle* mc_multi_handle(mc_multi* m, int g);                                  /* per-device handle (state checkpoints, counters, status) */
+int  mc_multi_range(const mc_multi* m, int g, int64_t* lo, int64_t* hi);         /* its site range [lo, hi) */
+int  mc_multi_set_sites(mc_multi* m, const mc_sites_soa* sites, const mc_initial_soa* init);
+int  mc_multi_step_days(mc_multi* m, int64_t day0, int32_t ndays, const mc_forcing_soa* forcing, mc_output_soa* out);
+int  mc_multi_step_days_async(mc_multi* m, int64_t day0, int32_t ndays, const mc_forcing_soa* forcing, mc_output_soa* out);
+int  mc_multi_wait(mc_multi* m);
 
 /* measured FP64 DFMA peak of the handle's device in TFLOP/s (micro-benchmark; SURVEY §8d:
  * MEASURED_PEAKS.json has no FP64 figure). */

@@ -22,6 +22,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ("mc_abi_version", "mc_backend_name", "mc_default_fluid", "mc_default_model", "mc_create", "mc_destroy",
            "mc_last_error", "mc_set_sites", "mc_get_state", "mc_set_state", "mc_step_days", "mc_step_days_device",
+           "mc_step_days_async", "mc_wait",
+           "mc_multi_create", "mc_multi_destroy", "mc_multi_last_error", "mc_multi_device_count", "mc_multi_handle", "mc_multi_range",
+           "mc_multi_set_sites", "mc_multi_step_days", "mc_multi_step_days_async", "mc_multi_wait",
            "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity")
 
 
@@ -84,6 +87,21 @@ def lib():
     L.mc_step_days.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
     L.mc_step_days_device.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
     L.mc_synchronize.argtypes = [H]
+    L.mc_step_days_async.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
+    L.mc_wait.argtypes = [H]
+    L.mc_multi_create.argtypes = [C.POINTER(A.ModelDesc), C.c_int64, C.POINTER(C.c_int), C.c_int, C.POINTER(H)]
+    L.mc_multi_destroy.argtypes = [H]
+    L.mc_multi_destroy.restype = None
+    L.mc_multi_last_error.argtypes = [H]
+    L.mc_multi_last_error.restype = C.c_char_p
+    L.mc_multi_device_count.argtypes = [H]
+    L.mc_multi_handle.argtypes = [H, C.c_int]
+    L.mc_multi_handle.restype = H
+    L.mc_multi_range.argtypes = [H, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mc_multi_set_sites.argtypes = [H, C.POINTER(A.SitesSoA), C.POINTER(A.InitialSoA)]
+    L.mc_multi_step_days.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
+    L.mc_multi_step_days_async.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA)]
+    L.mc_multi_wait.argtypes = [H]
     L.mc_get_counters.argtypes = [H, C.POINTER(A.Counters)]
     L.mc_reset_counters.argtypes = [H]
     L.mc_get_status.argtypes = [H, C.POINTER(C.c_int32)]

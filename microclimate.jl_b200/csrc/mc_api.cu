@@ -198,9 +198,16 @@ struct mc_handle {
     int device = 0;
     int N = 0;
     cudaStream_t stream = nullptr;
-    static constexpr int MAX_SLICES = 4;
-    cudaStream_t slice_stream[MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_ready = nullptr, ev_slice[MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr}, ev_kernel[MAX_SLICES] = {nullptr, nullptr, nullptr, nullptr};
+    /* host-buffer pipeline (mc_step_days_async): copy-in, compute and copy-out streams over two staging sets */
+    static constexpr int DEPTH = 2;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_h2d[DEPTH] = {nullptr, nullptr}, ev_k[DEPTH] = {nullptr, nullptr}, ev_d2h[DEPTH] = {nullptr, nullptr};
+    cudaEvent_t ev_t0[DEPTH] = {nullptr, nullptr}, ev_t1[DEPTH] = {nullptr, nullptr};
+    bool busy[DEPTH] = {false, false};                 /* a chunk enqueued on staging set b has not been harvested yet */
+    int32_t* status_dst[DEPTH] = {nullptr, nullptr};   /* where that chunk's status words land on the host */
+    std::vector<int32_t> status_own[DEPTH];
+    uint64_t chunk_seq = 0;
+    int last_flagged = 0; double pending_ms = 0.0; bool timed_by_ev01 = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     /* device arrays (all one arena) */
@@ -208,14 +215,14 @@ struct mc_handle {
     double *z0, *slope, *svf, *albedo, *bd, *md, *lam_m, *c_m, *psi_e, *ks, *bb, *rootd, *init_T, *init_theta;
     double *T, *theta, *sum_phase, *pool, *wetness, *L_ode, *L_prof, *tdeep_prev, *fsal;
     double *snow_T = nullptr, *snow_state = nullptr, *snow_nd = nullptr, *q_freeze = nullptr, *L_air = nullptr;
-    int32_t* doy_dev = nullptr; size_t doy_cap = 0;
+    int32_t* doy_dev[2] = {nullptr, nullptr}; size_t doy_cap[2] = {0, 0};      /* day-of-year vector of the chunk, one per staging set */
     int32_t* flags = nullptr;
     unsigned long long* counters = nullptr;
     bool has_init_T = false, sites_set = false;
     int64_t days_done = 0;
     /* chunk staging (grown on demand) */
-    double* stage_in = nullptr; size_t stage_in_doubles = 0;
-    double* stage_out = nullptr; size_t stage_out_doubles = 0;
+    double* stage_in[DEPTH] = {nullptr, nullptr}; size_t stage_in_doubles[DEPTH] = {0, 0};
+    double* stage_out[DEPTH] = {nullptr, nullptr}; size_t stage_out_doubles[DEPTH] = {0, 0};
     double* coop_scr = nullptr; size_t coop_scr_doubles = 0;      /* per-block scratch of the block-cooperative kernel */
     double* async_scr = nullptr; size_t async_scr_doubles = 0;    /* per-block L2-resident scratch of the asynchronous kernel */
     double last_ms = 0.0; unsigned long long last_launches = 0;
@@ -288,7 +295,6 @@ static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
     const size_t need = (size_t)grid * MC_COOP_ROWS(NA) * TB;
     if (h->coop_scr_doubles < need) {
         MC_CUDA(h, cudaStreamSynchronize(h->stream));
-        for (int k = 0; k < mc_handle::MAX_SLICES; k++) if (h->slice_stream[k]) MC_CUDA(h, cudaStreamSynchronize(h->slice_stream[k]));
         if (h->coop_scr) { MC_CUDA(h, cudaFree(h->coop_scr)); h->coop_scr = nullptr; h->coop_scr_doubles = 0; }
         MC_CUDA(h, cudaMalloc(&h->coop_scr, need * sizeof(double)));
         h->coop_scr_doubles = need;
@@ -327,7 +333,6 @@ static int launch_chunk_async(mc_handle* h, mcd::KArgs& a, cudaStream_t st, int 
     const size_t need = (size_t)grid * mcd::G_ARRAYS * NA * SLOTS;
     if (h->async_scr_doubles < need) {
         MC_CUDA(h, cudaStreamSynchronize(h->stream));
-        for (int k = 0; k < mc_handle::MAX_SLICES; k++) if (h->slice_stream[k]) MC_CUDA(h, cudaStreamSynchronize(h->slice_stream[k]));
         if (h->async_scr) { MC_CUDA(h, cudaFree(h->async_scr)); h->async_scr = nullptr; h->async_scr_doubles = 0; }
         MC_CUDA(h, cudaMalloc(&h->async_scr, need * sizeof(double)));
         h->async_scr_doubles = need;
@@ -411,11 +416,14 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-    for (int k = 0; k < mc_handle::MAX_SLICES; k++) {
-        if ((e = cudaStreamCreateWithFlags(&h->slice_stream[k], cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-        if ((e = cudaEventCreateWithFlags(&h->ev_slice[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-        if ((e = cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (int k = 0; k < mc_handle::DEPTH; k++) {
+        if ((e = cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_k[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&h->ev_d2h[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreate(&h->ev_t0[k])) != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaEventCreate(&h->ev_t1[k])) != cudaSuccess) return fail("cudaEventCreate", e);
     }
     const size_t S = (size_t)n_sites, N = (size_t)h->N;
     const size_t NSn = (size_t)model->n_snow;
@@ -443,31 +451,39 @@ void mc_destroy(mc_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->arena); cudaFree(h->doy_dev); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->stage_in); cudaFree(h->stage_out); cudaFree(h->coop_scr); cudaFree(h->async_scr);
+    if (h->s_in) cudaStreamSynchronize(h->s_in);
+    if (h->s_out) cudaStreamSynchronize(h->s_out);
+    cudaFree(h->arena); cudaFree(h->doy_dev[0]); cudaFree(h->doy_dev[1]); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->coop_scr); cudaFree(h->async_scr);
+    for (int k = 0; k < mc_handle::DEPTH; k++) { cudaFree(h->stage_in[k]); cudaFree(h->stage_out[k]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
-    for (int k = 0; k < mc_handle::MAX_SLICES; k++) { if (h->ev_slice[k]) cudaEventDestroy(h->ev_slice[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->slice_stream[k]) cudaStreamDestroy(h->slice_stream[k]); }
+    for (int k = 0; k < mc_handle::DEPTH; k++) {
+        cudaEvent_t evs[5] = {h->ev_h2d[k], h->ev_k[k], h->ev_d2h[k], h->ev_t0[k], h->ev_t1[k]};
+        for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
-int mc_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init)
+/* sites of this handle = columns [col0, col0 + S) of host arrays that are `host_pitch` doubles wide (a multi-device job shares one set of arrays) */
+static int set_sites_pitched(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init, int64_t host_pitch, int64_t col0)
 {
-    if (!h) return -1;
     if (!s || !init || !init->initial_soil_moisture) { h->err = "sites/init must be non-NULL and initial_soil_moisture given"; return -1; }
     MC_CUDA(h, cudaSetDevice(h->device));
-    const size_t S = (size_t)h->S, N = (size_t)h->N, bS = S * sizeof(double), bNS = N * bS;
+    if (mc_wait(h) < 0) return -1;
+    const size_t S = (size_t)h->S, N = (size_t)h->N, bS = S * sizeof(double), hp = (size_t)host_pitch * sizeof(double);
     const double* site_src[4] = {s->roughness_height, s->slope, s->sky_view_fraction, s->albedo};
     double* site_dst[4] = {h->z0, h->slope, h->svf, h->albedo};
     const double* node_src[8] = {s->bulk_density, s->mineral_density, s->mineral_conductivity, s->mineral_heat_capacity,
                                  s->air_entry_water_potential, s->saturated_hydraulic_conductivity, s->campbell_b_parameter, s->root_density};
     double* node_dst[8] = {h->bd, h->md, h->lam_m, h->c_m, h->psi_e, h->ks, h->bb, h->rootd};
-    for (int k = 0; k < 4; k++) { if (!site_src[k]) { h->err = "mc_sites_soa has a NULL site field"; return -1; } MC_CUDA(h, cudaMemcpyAsync(site_dst[k], site_src[k], bS, cudaMemcpyHostToDevice, h->stream)); }
-    for (int k = 0; k < 8; k++) { if (!node_src[k]) { h->err = "mc_sites_soa has a NULL node field"; return -1; } MC_CUDA(h, cudaMemcpyAsync(node_dst[k], node_src[k], bNS, cudaMemcpyHostToDevice, h->stream)); }
+    for (int k = 0; k < 4; k++) { if (!site_src[k]) { h->err = "mc_sites_soa has a NULL site field"; return -1; } MC_CUDA(h, cudaMemcpyAsync(site_dst[k], site_src[k] + col0, bS, cudaMemcpyHostToDevice, h->stream)); }
+    for (int k = 0; k < 8; k++) { if (!node_src[k]) { h->err = "mc_sites_soa has a NULL node field"; return -1; } MC_CUDA(h, cudaMemcpy2DAsync(node_dst[k], bS, node_src[k] + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream)); }
     h->has_init_T = init->initial_soil_temperature != nullptr;
-    if (h->has_init_T) MC_CUDA(h, cudaMemcpyAsync(h->init_T, init->initial_soil_temperature, bNS, cudaMemcpyHostToDevice, h->stream));
-    MC_CUDA(h, cudaMemcpyAsync(h->init_theta, init->initial_soil_moisture, bNS, cudaMemcpyHostToDevice, h->stream));
+    if (h->has_init_T) MC_CUDA(h, cudaMemcpy2DAsync(h->init_T, bS, init->initial_soil_temperature + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream));
+    MC_CUDA(h, cudaMemcpy2DAsync(h->init_theta, bS, init->initial_soil_moisture + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream));
     mcd::KArgs a; fill_site_state_args(h, a);
     init_state_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(a, h->N, h->model.n_snow, h->model.snow);
     MC_CUDA(h, cudaGetLastError());
@@ -475,6 +491,12 @@ int mc_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init
     MC_CUDA(h, cudaStreamSynchronize(h->stream));
     h->days_done = 0; h->sites_set = true;
     return 0;
+}
+
+int mc_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init)
+{
+    if (!h) return -1;
+    return set_sites_pitched(h, s, init, h->S, 0);
 }
 
 static int copy_state(mc_handle* h, const mc_state_soa* st, bool to_host)
@@ -511,7 +533,7 @@ static int check_forcing(mc_handle* h, const mc_forcing_soa* f)
 
 /* argument validation + KArgs for a chunk whose forcing/output pointers are DEVICE pointers; uploads the model constants and the
  * day-of-year vector on the handle's main stream */
-static int prepare_chunk(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o, mcd::KArgs& a)
+static int prepare_chunk(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o, mcd::KArgs& a, int b = 0)
 {
     if (!h->sites_set) { h->err = "mc_set_sites has not been called"; return -1; }
     if (!f || !o || ndays <= 0) { h->err = "forcing/out must be non-NULL and ndays positive"; return -1; }
@@ -535,9 +557,13 @@ static int prepare_chunk(mc_handle* h, int64_t day0, int32_t ndays, const mc_for
         if (!a.o_T || (h->model.n_snow > 0 && (!a.o_snow_depth || !a.o_snow_T))) { h->err = "solve_air! outputs need soil_temperature (and snow_depth + snow_temperature with SnowModel) selected"; return -1; }
     }
     if (f->day_of_year) {                /* MicroProblem.days: always a HOST pointer, staged here (used by the snow melt-factor / Q_freeze guards) */
-        if (h->doy_cap < (size_t)ndays) { if (h->doy_dev) MC_CUDA(h, cudaFree(h->doy_dev)); MC_CUDA(h, cudaMalloc(&h->doy_dev, (size_t)ndays * sizeof(int32_t))); h->doy_cap = (size_t)ndays; }
-        MC_CUDA(h, cudaMemcpyAsync(h->doy_dev, f->day_of_year, (size_t)ndays * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        a.doy = h->doy_dev;
+        if (h->doy_cap[b] < (size_t)ndays) {
+            MC_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (h->doy_dev[b]) MC_CUDA(h, cudaFree(h->doy_dev[b]));
+            MC_CUDA(h, cudaMalloc(&h->doy_dev[b], (size_t)ndays * sizeof(int32_t))); h->doy_cap[b] = (size_t)ndays;
+        }
+        MC_CUDA(h, cudaMemcpyAsync(h->doy_dev[b], f->day_of_year, (size_t)ndays * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        a.doy = h->doy_dev[b];
     }
     return 0;
 }
@@ -580,14 +606,29 @@ int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forc
 {
     if (!h) return -1;
     mcd::KArgs a;
-    if (int rc = prepare_chunk(h, day0, ndays, f, o, a)) return rc;
+    if (int rc = prepare_chunk(h, day0, ndays, f, o, a, (int)(h->chunk_seq++ & 1))) return rc;
     std::lock_guard<std::mutex> model_guard(g_model_mutex[h->device % MAX_DEVICES]);
     if (int rc = ensure_model_resident(h)) return rc;
     MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (int rc = launch_range(h, a, 0, h->S, h->stream)) return rc;
     MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    h->last_launches = 1;
+    h->last_launches = 1; h->timed_by_ev01 = true;
     h->days_done += ndays;
+    return 0;
+}
+
+/* a chunk on staging set b is complete on the device: collect its kernel time and flagged-site count */
+static int harvest(mc_handle* h, int b)
+{
+    if (!h->busy[b]) return 0;
+    MC_CUDA(h, cudaEventSynchronize(h->ev_d2h[b]));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_t0[b], h->ev_t1[b]) == cudaSuccess) h->pending_ms += ms;
+    int nbad = 0;
+    const int32_t* st = h->status_dst[b];
+    for (int64_t i = 0; i < h->S; i++) if (st[i]) nbad++;
+    h->last_flagged = nbad;
+    h->busy[b] = false;
     return 0;
 }
 
@@ -597,34 +638,38 @@ int mc_synchronize(mc_handle* h)
     MC_CUDA(h, cudaSetDevice(h->device));
     MC_CUDA(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;
-    if (h->last_launches && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+    if (h->timed_by_ev01 && h->last_launches && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
     return 0;
 }
 
 static int ensure_stage(mc_handle* h, double** buf, size_t* have, size_t need)
 {
     if (*have >= need) return 0;
+    /* growing a staging set: nothing may still be using the old one */
+    MC_CUDA(h, cudaStreamSynchronize(h->s_in)); MC_CUDA(h, cudaStreamSynchronize(h->stream)); MC_CUDA(h, cudaStreamSynchronize(h->s_out));
     if (*buf) { MC_CUDA(h, cudaFree(*buf)); *buf = nullptr; *have = 0; }
     MC_CUDA(h, cudaMalloc(buf, need * sizeof(double)));
     *have = need;
     return 0;
 }
 
-/* Host-buffer entry point.  The site range can be cut into up to 4 contiguous slices (MC_SLICES), each on its own stream:
- *     H2D(slice k forcing)  ->  soil_chunk_kernel(slice k)  ->  D2H(slice k outputs)
- * so the PCIe copies of one slice overlap the kernel of another (site-fastest SoA makes a slice a strided block per row:
- * cudaMemcpy2DAsync with pitch S*8).  Results do not depend on the slicing (sites are independent). */
-int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+/* Host-buffer chunk, asynchronous.  Three streams over two staging sets:
+ *     copy-in :  H2D(forcing q)                      waits for kernel q-2 (same staging set)
+ *     compute :  zero outputs, kernel q              waits for H2D q and for D2H q-2
+ *     copy-out:  D2H(outputs q, status)              waits for kernel q
+ * so the H2D of chunk q+1 and the D2H of chunk q-1 overlap the kernel of chunk q.  Host arrays may be wider than the handle (a multi-device
+ * job: `host_pitch` doubles per row, this handle's sites start at column `col0`); site-fastest SoA makes that a strided 2-D copy per plane. */
+static int step_days_enqueue(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o, int64_t host_pitch, int64_t col0)
 {
-    if (!h) return -1;
     if (!f || !o || ndays <= 0) { h->err = "forcing/out must be non-NULL and ndays positive"; return -1; }
     if (check_forcing(h, f)) return -1;
     MC_CUDA(h, cudaSetDevice(h->device));
+    const int b = (int)(h->chunk_seq & 1);
+    if (int rc = harvest(h, b)) return rc;                         /* at most DEPTH chunks in flight: reusing a staging set waits for its previous chunk */
     const size_t S = (size_t)h->S, N = (size_t)h->N, H = 24 * (size_t)ndays, D = (size_t)ndays;
     const size_t NSn = (size_t)h->model.n_snow;
     struct Plane { const double* host_in; double* host_out; double* dev; size_t rows; };   /* [rows][S] planes */
     std::vector<Plane> in_planes, out_planes;
-    /* stage forcing */
     const double* hourly_src[11] = {f->pressure, f->reference_temperature, f->reference_wind_speed, f->reference_humidity, f->cloud_cover,
                                     f->global_radiation, f->diffuse_fraction, f->zenith_angle, f->zenith_slope_angle, f->rainfall_hourly, f->longwave_radiation};
     const double* daily_src[8] = {f->leaf_area_index, f->shade, f->surface_emissivity, f->cloud_emissivity, f->soil_wetness, f->deep_soil_temperature,
@@ -633,18 +678,17 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     for (const double* p : hourly_src) if (p) need_in += H * S;
     for (const double* p : daily_src) if (p) need_in += D * S;
     if (f->prescribed_soil_moisture) need_in += D * N * S;
-    if (int rc = ensure_stage(h, &h->stage_in, &h->stage_in_doubles, need_in)) return rc;
+    if (int rc = ensure_stage(h, &h->stage_in[b], &h->stage_in_doubles[b], need_in)) return rc;
     mc_forcing_soa fd; std::memset(&fd, 0, sizeof(fd));
     const double** hourly_dst[11] = {&fd.pressure, &fd.reference_temperature, &fd.reference_wind_speed, &fd.reference_humidity, &fd.cloud_cover,
                                      &fd.global_radiation, &fd.diffuse_fraction, &fd.zenith_angle, &fd.zenith_slope_angle, &fd.rainfall_hourly, &fd.longwave_radiation};
     const double** daily_dst[8] = {&fd.leaf_area_index, &fd.shade, &fd.surface_emissivity, &fd.cloud_emissivity, &fd.soil_wetness, &fd.deep_soil_temperature,
                                    &fd.rainfall_daily, &fd.albedo_daily};
-    double* p = h->stage_in;
+    double* p = h->stage_in[b];
     for (int k = 0; k < 11; k++) if (hourly_src[k]) { in_planes.push_back({hourly_src[k], nullptr, p, H}); *hourly_dst[k] = p; p += H * S; }
     for (int k = 0; k < 8; k++) if (daily_src[k]) { in_planes.push_back({daily_src[k], nullptr, p, D}); *daily_dst[k] = p; p += D * S; }
     if (f->prescribed_soil_moisture) { in_planes.push_back({f->prescribed_soil_moisture, nullptr, p, D * N}); fd.prescribed_soil_moisture = p; p += D * N * S; }
     fd.day_of_year = f->day_of_year;
-    /* stage outputs */
     double* node_host[7] = {o->soil_temperature, o->soil_moisture, o->soil_water_potential, o->soil_humidity, o->soil_thermal_conductivity, o->soil_heat_capacity, o->soil_bulk_density};
     double* scal_host[5] = {o->surface_water, o->sky_temperature, NSn ? o->snow_fall : nullptr, NSn ? o->snow_depth : nullptr, NSn ? o->snow_density : nullptr};
     double* snowT_host = NSn ? o->snow_temperature : nullptr;
@@ -657,13 +701,13 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     double* profs_host[2] = {o->convective_heat_flux, o->friction_velocity};
     for (double* q2 : prof_host) if (q2) need_out += H * NH * S;
     for (double* q2 : profs_host) if (q2) need_out += H * S;
-    if (int rc = ensure_stage(h, &h->stage_out, &h->stage_out_doubles, need_out ? need_out : 1)) return rc;
+    if (int rc = ensure_stage(h, &h->stage_out[b], &h->stage_out_doubles[b], need_out ? need_out : 1)) return rc;
     mc_output_soa od; std::memset(&od, 0, sizeof(od));
     double** node_dev[7] = {&od.soil_temperature, &od.soil_moisture, &od.soil_water_potential, &od.soil_humidity, &od.soil_thermal_conductivity, &od.soil_heat_capacity, &od.soil_bulk_density};
     double** scal_dev[5] = {&od.surface_water, &od.sky_temperature, &od.snow_fall, &od.snow_depth, &od.snow_density};
     double** prof_dev[3] = {&od.air_temperature, &od.wind_speed, &od.relative_humidity};
     double** profs_dev[2] = {&od.convective_heat_flux, &od.friction_velocity};
-    double* q = h->stage_out;
+    double* q = h->stage_out[b];
     for (int k = 0; k < 7; k++) if (node_host[k]) { out_planes.push_back({nullptr, node_host[k], q, H * N}); *node_dev[k] = q; q += H * N * S; }
     for (int k = 0; k < 5; k++) if (scal_host[k]) { out_planes.push_back({nullptr, scal_host[k], q, H}); *scal_dev[k] = q; q += H * S; }
     if (snowT_host) { out_planes.push_back({nullptr, snowT_host, q, H * NSn}); od.snow_temperature = q; q += H * NSn * S; }
@@ -671,50 +715,64 @@ int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa
     for (int k = 0; k < 2; k++) if (profs_host[k]) { out_planes.push_back({nullptr, profs_host[k], q, H}); *profs_dev[k] = q; q += H * S; }
 
     mcd::KArgs a;
-    if (int rc = prepare_chunk(h, day0, ndays, &fd, &od, a)) return rc;
+    if (int rc = prepare_chunk(h, day0, ndays, &fd, &od, a, b)) return rc;
+    const size_t w = S * sizeof(double), hp = (size_t)host_pitch * sizeof(double);
+    /* copy-in */
+    MC_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_k[b], 0));      /* kernel q-2 has finished reading this staging set (no-op for a never-recorded event) */
+    for (const Plane& pl : in_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.dev, w, pl.host_in + col0, hp, w, pl.rows, cudaMemcpyHostToDevice, h->s_in));
+    MC_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
+    /* compute */
+    MC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[b], 0));
+    MC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_d2h[b], 0));  /* D2H q-2 has drained this staging set's outputs */
     /* cells the path never writes (e.g. water potential rows under PrescribedSoilMoisture) read back as zero */
-    if (need_out) MC_CUDA(h, cudaMemsetAsync(h->stage_out, 0, need_out * sizeof(double), h->stream));
-    MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    MC_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));          /* model constants, day-of-year and the zeroed outputs are in place */
-    const char* want_env = getenv("MC_SLICES");                  /* development/test knob: force the number of slices */
-    const int want = want_env ? atoi(want_env) : 0;
-    /* default ONE slice: on B200 + PCIe Gen5 the pinned copies are ~3 % of a step, while splitting the launch costs more in
-     * per-slice tail (measured 1/2/4 slices at 1 Mi sites: 92.8 k / 91.5 k / 84.7 k site-days/s end to end) */
-    int n_slices = want > 0 ? want : 1;
-    if (n_slices > mc_handle::MAX_SLICES) n_slices = mc_handle::MAX_SLICES;
-    std::vector<int32_t> status_tmp;
-    int32_t* status_host = o->status;
-    if (!status_host) { status_tmp.resize(S); status_host = status_tmp.data(); }
-    int prev_kernel = -1;
-    std::unique_lock<std::mutex> model_guard(g_model_mutex[h->device % MAX_DEVICES]);
-    if (int rc = ensure_model_resident(h)) return rc;
-    for (int k = 0; k < n_slices; k++) {
-        const size_t lo = S * (size_t)k / (size_t)n_slices, hi = S * (size_t)(k + 1) / (size_t)n_slices;
-        if (hi == lo) continue;
-        cudaStream_t st = h->slice_stream[k];
-        const size_t w = (hi - lo) * sizeof(double), pitch = S * sizeof(double);
-        MC_CUDA(h, cudaStreamWaitEvent(st, h->ev_ready, 0));
-        for (const Plane& pl : in_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.dev + lo, pitch, pl.host_in + lo, pitch, w, pl.rows, cudaMemcpyHostToDevice, st));
-        /* kernels run one after another (slice k+1 waits for slice k) so that the D2H of slice k overlaps the kernel of slice k+1;
-         * concurrent slice kernels would all finish together and leave every D2H at the end */
-        if (prev_kernel >= 0) MC_CUDA(h, cudaStreamWaitEvent(st, h->ev_kernel[prev_kernel], 0));
-        if (int rc = launch_range(h, a, (int64_t)lo, (int64_t)hi, st, k)) return rc;
-        MC_CUDA(h, cudaEventRecord(h->ev_kernel[k], st));
-        prev_kernel = k;
-        for (const Plane& pl : out_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.host_out + lo, pitch, pl.dev + lo, pitch, w, pl.rows, cudaMemcpyDeviceToHost, st));
-        MC_CUDA(h, cudaMemcpyAsync(status_host + lo, h->flags + lo, (hi - lo) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        MC_CUDA(h, cudaEventRecord(h->ev_slice[k], st));
-        MC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_slice[k], 0));
+    if (need_out) MC_CUDA(h, cudaMemsetAsync(h->stage_out[b], 0, need_out * sizeof(double), h->stream));
+    {
+        std::lock_guard<std::mutex> model_guard(g_model_mutex[h->device % MAX_DEVICES]);
+        if (int rc = ensure_model_resident(h)) return rc;
+        MC_CUDA(h, cudaEventRecord(h->ev_t0[b], h->stream));
+        if (int rc = launch_range(h, a, 0, h->S, h->stream)) return rc;
+        MC_CUDA(h, cudaEventRecord(h->ev_t1[b], h->stream));
     }
-    MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    model_guard.unlock();                                         /* everything that reads the constant bank is enqueued */
-    h->last_launches = (unsigned long long)n_slices;
+    MC_CUDA(h, cudaEventRecord(h->ev_k[b], h->stream));
+    /* copy-out */
+    int32_t* status_host = o->status ? o->status + col0 : nullptr;
+    if (!status_host) { h->status_own[b].resize(S); status_host = h->status_own[b].data(); }
+    MC_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_k[b], 0));
+    for (const Plane& pl : out_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.host_out + col0, hp, pl.dev, w, w, pl.rows, cudaMemcpyDeviceToHost, h->s_out));
+    MC_CUDA(h, cudaMemcpyAsync(status_host, h->flags, S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out));
+    MC_CUDA(h, cudaEventRecord(h->ev_d2h[b], h->s_out));
+    h->status_dst[b] = status_host; h->busy[b] = true;
+    h->chunk_seq++;
+    h->last_launches = 1; h->timed_by_ev01 = false;
     h->days_done += ndays;
-    int rc = mc_synchronize(h);
-    if (rc < 0) return rc;
-    int nbad = 0;
-    for (size_t i = 0; i < S; i++) if (status_host[i]) nbad++;
-    return nbad;
+    return 0;
+}
+
+int mc_step_days_async(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!h) return -1;
+    return step_days_enqueue(h, day0, ndays, f, o, h->S, 0);
+}
+
+/* wait for every chunk enqueued with mc_step_days_async; returns the flagged-site count of the most recent one */
+int mc_wait(mc_handle* h)
+{
+    if (!h) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    const int first = (int)(h->chunk_seq & 1);                     /* older chunk first */
+    for (int k = 0; k < mc_handle::DEPTH; k++) if (int rc = harvest(h, (first + k) & 1)) return rc;
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->last_ms = h->pending_ms; h->pending_ms = 0.0;
+    return h->last_flagged;
+}
+
+/* Host-buffer entry point: one chunk, synchronous (enqueue + wait). */
+int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!h) return -1;
+    if (int rc = mc_wait(h)) { if (rc < 0) return rc; }
+    if (int rc = step_days_enqueue(h, day0, ndays, f, o, h->S, 0)) return rc;
+    return mc_wait(h);
 }
 
 int mc_get_counters(mc_handle* h, mc_counters* c)
@@ -797,6 +855,72 @@ int mc_measure_fp64_peak(mc_handle* h, double* tflops)
     MC_CUDA(h, cudaFree(buf));
     *tflops = best;
     return 0;
+}
+
+/* ---------------------------------------------------------------- one host process, several GPUs ---- */
+/* The reference idiom is one process sweeping sites (reinit!(cache, inputs); solve!(cache), src/simulation.jl:266-277).  A multi handle shards the
+ * sites of ONE set of host arrays contiguously over several devices (replicated model, no collective); every device runs the asynchronous
+ * pipeline above on its column range, so all GPUs copy and integrate concurrently from a single host thread. */
+struct mc_multi { std::vector<mc_handle*> h; std::vector<int64_t> lo; int64_t S = 0; std::string err; };
+
+int mc_multi_create(const mc_model_desc* model, int64_t n_sites, const int* device_ids, int n_devices, mc_multi** out)
+{
+    if (out) *out = nullptr;
+    if (!out || !device_ids || n_devices <= 0 || n_sites < n_devices) { g_create_error = "mc_multi_create: need out, device_ids, n_devices >= 1 and at least one site per device"; return -1; }
+    mc_multi* m = new mc_multi(); m->S = n_sites;
+    for (int g = 0; g < n_devices; g++) {
+        const int64_t lo = n_sites * g / n_devices, hi = n_sites * (g + 1) / n_devices;
+        mc_handle* hg = nullptr;
+        const int rc = mc_create(model, hi - lo, device_ids[g], &hg);
+        if (rc) { mc_multi_destroy(m); return rc; }
+        m->h.push_back(hg); m->lo.push_back(lo);
+    }
+    m->lo.push_back(n_sites);
+    *out = m;
+    return 0;
+}
+void mc_multi_destroy(mc_multi* m) { if (!m) return; for (mc_handle* hg : m->h) mc_destroy(hg); delete m; }
+const char* mc_multi_last_error(const mc_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+int mc_multi_device_count(const mc_multi* m) { return m ? (int)m->h.size() : -1; }
+mc_handle* mc_multi_handle(mc_multi* m, int g) { return (m && g >= 0 && g < (int)m->h.size()) ? m->h[(size_t)g] : nullptr; }
+int mc_multi_range(const mc_multi* m, int g, int64_t* lo, int64_t* hi)
+{
+    if (!m || g < 0 || g >= (int)m->h.size()) return -1;
+    if (lo) *lo = m->lo[(size_t)g];
+    if (hi) *hi = m->lo[(size_t)g + 1];
+    return 0;
+}
+int mc_multi_set_sites(mc_multi* m, const mc_sites_soa* s, const mc_initial_soa* init)
+{
+    if (!m) return -1;
+    for (size_t g = 0; g < m->h.size(); g++)
+        if (int rc = set_sites_pitched(m->h[g], s, init, m->S, m->lo[g])) { m->err = "device " + std::to_string(g) + ": " + m->h[g]->err; return rc; }
+    return 0;
+}
+int mc_multi_step_days_async(mc_multi* m, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!m) return -1;
+    for (size_t g = 0; g < m->h.size(); g++)
+        if (int rc = step_days_enqueue(m->h[g], day0, ndays, f, o, m->S, m->lo[g])) { m->err = "device " + std::to_string(g) + ": " + m->h[g]->err; return rc; }
+    return 0;
+}
+int mc_multi_wait(mc_multi* m)
+{
+    if (!m) return -1;
+    int total = 0;
+    for (size_t g = 0; g < m->h.size(); g++) {
+        const int rc = mc_wait(m->h[g]);
+        if (rc < 0) { m->err = "device " + std::to_string(g) + ": " + m->h[g]->err; return rc; }
+        total += rc;
+    }
+    return total;
+}
+int mc_multi_step_days(mc_multi* m, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    if (!m) return -1;
+    if (int rc = mc_multi_wait(m)) { if (rc < 0) return rc; }
+    if (int rc = mc_multi_step_days_async(m, day0, ndays, f, o)) return rc;
+    return mc_multi_wait(m);
 }
 
 }  /* extern "C" */

@@ -71,6 +71,19 @@ class SoilEngine:
         cf, co = forcing.c_struct(), out.c_struct()
         return self._check(self._L.mc_step_days(self.h, day0, forcing.ndays, C.byref(cf), C.byref(co)), "mc_step_days")
 
+    def step_days_async(self, day0: int, forcing: M.ForcingBatch, out: M.OutputBatch):
+        """mc_step_days_async: enqueue H2D -> kernel -> D2H of this chunk and return; call wait() before reading `out`.  Issuing the next chunk
+        before wait() overlaps its H2D (and the previous chunk's D2H) with this chunk's kernel.  The batches must stay alive until wait()."""
+        if forcing.S != self.S or out.S != self.S or out.ndays != forcing.ndays:
+            raise ValueError("forcing/output batch shapes do not match the engine")
+        cf, co = forcing.c_struct(), out.c_struct()
+        self._keep = getattr(self, "_keep", [])[-3:] + [(forcing, out, cf, co)]
+        self._check(self._L.mc_step_days_async(self.h, day0, forcing.ndays, C.byref(cf), C.byref(co)), "mc_step_days_async")
+
+    def wait(self) -> int:
+        """mc_wait: all enqueued chunks complete; returns the flagged-site count of the most recent one."""
+        return self._check(self._L.mc_wait(self.h), "mc_wait")
+
     def step_days_device(self, day0: int, ndays: int, forcing_ptrs: dict, output_ptrs: dict):
         """Same with DEVICE pointers (ints) already resident on this GPU; asynchronous until synchronize()."""
         cf, co = A.ForcingSoA(), A.OutputSoA()
@@ -113,6 +126,98 @@ class SoilEngine:
         return v.value
 
 
+class _HandleView(SoilEngine):
+    """A per-device handle owned by a MultiSoilEngine (state, counters, status of that device's site range)."""
+
+    def __init__(self, lib, h, desc, n_sites, device):
+        self._L, self.h, self.desc, self.S, self.device = lib, C.c_void_p(h), desc, int(n_sites), int(device)
+
+    def close(self):
+        self.h = None
+
+
+class MultiSoilEngine:
+    """One host process, several GPUs (mc_multi_*): the sites of ONE set of host arrays are sharded contiguously over `devices`; every device
+    runs the asynchronous H2D / kernel / D2H pipeline on its column range and writes into its columns of the caller's output arrays."""
+
+    def __init__(self, desc: A.ModelDesc, n_sites: int, devices: Sequence[int]):
+        self.desc, self.S, self.devices = desc, int(n_sites), [int(d) for d in devices]
+        self._L = _lib.lib()
+        self.h = C.c_void_p()
+        ids = (C.c_int * len(self.devices))(*self.devices)
+        rc = self._L.mc_multi_create(C.byref(desc), self.S, ids, len(self.devices), C.byref(self.h))
+        if rc != 0:
+            msg = self._L.mc_multi_last_error(None)
+            self.h = None
+            raise RuntimeError(f"mc_multi_create failed (rc={rc}): {msg.decode() if msg else ''}")
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.mc_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            msg = self._L.mc_multi_last_error(self.h)
+            raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    def ranges(self):
+        out = []
+        for g in range(len(self.devices)):
+            lo, hi = C.c_int64(), C.c_int64()
+            self._check(self._L.mc_multi_range(self.h, g, C.byref(lo), C.byref(hi)), "mc_multi_range")
+            out.append((lo.value, hi.value))
+        return out
+
+    def device_engine(self, g: int) -> SoilEngine:
+        lo, hi = self.ranges()[g]
+        return _HandleView(self._L, self._L.mc_multi_handle(self.h, g), self.desc, hi - lo, self.devices[g])
+
+    def set_sites(self, sites: M.SitesBatch):
+        if sites.S != self.S or sites.N != self.desc.n_soil:
+            raise ValueError("SitesBatch shape does not match the engine")
+        cs, ci = sites.c_sites(), sites.c_initial()
+        self._check(self._L.mc_multi_set_sites(self.h, C.byref(cs), C.byref(ci)), "mc_multi_set_sites")
+
+    def step_days_async(self, day0: int, forcing: M.ForcingBatch, out: M.OutputBatch):
+        if forcing.S != self.S or out.S != self.S or out.ndays != forcing.ndays:
+            raise ValueError("forcing/output batch shapes do not match the engine")
+        cf, co = forcing.c_struct(), out.c_struct()
+        self._keep = self._keep[-3:] + [(forcing, out, cf, co)]
+        self._check(self._L.mc_multi_step_days_async(self.h, day0, forcing.ndays, C.byref(cf), C.byref(co)), "mc_multi_step_days_async")
+
+    def wait(self) -> int:
+        return self._check(self._L.mc_multi_wait(self.h), "mc_multi_wait")
+
+    def step_days(self, day0: int, forcing: M.ForcingBatch, out: M.OutputBatch) -> int:
+        self.step_days_async(day0, forcing, out)
+        return self.wait()
+
+    def counters(self) -> dict:
+        tot = None
+        for g in range(len(self.devices)):
+            c = self.device_engine(g).counters()
+            tot = c if tot is None else {k: (max(tot[k], v) if k == "gpu_ms" else tot[k] + v) for k, v in c.items()}
+        return tot
+
+    def status(self) -> np.ndarray:
+        return np.concatenate([self.device_engine(g).status() for g in range(len(self.devices))])
+
+
 def site_shards(n_sites: int, n_shards: int):
     """Contiguous, near-equal site ranges [lo, hi) — the only partitioning the path needs (no collective)."""
     base, rem = divmod(n_sites, n_shards)
@@ -126,13 +231,14 @@ def site_shards(n_sites: int, n_shards: int):
 
 def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, days: Sequence[int],
                        time_mode=None, fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS,
-                       chunk_days: Optional[int] = None, device: int = 0) -> M.OutputBatch:
+                       chunk_days: Optional[int] = None, device: int = 0, devices: Optional[Sequence[int]] = None) -> M.OutputBatch:
     """Batched `solve_soil!` (+ `solve_air!` when any of the profile fields air_temperature / wind_speed / relative_humidity /
     convective_heat_flux / friction_velocity is selected): one model, many inputs -> one OutputBatch (site-fastest);
     `site_result(s)` un-marshals a site into the reference's (nsteps, N) MicroResult layout.
 
     `chunk_days` streams time in chunks with the carried state resident on the GPU (results are identical
-    to a single chunk: the state carried between chunks is exactly what the reference carries between days)."""
+    to a single chunk: the state carried between chunks is exactly what the reference carries between days).  `devices` shards the sites
+    over several GPUs from this one process (MultiSoilEngine); chunks are pipelined (H2D / kernel / D2H overlap) either way."""
     time_mode = time_mode if time_mode is not None else T.NonConsecutiveDayMode()
     if len(inputs) == 0:
         raise ValueError("inputs must be non-empty")
@@ -141,18 +247,25 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
     forcing = M.ForcingBatch.from_inputs(model, inputs, days)
     ndays, S = len(days), len(inputs)
     out = M.OutputBatch(ndays, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
-    with SoilEngine(desc, S, device) as eng:
+    with (MultiSoilEngine(desc, S, devices) if devices else SoilEngine(desc, S, device)) as eng:
         eng.set_sites(sites)
         if not chunk_days or chunk_days >= ndays:
             eng.step_days(0, forcing, out)
         else:
-            d0 = 0
-            while d0 < ndays:
+            d0, parts = 0, []
+            while d0 < ndays:                     # enqueue chunk after chunk: copies of neighbouring chunks overlap the kernels
                 d1 = min(ndays, d0 + chunk_days)
                 part = M.OutputBatch(d1 - d0, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
-                eng.step_days(d0, forcing.day_slice(d0, d1), part)
-                out.assign_rows(24 * d0, part)
+                fpart = forcing.day_slice(d0, d1)
+                eng.step_days_async(d0, fpart, part)
+                parts.append((d0, part, fpart))
+                if len(parts) > 2:                # chunks older than the pipeline depth are complete
+                    r0, p0, _ = parts.pop(0)
+                    out.assign_rows(24 * r0, p0)
                 d0 = d1
+            eng.wait()
+            for r0, p0, _ in parts:
+                out.assign_rows(24 * r0, p0)
             out.status[:] = eng.status()
     return out
 

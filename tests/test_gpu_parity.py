@@ -166,20 +166,67 @@ def test_snow_model_matches_oracle(SoilEngine):
     assert state.snow_state is not None and state.snow_state[0, 0] == o1.snow_depth[-1, 0]      # current depth is carried
 
 
-def test_pipelined_site_slices_do_not_change_results(SoilEngine, synth, monkeypatch):
-    """mc_step_days cuts the site range into slices on separate streams (H2D / kernel / D2H overlap); forcing 3 ragged slices on
-    512 sites must give the single-launch result bit for bit."""
+def test_async_pipeline_and_multi_handle_match_single_call(SoilEngine, synth):
+    """mc_step_days_async / mc_wait (H2D, kernel and D2H of neighbouring day chunks overlap on three streams over two staging sets) and the
+    multi-device handle (sites of ONE set of host arrays sharded over devices, here three ragged shards; on a one-GPU box all on device 0, which
+    also exercises handles with different site counts sharing a device) must reproduce the single synchronous call bit for bit."""
+    import torch
+    from microclimate_jl_b200.simulation import MultiSoilEngine
     desc, sites, forcing = synth
     f = ("soil_temperature", "soil_moisture", "surface_water", "sky_temperature")
-    monkeypatch.setenv("MC_SLICES", "1")
-    one, _ = parity.run(SoilEngine, desc, sites, forcing, fields=f)
-    monkeypatch.setenv("MC_SLICES", "3")
-    three, e3 = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
-    assert e3.counters()["n_kernel_launches"] == 3
-    for name in f:
-        a, b = getattr(one, name), getattr(three, name)
-        assert np.array_equal(a[..., :509], b), name
-    assert np.array_equal(one.status[:509], three.status)
+    whole, _ = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    # three one-day chunks enqueued back to back, one wait at the end
+    eng = SoilEngine(desc, sites.S); eng.set_sites(sites)
+    parts = [M.OutputBatch(1, desc.n_soil, sites.S, f) for _ in range(3)]
+    fparts = [forcing.day_slice(d, d + 1) for d in range(3)]
+    for d in range(3):
+        eng.step_days_async(d, fparts[d], parts[d])
+    nbad = eng.wait()
+    piped = M.OutputBatch(3, desc.n_soil, sites.S, f)
+    for d in range(3):
+        piped.assign_rows(24 * d, parts[d])
+    parity.assert_bit_identical(piped, whole, f)
+    assert nbad == int((whole.status != 0).sum())
+    assert eng.counters()["n_site_days"] == 3 * sites.S
+    # multi-device handle: as many GPUs as the box has, at least three shards
+    ndev = torch.cuda.device_count()
+    devices = [g % ndev for g in range(max(3, ndev))]
+    with MultiSoilEngine(desc, 509, devices) as me:
+        assert me.ranges()[0][0] == 0 and me.ranges()[-1][1] == 509
+        me.set_sites(sites.slice(0, 509))
+        out = M.OutputBatch(3, desc.n_soil, 509, f)
+        me.step_days(0, forcing.site_slice(0, 509), out)
+        for name in f:
+            assert np.array_equal(getattr(out, name), getattr(whole, name)[..., :509]), name
+        assert np.array_equal(out.status, whole.status[:509])
+        assert me.counters()["n_site_days"] == 3 * 509
+
+
+def test_handles_with_different_models_share_a_device(SoilEngine):
+    """Two handles with DIFFERENT models (N = 10 prescribed-moisture vs N = 19 dynamic) alternate on one device through the asynchronous device-pointer
+    entry: the per-device constant bank must never be overwritten under a running kernel."""
+    import torch
+    p1, _ = configs.config1_monthly()
+    p2, _ = configs.config2_daily(3)
+    d1, s1, f1 = _problem_buffers(p1)
+    d2, s2, f2 = _problem_buffers(p2)
+    ref1, _ = parity.run(OracleEngine, d1, s1, f1, fields=("soil_temperature",))
+    ref2, _ = parity.run(OracleEngine, d2, s2, f2, fields=("soil_temperature", "soil_moisture"))
+    e1 = SoilEngine(d1, 1); e1.set_sites(s1)
+    e2 = SoilEngine(d2, 1); e2.set_sites(s2)
+    o1 = [M.OutputBatch(1, d1.n_soil, 1, ("soil_temperature",)) for _ in range(f1.ndays)]
+    o2 = [M.OutputBatch(1, d2.n_soil, 1, ("soil_temperature", "soil_moisture")) for _ in range(f2.ndays)]
+    k1 = [f1.day_slice(d, d + 1) for d in range(f1.ndays)]
+    k2 = [f2.day_slice(d, d + 1) for d in range(f2.ndays)]
+    for d in range(max(f1.ndays, f2.ndays)):         # interleave asynchronous chunks of the two models
+        if d < f1.ndays:
+            e1.step_days_async(d, k1[d], o1[d])
+        if d < f2.ndays:
+            e2.step_days_async(d, k2[d], o2[d])
+    e1.wait(); e2.wait()
+    got1 = np.concatenate([o.soil_temperature for o in o1]); got2 = np.concatenate([o.soil_temperature for o in o2])
+    assert np.array_equal(got1, ref1.soil_temperature) and np.array_equal(got2, ref2.soil_temperature)
+    assert np.array_equal(np.concatenate([o.soil_moisture for o in o2]), ref2.soil_moisture)
 
 
 @pytest.mark.parametrize("n_nodes", [7, 24], ids=["N7", "N24"])
@@ -214,6 +261,7 @@ def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     desc, sites, forcing = synth
     f = ("soil_temperature", "soil_moisture", "surface_water", "soil_water_potential")
     ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    monkeypatch.setenv("MC_KERNEL", "coop")                     # the block-synchronous cooperative kernel (round 1; the default is the asynchronous one)
     monkeypatch.setenv("MC_COOP_BLOCK", "1024")                 # one ragged block: 512 sites + 512 mirror threads
     a, ea = parity.run(SoilEngine, desc, sites, forcing, fields=f)
     parity.assert_bit_identical(a, ref, f)
@@ -224,10 +272,17 @@ def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     for name in f:
         assert np.array_equal(getattr(b, name), getattr(ref, name)[..., :509]), name
     monkeypatch.delenv("MC_COOP_BLOCK"); monkeypatch.delenv("MC_COOP_GRID")
-    monkeypatch.setenv("MC_KERNEL", "legacy")                   # the per-site kernel (what snow / tolerance-convergence models run)
+    monkeypatch.setenv("MC_KERNEL", "legacy")                   # the per-site kernel (what snow / flux-potential models run)
     c, ec = parity.run(SoilEngine, desc, sites, forcing, fields=f)
     parity.assert_bit_identical(c, ref, f)
     monkeypatch.delenv("MC_KERNEL")
+    # the asynchronous kernel under odd shapes: 3 blocks x 5 slots x 96 threads (passes claimed in pieces, slots reloaded many times), then one block
+    for grid, slots, threads in (("3", "5", "96"), ("1", "64", "1024")):
+        monkeypatch.setenv("MC_ASYNC_GRID", grid); monkeypatch.setenv("MC_ASYNC_SLOTS", slots); monkeypatch.setenv("MC_ASYNC_THREADS", threads)
+        d, ed = parity.run(SoilEngine, desc, sites.slice(0, 203), forcing.site_slice(0, 203), fields=f)
+        for name in f:
+            assert np.array_equal(getattr(d, name), getattr(ref, name)[..., :203]), name
+    monkeypatch.delenv("MC_ASYNC_GRID"); monkeypatch.delenv("MC_ASYNC_SLOTS"); monkeypatch.delenv("MC_ASYNC_THREADS")
 
 
 def test_solve_air_matches_oracle(SoilEngine):
