@@ -25,15 +25,45 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FIELDS = ("soil_temperature", "soil_moisture")
-# FP64 flop per site-day of the benchmark grid (DADD + DMUL + 2 DFMA thread instructions, ncu SASS counts, profiles/README.md):
-#   EXECUTED by the current kernel (build v10, profiles/r1_v10_*): 38.55e6 - this is what roofline.achieved uses;
-#   the reference algorithm run literally (every stomatal / moisture Newton iteration executed, build v9): 41.6e6 - reported beside it.
-FLOP_PER_SITE_DAY = 38.55e6
-ALG_FLOP_PER_SITE_DAY = 41.6e6
 ALG_BYTES_PER_SITE_DAY = (10 * 24 + 7) * 8 + 2 * 19 * 24 * 8     # hourly+daily forcing read, hourly T+theta written
-# dram__bytes_read.sum + dram__bytes_write.sum of the soil kernel per site-day (one ncu capture, profiles/r1_v10_metrics.csv: 1.271 TB + 0.338 TB over
-# 151 552 site-days): block scratch and thread-local arrays of 1024 resident sites per SM overflow L2 - the traffic is ~1100x the algorithmic bytes
-DRAM_BYTES_PER_SITE_DAY = (1.270695e12 + 337.769864e9) / 151552
+STATUS_BITS = {1: "NAN", 2: "DT_UNDERFLOW", 4: "NEWTON_MAXITER", 8: "STEP_LIMIT"}      # include/microclimate_b200.h MC_STATUS_*
+
+
+def library_hash():
+    """Identity of the built CUDA library: numbers calibrated with ncu (profiles/traffic.json) are only valid for the build they were taken on."""
+    import hashlib
+    from microclimate_jl_b200 import _lib
+    h = hashlib.sha256()
+    for d in sorted(_lib.DEPS):
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def walg_per_site_day(counters, site_days):
+    """W_alg = sum_k count_k * w_k, counts from the device counters of the timed region, weights = source-level FP64 operation counts of
+    the oracle's functions (tools/walg_weights.py, profiles/walg_weights.json).  Stomatal iterations are not credited (see the weights file)."""
+    path = os.path.join(ROOT, "profiles", "walg_weights.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        W = json.load(f)["regions"]
+    ev = {"other": 24 * counters["n_day_passes"], "rhs": counters["n_rhs"], "obukhov_iter": counters["n_obukhov_iter"], "newton_iter": counters["n_newton_iter"],
+          "infil_step": counters["n_infil_steps"], "step_control": counters["n_accept"] + counters["n_reject"]}
+    parts = {k: ev[k] * W[k]["flop_eq_per_event"] / site_days for k in ev}
+    return sum(parts.values()), parts
+
+
+def calibrated_traffic():
+    """DRAM bytes and executed FP64 flops per site-day from the ncu capture of THIS build (tools/gpu_profile.py writes profiles/traffic.json with the
+    library hash); a capture of another build is refused."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    t["stale"] = t.get("library_hash") != library_hash()
+    return t
 
 
 def _pinned(shape):
@@ -139,6 +169,8 @@ def main():
         times = cpu_run(desc, n, 0, n, 0, args.warmup + args.steps, threads=cores)      # n sites spanning the whole latitude sweep: same mix as a GPU shard
         tt = times[args.warmup:]
         v = n * len(tt) / sum(tt)
+        config = dict(config, sample_sites=n, sample_note="CPU arm: a %d-site sample of the same grid (one full latitude sweep, same per-site workload mix) x 1 day per step; "
+                                                            "the metric is a per-site-day rate, the label sites_per_gpu is the GPU arm's" % n)
         line = {"impl": "reference", "metric": "site-days/sec (hourly soil T+moisture)", "value": v, "unit": "site-days/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(tt) / len(tt), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -217,7 +249,14 @@ def main():
         wall_value = time.perf_counter() - t0
     dev_time = reduce_max(sum(kernel_ms) * 1e-3)
     counters = eng.counters()
-    status_bad = int((eng.status() != 0).sum())
+    st = eng.status()
+    status_bad = int((st != 0).sum())
+    flagged_by_bit = {name: int(((st & bit) != 0).sum()) for bit, name in STATUS_BITS.items()}
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "kernel_ms": kernel_ms, "flagged": status_bad, "flagged_by_bit": flagged_by_bit})
+    else:
+        per_rank = [{"rank": 0, "kernel_ms": kernel_ms, "flagged": status_bad, "flagged_by_bit": flagged_by_bit}]
     value = world * S * args.steps / dev_time
     del dev_days
     torch.cuda.empty_cache()
@@ -227,9 +266,10 @@ def main():
     day = day_timed0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.step_days(day, host_days[day], out_host)
+    for _ in range(args.steps):           # mc_step_days_async: the H2D of step k+1 and the D2H of step k-1 overlap the kernel of step k
+        eng.step_days_async(day, host_days[day], out_host)
         day += 1
+    eng.wait()
     barrier()
     e2e_time = reduce_max(time.perf_counter() - t0)
     e2e = world * S * args.steps / e2e_time
@@ -239,21 +279,32 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    flop_sd = FLOP_PER_SITE_DAY
     per_gpu = value / world
+    timed_site_days = S * args.steps
+    w_alg, w_parts = walg_per_site_day(counters, timed_site_days)
+    cal = calibrated_traffic()
+    exe = cal["fp64_flop_per_site_day"] if cal and not cal["stale"] else None
     roof = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf, "peak_how": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-            "achieved": (flop_sd * per_gpu / 1e12) if flop_sd else None, "frac": (flop_sd * per_gpu / 1e12 / peak_tf) if flop_sd else None,
-            "flop_per_site_day": flop_sd, "flop_per_site_day_reference_algorithm": ALG_FLOP_PER_SITE_DAY,
-            "achieved_reference_algorithm": ALG_FLOP_PER_SITE_DAY * per_gpu / 1e12, "traffic": DRAM_BYTES_PER_SITE_DAY * S,
-            "traffic_how": "DRAM bytes per launch (one launch = one step of %d site-days per GPU) scaled from one ncu capture of the same kernel; not re-measured in this run" % S,
+            # algorithmic work of THIS run: device counters of the timed region x source-level operation-count weights of the oracle (profiles/walg_weights.json)
+            "w_alg": w_alg, "w_alg_parts": w_parts, "achieved": (w_alg * per_gpu / 1e12) if w_alg else None, "frac": (w_alg * per_gpu / 1e12 / peak_tf) if w_alg else None,
+            "frac_alg": (w_alg * per_gpu / 1e12 / peak_tf) if w_alg else None,
+            "achieved_how": "W_alg (flop-equivalents per site-day: + - * / sqrt = 1, fma = 2, exp/log = 20, pow = 40, atan/cos = 25) x site-days/s per GPU",
+            # second view: FP64 flops the kernel EXECUTES (DADD + DMUL + 2 DFMA thread instructions, ncu capture of this build)
+            "executed_flop_per_site_day": exe, "achieved_executed": (exe * per_gpu / 1e12) if exe else None, "frac_executed": (exe * per_gpu / 1e12 / peak_tf) if exe else None,
+            "traffic": (cal["dram_bytes_per_site_day"] * S) if cal and not cal["stale"] else None,
+            "traffic_build_hash": cal.get("library_hash") if cal else None, "library_hash": library_hash(),
+            "traffic_how": ("DRAM bytes per launch (one launch = one step of %d site-days per GPU) from the ncu capture of this build (profiles/traffic.json)" % S) if cal and not cal["stale"]
+                           else "no ncu capture of this build (profiles/traffic.json absent or taken on another build): null rather than a stale number",
             "hbm": {"achieved": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9, "peak": 6536.0, "unit": "GB/s", "frac": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9 / 6536.0,
-                    "alg_bytes_per_site_day": ALG_BYTES_PER_SITE_DAY, "dram_traffic_GBps": DRAM_BYTES_PER_SITE_DAY * per_gpu / 1e9},
-            "work_per_site_day": {k: counters[k] / max(1, counters["n_site_days"] - S * args.warmup) for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter")}}
+                    "alg_bytes_per_site_day": ALG_BYTES_PER_SITE_DAY,
+                    "dram_traffic_GBps": (cal["dram_bytes_per_site_day"] * per_gpu / 1e9) if cal and not cal["stale"] else None},
+            "work_per_site_day": {k: counters[k] / max(1, timed_site_days) for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps")}}
     line = {"metric": "site-days/sec (hourly soil T+moisture)", "value": value, "unit": "site-days/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_time / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk.summary(),
             "e2e": {"value": e2e, "unit": "site-days/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_time / args.steps},
-            "gpu_launches": args.steps, "roofline": roof, "flagged_sites": status_bad, "wall_value_s": wall_value, "setup_s": t_gen, "checksum": checksum}
+            "gpu_launches": args.steps, "roofline": roof, "flagged_sites": status_bad, "flagged_by_bit": flagged_by_bit,
+            "per_rank": per_rank, "e2e_pipelined": True, "wall_value_s": wall_value, "setup_s": t_gen, "checksum": checksum}
     if world == 1 and not args.no_cpu_baseline:
         n = args.cpu_sites or max(64, min(S, 768 * cores))
         times = cpu_run(desc, n, 0, n, 0, 2, threads=cores)

@@ -36,6 +36,11 @@
 #include <omp.h>
 #endif
 
+/* region tags for the operation-counting build (oracle/opcount/opcount.cpp); no-ops in the normal build */
+#ifndef MCO_REGION
+#define MCO_REGION(r) ((void)0)
+#endif
+
 namespace mco {
 
 static const int MAXN = MC_MAX_SOIL_NODES;
@@ -193,6 +198,7 @@ static ObukhovOut calc_obukhov(double T_ref, double T_surf, double v_ref, double
     ObukhovOut o; o.L = L0; o.Q = 0; o.Stb = 0; o.Sts = 0; o.psi_h = 0; o.ustar = 0; o.iters = 0;
     double rel = 1.0; int count = 0; const double tiny = 1.0e-6;
     while (rel > tol && count < max_iter) {
+        MCO_REGION(R_OBUKHOV);
         count++;
         const double x = calc_phi_m(z, gamma, o.L);
         const double psi_m = calc_psi_m(x);
@@ -563,6 +569,7 @@ struct RhsParams {
 /* soil_energy_balance, heat_transport_1d.jl:137-302.  u, du in K and K/min. */
 static void soil_energy_balance(const double* u, const RhsParams& p, double t, double* du, Counters& cn)
 {
+    MCO_REGION(R_RHS);
     cn.n_rhs++;
     const mc_model_desc& m = *p.m; const Site& s = *p.site; const int M = p.M; const int ns = p.n_snow; const int N = M - ns;
     const double sigma = m.fluid.stefan_boltzmann;
@@ -696,6 +703,7 @@ static inline double rms_norm(const double* x, int n) { double s = 0; for (int i
 /* ode_determine_initdt (out-of-place), OrdinaryDiffEqCore initdt.jl */
 static double determine_initdt(const Integrator& I, const RhsParams& p, Counters& cn)
 {
+    MCO_REGION(R_STEP);
     const int M = I.M; const double dtmax = 1440.0;
     double sk[MAXM], tmp[MAXM], f0[MAXM], f1[MAXM], u1[MAXM];
     for (int i = 0; i < M; i++) sk[i] = I.abstol + std::fabs(I.u[i]) * I.reltol;
@@ -731,6 +739,7 @@ static void reinit(Integrator& I, const double* u0, const RhsParams& p, Counters
 /* one accepted step: SciMLBase.step!(integrator) = loopheader!/perform_step!/loopfooter! until accepted */
 static void step(Integrator& I, const RhsParams& p, Counters& cn)
 {
+    MCO_REGION(R_STEP);
     using namespace tsit5;
     const int M = I.M;
     double k2[MAXM], k3[MAXM], k4[MAXM], k5[MAXM], k6[MAXM], tmp[MAXM], unew[MAXM];
@@ -871,6 +880,7 @@ struct InfilOut { double evaporation, transpiration, surface_water_flux; int new
 static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const Site& s, int N, const double* depths,
                                   double P, double* theta, double rh_loc, double lai, double ET, const double* Tin, Counters& cn)
 {
+    MCO_REGION(R_INFIL);
     cn.n_infil++;
     const double Mw = 0.01801528, Dv = 2.4e-5, R = m.fluid.gas_constant, g = m.fluid.standard_gravity;
     const double dt = m.moisture_timestep_s; const int max_it = m.moisture_max_iterations; const double tolr = m.moisture_tolerance;
@@ -934,6 +944,7 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
     const double RL = m.leaf_resistance, PC = m.stomatal_closure_potential, SP = m.stomatal_stability_parameter;
     int counter = 0;
     while (counter < max_it) {                                                              /* :270-284 */
+        MCO_REGION(R_STOMATAL);
         if (psi_leaf > psi_bar) psi_leaf = psi_bar - TP * (R_bar + RL);
         const double xp = mcm::pow(psi_leaf / PC, SP);
         const double slope = TP * (R_bar + RL) * SP * xp / (psi_leaf * (1.0 + xp) * (1.0 + xp)) - 1.0;
@@ -949,6 +960,7 @@ static InfilOut infiltration_step(InfilBuffers& B, const mc_model_desc& m, const
     InfilOut out; out.hit_max = true; out.newton_iters = 0;
     counter = 0;
     while (counter < max_it) {                                                              /* :293-336 */
+        MCO_REGION(R_NEWTON);
         double err = 0.0;
         counter++; cn.n_newton++;
         for (int i = 2; i <= L; i++) {
