@@ -342,6 +342,10 @@ int  mc_multi_wait(mc_multi* m);
  * MEASURED_PEAKS.json has no FP64 figure). */
 int  mc_measure_fp64_peak(mc_handle* h, double* tflops);
 
+/* development probe (not part of the drop-in): work census of the asynchronous kernel (claims / items / cycles per task type, idle polls), collected
+ * when the environment variable MC_ASYNC_STATS is set; returns the number of values written (32) and resets the census */
+int  mc_get_async_stats(mc_handle* h, unsigned long long* out, int n);
+
 /* development probe (not part of the drop-in): rate of the hottest device function over independent (site, node) items —
  * the headroom of a node-parallel formulation, see DESIGN.md */
 int  mc_bench_conductivity(mc_handle* h, int64_t n_items, int reps, double* evals_per_s);

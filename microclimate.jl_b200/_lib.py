@@ -25,7 +25,7 @@ EXPORTS = ("mc_abi_version", "mc_backend_name", "mc_default_fluid", "mc_default_
            "mc_step_days_async", "mc_wait",
            "mc_multi_create", "mc_multi_destroy", "mc_multi_last_error", "mc_multi_device_count", "mc_multi_handle", "mc_multi_range",
            "mc_multi_set_sites", "mc_multi_step_days", "mc_multi_step_days_async", "mc_multi_wait",
-           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity")
+           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity", "mc_get_async_stats")
 
 
 def _nvcc():
@@ -107,5 +107,6 @@ def lib():
     L.mc_get_status.argtypes = [H, C.POINTER(C.c_int32)]
     L.mc_measure_fp64_peak.argtypes = [H, C.POINTER(C.c_double)]
     L.mc_bench_conductivity.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_double)]
+    L.mc_get_async_stats.argtypes = [H, C.POINTER(C.c_ulonglong), C.c_int]
     _lib = L
     return L

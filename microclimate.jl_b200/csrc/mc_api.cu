@@ -122,10 +122,14 @@ __global__ void __launch_bounds__(MC_ASYNC_THREADS, 1) soil_async_kernel(const _
 {
     extern __shared__ __align__(16) unsigned char mc_async_smem[];
     mcd::AsyncBlock<NA, SLOTS>& B = *reinterpret_cast<mcd::AsyncBlock<NA, SLOTS>*>(mc_async_smem);
-    mcd::async_block_init<NA, SLOTS>(B, (int)threadIdx.x, (int)blockDim.x, a.async_slots);
+    mcd::async_block_init<NA, SLOTS>(B, (int)threadIdx.x, (int)blockDim.x, a.async_slots, a.async_ser_min);
     __syncthreads();
     double* ga = a.async_scr + (size_t)blockIdx.x * ((size_t)mcd::G_ARRAYS * NA * SLOTS);
     mcd::async_worker<NA, SLOTS>(B, a, ga, (int)(threadIdx.x >> 5));
+    if (a.async_stats) {                                     /* work census: the block's tallies into the launch's */
+        __syncthreads();
+        for (int k = (int)threadIdx.x; k < mcd::MCA_STATS; k += (int)blockDim.x) if (B.stats[k]) atomicAdd(a.async_stats + k, B.stats[k]);
+    }
 }
 
 /* solve_air! for the rows of the chunk the soil kernel just wrote (reference src/simulation.jl:822-851) */
@@ -338,6 +342,8 @@ static int launch_chunk_async(mc_handle* h, mcd::KArgs& a, cudaStream_t st, int 
         h->async_scr_doubles = need;
     }
     a.async_scr = h->async_scr; a.async_slots = slots;
+    { const char* e = getenv("MC_ASYNC_SERMIN"); a.async_ser_min = e ? atoi(e) : 0; }                                  /* tuning knob */
+    a.async_stats = getenv("MC_ASYNC_STATS") ? h->counters + 16 : nullptr;                                             /* work census (development) */
     a.next_site = h->counters + 8 + slice;
     MC_CUDA(h, cudaMemsetAsync(a.next_site, 0, sizeof(unsigned long long), st));
     soil_async_kernel<NA, SLOTS><<<grid, threads, smem, st>>>(a);
@@ -440,8 +446,8 @@ int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle
     if (NSn) { h->snow_T = take(NSn * S); h->snow_nd = take(NSn * S); h->snow_state = take(MC_SNOW_STATE_FIELDS * S); h->q_freeze = take(S); }
     h->pool = take(S); h->wetness = take(S); h->L_ode = take(S); h->L_prof = take(S); h->tdeep_prev = take(S); h->L_air = take(S);
     if ((e = cudaMalloc(&h->flags, S * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc(flags)", e);
-    if ((e = cudaMalloc(&h->counters, 16 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
-    if ((e = cudaMemset(h->counters, 0, 16 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
+    if ((e = cudaMalloc(&h->counters, (16 + mcd::MCA_STATS) * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+    if ((e = cudaMemset(h->counters, 0, (16 + mcd::MCA_STATS) * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
     *out = h;
     return 0;
 }
@@ -787,6 +793,17 @@ int mc_get_counters(mc_handle* h, mc_counters* c)
     c->n_site_days = (uint64_t)(h->days_done * h->S);
     c->gpu_ms = h->last_ms; c->n_kernel_launches = h->last_launches;
     return 0;
+}
+
+/* development probe: the asynchronous kernel's work census since the last call (MC_ASYNC_STATS=1), see mcd::MCA_STATS */
+int mc_get_async_stats(mc_handle* h, unsigned long long* out, int n)
+{
+    if (!h || !out || n < mcd::MCA_STATS) return -1;
+    MC_CUDA(h, cudaSetDevice(h->device));
+    MC_CUDA(h, cudaMemcpyAsync(out, h->counters + 16, mcd::MCA_STATS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    MC_CUDA(h, cudaMemsetAsync(h->counters + 16, 0, mcd::MCA_STATS * sizeof(unsigned long long), h->stream));
+    MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return mcd::MCA_STATS;
 }
 
 int mc_reset_counters(mc_handle* h)

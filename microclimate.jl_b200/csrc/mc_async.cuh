@@ -75,6 +75,17 @@ enum { T0_COND = 0, T0_P2, T0_HOIST, T0_MU, T0_MF, T0_TYPES };
 enum { T1_SURF = 0, T1_CTRL, T1_THOMAS, T1_SUB, T1_SITE, T1_TYPES };
 enum { PC_LOAD = 0, PC_INIT_A, PC_INIT_B, PC_DAY_START, PC_PASS_START, PC_HOUR_START, PC_ODE_BEGIN, PC_HOUR_POST, PC_HOUR_END, PC_STORE, PC_DEAD };
 
+/* work census of a launch (optional): per task type {claims, items, clock cycles spent executing}, then {idle polls, idle cycles} */
+constexpr int MCA_STAT_TYPES = T0_TYPES + T1_TYPES;
+constexpr int MCA_STATS = 3 * MCA_STAT_TYPES + 2;
+#if defined(__CUDACC__)
+MC_DEV long long mca_clock() { return clock64(); }
+MC_DEV void mca_stat_add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+#else
+MC_DEV long long mca_clock() { return 0; }
+MC_DEV void mca_stat_add(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+#endif
+
 struct SlotState {
     /* Tsit5 controller (Own2) */
     double t, dt, dtpropose, qold, q11, tstop, target, w0, w1, w2, st_t, st_dt, req_t;
@@ -114,6 +125,8 @@ struct AsyncBlock {
     int req0[SLOTS];                                                       /* channel-0 request of a slot: type << 16 | items claimed so far */
     int pend[SLOTS];                                                       /* items of the slot's current pass not yet retired */
     int alive;                                                             /* slots that may still receive a site */
+    int ser_min;
+    unsigned long long stats[MCA_STATS];
     MC_MEMBER SlotState& z(int o) { return *reinterpret_cast<SlotState*>(zraw + (size_t)ZD * o); }
 };
 
@@ -217,8 +230,8 @@ MC_DEV void async_item_cond(AsyncBlock<NA, SLOTS>& B, const double* ga, int o, i
         if (stage == ST_7 && Tc != x) mca_add(&Z.clampflag, 1);
         MCA_SA(A_T, n) = Tc;
         if (n < m.N - 1)
-            MCA_SA(A_LAM, n) = soil_conductivity(Tc, Z.P, Z.p0p, Z.pp0, MCA_SA(A_TH, n), MC_LDG(&MCA_GA(G_PM, n)), MCA_SA(A_PG, n), MCA_SA(A_FW, n),
-                                                 MC_LDG(&MCA_GA(G_LM, n))) / m.dzg[n];
+            MCA_SA(A_LAM, n) = soil_conductivity(Tc, Z.P, Z.p0p, Z.pp0, MCA_SA(A_TH, n), (MCA_GA(G_PM, n)), MCA_SA(A_PG, n), MCA_SA(A_FW, n),
+                                                 (MCA_GA(G_LM, n))) / m.dzg[n];
     }
 }
 
@@ -258,9 +271,9 @@ MC_DEV void async_item_hoist(AsyncBlock<NA, SLOTS>& B, const double* ga, int o, 
     constexpr int SP = AsyncBlock<NA, SLOTS>::SP;
     const DevModel& m = MC_CONST_MODEL;
     double* sa = B.arr;
-    const double th = MCA_SA(A_TH, i), pm = MC_LDG(&MCA_GA(G_PM, i));
-    const double cp = MC_LDG(&MCA_GA(G_CPM, i)) + th * WATER_CP;
-    const double rho = th * WATER_RHO + MC_LDG(&MCA_GA(G_BD, i));
+    const double th = MCA_SA(A_TH, i), pm = (MCA_GA(G_PM, i));
+    const double cp = (MCA_GA(G_CPM, i)) + th * WATER_CP;
+    const double rho = th * WATER_RHO + (MCA_GA(G_BD, i));
     MCA_SA(A_CAP, i) = (rho * cp) * m.dzc[i] / 2.0;
     MCA_SA(A_PG, i) = jmax(0.0, 1.0 - th - pm);
     MCA_SA(A_FW, i) = 1.0 / (1.0 + mcm::pow(th / m.theta0, -m.recirc_pow));
@@ -274,7 +287,7 @@ MC_DEV void async_item_mu(AsyncBlock<NA, SLOTS>& B, const double* ga, int o, int
     const DevModel& m = MC_CONST_MODEL;
     double* sa = B.arr; const SlotState& Z = B.z(o);
     const int fl = Z.mflags, n = r + 1;                                     /* parameters of soil node i - 1 = r + 1 */
-    const double psi_e = MC_LDG(&MCA_GA(G_PSIE, n)), sat = MC_LDG(&MCA_GA(G_SAT, n)), bb = MC_LDG(&MCA_GA(G_BB, n));
+    const double psi_e = (MCA_GA(G_PSIE, n)), sat = (MCA_GA(G_SAT, n)), bb = (MCA_GA(G_BB, n));
     if (fl & MF_S0) {                                                       /* first pass of the hour: the hour's temperature-dependent constants of this row */
         const int U = Z.uarr();
         MCA_SA(W_KVC, r) = 0.66 * DV_INFIL * vapour_density_sat(MCA_SA(U, r + 1));      /* B.Ts[i] = T0[i-1] */
@@ -286,11 +299,11 @@ MC_DEV void async_item_mu(AsyncBlock<NA, SLOTS>& B, const double* ga, int o, int
     const double psi = psi_e * mcm::pow(sat / wcn, bb);
     MCA_SA(W_WCN, r) = wcn; MCA_SA(W_PSI, r) = psi;
     MCA_SA(W_H, r) = mcm::exp(MW_INFIL * psi / MCA_SA(W_RTS, r));
-    const double K = MC_LDG(&MCA_GA(G_KS, n)) * mcm::pow(psi_e / psi, MC_LDG(&MCA_GA(G_NEXP, n)));
+    const double K = (MCA_GA(G_KS, n)) * mcm::pow(psi_e / psi, (MCA_GA(G_NEXP, n)));
     MCA_SA(W_K, r) = K;
     if (fl & MF_FINAL) MCA_SA(A_TH, r) = wcn;
     if (fl & (MF_FINAL | MF_S0)) {          /* this state starts the next sub-step: root + soil resistance terms of its stomatal balance (campbell.jl:253-267) */
-        const double rt = MC_LDG(&MCA_GA(G_ROOTZ, n)) / K + MC_LDG(&MCA_GA(G_ROOTR, n));
+        const double rt = (MCA_GA(G_ROOTZ, n)) / K + (MCA_GA(G_ROOTR, n));
         MCA_SA(W_SUP, r) = rt; MCA_SA(W_SUB, r) = psi / rt; MCA_SA(W_DIA, r) = 1.0 / rt;       /* RT, Q1, Q2 live in rows the first MF pass overwrites */
     }
 }
@@ -306,7 +319,7 @@ MC_DEV void async_item_mf(AsyncBlock<NA, SLOTS>& B, const double* ga, int o, int
     const double g = m.g, dt = m.moist_dt;
     const bool first = (Z.mflags & MF_FIRST) != 0;
     const double psic = MCA_SA(W_PSI, r), Kc = MCA_SA(W_K, r), wcnc = MCA_SA(W_WCN, r), hc = MCA_SA(W_H, r);
-    const double nexp = MC_LDG(&MCA_GA(G_NEXP, n)), sat = MC_LDG(&MCA_GA(G_SAT, n));
+    const double nexp = (MCA_GA(G_NEXP, n)), sat = (MCA_GA(G_SAT, n));
     double psim, Km, jvm, djvm;
     if (i == 2) {
         const double EP = Z.EP, rh_loc = Z.rh_loc;
@@ -316,17 +329,17 @@ MC_DEV void async_item_mf(AsyncBlock<NA, SLOTS>& B, const double* ga, int o, int
     } else {
         psim = MCA_SA(W_PSI, r - 1); Km = MCA_SA(W_K, r - 1);
         const double wcnm = MCA_SA(W_WCN, r - 1), hm1 = MCA_SA(W_H, r - 1);
-        const double kvm = MCA_SA(W_KVC, r - 1) * (MC_LDG(&MCA_GA(G_SAT, n - 1)) - (wcnm + wcnc) / 2.0) / m.mdz[i - 1];
+        const double kvm = MCA_SA(W_KVC, r - 1) * ((MCA_GA(G_SAT, n - 1)) - (wcnm + wcnc) / 2.0) / m.mdz[i - 1];
         jvm = kvm * (hc - hm1);
         djvm = MW_INFIL * hm1 * kvm / MCA_SA(W_RTS, r - 1);
     }
     double psip, Kp, wcnp, hp;
     if (i + 1 <= L) { psip = MCA_SA(W_PSI, r + 1); Kp = MCA_SA(W_K, r + 1); wcnp = MCA_SA(W_WCN, r + 1); hp = MCA_SA(W_H, r + 1); }
-    else { psip = MC_LDG(&MCA_GA(G_PSIE, n)); Kp = MC_LDG(&MCA_GA(G_KS, n)); wcnp = sat; hp = first ? 1.0 : hc; }     /* row L+1: psi_e[L], ks[L], sat[L], h = 1 then h[L] */
+    else { psip = (MCA_GA(G_PSIE, n)); Kp = (MCA_GA(G_KS, n)); wcnp = sat; hp = first ? 1.0 : hc; }     /* row L+1: psi_e[L], ks[L], sat[L], h = 1 then h[L] */
     const double kv = MCA_SA(W_KVC, r) * (sat - (wcnc + wcnp) / 2.0) / m.mdz[i];
     const double jvi = kv * (hp - hc);
     const double djvi = MW_INFIL * hc * kv / MCA_SA(W_RTS, r);
-    const double cap = -1.0 * m.mmass[i] * wcnc / (MC_LDG(&MCA_GA(G_BB, n)) * psic * dt);
+    const double cap = -1.0 * m.mmass[i] * wcnc / ((MCA_GA(G_BB, n)) * psic * dt);
     const double sub = -1.0 * Km / m.mdz[i - 1] + g * nexp * Km / psim;
     const double sup = -1.0 * Kp / m.mdz[i];
     const double dia = Kc / m.mdz[i - 1] + Kc / m.mdz[i] + cap - g * nexp * Kc / psic + djvm + djvi;
@@ -550,7 +563,7 @@ MC_DEV_NOINLINE void async_task_thomas(AsyncBlock<NA, SLOTS>& B, const double* g
     double* sa = B.arr; SlotState& W = B.z(o);
     W.counter++; W.cn[4]++;
     W.K2 = MCA_SA(W_K, 0);
-    W.K3 = 3 <= L ? MCA_SA(W_K, 1) : MC_LDG(&MCA_GA(G_KS, L - 1));
+    W.K3 = 3 <= L ? MCA_SA(W_K, 1) : (MCA_GA(G_KS, L - 1));
     double err = 0.0, ccm = 0.0, rrm = 0.0, diaL = 0.0, FL = 0.0;
     MC_ROLLED for (int i = 2; i <= L; i++) {
         const int r = i - 2;
@@ -570,7 +583,7 @@ MC_DEV_NOINLINE void async_task_thomas(AsyncBlock<NA, SLOTS>& B, const double* g
     MC_ROLLED for (int i = L; i >= 2; i--) {
         const int r = i - 2;
         double psi = MCA_SA(W_PSI, r);
-        const double psi_e = MC_LDG(&MCA_GA(G_PSIE, r + 1));
+        const double psi_e = (MCA_GA(G_PSIE, r + 1));
         if (i == L) psi = jmin(psi - dpsi, psi_e);
         else {
             dpsi = MCA_SA(W_F, r) - MCA_SA(W_SUP, r) * dpsi;
@@ -594,8 +607,8 @@ MC_DEV_NOINLINE void async_task_sub(AsyncBlock<NA, SLOTS>& B, const double* ga, 
     const DevModel& m = MC_CONST_MODEL; const int L = m.N;
     double* sa = B.arr; SlotState& W = B.z(o);
     if (W.counter > 0) {                                              /* infiltration_step!'s outputs + pool */
-        const double psi2 = MCA_SA(W_PSI, 0), psi3 = 3 <= L ? MCA_SA(W_PSI, 1) : MC_LDG(&MCA_GA(G_PSIE, L - 1));
-        W.surface_water_flux = ((psi2 * W.K2 - psi3 * W.K3) / ((1.0 - MC_LDG(&MCA_GA(G_NEXP, 1))) * m.mdz[2]) + m.g * W.K2 + W.TR) * m.moist_dt;
+        const double psi2 = MCA_SA(W_PSI, 0), psi3 = 3 <= L ? MCA_SA(W_PSI, 1) : (MCA_GA(G_PSIE, L - 1));
+        W.surface_water_flux = ((psi2 * W.K2 - psi3 * W.K3) / ((1.0 - (MCA_GA(G_NEXP, 1))) * m.mdz[2]) + m.g * W.K2 + W.TR) * m.moist_dt;
         W.evaporation = W.EP * (MCA_SA(W_H, 0) - W.rh_loc) / (1.0 - W.rh_loc) * m.moist_dt;
         W.pool = jclamp(W.pool - jmax(0.0, W.surface_water_flux) - jmax(0.0, W.evaporation), 0.0, m.max_pool);
         if (W.pool > 0.0) {                                           /* wet_surface_node on theta[0] = row 2 */
@@ -604,13 +617,13 @@ MC_DEV_NOINLINE void async_task_sub(AsyncBlock<NA, SLOTS>& B, const double* ga, 
             W.pool = wet_surface_node(&th0, W.pool, W.sat0, W.half);
             if (th0 != before) MCA_SA(A_TH, 0) = th0;
             if (th0 != before && W.k + 1 < m.niter_moist) {           /* the next sub-step's start recomputes the state of row 2 from the wetted water content */
-                const double psi_e = MC_LDG(&MCA_GA(G_PSIE, 1));
-                const double psi = psi_e * mcm::pow(MC_LDG(&MCA_GA(G_SAT, 1)) / th0, MC_LDG(&MCA_GA(G_BB, 1)));
+                const double psi_e = (MCA_GA(G_PSIE, 1));
+                const double psi = psi_e * mcm::pow((MCA_GA(G_SAT, 1)) / th0, (MCA_GA(G_BB, 1)));
                 MCA_SA(W_WCN, 0) = th0; MCA_SA(W_PSI, 0) = psi;
                 MCA_SA(W_H, 0) = mcm::exp(MW_INFIL * psi / MCA_SA(W_RTS, 0));
-                const double K = MC_LDG(&MCA_GA(G_KS, 1)) * mcm::pow(psi_e / psi, MC_LDG(&MCA_GA(G_NEXP, 1)));
+                const double K = (MCA_GA(G_KS, 1)) * mcm::pow(psi_e / psi, (MCA_GA(G_NEXP, 1)));
                 MCA_SA(W_K, 0) = K;
-                const double rt = MC_LDG(&MCA_GA(G_ROOTZ, 1)) / K + MC_LDG(&MCA_GA(G_ROOTR, 1));
+                const double rt = (MCA_GA(G_ROOTZ, 1)) / K + (MCA_GA(G_ROOTR, 1));
                 MCA_SA(W_SUP, 0) = rt; MCA_SA(W_SUB, 0) = psi / rt; MCA_SA(W_DIA, 0) = 1.0 / rt;
             }
         }
@@ -917,7 +930,7 @@ MC_DEV_NOINLINE void async_task_site(AsyncBlock<NA, SLOTS>& B, const KArgs& a, d
                     const double Tsc = T_surf < T_LO ? T_LO : T_surf;
                     const double Qe = (hd * (vapour_density_sat(Tsc) - wa.vapour_density)) * latent_heat(Tsc);      /* saturated=true */
                     const double EPot = jmax(1e-7, Qe / latent_heat(T_surf));
-                    Z.sat0 = MC_LDG(&MCA_GA(G_SAT, 0));
+                    Z.sat0 = (MCA_GA(G_SAT, 0));
                     Z.half = (m.depths[1] - m.depths[0]) / 2.0;
                     {   double th0 = MCA_SA(A_TH, 0); const double before = th0;
                         Z.pool = wet_surface_node(&th0, Z.pool, Z.sat0, Z.half);
@@ -939,7 +952,7 @@ MC_DEV_NOINLINE void async_task_site(AsyncBlock<NA, SLOTS>& B, const KArgs& a, d
             const int jl = Z.jl, i = Z.hr, step = jl * 24 + i;
             const int U = Z.uarr();
             if (Z.have_infil) {
-                if (m.niter_moist > 0) MCA_SA(A_TH, N - 1) = MC_LDG(&MCA_GA(G_SAT, N - 1));      /* water_content[L+1] = saturation of the last row */
+                if (m.niter_moist > 0) MCA_SA(A_TH, N - 1) = (MCA_GA(G_SAT, N - 1));      /* water_content[L+1] = saturation of the last row */
                 Z.wet_dyn = jclamp(jmax(0.0, Z.evaporation) / (Z.EPot * m.moist_dt), 0.0, 1.0);
             }
             const int out_row = step + 1;
@@ -949,7 +962,7 @@ MC_DEV_NOINLINE void async_task_site(AsyncBlock<NA, SLOTS>& B, const KArgs& a, d
                 r.put_scalar(a.o_sky, out_row, Z.sky_T);
                 if (Z.have_infil && (a.o_psi || a.o_h)) {
                     MC_ROLLED for (int k = 0; k < N - 1; k++) { r.put_node(a.o_psi, out_row, k, MCA_SA(W_PSI, k)); r.put_node(a.o_h, out_row, k, MCA_SA(W_H, k)); }
-                    r.put_node(a.o_psi, out_row, N - 1, MC_LDG(&MCA_GA(G_PSIE, N - 1))); r.put_node(a.o_h, out_row, N - 1, MCA_SA(W_H, N - 2));      /* row L+1: psi_e[L], h[L+1] = h[L] */
+                    r.put_node(a.o_psi, out_row, N - 1, (MCA_GA(G_PSIE, N - 1))); r.put_node(a.o_h, out_row, N - 1, MCA_SA(W_H, N - 2));      /* row L+1: psi_e[L], h[L+1] = h[L] */
                 }
                 put_props(out_row, U, r.hourly(a.f_P, out_row));
             }
@@ -1006,7 +1019,7 @@ MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt)
         if (cnt > n1) { n1 = cnt; best1 = t; }
     }
     if (best0 < 0 && best1 < 0) return c;
-    const bool take0 = best0 >= 0 && (n0 >= MCA_LANES || best1 < 0 || n1 < MCA_LANES / 4);
+    const bool take0 = best0 >= 0 && (n0 >= MCA_LANES || best1 < 0 || n1 < B.ser_min);
     if (take0) {
         const int t = best0, n = async_items(t, N);
         int got = 0;
@@ -1073,6 +1086,12 @@ MC_DEV int mca_nth_bit(unsigned lo, unsigned hi, int n)
 }
 #endif
 
+#if defined(__CUDACC__)
+#define MCA_IS_LEADER ((threadIdx.x & 31) == 0)
+#else
+#define MCA_IS_LEADER true
+#endif
+
 /* body of one worker warp; on the host (tests/hostemu) a "warp" is an OS thread that runs its MCA_LANES lanes one after the other */
 template <int NA, int SLOTS>
 MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, int warp)
@@ -1094,9 +1113,12 @@ MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, i
         salt++;
         if (c.chan < 0) {
             if (mca_ld(&B.alive) <= 0) return;
+            const long long ti = mca_clock();
             mca_idle();
+            if (a.async_stats && MCA_IS_LEADER) { mca_stat_add(&B.stats[3 * MCA_STAT_TYPES], 1ull); mca_stat_add(&B.stats[3 * MCA_STAT_TYPES + 1], (unsigned long long)(mca_clock() - ti)); }
             continue;
         }
+        const long long t_begin = mca_clock();
         if (c.chan == 0) {
 #if defined(__CUDACC__)
             {
@@ -1148,12 +1170,16 @@ MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, i
                 }
             }
         }
+        if (a.async_stats && MCA_IS_LEADER) {
+            unsigned long long* st = &B.stats[3 * (c.chan == 0 ? c.type : T0_TYPES + c.type)];
+            mca_stat_add(st, 1ull); mca_stat_add(st + 1, (unsigned long long)c.total); mca_stat_add(st + 2, (unsigned long long)(mca_clock() - t_begin));
+        }
     }
 }
 
 /* block set-up: every slot starts by asking for a site */
 template <int NA, int SLOTS>
-MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, int active_slots)
+MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, int active_slots, int ser_min = 0)
 {
     const int n = active_slots <= 0 || active_slots > SLOTS ? SLOTS : active_slots;
     for (int o = tid; o < SLOTS; o += nthreads) { B.z(o).pc = o < n ? PC_LOAD : PC_DEAD; B.req0[o] = 0; B.pend[o] = 0; }
@@ -1163,5 +1189,7 @@ MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, in
         B.mask1[T1_SITE][0] = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
         B.mask1[T1_SITE][1] = n > 32 ? (n >= 64 ? 0xffffffffu : ((1u << (n - 32)) - 1u)) : 0u;
         B.alive = n;
+        B.ser_min = ser_min > 0 ? ser_min : MCA_LANES / 4;
+        for (int k = 0; k < MCA_STATS; k++) B.stats[k] = 0;
     }
 }

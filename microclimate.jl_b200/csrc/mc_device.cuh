@@ -164,6 +164,8 @@ struct KArgs {
     double* async_scr;              /* asynchronous kernel: per-block L2-resident scratch [block][G_ARRAYS][NA][SLOTS] (site constants, hourly / daily copies) */
     unsigned long long* next_site;  /* asynchronous kernel: the launch's site cursor (slots take their next site from it) */
     int32_t async_slots;            /* asynchronous kernel: slots a block activates (fewer than its capacity when the range is small, so that every SM gets sites) */
+    int32_t async_ser_min;          /* asynchronous kernel: single-lane tasks of one type that must be waiting before a warp prefers them to node items */
+    unsigned long long* async_stats;/* asynchronous kernel: [MCA_STATS] work census (claims, items, cycles per task type; idle polls), or NULL */
 };
 
 struct Counters { unsigned int n_rhs, n_accept, n_reject, n_obukhov, n_newton, n_infil, n_day_passes; };
