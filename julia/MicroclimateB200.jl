@@ -3,14 +3,16 @@
 # site-fastest SoA and `ccall`s libmicroclimate_b200.so.
 #
 # NOT RUN in the build container (no Julia there); it is the binding INTEGRATION.md describes.  The Python mirror
-# (microclimate.jl_b200/marshal.py + simulation.py) performs the same marshalling and is what the tests drive.
+# (microclimate.jl_b200/marshal.py + simulation.py) performs the same marshalling and is what the tests drive.  The struct
+# mirrors below are checked field by field against the C header by tests/test_julia_binding.py, so they cannot rot unnoticed.
 module MicroclimateB200
 
 using Microclimate
 using Unitful
 import Microclimate: MicroModel, MicroInputs, MicroProblem, MicroCache, NoSnow, SnowModel,
     NonConsecutiveDayMode, ConsecutiveDayMode, FixedSoilTemperatureIterations, SoilTemperatureConvergenceTolerance,
-    DailyRainfall, HourlyRainfall, PrescribedSoilMoisture, DynamicSoilMoisture, MatricFluxPotentialAlgorithm
+    DailyRainfall, HourlyRainfall, PrescribedSoilMoisture, DynamicSoilMoisture, MatricFluxPotentialAlgorithm,
+    SwinbankAtmosphericRadiation, BonacinaStep, TanhSmoothed, Gaussian, WestermannSigmoid
 
 const LIB = get(ENV, "MICROCLIMATE_B200_LIB", joinpath(@__DIR__, "..", "microclimate.jl_b200", "csrc", "libmicroclimate_b200.so"))
 const MC_MAX_SOIL_NODES = 24
@@ -60,16 +62,46 @@ struct McForcing; hourly::NTuple{11,Ptr{Cdouble}}; daily::NTuple{8,Ptr{Cdouble}}
 struct McOutput;  node::NTuple{7,Ptr{Cdouble}}; scalar::NTuple{5,Ptr{Cdouble}}; snow_T::Ptr{Cdouble}
                   profile::NTuple{3,Ptr{Cdouble}}; profile_scalar::NTuple{2,Ptr{Cdouble}}; status::Ptr{Cint}; end   # profile = solve_air! outputs (NULL = skip)
 
-check(h, rc, what) = rc < 0 ? error("$what failed (rc=$rc): " * unsafe_string(ccall((:mc_last_error, LIB), Cstring, (Ptr{Cvoid},), h))) : rc
+const NULLD = Ptr{Cdouble}(C_NULL)
+last_error(h) = unsafe_string(ccall((:mc_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+multi_error(h) = unsafe_string(ccall((:mc_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+check(h, rc, what; err=last_error) = rc < 0 ? error("$what failed (rc=$rc): " * err(h)) : rc
 
 si(x, u) = Float64(ustrip(u, x))
+degC(x) = Float64(ustrip(u"°C", x))
+
+"SnowModel + the inputs' initial snowpack -> mc_snow_desc (src/snow/snow_model.jl:3-54, src/types.jl:146-157)."
+function snow_desc(sn::SnowModel, inputs0::MicroInputs)
+    length(sn.snow_node_thresholds) == MC_SNOW_NODES || error("SnowModel must have $MC_SNOW_NODES snow nodes")
+    a = sn.apparent_heat_capacity
+    # defaults of the closures that are not selected (the kernel reads only the fields of ahc_kind)
+    kind, Tlo, Thi, win, smo, Tm, wid = 0, -0.45, 0.4, 1.0, 0.1, 0.0, 0.2
+    if a isa BonacinaStep
+        kind, Tlo, Thi, win = 0, degC(a.T_low), degC(a.T_high), si(a.window, u"K")
+    elseif a isa TanhSmoothed
+        kind, Tlo, Thi, win, smo = 1, degC(a.T_low), degC(a.T_high), si(a.window, u"K"), si(a.smoothing, u"K")
+    elseif a isa Gaussian
+        kind, Tm, wid = 2, degC(a.T_melt), si(a.width, u"K")
+    elseif a isa WestermannSigmoid
+        kind, Tm, wid = 3, degC(a.T_melt), si(a.width, u"K")
+    else
+        error("unsupported apparent heat capacity closure $(typeof(a))")
+    end
+    McSnow(degC(sn.snow_temperature_threshold), si(sn.snow_density, u"g/cm^3"), sn.snow_melt_factor, sn.undercatch,
+        sn.rain_multiplier, sn.rain_melt_factor, NTuple{4,Cdouble}(sn.density_function), si(sn.snow_conductivity, u"W/m/K"),
+        sn.canopy_interception, si(sn.min_snow_depth, u"cm"), ntuple(i -> si(sn.snow_node_thresholds[i], u"cm"), MC_SNOW_NODES),
+        degC(sn.melt_threshold), kind, Tlo, Thi, win, smo, Tm, wid,
+        si(inputs0.initial_snow_depth, u"cm"), si(u"K"(inputs0.initial_snow_temperature), u"K"),
+        isnothing(inputs0.initial_snow_density) ? -1.0 : si(inputs0.initial_snow_density, u"g/cm^3"))
+end
 
 "Flatten MicroModel + MicroConfig + time mode into mc_model_desc (reference src/types.jl:71-120)."
-function model_desc(model::MicroModel, time_mode)
+function model_desc(model::MicroModel, time_mode, inputs0::MicroInputs)
     d = Ref{McModel}()
     ccall((:mc_default_model, LIB), Cvoid, (Ref{McModel},), d)
     m = d[]
     N = length(model.depths)
+    N <= MC_MAX_SOIL_NODES || error("at most $MC_MAX_SOIL_NODES soil nodes")
     depths = ntuple(i -> i <= N ? si(model.depths[i], u"m") : 0.0, MC_MAX_SOIL_NODES)
     sem, sp, sh, cfg = model.soil_energy_model, model.soil_properties_model, model.soil_hydraulic_model, model.config
     tm, ipd, spin = time_mode isa NonConsecutiveDayMode ? (0, time_mode.iterations_per_day, 0) : (1, 1, Int(time_mode.spinup_first_day))
@@ -77,7 +109,9 @@ function model_desc(model::MicroModel, time_mode)
     ck, ci, ct = cv isa FixedSoilTemperatureIterations ? (0, cv.iterations_per_day, 0.0) : (1, cv.max_iterations_per_day, si(cv.tolerance, u"K"))
     sm = cfg.soil_moisture_strategy
     dyn = sm isa DynamicSoilMoisture
-    McModel(N, model.snow_model isa NoSnow ? 0 : MC_SNOW_NODES, depths,
+    has_snow = model.snow_model isa SnowModel
+    swinbank = model.radiation.longwave_model.atmospheric_radiation_model isa SwinbankAtmosphericRadiation
+    McModel(N, has_snow ? MC_SNOW_NODES : 0, depths,
         si(last(model.heights), u"m"), si(first(model.heights), u"m"),
         length(model.heights), 0, ntuple(i -> i <= length(model.heights) ? si(model.heights[i], u"m") : 0.0, MC_MAX_HEIGHTS),
         ustrip(sem.ode_kwargs.reltol), si(sem.ode_kwargs.abstol, u"K"), si(u"K"(sem.maximum_surface_temperature), u"K"),
@@ -89,27 +123,50 @@ function model_desc(model::MicroModel, time_mode)
         tm, ipd, spin, ck, ci, ct,
         cfg.rainfall_schedule isa HourlyRainfall ? 1 : 0, dyn ? 1 : 0,
         dyn ? si(sm.moisture_tolerance, u"kg/m^2/s") : 1e-6, dyn ? sm.moisture_max_iterations : 500, dyn ? si(sm.moisture_timestep, u"s") : 360.0,
-        si(cfg.max_surface_pool, u"kg/m^2"), 0, 0, m.fluid, m.snow)
+        si(cfg.max_surface_pool, u"kg/m^2"), swinbank ? 1 : 0, 0, m.fluid,
+        has_snow ? snow_desc(model.snow_model, inputs0) : m.snow)
 end
 
 """
-    solve_soil_batched!(caches::Vector{<:MicroCache}; device=0, chunk_days=nothing)
+    solve_soil_batched!(caches::Vector{<:MicroCache}; device=0, devices=nothing, chunk_days=nothing)
 
 Batched replacement of `Microclimate.solve_soil!(cache)` (src/simulation.jl:355-819): all caches share one `MicroModel`
 (the reference's own many-sites idiom, src/types.jl:143-144) and have had `solve_solar!` + `populate_weather!` run, so
 `cache.output` holds the hourly weather the path reads (src/simulation.jl:1006-1021,1051-1070).  Fills
 `cache.output.{soil_temperature, soil_moisture, soil_water_potential, soil_humidity, soil_thermal_conductivity,
-soil_heat_capacity, soil_bulk_density, surface_water, sky_temperature}` of every cache, so `solve_air!` runs unchanged.
+soil_heat_capacity, soil_bulk_density, surface_water, sky_temperature}` (and the snow fields with a `SnowModel`) of every cache,
+so `solve_air!` runs unchanged.
+
+`devices = [0, 1, ...]` shards the sites over several GPUs from this one process (`mc_multi_*`); `chunk_days` streams time in
+chunks through the asynchronous entry (`mc_step_days_async` / `mc_wait`): the H2D of chunk q+1 and the D2H of chunk q-1 overlap
+the kernel of chunk q, and the carried state stays on the device between chunks (identical results to one chunk).
+The initial snowpack (`initial_snow_*`) is model-level in the ABI: it must be the same for every cache of a batch.
 """
-function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integer=0, chunk_days=nothing)
+function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integer=0, devices=nothing, chunk_days=nothing)
     mp = first(caches).problem
     model, S, N, D = mp.model, length(caches), length(mp.model.depths), length(mp.days)
     H = 24D
-    desc = Ref(model_desc(model, mp.time_mode))
+    inp(c) = c.problem.inputs
+    i0 = inp(first(caches))
+    has_snow = model.snow_model isa SnowModel
+    if has_snow
+        all(c -> inp(c).initial_snow_depth == i0.initial_snow_depth && inp(c).initial_snow_temperature == i0.initial_snow_temperature &&
+                 inp(c).initial_snow_density == i0.initial_snow_density, caches) || error("initial_snow_* must be identical for all sites of a batch")
+    end
+    desc = Ref(model_desc(model, mp.time_mode, i0))
+    multi = !isnothing(devices)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(C_NULL, ccall((:mc_create, LIB), Cint, (Ref{McModel}, Int64, Cint, Ref{Ptr{Cvoid}}), desc, S, device, h), "mc_create")
+    if multi
+        devs = Cint.(collect(devices))
+        check(C_NULL, ccall((:mc_multi_create, LIB), Cint, (Ref{McModel}, Int64, Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}), desc, S, devs, length(devs), h), "mc_multi_create"; err=multi_error)
+    else
+        check(C_NULL, ccall((:mc_create, LIB), Cint, (Ref{McModel}, Int64, Cint, Ref{Ptr{Cvoid}}), desc, S, device, h), "mc_create")
+    end
+    err = multi ? multi_error : last_error
+    f_set = multi ? :mc_multi_set_sites : :mc_set_sites
+    f_async = multi ? :mc_multi_step_days_async : :mc_step_days_async
+    f_wait = multi ? :mc_multi_wait : :mc_wait
     try
-        inp(c) = c.problem.inputs
         # ---- sites: [S] and [N][S] (site fastest) ------------------------------------------------------------
         sitev(f) = Float64[f(inp(c)) for c in caches]
         nodev(f) = Float64[f(inp(c), i) for c in caches, i in 1:N]            # S×N column-major == [N][S] row-major
@@ -120,38 +177,55 @@ function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integ
                        nodev((x, i) -> si(x.soil_profile.hydraulics.air_entry_water_potential[i], u"J/kg")),
                        nodev((x, i) -> si(x.soil_profile.hydraulics.saturated_hydraulic_conductivity[i], u"kg*s/m^3")),
                        nodev((x, i) -> x.soil_profile.hydraulics.campbell_b_parameter[i]), nodev((x, i) -> si(x.soil_profile.hydraulics.root_density[i], u"m/m^3")))
-        has_T = !isnothing(inp(first(caches)).initial_soil_temperature)
+        has_T = !isnothing(i0.initial_soil_temperature)
         T_init = has_T ? nodev((x, i) -> si(u"K"(x.initial_soil_temperature[i]), u"K")) : Float64[]
         th_init = nodev((x, i) -> x.initial_soil_moisture[i])
-        # ---- forcing: hourly [H][S], daily [D][S] ----------------------------------------------------------------
+        # ---- forcing: hourly [H][S], daily [D][S], prescribed moisture [D][N][S] ------------------------------------
         hourly(f) = Float64[f(c, t) for c in caches, t in 1:H]
         daily(f) = Float64[f(inp(c).environment_daily, d) for c in caches, d in 1:D]
         o(c) = c.output
         so(c) = c.buffers.solar_out
         hrain = model.config.rainfall_schedule isa HourlyRainfall
+        has_lw = !isnothing(i0.environment_hourly.longwave_radiation)
+        has_alb = !isnothing(i0.environment_daily.albedo)
+        sms = model.config.soil_moisture_strategy
+        has_presc = sms isa PrescribedSoilMoisture && !isnothing(sms.precomputed_soil_moisture)
         hourly_arrays = (hourly((c, t) -> si(o(c).pressure[t], u"Pa")), hourly((c, t) -> si(u"K"(o(c).reference_temperature[t]), u"K")),
                          hourly((c, t) -> si(o(c).reference_wind_speed[t], u"m/s")), hourly((c, t) -> o(c).reference_humidity[t]),
                          hourly((c, t) -> o(c).cloud_cover[t]), hourly((c, t) -> si(o(c).global_radiation[t], u"W/m^2")),
                          hourly((c, t) -> o(c).diffuse_fraction[t]), hourly((c, t) -> min(si(so(c).zenith_angle[t], u"°"), 90.0)),
                          hourly((c, t) -> min(si(so(c).zenith_slope_angle[t], u"°"), 90.0)),
-                         hrain ? hourly((c, t) -> si(inp(c).environment_hourly.rainfall[t], u"kg/m^2")) : Float64[], Float64[])
+                         hrain ? hourly((c, t) -> si(inp(c).environment_hourly.rainfall[t], u"kg/m^2")) : Float64[],
+                         has_lw ? hourly((c, t) -> si(inp(c).environment_hourly.longwave_radiation[t], u"W/m^2")) : Float64[])
         daily_arrays = (daily((e, d) -> ustrip(e.leaf_area_index[d])), daily((e, d) -> e.shade[d]), daily((e, d) -> e.surface_emissivity[d]),
                         daily((e, d) -> e.cloud_emissivity[d]), daily((e, d) -> e.soil_wetness[d]),
-                        daily((e, d) -> si(u"K"(e.deep_soil_temperature[d]), u"K")), daily((e, d) -> si(e.rainfall[d], u"kg/m^2")), Float64[])
+                        daily((e, d) -> si(u"K"(e.deep_soil_temperature[d]), u"K")), daily((e, d) -> si(e.rainfall[d], u"kg/m^2")),
+                        has_alb ? daily((e, d) -> e.albedo[d]) : Float64[])
+        # PrescribedSoilMoisture.precomputed_soil_moisture is one N x D matrix of the MODEL (src/soil_moisture/prescribed.jl:10-14): replicated per site
+        presc = has_presc ? Float64[sms.precomputed_soil_moisture[i, d] for c in caches, i in 1:N, d in 1:D] : Float64[]      # S×N×D == [D][N][S]
         doy = Cint.(mp.days)
-        # ---- outputs: [H][N][S] and [H][S] --------------------------------------------------------------------------
+        # ---- outputs: [H][N][S], [H][S], snow temperature [H][8][S] ------------------------------------------------------
         node_out = ntuple(_ -> zeros(S, N, H), 7)
-        scal_out = (zeros(S, H), zeros(S, H))
+        scal_out = ntuple(k -> (k <= 2 || has_snow) ? zeros(S, H) : Float64[], 5)      # surface water, sky T, snow fall / depth / density
+        snowT_out = has_snow ? zeros(S, MC_SNOW_NODES, H) : Float64[]
         status = zeros(Cint, S)
-        ptr(a) = isempty(a) ? Ptr{Cdouble}(C_NULL) : pointer(a)
-        GC.@preserve site_arrays T_init th_init hourly_arrays daily_arrays doy node_out scal_out status begin
+        ptr(a) = isempty(a) ? NULLD : pointer(a)
+        at(a, off) = isempty(a) ? NULLD : pointer(a, off + 1)                          # row offset into a site-fastest array
+        cd = isnothing(chunk_days) ? D : min(Int(chunk_days), D)
+        GC.@preserve site_arrays T_init th_init hourly_arrays daily_arrays presc doy node_out scal_out snowT_out status begin
             sites = Ref(McSites(map(ptr, site_arrays)))
             init = Ref(McInitial(ptr(T_init), ptr(th_init)))
-            check(h[], ccall((:mc_set_sites, LIB), Cint, (Ptr{Cvoid}, Ref{McSites}, Ref{McInitial}), h[], sites, init), "mc_set_sites")
-            forcing = Ref(McForcing(map(ptr, hourly_arrays), map(ptr, daily_arrays), Ptr{Cdouble}(C_NULL), pointer(doy)))
-            out = Ref(McOutput(map(pointer, node_out), (pointer(scal_out[1]), pointer(scal_out[2]), Ptr{Cdouble}(C_NULL), Ptr{Cdouble}(C_NULL), Ptr{Cdouble}(C_NULL)),
-                               Ptr{Cdouble}(C_NULL), ntuple(_ -> Ptr{Cdouble}(C_NULL), 3), ntuple(_ -> Ptr{Cdouble}(C_NULL), 2), pointer(status)))   # pass profile buffers here to run solve_air! on the GPU too
-            check(h[], ccall((:mc_step_days, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ref{McForcing}, Ref{McOutput}), h[], 0, D, forcing, out), "mc_step_days")
+            check(h[], ccall((f_set, LIB), Cint, (Ptr{Cvoid}, Ref{McSites}, Ref{McInitial}), h[], sites, init), String(f_set); err)
+            d0 = 0
+            while d0 < D                       # enqueue chunk after chunk; the library keeps two in flight and overlaps their copies with the kernels
+                nd = min(cd, D - d0)
+                forcing = Ref(McForcing(map(a -> at(a, 24 * d0 * S), hourly_arrays), map(a -> at(a, d0 * S), daily_arrays), at(presc, d0 * N * S), pointer(doy, d0 + 1)))
+                out = Ref(McOutput(map(a -> at(a, 24 * d0 * N * S), node_out), map(a -> at(a, 24 * d0 * S), scal_out), at(snowT_out, 24 * d0 * MC_SNOW_NODES * S),
+                                   ntuple(_ -> NULLD, 3), ntuple(_ -> NULLD, 2), pointer(status)))   # pass profile buffers here to run solve_air! on the GPU too
+                check(h[], ccall((f_async, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ref{McForcing}, Ref{McOutput}), h[], d0, nd, forcing, out), String(f_async); err)
+                d0 += nd
+            end
+            check(h[], ccall((f_wait, LIB), Cint, (Ptr{Cvoid},), h[]), String(f_wait); err)
         end
         # ---- un-marshal into each cache's MicroResult (nsteps × N, unit-tagged) so solve_air! runs unchanged ----------
         fields = (:soil_temperature => u"K", :soil_moisture => 1, :soil_water_potential => u"J/kg", :soil_humidity => 1,
@@ -162,10 +236,18 @@ function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integ
         for (s, c) in enumerate(caches), t in 1:H
             c.output.surface_water[t] = scal_out[1][s, t] * u"kg/m^2"
             c.output.sky_temperature[t] = scal_out[2][s, t] * u"K"
+            if has_snow
+                c.output.snow_fall[t] = scal_out[3][s, t] * u"cm/hr"
+                c.output.snow_depth[t] = scal_out[4][s, t] * u"cm"
+                c.output.snow_density[t] = scal_out[5][s, t] * u"g/cm^3"
+                for k in 1:MC_SNOW_NODES
+                    c.output.snow_temperature[t, k] = snowT_out[s, k, t] * u"K"
+                end
+            end
         end
         return status
     finally
-        ccall((:mc_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+        multi ? ccall((:mc_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[]) : ccall((:mc_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
     end
 end
 

@@ -1,22 +1,124 @@
 # parity.jl — run wherever Julia + Microclimate.jl resolve AND a B200 is visible:
-#   julia --project=/path/to/Microclimate.jl julia/parity.jl
-# Runs the reference's own `solve_soil!` and the B200 engine on the reference's test problems and prints the deviation table
-# (north-star tolerances: 1e-3 K soil temperature, 1e-5 m3/m3 moisture).  Until this has been run, parity vs the Julia
-# reference itself is UNPINNED (DESIGN.md §5); parity vs the C++ restatement is bit-exact.
-using Microclimate, Unitful
+#
+#   julia --project=/path/to/Microclimate.jl julia/parity.jl [DATASET_DIR]
+#
+# Runs the reference's own `solve_soil!` and the B200 engine (julia/MicroclimateB200.jl, through the C ABI) on
+#   1-4. the reference's four test problems (test/micro_testrun_monthly.jl, micro_testrun_daily.jl, micro_testrun_monthly_snow.jl,
+#        micro_testrun_snow_scan329.jl - the problems are built by including those scripts, so they are exactly the reference's), and
+#   5.   the first 1000 sites of a synthetic grid written by `python tools/dataset.py make DATASET_DIR --sites 4096 --days 8` (the containers of
+#        microclimate.jl_b200/storage.py, memory-mapped here; INTEGRATION.md §6),
+# and prints, per problem and per field, the maximum and the 99.9th percentile of |reference - B200| plus every entry above the north-star
+# tolerance (1e-3 K soil temperature, 1e-5 m3/m3 moisture).  The path is ill-conditioned at its discontinuities (tests/test_conditioning.py:
+# a 1-ulp forcing change moves T by > 1e-3 K at ~0.2 % of entries), so against Julia's own libm the tolerance can only be met statistically:
+# report max AND p99.9 AND the outlier list, never the max alone.  Until this has been run, parity vs the Julia reference itself is
+# UNPINNED (DESIGN.md §5); parity vs the C++ restatement is bit-exact.
+#
+# NOT RUN in the build container (no Julia there).
+using Microclimate, Unitful, Statistics, Mmap
+import JSON
 include(joinpath(@__DIR__, "MicroclimateB200.jl"))
 using .MicroclimateB200
 
-function deviation(problem)
-    ref = init(problem); Microclimate.solve_solar!(ref); Microclimate.populate_weather!(ref); Microclimate.solve_soil!(ref)
-    gpu = init(problem); Microclimate.solve_solar!(gpu); Microclimate.populate_weather!(gpu)
-    MicroclimateB200.solve_soil_batched!([gpu])
-    dT = maximum(abs.(ustrip.(u"K", ref.output.soil_temperature) .- ustrip.(u"K", gpu.output.soil_temperature)))
-    dθ = maximum(abs.(ref.output.soil_moisture .- gpu.output.soil_moisture))
-    return dT, dθ
+const TOL = Dict(:soil_temperature => 1e-3, :soil_moisture => 1e-5)
+const REFTEST = joinpath(dirname(dirname(pathof(Microclimate))), "test")
+
+"The reference's own solve (weather populated once) and the B200 engine on copies of the same caches."
+function run_pair(problems::Vector; kw...)
+    ref = map(p -> (c = init(p); Microclimate.solve_solar!(c); Microclimate.populate_weather!(c); Microclimate.solve_soil!(c); c), problems)
+    gpu = map(p -> (c = init(p); Microclimate.solve_solar!(c); Microclimate.populate_weather!(c); c), problems)
+    status = MicroclimateB200.solve_soil_batched!(gpu; kw...)
+    return ref, gpu, status
 end
 
-for (name, problem) in ("example_microclimate_problem" => Microclimate.example_microclimate_problem(),)
-    dT, dθ = deviation(problem)
-    println(rpad(name, 36), " max|ΔT| = ", dT, " K   max|Δθ| = ", dθ, "   ", (dT <= 1e-3 && dθ <= 1e-5) ? "OK" : "ABOVE TOLERANCE")
+function report(name, ref, gpu, status)
+    println("== ", name, "  (", length(ref), " site", length(ref) == 1 ? "" : "s", ", flagged by the engine: ", count(!=(0), status), ")")
+    for (f, unit) in ((:soil_temperature, u"K"), (:soil_moisture, NoUnits))
+        d = reduce(vcat, [vec(abs.(ustrip.(unit, getproperty(r.output, f)) .- ustrip.(unit, getproperty(g.output, f)))) for (r, g) in zip(ref, gpu)])
+        d = filter(isfinite, d)
+        tol = TOL[f]
+        nbad = count(>(tol), d)
+        println(rpad("   " * String(f), 24), " max = ", maximum(d), "   p99.9 = ", quantile(d, 0.999), "   entries > ", tol, ": ", nbad, " of ", length(d),
+                nbad == 0 ? "   OK" : "   ABOVE TOLERANCE")
+        if nbad > 0
+            for (s, (r, g)) in enumerate(zip(ref, gpu))
+                e = abs.(ustrip.(unit, getproperty(r.output, f)) .- ustrip.(unit, getproperty(g.output, f)))
+                idx = findall(>(tol), e)
+                isempty(idx) && continue
+                worst = idx[argmax(e[idx])]
+                println("      site ", s, ": ", length(idx), " entries, first at (step, node) = ", Tuple(first(idx)), ", worst ", e[worst], " at ", Tuple(worst))
+            end
+        end
+    end
+end
+
+# ---- 1-4: the reference's test problems (each script leaves `problem` at top level of its sandbox module) ----------------------------------
+function reference_problem(script)
+    m = Module(Symbol("sandbox_", replace(script, "." => "_")))
+    Core.eval(m, :(using Microclimate, Unitful, Test, CSV, DataFrames, Dates, Statistics))
+    Base.include(m, joinpath(REFTEST, script))
+    return Core.eval(m, :problem)
+end
+for script in ("micro_testrun_monthly.jl", "micro_testrun_daily.jl", "micro_testrun_monthly_snow.jl", "micro_testrun_snow_scan329.jl")
+    isfile(joinpath(REFTEST, script)) || (println("== ", script, ": not found under ", REFTEST); continue)
+    p = reference_problem(script)
+    ref, gpu, status = run_pair([p])
+    report(script, ref, gpu, status)
+end
+
+# ---- 5: first 1000 sites of a synthetic grid from the on-disk containers -----------------------------------------------------------------------
+"Memory-map one container of microclimate.jl_b200/storage.py: returns (header, name => array) with arrays site-fastest (Julia dims reversed)."
+function read_container(path)
+    io = open(path)
+    magic = read(io, 8); magic == UInt8[0x4d, 0x43, 0x42, 0x32, 0x30, 0x30, 0x00, 0x01] || error("$path: not an MCB200 container")
+    L = read(io, UInt64)
+    hdr = JSON.parse(String(read(io, L)))
+    arrays = Dict{String,Any}()
+    for a in hdr["arrays"]
+        T = Dict("<f8" => Float64, "<i4" => Int32, "<i8" => Int64)[a["dtype"]]
+        arrays[a["name"]] = Mmap.mmap(io, Array{T,length(a["shape"])}, Tuple(reverse(Int.(a["shape"]))), a["offset"])      # C order -> reversed dims
+    end
+    return hdr, arrays
+end
+
+function synthetic_problems(dir, nsites)
+    _, S = read_container(joinpath(dir, "sites.mcb"))
+    chunks = sort(filter(f -> startswith(f, "forcing_d") && endswith(f, ".mcb"), readdir(dir)))
+    F = [read_container(joinpath(dir, c))[2] for c in chunks]
+    cat_h(name) = reduce(hcat, [f[name] for f in F])                 # [S, H]
+    hourly = Dict(n => cat_h(n) for n in ("pressure", "reference_temperature", "reference_wind_speed", "reference_humidity", "cloud_cover",
+                                          "global_radiation", "zenith_angle", "rainfall_hourly"))
+    daily = Dict(n => cat_h(n) for n in ("leaf_area_index", "shade", "surface_emissivity", "cloud_emissivity", "soil_wetness", "deep_soil_temperature", "rainfall_daily"))
+    D = size(daily["shade"], 2)
+    depths = Microclimate.DEFAULT_DEPTHS
+    model = MicroModel(; depths, heights = [0.01, 2.0]u"m",
+        config = Microclimate.MicroConfig(; convergence = Microclimate.FixedSoilTemperatureIterations(1), rainfall_schedule = Microclimate.HourlyRainfall(),
+                                          soil_moisture_strategy = Microclimate.DynamicSoilMoisture()))
+    map(1:min(nsites, size(S["albedo"], 1))) do s
+        site = Microclimate.Site(; latitude = 0.0u"°", longitude = 0.0u"°", elevation = 0.0u"m", slope = S["slope"][s] * u"°", aspect = 0.0u"°",
+            horizon_angles = fill(0.0u"°", 24), sky_view_fraction = S["sky_view_fraction"][s], albedo = S["albedo"][s],
+            roughness_height = S["roughness_height"][s] * u"m", atmospheric_pressure = hourly["pressure"][s, 1] * u"Pa")
+        hyd = Microclimate.CampbellHydraulicProfile(; air_entry_water_potential = S["air_entry_water_potential"][s, :] .* u"J/kg",
+            saturated_hydraulic_conductivity = S["saturated_hydraulic_conductivity"][s, :] .* u"kg*s/m^3",
+            campbell_b_parameter = S["campbell_b_parameter"][s, :], root_density = S["root_density"][s, :] .* u"m/m^3")
+        soil = Microclimate.SoilProfile(; bulk_density = S["bulk_density"][s, :] .* u"kg/m^3", mineral_density = S["mineral_density"][s, :] .* u"kg/m^3",
+            mineral_conductivity = S["mineral_conductivity"][s, :] .* u"W/m/K", mineral_heat_capacity = S["mineral_heat_capacity"][s, :] .* u"J/kg/K", hydraulics = hyd)
+        eh = Microclimate.HourlyTimeseries(; pressure = hourly["pressure"][s, :] .* u"Pa", reference_temperature = hourly["reference_temperature"][s, :] .* u"K",
+            reference_humidity = hourly["reference_humidity"][s, :], reference_wind_speed = hourly["reference_wind_speed"][s, :] .* u"m/s",
+            global_radiation = hourly["global_radiation"][s, :] .* u"W/m^2", longwave_radiation = nothing, cloud_cover = hourly["cloud_cover"][s, :],
+            rainfall = hourly["rainfall_hourly"][s, :] .* u"kg/m^2", zenith_angle = hourly["zenith_angle"][s, :] .* u"°")
+        ed = Microclimate.DailyTimeseries(; shade = daily["shade"][s, :], soil_wetness = daily["soil_wetness"][s, :], surface_emissivity = daily["surface_emissivity"][s, :],
+            cloud_emissivity = daily["cloud_emissivity"][s, :], rainfall = daily["rainfall_daily"][s, :] .* u"kg/m^2",
+            deep_soil_temperature = daily["deep_soil_temperature"][s, :] .* u"K", leaf_area_index = daily["leaf_area_index"][s, :])
+        inputs = MicroInputs(; site, soil_profile = soil, environment_hourly = eh, environment_daily = ed,
+            initial_soil_temperature = S["initial_soil_temperature"][s, :] .* u"K", initial_soil_moisture = S["initial_soil_moisture"][s, :])
+        MicroProblem(model, inputs; days = collect(1:D), time_mode = Microclimate.ConsecutiveDayMode())
+    end
+end
+
+if length(ARGS) >= 1
+    problems = synthetic_problems(ARGS[1], 1000)
+    ref, gpu, status = run_pair(problems; chunk_days = 2)
+    report("synthetic grid, first $(length(problems)) sites of $(ARGS[1])", ref, gpu, status)
+else
+    println("== synthetic grid: pass the directory written by `python tools/dataset.py make DIR --sites 4096 --days 8` as the first argument")
 end

@@ -62,6 +62,7 @@ void run_blocks_threaded(const mcd::KArgs& a, int TB, int grid, unsigned long lo
  * -DMC_HOST_THREADS; otherwise a single warp on the calling thread) that executes its MCA_LANES lanes one after the other; the request masks, cursor
  * words and retire counters are real atomics, so the claim / retire protocol runs under arbitrary interleavings. */
 static long long g_async_runs = 0;
+static unsigned long long g_async_stats[64];
 template <int NA>
 void run_async(mcd::KArgs a, int nwarps, int grid, unsigned long long* counters)
 {
@@ -69,10 +70,12 @@ void run_async(mcd::KArgs a, int nwarps, int grid, unsigned long long* counters)
     using Blk = mcd::AsyncBlock<NA, HE_SLOTS>;
     unsigned long long cursor = 0, cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     a.next_site = &cursor; a.counters = cnt;
+    a.async_stats = getenv("MC_ASYNC_STATS") ? g_async_stats : nullptr;
+    { const char* e = getenv("MC_ASYNC_SERMIN"); a.async_ser_min = e ? atoi(e) : 0; }
     std::vector<Blk*> blocks; std::vector<std::vector<double>> scr;
     for (int b = 0; b < grid; b++) {
         Blk* B = new Blk(); std::memset(B, 0, sizeof(Blk));
-        for (int t = 0; t < HE_SLOTS; t++) mcd::async_block_init<NA, HE_SLOTS>(*B, t, HE_SLOTS, a.async_slots);
+        for (int t = 0; t < HE_SLOTS; t++) mcd::async_block_init<NA, HE_SLOTS>(*B, t, HE_SLOTS, a.async_slots, a.async_ser_min);
         blocks.push_back(B); scr.emplace_back((size_t)mcd::G_ARRAYS * NA * HE_SLOTS, 0.0);
     }
 #ifdef MC_HOST_THREADS
@@ -84,6 +87,7 @@ void run_async(mcd::KArgs a, int nwarps, int grid, unsigned long long* counters)
     (void)nwarps;
     for (int b = 0; b < grid; b++) mcd::async_worker<NA, HE_SLOTS>(*blocks[b], a, scr[b].data(), 0);
 #endif
+    if (a.async_stats) for (auto* B : blocks) for (int k = 0; k < mcd::MCA_STATS; k++) g_async_stats[k] += B->stats[k];
     for (auto* B : blocks) delete B;
     for (int k = 0; k < 7; k++) counters[k] += cnt[k];
 }
@@ -266,6 +270,7 @@ extern "C" double he_stomatal_newton_plain(const mc_model_desc* m, double psi_ba
     return psi_leaf;
 }
 
+extern "C" void he_async_stats(unsigned long long* out) { for (int k = 0; k < 64; k++) { out[k] = g_async_stats[k]; g_async_stats[k] = 0; } }
 extern "C" long long he_async_runs(void) { return g_async_runs; }      /* how many chunks went through the asynchronous kernel body */
 
 extern "C" int he_set_state(void* h, const mc_state_soa* st)
