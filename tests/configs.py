@@ -87,6 +87,38 @@ def config2_daily(ndays=30):
     return problem, g
 
 
+def config4_scan329(ndays=365):
+    """Config 4 (SCAN / SNOTEL 329, Utah, 2013; test/micro_testrun_snow_scan329.jl:1-238): S=1, N=19 + 8 snow nodes, consecutive days,
+    dynamic soil moisture, DailyRainfall, SnowModel with the density function - the only configuration with snow + moisture + a full year."""
+    g = load("config4_scan329.npz")
+    H, n = 24 * ndays, 19
+    site = mc.Site(elevation=float(g["elevation"]), slope=0.0, sky_view_fraction=1.0, albedo=float(g["albedo"]), roughness_height=float(g["roughness_height"]))
+    soil_profile = mc.SoilProfile(
+        bulk_density=np.full(n, float(g["bulk_density"])), mineral_density=np.full(n, float(g["mineral_density"])),
+        mineral_conductivity=g["mineral_conductivity"], mineral_heat_capacity=g["mineral_heat_capacity"],
+        hydraulics=mc.CampbellHydraulicProfile(np.full(n, float(g["air_entry_water_potential"])), np.full(n, float(g["saturated_hydraulic_conductivity"])),
+                                               np.full(n, float(g["campbell_b_parameter"])), g["root_density"]))
+    e = float(g["emissivity"])
+    daily = mc.DailyTimeseries(shade=np.zeros(ndays), soil_wetness=np.zeros(ndays), surface_emissivity=np.full(ndays, e), cloud_emissivity=np.full(ndays, e),
+                               rainfall=g["rainfall"][:ndays], deep_soil_temperature=g["deep_soil_temperature"][:ndays].astype(float),
+                               leaf_area_index=np.full(ndays, 0.1))
+    hourly = mc.HourlyWeather(pressure=np.full(H, float(g["pressure"])), reference_temperature=g["TAREF"][:H], reference_wind_speed=g["VREF"][:H],
+                              reference_humidity=g["RH"][:H], cloud_cover=g["cloud"][:H], global_radiation=g["SOLR"][:H], zenith_angle=g["ZEN"][:H])
+    snow_model = mc.SnowModel(snow_temperature_threshold=float(g["snowtemp"]), snow_density=float(g["snowdens"]), snow_melt_factor=float(g["snowmelt"]),
+                              undercatch=float(g["undercatch"]), rain_multiplier=1.0, rain_melt_factor=float(g["rainmelt"]),
+                              density_function=tuple(float(x) for x in g["densfun"]), snow_conductivity=float(g["snowcond"]),
+                              canopy_interception=float(g["intercept"]))
+    config = mc.MicroConfig(convergence=mc.FixedSoilTemperatureIterations(3), rainfall_schedule=mc.DailyRainfall(),
+                            soil_moisture_strategy=mc.DynamicSoilMoisture())
+    model = mc.MicroModel(depths=g["depths"], heights=g["heights"], snow_model=snow_model, config=config,
+                          soil_properties_model=mc.CampbelldeVriesSoilProperties(de_vries_shape_factor=float(g["de_vries_shape_factor"]),
+                                                                                 recirculation_power=4.0, return_flow_threshold=0.162))
+    inputs = mc.MicroInputs(site=site, soil_profile=soil_profile, environment_daily=daily, environment_hourly=hourly,
+                            initial_soil_temperature=g["initial_soil_temperature"], initial_soil_moisture=g["initial_soil_moisture"])
+    problem = mc.MicroProblem(model, inputs, days=[int(d) for d in g["days"][:ndays]], time_mode=mc.ConsecutiveDayMode(spinup_first_day=False))
+    return problem, g
+
+
 def regrid(problem, depths):
     """The same problem on another depth grid (per-node soil parameters / initial state taken from the nearest old node)."""
     import copy

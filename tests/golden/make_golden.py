@@ -6,6 +6,7 @@ Reads the NicheMapR fixture CSVs the reference's tests read (test/micro_testrun_
 test/micro_testrun_daily.jl:11-180) and writes compact .npz files next to this script:
   config1_monthly.npz  inputs + NicheMapR goldens of config 1 (12 non-consecutive days, N=10)
   config2_daily.npz    inputs + NicheMapR goldens of config 2 (30 consecutive days, N=19, dynamic moisture)
+  config4_scan329.npz  inputs + NicheMapR goldens of config 4 (SCAN 329: 365 consecutive days, N=19 + 8 snow nodes, dynamic moisture, snow)
 Hourly forcing for config 1 is NicheMapR's own expansion found in the golden output
 (metout_monthly.csv TAREF/RH/VREF/SOLR/ZEN) because the diel engine / solar model are pre-processing
 outside the hot path.
@@ -144,9 +145,58 @@ def config2():
     print("wrote config2_daily.npz", {k: np.shape(v) for k, v in d.items() if np.ndim(v)})
 
 
+def config4():
+    """BASELINE config 4, SCAN/SNOTEL 329 (test/micro_testrun_snow_scan329.jl:1-238): N=19 + 8 snow nodes, 365 consecutive days of 2013, dynamic
+    moisture, DailyRainfall, snow.  The reference expands daily min/max to hourly with its diel engine (pre-processing outside the hot path); as for
+    config 1 the hourly forcing here is NicheMapR's own expansion found in the golden output (metout.csv TAREF/RH/VREF/SOLR/ZEN); cloud cover is
+    held at the day's mean of (CCmin, CCmax) because metout carries no hourly cloud column.  Goldens: soil.csv, soilmoist.csv, metout.csv snow columns."""
+    d = f"{REF}/scan329"
+    met = pd.read_csv(f"{d}/metout.csv")
+    soil = pd.read_csv(f"{d}/soil.csv")
+    moist = pd.read_csv(f"{d}/soilmoist.csv")
+    sun = pd.read_csv(f"{d}/sunsnow.csv")
+    frc = pd.read_csv(f"{d}/nmr_forcing.csv")
+    ini = pd.read_csv(f"{d}/nmr_initial.csv")
+    par = pd.read_csv(f"{d}/nmr_params.csv").iloc[0]
+    nd = 365
+    H = 24 * nd
+    sm10 = np.array([ini[f"SM{i}"][0] for i in range(1, 11)], float)
+    st = np.full(19, 274.15)
+    st[18] = 273.15 + 6.4; st[17] = 273.15 + (6.4 + 3.0) / 2.0; st[16] = st[15] = st[14] = 273.15 + 3.0          # script lines 84-89
+    cc = 0.5 * (frc["CCmin_pct"].to_numpy(float)[:nd] + frc["CCmax_pct"].to_numpy(float)[:nd]) / 100.0
+    out = dict(
+        days=frc["doy"].to_numpy(int)[:nd],
+        depths=np.array([0.0, 1.25, 2.5, 3.75, 5.0, 7.5, 10.0, 12.5, 15.0, 17.5, 20.0, 25.0, 30.0, 40.0, 50.0, 75.0, 100.0, 150.0, 200.0]) / 100.0,
+        heights=np.array([0.01, 2.0]), roughness_height=float(par["RUF"]), elevation=float(par["elevation_m"]), albedo=float(par["REFL"]),
+        emissivity=float(par["SLE"]), bulk_density=1300.0, mineral_density=2560.0,
+        mineral_conductivity=np.array([0.2, 0.2, 0.2, 1.35] + [2.5] * 15), mineral_heat_capacity=np.array([1920.0, 1920.0, 1920.0, 1395.0] + [870.0] * 15),
+        de_vries_shape_factor=0.0167238, air_entry_water_potential=1.1, saturated_hydraulic_conductivity=0.0037, campbell_b_parameter=4.5,
+        root_density=np.array([0.0, 0.0, 82000.0, 80000.0, 78000.0, 74000.0, 71000.0, 64000.0, 58000.0, 48000.0, 40000.0, 18000.0, 9000.0, 6000.0, 8000.0,
+                               4000.0, 4000.0, 0.0, 0.0]),
+        initial_soil_moisture=expand_fine(sm10), initial_soil_temperature=st,
+        rainfall=frc["Rain_mm"].to_numpy(float)[:nd], deep_soil_temperature=soil["D200cm"].to_numpy(float)[0:H:24] + 273.15,
+        pressure=pressure_from_elevation(float(par["elevation_m"])),
+        snowtemp=float(par["snowtemp"]), snowdens=float(par["snowdens"]), snowmelt=float(par["snowmelt"]), undercatch=float(par["undercatch"]),
+        rainmelt=float(par["rainmelt"]), densfun=np.array([par["densfun1"], par["densfun2"], par["densfun3"], par["densfun4"]], float),
+        snowcond=float(par["snowcond"]), intercept=float(par["intercept"]),
+        TAREF=met["TAREF"].to_numpy(float)[:H] + 273.15, RH=np.clip(met["RH"].to_numpy(float)[:H], 0, 100) / 100.0,
+        VREF=met["VREF"].to_numpy(float)[:H], SOLR=met["SOLR"].to_numpy(float)[:H], ZEN=met["ZEN"].to_numpy(float)[:H], cloud=np.repeat(cc, 24),
+        # goldens (float32 keeps the fixture small; the comparisons are at 1e-1 relative / kelvin level)
+        soil_nmr=(soil.iloc[:H, 2:12].to_numpy(float) + 273.15).astype(np.float32), soilmoist_nmr=moist.iloc[:H, 2:12].to_numpy(float).astype(np.float32),
+        SNOWDEP=met["SNOWDEP"].to_numpy(float)[:H].astype(np.float32), SNOWFALL=met["SNOWFALL"].to_numpy(float)[:H].astype(np.float32),
+        SNOWDENS=met["SNOWDENS"].to_numpy(float)[:H].astype(np.float32), TSKYC=(met["TSKYC"].to_numpy(float)[:H] + 273.15).astype(np.float32),
+        sunsnow=(sun.iloc[:H, 2:11].to_numpy(float) + 273.15).astype(np.float32),
+    )
+    for k in ("TAREF", "RH", "VREF", "SOLR", "ZEN"):
+        out[k] = out[k].astype(np.float64)
+    np.savez_compressed(f"{OUT}/config4_scan329.npz", **out)
+    print("wrote config4_scan329.npz", os.path.getsize(f"{OUT}/config4_scan329.npz") // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference test data not found (this script only runs in the build container)")
     config1()
     config1(tag="monthly_snow", init="init_monthly_snow", metout="metout_monthly_snow.csv", soil="soil_monthly_snow.csv")
     config2()
+    config4()

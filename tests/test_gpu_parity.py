@@ -427,3 +427,21 @@ def test_file_driven_run_matches_in_memory(SoilEngine, tmp_path):
         got = np.concatenate([getattr(st.load_outputs(os.path.join(d, f"out_d{k:04d}_s0-{S}.mcb")), name) for k in range(ND)])
         assert np.array_equal(got, getattr(ref, name)), name
     assert int(st.load_state(os.path.join(d, f"state_s0-{S}.mcb")).days_done[0]) == ND
+
+
+def test_config4_scan329_full_year_matches_oracle(SoilEngine):
+    """BASELINE config 4 (SCAN / SNOTEL 329, test/micro_testrun_snow_scan329.jl:1-238): N=19 + 8 snow nodes, 365 consecutive days, dynamic moisture,
+    DailyRainfall, snow - every output field incl. the snow fields over the whole year, bit for bit, in 73-day chunks (the snowpack is carried state)."""
+    p, g = configs.config4_scan329()
+    desc, sites, forcing = _problem_buffers(p)
+    f = parity.ALL_FIELDS + parity.SNOW_FIELDS
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f, chunks=[73] * 5)
+    out, eg = parity.run(SoilEngine, desc, sites, forcing, fields=f, chunks=[73] * 5)
+    parity.assert_within_north_star(out, ref, f)
+    parity.assert_bit_identical(out, ref, f)
+    co, cg = eo.counters(), eg.counters()
+    for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps", "n_day_passes"):
+        assert co[k] == cg[k], k
+    # the reference's usual NicheMapR bar on the CUDA output itself
+    T, G = out.soil_temperature[:, ::2, 0], g["soil_nmr"].astype(float)
+    assert np.abs(T / G - 1).max() < 1e-1 and np.corrcoef(out.snow_depth[:, 0], g["SNOWDEP"].astype(float))[0, 1] > 0.85

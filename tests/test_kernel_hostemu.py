@@ -299,3 +299,17 @@ def test_solve_air_bit_identical_incl_snow_surface_and_chunking():
     assert np.all(out.wind_speed[:, 0, 0] == 0.0) and np.array_equal(out.air_temperature[:, 3, 0], forcing.reference_temperature[:, 0])
     chunked, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f, chunks=[7, 5])
     parity.assert_bit_identical(chunked, ref, parity.AIR_FIELDS)
+
+
+def test_config4_scan329_bit_identical():
+    """BASELINE config 4 (SCAN 329: snow + dynamic moisture + DailyRainfall, consecutive days): the first 40 days (mid-winter, snowpack building) through the
+    kernel body; the full year runs on the GPU (tests/test_gpu_parity.py)."""
+    p, _ = configs.config4_scan329(40)
+    desc, sites, forcing = _buffers(p)
+    f = parity.ALL_FIELDS + parity.SNOW_FIELDS
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f)
+    out, ee = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(out, ref, f)
+    assert ref.snow_depth.max() > 5.0
+    co, ce = eo.counters(), ee.counters()
+    assert all(co[k] == ce[k] for k in ("n_rhs", "n_accept", "n_reject", "n_newton_iter", "n_infil_steps"))

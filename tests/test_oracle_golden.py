@@ -246,3 +246,30 @@ def test_solve_air_profiles_vs_nichemapr(g1):
     assert nrel(Ta[:, 0], g1["TALOC"]) < 1e-3 and nrel(v[:, 0], g1["VLOC"]) < 5e-3 and nrel(rh[:, 0], g1["RHLOC"]) < 2e-2
     assert np.array_equal(Ta[:, 1], g1["TAREF"]) and np.array_equal(v[:, 1], g1["VREF"])      # the reference-height slot is pinned to the measurement
     assert np.all(out.friction_velocity > 0) and np.all(np.isfinite(out.convective_heat_flux))
+
+
+def test_config4_scan329_full_year_against_nichemapr():
+    """BASELINE config 4 (SCAN / SNOTEL 329, test/micro_testrun_snow_scan329.jl): 365 consecutive days, N=19 + 8 snow nodes, dynamic moisture, DailyRainfall,
+    snow with the density function.  The reference script is manual and has no assertions; the oracle is held to the reference's usual NicheMapR bar
+    (rtol 1e-1 on kelvin, micro_testrun_monthly.jl:172) over the whole year, plus RMSE / snowpack-agreement bounds a little above what is observed
+    (soil T rmse 2.7 K, moisture rmse 0.041, snow-depth correlation 0.91; hourly forcing is NicheMapR's expansion with day-mean cloud, see make_golden.py)."""
+    import configs
+    import parity
+    from microclimate_jl_b200 import marshal as M
+    p, g = configs.config4_scan329()
+    desc = M.model_desc(p.model, p.time_mode, inputs0=p.inputs)
+    assert desc.n_soil == 19 and desc.n_snow == 8 and desc.moisture_strategy == 1 and desc.time_mode == 1
+    sites = M.SitesBatch.from_inputs(p.model, [p.inputs])
+    forcing = M.ForcingBatch.from_inputs(p.model, [p.inputs], p.days)
+    out, eng = parity.run(OracleEngine, desc, sites, forcing, fields=parity.ALL_FIELDS + parity.SNOW_FIELDS)
+    assert out.status[0] == 0 and eng.counters()["n_day_passes"] == 365
+    T, G = out.soil_temperature[:, ::2, 0], g["soil_nmr"].astype(float)
+    assert np.abs(T / G - 1).max() < 1e-1
+    assert np.sqrt(((T - G) ** 2).mean()) < 3.5
+    assert np.abs(T[:, 9] - G[:, 9]).max() < 1e-3                      # the deep node is the prescribed boundary
+    th, GM = out.soil_moisture[:, ::2, 0], g["soilmoist_nmr"].astype(float)
+    assert np.sqrt(((th - GM) ** 2).mean()) < 0.06
+    sd, gsd = out.snow_depth[:, 0], g["SNOWDEP"].astype(float)
+    assert np.corrcoef(sd, gsd)[0, 1] > 0.85 and sd.max() > 20.0
+    assert abs(out.snow_fall[:, 0].sum() / g["SNOWFALL"].sum() - 1) < 0.15
+    assert np.all(np.isfinite(out.soil_temperature)) and np.all((out.soil_moisture >= 0) & (out.soil_moisture <= 1))
