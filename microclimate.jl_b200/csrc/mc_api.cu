@@ -126,10 +126,6 @@ __global__ void __launch_bounds__(MC_ASYNC_THREADS, 1) soil_async_kernel(const _
     __syncthreads();
     double* ga = a.async_scr + (size_t)blockIdx.x * ((size_t)mcd::G_ARRAYS * NA * SLOTS);
     mcd::async_worker<NA, SLOTS>(B, a, ga, (int)(threadIdx.x >> 5));
-    if (a.async_stats) {                                     /* work census: the block's tallies into the launch's */
-        __syncthreads();
-        for (int k = (int)threadIdx.x; k < mcd::MCA_STATS; k += (int)blockDim.x) if (B.stats[k]) atomicAdd(a.async_stats + k, B.stats[k]);
-    }
 }
 
 /* solve_air! for the rows of the chunk the soil kernel just wrote (reference src/simulation.jl:822-851) */
@@ -343,6 +339,7 @@ static int launch_chunk_async(mc_handle* h, mcd::KArgs& a, cudaStream_t st, int 
     }
     a.async_scr = h->async_scr; a.async_slots = slots;
     { const char* e = getenv("MC_ASYNC_SERMIN"); a.async_ser_min = e ? atoi(e) : 0; }                                  /* tuning knob */
+    { const char* e = getenv("MC_ASYNC_IDLE_NS"); a.async_idle_ns = e ? atoi(e) : 0; }
     a.async_stats = getenv("MC_ASYNC_STATS") ? h->counters + 16 : nullptr;                                             /* work census (development) */
     a.next_site = h->counters + 8 + slice;
     MC_CUDA(h, cudaMemsetAsync(a.next_site, 0, sizeof(unsigned long long), st));
@@ -592,7 +589,13 @@ static int launch_range(mc_handle* h, mcd::KArgs a, int64_t lo, int64_t hi, cuda
     cudaError_t e = cudaSuccess;
     if (async_enabled(h)) {
         /* slices of one async scratch would overlap: concurrent slices share h->async_scr only because slice kernels are serialised (mc_step_days) */
-        if (int rc = na == 10 ? launch_chunk_async<10, 64>(h, a, st, slice) : (na == 19 ? launch_chunk_async<19, 64>(h, a, st, slice) : launch_chunk_async<MC_MAX_SOIL_NODES, 48>(h, a, st, slice))) return rc;
+        const char* se = getenv("MC_ASYNC_SLOTS");
+        const bool half = se && atoi(se) > 0 && atoi(se) <= 32;      /* tuning knob: the 32-slot build (half the shared memory, more L1) */
+        int rc;
+        if (na == 10) rc = half ? launch_chunk_async<10, 32>(h, a, st, slice) : launch_chunk_async<10, 64>(h, a, st, slice);
+        else if (na == 19) rc = half ? launch_chunk_async<19, 32>(h, a, st, slice) : launch_chunk_async<19, 64>(h, a, st, slice);
+        else rc = half ? launch_chunk_async<MC_MAX_SOIL_NODES, 32>(h, a, st, slice) : launch_chunk_async<MC_MAX_SOIL_NODES, 48>(h, a, st, slice);
+        if (rc) return rc;
     }
     else if (coop_enabled(h)) {
         if (int rc = na == 10 ? launch_chunk_coop<10>(h, a, st) : (na == 19 ? launch_chunk_coop<19>(h, a, st) : launch_chunk_coop<MC_MAX_SOIL_NODES>(h, a, st))) return rc;
@@ -623,11 +626,21 @@ int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forc
     return 0;
 }
 
+/* the asynchronous kernel gives up (instead of hanging the device) when a warp sees no work for ~70 s; counters[7] counts such blocks */
+static int check_watchdog(mc_handle* h)
+{
+    unsigned long long v = 0;
+    MC_CUDA(h, cudaMemcpy(&v, h->counters + 7, sizeof(v), cudaMemcpyDeviceToHost));
+    if (v) { h->err = "soil_async_kernel watchdog: " + std::to_string(v) + " block(s) stopped after ~70 s without work; results of this chunk are incomplete"; return -5; }
+    return 0;
+}
+
 /* a chunk on staging set b is complete on the device: collect its kernel time and flagged-site count */
 static int harvest(mc_handle* h, int b)
 {
     if (!h->busy[b]) return 0;
     MC_CUDA(h, cudaEventSynchronize(h->ev_d2h[b]));
+    if (int rc = check_watchdog(h)) { h->busy[b] = false; return rc; }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev_t0[b], h->ev_t1[b]) == cudaSuccess) h->pending_ms += ms;
     int nbad = 0;
@@ -645,7 +658,7 @@ int mc_synchronize(mc_handle* h)
     MC_CUDA(h, cudaStreamSynchronize(h->stream));
     float ms = 0.f;
     if (h->timed_by_ev01 && h->last_launches && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
-    return 0;
+    return check_watchdog(h);
 }
 
 static int ensure_stage(mc_handle* h, double** buf, size_t* have, size_t need)

@@ -40,7 +40,7 @@ MC_DEV unsigned mca_or32(unsigned* p, unsigned v) { return atomicOr(p, v); }
 MC_DEV int mca_ld(const int* p) { return *(const volatile int*)p; }
 MC_DEV unsigned mca_ldu(const unsigned* p) { return *(const volatile unsigned*)p; }
 MC_DEV void mca_fence() { __threadfence_block(); }
-MC_DEV void mca_idle() { __nanosleep(100); }
+MC_DEV void mca_idle(int ns) { __nanosleep(ns > 0 ? (unsigned)ns : 100u); }
 MC_DEV unsigned long long mca_grab(unsigned long long* p) { return atomicAdd(p, 1ull); }
 MC_DEV void mca_gadd(unsigned long long* p, unsigned long long v) { if (v) atomicAdd(p, v); }
 MC_DEV int mca_popc(unsigned v) { return __popc(v); }
@@ -56,7 +56,7 @@ MC_DEV unsigned mca_or32(unsigned* p, unsigned v) { return __atomic_fetch_or(p, 
 MC_DEV int mca_ld(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 MC_DEV unsigned mca_ldu(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 MC_DEV void mca_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-MC_DEV void mca_idle() { std::this_thread::yield(); }
+MC_DEV void mca_idle(int) { std::this_thread::yield(); }
 MC_DEV unsigned long long mca_grab(unsigned long long* p) { return __atomic_fetch_add(p, 1ull, __ATOMIC_ACQ_REL); }
 MC_DEV void mca_gadd(unsigned long long* p, unsigned long long v) { if (v) __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 MC_DEV int mca_popc(unsigned v) { return __builtin_popcount(v); }
@@ -126,7 +126,8 @@ struct AsyncBlock {
     int pend[SLOTS];                                                       /* items of the slot's current pass not yet retired */
     int alive;                                                             /* slots that may still receive a site */
     int ser_min;
-    unsigned long long stats[MCA_STATS];
+    int abort;                                                             /* watchdog: a warp saw no work for far longer than any launch lasts */
+    int nreq;                                                              /* requests with unclaimed items: what an idle warp polls (one word) before it scans the masks */
     MC_MEMBER SlotState& z(int o) { return *reinterpret_cast<SlotState*>(zraw + (size_t)ZD * o); }
 };
 
@@ -141,6 +142,7 @@ MC_DEV void async_enqueue1(AsyncBlock<NA, SLOTS>& B, int type, int o)
 {
     mca_fence();
     mca_or32(&B.mask1[type][o >> 5], 1u << (o & 31));
+    mca_add(&B.nreq, 1);
 }
 template <int NA, int SLOTS>
 MC_DEV void async_request0(AsyncBlock<NA, SLOTS>& B, int type, int o, int extra_pending)
@@ -150,6 +152,7 @@ MC_DEV void async_request0(AsyncBlock<NA, SLOTS>& B, int type, int o, int extra_
     B.pend[o] = async_items(type, N) + extra_pending;
     mca_fence();
     mca_or32(&B.mask0[type][o >> 5], 1u << (o & 31));
+    mca_add(&B.nreq, 1);
 }
 
 /* ---- forcing: staged knots of the current hour, global fallback for a stage time that sits exactly on the next knot ---- */
@@ -544,6 +547,7 @@ MC_DEV void async_publish_rhs(AsyncBlock<NA, SLOTS>& B, const KArgs& a, int o)
     Z.code = Z.stage | (Z.kswap ? 16 : 0) | (Z.uswap ? 32 : 0);
     async_request0(B, T0_COND, o, 1);
     mca_or32(&B.mask1[T1_SURF][o >> 5], 1u << (o & 31));
+    mca_add(&B.nreq, 1);
 }
 
 /* CTRL: an RHS evaluation is complete -> resume the integrator */
@@ -1006,6 +1010,7 @@ MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt)
 {
     const int N = MC_CONST_MODEL.N;
     AsyncClaim c; c.chan = -1; c.type = 0; c.total = 0; c.nseg = 0; c.bits[0] = 0; c.bits[1] = 0;
+    if (mca_ld(&B.nreq) <= 0) return c;                                    /* nothing on offer: one load instead of a scan of every mask */
     unsigned m0[T0_TYPES][2], m1[T1_TYPES][2];
     int best0 = -1, n0 = 0, best1 = -1, n1 = 0;
     for (int t = 0; t < T0_TYPES; t++) {
@@ -1035,7 +1040,7 @@ MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt)
                     if ((rq >> 16) != t || cur >= n) break;
                     const int take = (n - cur) < (MCA_LANES - got) ? (n - cur) : (MCA_LANES - got);
                     if (mca_cas(&B.req0[o], rq, rq + take) == rq) {
-                        if (cur + take >= n) mca_and32(&B.mask0[t][w], ~(1u << b));      /* the last items are taken: withdraw the offer (before they run, so before any re-request) */
+                        if (cur + take >= n) { mca_and32(&B.mask0[t][w], ~(1u << b)); mca_add(&B.nreq, -1); }      /* the last items are taken: withdraw the offer (before they run, so before any re-request) */
                         c.seg[c.nseg++] = (unsigned)o | ((unsigned)cur << 8) | ((unsigned)take << 16);
                         got += take;
                         break;
@@ -1057,7 +1062,7 @@ MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt)
             c.bits[w] = old & want;
             got += mca_popc(c.bits[w]);
         }
-        if (got) { c.chan = 1; c.type = t; c.total = got; mca_fence(); }
+        if (got) { c.chan = 1; c.type = t; c.total = got; mca_add(&B.nreq, -got); mca_fence(); }
         return c;
     }
 }
@@ -1097,6 +1102,10 @@ template <int NA, int SLOTS>
 MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, int warp)
 {
     int salt = warp;
+    unsigned long long wst[MCA_STATS];                                     /* this warp's census (leader lane) */
+    for (int k = 0; k < MCA_STATS; k++) wst[k] = 0;
+    long long t_last_work = mca_clock();
+    int backoff = 0;                                                       /* idle sleep doubles from the base up to 16x while nothing turns up: idle warps must not eat the issue slots of working ones */
     for (;;) {
         AsyncClaim c;
 #if defined(__CUDACC__)
@@ -1112,12 +1121,16 @@ MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, i
 #endif
         salt++;
         if (c.chan < 0) {
-            if (mca_ld(&B.alive) <= 0) return;
+            if (mca_ld(&B.alive) <= 0 || mca_ld(&B.abort)) break;
             const long long ti = mca_clock();
-            mca_idle();
-            if (a.async_stats && MCA_IS_LEADER) { mca_stat_add(&B.stats[3 * MCA_STAT_TYPES], 1ull); mca_stat_add(&B.stats[3 * MCA_STAT_TYPES + 1], (unsigned long long)(mca_clock() - ti)); }
+            mca_idle((a.async_idle_ns > 0 ? a.async_idle_ns : 250) << backoff);
+            if (backoff < 4) backoff++;
+            const long long tn = mca_clock();
+            wst[3 * MCA_STAT_TYPES] += 1; wst[3 * MCA_STAT_TYPES + 1] += (unsigned long long)(tn - ti);
+            if (tn - t_last_work > (1ll << 37)) { B.abort = 1; mca_fence(); }          /* ~70 s without work: give up rather than hang the device (the host reports it) */
             continue;
         }
+        backoff = 0;
         const long long t_begin = mca_clock();
         if (c.chan == 0) {
 #if defined(__CUDACC__)
@@ -1170,11 +1183,14 @@ MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, i
                 }
             }
         }
-        if (a.async_stats && MCA_IS_LEADER) {
-            unsigned long long* st = &B.stats[3 * (c.chan == 0 ? c.type : T0_TYPES + c.type)];
-            mca_stat_add(st, 1ull); mca_stat_add(st + 1, (unsigned long long)c.total); mca_stat_add(st + 2, (unsigned long long)(mca_clock() - t_begin));
+        {
+            const int k = 3 * (c.chan == 0 ? c.type : T0_TYPES + c.type);
+            t_last_work = mca_clock();
+            wst[k] += 1; wst[k + 1] += (unsigned long long)c.total; wst[k + 2] += (unsigned long long)(t_last_work - t_begin);
         }
     }
+    if (a.async_stats && MCA_IS_LEADER) { for (int k = 0; k < MCA_STATS; k++) if (wst[k]) mca_stat_add(a.async_stats + k, wst[k]); }
+    if (MCA_IS_LEADER && warp == 0 && mca_ld(&B.abort) && a.flags) mca_stat_add(a.counters + 7, 1ull);      /* counters[7]: watchdog aborts */
 }
 
 /* block set-up: every slot starts by asking for a site */
@@ -1190,6 +1206,7 @@ MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, in
         B.mask1[T1_SITE][1] = n > 32 ? (n >= 64 ? 0xffffffffu : ((1u << (n - 32)) - 1u)) : 0u;
         B.alive = n;
         B.ser_min = ser_min > 0 ? ser_min : MCA_LANES / 4;
-        for (int k = 0; k < MCA_STATS; k++) B.stats[k] = 0;
+        B.abort = 0;
+        B.nreq = n;                                                        /* the initial SITE requests */
     }
 }

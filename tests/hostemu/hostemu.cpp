@@ -87,7 +87,6 @@ void run_async(mcd::KArgs a, int nwarps, int grid, unsigned long long* counters)
     (void)nwarps;
     for (int b = 0; b < grid; b++) mcd::async_worker<NA, HE_SLOTS>(*blocks[b], a, scr[b].data(), 0);
 #endif
-    if (a.async_stats) for (auto* B : blocks) for (int k = 0; k < mcd::MCA_STATS; k++) g_async_stats[k] += B->stats[k];
     for (auto* B : blocks) delete B;
     for (int k = 0; k < 7; k++) counters[k] += cnt[k];
 }
