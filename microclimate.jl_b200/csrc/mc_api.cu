@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(MC_ASYNC_THREADS, 1) soil_async_kernel(const _
 {
     extern __shared__ __align__(16) unsigned char mc_async_smem[];
     mcd::AsyncBlock<NA, SLOTS>& B = *reinterpret_cast<mcd::AsyncBlock<NA, SLOTS>*>(mc_async_smem);
-    mcd::async_block_init<NA, SLOTS>(B, (int)threadIdx.x, (int)blockDim.x, a.async_slots, a.async_ser_min);
+    mcd::async_block_init<NA, SLOTS>(B, (int)threadIdx.x, (int)blockDim.x, a.async_slots, a.async_ser_min, a.async_affinity);
     __syncthreads();
     double* ga = a.async_scr + (size_t)blockIdx.x * ((size_t)mcd::G_ARRAYS * NA * SLOTS);
     mcd::async_worker<NA, SLOTS>(B, a, ga, (int)(threadIdx.x >> 5));
@@ -321,6 +321,8 @@ static int launch_chunk_async(mc_handle* h, mcd::KArgs& a, cudaStream_t st, int 
     if (!attr_set) {
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         MC_CUDA(h, cudaFuncSetAttribute(soil_async_kernel<NA, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        /* shared memory exactly as large as the tile needs: whatever is left of the 256 KB stays L1 (the stack frames of the math calls live there) */
+        MC_CUDA(h, cudaFuncSetAttribute(soil_async_kernel<NA, SLOTS>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1)));
         attr_set = true;
     }
     const int64_t n = a.s_end - a.s_begin;
@@ -340,6 +342,7 @@ static int launch_chunk_async(mc_handle* h, mcd::KArgs& a, cudaStream_t st, int 
     a.async_scr = h->async_scr; a.async_slots = slots;
     { const char* e = getenv("MC_ASYNC_SERMIN"); a.async_ser_min = e ? atoi(e) : 0; }                                  /* tuning knob */
     { const char* e = getenv("MC_ASYNC_IDLE_NS"); a.async_idle_ns = e ? atoi(e) : 0; }
+    { const char* e = getenv("MC_ASYNC_AFFINITY"); a.async_affinity = e ? atoi(e) : 0; }
     a.async_stats = getenv("MC_ASYNC_STATS") ? h->counters + 16 : nullptr;                                             /* work census (development) */
     a.next_site = h->counters + 8 + slice;
     MC_CUDA(h, cudaMemsetAsync(a.next_site, 0, sizeof(unsigned long long), st));

@@ -127,6 +127,7 @@ struct AsyncBlock {
     int alive;                                                             /* slots that may still receive a site */
     int ser_min;
     int abort;                                                             /* watchdog: a warp saw no work for far longer than any launch lasts */
+    int affinity;
     int nreq;                                                              /* requests with unclaimed items: what an idle warp polls (one word) before it scans the masks */
     MC_MEMBER SlotState& z(int o) { return *reinterpret_cast<SlotState*>(zraw + (size_t)ZD * o); }
 };
@@ -1006,7 +1007,7 @@ struct AsyncClaim { int chan, type, total, nseg; unsigned seg[4]; unsigned bits[
 /* Pick a task type and claim up to MCA_LANES items of it (executed by one lane per warp).  Node-item types are preferred while a full warp of
  * them is on offer; single-lane tasks are taken in batches where possible (they unlock the node items) and always when nothing else is. */
 template <int NA, int SLOTS>
-MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt)
+MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt, int warp)
 {
     const int N = MC_CONST_MODEL.N;
     AsyncClaim c; c.chan = -1; c.type = 0; c.total = 0; c.nseg = 0; c.bits[0] = 0; c.bits[1] = 0;
@@ -1024,7 +1025,22 @@ MC_DEV AsyncClaim async_try_claim(AsyncBlock<NA, SLOTS>& B, int salt)
         if (cnt > n1) { n1 = cnt; best1 = t; }
     }
     if (best0 < 0 && best1 < 0) return c;
-    const bool take0 = best0 >= 0 && (n0 >= MCA_LANES || best1 < 0 || n1 < B.ser_min);
+    bool take0 = best0 >= 0 && (n0 >= MCA_LANES || best1 < 0 || n1 < B.ser_min);
+    if (B.affinity) {
+        /* Warp w issues from scheduler w & 3.  Keeping the warps of one scheduler in one task class keeps that scheduler's instruction cache on one
+         * code region: schedulers 0-1 take the ODE node items, scheduler 2 the soil-water node items, scheduler 3 the single-lane tasks; a warp whose
+         * class has nothing on offer falls back to the general rule above. */
+        const int cls = warp & 3;
+        if (cls <= 1) {
+            int bt = -1, bn = 0;
+            for (int t = T0_COND; t <= T0_HOIST; t++) { const int cnt = (mca_popc(m0[t][0]) + mca_popc(m0[t][1])) * async_items(t, N); if (cnt > bn) { bn = cnt; bt = t; } }
+            if (bt >= 0) { best0 = bt; take0 = true; }
+        } else if (cls == 2) {
+            int bt = -1, bn = 0;
+            for (int t = T0_MU; t <= T0_MF; t++) { const int cnt = (mca_popc(m0[t][0]) + mca_popc(m0[t][1])) * async_items(t, N); if (cnt > bn) { bn = cnt; bt = t; } }
+            if (bt >= 0) { best0 = bt; take0 = true; }
+        } else if (best1 >= 0) take0 = false;
+    }
     if (take0) {
         const int t = best0, n = async_items(t, N);
         int got = 0;
@@ -1110,14 +1126,14 @@ MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, i
         AsyncClaim c;
 #if defined(__CUDACC__)
         const int lane = threadIdx.x & 31;
-        if (lane == 0) c = async_try_claim(B, salt);
+        if (lane == 0) c = async_try_claim(B, salt, warp);
         c.chan = __shfl_sync(0xffffffffu, c.chan, 0); c.type = __shfl_sync(0xffffffffu, c.type, 0); c.total = __shfl_sync(0xffffffffu, c.total, 0);
         c.nseg = __shfl_sync(0xffffffffu, c.nseg, 0);
         c.seg[0] = __shfl_sync(0xffffffffu, c.seg[0], 0); c.seg[1] = __shfl_sync(0xffffffffu, c.seg[1], 0);
         c.seg[2] = __shfl_sync(0xffffffffu, c.seg[2], 0); c.seg[3] = __shfl_sync(0xffffffffu, c.seg[3], 0);
         c.bits[0] = __shfl_sync(0xffffffffu, c.bits[0], 0); c.bits[1] = __shfl_sync(0xffffffffu, c.bits[1], 0);
 #else
-        c = async_try_claim(B, salt);
+        c = async_try_claim(B, salt, warp);
 #endif
         salt++;
         if (c.chan < 0) {
@@ -1195,7 +1211,7 @@ MC_DEV void async_worker(AsyncBlock<NA, SLOTS>& B, const KArgs& a, double* ga, i
 
 /* block set-up: every slot starts by asking for a site */
 template <int NA, int SLOTS>
-MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, int active_slots, int ser_min = 0)
+MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, int active_slots, int ser_min = 0, int affinity = 0)
 {
     const int n = active_slots <= 0 || active_slots > SLOTS ? SLOTS : active_slots;
     for (int o = tid; o < SLOTS; o += nthreads) { B.z(o).pc = o < n ? PC_LOAD : PC_DEAD; B.req0[o] = 0; B.pend[o] = 0; }
@@ -1206,7 +1222,7 @@ MC_DEV void async_block_init(AsyncBlock<NA, SLOTS>& B, int tid, int nthreads, in
         B.mask1[T1_SITE][1] = n > 32 ? (n >= 64 ? 0xffffffffu : ((1u << (n - 32)) - 1u)) : 0u;
         B.alive = n;
         B.ser_min = ser_min > 0 ? ser_min : MCA_LANES / 4;
-        B.abort = 0;
+        B.abort = 0; B.affinity = affinity;
         B.nreq = n;                                                        /* the initial SITE requests */
     }
 }

@@ -165,6 +165,7 @@ struct KArgs {
     unsigned long long* next_site;  /* asynchronous kernel: the launch's site cursor (slots take their next site from it) */
     int32_t async_slots;            /* asynchronous kernel: slots a block activates (fewer than its capacity when the range is small, so that every SM gets sites) */
     int32_t async_ser_min;          /* asynchronous kernel: single-lane tasks of one type that must be waiting before a warp prefers them to node items */
+    int32_t async_affinity;         /* asynchronous kernel: 1 = warps prefer one task class per scheduler (instruction-cache locality) */
     int32_t async_idle_ns;          /* asynchronous kernel: sleep of a warp that found nothing to claim */
     unsigned long long* async_stats;/* asynchronous kernel: [MCA_STATS] work census (claims, items, cycles per task type; idle polls), or NULL */
 };

@@ -72,10 +72,11 @@ void run_async(mcd::KArgs a, int nwarps, int grid, unsigned long long* counters)
     a.next_site = &cursor; a.counters = cnt;
     a.async_stats = getenv("MC_ASYNC_STATS") ? g_async_stats : nullptr;
     { const char* e = getenv("MC_ASYNC_SERMIN"); a.async_ser_min = e ? atoi(e) : 0; }
+    { const char* e = getenv("MC_ASYNC_AFFINITY"); a.async_affinity = e ? atoi(e) : 0; }
     std::vector<Blk*> blocks; std::vector<std::vector<double>> scr;
     for (int b = 0; b < grid; b++) {
         Blk* B = new Blk(); std::memset(B, 0, sizeof(Blk));
-        for (int t = 0; t < HE_SLOTS; t++) mcd::async_block_init<NA, HE_SLOTS>(*B, t, HE_SLOTS, a.async_slots, a.async_ser_min);
+        for (int t = 0; t < HE_SLOTS; t++) mcd::async_block_init<NA, HE_SLOTS>(*B, t, HE_SLOTS, a.async_slots, a.async_ser_min, a.async_affinity);
         blocks.push_back(B); scr.emplace_back((size_t)mcd::G_ARRAYS * NA * HE_SLOTS, 0.0);
     }
 #ifdef MC_HOST_THREADS

@@ -28,13 +28,14 @@ torch.cuda.synchronize()
 os.environ["MC_ASYNC_STATS"] = "1"
 ref = None
 for cfg in (sys.argv[1:] or ["1024 64 8"]):
-    for k in ("MC_KERNEL", "MC_ASYNC_THREADS", "MC_ASYNC_SLOTS", "MC_ASYNC_SERMIN"):
+    for k in ("MC_KERNEL", "MC_ASYNC_THREADS", "MC_ASYNC_SLOTS", "MC_ASYNC_SERMIN", "MC_ASYNC_AFFINITY"):
         os.environ.pop(k, None)
     if cfg in ("coop", "legacy"):
         os.environ["MC_KERNEL"] = cfg
     else:
-        th, sl, sm = cfg.split()
+        th, sl, sm, *rest = cfg.split()
         os.environ["MC_ASYNC_THREADS"], os.environ["MC_ASYNC_SLOTS"], os.environ["MC_ASYNC_SERMIN"] = th, sl, sm
+        os.environ["MC_ASYNC_AFFINITY"] = rest[0] if rest else "0"
     eng = SoilEngine(desc, S)
     eng.set_sites(sites)
     ms = []
@@ -45,7 +46,7 @@ for cfg in (sys.argv[1:] or ["1024 64 8"]):
     chk = float(out["soil_temperature"].sum().item())
     if ref is None:
         ref = chk
-    print(f"== {cfg:14s} ms/day {' '.join('%.1f' % x for x in ms)}  -> {S / (ms[-1] * 1e-3):9.0f} site-days/s  checksum {'same' if chk == ref else 'DIFFERENT'}", flush=True)
+    print(f"== {os.path.basename(os.environ.get('MC_LIB', 'default'))} {cfg:14s} ms/day {' '.join('%.1f' % x for x in ms)}  -> {S / (ms[-1] * 1e-3):9.0f} site-days/s  checksum {'same' if chk == ref else 'DIFFERENT'}", flush=True)
     if cfg not in ("coop", "legacy"):
         buf = (C.c_ulonglong * 64)()
         n = eng._L.mc_get_async_stats(eng.h, buf, 64)
