@@ -168,10 +168,10 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
     int nbad = 0;
     /* same kernel selection as launch_range(): the block-cooperative path (here a "block" of one thread) for NoSnow + FixedIterations */
     const char* kenv = getenv("MC_KERNEL");
-    const bool legacy = kenv && std::strcmp(kenv, "legacy") == 0, force_coop = kenv && std::strcmp(kenv, "coop") == 0;
+    const bool legacy = kenv && std::strcmp(kenv, "legacy") == 0, want_async = kenv && std::strcmp(kenv, "async") == 0;
     const bool coop = !legacy && e->model.n_snow == 0 && mcd::g_model_h.conv_kind == MC_CONV_FIXED;
-    /* same kernel selection as launch_range(): the asynchronous kernel for every NoSnow model with the water-potential infiltration form */
-    if (!legacy && !force_coop && e->model.n_snow == 0 && !mcd::g_model_h.flux_alg) {
+    /* same kernel selection as launch_range(): the asynchronous kernel is opt-in (MC_KERNEL=async), for NoSnow models with the water-potential infiltration form */
+    if (want_async && e->model.n_snow == 0 && !mcd::g_model_h.flux_alg) {
         const char* we = getenv("HE_WARPS"); const int nwarps = we ? atoi(we) : 3;
         const char* ge = getenv("HE_GRID"); const int grid = ge && atoi(ge) > 0 ? atoi(ge) : 2;
         if (e->N <= 10) run_async<10>(a, nwarps, grid, e->counters); else if (e->N <= 19) run_async<19>(a, nwarps, grid, e->counters); else run_async<MC_MAX_SOIL_NODES>(a, nwarps, grid, e->counters);

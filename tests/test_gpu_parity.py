@@ -261,7 +261,6 @@ def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     desc, sites, forcing = synth
     f = ("soil_temperature", "soil_moisture", "surface_water", "soil_water_potential")
     ref, eo = parity.run(OracleEngine, desc, sites, forcing, fields=f)
-    monkeypatch.setenv("MC_KERNEL", "coop")                     # the block-synchronous cooperative kernel (round 1; the default is the asynchronous one)
     monkeypatch.setenv("MC_COOP_BLOCK", "1024")                 # one ragged block: 512 sites + 512 mirror threads
     a, ea = parity.run(SoilEngine, desc, sites, forcing, fields=f)
     parity.assert_bit_identical(a, ref, f)
@@ -271,18 +270,27 @@ def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     b, eb = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
     for name in f:
         assert np.array_equal(getattr(b, name), getattr(ref, name)[..., :509]), name
+    monkeypatch.setenv("MC_COOP_INTERLEAVE", "1")               # warp-interleaved site batches (32-site groups from all over the range), ragged tail
+    b2, _ = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
+    for name in f:
+        assert np.array_equal(getattr(b2, name), getattr(ref, name)[..., :509]), name
     monkeypatch.delenv("MC_COOP_BLOCK"); monkeypatch.delenv("MC_COOP_GRID")
+    b3, eb3 = parity.run(SoilEngine, desc, sites, forcing, fields=f)
+    parity.assert_bit_identical(b3, ref, f)
+    assert eb3.counters()["n_rhs"] == eo.counters()["n_rhs"]
+    monkeypatch.delenv("MC_COOP_INTERLEAVE")
     monkeypatch.setenv("MC_KERNEL", "legacy")                   # the per-site kernel (what snow / flux-potential models run)
     c, ec = parity.run(SoilEngine, desc, sites, forcing, fields=f)
     parity.assert_bit_identical(c, ref, f)
     monkeypatch.delenv("MC_KERNEL")
-    # the asynchronous kernel under odd shapes: 3 blocks x 5 slots x 96 threads (passes claimed in pieces, slots reloaded many times), then one block
-    for grid, slots, threads in (("3", "5", "96"), ("1", "64", "1024")):
+    # the opt-in asynchronous kernel under odd shapes: 3 blocks x 5 slots x 96 threads (passes claimed in pieces, slots reloaded many times), one full block, defaults
+    monkeypatch.setenv("MC_KERNEL", "async")
+    for grid, slots, threads in (("3", "5", "96"), ("1", "64", "1024"), ("148", "64", "1024")):
         monkeypatch.setenv("MC_ASYNC_GRID", grid); monkeypatch.setenv("MC_ASYNC_SLOTS", slots); monkeypatch.setenv("MC_ASYNC_THREADS", threads)
         d, ed = parity.run(SoilEngine, desc, sites.slice(0, 203), forcing.site_slice(0, 203), fields=f)
         for name in f:
             assert np.array_equal(getattr(d, name), getattr(ref, name)[..., :203]), name
-    monkeypatch.delenv("MC_ASYNC_GRID"); monkeypatch.delenv("MC_ASYNC_SLOTS"); monkeypatch.delenv("MC_ASYNC_THREADS")
+    monkeypatch.delenv("MC_ASYNC_GRID"); monkeypatch.delenv("MC_ASYNC_SLOTS"); monkeypatch.delenv("MC_ASYNC_THREADS"); monkeypatch.delenv("MC_KERNEL")
 
 
 def test_solve_air_matches_oracle(SoilEngine):
@@ -445,3 +453,24 @@ def test_config4_scan329_full_year_matches_oracle(SoilEngine):
     # the reference's usual NicheMapR bar on the CUDA output itself
     T, G = out.soil_temperature[:, ::2, 0], g["soil_nmr"].astype(float)
     assert np.abs(T / G - 1).max() < 1e-1 and np.corrcoef(out.snow_depth[:, 0], g["SNOWDEP"].astype(float))[0, 1] > 0.85
+
+
+@pytest.mark.parametrize("case", ["config1_monthly", "config2_daily", "tolerance", "synthetic"])
+def test_async_kernel_matches_oracle(SoilEngine, case, monkeypatch, synth):
+    """The opt-in asynchronous shared-memory-resident kernel (MC_KERNEL=async, mc_async.cuh): per-site state machines, node items and single-lane tasks
+    claimed by worker warps.  Same bits and counters as the oracle, incl. the per-site pass counts of the tolerance-based convergence."""
+    import microclimate_jl_b200 as mc
+    monkeypatch.setenv("MC_KERNEL", "async")
+    if case == "synthetic":
+        desc, sites, forcing = synth
+    else:
+        p = {"config1_monthly": lambda: configs.config1_monthly()[0], "config2_daily": lambda: configs.config2_daily(6)[0],
+             "tolerance": lambda: _variant(configs.config1_monthly()[0], convergence=mc.SoilTemperatureConvergenceTolerance(tolerance=0.5, max_iterations_per_day=6),
+                                           time_mode=mc.NonConsecutiveDayMode(iterations_per_day=6))}[case]()
+        desc, sites, forcing = _problem_buffers(p)
+    ref, eo = parity.run(OracleEngine, desc, sites, forcing)
+    out, eg = parity.run(SoilEngine, desc, sites, forcing)
+    parity.assert_bit_identical(out, ref)
+    co, cg = eo.counters(), eg.counters()
+    for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps", "n_day_passes"):
+        assert co[k] == cg[k], k

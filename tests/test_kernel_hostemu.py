@@ -147,7 +147,6 @@ def test_block_protocol_with_real_threads(defs, monkeypatch):
         LIB = hostemu_engine.variant("threads" + ("_cm" if defs else ""), ["-DMC_HOST_THREADS", "-std=c++20", "-pthread", *defs])
 
     monkeypatch.setenv("HE_TB", "8")
-    monkeypatch.setenv("MC_KERNEL", "coop")      # the block-synchronous cooperative kernel (the default is the asynchronous one, tested below)
     desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
     sites, forcing = syn.make_sites(0, 21, 21, with_sand=True), syn.make_forcing(0, 21, 21, 0, 2)      # 3 batches, the last one 5 sites + 3 mirrors
     ref, eo = parity.run(OracleEngine, desc, sites, forcing)
@@ -171,6 +170,7 @@ def test_async_protocol_with_real_threads(slots, lanes, monkeypatch):
         LIB = hostemu_engine.variant(f"async_{slots}_{lanes}", ["-DMC_HOST_THREADS", "-std=c++20", "-pthread", f"-DHE_SLOTS={slots}", f"-DMCA_LANES={lanes}"])
 
     AsyncEngine.LIB.he_async_runs.restype = C.c_longlong
+    monkeypatch.setenv("MC_KERNEL", "async")      # opt-in: the default NoSnow kernel is the block-synchronous cooperative one
     desc = M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode())
     sites, forcing = syn.make_sites(0, 29, 29, with_sand=True), syn.make_forcing(0, 29, 29, 0, 2)
     ref, eo = parity.run(OracleEngine, desc, sites, forcing, chunks=[1, 1])

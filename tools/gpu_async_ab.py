@@ -33,6 +33,7 @@ for cfg in (sys.argv[1:] or ["1024 64 8"]):
     if cfg in ("coop", "legacy"):
         os.environ["MC_KERNEL"] = cfg
     else:
+        os.environ["MC_KERNEL"] = "async"
         th, sl, sm, *rest = cfg.split()
         os.environ["MC_ASYNC_THREADS"], os.environ["MC_ASYNC_SLOTS"], os.environ["MC_ASYNC_SERMIN"] = th, sl, sm
         os.environ["MC_ASYNC_AFFINITY"] = rest[0] if rest else "0"
