@@ -90,18 +90,10 @@ __global__ void __launch_bounds__(mcd::COOP_TB, MC_COOP_MIN_BLOCKS) soil_chunk_c
     __syncthreads();
     mcd::Counters cn = {};
     double* scr = a.coop_scr + (size_t)blockIdx.x * (MC_COOP_ROWS(NA) * blockDim.x);
-    /* site batches of the block.  Contiguous (batch b = sites [b TB, (b+1) TB)), or warp-interleaved: the range is cut into groups of 32 consecutive sites
-     * (one coalesced 256-byte request per array row) and warp w of batch b takes group w * nbatch + b, so that every block sees the whole range's mix of
-     * sites and a cluster of slow neighbouring sites (Newton solves that run to their cap) is spread over many blocks instead of stalling one. */
-    const int64_t n_sites = a.s_end - a.s_begin;
-    const int64_t nbatch = (n_sites + blockDim.x - 1) / blockDim.x;
-    const int64_t ngroups = (n_sites + 31) / 32;
-    for (int64_t bb = blockIdx.x; bb < nbatch; bb += gridDim.x) {
-        int64_t s;
-        if (a.coop_interleave) {
-            const int64_t g = (int64_t)(threadIdx.x >> 5) * nbatch + bb;
-            s = g < ngroups ? a.s_begin + g * 32 + (threadIdx.x & 31) : a.s_end;
-        } else s = a.s_begin + bb * blockDim.x + threadIdx.x;
+    /* contiguous site batches (a warp-interleaved assignment that gives every block the whole range's mix of sites was measured 12 % slower: blocks
+     * of neighbouring, climatically similar sites need fewer rounds per hour, profiles/README.md) */
+    for (int64_t base = a.s_begin + (int64_t)blockIdx.x * blockDim.x; base < a.s_end; base += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = base + threadIdx.x;
         const bool valid = s < a.s_end;
         if (!valid) s = a.s_end - 1;
         mcd::Counters c1 = {};
@@ -310,7 +302,6 @@ static int launch_chunk_coop(mc_handle* h, mcd::KArgs& a, cudaStream_t st)
         h->coop_scr_doubles = need;
     }
     a.coop_scr = h->coop_scr;
-    { const char* e = getenv("MC_COOP_INTERLEAVE"); a.coop_interleave = e ? atoi(e) : 0; }
     soil_chunk_coop_kernel<NA><<<grid, TB, 0, st>>>(a);
     MC_CUDA(h, cudaGetLastError());
     return 0;

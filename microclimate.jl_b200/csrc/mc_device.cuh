@@ -160,7 +160,6 @@ struct KArgs {
     double *L_air;                                        /* [S] Obukhov warm start of the air-profile buffer */
     int32_t n_snow;
     unsigned long long* counters;   /* [8]: rhs, accept, reject, obukhov, newton, infil, day_passes, spare */
-    int32_t coop_interleave;        /* cooperative kernel: 1 = a block's warps take 32-site groups from all over the range (spreads slow sites over blocks) */
     double* coop_scr;               /* block-cooperative kernel: per-block scratch [block][SCR_ARRAYS][NA][block threads] */
     double* async_scr;              /* asynchronous kernel: per-block L2-resident scratch [block][G_ARRAYS][NA][SLOTS] (site constants, hourly / daily copies) */
     unsigned long long* next_site;  /* asynchronous kernel: the launch's site cursor (slots take their next site from it) */

@@ -270,15 +270,7 @@ def test_cooperative_kernel_block_shapes(SoilEngine, synth, monkeypatch):
     b, eb = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
     for name in f:
         assert np.array_equal(getattr(b, name), getattr(ref, name)[..., :509]), name
-    monkeypatch.setenv("MC_COOP_INTERLEAVE", "1")               # warp-interleaved site batches (32-site groups from all over the range), ragged tail
-    b2, _ = parity.run(SoilEngine, desc, sites.slice(0, 509), forcing.site_slice(0, 509), fields=f)
-    for name in f:
-        assert np.array_equal(getattr(b2, name), getattr(ref, name)[..., :509]), name
     monkeypatch.delenv("MC_COOP_BLOCK"); monkeypatch.delenv("MC_COOP_GRID")
-    b3, eb3 = parity.run(SoilEngine, desc, sites, forcing, fields=f)
-    parity.assert_bit_identical(b3, ref, f)
-    assert eb3.counters()["n_rhs"] == eo.counters()["n_rhs"]
-    monkeypatch.delenv("MC_COOP_INTERLEAVE")
     monkeypatch.setenv("MC_KERNEL", "legacy")                   # the per-site kernel (what snow / flux-potential models run)
     c, ec = parity.run(SoilEngine, desc, sites, forcing, fields=f)
     parity.assert_bit_identical(c, ref, f)
