@@ -54,15 +54,43 @@ def walg_per_site_day(counters, site_days):
     return sum(parts.values()), parts
 
 
+def kernel_sass_hash(name="soil_chunk_coop_kernelILi19E"):
+    """Identity of the compiled soil kernel itself: hash of its SASS (instruction text + encodings) from `cuobjdump -sass` of the built library.
+    Unlike library_hash() it survives edits that do not change the kernel's machine code (new entry points, other translation units)."""
+    import hashlib
+    import re
+    import shutil
+    from microclimate_jl_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        txt = subprocess.run([exe, "-sass", _lib.SO], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    h, on, n = hashlib.sha256(), False, 0
+    for l in txt.split("\n"):
+        m = re.match(r"\s*Function : (\S+)", l)
+        if m:
+            on = name in m.group(1)
+            continue
+        if on and re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
+            h.update(l.strip().encode())
+            n += 1
+    return h.hexdigest()[:16] if n else None
+
+
 def calibrated_traffic():
-    """DRAM bytes and executed FP64 flops per site-day from the ncu capture of THIS build (tools/gpu_profile.py writes profiles/traffic.json with the
-    library hash); a capture of another build is refused."""
+    """DRAM bytes and executed FP64 flops per site-day from the ncu capture of THIS kernel build (tools/ncu_traffic.py writes profiles/traffic.json with the
+    library's source hash and the kernel's SASS hash); a capture of another build is refused.  Valid when either identity matches: the source hash
+    (nothing changed) or the SASS hash of soil_chunk_coop_kernel<19> (sources changed elsewhere, the kernel's machine code did not)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         t = json.load(f)
-    t["stale"] = t.get("library_hash") != library_hash()
+    t["matched_by"] = "library_hash" if t.get("library_hash") == library_hash() else None
+    if t["matched_by"] is None and t.get("kernel_sass_hash") and t["kernel_sass_hash"] == kernel_sass_hash():
+        t["matched_by"] = "kernel_sass_hash"
+    t["stale"] = t["matched_by"] is None
     return t
 
 
@@ -293,6 +321,7 @@ def main():
             "executed_flop_per_site_day": exe, "achieved_executed": (exe * per_gpu / 1e12) if exe else None, "frac_executed": (exe * per_gpu / 1e12 / peak_tf) if exe else None,
             "traffic": (cal["dram_bytes_per_site_day"] * S) if cal and not cal["stale"] else None,
             "traffic_build_hash": cal.get("library_hash") if cal else None, "library_hash": library_hash(),
+            "traffic_kernel_sass_hash": cal.get("kernel_sass_hash") if cal else None, "traffic_matched_by": cal.get("matched_by") if cal else None,
             "traffic_how": ("DRAM bytes per launch (one launch = one step of %d site-days per GPU) from the ncu capture of this build (profiles/traffic.json)" % S) if cal and not cal["stale"]
                            else "no ncu capture of this build (profiles/traffic.json absent or taken on another build): null rather than a stale number",
             "hbm": {"achieved": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9, "peak": 6536.0, "unit": "GB/s", "frac": ALG_BYTES_PER_SITE_DAY * per_gpu / 1e9 / 6536.0,

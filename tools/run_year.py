@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--days", type=int, default=365)
     ap.add_argument("--chunk", type=int, default=1, help="days per kernel launch")
     ap.add_argument("--spot", type=int, default=64, help="spot-check sites over the whole grid (0 = none)")
+    ap.add_argument("--spot-budget-s", type=float, default=240.0, help="wall-clock bound of the CPU spot check per rank (sites not reached are reported as skipped)")
     ap.add_argument("--with-sand", action="store_true")
     ap.add_argument("--out", default="gpurun_out/year")
     args = ap.parse_args()
@@ -40,7 +41,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        import datetime
         dist.init_process_group("nccl", device_id=dev)
+        # the result gather is host-side pickles after a CPU spot check that may take minutes on some ranks: its own gloo group with a long timeout,
+        # so that a slow rank cannot run into NCCL's 10-minute watchdog (the first 8-GPU year run lost its summary exactly there)
+        host_pg = dist.new_group(backend="gloo", timeout=datetime.timedelta(hours=2))
     S_total, D, C = args.sites, args.days, args.chunk
     lo, hi = site_shards(S_total, world)[rank]
     S = hi - lo
@@ -49,6 +54,8 @@ def main():
     eng = SoilEngine(desc, S, device=local_rank)
     eng.set_sites(syn.make_sites(lo, hi, S_total, with_sand=args.with_sand))
     gen = sd.DeviceForcing(lo, hi, S_total, C, dev)
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    open(f"{args.out}_rank{rank}_trace.jsonl", "w").close()
     out_dev = {f: torch.zeros((24 * C, N, S), dtype=torch.float64, device=dev) for f in ("soil_temperature", "soil_moisture")}
     optr = {f: t.data_ptr() for f, t in out_dev.items()}
     # spot-check sites: spread over the whole grid, each rank keeps the ones in its shard
@@ -77,6 +84,8 @@ def main():
         st = eng.status()
         by_bit = {STATUS_BITS[b]: int(((st & b) != 0).sum()) for b in bits_names}
         trace.append({"day0": d, "days": c, "gpu_ms": ms, "wall_s": wall, "flagged": int((st != 0).sum()), "by_bit": by_bit})
+        with open(f"{args.out}_rank{rank}_trace.jsonl", "a") as tf:      # incremental: a cut-off run keeps what it measured
+            tf.write(json.dumps(trace[-1]) + "\n")
         if len(spot):
             spot_T.append(out_dev["soil_temperature"][:24 * c].index_select(2, spot_idx).cpu().numpy())
             spot_th.append(out_dev["soil_moisture"][:24 * c].index_select(2, spot_idx).cpu().numpy())
@@ -90,11 +99,15 @@ def main():
     counters = eng.counters()
     # spot check against the oracle, from the very forcing the device used
     worst_T = worst_th = 0.0
+    spot_done = 0
+    t_spot = time.perf_counter()
     if len(spot):
         from oracle.oracle import OracleEngine
         T_dev, th_dev = np.concatenate(spot_T, axis=0), np.concatenate(spot_th, axis=0)
         sites_all = syn.make_sites(lo, hi, S_total, with_sand=args.with_sand)
         for k, s in enumerate(spot):
+            if time.perf_counter() - t_spot > args.spot_budget_s:      # a site whose Newton solves run to the cap costs the CPU ~200x a normal one
+                break
             o = OracleEngine(desc, 1)
             o.set_sites(sites_all.slice(int(s), int(s) + 1))
             d0 = 0
@@ -108,11 +121,12 @@ def main():
                 d0 += fb.ndays
             worst_T = max(worst_T, float(np.abs(np.concatenate(rows_T) - T_dev[:, :, k]).max()))
             worst_th = max(worst_th, float(np.abs(np.concatenate(rows_th) - th_dev[:, :, k]).max()))
-    mine = {"rank": rank, "sites": S, "device_s": dev_s, "wall_s": run_wall, "trace": trace, "spot_sites": int(len(spot)), "spot_max_dT": worst_T,
+            spot_done += 1
+    mine = {"rank": rank, "sites": S, "device_s": dev_s, "wall_s": run_wall, "trace": trace, "spot_sites": int(spot_done), "spot_sites_planned": int(len(spot)), "spot_max_dT": worst_T,
             "spot_max_dtheta": worst_th, "counters": {k: int(v) for k, v in counters.items() if k.startswith("n_")}}
     if world > 1:
         gathered = [None] * world
-        dist.all_gather_object(gathered, mine)
+        dist.all_gather_object(gathered, mine, group=host_pg)
     else:
         gathered = [mine]
     if rank == 0:
@@ -129,7 +143,7 @@ def main():
                    "chunk_ms_median": med, "chunk_ms_max": max(per_chunk_max), "slowest_chunk_over_median": max(per_chunk_max) / med,
                    "chunks_slower_than_1p10_median": int(sum(1 for x in per_chunk_max if x > 1.10 * med)),
                    "flagged_by_bit_final": flagged_last, "flagged_final": sum(g["trace"][-1]["flagged"] for g in gathered),
-                   "spot_check": {"sites": sum(g["spot_sites"] for g in gathered), "days": D, "max_abs_dT_K": max(g["spot_max_dT"] for g in gathered),
+                   "spot_check": {"sites": sum(g["spot_sites"] for g in gathered), "sites_planned": sum(g["spot_sites_planned"] for g in gathered), "days": D, "max_abs_dT_K": max(g["spot_max_dT"] for g in gathered),
                                   "max_abs_dtheta": max(g["spot_max_dtheta"] for g in gathered)},
                    "work_per_site_day": {k: sum(g["counters"][k] for g in gathered) / (S_total * D) for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps")}}
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
