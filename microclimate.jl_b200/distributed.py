@@ -19,22 +19,27 @@ def run_shard(engine_factory: Callable, desc, sites: M.SitesBatch, forcing: M.Fo
               fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS, chunk_days: Optional[int] = None):
     """Integrate this rank's contiguous shard of a batch that every rank can see (or regenerate)."""
     lo, hi = site_shards(sites.S, world)[rank]
-    out = M.OutputBatch(forcing.ndays, desc.n_soil, hi - lo, fields, desc.n_snow)
+    out = M.OutputBatch(forcing.ndays, desc.n_soil, hi - lo, fields, desc.n_snow, desc.n_heights)
     if hi == lo:
         return out, (lo, hi)
     eng = engine_factory(desc, hi - lo)
-    eng.set_sites(sites.slice(lo, hi))
-    f = forcing.site_slice(lo, hi)
-    if not chunk_days:
-        eng.step_days(0, f, out)
-    else:
-        d0 = 0
-        while d0 < forcing.ndays:
-            d1 = min(forcing.ndays, d0 + chunk_days)
-            part = M.OutputBatch(d1 - d0, desc.n_soil, hi - lo, fields, desc.n_snow)
-            eng.step_days(d0, f.day_slice(d0, d1), part)
-            out.assign_rows(24 * d0, part)
-            d0 = d1
+    try:
+        eng.set_sites(sites.slice(lo, hi))
+        f = forcing.site_slice(lo, hi)
+        if not chunk_days:
+            eng.step_days(0, f, out)
+        else:
+            d0 = 0
+            while d0 < forcing.ndays:
+                d1 = min(forcing.ndays, d0 + chunk_days)
+                part = M.OutputBatch(d1 - d0, desc.n_soil, hi - lo, fields, desc.n_snow, desc.n_heights)
+                eng.step_days(d0, f.day_slice(d0, d1), part)
+                out.assign_rows(24 * d0, part)
+                d0 = d1
+    finally:
+        close = getattr(eng, "close", None)
+        if close:
+            close()
     return out, (lo, hi)
 
 
@@ -46,8 +51,14 @@ def gather_outputs(local: M.OutputBatch, n_sites_total: int, group=None, dst: in
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     shards = site_shards(n_sites_total, world)
     width = max(hi - lo for lo, hi in shards)
-    fields = [f for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS if getattr(local, f) is not None]
-    full = M.OutputBatch(local.ndays, local.N, n_sites_total, fields) if rank == dst else None
+    # every selected array travels: node fields, scalars, the snow temperature profile and the solve_air! profile fields
+    fields = [f for f in A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS + ("snow_temperature",) + A.OUTPUT_PROFILE_FIELDS + A.OUTPUT_PROFILE_SCALARS
+              if getattr(local, f, None) is not None]
+    n_snow = 0 if local.snow_temperature is None else local.snow_temperature.shape[1]
+    n_heights = max([getattr(local, f).shape[1] for f in A.OUTPUT_PROFILE_FIELDS if getattr(local, f, None) is not None], default=0)
+    if n_heights == 0 and any(getattr(local, f, None) is not None for f in A.OUTPUT_PROFILE_SCALARS):
+        n_heights = 1          # profile scalars only: OutputBatch allocates them whenever heights exist
+    full = M.OutputBatch(local.ndays, local.N, n_sites_total, fields, n_snow, n_heights) if rank == dst else None
 
     def padded(a):
         t = torch.zeros(a.shape[:-1] + (width,), dtype=torch.float64)

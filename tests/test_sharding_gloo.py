@@ -58,3 +58,57 @@ def test_two_rank_sharded_run_equals_single_process():
         assert np.array_equal(got["th"], ref.soil_moisture)
         assert np.array_equal(got["pool"], ref.surface_water)
         assert np.array_equal(got["status"], ref.status)
+
+
+def _snow_air_problem(S=3):
+    """Config-1-with-snow model (8 snow nodes) with four air heights, replicated over S sites whose air temperature is shifted site by site."""
+    import copy
+    import configs
+    from microclimate_jl_b200 import marshal as M
+    p, _ = configs.config1_monthly(snow=True)
+    p = copy.deepcopy(p)
+    p.model.heights = np.array([0.002, 0.01, 0.5, 2.0])
+    inputs = []
+    for s in range(S):
+        i = copy.deepcopy(p.inputs)
+        i.environment_hourly.reference_temperature = i.environment_hourly.reference_temperature - 1.5 * s
+        inputs.append(i)
+    desc = M.model_desc(p.model, p.time_mode, inputs0=inputs[0])
+    return desc, M.SitesBatch.from_inputs(p.model, inputs), M.ForcingBatch.from_inputs(p.model, inputs, p.days[:2])
+
+
+def _worker_snow_air(rank, world, port, path):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    import parity
+    from hostemu_engine import HostEmuEngine
+    from microclimate_jl_b200 import distributed as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    desc, sites, forcing = _snow_air_problem()
+    f = parity.ALL_FIELDS + parity.SNOW_FIELDS + parity.AIR_FIELDS
+    local, _ = D.run_shard(HostEmuEngine, desc, sites, forcing, rank, world, fields=f, chunk_days=1)
+    full = D.gather_outputs(local, sites.S)
+    if rank == 0:
+        np.savez(path, **{k: getattr(full, k) for k in f}, status=full.status)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_carries_snow_and_air_profile_outputs():
+    """the host gather used to drop snow_temperature and the solve_air! fields; every selected array must arrive on rank 0."""
+    from hostemu_engine import HostEmuEngine
+    import parity
+    desc, sites, forcing = _snow_air_problem()
+    f = parity.ALL_FIELDS + parity.SNOW_FIELDS + parity.AIR_FIELDS
+    assert desc.n_snow == 8 and desc.n_heights == 4 and "snow_temperature" in f and "air_temperature" in f
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.npz")
+        mp.spawn(_worker_snow_air, args=(2, _free_port(), path), nprocs=2, join=True)
+        got = np.load(path)
+        ref, _ = parity.run(HostEmuEngine, desc, sites, forcing, fields=f)
+        for k in f:
+            assert got[k].shape == getattr(ref, k).shape, k
+            assert np.array_equal(got[k], getattr(ref, k)), k
+        assert np.array_equal(got["status"], ref.status)
