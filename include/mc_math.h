@@ -304,5 +304,101 @@ MCM_FN double cos(double x)
 
 MCM_FN double pow4(double x) { const double x2 = x * x; return x2 * x2; }
 
+/* ---- sin / cos for |x| <= 64 (solar geometry: day angles <= 2 pi * 366/365, hour angles in [-pi, pi]) ------------------------
+ * One Cody-Waite reduction by n * pi/2 with the two-word split of fdlibm's e_rem_pio2.c (first iteration): n * pio2_1 is exact for
+ * |n| < 2^20 (pio2_1 has 33 significant bits), the tail is carried as y1.  Outside the range: NaN on purpose. */
+MCM_FN int rem_pio2_small(double x, double* y0, double* y1)
+{
+    const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+    const double fn = rne(x * invpio2);
+    const double r = x - fn * pio2_1;
+    const double w = fn * pio2_1t;
+    *y0 = r - w;
+    *y1 = (r - *y0) - w;
+    return (int)fn;
+}
+MCM_FN double sin_r(double x)
+{
+    const double ax = x < 0.0 ? -x : x;
+    if (!(ax <= 64.0)) return u2d(0x7ff8000000000000ULL);
+    if (ax <= 0.78539816339744830962) return kernel_sin(x, 0.0);
+    double y0, y1;
+    const int n = rem_pio2_small(x, &y0, &y1) & 3;
+    const double a0 = y0 < 0.0 ? -y0 : y0, a1 = y0 < 0.0 ? -y1 : y1;     /* kernel_cos wants a non-negative argument */
+    if (n == 0) return kernel_sin(y0, y1);
+    if (n == 1) return kernel_cos(a0, a1);
+    if (n == 2) return -kernel_sin(y0, y1);
+    return -kernel_cos(a0, a1);
+}
+MCM_FN double cos_r(double x)
+{
+    const double ax = x < 0.0 ? -x : x;
+    if (!(ax <= 64.0)) return u2d(0x7ff8000000000000ULL);
+    if (ax <= 0.78539816339744830962) return kernel_cos(ax, 0.0);
+    double y0, y1;
+    const int n = rem_pio2_small(x, &y0, &y1) & 3;
+    const double a0 = y0 < 0.0 ? -y0 : y0, a1 = y0 < 0.0 ? -y1 : y1;
+    if (n == 0) return kernel_cos(a0, a1);
+    if (n == 1) return -kernel_sin(y0, y1);
+    if (n == 2) return -kernel_cos(a0, a1);
+    return kernel_sin(y0, y1);
+}
+/* sine / cosine of an angle in DEGREES, |deg| <= 720 (Julia's sind / cosd are exact at multiples of 90: so are these) */
+MCM_FN void sincosd(double deg, double* s, double* c)
+{
+    double d = deg;
+    while (d >= 360.0) d -= 360.0;                  /* exact: Sterbenz / small integers times 360 */
+    while (d < 0.0) d += 360.0;
+    int q = 0;                                      /* d = 90 q + r, r in [-45, 45] */
+    if (d > 315.0) { d -= 360.0; }
+    else if (d > 225.0) { d -= 270.0; q = 3; }
+    else if (d > 135.0) { d -= 180.0; q = 2; }
+    else if (d > 45.0) { d -= 90.0; q = 1; }
+    const double r = d * 1.74532925199432957692e-02;        /* pi / 180 */
+    const double sr = kernel_sin(r, 0.0), cr = kernel_cos(r < 0.0 ? -r : r, 0.0);
+    if (q == 0) { *s = sr; *c = cr; }
+    else if (q == 1) { *s = cr; *c = -sr; }
+    else if (q == 2) { *s = -sr; *c = -cr; }
+    else { *s = -cr; *c = sr; }
+}
+
+/* ---- acos (fdlibm e_acos.c, restated) ---------------------------------------------------------------------------------------- */
+MCM_FN double acos_rational(double z)
+{
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+                 pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+                 qS4 = 7.70381505559019352791e-02;
+    const double p = z * ffma(z, ffma(z, ffma(z, ffma(z, ffma(z, pS5, pS4), pS3), pS2), pS1), pS0);
+    const double q = ffma(z, ffma(z, ffma(z, ffma(z, qS4, qS3), qS2), qS1), 1.0);
+    return p / q;
+}
+MCM_FN double acos(double x)
+{
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17, pi = 3.14159265358979311600e+00;
+    const double ax = x < 0.0 ? -x : x;
+    if (!(ax <= 1.0)) return u2d(0x7ff8000000000000ULL);
+    if (ax == 1.0) return x > 0.0 ? 0.0 : pi + 2.0 * pio2_lo;
+    if (ax < 0.5) {
+        if (ax <= 5.5511151231257827e-17) return pio2_hi + pio2_lo;         /* |x| <= 2^-54 */
+        const double r = acos_rational(x * x);
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (x < 0.0) {                                  /* x <= -0.5 */
+        const double z = (1.0 + x) * 0.5;
+        const double s = sqrt(z);
+        const double r = acos_rational(z);
+        const double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    }
+    const double z = (1.0 - x) * 0.5;               /* x >= 0.5 */
+    const double s = sqrt(z);
+    const double df = u2d(d2u(s) & 0xffffffff00000000ULL);
+    const double c = (z - df * df) / (s + df);
+    const double r = acos_rational(z);
+    const double w = r * s + c;
+    return 2.0 * (df + w);
+}
+
 }  // namespace mcm
 #endif /* MC_MATH_H */

@@ -338,6 +338,118 @@ int  mc_multi_step_days(mc_multi* m, int64_t day0, int32_t ndays, const mc_forci
 int  mc_multi_step_days_async(mc_multi* m, int64_t day0, int32_t ndays, const mc_forcing_soa* forcing, mc_output_soa* out);
 int  mc_multi_wait(mc_multi* m);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * Widening: populate_weather! and the solar geometry it needs, on the device.
+ *
+ * Replaces, for S sites at once, what solve! does between init and solve_soil! (reference src/simulation.jl:20-36, 291-352):
+ *     solve_solar!  -> zenith / slope-zenith angle per hour, solar noon and sunrise hour angle per day   (geometry only, see below)
+ *     interpolate_minmax! -> the declarative diel engine of src/inputs/diel.jl (DielCurve of Sine / Decay / Linear shapes over
+ *                            Sunrise / Sunset / Midday / Midnight / ClockTime anchors, seam heights handed off between shapes)
+ *     adjust_for_cloud_cover! -> AngstromMaxwellShortwave + ErbsDiffuseFraction (src/radiation/shortwave/angstrom_maxwell.jl:21-46,
+ *                            src/radiation/diffuse/erbs.jl:14-23, src/radiation/sunshine_fraction/angstrom.jl:8-14)
+ * The hourly arrays it writes are exactly the hourly members of mc_forcing_soa, in the same [24*ndays][S] layout, so a min/max-driven
+ * run ships ~60 doubles per site-day to the GPU instead of 223 (mc_step_days_minmax).
+ *
+ * Solar geometry lives in the un-vendored SolarRadiation.jl (reference Project.toml; call at src/simulation.jl:291-304).  The geometry
+ * restated here is the published McCullough & Porter (1971) form NicheMapR's SOLRAD uses, anchored on the reference's golden ZEN columns
+ * (tests/test_weather.py: three data sets, <= 3e-6 degrees).  The spectral clear-sky model (111 wavelengths with ozone / aerosol /
+ * water-vapour tables) cannot be restated without its source: clear-sky direct and diffuse horizontal irradiance stay CALLER-SUPPLIED
+ * hourly arrays (SolarRadiation.solar_radiation!'s `direct_horizontal`, `diffuse_horizontal`).
+ * ---------------------------------------------------------------------------------------------------------------------------- */
+
+/* TimeOfDay (src/inputs/diel.jl:19-85): value = offset in hours for the solar events and Midnight, the clock hour for ClockTime */
+enum { MC_TOD_CLOCK = 0, MC_TOD_SUNRISE = 1, MC_TOD_SUNSET = 2, MC_TOD_MIDDAY = 3, MC_TOD_MIDNIGHT = 4 };
+typedef struct mc_time_of_day { int32_t kind; int32_t _pad; double value; } mc_time_of_day;
+/* Shape (src/inputs/diel.jl:98-150): Sine(trough, peak) fills whatever the bounded shapes leave; Decay / Linear(from, to) cover [from, to) */
+enum { MC_SHAPE_SINE = 0, MC_SHAPE_DECAY = 1, MC_SHAPE_LINEAR = 2 };
+typedef struct mc_diel_shape { int32_t kind; int32_t _pad; mc_time_of_day a, b; } mc_diel_shape;
+#define MC_DIEL_MAX_SHAPES 6
+#define MC_DIEL_MAX_INPUTS 6
+/* DielCurve (src/inputs/diel.jl:152-180): shapes + the times whose heights are fed from outside, in value-series order */
+typedef struct mc_diel_curve {
+    int32_t n_shapes, n_inputs;
+    mc_diel_shape shapes[MC_DIEL_MAX_SHAPES];
+    mc_time_of_day inputs[MC_DIEL_MAX_INPUTS];
+} mc_diel_curve;
+
+enum { MC_DIFFUSE_ERBS = 0 };                                    /* src/radiation/diffuse/erbs.jl */
+/* forcing model + shortwave model + geometry constants; mc_default_weather() = minmax_forcing_model() with its default offsets
+ * (src/inputs/diel.jl:456-495), AngstromMaxwellShortwave(), Angstrom(0.36, 0.64, 1.0) */
+typedef struct mc_weather_desc {
+    mc_diel_curve reference_temperature, reference_wind_speed, reference_humidity, cloud_cover;
+    double  angstrom_a, angstrom_b, angstrom_gamma;
+    double  solar_constant;                 /* W/m2, 1367 (angstrom_maxwell.jl:27) */
+    int32_t diffuse_model;                  /* MC_DIFFUSE_* */
+    int32_t refraction;                     /* 1: apparent zenith within 2 degrees of the horizon (NicheMapR SOLRAD; goldens need it) */
+    double  orbital_eccentricity;           /* 0.0167238 */
+    double  sin_obliquity;                  /* 0.39784993 */
+    double  days_per_year;                  /* 365 */
+    double  equinox_day;                    /* 80 */
+} mc_weather_desc;
+
+/* the Site fields SolarTerrain(site) passes to the geometry (src/site/site.jl:48-60) */
+typedef struct mc_solar_sites_soa {
+    const double* latitude;                 /* [S] degrees, north positive */
+    const double* slope;                    /* [S] degrees, or NULL = 0 */
+    const double* aspect;                   /* [S] degrees clockwise from north of the downslope direction, or NULL = 0 */
+    const double* solar_noon_offset_h;      /* [S] hours added to 12:00 for local solar noon (longitude / time-zone correction), or NULL = 0 */
+} mc_solar_sites_soa;
+
+/* per-day value series of every curve input ([ndays][S]; values[i] belongs to curve.inputs[i]) + what populate_weather! takes from solve_solar! */
+typedef struct mc_weather_in_soa {
+    const double* reference_temperature_values[MC_DIEL_MAX_INPUTS];   /* K */
+    const double* reference_wind_speed_values[MC_DIEL_MAX_INPUTS];    /* m/s */
+    const double* reference_humidity_values[MC_DIEL_MAX_INPUTS];      /* 0..1 */
+    const double* cloud_cover_values[MC_DIEL_MAX_INPUTS];             /* 0..1 */
+    const double* hour_solar_noon;          /* [ndays][S] h, or NULL: built-in geometry (needs mc_solar_sites_soa) */
+    const double* hour_angle_sunrise;       /* [ndays][S] h from noon back to sunrise, or NULL: built-in geometry */
+    const double* direct_horizontal;        /* [24*ndays][S] W/m2 clear-sky direct on the horizontal (SolarRadiation.jl) */
+    const double* diffuse_horizontal;       /* [24*ndays][S] W/m2 clear-sky diffuse */
+    const double* global_radiation_hourly;  /* [24*ndays][S] W/m2 environment_hourly.global_radiation override, or NULL */
+    const double* pressure_hourly;          /* [24*ndays][S] Pa environment_hourly.pressure, or NULL: pressure_site repeated */
+    const double* pressure_site;            /* [S] Pa */
+    const int32_t* day_of_year;             /* [ndays] MicroProblem.days — always a HOST pointer */
+} mc_weather_in_soa;
+
+/* what populate_weather! / solve_solar! leave in cache.output and solar_out; NULL = not wanted.  Hourly [24*ndays][S], daily [ndays][S]. */
+typedef struct mc_weather_out_soa {
+    double* pressure;
+    double* reference_temperature;
+    double* reference_wind_speed;
+    double* reference_humidity;
+    double* cloud_cover;
+    double* global_radiation;
+    double* diffuse_fraction;
+    double* zenith_angle;                   /* capped at 90 (src/simulation.jl:301) */
+    double* zenith_slope_angle;             /* capped at 90 (src/simulation.jl:302) */
+    double* hour_solar_noon;                /* [ndays][S] */
+    double* hour_angle_sunrise;             /* [ndays][S] */
+} mc_weather_out_soa;
+
+void mc_default_weather(mc_weather_desc* out);
+/* DielCurve constructor checks (src/inputs/diel.jl:182-222: overlap, gaps without a space-filling shape, inputs that are no endpoint)
+ * plus the ABI's own limits; 0 ok, <0 with a message in `err` (may be NULL) */
+int  mc_validate_weather(const mc_weather_desc* w, char* err, int err_len);
+
+/* replaces solve_solar! (geometry part) + populate_weather! (src/simulation.jl:20-36,291-352) for S sites: host arrays in, host arrays out */
+int  mc_populate_weather(mc_handle* h, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
+                         const mc_weather_in_soa* in, mc_weather_out_soa* out);
+/* same with DEVICE pointers everywhere (day_of_year stays a host pointer); asynchronous on the handle's stream until mc_synchronize */
+int  mc_populate_weather_device(mc_handle* h, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites_dev,
+                                const mc_weather_in_soa* in_dev, mc_weather_out_soa* out_dev);
+/* solve!(cache) for a min/max-driven problem (src/simulation.jl:246-260 minus solve_air!'s own outputs, which `out` may select as usual):
+ * weather expanded on the device straight into the soil kernel's forcing arrays, then solve_soil! for days [day0, day0+ndays).
+ * `rest` supplies what populate_weather! does not produce — the daily members, rainfall_hourly, longwave_radiation, prescribed_soil_moisture,
+ * day_of_year — and MAY supply zenith_angle + zenith_slope_angle (SolarRadiation.jl's own; NULL = built-in geometry); its other hourly members
+ * are ignored.  `weather_host` (may be NULL) receives the expanded hourly weather. */
+int  mc_step_days_minmax(mc_handle* h, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
+                         const mc_weather_in_soa* in, const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host);
+
+/* struct sizes of the loaded library, for bindings to check their mirrors against (index: 0 mc_model_desc, 1 mc_sites_soa, 2 mc_initial_soa,
+ * 3 mc_state_soa, 4 mc_forcing_soa, 5 mc_output_soa, 6 mc_counters, 7 mc_weather_desc, 8 mc_solar_sites_soa, 9 mc_weather_in_soa,
+ * 10 mc_weather_out_soa); -1 for an unknown index */
+int64_t mc_abi_sizeof(int which);
+
 /* measured FP64 DFMA peak of the handle's device in TFLOP/s (micro-benchmark; SURVEY §8d:
  * MEASURED_PEAKS.json has no FP64 figure). */
 int  mc_measure_fp64_peak(mc_handle* h, double* tflops);

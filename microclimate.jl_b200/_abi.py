@@ -138,3 +138,63 @@ def default_fluid():
     f.molar_latent_heat_a = 45144.0
     f.molar_latent_heat_b = 48.0
     return f
+
+
+# ---- widening rows f2 / f3: populate_weather! + solar geometry (include/microclimate_b200.h, "Widening") ----
+MC_TOD_CLOCK, MC_TOD_SUNRISE, MC_TOD_SUNSET, MC_TOD_MIDDAY, MC_TOD_MIDNIGHT = 0, 1, 2, 3, 4
+MC_SHAPE_SINE, MC_SHAPE_DECAY, MC_SHAPE_LINEAR = 0, 1, 2
+MC_DIEL_MAX_SHAPES = 6
+MC_DIEL_MAX_INPUTS = 6
+MC_DIFFUSE_ERBS = 0
+
+
+class TimeOfDay(C.Structure):
+    _fields_ = [("kind", _i32), ("_pad", _i32), ("value", _d)]
+
+
+class DielShape(C.Structure):
+    _fields_ = [("kind", _i32), ("_pad", _i32), ("a", TimeOfDay), ("b", TimeOfDay)]
+
+
+class DielCurve(C.Structure):
+    _fields_ = [("n_shapes", _i32), ("n_inputs", _i32), ("shapes", DielShape * MC_DIEL_MAX_SHAPES), ("inputs", TimeOfDay * MC_DIEL_MAX_INPUTS)]
+
+
+WEATHER_QUANTITIES = ("reference_temperature", "reference_wind_speed", "reference_humidity", "cloud_cover")
+
+
+class WeatherDesc(C.Structure):
+    _fields_ = ([(n, DielCurve) for n in WEATHER_QUANTITIES]
+                + [("angstrom_a", _d), ("angstrom_b", _d), ("angstrom_gamma", _d), ("solar_constant", _d),
+                   ("diffuse_model", _i32), ("refraction", _i32),
+                   ("orbital_eccentricity", _d), ("sin_obliquity", _d), ("days_per_year", _d), ("equinox_day", _d)])
+
+
+SOLAR_SITE_FIELDS = ("latitude", "slope", "aspect", "solar_noon_offset_h")
+
+
+class SolarSitesSoA(C.Structure):
+    _fields_ = [(n, _pd) for n in SOLAR_SITE_FIELDS]
+
+
+WEATHER_IN_DAILY = ("hour_solar_noon", "hour_angle_sunrise")
+WEATHER_IN_HOURLY = ("direct_horizontal", "diffuse_horizontal", "global_radiation_hourly", "pressure_hourly")
+
+
+class WeatherInSoA(C.Structure):
+    _fields_ = ([(n + "_values", _pd * MC_DIEL_MAX_INPUTS) for n in WEATHER_QUANTITIES]
+                + [(n, _pd) for n in WEATHER_IN_DAILY] + [(n, _pd) for n in WEATHER_IN_HOURLY]
+                + [("pressure_site", _pd), ("day_of_year", C.POINTER(_i32))])
+
+
+WEATHER_OUT_HOURLY = ("pressure", "reference_temperature", "reference_wind_speed", "reference_humidity", "cloud_cover",
+                      "global_radiation", "diffuse_fraction", "zenith_angle", "zenith_slope_angle")
+WEATHER_OUT_DAILY = ("hour_solar_noon", "hour_angle_sunrise")
+
+
+class WeatherOutSoA(C.Structure):
+    _fields_ = [(n, _pd) for n in WEATHER_OUT_HOURLY + WEATHER_OUT_DAILY]
+
+
+# mc_abi_sizeof(which): the order of include/microclimate_b200.h
+ABI_SIZEOF = (ModelDesc, SitesSoA, InitialSoA, StateSoA, ForcingSoA, OutputSoA, Counters, WeatherDesc, SolarSitesSoA, WeatherInSoA, WeatherOutSoA)

@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO = os.environ.get("MC_LIB") or os.path.join(CSRC, "libmicroclimate_b200.so")   # MC_LIB: development override (tuning variants)
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "microclimate_b200.h")
-SOURCES = [os.path.join(CSRC, "mc_api.cu")]
-DEPS = SOURCES + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + [INCLUDE, os.path.join(os.path.dirname(INCLUDE), "mc_math.h")]
+SOURCES = [os.path.join(CSRC, "mc_api.cu"), os.path.join(CSRC, "mc_weather.cu")]      # two translation units, no relocatable device code
+DEPS = SOURCES + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [INCLUDE, os.path.join(os.path.dirname(INCLUDE), "mc_math.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "--shared", "-Xcompiler", "-fPIC"]
 
@@ -25,7 +25,8 @@ EXPORTS = ("mc_abi_version", "mc_backend_name", "mc_default_fluid", "mc_default_
            "mc_step_days_async", "mc_wait",
            "mc_multi_create", "mc_multi_destroy", "mc_multi_last_error", "mc_multi_device_count", "mc_multi_handle", "mc_multi_range",
            "mc_multi_set_sites", "mc_multi_step_days", "mc_multi_step_days_async", "mc_multi_wait",
-           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity", "mc_get_async_stats")
+           "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity", "mc_get_async_stats",
+           "mc_default_weather", "mc_validate_weather", "mc_populate_weather", "mc_populate_weather_device", "mc_step_days_minmax", "mc_abi_sizeof")
 
 
 def _nvcc():
@@ -108,5 +109,19 @@ def lib():
     L.mc_measure_fp64_peak.argtypes = [H, C.POINTER(C.c_double)]
     L.mc_bench_conductivity.argtypes = [H, C.c_int64, C.c_int, C.POINTER(C.c_double)]
     L.mc_get_async_stats.argtypes = [H, C.POINTER(C.c_ulonglong), C.c_int]
+    L.mc_default_weather.argtypes = [C.POINTER(A.WeatherDesc)]
+    L.mc_default_weather.restype = None
+    L.mc_validate_weather.argtypes = [C.POINTER(A.WeatherDesc), C.c_char_p, C.c_int]
+    _wx = [H, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA), C.POINTER(A.WeatherOutSoA)]
+    L.mc_populate_weather.argtypes = _wx
+    L.mc_populate_weather_device.argtypes = _wx
+    L.mc_step_days_minmax.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA),
+                                      C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA), C.POINTER(A.WeatherOutSoA)]
+    L.mc_abi_sizeof.argtypes = [C.c_int]
+    L.mc_abi_sizeof.restype = C.c_int64
+    # a stale or foreign library whose struct layout differs from the ctypes mirrors would corrupt memory silently: refuse it
+    for k, cls in enumerate(A.ABI_SIZEOF):
+        if L.mc_abi_sizeof(k) != C.sizeof(cls):
+            raise RuntimeError(f"{SO}: sizeof({cls.__name__}) is {L.mc_abi_sizeof(k)} in the library, {C.sizeof(cls)} in _abi.py - rebuild the library (stale build?)")
     _lib = L
     return L

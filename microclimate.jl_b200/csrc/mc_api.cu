@@ -406,6 +406,16 @@ void mc_default_model(mc_model_desc* m)
 
 const char* mc_last_error(const mc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+}  // extern "C"
+/* accessors for the library's other translation unit (mc_weather.cu: the widening rows); hidden, not part of the ABI */
+#include "mc_internal.h"
+int mc_i_device(const mc_handle* h) { return h->device; }
+cudaStream_t mc_i_stream(const mc_handle* h) { return h->stream; }
+int64_t mc_i_sites(const mc_handle* h) { return h->S; }
+const mc_model_desc* mc_i_model(const mc_handle* h) { return &h->model; }
+int mc_i_fail(mc_handle* h, const char* msg, int rc) { h->err = msg; return rc; }
+extern "C" {
+
 int mc_create(const mc_model_desc* model, int64_t n_sites, int device, mc_handle** out)
 {
     if (out) *out = nullptr;
@@ -462,6 +472,7 @@ void mc_destroy(mc_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    mc_i_weather_release(h);                           /* staging of mc_step_days_minmax / mc_populate_weather (mc_weather.cu) */
     if (h->s_in) cudaStreamSynchronize(h->s_in);
     if (h->s_out) cudaStreamSynchronize(h->s_out);
     cudaFree(h->arena); cudaFree(h->doy_dev[0]); cudaFree(h->doy_dev[1]); cudaFree(h->flags); cudaFree(h->counters); cudaFree(h->coop_scr); cudaFree(h->async_scr);

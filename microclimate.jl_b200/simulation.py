@@ -84,6 +84,33 @@ class SoilEngine:
         """mc_wait: all enqueued chunks complete; returns the flagged-site count of the most recent one."""
         return self._check(self._L.mc_wait(self.h), "mc_wait")
 
+    # -- widening: populate_weather! + solar geometry on the device (weather.py, csrc/mc_weather.cuh) -----------------
+    def populate_weather(self, wdesc: A.WeatherDesc, win, wout, solar_sites=None):
+        """solve_solar! (geometry) + populate_weather! (src/simulation.jl:20-36,291-352) for this engine's sites: host arrays in, host arrays out."""
+        if win.S != self.S or wout.S != self.S or wout.ndays != win.ndays or (solar_sites is not None and solar_sites.S != self.S):
+            raise ValueError("weather batch shapes do not match the engine")
+        ci, co = win.c_struct(), wout.c_struct()
+        cs = solar_sites.c_struct() if solar_sites is not None else None
+        self._check(self._L.mc_populate_weather(self.h, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(co)),
+                    "mc_populate_weather")
+        return wout
+
+    def step_days_minmax(self, day0: int, wdesc: A.WeatherDesc, win, rest: M.ForcingBatch, out: M.OutputBatch, solar_sites=None, weather_out=None,
+                         use_rest_zenith: bool = False) -> int:
+        """solve!(cache) of a min/max-driven problem (src/simulation.jl:246-260): the hourly weather is expanded on the device straight into the soil kernel's
+        forcing arrays, then solve_soil! runs for days [day0, day0 + ndays).  `rest` carries what populate_weather! does not produce (daily members, rainfall,
+        longwave, prescribed moisture); with `use_rest_zenith` its zenith / slope-zenith angles (SolarRadiation.jl's own) are used, otherwise the built-in
+        geometry computes them from `solar_sites`."""
+        if win.S != self.S or out.S != self.S or rest.S != self.S or out.ndays != win.ndays or rest.ndays != win.ndays:
+            raise ValueError("weather/forcing/output batch shapes do not match the engine")
+        ci, cf, co = win.c_struct(), rest.c_struct(), out.c_struct()
+        if not use_rest_zenith:
+            cf.zenith_angle, cf.zenith_slope_angle = None, None
+        cs = solar_sites.c_struct() if solar_sites is not None else None
+        cw = weather_out.c_struct() if weather_out is not None else None
+        return self._check(self._L.mc_step_days_minmax(self.h, day0, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(cf),
+                                                       C.byref(co), C.byref(cw) if cw is not None else None), "mc_step_days_minmax")
+
     def step_days_device(self, day0: int, ndays: int, forcing_ptrs: dict, output_ptrs: dict):
         """Same with DEVICE pointers (ints) already resident on this GPU; asynchronous until synchronize()."""
         cf, co = A.ForcingSoA(), A.OutputSoA()

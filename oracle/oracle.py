@@ -15,9 +15,9 @@ _SO = os.path.join(_HERE, "libmc_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "mc_oracle.cpp")
-    hdr = os.path.join(_HERE, "..", "include", "microclimate_b200.h")
-    if (not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    deps = [os.path.join(_HERE, "mc_oracle.cpp"), os.path.join(_HERE, "mc_weather_oracle.cpp"),
+            os.path.join(_HERE, "..", "include", "microclimate_b200.h"), os.path.join(_HERE, "..", "include", "mc_math.h")]
+    if (not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(d) for d in deps)):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-B", "libmc_oracle.so"], stdout=subprocess.DEVNULL)
     return _SO
@@ -51,6 +51,8 @@ def lib():
         L.mco_fastpow.restype = C.c_double
         L.mco_fastpow.argtypes = [C.c_double, C.c_double]
         L.mco_phase_transition.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 5
+        L.mco_populate_weather.argtypes = [C.c_int64, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA),
+                                           C.POINTER(A.WeatherOutSoA)]
         _lib = L
     return _lib
 
@@ -93,3 +95,13 @@ class OracleEngine:
         cs = st.c_struct()
         lib().mco_get_state(self.h, C.byref(cs))
         return st
+
+
+def populate_weather(wdesc, win, wout, solar_sites=None):
+    """Oracle of populate_weather! + solar geometry (oracle/mc_weather_oracle.cpp); same batches as SoilEngine.populate_weather."""
+    ci, co = win.c_struct(), wout.c_struct()
+    cs = solar_sites.c_struct() if solar_sites is not None else None
+    rc = lib().mco_populate_weather(win.S, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(co))
+    if rc:
+        raise RuntimeError(f"mco_populate_weather failed (rc={rc}): a required input is missing")
+    return wout

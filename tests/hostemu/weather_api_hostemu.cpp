@@ -1,0 +1,75 @@
+/* TEST HARNESS ONLY (CPU tier).  Compiles the product's weather translation unit — microclimate.jl_b200/csrc/mc_weather.cu: the kernel, the
+ * argument checks, the staging plans of mc_populate_weather and mc_step_days_minmax — with g++ over a stand-in CUDA runtime in which device
+ * memory is host memory, streams are synchronous and a launch is a loop over the thread grid.  The soil side of mc_step_days_minmax
+ * (mc_step_days_device etc.) is served by the soil host emulation (hostemu.cpp, linked into the same library).  Nothing here ships. */
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define MCW_HOST_EMULATION 1
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+static dim3 blockIdx, threadIdx;
+#define __global__
+#define __launch_bounds__(n)
+#define __grid_constant__
+static long g_fake_allocs = 0;
+static inline const char* cudaGetErrorString(cudaError_t) { return "fake"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::malloc(n ? n : 1); std::memset(*p, 0xA5, n); g_fake_allocs++; return *p ? cudaSuccess : 2; }
+static inline cudaError_t cudaFree(void* p) { if (p) g_fake_allocs--; std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+
+#include "../../include/microclimate_b200.h"
+
+/* the soil host emulation (hostemu.cpp) */
+extern "C" {
+void* he_create(const mc_model_desc* m, int64_t S);
+void he_destroy(void* h);
+int he_set_sites(void* h, const mc_sites_soa* s, const mc_initial_soa* init);
+int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o);
+}
+
+struct mc_handle { void* emu; int64_t S; mc_model_desc model; std::string err; std::vector<int32_t> status; };
+
+#include "../../microclimate.jl_b200/csrc/mc_weather.cu"
+
+int mc_i_device(const mc_handle*) { return 0; }
+cudaStream_t mc_i_stream(const mc_handle*) { return nullptr; }
+int64_t mc_i_sites(const mc_handle* h) { return h->S; }
+const mc_model_desc* mc_i_model(const mc_handle* h) { return &h->model; }
+int mc_i_fail(mc_handle* h, const char* msg, int rc) { h->err = msg; return rc; }
+
+extern "C" {
+/* the entry points of mc_api.cu that mc_step_days_minmax calls, on the emulated soil engine ("device" pointers are host pointers here) */
+int mc_wait(mc_handle*) { return 0; }
+int mc_synchronize(mc_handle*) { return 0; }
+int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
+{
+    mc_output_soa oo = *o;
+    oo.status = h->status.data();
+    const int rc = he_step_days(h->emu, day0, ndays, f, &oo);
+    return rc < 0 ? rc : 0;
+}
+int mc_get_status(mc_handle* h, int32_t* out) { std::memcpy(out, h->status.data(), (size_t)h->S * sizeof(int32_t)); return 0; }
+
+mc_handle* wa_create(const mc_model_desc* m, int64_t S)
+{
+    mc_handle* h = new mc_handle();
+    h->emu = he_create(m, S); h->S = S; h->model = *m; h->status.assign((size_t)S, 0);
+    if (!h->emu) { delete h; return nullptr; }
+    return h;
+}
+void wa_destroy(mc_handle* h) { if (!h) return; mc_i_weather_release(h); he_destroy(h->emu); delete h; }
+int wa_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* i) { return he_set_sites(h->emu, s, i); }
+const char* wa_last_error(const mc_handle* h) { return h->err.c_str(); }
+long wa_live_allocations(void) { return g_fake_allocs; }
+}

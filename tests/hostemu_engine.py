@@ -106,3 +106,101 @@ class HostEmuEngine:
     def set_state(self, st):
         cs = st.c_struct()
         assert self._L.he_set_state(self.h, C.byref(cs)) == 0
+
+
+# ---- weather device code (csrc/mc_weather.cuh) on the CPU ----
+_WSO = os.path.join(_HERE, "libmc_weather_hostemu.so")
+_wlib = None
+
+
+def weather_lib():
+    global _wlib
+    if _wlib is None:
+        src = os.path.join(_HERE, "weather_hostemu.cpp")
+        deps = [src, os.path.join(_CSRC, "mc_weather.cuh"), os.path.join(_ROOT, "include", "mc_math.h"), os.path.join(_ROOT, "include", "microclimate_b200.h")]
+        if not os.path.exists(_WSO) or os.path.getmtime(_WSO) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-mfma", "-o", _WSO, src])
+        L = C.CDLL(_WSO)
+        L.he_populate_weather.argtypes = [C.c_int64, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA),
+                                          C.POINTER(A.WeatherOutSoA)]
+        _wlib = L
+    return _wlib
+
+
+def populate_weather(wdesc, win, wout, solar_sites=None):
+    """weather_kernel's body (mcw::site_day) run over the (site, day) grid on the CPU; same batches as SoilEngine.populate_weather."""
+    ci, co = win.c_struct(), wout.c_struct()
+    cs = solar_sites.c_struct() if solar_sites is not None else None
+    weather_lib().he_populate_weather(win.S, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(co))
+    return wout
+
+
+# ---- the weather translation unit (csrc/mc_weather.cu: entry points + staging plans + kernel) over a stand-in CUDA runtime ----
+_WASO = os.path.join(_HERE, "libmc_weather_api_hostemu.so")
+_walib = None
+
+
+def weather_api_lib():
+    global _walib
+    if _walib is None:
+        srcs = [os.path.join(_HERE, "weather_api_hostemu.cpp"), os.path.join(_HERE, "hostemu.cpp")]
+        deps = srcs + _DEPS + [os.path.join(_CSRC, "mc_weather.cu"), os.path.join(_CSRC, "mc_weather.cuh"), os.path.join(_CSRC, "mc_internal.h")]
+        if not os.path.exists(_WASO) or os.path.getmtime(_WASO) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-mfma", "-o", _WASO, *srcs])
+        L = C.CDLL(_WASO)
+        H = C.c_void_p
+        L.wa_create.restype = H
+        L.wa_create.argtypes = [C.POINTER(A.ModelDesc), C.c_int64]
+        L.wa_destroy.argtypes = [H]
+        L.wa_set_sites.argtypes = [H, C.POINTER(A.SitesSoA), C.POINTER(A.InitialSoA)]
+        L.wa_last_error.argtypes = [H]
+        L.wa_last_error.restype = C.c_char_p
+        L.wa_live_allocations.restype = C.c_long
+        wx = [H, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA), C.POINTER(A.WeatherOutSoA)]
+        L.mc_populate_weather.argtypes = wx
+        L.mc_populate_weather_device.argtypes = wx
+        L.mc_step_days_minmax.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA),
+                                          C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA), C.POINTER(A.WeatherOutSoA)]
+        _walib = L
+    return _walib
+
+
+class WeatherApiEmu:
+    """Same weather methods as microclimate_jl_b200.SoilEngine, served by mc_weather.cu compiled for the host (see weather_api_hostemu.cpp)."""
+
+    def __init__(self, desc, n_sites):
+        self.desc, self.S = desc, n_sites
+        self._L = weather_api_lib()
+        self.h = self._L.wa_create(C.byref(desc), n_sites)
+        if not self.h:
+            raise RuntimeError("wa_create failed")
+
+    def close(self):
+        if self.h:
+            self._L.wa_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"{what} failed (rc={rc}): {self._L.wa_last_error(self.h).decode()}")
+        return rc
+
+    def set_sites(self, sites):
+        cs, ci = sites.c_sites(), sites.c_initial()
+        self._check(self._L.wa_set_sites(self.h, C.byref(cs), C.byref(ci)), "he_set_sites")
+
+    def populate_weather(self, wdesc, win, wout, solar_sites=None, device_entry=False):
+        ci, co = win.c_struct(), wout.c_struct()
+        cs = solar_sites.c_struct() if solar_sites is not None else None
+        fn = self._L.mc_populate_weather_device if device_entry else self._L.mc_populate_weather
+        self._check(fn(self.h, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(co)), "mc_populate_weather")
+        return wout
+
+    def step_days_minmax(self, day0, wdesc, win, rest, out, solar_sites=None, weather_out=None, use_rest_zenith=False):
+        ci, cf, co = win.c_struct(), rest.c_struct(), out.c_struct()
+        if not use_rest_zenith:
+            cf.zenith_angle, cf.zenith_slope_angle = None, None
+        cs = solar_sites.c_struct() if solar_sites is not None else None
+        cw = weather_out.c_struct() if weather_out is not None else None
+        return self._check(self._L.mc_step_days_minmax(self.h, day0, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(cf),
+                                                       C.byref(co), C.byref(cw) if cw is not None else None), "mc_step_days_minmax")

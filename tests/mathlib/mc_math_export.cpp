@@ -12,6 +12,11 @@ extern "C" void mcm_apply(int fn, const double* x, const double* y, double* out,
         case 5: out[i] = mcm::atan(x[i]); break;
         case 6: out[i] = mcm::cos(x[i]); break;
         case 7: out[i] = mcm::exp2(x[i]); break;
+        case 8: out[i] = mcm::sin_r(x[i]); break;
+        case 9: out[i] = mcm::cos_r(x[i]); break;
+        case 10: out[i] = mcm::acos(x[i]); break;
+        case 11: { double sn, cs; mcm::sincosd(x[i], &sn, &cs); out[i] = sn; break; }
+        case 12: { double sn, cs; mcm::sincosd(x[i], &sn, &cs); out[i] = cs; break; }
         default: out[i] = 0.0;
         }
     }

@@ -78,3 +78,30 @@ def test_special_values(L):
     assert r[0] == np.inf and r[1] == 0.0 and r[2] == pytest.approx(1024.0, rel=1e-15) and r[3] == pytest.approx(-8.0, rel=1e-15) and np.isnan(r[4]) and r[5] == 1.0
     r = ap(L, 5, [np.inf, -np.inf])
     assert r[0] == pytest.approx(math.pi / 2) and r[1] == pytest.approx(-math.pi / 2)
+
+
+def test_solar_geometry_functions(L):
+    """sin_r / cos_r (|x| <= 64), acos, sincosd: the functions the solar-geometry and weather kernels add (<= 1 ulp, exact at multiples of 90 degrees)."""
+    x = np.concatenate([RNG.uniform(-64, 64, N), RNG.uniform(-7, 7, N), RNG.uniform(-1e-3, 1e-3, 1000), [0.0, math.pi / 2, math.pi, -math.pi, 2 * math.pi, 6.3]])
+    # near the zeros of sin/cos a two-word pi/2 leaves an ABSOLUTE error ~1e-21 |n|: compare in ulps away from them, absolutely near them
+    s, c = ap(L, 8, x), ap(L, 9, x)
+    rs, rc = np.sin(x), np.cos(x)
+    for got, ref in ((s, rs), (c, rc)):
+        big = np.abs(ref) > 1e-3
+        assert ulps(got[big], ref[big]).max() <= 1.0
+        assert np.abs(got[~big] - ref[~big]).max() < 1e-18
+    assert np.isnan(ap(L, 8, [65.0, np.nan])).all() and np.isnan(ap(L, 9, [-100.0])).all()
+    x = np.concatenate([RNG.uniform(-1, 1, N), RNG.uniform(-1e-3, 1e-3, 1000), 1 - np.exp(RNG.uniform(-40, -1, 2000)), -1 + np.exp(RNG.uniform(-40, -1, 2000)), [1.0, -1.0, 0.0, 0.5, -0.5]])
+    a = ap(L, 10, x)
+    assert ulps(a, np.arccos(x)).max() <= 1.0 and a[-5] == 0.0 and a[-4] == math.pi
+    assert np.isnan(ap(L, 10, [1.0000001, -2.0, np.nan])).all()
+    d = np.concatenate([RNG.uniform(-720, 720, N), np.arange(-720.0, 721.0, 15.0)])
+    sd, cd = ap(L, 11, d), ap(L, 12, d)
+    rad = np.fmod(d, 360.0).astype(np.longdouble) * (np.longdouble("3.14159265358979323846264338327950288") / 180)      # 80-bit reference
+    rs, rc = np.sin(rad).astype(float), np.cos(rad).astype(float)
+    assert np.abs(sd - rs).max() < 2.3e-16 and np.abs(cd - rc).max() < 2.3e-16
+    for deg, es, ec in ((0, 0, 1), (90, 1, 0), (180, 0, -1), (270, -1, 0), (360, 0, 1), (-90, -1, 0), (450, 1, 0), (30, None, None)):
+        sv, cv = ap(L, 11, [float(deg)])[0], ap(L, 12, [float(deg)])[0]
+        if es is not None:
+            assert sv == es and cv == ec, deg
+    assert abs(ap(L, 11, [30.0])[0] - 0.5) <= 1.2e-16 and abs(ap(L, 12, [60.0])[0] - 0.5) <= 1.2e-16

@@ -1,0 +1,99 @@
+"""GPU tests of the widening rows f2 / f3 (run on the B200 with `-m gpu`): weather_kernel through the C ABI against the oracle, bit for bit, on the cases
+of tests/test_weather.py; the golden ZEN vectors through CUDA; and the fused min/max step (expand on the device, then solve_soil!) against
+populate-then-solve with the CPU oracle on both halves."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from microclimate_jl_b200 import _abi as A
+from microclimate_jl_b200 import marshal as M
+from microclimate_jl_b200 import synthetic as syn
+from microclimate_jl_b200 import weather as W
+from oracle import oracle as O
+from oracle.oracle import OracleEngine
+from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _random_problem, _soil_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def SoilEngine():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from microclimate_jl_b200.simulation import SoilEngine as E
+    return E
+
+
+def _engine(SoilEngine, S):
+    return SoilEngine(M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode()), S)
+
+
+@pytest.mark.parametrize("case", ["standard", "custom", "given_solar"])
+def test_weather_kernel_matches_oracle(SoilEngine, case):
+    """4 099 sites (a ragged last block) x 6 days incl. polar, sloped and clamped cases: every hourly and daily output of weather_kernel == oracle, bit for bit."""
+    w, win, sites, _ = _random_problem({"standard": 31, "custom": 32, "given_solar": 33}[case], S=4099, D=6, curves=CUSTOM_CURVES if case == "custom" else None,
+                                       with_given_solar=case == "given_solar")
+    ref, got = W.WeatherOutBatch(win.ndays, win.S), W.WeatherOutBatch(win.ndays, win.S)
+    O.populate_weather(w, win, ref, sites)
+    with _engine(SoilEngine, win.S) as eng:
+        eng.populate_weather(w, win, got, sites)
+        for k in ALL_OUT:
+            a, b = getattr(ref, k), getattr(got, k)
+            assert np.array_equal(a, b, equal_nan=True), (k, float(np.nanmax(np.abs(a - b))))
+        part = W.WeatherOutBatch(win.ndays, win.S, ("diffuse_fraction", "zenith_slope_angle", "hour_angle_sunrise"))
+        eng.populate_weather(w, win, part, sites)
+        for k in ("diffuse_fraction", "zenith_slope_angle", "hour_angle_sunrise"):
+            assert np.array_equal(getattr(part, k), getattr(ref, k), equal_nan=True), k
+        with pytest.raises(RuntimeError, match="clear-sky"):
+            eng.populate_weather(w, W.WeatherInBatch(win.days, win.S, win.forcings, pressure_site=win.pressure_site), W.WeatherOutBatch(win.ndays, win.S), sites)
+
+
+@pytest.mark.parametrize("name", ["monthly", "daily", "scan329"])
+def test_golden_zenith_through_cuda(SoilEngine, name):
+    """The reference's golden ZEN columns (9 768 hourly values, three sites) reproduced by the device geometry to <= 1e-5 degrees."""
+    doy, zen, lat = GOLD[f"zen_{name}_doy"], GOLD[f"zen_{name}_zen"], float(GOLD[f"zen_{name}_lat"])
+    days = doy[::24]
+    out = W.WeatherOutBatch(len(days), 1, ("zenith_angle", "zenith_slope_angle"))
+    with _engine(SoilEngine, 1) as eng:
+        eng.populate_weather(W.weather_desc(), W.WeatherInBatch(days, 1, {}), out, W.SolarSitesBatch([lat]))
+    assert np.abs(out.zenith_angle[:, 0] - zen).max() <= 1e-5
+    assert np.array_equal(out.zenith_slope_angle, out.zenith_angle)
+
+
+def test_step_days_minmax_matches_populate_then_solve(SoilEngine):
+    """mc_step_days_minmax on the B200 (weather expanded on the device into the soil kernel's forcing, then the soil kernel) == oracle weather followed by
+    the oracle soil integration: every soil output and the expanded weather bit for bit; then the same run day by day."""
+    desc, sites, rest, win, solar = _soil_case(S=96, D=3, seed=41)
+    w = W.weather_desc()
+    S, D = win.S, win.ndays
+    wx = W.WeatherOutBatch(D, S)
+    O.populate_weather(w, win, wx, solar)
+    hourly = copy.deepcopy(rest)
+    for k in A.WEATHER_OUT_HOURLY:
+        getattr(hourly, k)[...] = getattr(wx, k)
+    fields = parity.ALL_FIELDS
+    ref, _ = parity.run(OracleEngine, desc, sites, hourly, fields=fields)
+    with SoilEngine(desc, S) as eng:
+        eng.set_sites(sites)
+        out = M.OutputBatch(D, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
+        got_wx = W.WeatherOutBatch(D, S)
+        eng.step_days_minmax(0, w, win, rest, out, solar, got_wx)
+        parity.assert_within_north_star(out, ref)
+        parity.assert_bit_identical(out, ref, fields)
+        for k in ALL_OUT:
+            assert np.array_equal(getattr(got_wx, k), getattr(wx, k)), k
+    with SoilEngine(desc, S) as eng:
+        eng.set_sites(sites)
+        out = M.OutputBatch(D, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
+        for d in range(D):
+            part = M.OutputBatch(1, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
+            wd = W.WeatherInBatch(win.days[d:d + 1], S, {q: tuple(v[d:d + 1] for v in win.forcings[q]) for q in A.WEATHER_QUANTITIES},
+                                  direct_horizontal=win.direct_horizontal[24 * d:24 * d + 24], diffuse_horizontal=win.diffuse_horizontal[24 * d:24 * d + 24],
+                                  pressure_site=win.pressure_site)
+            eng.step_days_minmax(d, w, wd, hourly.day_slice(d, d + 1), part, solar, None, use_rest_zenith=(d == 1))
+            out.assign_rows(24 * d, part)
+        # soil_humidity: see tests/test_weather.py (row 1 quirk of initialise_soil_humidity! under chunking)
+        parity.assert_bit_identical(out, ref, tuple(k for k in fields if k != "soil_humidity"))
