@@ -62,6 +62,24 @@ struct McForcing; hourly::NTuple{11,Ptr{Cdouble}}; daily::NTuple{8,Ptr{Cdouble}}
 struct McOutput;  node::NTuple{7,Ptr{Cdouble}}; scalar::NTuple{5,Ptr{Cdouble}}; snow_T::Ptr{Cdouble}
                   profile::NTuple{3,Ptr{Cdouble}}; profile_scalar::NTuple{2,Ptr{Cdouble}}; status::Ptr{Cint}; end   # profile = solve_air! outputs (NULL = skip)
 
+# widening rows f2 / f3: populate_weather! + solar geometry (header section "Widening")
+const MC_DIEL_MAX_SHAPES = 6
+const MC_DIEL_MAX_INPUTS = 6
+struct McTimeOfDay; kind::Cint; _pad::Cint; value::Cdouble; end
+struct McDielShape; kind::Cint; _pad::Cint; a::McTimeOfDay; b::McTimeOfDay; end
+struct McDielCurve; n_shapes::Cint; n_inputs::Cint; shapes::NTuple{MC_DIEL_MAX_SHAPES,McDielShape}; inputs::NTuple{MC_DIEL_MAX_INPUTS,McTimeOfDay}; end
+struct McWeather
+    reference_temperature::McDielCurve; reference_wind_speed::McDielCurve; reference_humidity::McDielCurve; cloud_cover::McDielCurve
+    angstrom_a::Cdouble; angstrom_b::Cdouble; angstrom_gamma::Cdouble; solar_constant::Cdouble
+    diffuse_model::Cint; refraction::Cint
+    orbital_eccentricity::Cdouble; sin_obliquity::Cdouble; days_per_year::Cdouble; equinox_day::Cdouble
+end
+struct McSolarSites; p::NTuple{4,Ptr{Cdouble}}; end         # latitude, slope, aspect, solar_noon_offset_h
+struct McWeatherIn                                          # values[q][i]: quantity q (T, wind, RH, cloud), curve input i
+    values::NTuple{24,Ptr{Cdouble}}; daily::NTuple{2,Ptr{Cdouble}}; hourly::NTuple{4,Ptr{Cdouble}}; pressure_site::Ptr{Cdouble}; doy::Ptr{Cint}
+end
+struct McWeatherOut; hourly::NTuple{9,Ptr{Cdouble}}; daily::NTuple{2,Ptr{Cdouble}}; end
+
 const NULLD = Ptr{Cdouble}(C_NULL)
 last_error(h) = unsafe_string(ccall((:mc_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
 multi_error(h) = unsafe_string(ccall((:mc_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
@@ -249,6 +267,100 @@ function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integ
     finally
         multi ? ccall((:mc_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[]) : ccall((:mc_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
     end
+end
+
+# ---- populate_weather! on the device (widening rows f2 / f3) ---------------------------------------------------------------------
+import Microclimate: Sunrise, Sunset, Midday, Midnight, ClockTime, Sine, Decay, Linear, DielCurve, DielForcing, AngstromMaxwellShortwave, Angstrom, ErbsDiffuseFraction
+
+tod(t::ClockTime) = McTimeOfDay(0, 0, t.hour)
+tod(t::Sunrise) = McTimeOfDay(1, 0, t.offset)
+tod(t::Sunset) = McTimeOfDay(2, 0, t.offset)
+tod(t::Midday) = McTimeOfDay(3, 0, t.offset)
+tod(t::Midnight) = McTimeOfDay(4, 0, t.offset)
+shape(s::Sine) = McDielShape(0, 0, tod(s.trough), tod(s.peak))
+shape(s::Decay) = McDielShape(1, 0, tod(s.from), tod(s.to))
+shape(s::Linear) = McDielShape(2, 0, tod(s.from), tod(s.to))
+const TOD0 = McTimeOfDay(0, 0, 0.0)
+function curve_desc(c::DielCurve)
+    length(c.shapes) <= MC_DIEL_MAX_SHAPES && length(c.inputs) <= MC_DIEL_MAX_INPUTS || error("DielCurve does not fit the C ABI (at most 6 shapes and 6 inputs)")
+    McDielCurve(length(c.shapes), length(c.inputs),
+        ntuple(i -> i <= length(c.shapes) ? shape(c.shapes[i]) : McDielShape(0, 0, TOD0, TOD0), MC_DIEL_MAX_SHAPES),
+        ntuple(i -> i <= length(c.inputs) ? tod(c.inputs[i]) : TOD0, MC_DIEL_MAX_INPUTS))
+end
+
+"mc_weather_desc from an environment's forcings (DielForcing per quantity) and the shortwave model; geometry constants = the library defaults."
+function weather_desc(forcings::NamedTuple, sw::AngstromMaxwellShortwave)
+    sw.diffuse_fraction_model isa ErbsDiffuseFraction || error("only ErbsDiffuseFraction exists on the device")
+    all(f -> f isa DielForcing, (forcings.reference_temperature, forcings.reference_wind_speed, forcings.reference_humidity, forcings.cloud_cover)) ||
+        error("Derived forcing quantities are not supported on the device: expand them with Microclimate.populate_weather!")
+    d = Ref{McWeather}()
+    ccall((:mc_default_weather, LIB), Cvoid, (Ref{McWeather},), d)
+    w, a = d[], sw.sunshine_fraction_model
+    McWeather(curve_desc(forcings.reference_temperature.curve), curve_desc(forcings.reference_wind_speed.curve), curve_desc(forcings.reference_humidity.curve),
+              curve_desc(forcings.cloud_cover.curve), a.a, a.b, a.gamma, w.solar_constant, w.diffuse_model, w.refraction,
+              w.orbital_eccentricity, w.sin_obliquity, w.days_per_year, w.equinox_day)
+end
+
+"""
+    populate_weather_batched!(caches::Vector{<:MicroCache}; device=0, builtin_geometry=false)
+
+Batched replacement of `populate_weather!` (src/simulation.jl:20-36) for caches that share one model and day list: the diel expansion of every
+site's min/max series, the Angstrom cloud adjustment and the Erbs diffuse fraction run in one `weather_kernel` launch (`mc_populate_weather`), and the
+hourly results are written into each `cache.output` exactly where `populate_weather!` leaves them.  `solve_solar!` must have run (its clear-sky
+`direct_horizontal` / `diffuse_horizontal` are inputs; with `builtin_geometry=false` its `hour_solar_noon` / `hour_angle_sunrise` are used too,
+otherwise the library's own geometry).  For the fused form that never brings the hourly weather back to the host see `mc_step_days_minmax`.
+"""
+function populate_weather_batched!(caches::AbstractVector{<:MicroCache}; device::Integer=0, builtin_geometry::Bool=false)
+    mp = first(caches).problem
+    S, D = length(caches), length(mp.days)
+    H = 24D
+    envs = [c.problem.inputs.environment_minmax for c in caches]
+    w = Ref(weather_desc(first(envs).forcings, mp.model.radiation.shortwave_model))
+    so(c) = c.buffers.solar_out
+    quantities = (:reference_temperature, :reference_wind_speed, :reference_humidity, :cloud_cover)
+    units = (u"K", u"m/s", 1, 1)
+    # values[q][i][d, s] -> [D][S] site-fastest; eltype conversion as evaluate! does it (diel.jl:337)
+    series = [[Float64[si(unit == 1 ? collect(getproperty(e.forcings, q).values[i])[d] : unit(collect(getproperty(e.forcings, q).values[i])[d]), unit) for e in envs, d in 1:D]
+               for i in 1:length(getproperty(first(envs).forcings, q).values)] for (q, unit) in zip(quantities, units)]
+    daily(f) = Float64[f(c, d) for c in caches, d in 1:D]
+    hourly(f) = Float64[f(c, t) for c in caches, t in 1:H]
+    noon = builtin_geometry ? Float64[] : daily((c, d) -> Float64(ustrip(so(c).hour_solar_noon[d])))
+    ha = builtin_geometry ? Float64[] : daily((c, d) -> Float64(ustrip(so(c).hour_angle_sunrise[d])))
+    direct = hourly((c, t) -> si(so(c).direct_horizontal[t], u"W/m^2"))
+    diffuse = hourly((c, t) -> si(so(c).diffuse_horizontal[t], u"W/m^2"))
+    eh(c) = c.problem.inputs.environment_hourly
+    has_gr = !isnothing(eh(first(caches)).global_radiation)
+    gr = has_gr ? hourly((c, t) -> si(eh(c).global_radiation[t], u"W/m^2")) : Float64[]
+    pres = hourly((c, t) -> si(eh(c).pressure[t], u"Pa"))
+    lat = Float64[si(c.problem.inputs.site.latitude, u"°") for c in caches]
+    doy = Cint.(mp.days)
+    out = ntuple(_ -> zeros(S, H), 7)                       # pressure, T, wind, RH, cloud, global radiation, diffuse fraction
+    ptr(a) = isempty(a) ? NULLD : pointer(a)
+    desc = Ref(model_desc(mp.model, mp.time_mode, first(caches).problem.inputs))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:mc_create, LIB), Cint, (Ref{McModel}, Int64, Cint, Ref{Ptr{Cvoid}}), desc, S, device, h), "mc_create")
+    try
+        GC.@preserve series noon ha direct diffuse gr pres lat doy out begin
+            vals = ntuple(k -> (q = (k - 1) ÷ MC_DIEL_MAX_INPUTS + 1; i = (k - 1) % MC_DIEL_MAX_INPUTS + 1; i <= length(series[q]) ? pointer(series[q][i]) : NULLD), 24)
+            win = Ref(McWeatherIn(vals, (ptr(noon), ptr(ha)), (pointer(direct), pointer(diffuse), ptr(gr), pointer(pres)), NULLD, pointer(doy)))
+            sites = Ref(McSolarSites((pointer(lat), NULLD, NULLD, NULLD)))
+            wout = Ref(McWeatherOut((map(pointer, out)..., NULLD, NULLD), (NULLD, NULLD)))
+            check(h[], ccall((:mc_populate_weather, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{McWeather}, Ref{McSolarSites}, Ref{McWeatherIn}, Ref{McWeatherOut}),
+                             h[], D, w, sites, win, wout), "mc_populate_weather")
+        end
+        for (s, c) in enumerate(caches), t in 1:H
+            c.output.pressure[t] = out[1][s, t] * u"Pa"
+            c.output.reference_temperature[t] = out[2][s, t] * u"K"
+            c.output.reference_wind_speed[t] = out[3][s, t] * u"m/s"
+            c.output.reference_humidity[t] = out[4][s, t]
+            c.output.cloud_cover[t] = out[5][s, t]
+            c.output.global_radiation[t] = out[6][s, t] * u"W/m^2"
+            c.output.diffuse_fraction[t] = out[7][s, t]
+        end
+    finally
+        ccall((:mc_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    return caches
 end
 
 end # module

@@ -11,7 +11,8 @@ from microclimate_jl_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = open(os.path.join(ROOT, "julia", "MicroclimateB200.jl")).read()
-CONSTS = {"MC_MAX_SOIL_NODES": A.MC_MAX_SOIL_NODES, "MC_SNOW_NODES": A.MC_SNOW_NODES, "MC_MAX_HEIGHTS": A.MC_MAX_HEIGHTS}
+CONSTS = {"MC_MAX_SOIL_NODES": A.MC_MAX_SOIL_NODES, "MC_SNOW_NODES": A.MC_SNOW_NODES, "MC_MAX_HEIGHTS": A.MC_MAX_HEIGHTS,
+          "MC_DIEL_MAX_SHAPES": A.MC_DIEL_MAX_SHAPES, "MC_DIEL_MAX_INPUTS": A.MC_DIEL_MAX_INPUTS}
 SIZES = {"Cdouble": 8, "Cint": 4, "Ptr{Cdouble}": 8, "Ptr{Cint}": 8}
 
 
@@ -89,3 +90,26 @@ def test_julia_binding_marshals_what_round_1_dropped():
                    "SwinbankAtmosphericRadiation", "chunk_days", "mc_multi_create", "snow_temperature"):
         assert needle in SRC, needle
     assert "m.fluid, m.snow)" not in SRC          # the zeroed default snow descriptor must not be passed for a SnowModel
+
+
+def test_julia_weather_structs_match_the_header():
+    """The widening structs (populate_weather! / solar geometry): nested PODs field by field, pointer tables by arity and total size."""
+    structs = {"McTimeOfDay": A.TimeOfDay, "McDielShape": A.DielShape, "McDielCurve": A.DielCurve}
+    for jname, ct in (("McTimeOfDay", A.TimeOfDay), ("McDielShape", A.DielShape), ("McDielCurve", A.DielCurve), ("McWeather", A.WeatherDesc)):
+        jf, cf = julia_struct(jname), flat(ct)
+        assert [n for n, _ in jf] == [n for n, _, _ in cf], f"{jname}: field names / order differ from the header"
+        for (n, t), (_, size, _count) in zip(jf, cf):
+            assert julia_sizeof(t, structs)[0] == size, f"{jname}.{n}"
+        assert sum(julia_sizeof(t, structs)[0] for _, t in jf) == C.sizeof(ct), jname          # no padding holes in these structs
+    for jname, ct in (("McSolarSites", A.SolarSitesSoA), ("McWeatherIn", A.WeatherInSoA), ("McWeatherOut", A.WeatherOutSoA)):
+        assert sum(julia_sizeof(t, {})[0] for _, t in julia_struct(jname)) == C.sizeof(ct), jname
+    wi = dict(julia_struct("McWeatherIn"))
+    assert wi["values"] == "NTuple{24,Ptr{Cdouble}}" and 24 == 4 * A.MC_DIEL_MAX_INPUTS and wi["doy"] == "Ptr{Cint}"
+    assert dict(julia_struct("McWeatherOut"))["hourly"] == "NTuple{9,Ptr{Cdouble}}" and len(A.WEATHER_OUT_HOURLY) == 9
+    # the enum values the Julia marshaller hard-codes (tod / shape)
+    for pat, val in ((r"tod\(t::ClockTime\) = McTimeOfDay\((\d)", A.MC_TOD_CLOCK), (r"tod\(t::Sunrise\) = McTimeOfDay\((\d)", A.MC_TOD_SUNRISE),
+                     (r"tod\(t::Sunset\) = McTimeOfDay\((\d)", A.MC_TOD_SUNSET), (r"tod\(t::Midday\) = McTimeOfDay\((\d)", A.MC_TOD_MIDDAY),
+                     (r"tod\(t::Midnight\) = McTimeOfDay\((\d)", A.MC_TOD_MIDNIGHT), (r"shape\(s::Sine\) = McDielShape\((\d)", A.MC_SHAPE_SINE),
+                     (r"shape\(s::Decay\) = McDielShape\((\d)", A.MC_SHAPE_DECAY), (r"shape\(s::Linear\) = McDielShape\((\d)", A.MC_SHAPE_LINEAR)):
+        assert int(re.search(pat, SRC).group(1)) == val, pat
+    assert "mc_populate_weather" in set(re.findall(r"\(\s*:(mc_\w+)\s*,\s*LIB\s*\)", SRC)) and "mc_populate_weather" in _lib.EXPORTS
