@@ -269,6 +269,11 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
     time_mode = time_mode if time_mode is not None else T.NonConsecutiveDayMode()
     if len(inputs) == 0:
         raise ValueError("inputs must be non-empty")
+    if isinstance(model.snow_model, T.SnowModel):
+        # the initial snowpack is model-level in the ABI (mc_snow_desc.initial_snow_*): a batch whose sites differ would silently run on site 0's values
+        key = lambda i: (i.initial_snow_depth, i.initial_snow_temperature, i.initial_snow_density)      # noqa: E731
+        if any(key(i) != key(inputs[0]) for i in inputs[1:]):
+            raise ValueError("initial_snow_depth / _temperature / _density must be identical for all sites of a batch (model-level in the C ABI)")
     desc = M.model_desc(model, time_mode, inputs0=inputs[0])
     sites = M.SitesBatch.from_inputs(model, inputs)
     forcing = M.ForcingBatch.from_inputs(model, inputs, days)
