@@ -94,6 +94,19 @@ def calibrated_traffic():
     return t
 
 
+def weather_probe(timeout_s=300):
+    """Throughput + HBM roofline + oracle parity of the weather kernel, measured by tools/gpu_weather_probe.py in a SEPARATE process
+    after the headline measurement is complete: whatever happens there (a CUDA error included) cannot touch this process or its numbers."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_weather_probe.py")], capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": "probe exited %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
+    except Exception as e:          # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def _pinned(shape):
     import torch
     return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
@@ -175,6 +188,7 @@ def main():
     ap.add_argument("--sites", type=int, default=1 << 20, help="sites per GPU (weak scaling)")
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites of the bounded CPU sample (0 = sized for ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weather-probe", action="store_true", help="skip the weather-kernel probe (tools/gpu_weather_probe.py, N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -339,6 +353,8 @@ def main():
         times = cpu_run(desc, n, 0, n, 0, 2, threads=cores)
         line["cpu_baseline"] = {"value": n / times[1], "unit": "site-days/s", "cores": cores, "kind": "port",
                                 "sample": "%d sites (one full latitude sweep) x 1 day (day 1 after a 1-day warm-up), OpenMP over sites, %.1f s; C++ restatement of the reference (Julia not installable here)" % (n, times[1])}
+    if world == 1 and not args.no_weather_probe:
+        line["widening"] = {"weather_kernel": weather_probe()}
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -35,3 +35,23 @@ def test_product_arm_fails_loudly_without_cuda():
         return
     p = subprocess.run([sys.executable, "bench.py", "--sites", "64", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and "no CPU path" in (p.stderr + p.stdout)
+
+
+def test_weather_probe_self_test_and_bench_attachment():
+    """tools/gpu_weather_probe.py (what bench.py attaches as `widening.weather_kernel` at N = 1) run against the host emulation of mc_weather.cu: the script's
+    struct filling, launch loop, byte accounting and oracle check are exercised here; on a box without a GPU bench.weather_probe() degrades to an error object."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_weather_probe.py"), "--emulate", "--sites", "1500", "--days", "2", "--reps", "1", "--check", "300"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-800:]
+    p = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert p["parity"] == {"sites_checked": 300, "bit_identical_to_oracle": True}
+    assert p["roofline"]["bound"] == "hbm" and abs(p["roofline"]["alg_bytes_per_site_day"] - 2232.0) < 1.0 and p["site_days_per_s"] > 0
+    sys.path.insert(0, root)
+    import bench
+    import torch
+    if not torch.cuda.is_available():
+        assert "error" in bench.weather_probe(120)
