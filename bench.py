@@ -94,17 +94,27 @@ def calibrated_traffic():
     return t
 
 
-def weather_probe(timeout_s=300):
-    """Throughput + HBM roofline + oracle parity of the weather kernel (SURVEY 8f rows 2-3), measured by tools/gpu_weather_probe.py in a SEPARATE process
-    after the headline measurement is complete: whatever happens there (a CUDA error included) cannot touch this process or its numbers."""
+def _probe(script, timeout_s):
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_weather_probe.py")], capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script)], capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode == 0 and lines:
             return json.loads(lines[-1])
         return {"error": "probe exited %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
     except Exception as e:          # noqa: BLE001
         return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def sand_probe(timeout_s=420):
+    """The same kernel on the six-class texture grid of SURVEY 8d (incl. pure sand) next to the headline grid, one wave of sites (tools/gpu_sand_probe.py), in a
+    separate process after the headline measurement."""
+    return _probe("gpu_sand_probe.py", timeout_s)
+
+
+def weather_probe(timeout_s=300):
+    """Throughput + HBM roofline + oracle parity of the weather kernel (SURVEY 8f rows 2-3), measured by tools/gpu_weather_probe.py in a SEPARATE process
+    after the headline measurement is complete: whatever happens there (a CUDA error included) cannot touch this process or its numbers."""
+    return _probe("gpu_weather_probe.py", timeout_s)
 
 
 def _pinned(shape):
@@ -188,7 +198,7 @@ def main():
     ap.add_argument("--sites", type=int, default=1 << 20, help="sites per GPU (weak scaling)")
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites of the bounded CPU sample (0 = sized for ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-weather-probe", action="store_true", help="skip the weather-kernel probe (tools/gpu_weather_probe.py, N = 1 only)")
+    ap.add_argument("--no-probes", action="store_true", help="skip the two post-measurement probes (tools/gpu_sand_probe.py, tools/gpu_weather_probe.py; N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -353,7 +363,9 @@ def main():
         times = cpu_run(desc, n, 0, n, 0, 2, threads=cores)
         line["cpu_baseline"] = {"value": n / times[1], "unit": "site-days/s", "cores": cores, "kind": "port",
                                 "sample": "%d sites (one full latitude sweep) x 1 day (day 1 after a 1-day warm-up), OpenMP over sites, %.1f s; C++ restatement of the reference (Julia not installable here)" % (n, times[1])}
-    if world == 1 and not args.no_weather_probe:
+    if world == 1 and not args.no_probes:
+        eng.close()                       # the probes are separate processes on the same GPU: give the memory back first
+        line["with_sand"] = sand_probe()
         line["widening"] = {"weather_kernel": weather_probe()}
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -50,6 +50,11 @@ def test_weather_probe_self_test_and_bench_attachment():
     p = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert p["parity"] == {"sites_checked": 300, "bit_identical_to_oracle": True}
     assert p["roofline"]["bound"] == "hbm" and abs(p["roofline"]["alg_bytes_per_site_day"] - 2232.0) < 1.0 and p["site_days_per_s"] > 0
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_sand_probe.py"), "--emulate", "--sites", "12", "--steps", "1"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-800:]
+    q = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert set(q) >= {"with_sand", "without_sand", "ratio", "workload"} and q["with_sand"]["work_per_site_day"]["n_infil_steps"] == 240.0
     sys.path.insert(0, root)
     import bench
     import torch
