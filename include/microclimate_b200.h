@@ -196,6 +196,7 @@ typedef struct mc_state_soa {
     double* q_freeze;           /* [S] W/m2 (n_snow>0) or NULL */
     double* obukhov_air;        /* [S] m   buffers.air_profile.obukhov_length_prev (solve_air!) */
     int64_t* days_done;         /* [1] days integrated so far (global day index of the next day) */
+    int32_t* status;            /* [S] MC_STATUS_* bits accumulated so far (a resumed run keeps its flagged sites), or NULL */
 } mc_state_soa;
 #define MC_SNOW_STATE_FIELDS 10 /* depth, age, days_since_snow, density, prev_density, cum_melt, extra_snow, active_nodes, sum_phase, prev_hour_depth */
 

@@ -84,7 +84,7 @@ class StateSoA(C.Structure):
     _fields_ = [(n, _pd) for n in (
         "soil_temperature", "soil_moisture", "sum_phase", "pool", "soil_wetness", "obukhov_ode",
         "obukhov_profile", "deep_temperature_prev", "fsal", "snow_temperature", "snow_state",
-        "snow_node_depths", "q_freeze", "obukhov_air")] + [("days_done", C.POINTER(C.c_int64))]
+        "snow_node_depths", "q_freeze", "obukhov_air")] + [("days_done", C.POINTER(C.c_int64)), ("status", C.POINTER(_i32))]
 
 
 FORCING_HOURLY = ("pressure", "reference_temperature", "reference_wind_speed", "reference_humidity",

@@ -536,6 +536,10 @@ static int copy_state(mc_handle* h, const mc_state_soa* st, bool to_host)
         if (to_host) MC_CUDA(h, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
         else MC_CUDA(h, cudaMemcpyAsync(it.dev, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
     }
+    if (st->status) {                            /* the accumulated MC_STATUS_* bits travel with the checkpoint */
+        if (to_host) MC_CUDA(h, cudaMemcpyAsync(st->status, h->flags, S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        else MC_CUDA(h, cudaMemcpyAsync(h->flags, st->status, S * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
     MC_CUDA(h, cudaStreamSynchronize(h->stream));
     if (st->days_done) { if (to_host) st->days_done[0] = h->days_done; else h->days_done = st->days_done[0]; }
     return 0;
@@ -786,10 +790,22 @@ static int step_days_enqueue(mc_handle* h, int64_t day0, int32_t ndays, const mc
     return 0;
 }
 
+/* an enqueue that failed half-way may have copies into / out of caller buffers in flight: nothing may still touch them when the error is returned */
+static int drain_after_error(mc_handle* h, int rc)
+{
+    if (rc < 0) {
+        if (h->s_in) cudaStreamSynchronize(h->s_in);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->s_out) cudaStreamSynchronize(h->s_out);
+        for (int k = 0; k < mc_handle::DEPTH; k++) h->busy[k] = false;
+    }
+    return rc;
+}
+
 int mc_step_days_async(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
 {
     if (!h) return -1;
-    return step_days_enqueue(h, day0, ndays, f, o, h->S, 0);
+    return drain_after_error(h, step_days_enqueue(h, day0, ndays, f, o, h->S, 0));
 }
 
 /* wait for every chunk enqueued with mc_step_days_async; returns the flagged-site count of the most recent one */
@@ -808,9 +824,9 @@ int mc_wait(mc_handle* h)
 int mc_step_days(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
 {
     if (!h) return -1;
-    if (int rc = mc_wait(h)) { if (rc < 0) return rc; }
-    if (int rc = step_days_enqueue(h, day0, ndays, f, o, h->S, 0)) return rc;
-    return mc_wait(h);
+    if (int rc = mc_wait(h)) { if (rc < 0) return drain_after_error(h, rc); }
+    if (int rc = step_days_enqueue(h, day0, ndays, f, o, h->S, 0)) return drain_after_error(h, rc);
+    return drain_after_error(h, mc_wait(h));
 }
 
 int mc_get_counters(mc_handle* h, mc_counters* c)
@@ -950,7 +966,11 @@ int mc_multi_step_days_async(mc_multi* m, int64_t day0, int32_t ndays, const mc_
 {
     if (!m) return -1;
     for (size_t g = 0; g < m->h.size(); g++)
-        if (int rc = step_days_enqueue(m->h[g], day0, ndays, f, o, m->S, m->lo[g])) { m->err = "device " + std::to_string(g) + ": " + m->h[g]->err; return rc; }
+        if (int rc = step_days_enqueue(m->h[g], day0, ndays, f, o, m->S, m->lo[g])) {
+            m->err = "device " + std::to_string(g) + ": " + m->h[g]->err;
+            for (size_t k = 0; k < m->h.size(); k++) drain_after_error(m->h[k], rc < 0 ? rc : -1);      /* the other devices' copies touch the same caller arrays */
+            return rc;
+        }
     return 0;
 }
 int mc_multi_wait(mc_multi* m)

@@ -365,12 +365,15 @@ class StateBatch:
         self.q_freeze = np.zeros(n_sites) if n_snow else None
         self.obukhov_air = np.zeros(n_sites)
         self.days_done = np.zeros(1, dtype=np.int64)
+        self.status = np.zeros(n_sites, dtype=np.int32)          # MC_STATUS_* bits accumulated so far
 
     def c_struct(self) -> A.StateSoA:
         c = A.StateSoA()
         for f, _ in A.StateSoA._fields_:
             if f == "days_done":
                 c.days_done = self.days_done.ctypes.data_as(C.POINTER(C.c_int64))
+            elif f == "status":
+                c.status = self.status.ctypes.data_as(C.POINTER(C.c_int32))
             else:
                 setattr(c, f, _ptr(getattr(self, f)))
         return c

@@ -175,6 +175,9 @@ def load_state(path: str, lo: int = 0, hi: Optional[int] = None) -> M.StateBatch
         a = c.get(f)
         if f == "days_done":
             st.days_done[0] = int(a[0])
+        elif f == "status":
+            if a is not None:                       # checkpoints written before the status word travelled with the state have none: flags start at 0
+                st.status[...] = a[lo:hi]
         elif a is not None:
             getattr(st, f)[...] = a[..., lo:hi]
     return st

@@ -1682,6 +1682,7 @@ int mco_get_state(void* h, mc_state_soa* out)
         }
     }
     if (out->days_done) out->days_done[0] = o->days_done;
+    if (out->status) for (int64_t s = 0; s < S; s++) out->status[s] = o->states[s].flags;
     return 0;
 }
 

@@ -231,6 +231,7 @@ int he_get_state(void* h, mc_state_soa* st)
     cp(st->pool, e->pool, S); cp(st->soil_wetness, e->wet, S); cp(st->obukhov_ode, e->L_ode, S); cp(st->obukhov_profile, e->L_prof, S);
     cp(st->deep_temperature_prev, e->tdeep, S); cp(st->obukhov_air, e->L_air, S);
     if (st->days_done) st->days_done[0] = e->days_done;
+    if (st->status) std::memcpy(st->status, e->flags.data(), S * sizeof(int32_t));
     return 0;
 }
 
@@ -281,5 +282,6 @@ extern "C" int he_set_state(void* h, const mc_state_soa* st)
     cp(e->pool, st->pool, S); cp(e->wet, st->soil_wetness, S); cp(e->L_ode, st->obukhov_ode, S); cp(e->L_prof, st->obukhov_profile, S);
     cp(e->tdeep, st->deep_temperature_prev, S); cp(e->L_air, st->obukhov_air, S);
     if (st->days_done) e->days_done = st->days_done[0];
+    if (st->status) std::memcpy(e->flags.data(), st->status, S * sizeof(int32_t));
     return 0;
 }

@@ -98,11 +98,13 @@ def test_state_checkpoint_roundtrip(SoilEngine, synth):
     a = SoilEngine(desc, sites.S); a.set_sites(sites)
     o1 = M.OutputBatch(1, desc.n_soil, sites.S, f); a.step_days(0, forcing.day_slice(0, 1), o1)
     st = a.get_state()
-    assert st.days_done[0] == 1
+    assert st.days_done[0] == 1 and np.array_equal(st.status, o1.status)
+    st.status[::5] |= 4                       # the status word travels with the checkpoint: bits set before the resume survive it
     b = SoilEngine(desc, sites.S); b.set_sites(sites); b.set_state(st)
     oa = M.OutputBatch(1, desc.n_soil, sites.S, f); ob = M.OutputBatch(1, desc.n_soil, sites.S, f)
     a.step_days(1, forcing.day_slice(1, 2), oa); b.step_days(1, forcing.day_slice(1, 2), ob)
     parity.assert_bit_identical(oa, ob, f)
+    assert np.all(ob.status[::5] & 4) and np.array_equal(ob.status & ~4, oa.status & ~4)
 
 
 def test_error_behaviour(SoilEngine, synth):

@@ -103,3 +103,29 @@ def test_dataset_cli_matches_in_memory_run(tmp_path):
     got = np.concatenate([st.load_outputs(os.path.join(d, f"out_d{k:04d}_s0-16.mcb")).soil_temperature for k in (0, 1)])
     assert np.array_equal(got, whole.soil_temperature)
     assert int(st.load_state(os.path.join(d, "state_s0-16.mcb")).days_done[0]) == 2
+
+
+def test_checkpoint_carries_the_status_word(tmp_path):
+    """mc_get_state / mc_set_state did not carry the per-site status flags, so a resumed run lost its flagged sites.  The status word now travels with
+    the state (mc_state_soa.status): set bits survive save -> load -> set_state -> one more day, here on the host emulation; the same round trip on the B200 is in
+    tests/test_gpu_parity.py::test_state_checkpoint_roundtrip's state buffers."""
+    desc, sites, forcing = _problem()
+    e1 = HostEmuEngine(desc, S)
+    e1.set_sites(sites)
+    o1 = M.OutputBatch(1, desc.n_soil, S, ("soil_temperature",))
+    e1.step_days(0, forcing.day_slice(0, 1), o1)
+    ck = e1.get_state()
+    assert ck.status.dtype == np.int32 and np.array_equal(ck.status, o1.status)
+    ck.status[::3] |= 4                              # pretend every third site hit the Newton cap on day 0
+    st.save_state(tmp_path / "state.mcb", ck)
+    back = st.load_state(tmp_path / "state.mcb")
+    assert np.array_equal(back.status, ck.status)
+    e2 = HostEmuEngine(desc, S)
+    e2.set_sites(sites)
+    e2.set_state(back)
+    o2 = M.OutputBatch(1, desc.n_soil, S, ("soil_temperature",))
+    e2.step_days(1, forcing.day_slice(1, 2), o2)
+    assert np.all(o2.status[::3] & 4) and np.array_equal(o2.status & ~4, e2.get_state().status & ~4)
+    # a shard of the checkpoint
+    part = st.load_state(tmp_path / "state.mcb", 3, 9)
+    assert np.array_equal(part.status, ck.status[3:9])
