@@ -31,6 +31,8 @@
 extern "C" {
 #endif
 
+/* bumped on every layout change of a struct below (2: mc_state_soa.status, the weather structs); bindings compare it and mc_abi_sizeof() with their mirrors */
+#define MC_ABI_VERSION 2
 #define MC_MAX_SOIL_NODES 24
 #define MC_SNOW_NODES 8
 #define MC_MAX_ODE_NODES (MC_MAX_SOIL_NODES + MC_SNOW_NODES)

@@ -5,6 +5,7 @@ oracle wrapper (`oracle/oracle.py`), so both sides are fed byte-identical buffer
 """
 import ctypes as C
 
+MC_ABI_VERSION = 2
 MC_MAX_SOIL_NODES = 24
 MC_SNOW_NODES = 8
 MC_MAX_ODE_NODES = MC_MAX_SOIL_NODES + MC_SNOW_NODES

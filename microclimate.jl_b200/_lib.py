@@ -119,6 +119,8 @@ def lib():
                                       C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA), C.POINTER(A.WeatherOutSoA)]
     L.mc_abi_sizeof.argtypes = [C.c_int]
     L.mc_abi_sizeof.restype = C.c_int64
+    if L.mc_abi_version() != A.MC_ABI_VERSION:
+        raise RuntimeError(f"{SO}: ABI version {L.mc_abi_version()}, this package expects {A.MC_ABI_VERSION} - rebuild the library (stale build?)")
     # a stale or foreign library whose struct layout differs from the ctypes mirrors would corrupt memory silently: refuse it
     for k, cls in enumerate(A.ABI_SIZEOF):
         if L.mc_abi_sizeof(k) != C.sizeof(cls):

@@ -371,7 +371,7 @@ static void fill_site_state_args(mc_handle* h, mcd::KArgs& a)
 /* ---------------------------------------------------------------- C ABI ---- */
 extern "C" {
 
-int mc_abi_version(void) { return 1; }
+int mc_abi_version(void) { return MC_ABI_VERSION; }
 const char* mc_backend_name(void) { return "cuda-sm_100a"; }
 
 void mc_default_fluid(mc_fluid_constants* f)

@@ -27,19 +27,31 @@ def test_every_declared_symbol_is_exported(L):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.mc_abi_version() == 1 and L.mc_backend_name() == b"cuda-sm_100a"
+    assert L.mc_abi_version() == A.MC_ABI_VERSION == 2 and L.mc_backend_name() == b"cuda-sm_100a"
 
 
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors (microclimate.jl_b200/_abi.py) vs sizes computed by the C compiler from the header."""
     import subprocess, tempfile
-    src = '#include "microclimate_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mc_fluid_constants), sizeof(mc_snow_desc), sizeof(mc_model_desc), sizeof(mc_sites_soa), sizeof(mc_initial_soa), sizeof(mc_state_soa), sizeof(mc_forcing_soa), sizeof(mc_output_soa), sizeof(mc_counters));return 0;}\n'
+    names = ["mc_fluid_constants", "mc_snow_desc", "mc_model_desc", "mc_sites_soa", "mc_initial_soa", "mc_state_soa", "mc_forcing_soa", "mc_output_soa", "mc_counters",
+             "mc_time_of_day", "mc_diel_shape", "mc_diel_curve", "mc_weather_desc", "mc_solar_sites_soa", "mc_weather_in_soa", "mc_weather_out_soa"]
+    mirrors = [A.FluidConstants, A.SnowDesc, A.ModelDesc, A.SitesSoA, A.InitialSoA, A.StateSoA, A.ForcingSoA, A.OutputSoA, A.Counters,
+               A.TimeOfDay, A.DielShape, A.DielCurve, A.WeatherDesc, A.SolarSitesSoA, A.WeatherInSoA, A.WeatherOutSoA]
+    # sizes AND the offset of every field, computed by the C compiler from the header
+    lines = []
+    for n, m in zip(names, mirrors):
+        lines.append('printf("%%zu", sizeof(%s));' % n)
+        for fname, _ in m._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (n, fname))
+        lines.append('printf("\\n");')
+    src = '#include "microclimate_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){%s return MC_ABI_VERSION == %d ? 0 : 1;}\n' % ("".join(lines), A.MC_ABI_VERSION)
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
-        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
-    mirrors = [A.FluidConstants, A.SnowDesc, A.ModelDesc, A.SitesSoA, A.InitialSoA, A.StateSoA, A.ForcingSoA, A.OutputSoA, A.Counters]
-    assert sizes == [C.sizeof(m) for m in mirrors]
+        rows = [[int(x) for x in l.split()] for l in subprocess.check_output([os.path.join(d, "s")]).decode().splitlines()]
+    for n, m, row in zip(names, mirrors, rows):
+        assert row[0] == C.sizeof(m), n
+        assert row[1:] == [getattr(m, fname).offset for fname, _ in m._fields_], n
 
 
 def test_default_model_mirrors_reference_defaults(L):
