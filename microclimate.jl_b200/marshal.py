@@ -222,6 +222,8 @@ class ForcingBatch:
             h, d = inp.environment_hourly, inp.environment_daily
 
             def hv(x):
+                if x is None:               # a min/max-driven problem leaves these `nothing` (test/micro_testrun_monthly.jl:66-76): populate_weather! fills them
+                    return np.zeros(H)
                 x = np.asarray(x, float)
                 return np.broadcast_to(x, (H,)) if x.ndim == 0 or x.shape[0] == 1 else x[:H]
             b.pressure[:, s] = hv(h.pressure)

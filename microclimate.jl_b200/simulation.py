@@ -274,6 +274,10 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
         key = lambda i: (i.initial_snow_depth, i.initial_snow_temperature, i.initial_snow_density)      # noqa: E731
         if any(key(i) != key(inputs[0]) for i in inputs[1:]):
             raise ValueError("initial_snow_depth / _temperature / _density must be identical for all sites of a batch (model-level in the C ABI)")
+    for name in ("reference_temperature", "reference_wind_speed", "reference_humidity", "cloud_cover", "global_radiation", "zenith_angle"):
+        if any(getattr(i.environment_hourly, name) is None for i in inputs):
+            raise ValueError(f"environment_hourly.{name} is missing: solve_soil_batched needs the hourly weather populate_weather! leaves in cache.output "
+                             "(for min/max-driven inputs use solve_minmax_batched)")
     desc = M.model_desc(model, time_mode, inputs0=inputs[0])
     sites = M.SitesBatch.from_inputs(model, inputs)
     forcing = M.ForcingBatch.from_inputs(model, inputs, days)
@@ -300,6 +304,69 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
                 out.assign_rows(24 * r0, p0)
             out.status[:] = eng.status()
     return out
+
+
+def solve_minmax_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, days: Sequence[int], clear_sky_direct, clear_sky_diffuse,
+                         time_mode=None, shortwave=None, geometry=None, fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS, device: int = 0,
+                         chunk_days: Optional[int] = None, zenith_angle=None, zenith_slope_angle=None, return_weather: bool = False, engine_factory=None):
+    """Batched `solve!(cache)` for min/max-driven problems (src/simulation.jl:246-260): every `inputs[s].environment_minmax` (MonthlyMinMaxEnvironment /
+    DailyMinMaxEnvironment, all with the same forcing model) is expanded to hourly weather ON THE DEVICE (populate_weather!), the soil path integrates it
+    (solve_soil!, plus solve_air! when profile fields are selected) and only the selected outputs come back (mc_step_days_minmax).
+
+    `clear_sky_direct` / `clear_sky_diffuse` are SolarRadiation.jl's hourly clear-sky irradiances on the horizontal, [24*ndays][S] (its spectral model is not part of
+    this library).  Zenith and slope-zenith angles come from the built-in geometry (site latitude / slope / aspect) unless given.  `environment_hourly` supplies
+    `pressure` (scalar or hourly), rainfall / longwave when the model uses them, and an optional `global_radiation` override.  Returns the OutputBatch, and with
+    `return_weather` also the expanded hourly weather (WeatherOutBatch)."""
+    from . import weather as W
+    time_mode = time_mode if time_mode is not None else T.NonConsecutiveDayMode()
+    if len(inputs) == 0 or any(i.environment_minmax is None for i in inputs):
+        raise ValueError("every input needs environment_minmax (use solve_soil_batched for hourly-driven problems)")
+    ndays, S = len(days), len(inputs)
+    H = 24 * ndays
+    env0 = inputs[0].environment_minmax
+    curves = {q: env0.forcings[q].curve for q in A.WEATHER_QUANTITIES}
+    for i in inputs[1:]:
+        if any(i.environment_minmax.forcings[q].curve is not curves[q] and
+               (i.environment_minmax.forcings[q].curve.shapes, i.environment_minmax.forcings[q].curve.inputs) != (curves[q].shapes, curves[q].inputs)
+               for q in A.WEATHER_QUANTITIES):
+            raise ValueError("all sites of a batch must share one forcing model (the DielCurves are model-level in the C ABI)")
+    wdesc = W.weather_desc(curves, shortwave or W.AngstromMaxwellShortwave(), geometry or W.SolarGeometry())
+    desc = M.model_desc(model, time_mode, inputs0=inputs[0])
+    sites = M.SitesBatch.from_inputs(model, inputs)
+    rest = M.ForcingBatch.from_inputs(model, inputs, days)
+    h0 = inputs[0].environment_hourly
+    gr = np.ascontiguousarray(rest.global_radiation) if h0.global_radiation is not None else None
+    win = W.WeatherInBatch.from_environments(np.asarray(days, dtype=np.int32), [i.environment_minmax for i in inputs],
+                                             direct_horizontal=clear_sky_direct, diffuse_horizontal=clear_sky_diffuse,
+                                             global_radiation_hourly=gr, pressure_hourly=rest.pressure)
+    solar = W.SolarSitesBatch([i.site.latitude for i in inputs], [i.site.slope for i in inputs], [i.site.aspect for i in inputs])
+    own_zenith = zenith_angle is not None and zenith_slope_angle is not None
+    if own_zenith:
+        rest.zenith_angle[...] = np.minimum(zenith_angle, 90.0)
+        rest.zenith_slope_angle[...] = np.minimum(zenith_slope_angle, 90.0)
+    out = M.OutputBatch(ndays, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
+    wx = W.WeatherOutBatch(ndays, S) if return_weather else None
+    eng = (engine_factory or (lambda d, n: SoilEngine(d, n, device)))(desc, S)
+    try:
+        eng.set_sites(sites)
+        cd = ndays if not chunk_days else min(int(chunk_days), ndays)
+        d0 = 0
+        while d0 < ndays:
+            d1 = min(ndays, d0 + cd)
+            part = out if (d0 == 0 and d1 == ndays) else M.OutputBatch(d1 - d0, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
+            wpart = wx if (d0 == 0 and d1 == ndays) or wx is None else W.WeatherOutBatch(d1 - d0, S)
+            eng.step_days_minmax(d0, wdesc, win.day_slice(d0, d1), rest.day_slice(d0, d1), part, solar, wpart, use_rest_zenith=own_zenith)
+            if part is not out:
+                out.assign_rows(24 * d0, part)
+                if wx is not None:
+                    for k in A.WEATHER_OUT_HOURLY:
+                        getattr(wx, k)[24 * d0:24 * d1] = getattr(wpart, k)
+                    for k in A.WEATHER_OUT_DAILY:
+                        getattr(wx, k)[d0:d1] = getattr(wpart, k)
+            d0 = d1
+    finally:
+        eng.close()
+    return (out, wx) if return_weather else out
 
 
 def solve_soil(problem: T.MicroProblem, **kw) -> T.MicroResult:

@@ -267,14 +267,16 @@ class DailyTimeseries:                           # src/inputs/daily_timeseries.j
 class HourlyWeather:
     """What `populate_weather!` + `solve_solar!` leave in `cache.output` / `solar_out` for solve_soil!
     to read (src/simulation.jl:1006-1021,1056-1062): hourly vectors of length 24*ndays.
-    `rainfall`/`longwave_radiation` are HourlyTimeseries fields (src/inputs/hourly_timeseries.jl:1-11)."""
+    `rainfall`/`longwave_radiation` are HourlyTimeseries fields (src/inputs/hourly_timeseries.jl:1-11).
+    For a min/max-driven problem (MicroInputs.environment_minmax set) only `pressure` (+ rainfall / longwave / an optional global_radiation override)
+    is given, as in the reference's HourlyTimeseries with `nothing` fields; solve_minmax_batched fills the rest on the device."""
     pressure: np.ndarray
-    reference_temperature: np.ndarray            # K
-    reference_wind_speed: np.ndarray
-    reference_humidity: np.ndarray               # 0..1
-    cloud_cover: np.ndarray                      # 0..1
-    global_radiation: np.ndarray                 # W/m2
-    zenith_angle: np.ndarray                     # deg (capped at 90)
+    reference_temperature: Optional[np.ndarray] = None   # K
+    reference_wind_speed: Optional[np.ndarray] = None
+    reference_humidity: Optional[np.ndarray] = None      # 0..1
+    cloud_cover: Optional[np.ndarray] = None             # 0..1
+    global_radiation: Optional[np.ndarray] = None        # W/m2
+    zenith_angle: Optional[np.ndarray] = None            # deg (capped at 90)
     diffuse_fraction: Optional[np.ndarray] = None
     zenith_slope_angle: Optional[np.ndarray] = None
     rainfall: Optional[np.ndarray] = None
@@ -292,6 +294,7 @@ class MicroInputs:                               # src/types.jl:146-157
     initial_snow_depth: float = 0.0              # cm
     initial_snow_temperature: float = 273.15
     initial_snow_density: Optional[float] = None
+    environment_minmax: Optional[object] = None  # weather.MonthlyMinMaxEnvironment / DailyMinMaxEnvironment (src/types.jl:149); None = hourly-driven
 
 
 @dataclass

@@ -327,6 +327,15 @@ class WeatherInBatch:
                       for i in range(len(envs[0].forcings[q].values))) for q in A.WEATHER_QUANTITIES}
         return cls(days, S, f, **kw)
 
+    def day_slice(self, d0: int, d1: int) -> "WeatherInBatch":
+        """Days [d0, d1) of this batch (time-chunked runs)."""
+        cut = lambda a, k: None if a is None else np.ascontiguousarray(a[k * d0:k * d1])      # noqa: E731
+        return WeatherInBatch(self.days[d0:d1], self.S, {q: tuple(cut(v, 1) for v in self.forcings[q]) for q in A.WEATHER_QUANTITIES},
+                              direct_horizontal=cut(self.direct_horizontal, 24), diffuse_horizontal=cut(self.diffuse_horizontal, 24),
+                              hour_solar_noon=cut(self.hour_solar_noon, 1), hour_angle_sunrise=cut(self.hour_angle_sunrise, 1),
+                              global_radiation_hourly=cut(self.global_radiation_hourly, 24), pressure_hourly=cut(self.pressure_hourly, 24),
+                              pressure_site=self.pressure_site)
+
     def c_struct(self) -> A.WeatherInSoA:
         c = A.WeatherInSoA()
         for q in A.WEATHER_QUANTITIES:

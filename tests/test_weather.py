@@ -457,3 +457,55 @@ def test_config1_driven_from_its_minmax_inputs_meets_the_reference_tolerances():
     assert np.abs(T / Tn - 1).max() < 1e-1                                   # the reference's own bar
     assert np.abs(T / Tn - 1).max() < 2e-2 and np.sqrt(np.mean((T - Tn) ** 2)) < 0.25      # what is actually observed (1.2e-2, 0.18 K)
     assert relnorm(out.sky_temperature[:, 0], g["TSKYC"]) <= 2e-3
+
+
+def test_solve_minmax_batched_reference_shaped_call():
+    check_solve_minmax_batched(HE.WeatherApiEmu)
+
+
+def check_solve_minmax_batched(engine_factory):
+    """The host mirror's one-call form of solve!(cache) for min/max-driven inputs (MicroInputs.environment_minmax, HourlyTimeseries with `nothing` weather fields, as
+    test/micro_testrun_monthly.jl:66-102 builds them): config 1 for three sites, whole and in day chunks, against populate-then-solve with the oracle."""
+    import copy
+    import configs
+    import parity
+    import microclimate_jl_b200 as mc
+    from microclimate_jl_b200 import marshal as M, simulation as sim
+    from oracle.oracle import OracleEngine
+    p, g = configs.config1_monthly()
+    days, env = _monthly_inputs()
+    S = 3
+    inputs, envs = [], []
+    for s in range(S):
+        f = W.minmax_forcings(reference_temperature_min=GOLD["monthly_tmin_C"] + 273.15 - 2.0 * s, reference_temperature_max=GOLD["monthly_tmax_C"] + 273.15 - 1.5 * s,
+                              reference_wind_speed_min=GOLD["monthly_wind_min"], reference_wind_speed_max=GOLD["monthly_wind_max"] * (1 + 0.1 * s),
+                              reference_humidity_min=GOLD["monthly_rh_min"], reference_humidity_max=GOLD["monthly_rh_max"],
+                              cloud_cover_min=GOLD["monthly_cloud_min"] * 0.5, cloud_cover_max=GOLD["monthly_cloud_max"])
+        i = copy.deepcopy(p.inputs)
+        i.environment_minmax = W.MonthlyMinMaxEnvironment(f)
+        i.environment_hourly = mc.HourlyWeather(pressure=float(g["pressure"]))
+        i.site.latitude, i.site.slope, i.site.aspect = float(GOLD["zen_monthly_lat"]) - 10.0 * s, 12.0 * s, 135.0
+        inputs.append(i)
+    H = 24 * len(days)
+    clear = np.stack([g["SOLR"] * (1.0 + 0.2 * s) for s in range(S)], axis=1)
+    with pytest.raises(ValueError, match="solve_minmax_batched"):
+        sim.solve_soil_batched(p.model, inputs, days=p.days, time_mode=p.time_mode)
+    out, wx = sim.solve_minmax_batched(p.model, inputs, days=p.days, time_mode=p.time_mode, clear_sky_direct=0.8 * clear, clear_sky_diffuse=0.2 * clear,
+                                       fields=parity.ALL_FIELDS, return_weather=True, engine_factory=engine_factory)
+    # reference: oracle weather -> hourly forcing -> oracle soil
+    win = W.WeatherInBatch.from_environments(days, [i.environment_minmax for i in inputs], direct_horizontal=0.8 * clear, diffuse_horizontal=0.2 * clear,
+                                             pressure_site=np.full(S, float(g["pressure"])))
+    ref_wx = W.WeatherOutBatch(len(days), S)
+    O.populate_weather(W.weather_desc(), win, ref_wx, W.SolarSitesBatch([i.site.latitude for i in inputs], [i.site.slope for i in inputs], [i.site.aspect for i in inputs]))
+    for k in ALL_OUT:
+        assert np.array_equal(getattr(wx, k), getattr(ref_wx, k)), k
+    desc = M.model_desc(p.model, p.time_mode, inputs0=inputs[0])
+    hourly = M.ForcingBatch.from_inputs(p.model, inputs, p.days)
+    for k in A.WEATHER_OUT_HOURLY:
+        getattr(hourly, k)[...] = getattr(ref_wx, k)
+    ref, _ = parity.run(OracleEngine, desc, M.SitesBatch.from_inputs(p.model, inputs), hourly, fields=parity.ALL_FIELDS)
+    parity.assert_bit_identical(out, ref, parity.ALL_FIELDS)
+    assert ref.soil_temperature[:, 0, 0].std() > 5.0 and not np.array_equal(ref.soil_temperature[:, :, 0], ref.soil_temperature[:, :, 2])
+    chunked = sim.solve_minmax_batched(p.model, inputs, days=p.days, time_mode=p.time_mode, clear_sky_direct=0.8 * clear, clear_sky_diffuse=0.2 * clear,
+                                       fields=parity.ALL_FIELDS, chunk_days=5, engine_factory=engine_factory)
+    parity.assert_bit_identical(chunked, ref, parity.ALL_FIELDS)          # PrescribedSoilMoisture: no humidity rows, nothing chunk-dependent

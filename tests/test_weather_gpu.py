@@ -14,7 +14,7 @@ from microclimate_jl_b200 import synthetic as syn
 from microclimate_jl_b200 import weather as W
 from oracle import oracle as O
 from oracle.oracle import OracleEngine
-from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _random_problem, _soil_case
+from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _random_problem, _soil_case, check_solve_minmax_batched
 
 pytestmark = pytest.mark.gpu
 
@@ -97,3 +97,8 @@ def test_step_days_minmax_matches_populate_then_solve(SoilEngine):
             out.assign_rows(24 * d, part)
         # soil_humidity: see tests/test_weather.py (row 1 quirk of initialise_soil_humidity! under chunking)
         parity.assert_bit_identical(out, ref, tuple(k for k in fields if k != "soil_humidity"))
+
+
+def test_solve_minmax_batched_on_the_b200(SoilEngine):
+    """solve_minmax_batched (config 1 from its min/max inputs, three sites incl. sloped ones, whole and in day chunks) through the CUDA library == oracle weather + oracle soil."""
+    check_solve_minmax_batched(None)
