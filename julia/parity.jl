@@ -65,6 +65,29 @@ for script in ("micro_testrun_monthly.jl", "micro_testrun_daily.jl", "micro_test
     report(script, ref, gpu, status)
 end
 
+# ---- weather: populate_weather! vs the device expansion on the min/max-driven problems (configs 1, 3, 4) ---------------------------------------------
+# The diel engine and Angstrom / Erbs are restated from the reference's own source, so the expected deviation is the last bits of exp / cospi / sind; the solar
+# noon and sunrise hour angle are taken from SolarRadiation.jl here (builtin_geometry = false).  A second pass with builtin_geometry = true reports how far the
+# library's own geometry (anchored on NicheMapR's ZEN goldens, DESIGN.md section 7) moves the hourly weather.
+function weather_report(script)
+    p = reference_problem(script)
+    isnothing(p.inputs.environment_minmax) && return
+    ref = init(p); Microclimate.solve_solar!(ref); Microclimate.populate_weather!(ref)
+    for builtin in (false, true)
+        gpu = init(p); Microclimate.solve_solar!(gpu)
+        MicroclimateB200.populate_weather_batched!([gpu]; builtin_geometry = builtin)
+        println("== weather of ", script, builtin ? "  (built-in geometry)" : "  (SolarRadiation.jl's solar noon / sunrise)")
+        for (f, unit) in ((:reference_temperature, u"K"), (:reference_wind_speed, u"m/s"), (:reference_humidity, NoUnits), (:cloud_cover, NoUnits),
+                          (:global_radiation, u"W/m^2"), (:diffuse_fraction, NoUnits))
+            d = abs.(ustrip.(unit, getproperty(ref.output, f)) .- ustrip.(unit, getproperty(gpu.output, f)))
+            println(rpad("   " * String(f), 26), " max = ", maximum(d), "   p99.9 = ", quantile(vec(d), 0.999))
+        end
+    end
+end
+for script in ("micro_testrun_monthly.jl", "micro_testrun_monthly_snow.jl", "micro_testrun_snow_scan329.jl")
+    isfile(joinpath(REFTEST, script)) && weather_report(script)
+end
+
 # ---- 5: first 1000 sites of a synthetic grid from the on-disk containers -----------------------------------------------------------------------
 "Memory-map one container of microclimate.jl_b200/storage.py: returns (header, name => array) with arrays site-fastest (Julia dims reversed)."
 function read_container(path)
