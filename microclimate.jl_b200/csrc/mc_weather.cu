@@ -174,12 +174,17 @@ int make_args(mc_handle* h, int32_t ndays, const mc_weather_desc* w, const mc_so
     return 0;
 }
 
+#ifdef MCW_HOST_EMULATION
+bool mcw_emulation_check(const mcw::WArgs& a);         /* the harness knows which addresses its stand-in cudaMalloc handed out */
+#endif
+
 int launch(mc_handle* h, const mc_weather_desc* w, const mcw::WArgs& a)
 {
     const dim3 grid((unsigned)((a.S + WX_BLOCK - 1) / WX_BLOCK), (unsigned)a.ndays);
 #ifndef MCW_HOST_EMULATION
     weather_kernel<<<grid, WX_BLOCK, 0, mc_i_stream(h)>>>(*w, a);
 #else
+    if (!mcw_emulation_check(a)) return mc_i_fail(h, "emulation: a pointer that is not device memory reached weather_kernel", -9);
     for (blockIdx.y = 0; blockIdx.y < grid.y; blockIdx.y++) for (blockIdx.x = 0; blockIdx.x < grid.x; blockIdx.x++)
         for (threadIdx.x = 0; threadIdx.x < (unsigned)WX_BLOCK; threadIdx.x++) weather_kernel(*w, a);
 #endif

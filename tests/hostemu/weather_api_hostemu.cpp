@@ -19,12 +19,36 @@ static dim3 blockIdx, threadIdx;
 #define __launch_bounds__(n)
 #define __grid_constant__
 static long g_fake_allocs = 0;
+/* every live "device" allocation, so the harness can tell device memory from host memory the way a real GPU would (by faulting) */
+struct FakeAlloc { const char* base; size_t bytes; };
+static std::vector<FakeAlloc> g_fake_live;
+static bool g_allow_foreign = false;                     /* the *_device entry points are handed caller-owned "device" memory */
+static bool fake_is_device(const void* p)
+{
+    if (!p || g_allow_foreign) return true;
+    for (const FakeAlloc& a : g_fake_live) if ((const char*)p >= a.base && (const char*)p < a.base + a.bytes) return true;
+    return false;
+}
 static inline const char* cudaGetErrorString(cudaError_t) { return "fake"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std::malloc(n ? n : 1); std::memset(*p, 0xA5, n); g_fake_allocs++; return *p ? cudaSuccess : 2; }
-static inline cudaError_t cudaFree(void* p) { if (p) g_fake_allocs--; std::free(p); return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n)
+{
+    *p = (T*)std::malloc(n ? n : 1);
+    if (!*p) return 2;
+    std::memset(*p, 0xA5, n);
+    g_fake_allocs++; g_fake_live.push_back({(const char*)*p, n ? n : 1});
+    return cudaSuccess;
+}
+static inline cudaError_t cudaFree(void* p)
+{
+    if (!p) return cudaSuccess;
+    g_fake_allocs--;
+    for (size_t i = 0; i < g_fake_live.size(); i++) if (g_fake_live[i].base == (const char*)p) { g_fake_live.erase(g_fake_live.begin() + (long)i); break; }
+    std::free(p);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
 
@@ -42,6 +66,17 @@ struct mc_handle { void* emu; int64_t S; mc_model_desc model; std::string err; s
 
 #include "../../microclimate.jl_b200/csrc/mc_weather.cu"
 
+namespace {
+bool mcw_emulation_check(const mcw::WArgs& a)
+{
+    const void* ptrs[] = {a.doy, a.lat, a.slope, a.aspect, a.noon_off, a.noon_in, a.ha_in, a.direct, a.diffuse, a.gr_hourly, a.p_hourly, a.p_site,
+                          a.o_P, a.o_T, a.o_wind, a.o_rh, a.o_cloud, a.o_gr, a.o_df, a.o_zen, a.o_szen, a.o_noon, a.o_ha};
+    for (const void* p : ptrs) if (!fake_is_device(p)) return false;
+    for (int q = 0; q < 4; q++) for (int i = 0; i < MC_DIEL_MAX_INPUTS; i++) if (!fake_is_device(a.vals[q][i])) return false;
+    return true;
+}
+}
+
 int mc_i_device(const mc_handle*) { return 0; }
 cudaStream_t mc_i_stream(const mc_handle*) { return nullptr; }
 int64_t mc_i_sites(const mc_handle* h) { return h->S; }
@@ -54,6 +89,15 @@ int mc_wait(mc_handle*) { return 0; }
 int mc_synchronize(mc_handle*) { return 0; }
 int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, mc_output_soa* o)
 {
+    /* the real entry point hands these pointers to a kernel: every one must be device memory (day_of_year is the documented host pointer) */
+    const void* fp[] = {f->pressure, f->reference_temperature, f->reference_wind_speed, f->reference_humidity, f->cloud_cover, f->global_radiation, f->diffuse_fraction,
+                        f->zenith_angle, f->zenith_slope_angle, f->rainfall_hourly, f->longwave_radiation, f->leaf_area_index, f->shade, f->surface_emissivity,
+                        f->cloud_emissivity, f->soil_wetness, f->deep_soil_temperature, f->rainfall_daily, f->albedo_daily, f->prescribed_soil_moisture,
+                        o->soil_temperature, o->soil_moisture, o->soil_water_potential, o->soil_humidity, o->soil_thermal_conductivity, o->soil_heat_capacity,
+                        o->soil_bulk_density, o->surface_water, o->sky_temperature, o->snow_fall, o->snow_depth, o->snow_density, o->snow_temperature,
+                        o->air_temperature, o->wind_speed, o->relative_humidity, o->convective_heat_flux, o->friction_velocity};
+    for (const void* p : fp) if (!fake_is_device(p)) { h->err = "emulation: mc_step_days_device was handed a pointer that is not device memory"; return -9; }
+    if (fake_is_device(f->day_of_year) && !g_allow_foreign && f->day_of_year) { h->err = "emulation: day_of_year must stay a host pointer"; return -9; }
     mc_output_soa oo = *o;
     oo.status = h->status.data();
     const int rc = he_step_days(h->emu, day0, ndays, f, &oo);
@@ -72,4 +116,5 @@ void wa_destroy(mc_handle* h) { if (!h) return; mc_i_weather_release(h); he_dest
 int wa_set_sites(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* i) { return he_set_sites(h->emu, s, i); }
 const char* wa_last_error(const mc_handle* h) { return h->err.c_str(); }
 long wa_live_allocations(void) { return g_fake_allocs; }
+void wa_allow_foreign_pointers(int on) { g_allow_foreign = on != 0; }
 }

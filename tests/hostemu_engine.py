@@ -193,7 +193,11 @@ class WeatherApiEmu:
         ci, co = win.c_struct(), wout.c_struct()
         cs = solar_sites.c_struct() if solar_sites is not None else None
         fn = self._L.mc_populate_weather_device if device_entry else self._L.mc_populate_weather
-        self._check(fn(self.h, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(co)), "mc_populate_weather")
+        self._L.wa_allow_foreign_pointers(1 if device_entry else 0)      # the *_device entry is handed caller-owned "device" memory (host arrays here)
+        try:
+            self._check(fn(self.h, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(co)), "mc_populate_weather")
+        finally:
+            self._L.wa_allow_foreign_pointers(0)
         return wout
 
     def step_days_minmax(self, day0, wdesc, win, rest, out, solar_sites=None, weather_out=None, use_rest_zenith=False):

@@ -94,6 +94,8 @@ def main():
         L, h = eng._L, eng.h
         eng_sync = (lambda: None) if args.emulate else eng.synchronize
         last_error = L.wa_last_error if args.emulate else L.mc_last_error
+        if args.emulate:
+            L.wa_allow_foreign_pointers(1)          # the emulation tells "device" from host memory; this entry point is handed caller-owned device memory
 
         def launch():
             rc = L.mc_populate_weather_device(h, D, C.byref(w), C.byref(cs), C.byref(ci), C.byref(co))
