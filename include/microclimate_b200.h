@@ -376,6 +376,10 @@ typedef struct mc_diel_curve {
 } mc_diel_curve;
 
 enum { MC_DIFFUSE_ERBS = 0 };                                    /* src/radiation/diffuse/erbs.jl */
+/* where the hourly relative humidity comes from: its own diel curve, or Derived(RelativeHumidityFromVapourPressureAndTemperature(GoffGratch()),
+ * (:actual_vapour_pressure, :reference_temperature)) (src/inputs/diel.jl:264-301, fill_derived! :438-444): the `reference_humidity` curve and value series then
+ * describe the ACTUAL VAPOUR PRESSURE in Pa and humidity = clamp(e / e_sat(T), 0, 1) hour by hour */
+enum { MC_HUMIDITY_CURVE = 0, MC_HUMIDITY_FROM_VAPOUR_PRESSURE = 1 };
 /* forcing model + shortwave model + geometry constants; mc_default_weather() = minmax_forcing_model() with its default offsets
  * (src/inputs/diel.jl:456-495), AngstromMaxwellShortwave(), Angstrom(0.36, 0.64, 1.0) */
 typedef struct mc_weather_desc {
@@ -384,6 +388,8 @@ typedef struct mc_weather_desc {
     double  solar_constant;                 /* W/m2, 1367 (angstrom_maxwell.jl:27) */
     int32_t diffuse_model;                  /* MC_DIFFUSE_* */
     int32_t refraction;                     /* 1: apparent zenith within 2 degrees of the horizon (NicheMapR SOLRAD; goldens need it) */
+    int32_t humidity_source;                /* MC_HUMIDITY_* */
+    int32_t _pad0;
     double  orbital_eccentricity;           /* 0.0167238 */
     double  sin_obliquity;                  /* 0.39784993 */
     double  days_per_year;                  /* 365 */

@@ -71,7 +71,7 @@ struct McDielCurve; n_shapes::Cint; n_inputs::Cint; shapes::NTuple{MC_DIEL_MAX_S
 struct McWeather
     reference_temperature::McDielCurve; reference_wind_speed::McDielCurve; reference_humidity::McDielCurve; cloud_cover::McDielCurve
     angstrom_a::Cdouble; angstrom_b::Cdouble; angstrom_gamma::Cdouble; solar_constant::Cdouble
-    diffuse_model::Cint; refraction::Cint
+    diffuse_model::Cint; refraction::Cint; humidity_source::Cint; _pad0::Cint
     orbital_eccentricity::Cdouble; sin_obliquity::Cdouble; days_per_year::Cdouble; equinox_day::Cdouble
 end
 struct McSolarSites; p::NTuple{4,Ptr{Cdouble}}; end         # latitude, slope, aspect, solar_noon_offset_h
@@ -270,7 +270,9 @@ function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integ
 end
 
 # ---- populate_weather! on the device (widening rows f2 / f3) ---------------------------------------------------------------------
-import Microclimate: Sunrise, Sunset, Midday, Midnight, ClockTime, Sine, Decay, Linear, DielCurve, DielForcing, AngstromMaxwellShortwave, Angstrom, ErbsDiffuseFraction
+import Microclimate: Sunrise, Sunset, Midday, Midnight, ClockTime, Sine, Decay, Linear, DielCurve, DielForcing, Derived, RelativeHumidityFromVapourPressureAndTemperature,
+    AngstromMaxwellShortwave, Angstrom, ErbsDiffuseFraction
+import Microclimate: derived_inputs
 
 tod(t::ClockTime) = McTimeOfDay(0, 0, t.hour)
 tod(t::Sunrise) = McTimeOfDay(1, 0, t.offset)
@@ -291,14 +293,26 @@ end
 "mc_weather_desc from an environment's forcings (DielForcing per quantity) and the shortwave model; geometry constants = the library defaults."
 function weather_desc(forcings::NamedTuple, sw::AngstromMaxwellShortwave)
     sw.diffuse_fraction_model isa ErbsDiffuseFraction || error("only ErbsDiffuseFraction exists on the device")
-    all(f -> f isa DielForcing, (forcings.reference_temperature, forcings.reference_wind_speed, forcings.reference_humidity, forcings.cloud_cover)) ||
-        error("Derived forcing quantities are not supported on the device: expand them with Microclimate.populate_weather!")
+    all(f -> f isa DielForcing, (forcings.reference_temperature, forcings.reference_wind_speed, forcings.cloud_cover)) ||
+        error("Derived is supported on the device for reference_humidity only: expand the others with Microclimate.populate_weather!")
+    hum, hum_source = humidity_forcing(forcings)
     d = Ref{McWeather}()
     ccall((:mc_default_weather, LIB), Cvoid, (Ref{McWeather},), d)
     w, a = d[], sw.sunshine_fraction_model
-    McWeather(curve_desc(forcings.reference_temperature.curve), curve_desc(forcings.reference_wind_speed.curve), curve_desc(forcings.reference_humidity.curve),
-              curve_desc(forcings.cloud_cover.curve), a.a, a.b, a.gamma, w.solar_constant, w.diffuse_model, w.refraction,
+    McWeather(curve_desc(forcings.reference_temperature.curve), curve_desc(forcings.reference_wind_speed.curve), curve_desc(hum.curve),
+              curve_desc(forcings.cloud_cover.curve), a.a, a.b, a.gamma, w.solar_constant, w.diffuse_model, w.refraction, hum_source, 0,
               w.orbital_eccentricity, w.sin_obliquity, w.days_per_year, w.equinox_day)
+end
+
+"The DielForcing that fills the ABI's humidity slot and MC_HUMIDITY_*: the humidity's own curve (0), or the vapour-pressure forcing a Derived humidity reads (1)."
+function humidity_forcing(forcings::NamedTuple)
+    f = forcings.reference_humidity
+    f isa DielForcing && return f, Cint(0)
+    if f isa Derived && f.functor isa RelativeHumidityFromVapourPressureAndTemperature
+        names = derived_inputs(f)
+        length(names) == 2 && names[2] == :reference_temperature && getproperty(forcings, names[1]) isa DielForcing && return getproperty(forcings, names[1]), Cint(1)
+    end
+    error("reference_humidity must be a DielForcing or Derived(RelativeHumidityFromVapourPressureAndTemperature(GoffGratch()), (<vapour pressure>, :reference_temperature))")
 end
 
 """
@@ -317,11 +331,13 @@ function populate_weather_batched!(caches::AbstractVector{<:MicroCache}; device:
     envs = [c.problem.inputs.environment_minmax for c in caches]
     w = Ref(weather_desc(first(envs).forcings, mp.model.radiation.shortwave_model))
     so(c) = c.buffers.solar_out
+    hum_source = humidity_forcing(first(envs).forcings)[2]
+    slot(e, q) = q == :reference_humidity ? humidity_forcing(e.forcings)[1] : getproperty(e.forcings, q)      # the DielForcing behind each ABI slot
     quantities = (:reference_temperature, :reference_wind_speed, :reference_humidity, :cloud_cover)
-    units = (u"K", u"m/s", 1, 1)
+    units = (u"K", u"m/s", hum_source == 1 ? u"Pa" : 1, 1)
     # values[q][i][d, s] -> [D][S] site-fastest; eltype conversion as evaluate! does it (diel.jl:337)
-    series = [[Float64[si(unit == 1 ? collect(getproperty(e.forcings, q).values[i])[d] : unit(collect(getproperty(e.forcings, q).values[i])[d]), unit) for e in envs, d in 1:D]
-               for i in 1:length(getproperty(first(envs).forcings, q).values)] for (q, unit) in zip(quantities, units)]
+    series = [[Float64[si(unit == 1 ? collect(slot(e, q).values[i])[d] : unit(collect(slot(e, q).values[i])[d]), unit) for e in envs, d in 1:D]
+               for i in 1:length(slot(first(envs), q).values)] for (q, unit) in zip(quantities, units)]
     daily(f) = Float64[f(c, d) for c in caches, d in 1:D]
     hourly(f) = Float64[f(c, t) for c in caches, t in 1:H]
     noon = builtin_geometry ? Float64[] : daily((c, d) -> Float64(ustrip(so(c).hour_solar_noon[d])))

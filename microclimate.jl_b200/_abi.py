@@ -147,6 +147,7 @@ MC_SHAPE_SINE, MC_SHAPE_DECAY, MC_SHAPE_LINEAR = 0, 1, 2
 MC_DIEL_MAX_SHAPES = 6
 MC_DIEL_MAX_INPUTS = 6
 MC_DIFFUSE_ERBS = 0
+MC_HUMIDITY_CURVE, MC_HUMIDITY_FROM_VAPOUR_PRESSURE = 0, 1
 
 
 class TimeOfDay(C.Structure):
@@ -167,7 +168,7 @@ WEATHER_QUANTITIES = ("reference_temperature", "reference_wind_speed", "referenc
 class WeatherDesc(C.Structure):
     _fields_ = ([(n, DielCurve) for n in WEATHER_QUANTITIES]
                 + [("angstrom_a", _d), ("angstrom_b", _d), ("angstrom_gamma", _d), ("solar_constant", _d),
-                   ("diffuse_model", _i32), ("refraction", _i32),
+                   ("diffuse_model", _i32), ("refraction", _i32), ("humidity_source", _i32), ("_pad0", _i32),
                    ("orbital_eccentricity", _d), ("sin_obliquity", _d), ("days_per_year", _d), ("equinox_day", _d)])
 
 

@@ -140,6 +140,7 @@ int validate_weather(const mc_weather_desc* w, std::string& err)
     static const char* names[4] = {"reference_temperature", "reference_wind_speed", "reference_humidity", "cloud_cover"};
     for (int q = 0; q < 4; q++) if (int rc = validate_curve(*curve_of(w, q), names[q], err)) return rc;
     if (w->diffuse_model != MC_DIFFUSE_ERBS) { err = "diffuse_model: only MC_DIFFUSE_ERBS exists"; return -1; }
+    if (w->humidity_source != MC_HUMIDITY_CURVE && w->humidity_source != MC_HUMIDITY_FROM_VAPOUR_PRESSURE) { err = "humidity_source: unknown value"; return -1; }
     if (!(w->days_per_year > 0.0)) { err = "days_per_year must be positive"; return -1; }
     return 0;
 }
@@ -159,7 +160,7 @@ int make_args(mc_handle* h, int32_t ndays, const mc_weather_desc* w, const mc_so
     const bool want_sw = out->global_radiation || out->diffuse_fraction;
     if (want_sw && (!in->direct_horizontal || !in->diffuse_horizontal)) return mc_i_fail(h, "global_radiation / diffuse_fraction need the clear-sky direct_horizontal and diffuse_horizontal", -1);
     for (int q = 0; q < 4; q++) {
-        const bool wanted = wx_out_of(out, q) || (q == 3 && want_sw);
+        const bool wanted = wx_out_of(out, q) || (q == 3 && want_sw) || (q == 0 && out->reference_humidity && w->humidity_source == MC_HUMIDITY_FROM_VAPOUR_PRESSURE);
         for (int i = 0; i < curve_of(w, q)->n_inputs; i++) {
             if (wanted && !series_of(in, q)[i]) return mc_i_fail(h, "a value series of a wanted quantity is NULL (values[i] belongs to curve.inputs[i])", -1);
             a.vals[q][i] = series_of(in, q)[i];
@@ -236,6 +237,7 @@ void mc_default_weather(mc_weather_desc* w)
     w->solar_constant = 1367.0;                                   /* angstrom_maxwell.jl:27 */
     w->diffuse_model = MC_DIFFUSE_ERBS;
     w->refraction = 1;
+    w->humidity_source = MC_HUMIDITY_CURVE;
     w->orbital_eccentricity = 0.0167238; w->sin_obliquity = 0.39784993; w->days_per_year = 365.0; w->equinox_day = 80.0;
 }
 

@@ -141,6 +141,22 @@ MCW_DEV void resolve_curve(const mc_diel_curve& c, const Day& day, const double*
     }
 }
 
+/* vapour_pressure(GoffGratch(), T) [Pa] (FluidProperties.jl; the functor of Derived(RelativeHumidityFromVapourPressureAndTemperature), diel.jl:285-287) */
+MCW_DEV double saturation_vapour_pressure(double T)
+{
+    const double Tp = T + 0.01;
+    double loge;
+    if (Tp <= 273.16) {
+        const double r = 273.16 / Tp;
+        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - Tp / 273.16) + 0.7858350313586662;
+    } else {
+        const double r = 373.16 / Tp;
+        loge = -7.90298 * (r - 1.0) + 5.02808 * mcm::log10(r) - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - Tp / 373.16)) - 1.0)
+             + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314;
+    }
+    return 100.0 * mcm::exp10(loge);
+}
+
 /* ---- shortwave (angstrom_maxwell.jl:21-46) -------------------------------------------------------------------------------------- */
 MCW_DEV double erbs(double ci)                                                           /* erbs.jl:14-23 */
 {
@@ -244,10 +260,12 @@ MCW_DEV void site_day(const mc_weather_desc& w, const WArgs& a, int64_t s, int d
     day.sunset = 2 * noon - day.sunrise;
 
     const bool want_sw = a.o_gr || a.o_df;
+    const bool derived_rh = w.humidity_source == MC_HUMIDITY_FROM_VAPOUR_PRESSURE && a.o_rh;
     const mc_diel_curve* curves[4] = {&w.reference_temperature, &w.reference_wind_speed, &w.reference_humidity, &w.cloud_cover};
     double* dst[4] = {a.o_T, a.o_wind, a.o_rh, a.o_cloud};
+    double T_hour[24];                                             /* only touched when the humidity is derived from vapour pressure and temperature */
     for (int q = 0; q < 4; q++) {
-        if (!dst[q] && !(q == 3 && want_sw)) continue;
+        if (!dst[q] && !(q == 3 && want_sw) && !(q == 0 && derived_rh)) continue;
         const mc_diel_curve& c = *curves[q];
         double vals[MC_DIEL_MAX_INPUTS];
         for (int i = 0; i < MC_DIEL_MAX_INPUTS; i++) vals[i] = (i < c.n_inputs && a.vals[q][i]) ? MCW_LDG(a.vals[q][i] + ds) : qnan();
@@ -257,6 +275,8 @@ MCW_DEV void site_day(const mc_weather_desc& w, const WArgs& a, int64_t s, int d
         for (int h = 0; h < 24; h++) {
             const size_t hs = h0 + (size_t)h * S;
             double v = sample(r, (double)h);
+            if (q == 0 && derived_rh) T_hour[h] = v;
+            if (q == 2 && derived_rh) v = clampd(v / saturation_vapour_pressure(T_hour[h]), 0.0, 1.0);      /* fill_derived!, diel.jl:285-287,438-444 */
             if (q >= 2 && v > 1.0) v = 1.0;                        /* humidity and cloud cover, src/simulation.jl:317-326 */
             if (dst[q]) dst[q][hs] = v;
             if (q == 3 && want_sw) {

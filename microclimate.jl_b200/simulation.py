@@ -324,13 +324,14 @@ def solve_minmax_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *
     ndays, S = len(days), len(inputs)
     H = 24 * ndays
     env0 = inputs[0].environment_minmax
-    curves = {q: env0.forcings[q].curve for q in A.WEATHER_QUANTITIES}
+    curves = {q: W.forcing_of(env0.forcings, q).curve for q in A.WEATHER_QUANTITIES}
     for i in inputs[1:]:
-        if any(i.environment_minmax.forcings[q].curve is not curves[q] and
-               (i.environment_minmax.forcings[q].curve.shapes, i.environment_minmax.forcings[q].curve.inputs) != (curves[q].shapes, curves[q].inputs)
-               for q in A.WEATHER_QUANTITIES):
+        fi = i.environment_minmax.forcings
+        if W.humidity_forcing(fi)[1] != W.humidity_forcing(env0.forcings)[1] or any(
+                W.forcing_of(fi, q).curve is not curves[q] and (W.forcing_of(fi, q).curve.shapes, W.forcing_of(fi, q).curve.inputs) != (curves[q].shapes, curves[q].inputs)
+                for q in A.WEATHER_QUANTITIES):
             raise ValueError("all sites of a batch must share one forcing model (the DielCurves are model-level in the C ABI)")
-    wdesc = W.weather_desc(curves, shortwave or W.AngstromMaxwellShortwave(), geometry or W.SolarGeometry())
+    wdesc = W.weather_desc(None, shortwave or W.AngstromMaxwellShortwave(), geometry or W.SolarGeometry(), forcings=env0.forcings)
     desc = M.model_desc(model, time_mode, inputs0=inputs[0])
     sites = M.SitesBatch.from_inputs(model, inputs)
     rest = M.ForcingBatch.from_inputs(model, inputs, days)

@@ -207,6 +207,52 @@ def minmax_forcings(*, reference_temperature_min, reference_temperature_max, ref
     return {k: DielForcing(spec.curve, tuple(g[n] for n in spec.inputs)) for k, spec in model.items()}
 
 
+# ---- Derived quantities (diel.jl:264-312): computed hour by hour from other quantities instead of interpolated from a curve ----
+@dataclass(frozen=True)
+class GoffGratch:                                           # FluidProperties.jl's default vapour-pressure equation (the only one the path uses)
+    pass
+
+
+@dataclass(frozen=True)
+class RelativeHumidityFromVapourPressureAndTemperature:     # diel.jl:280-287: (e, T) -> clamp(e / e_sat(T), 0, 1)
+    saturation_method: object = field(default_factory=GoffGratch)
+
+
+@dataclass(frozen=True)
+class VapourPressureFromRelativeHumidityAndTemperature:     # diel.jl:289-301: (rh, T) -> rh * e_sat(T); an intermediate, never an output of populate_weather!
+    saturation_method: object = field(default_factory=GoffGratch)
+
+
+@dataclass(frozen=True)
+class Derived:
+    functor: object
+    inputs: Tuple[str, ...]
+
+
+def humidity_forcing(forcings: Dict[str, object]):
+    """The DielForcing that fills the ABI's reference_humidity slot, and mc_weather_desc.humidity_source: the humidity's own curve, or — for
+    `reference_humidity = Derived(RelativeHumidityFromVapourPressureAndTemperature(GoffGratch()), ("actual_vapour_pressure", "reference_temperature"))` — the
+    curve and series of the vapour pressure it is derived from (Pa)."""
+    f = forcings["reference_humidity"]
+    if isinstance(f, DielForcing):
+        return f, A.MC_HUMIDITY_CURVE
+    if (isinstance(f, Derived) and isinstance(f.functor, RelativeHumidityFromVapourPressureAndTemperature) and isinstance(f.functor.saturation_method, GoffGratch)
+            and len(f.inputs) == 2 and f.inputs[1] == "reference_temperature" and isinstance(forcings.get(f.inputs[0]), DielForcing)):
+        return forcings[f.inputs[0]], A.MC_HUMIDITY_FROM_VAPOUR_PRESSURE
+    raise ValueError("reference_humidity must be a DielForcing or Derived(RelativeHumidityFromVapourPressureAndTemperature(GoffGratch()), "
+                     "(<vapour pressure forcing>, 'reference_temperature')); other Derived quantities are not on the device")
+
+
+def forcing_of(forcings: Dict[str, object], q: str) -> DielForcing:
+    """The DielForcing behind the ABI slot of output quantity q."""
+    if q == "reference_humidity":
+        return humidity_forcing(forcings)[0]
+    f = forcings[q]
+    if not isinstance(f, DielForcing):
+        raise ValueError(f"{q} must be a DielForcing (Derived is supported for reference_humidity only)")
+    return f
+
+
 @dataclass
 class MonthlyMinMaxEnvironment:                             # src/inputs/monthly_minmax.jl:13-16
     forcings: Dict[str, DielForcing]
@@ -258,8 +304,12 @@ class SolarGeometry:
 
 
 def weather_desc(curves: Optional[Dict[str, DielCurve]] = None, shortwave: AngstromMaxwellShortwave = AngstromMaxwellShortwave(),
-                 geometry: SolarGeometry = SolarGeometry()) -> A.WeatherDesc:
-    """Flatten forcing curves + shortwave model + geometry constants into mc_weather_desc."""
+                 geometry: SolarGeometry = SolarGeometry(), humidity_source: int = A.MC_HUMIDITY_CURVE, forcings: Optional[Dict[str, object]] = None) -> A.WeatherDesc:
+    """Flatten forcing curves + shortwave model + geometry constants into mc_weather_desc.  Pass either `curves` (one DielCurve per output quantity) or an
+    environment's `forcings` (DielForcing / Derived nodes, as bind_forcings leaves them): the latter also resolves a derived humidity."""
+    if forcings is not None:
+        curves = {q: forcing_of(forcings, q).curve for q in A.WEATHER_QUANTITIES}
+        humidity_source = humidity_forcing(forcings)[1]
     if not isinstance(shortwave.diffuse_fraction_model, ErbsDiffuseFraction):
         raise ValueError("only ErbsDiffuseFraction exists (src/radiation/diffuse)")
     curves = curves or {k: s.curve for k, s in MINMAX_FORCING_MODEL.items()}
@@ -271,6 +321,7 @@ def weather_desc(curves: Optional[Dict[str, DielCurve]] = None, shortwave: Angst
     w.solar_constant = 1367.0
     w.diffuse_model = A.MC_DIFFUSE_ERBS
     w.refraction = 1 if geometry.refraction else 0
+    w.humidity_source = humidity_source
     w.orbital_eccentricity, w.sin_obliquity = geometry.orbital_eccentricity, geometry.sin_obliquity
     w.days_per_year, w.equinox_day = geometry.days_per_year, geometry.equinox_day
     return w
@@ -323,8 +374,8 @@ class WeatherInBatch:
     def from_environments(cls, days, envs: Sequence, **kw):
         """One MonthlyMinMaxEnvironment / DailyMinMaxEnvironment per site (the reference's per-site inputs), transposed to site-fastest arrays."""
         S = len(envs)
-        f = {q: tuple(np.stack([np.asarray(e.forcings[q].values[i], dtype=np.float64) for e in envs], axis=1)
-                      for i in range(len(envs[0].forcings[q].values))) for q in A.WEATHER_QUANTITIES}
+        f = {q: tuple(np.stack([np.asarray(forcing_of(e.forcings, q).values[i], dtype=np.float64) for e in envs], axis=1)
+                      for i in range(len(forcing_of(envs[0].forcings, q).values))) for q in A.WEATHER_QUANTITIES}
         return cls(days, S, f, **kw)
 
     def day_slice(self, d0: int, d1: int) -> "WeatherInBatch":

@@ -116,6 +116,23 @@ static double sample(const mc_diel_curve& c, double h, const Day& day, const dou
     return sample_shape(covering_shape(c, h, day), h, day, c, vals, 0);
 }
 
+/* vapour_pressure(GoffGratch(), T) [Pa] of the un-vendored FluidProperties.jl (the functor of Derived, diel.jl:285-287): same published formula as
+ * mc_oracle.cpp's goff_gratch (pinned there against the reference's RHLOC goldens), ice branch at or below 273.16 K */
+static double saturation_vapour_pressure(double T)
+{
+    const double Tp = T + 0.01;
+    double loge;
+    if (Tp <= 273.16) {
+        const double r = 273.16 / Tp;
+        loge = -9.09718 * (r - 1.0) - 3.56654 * mcm::log10(r) + 0.876793 * (1.0 - Tp / 273.16) + 0.7858350313586662;
+    } else {
+        const double r = 373.16 / Tp;
+        loge = -7.90298 * (r - 1.0) + 5.02808 * mcm::log10(r) - 1.3816e-7 * (mcm::exp10(11.344 * (1.0 - Tp / 373.16)) - 1.0)
+             + 8.1328e-3 * (mcm::exp10(-3.49149 * (r - 1.0)) - 1.0) + 3.0057148979490314;
+    }
+    return 100.0 * mcm::exp10(loge);
+}
+
 /* ---- shortwave (angstrom_maxwell.jl:21-46) ------------------------------------------------------------------------------------- */
 static double erbs(double ci)                                                            /* erbs.jl:14-23 */
 {
@@ -218,7 +235,9 @@ int mco_populate_weather(int64_t S, int32_t ndays, const mc_weather_desc* w, con
     const mc_diel_curve* curves[4] = {&w->reference_temperature, &w->reference_wind_speed, &w->reference_humidity, &w->cloud_cover};
     const double* const* series[4] = {in->reference_temperature_values, in->reference_wind_speed_values, in->reference_humidity_values, in->cloud_cover_values};
     double* dst[4] = {out->reference_temperature, out->reference_wind_speed, out->reference_humidity, out->cloud_cover};
-    for (int q = 0; q < 4; q++) if (dst[q] || (q == 3 && want_sw)) for (int i = 0; i < curves[q]->n_inputs; i++) if (!series[q][i]) return -1;
+    for (int q = 0; q < 4; q++)
+        if (dst[q] || (q == 3 && want_sw) || (q == 0 && dst[2] && w->humidity_source == MC_HUMIDITY_FROM_VAPOUR_PRESSURE))
+            for (int i = 0; i < curves[q]->n_inputs; i++) if (!series[q][i]) return -1;
     if (out->pressure && !in->pressure_hourly && !in->pressure_site) return -1;
 #pragma omp parallel for schedule(static)
     for (int64_t s = 0; s < S; s++) {
@@ -237,12 +256,16 @@ int mco_populate_weather(int64_t S, int32_t ndays, const mc_weather_desc* w, con
             day.sunset = 2 * noon - day.sunrise;
             double vals[4][MC_DIEL_MAX_INPUTS];
             for (int q = 0; q < 4; q++) for (int i = 0; i < curves[q]->n_inputs; i++) vals[q][i] = series[q][i] ? series[q][i][ds] : NaN;
+            const bool derived_rh = w->humidity_source == MC_HUMIDITY_FROM_VAPOUR_PRESSURE;
             for (int h = 0; h < 24; h++) {
                 const size_t hs = ((size_t)d * 24 + (size_t)h) * (size_t)S + (size_t)s;
-                double cloud = NaN;
+                double cloud = NaN, T_hour = NaN;
                 for (int q = 0; q < 4; q++) {
-                    if (!dst[q] && !(q == 3 && want_sw)) continue;
+                    const bool feeds_rh = q == 0 && derived_rh && dst[2];          /* the derived humidity reads the hour's temperature (populate_quantities!: forcings first) */
+                    if (!dst[q] && !(q == 3 && want_sw) && !feeds_rh) continue;
                     double v = sample(*curves[q], (double)h, day, vals[q]);
+                    if (q == 0) T_hour = v;
+                    if (q == 2 && derived_rh) v = clampd(v / saturation_vapour_pressure(T_hour), 0.0, 1.0);   /* fill_derived!, diel.jl:285-287,438-444 */
                     if ((q == 2 || q == 3) && v > 1.0) v = 1.0;                          /* src/simulation.jl:317-326 */
                     if (dst[q]) dst[q][hs] = v;
                     if (q == 3) cloud = v;

@@ -509,3 +509,58 @@ def check_solve_minmax_batched(engine_factory):
     chunked = sim.solve_minmax_batched(p.model, inputs, days=p.days, time_mode=p.time_mode, clear_sky_direct=0.8 * clear, clear_sky_diffuse=0.2 * clear,
                                        fields=parity.ALL_FIELDS, chunk_days=5, engine_factory=engine_factory)
     parity.assert_bit_identical(chunked, ref, parity.ALL_FIELDS)          # PrescribedSoilMoisture: no humidity rows, nothing chunk-dependent
+
+
+def _derived_case(S=40, D=3, seed=17):
+    rng = np.random.default_rng(seed)
+    days = np.array([20, 180, 300], dtype=np.int32)[:D]
+    tmin = rng.uniform(250.0, 295.0, (D, S))
+    base = W.minmax_forcings(reference_temperature_min=tmin, reference_temperature_max=tmin + rng.uniform(4.0, 15.0, (D, S)),
+                             reference_wind_speed_min=rng.uniform(0.2, 1.0, (D, S)), reference_wind_speed_max=rng.uniform(2.0, 6.0, (D, S)),
+                             reference_humidity_min=np.zeros((D, S)), reference_humidity_max=np.ones((D, S)),
+                             cloud_cover_min=rng.uniform(0.0, 0.4, (D, S)), cloud_cover_max=rng.uniform(0.4, 1.0, (D, S)))
+    e_curve = W.DielCurve((W.Sine(W.Sunrise(), W.Midday(2.0)),), inputs=(W.Sunrise(), W.Midday(2.0)))
+    e_lo = rng.uniform(50.0, 900.0, (D, S))
+    forcings = dict(base, actual_vapour_pressure=W.DielForcing(e_curve, (e_lo, e_lo * rng.uniform(1.0, 6.0, (D, S)))),
+                    reference_humidity=W.Derived(W.RelativeHumidityFromVapourPressureAndTemperature(), ("actual_vapour_pressure", "reference_temperature")))
+    w = W.weather_desc(forcings=forcings)
+    win = W.WeatherInBatch(days, S, {q: W.forcing_of(forcings, q).values for q in A.WEATHER_QUANTITIES}, pressure_site=np.full(S, 9e4))
+    return w, win, W.SolarSitesBatch(rng.uniform(-55, 60, S)), forcings, e_curve
+
+
+def test_derived_humidity_from_vapour_pressure():
+    """Derived(RelativeHumidityFromVapourPressureAndTemperature(GoffGratch()), (:actual_vapour_pressure, :reference_temperature)) (diel.jl:264-301,438-444): the
+    vapour pressure follows its own diel curve, humidity = clamp(e / e_sat(T), 0, 1) hour by hour.  Oracle against a numpy statement of the functor (e_sat from the
+    soil oracle's Goff-Gratch, which the RHLOC goldens pin), kernel body and entry point bit-identical to the oracle."""
+    from microclimate_jl_b200 import marshal as M, synthetic as syn
+    w, win, sites, forcings, e_curve = _derived_case()
+    S, D, days = win.S, win.ndays, win.days
+    assert w.humidity_source == A.MC_HUMIDITY_FROM_VAPOUR_PRESSURE and w.reference_humidity.n_shapes == 1
+    fields = ("reference_temperature", "reference_humidity", "cloud_cover")
+    ref = W.WeatherOutBatch(D, S, fields)
+    O.populate_weather(w, win, ref, sites)
+    # the functor in numpy: the vapour-pressure curve sampled on its own through the (unclamped) temperature slot of a second descriptor, divided by e_sat(T)
+    model = W.minmax_forcing_model()
+    w_T = W.weather_desc({**{q: model[q].curve for q in A.WEATHER_QUANTITIES}, "reference_temperature": e_curve})
+    eT = W.WeatherOutBatch(D, S, ("reference_temperature",))
+    O.populate_weather(w_T, W.WeatherInBatch(days, S, {"reference_temperature": win.forcings["reference_humidity"]}), eT, sites)
+    gg = np.vectorize(lambda t: O.lib().mco_goff_gratch(float(t)))
+    expect = np.clip(eT.reference_temperature / gg(ref.reference_temperature), 0.0, 1.0)
+    assert np.array_equal(ref.reference_humidity, expect)
+    assert 0.05 < (ref.reference_humidity == 1.0).mean() < 0.9 and ref.reference_humidity.min() > 0.0         # both the clamped and the free regime occur
+    # humidity wanted without the temperature output: the temperature curve it depends on is still evaluated
+    for run in (O.populate_weather, HE.populate_weather, None):
+        for flds in (fields, ("reference_humidity",)):
+            got = W.WeatherOutBatch(D, S, flds)
+            if run is not None:
+                run(w, win, got, sites)
+            else:
+                eng = HE.WeatherApiEmu(M.model_desc(syn.synthetic_model(), syn.synthetic_time_mode()), S)
+                try:
+                    eng.populate_weather(w, win, got, sites)
+                finally:
+                    eng.close()
+            for k in flds:
+                assert np.array_equal(getattr(got, k), getattr(ref, k)), (k, run)
+    with pytest.raises(ValueError, match="not on the device"):
+        W.weather_desc(forcings=dict(forcings, reference_humidity=W.Derived(W.VapourPressureFromRelativeHumidityAndTemperature(), ("a", "b"))))

@@ -14,7 +14,7 @@ from microclimate_jl_b200 import synthetic as syn
 from microclimate_jl_b200 import weather as W
 from oracle import oracle as O
 from oracle.oracle import OracleEngine
-from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _random_problem, _soil_case, check_solve_minmax_batched
+from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _derived_case, _random_problem, _soil_case, check_solve_minmax_batched
 
 pytestmark = pytest.mark.gpu
 
@@ -102,3 +102,17 @@ def test_step_days_minmax_matches_populate_then_solve(SoilEngine):
 def test_solve_minmax_batched_on_the_b200(SoilEngine):
     """solve_minmax_batched (config 1 from its min/max inputs, three sites incl. sloped ones, whole and in day chunks) through the CUDA library == oracle weather + oracle soil."""
     check_solve_minmax_batched(None)
+
+
+def test_derived_humidity_matches_oracle(SoilEngine):
+    """Derived(RelativeHumidityFromVapourPressureAndTemperature) on the device: humidity = clamp(e / e_sat(T), 0, 1) from the vapour-pressure curve and the hour's temperature."""
+    w, win, sites, _, _ = _derived_case(S=3001, D=3, seed=51)
+    fields = ("reference_temperature", "reference_humidity", "cloud_cover")
+    ref = W.WeatherOutBatch(win.ndays, win.S, fields)
+    O.populate_weather(w, win, ref, sites)
+    with _engine(SoilEngine, win.S) as eng:
+        for flds in (fields, ("reference_humidity",)):
+            got = W.WeatherOutBatch(win.ndays, win.S, flds)
+            eng.populate_weather(w, win, got, sites)
+            for k in flds:
+                assert np.array_equal(getattr(got, k), getattr(ref, k)), k
