@@ -331,7 +331,8 @@ def solve_minmax_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *
                 W.forcing_of(fi, q).curve is not curves[q] and (W.forcing_of(fi, q).curve.shapes, W.forcing_of(fi, q).curve.inputs) != (curves[q].shapes, curves[q].inputs)
                 for q in A.WEATHER_QUANTITIES):
             raise ValueError("all sites of a batch must share one forcing model (the DielCurves are model-level in the C ABI)")
-    wdesc = W.weather_desc(None, shortwave or W.AngstromMaxwellShortwave(), geometry or W.SolarGeometry(), forcings=env0.forcings)
+    wdesc = W.weather_desc(None, shortwave or getattr(model.radiation, "shortwave_model", None) or W.AngstromMaxwellShortwave(), geometry or W.SolarGeometry(),
+                           forcings=env0.forcings)
     desc = M.model_desc(model, time_mode, inputs0=inputs[0])
     sites = M.SitesBatch.from_inputs(model, inputs)
     rest = M.ForcingBatch.from_inputs(model, inputs, days)

@@ -100,8 +100,9 @@ class ViewFactorLongwave:                       # src/radiation/longwave/view_fa
 
 
 @dataclass(frozen=True)
-class RadiationModel:                           # src/types.jl:52-56 (solar/shortwave models are pre-processing, out of scope)
+class RadiationModel:                           # src/types.jl:52-56 (the solar_radiation_model stays SolarRadiation.jl's)
     longwave_model: ViewFactorLongwave = ViewFactorLongwave()
+    shortwave_model: object = None              # weather.AngstromMaxwellShortwave; None = its defaults (used by solve_minmax_batched / populate_weather)
 
 
 # ---- apparent heat capacity: src/apparent_heat_capacity/*.jl ------------------------------------
