@@ -454,6 +454,11 @@ int  mc_populate_weather_device(mc_handle* h, int32_t ndays, const mc_weather_de
 int  mc_step_days_minmax(mc_handle* h, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
                          const mc_weather_in_soa* in, const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host);
 
+/* mc_step_days_minmax over the devices of a multi handle (declared above with mc_multi_*): every device expands and integrates its contiguous column range of
+ * ONE set of host arrays [rows][n_sites]; returns the flagged-site count summed over devices */
+int  mc_multi_step_days_minmax(mc_multi* m, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
+                               const mc_weather_in_soa* in, const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host);
+
 /* struct sizes of the loaded library, for bindings to check their mirrors against (index: 0 mc_model_desc, 1 mc_sites_soa, 2 mc_initial_soa,
  * 3 mc_state_soa, 4 mc_forcing_soa, 5 mc_output_soa, 6 mc_counters, 7 mc_weather_desc, 8 mc_solar_sites_soa, 9 mc_weather_in_soa,
  * 10 mc_weather_out_soa); -1 for an unknown index */

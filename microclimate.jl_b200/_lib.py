@@ -26,7 +26,8 @@ EXPORTS = ("mc_abi_version", "mc_backend_name", "mc_default_fluid", "mc_default_
            "mc_multi_create", "mc_multi_destroy", "mc_multi_last_error", "mc_multi_device_count", "mc_multi_handle", "mc_multi_range",
            "mc_multi_set_sites", "mc_multi_step_days", "mc_multi_step_days_async", "mc_multi_wait",
            "mc_synchronize", "mc_get_counters", "mc_reset_counters", "mc_get_status", "mc_measure_fp64_peak", "mc_bench_conductivity", "mc_get_async_stats",
-           "mc_default_weather", "mc_validate_weather", "mc_populate_weather", "mc_populate_weather_device", "mc_step_days_minmax", "mc_abi_sizeof")
+           "mc_default_weather", "mc_validate_weather", "mc_populate_weather", "mc_populate_weather_device", "mc_step_days_minmax", "mc_multi_step_days_minmax",
+           "mc_abi_sizeof")
 
 
 def _nvcc():
@@ -117,6 +118,7 @@ def lib():
     L.mc_populate_weather_device.argtypes = _wx
     L.mc_step_days_minmax.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA),
                                       C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA), C.POINTER(A.WeatherOutSoA)]
+    L.mc_multi_step_days_minmax.argtypes = L.mc_step_days_minmax.argtypes
     L.mc_abi_sizeof.argtypes = [C.c_int]
     L.mc_abi_sizeof.restype = C.c_int64
     if L.mc_abi_version() != A.MC_ABI_VERSION:

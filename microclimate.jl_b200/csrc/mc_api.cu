@@ -927,6 +927,9 @@ int mc_measure_fp64_peak(mc_handle* h, double* tflops)
  * sites of ONE set of host arrays contiguously over several devices (replicated model, no collective); every device runs the asynchronous
  * pipeline above on its column range, so all GPUs copy and integrate concurrently from a single host thread. */
 struct mc_multi { std::vector<mc_handle*> h; std::vector<int64_t> lo; int64_t S = 0; std::string err; };
+}  // extern "C"
+int mc_i_multi_fail(mc_multi* m, int device_index, const char* msg, int rc) { m->err = "device " + std::to_string(device_index) + ": " + (msg ? msg : ""); return rc; }
+extern "C" {
 
 int mc_multi_create(const mc_model_desc* model, int64_t n_sites, const int* device_ids, int n_devices, mc_multi** out)
 {

@@ -12,5 +12,6 @@ MC_HIDDEN cudaStream_t mc_i_stream(const mc_handle* h);               /* the han
 MC_HIDDEN int64_t mc_i_sites(const mc_handle* h);
 MC_HIDDEN const mc_model_desc* mc_i_model(const mc_handle* h);
 MC_HIDDEN int mc_i_fail(mc_handle* h, const char* msg, int rc);       /* sets mc_last_error(h), returns rc */
+MC_HIDDEN int mc_i_multi_fail(mc_multi* m, int device_index, const char* msg, int rc);   /* sets mc_multi_last_error(m) to "device g: msg", returns rc */
 /* mc_weather.cu */
 MC_HIDDEN void mc_i_weather_release(mc_handle* h);                     /* frees the weather staging of a handle (called by mc_destroy) */

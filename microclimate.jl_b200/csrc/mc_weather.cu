@@ -340,11 +340,24 @@ int mc_populate_weather(mc_handle* h, int32_t ndays, const mc_weather_desc* w, c
     return 0;
 }
 
-/* solve!(cache) of a min/max-driven problem: expand the weather on the device into the soil kernel's forcing arrays, integrate, copy the outputs back */
-int mc_step_days_minmax(mc_handle* h, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
-                        const mc_weather_in_soa* in, const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host)
+}  // extern "C"
+
+namespace {
+
+/* one [rows][S] plane between a host array that is `pitch` doubles wide (this handle's sites start at column col0) and the packed device copy */
+cudaError_t copy_plane(const Plane& pl, bool to_device, size_t S, size_t pitch, size_t col0, cudaStream_t s)
 {
-    if (!h) return -1;
+    const size_t w = S * sizeof(double);
+    if (pitch == S)
+        return to_device ? cudaMemcpyAsync(pl.dev, pl.host_in, pl.rows * w, cudaMemcpyHostToDevice, s) : cudaMemcpyAsync(pl.host_out, pl.dev, pl.rows * w, cudaMemcpyDeviceToHost, s);
+    return to_device ? cudaMemcpy2DAsync(pl.dev, w, pl.host_in + col0, pitch * sizeof(double), w, pl.rows, cudaMemcpyHostToDevice, s)
+                     : cudaMemcpy2DAsync(pl.host_out + col0, pitch * sizeof(double), pl.dev, w, w, pl.rows, cudaMemcpyDeviceToHost, s);
+}
+
+/* everything of mc_step_days_minmax up to and including the enqueued device-to-host copies; host arrays may be wider than the handle (a multi-device job) */
+int minmax_enqueue(mc_handle* h, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites, const mc_weather_in_soa* in,
+                   const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host, size_t pitch, size_t col0)
+{
     if (!in || !rest || !out || ndays <= 0) return mc_i_fail(h, "weather in / rest / out must be non-NULL and ndays positive", -1);
     if (!in->day_of_year && !rest->day_of_year) return mc_i_fail(h, "day_of_year is required (mc_weather_in_soa or mc_forcing_soa)", -1);
     const int32_t* doy_host = in->day_of_year ? in->day_of_year : rest->day_of_year;
@@ -431,7 +444,7 @@ int mc_step_days_minmax(mc_handle* h, int64_t day0, int32_t ndays, const mc_weat
 
     cudaStream_t s = mc_i_stream(h);
     WX_CUDA(h, cudaMemcpyAsync(st->doy, doy_host, D * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    for (const Plane& pl : planes) if (pl.host_in) WX_CUDA(h, cudaMemcpyAsync(pl.dev, pl.host_in, pl.rows * S * sizeof(double), cudaMemcpyHostToDevice, s));
+    for (const Plane& pl : planes) if (pl.host_in) WX_CUDA(h, copy_plane(pl, true, S, pitch, col0, s));
     if (out_end > out_begin) WX_CUDA(h, cudaMemsetAsync(base + out_begin, 0, (out_end - out_begin) * sizeof(double), s));   /* cells the path never writes read back as zero */
     if (int rc = launch(h, w, a)) return rc;
 
@@ -451,15 +464,65 @@ int mc_step_days_minmax(mc_handle* h, int64_t day0, int32_t ndays, const mc_weat
     odv.convective_heat_flux = at(o_profs[0]); odv.friction_velocity = at(o_profs[1]);
     /* same stream: the soil kernel starts when the weather kernel has written its forcing */
     if (int rc = mc_step_days_device(h, day0, ndays, &fd, &odv)) return rc;
-    for (const Plane& pl : planes) if (pl.host_out) WX_CUDA(h, cudaMemcpyAsync(pl.host_out, pl.dev, pl.rows * S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    for (const Plane& pl : planes) if (pl.host_out) WX_CUDA(h, copy_plane(pl, false, S, pitch, col0, s));
+    return 0;
+}
+
+/* wait for the chunk, fetch the status words (into out->status at this handle's columns when given); returns the flagged-site count */
+int minmax_finish(mc_handle* h, mc_output_soa* out, size_t col0)
+{
     if (int rc = mc_synchronize(h)) return rc;
+    const size_t S = (size_t)mc_i_sites(h);
     std::vector<int32_t> own;
-    int32_t* status = out->status;
+    int32_t* status = out->status ? out->status + col0 : nullptr;
     if (!status) { own.resize(S); status = own.data(); }
     if (int rc = mc_get_status(h, status)) return rc;
     int nbad = 0;
     for (size_t i = 0; i < S; i++) if (status[i]) nbad++;
     return nbad;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* solve!(cache) of a min/max-driven problem: expand the weather on the device into the soil kernel's forcing arrays, integrate, copy the outputs back */
+int mc_step_days_minmax(mc_handle* h, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
+                        const mc_weather_in_soa* in, const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host)
+{
+    if (!h) return -1;
+    const size_t S = (size_t)mc_i_sites(h);
+    if (int rc = minmax_enqueue(h, day0, ndays, w, sites, in, rest, out, weather_host, S, 0)) { if (rc < 0) cudaStreamSynchronize(mc_i_stream(h)); return rc; }
+    return minmax_finish(h, out, 0);
+}
+
+/* the same over the devices of a multi handle: every device expands and integrates its contiguous column range of ONE set of host arrays; all devices are
+ * enqueued before the first one is waited for, so their kernels run concurrently */
+int mc_multi_step_days_minmax(mc_multi* m, int64_t day0, int32_t ndays, const mc_weather_desc* w, const mc_solar_sites_soa* sites,
+                              const mc_weather_in_soa* in, const mc_forcing_soa* rest, mc_output_soa* out, mc_weather_out_soa* weather_host)
+{
+    if (!m) return -1;
+    const int G = mc_multi_device_count(m);
+    int64_t S_total = 0;
+    for (int g = 0; g < G; g++) { int64_t lo, hi; mc_multi_range(m, g, &lo, &hi); if (hi > S_total) S_total = hi; }
+    int rc_all = 0, enq = 0;
+    for (; enq < G; enq++) {
+        int64_t lo, hi; mc_multi_range(m, enq, &lo, &hi);
+        mc_handle* h = mc_multi_handle(m, enq);
+        if (hi == lo) continue;
+        const int rc = h ? minmax_enqueue(h, day0, ndays, w, sites, in, rest, out, weather_host, (size_t)S_total, (size_t)lo) : -1;
+        if (rc < 0) { rc_all = mc_i_multi_fail(m, enq, h ? mc_last_error(h) : "no handle", rc); break; }
+    }
+    int total = 0;
+    for (int g = 0; g < (rc_all < 0 ? enq : G); g++) {                 /* on an error: still drain what was enqueued, nothing may keep touching the caller's arrays */
+        int64_t lo, hi; mc_multi_range(m, g, &lo, &hi);
+        if (hi == lo) continue;
+        mc_handle* h = mc_multi_handle(m, g);
+        const int rc = minmax_finish(h, out, (size_t)lo);
+        if (rc < 0 && rc_all == 0) rc_all = mc_i_multi_fail(m, g, mc_last_error(h), rc);
+        else if (rc > 0) total += rc;
+    }
+    return rc_all < 0 ? rc_all : total;
 }
 
 }  // extern "C"

@@ -234,6 +234,19 @@ class MultiSoilEngine:
         self.step_days_async(day0, forcing, out)
         return self.wait()
 
+    def step_days_minmax(self, day0: int, wdesc: A.WeatherDesc, win, rest: M.ForcingBatch, out: M.OutputBatch, solar_sites=None, weather_out=None,
+                         use_rest_zenith: bool = False) -> int:
+        """SoilEngine.step_days_minmax over all devices of this engine (mc_multi_step_days_minmax): every GPU expands the weather of, and integrates, its column range."""
+        if win.S != self.S or out.S != self.S or rest.S != self.S or out.ndays != win.ndays or rest.ndays != win.ndays:
+            raise ValueError("weather/forcing/output batch shapes do not match the engine")
+        ci, cf, co = win.c_struct(), rest.c_struct(), out.c_struct()
+        if not use_rest_zenith:
+            cf.zenith_angle, cf.zenith_slope_angle = None, None
+        cs = solar_sites.c_struct() if solar_sites is not None else None
+        cw = weather_out.c_struct() if weather_out is not None else None
+        return self._check(self._L.mc_multi_step_days_minmax(self.h, day0, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(cf),
+                                                             C.byref(co), C.byref(cw) if cw is not None else None), "mc_multi_step_days_minmax")
+
     def counters(self) -> dict:
         tot = None
         for g in range(len(self.devices)):
@@ -308,15 +321,16 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
 
 def solve_minmax_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, days: Sequence[int], clear_sky_direct, clear_sky_diffuse,
                          time_mode=None, shortwave=None, geometry=None, fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS, device: int = 0,
-                         chunk_days: Optional[int] = None, zenith_angle=None, zenith_slope_angle=None, return_weather: bool = False, engine_factory=None):
+                         chunk_days: Optional[int] = None, zenith_angle=None, zenith_slope_angle=None, return_weather: bool = False, engine_factory=None,
+                         devices: Optional[Sequence[int]] = None):
     """Batched `solve!(cache)` for min/max-driven problems (src/simulation.jl:246-260): every `inputs[s].environment_minmax` (MonthlyMinMaxEnvironment /
     DailyMinMaxEnvironment, all with the same forcing model) is expanded to hourly weather ON THE DEVICE (populate_weather!), the soil path integrates it
     (solve_soil!, plus solve_air! when profile fields are selected) and only the selected outputs come back (mc_step_days_minmax).
 
     `clear_sky_direct` / `clear_sky_diffuse` are SolarRadiation.jl's hourly clear-sky irradiances on the horizontal, [24*ndays][S] (its spectral model is not part of
     this library).  Zenith and slope-zenith angles come from the built-in geometry (site latitude / slope / aspect) unless given.  `environment_hourly` supplies
-    `pressure` (scalar or hourly), rainfall / longwave when the model uses them, and an optional `global_radiation` override.  Returns the OutputBatch, and with
-    `return_weather` also the expanded hourly weather (WeatherOutBatch)."""
+    `pressure` (scalar or hourly), rainfall / longwave when the model uses them, and an optional `global_radiation` override.  `devices` shards the sites over
+    several GPUs from this one process.  Returns the OutputBatch, and with `return_weather` also the expanded hourly weather (WeatherOutBatch)."""
     from . import weather as W
     time_mode = time_mode if time_mode is not None else T.NonConsecutiveDayMode()
     if len(inputs) == 0 or any(i.environment_minmax is None for i in inputs):
@@ -348,7 +362,7 @@ def solve_minmax_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *
         rest.zenith_slope_angle[...] = np.minimum(zenith_slope_angle, 90.0)
     out = M.OutputBatch(ndays, desc.n_soil, S, fields, desc.n_snow, desc.n_heights)
     wx = W.WeatherOutBatch(ndays, S) if return_weather else None
-    eng = (engine_factory or (lambda d, n: SoilEngine(d, n, device)))(desc, S)
+    eng = (engine_factory or (lambda d, n: MultiSoilEngine(d, n, devices) if devices else SoilEngine(d, n, device)))(desc, S)
     try:
         eng.set_sites(sites)
         cd = ndays if not chunk_days else min(int(chunk_days), ndays)

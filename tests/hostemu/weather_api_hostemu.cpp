@@ -51,6 +51,11 @@ static inline cudaError_t cudaFree(void* p)
 }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
+{
+    for (size_t r = 0; r < height; r++) std::memcpy((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+    return cudaSuccess;
+}
 
 #include "../../include/microclimate_b200.h"
 
@@ -63,6 +68,8 @@ int he_step_days(void* h, int64_t day0, int32_t ndays, const mc_forcing_soa* f, 
 }
 
 struct mc_handle { void* emu; int64_t S; mc_model_desc model; std::string err; std::vector<int32_t> status; };
+/* a multi handle of the emulation: contiguous column ranges over several emulated "devices" (mc_api.cu's mc_multi, reduced to what mc_weather.cu uses) */
+struct mc_multi { std::vector<mc_handle*> h; std::vector<int64_t> lo; int64_t S = 0; std::string err; };
 
 #include "../../microclimate.jl_b200/csrc/mc_weather.cu"
 
@@ -82,6 +89,7 @@ cudaStream_t mc_i_stream(const mc_handle*) { return nullptr; }
 int64_t mc_i_sites(const mc_handle* h) { return h->S; }
 const mc_model_desc* mc_i_model(const mc_handle* h) { return &h->model; }
 int mc_i_fail(mc_handle* h, const char* msg, int rc) { h->err = msg; return rc; }
+int mc_i_multi_fail(mc_multi* m, int g, const char* msg, int rc) { m->err = "device " + std::to_string(g) + ": " + (msg ? msg : ""); return rc; }
 
 extern "C" {
 /* the entry points of mc_api.cu that mc_step_days_minmax calls, on the emulated soil engine ("device" pointers are host pointers here) */
@@ -104,6 +112,25 @@ int mc_step_days_device(mc_handle* h, int64_t day0, int32_t ndays, const mc_forc
     return rc < 0 ? rc : 0;
 }
 int mc_get_status(mc_handle* h, int32_t* out) { std::memcpy(out, h->status.data(), (size_t)h->S * sizeof(int32_t)); return 0; }
+
+const char* mc_last_error(const mc_handle* h) { return h ? h->err.c_str() : ""; }
+int mc_multi_device_count(const mc_multi* m) { return (int)m->h.size(); }
+mc_handle* mc_multi_handle(mc_multi* m, int g) { return m->h[(size_t)g]; }
+int mc_multi_range(const mc_multi* m, int g, int64_t* lo, int64_t* hi) { *lo = m->lo[(size_t)g]; *hi = m->lo[(size_t)g + 1]; return 0; }
+
+mc_handle* wa_create(const mc_model_desc* m, int64_t S);
+void wa_destroy(mc_handle* h);
+mc_multi* wa_multi_create(const mc_model_desc* desc, int64_t S, int n_devices)
+{
+    mc_multi* m = new mc_multi(); m->S = S;
+    const int64_t base = S / n_devices, rem = S % n_devices;
+    int64_t lo = 0;
+    for (int g = 0; g < n_devices; g++) { const int64_t n = base + (g < rem ? 1 : 0); m->lo.push_back(lo); m->h.push_back(n > 0 ? wa_create(desc, n) : nullptr); lo += n; }
+    m->lo.push_back(S);
+    return m;
+}
+void wa_multi_destroy(mc_multi* m) { if (!m) return; for (mc_handle* h : m->h) wa_destroy(h); delete m; }
+const char* wa_multi_last_error(const mc_multi* m) { return m->err.c_str(); }
 
 mc_handle* wa_create(const mc_model_desc* m, int64_t S)
 {

@@ -161,6 +161,15 @@ def weather_api_lib():
         L.mc_populate_weather_device.argtypes = wx
         L.mc_step_days_minmax.argtypes = [H, C.c_int64, C.c_int32, C.POINTER(A.WeatherDesc), C.POINTER(A.SolarSitesSoA), C.POINTER(A.WeatherInSoA),
                                           C.POINTER(A.ForcingSoA), C.POINTER(A.OutputSoA), C.POINTER(A.WeatherOutSoA)]
+        L.mc_multi_step_days_minmax.argtypes = L.mc_step_days_minmax.argtypes
+        L.wa_multi_create.restype = H
+        L.wa_multi_create.argtypes = [C.POINTER(A.ModelDesc), C.c_int64, C.c_int]
+        L.wa_multi_destroy.argtypes = [H]
+        L.wa_multi_last_error.argtypes = [H]
+        L.wa_multi_last_error.restype = C.c_char_p
+        L.mc_multi_handle.argtypes = [H, C.c_int]
+        L.mc_multi_handle.restype = H
+        L.mc_multi_range.argtypes = [H, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _walib = L
     return _walib
 
@@ -208,3 +217,44 @@ class WeatherApiEmu:
         cw = weather_out.c_struct() if weather_out is not None else None
         return self._check(self._L.mc_step_days_minmax(self.h, day0, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(cf),
                                                        C.byref(co), C.byref(cw) if cw is not None else None), "mc_step_days_minmax")
+
+
+class WeatherApiMultiEmu:
+    """MultiSoilEngine's min/max step on the emulation: `n_devices` emulated devices over contiguous column ranges of one set of host arrays."""
+
+    def __init__(self, desc, n_sites, n_devices):
+        self.desc, self.S, self.G = desc, n_sites, n_devices
+        self._L = weather_api_lib()
+        self.h = self._L.wa_multi_create(C.byref(desc), n_sites, n_devices)
+
+    def close(self):
+        if self.h:
+            self._L.wa_multi_destroy(self.h)
+            self.h = None
+
+    def ranges(self):
+        out = []
+        for g in range(self.G):
+            lo, hi = C.c_int64(), C.c_int64()
+            self._L.mc_multi_range(self.h, g, C.byref(lo), C.byref(hi))
+            out.append((lo.value, hi.value))
+        return out
+
+    def set_sites(self, sites):
+        for g, (lo, hi) in enumerate(self.ranges()):
+            if hi > lo:
+                part = sites.slice(lo, hi)
+                cs, ci = part.c_sites(), part.c_initial()
+                assert self._L.wa_set_sites(self._L.mc_multi_handle(self.h, g), C.byref(cs), C.byref(ci)) == 0
+
+    def step_days_minmax(self, day0, wdesc, win, rest, out, solar_sites=None, weather_out=None, use_rest_zenith=False):
+        ci, cf, co = win.c_struct(), rest.c_struct(), out.c_struct()
+        if not use_rest_zenith:
+            cf.zenith_angle, cf.zenith_slope_angle = None, None
+        cs = solar_sites.c_struct() if solar_sites is not None else None
+        cw = weather_out.c_struct() if weather_out is not None else None
+        rc = self._L.mc_multi_step_days_minmax(self.h, day0, win.ndays, C.byref(wdesc), C.byref(cs) if cs is not None else None, C.byref(ci), C.byref(cf),
+                                               C.byref(co), C.byref(cw) if cw is not None else None)
+        if rc < 0:
+            raise RuntimeError(f"mc_multi_step_days_minmax failed (rc={rc}): {self._L.wa_multi_last_error(self.h).decode()}")
+        return rc

@@ -564,3 +564,40 @@ def test_derived_humidity_from_vapour_pressure():
                 assert np.array_equal(getattr(got, k), getattr(ref, k)), (k, run)
     with pytest.raises(ValueError, match="not on the device"):
         W.weather_desc(forcings=dict(forcings, reference_humidity=W.Derived(W.VapourPressureFromRelativeHumidityAndTemperature(), ("a", "b"))))
+
+
+def test_multi_device_minmax_step_equals_single_device():
+    """mc_multi_step_days_minmax: three emulated devices over ragged contiguous column ranges (4 + 3 + 3 sites) of ONE set of host arrays — pitched copies in and
+    out, weather read-back and status included — against the single-handle call."""
+    import parity
+    from microclimate_jl_b200 import marshal as M
+    desc, sites, rest, win, solar = _soil_case(S=10, D=2, seed=29)
+    w = W.weather_desc()
+    S, D = win.S, win.ndays
+    fields = ("soil_temperature", "soil_moisture", "surface_water", "sky_temperature")
+    one = HE.WeatherApiEmu(desc, S)
+    try:
+        one.set_sites(sites)
+        ref, ref_wx = M.OutputBatch(D, desc.n_soil, S, fields), W.WeatherOutBatch(D, S)
+        one.step_days_minmax(0, w, win, rest, ref, solar, ref_wx)
+    finally:
+        one.close()
+    multi = HE.WeatherApiMultiEmu(desc, S, 3)
+    try:
+        assert multi.ranges() == [(0, 4), (4, 7), (7, 10)]
+        multi.set_sites(sites)
+        out, wx = M.OutputBatch(D, desc.n_soil, S, fields), W.WeatherOutBatch(D, S)
+        out.status[:] = -1
+        multi.step_days_minmax(0, w, win, rest, out, solar, wx)
+        parity.assert_bit_identical(out, ref, fields)
+        assert np.array_equal(out.status, ref.status)
+        for k in ALL_OUT:
+            assert np.array_equal(getattr(wx, k), getattr(ref_wx, k)), k
+        # an error on one device is reported with its index
+        bad = W.weather_desc()
+        bad.cloud_cover.n_shapes = 0
+        with pytest.raises(RuntimeError, match="device 0: .*n_shapes"):
+            multi.step_days_minmax(D, bad, win, rest, out, solar, wx)
+    finally:
+        multi.close()
+    assert HE.weather_api_lib().wa_live_allocations() == 0

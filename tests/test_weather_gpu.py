@@ -116,3 +116,28 @@ def test_derived_humidity_matches_oracle(SoilEngine):
             eng.populate_weather(w, win, got, sites)
             for k in flds:
                 assert np.array_equal(getattr(got, k), getattr(ref, k)), k
+
+
+def test_multi_device_minmax_step_on_the_b200(SoilEngine):
+    """mc_multi_step_days_minmax: one host process, the sites of ONE set of host arrays sharded over three pipelines (the same GPU listed three times on a 1-GPU box, as
+    many distinct GPUs as there are otherwise) — soil outputs, weather read-back and status equal to the single-handle call."""
+    import torch
+    from microclimate_jl_b200.simulation import MultiSoilEngine
+    desc, sites, rest, win, solar = _soil_case(S=70, D=2, seed=43)
+    w = W.weather_desc()
+    S, D = win.S, win.ndays
+    fields = ("soil_temperature", "soil_moisture", "surface_water", "sky_temperature")
+    with SoilEngine(desc, S) as one:
+        one.set_sites(sites)
+        ref, ref_wx = M.OutputBatch(D, desc.n_soil, S, fields), W.WeatherOutBatch(D, S)
+        one.step_days_minmax(0, w, win, rest, ref, solar, ref_wx)
+    n = torch.cuda.device_count()
+    devices = [g % n for g in range(3)]
+    with MultiSoilEngine(desc, S, devices) as multi:
+        multi.set_sites(sites)
+        out, wx = M.OutputBatch(D, desc.n_soil, S, fields), W.WeatherOutBatch(D, S)
+        multi.step_days_minmax(0, w, win, rest, out, solar, wx)
+        parity.assert_bit_identical(out, ref, fields)
+        assert np.array_equal(out.status, ref.status)
+        for k in ALL_OUT:
+            assert np.array_equal(getattr(wx, k), getattr(ref_wx, k)), k
