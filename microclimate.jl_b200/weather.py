@@ -193,6 +193,11 @@ class DielForcing:                                          # diel.jl:224-236: a
     values: Tuple[np.ndarray, ...]
 
 
+def bind_forcings(model: Dict[str, object], valuesource) -> Dict[str, object]:
+    """bind_forcings(model, valuesource) (diel.jl:414-431): ForcingSpecs are bound to the value series `valuesource(name)` of their inputs, Derived nodes pass through."""
+    return {k: (DielForcing(n.curve, tuple(np.asarray(valuesource(i), dtype=np.float64) for i in n.inputs)) if isinstance(n, ForcingSpec) else n) for k, n in model.items()}
+
+
 def minmax_forcings(*, reference_temperature_min, reference_temperature_max, reference_wind_speed_min, reference_wind_speed_max,
                     reference_humidity_min, reference_humidity_max, cloud_cover_min, cloud_cover_max, **offsets) -> Dict[str, DielForcing]:
     """Bind the standard min/max model to per-day series (diel.jl:516-542); the means are (min + max) / 2 as in the reference."""
@@ -204,7 +209,7 @@ def minmax_forcings(*, reference_temperature_min, reference_temperature_max, ref
     for q in ("reference_wind_speed", "reference_humidity", "cloud_cover"):
         g[q + "_mean"] = (g[q + "_min"] + g[q + "_max"]) / 2
     model = minmax_forcing_model(**offsets) if offsets else MINMAX_FORCING_MODEL
-    return {k: DielForcing(spec.curve, tuple(g[n] for n in spec.inputs)) for k, spec in model.items()}
+    return bind_forcings(model, lambda name: g[name])
 
 
 # ---- Derived quantities (diel.jl:264-312): computed hour by hour from other quantities instead of interpolated from a curve ----
