@@ -335,8 +335,9 @@ function populate_weather_batched!(caches::AbstractVector{<:MicroCache}; device:
     slot(e, q) = q == :reference_humidity ? humidity_forcing(e.forcings)[1] : getproperty(e.forcings, q)      # the DielForcing behind each ABI slot
     quantities = (:reference_temperature, :reference_wind_speed, :reference_humidity, :cloud_cover)
     units = (u"K", u"m/s", hum_source == 1 ? u"Pa" : 1, 1)
-    # values[q][i][d, s] -> [D][S] site-fastest; eltype conversion as evaluate! does it (diel.jl:337)
-    series = [[Float64[si(unit == 1 ? collect(slot(e, q).values[i])[d] : unit(collect(slot(e, q).values[i])[d]), unit) for e in envs, d in 1:D]
+    # values[q][i][d, s] -> [D][S] site-fastest; unit conversion as evaluate! does it (diel.jl:337); the means of minmax_forcings are lazy Broadcasted objects
+    num(x, unit) = unit == 1 ? Float64(x) : Float64(ustrip(unit, uconvert(unit, x)))
+    series = [[(v = Base.materialize.([slot(e, q).values[i] for e in envs]); Float64[num(v[s][d], unit) for s in 1:S, d in 1:D])
                for i in 1:length(slot(first(envs), q).values)] for (q, unit) in zip(quantities, units)]
     daily(f) = Float64[f(c, d) for c in caches, d in 1:D]
     hourly(f) = Float64[f(c, t) for c in caches, t in 1:H]
