@@ -12,7 +12,7 @@ __all__ = ["_abi", "types", "marshal", "weather"]
 
 def __getattr__(name):
     # engine/simulation need the CUDA library; import lazily so type-only users work without it
-    if name in ("SoilEngine", "MultiSoilEngine", "solve_soil_batched", "solve_soil", "solve_minmax_batched"):
+    if name in ("SoilEngine", "MultiSoilEngine", "solve_soil_batched", "solve_soil", "solve_minmax_batched", "solve"):
         from . import simulation
         return getattr(simulation, name)
     raise AttributeError(name)

@@ -389,3 +389,17 @@ def solve_soil(problem: T.MicroProblem, **kw) -> T.MicroResult:
     """Single-site convenience mirroring `solve(problem)` for the soil path."""
     out = solve_soil_batched(problem.model, [problem.inputs], days=problem.days, time_mode=problem.time_mode, **kw)
     return out.site_result(0)
+
+
+def solve(problem: T.MicroProblem, *, clear_sky_direct=None, clear_sky_diffuse=None, **kw) -> T.MicroResult:
+    """`solve(problem)` (src/simulation.jl:262-264) for one site: populate_weather! (when the inputs carry a min/max environment) + solve_soil! (+ solve_air! when profile
+    fields are selected).  The spectral clear-sky model of SolarRadiation.jl is not part of this library: a min/max-driven problem needs its hourly clear-sky
+    `direct_horizontal` / `diffuse_horizontal` ([24*ndays]) here."""
+    if problem.inputs.environment_minmax is None:
+        return solve_soil(problem, **kw)
+    if clear_sky_direct is None or clear_sky_diffuse is None:
+        raise ValueError("a min/max-driven problem needs clear_sky_direct / clear_sky_diffuse (SolarRadiation.jl's hourly clear-sky irradiance on the horizontal)")
+    H = 24 * len(problem.days)
+    out = solve_minmax_batched(problem.model, [problem.inputs], days=problem.days, time_mode=problem.time_mode,
+                               clear_sky_direct=np.asarray(clear_sky_direct, float).reshape(H, 1), clear_sky_diffuse=np.asarray(clear_sky_diffuse, float).reshape(H, 1), **kw)
+    return out.site_result(0)

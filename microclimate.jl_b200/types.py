@@ -371,3 +371,39 @@ def example_daily_environment(days=DEFAULT_DAYS, **kw) -> DailyTimeseries:
              deep_soil_temperature=np.full(n, 7.741666 + 273.15), leaf_area_index=np.full(n, 0.1), albedo=None)
     d.update(kw)
     return DailyTimeseries(**d)
+
+
+def example_hourly_environment(days=DEFAULT_DAYS, *, elevation: float = 226.0, **kw) -> HourlyWeather:      # src/inputs/hourly_timeseries.jl:13-29
+    """Only the pressure is given; every weather field stays None (`nothing` upstream) and is filled by populate_weather! from the min/max environment."""
+    d = dict(pressure=np.full(24 * len(days), atmospheric_pressure(elevation)))
+    d.update(kw)
+    return HourlyWeather(**d)
+
+
+def example_soil_properties_model(**kw) -> CampbelldeVriesSoilProperties:                                   # src/soil_properties/campbell_devries.jl:11-19
+    return CampbelldeVriesSoilProperties(**kw)
+
+
+def example_soil_hydraulic_model(**kw) -> CampbellSoilHydraulics:                                           # src/soil_hydraulics/campbell.jl:69-81
+    return CampbellSoilHydraulics(**kw)
+
+
+def example_microclimate_problem(*, days=DEFAULT_DAYS, depths=DEFAULT_DEPTHS, heights=(0.01, 2.0), site=None, soil_profile=None, soil_properties_model=None,
+                                 soil_hydraulic_model=None, snow_model=None, environment_minmax=None, environment_daily=None, environment_hourly=None, config=None,
+                                 initial_soil_temperature=None, initial_soil_moisture=None) -> MicroProblem:
+    """example_microclimate_problem() (src/types.jl:185-210): Madison, Wisconsin, twelve mid-month days driven by monthly min/max weather — solve it with
+    `simulation.solve` / `solve_minmax_batched` (the clear-sky irradiance of SolarRadiation.jl is an input there)."""
+    from . import weather as W
+    site = site if site is not None else example_site()
+    depths = np.asarray(depths, float)
+    model = MicroModel(depths=depths, heights=np.asarray(heights, float),
+                       soil_properties_model=soil_properties_model or example_soil_properties_model(),
+                       soil_hydraulic_model=soil_hydraulic_model or example_soil_hydraulic_model(),
+                       snow_model=snow_model if snow_model is not None else NoSnow(), config=config or MicroConfig())
+    inputs = MicroInputs(site=site, soil_profile=soil_profile or example_soil_profile(depths),
+                         environment_minmax=environment_minmax or W.example_monthly_weather(),
+                         environment_daily=environment_daily or example_daily_environment(days),
+                         environment_hourly=environment_hourly or example_hourly_environment(days, elevation=site.elevation),
+                         initial_soil_temperature=np.full(len(depths), 7.741667 + 273.15) if initial_soil_temperature is None else np.asarray(initial_soil_temperature, float),
+                         initial_soil_moisture=np.full(len(depths), 0.42 * 0.25) if initial_soil_moisture is None else np.asarray(initial_soil_moisture, float))
+    return MicroProblem(model, inputs, days=tuple(days))

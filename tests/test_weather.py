@@ -631,3 +631,31 @@ def test_slope_zenith_against_the_vector_form():
             up = z < 89.999                       # below the horizon the reference caps both angles; the slope formula is only meaningful with the sun up
             worst = max(worst, np.abs(out.zenith_slope_angle[row][up] - zs[up]).max() if up.any() else 0.0)
     assert worst < 1e-6, worst
+
+
+def test_example_constructors_and_example_problem_end_to_end():
+    check_example_problem(HE.WeatherApiEmu)
+
+
+def check_example_problem(engine_factory):
+    """test/example_constructors.jl mirrored: every example_* constructor builds, and example_microclimate_problem() — min/max-driven, as upstream — solves end to
+    end with the same assertions (288 x 19 soil temperatures, no NaN, all within 200..350 K).  The clear-sky irradiance is a stand-in (SolarRadiation.jl is not part
+    of this library); the engine is the host emulation in this tier."""
+    import microclimate_jl_b200 as mc
+    from microclimate_jl_b200 import simulation as sim
+    assert isinstance(mc.example_site(), mc.Site) and isinstance(W.example_monthly_weather(), W.MonthlyMinMaxEnvironment)
+    assert isinstance(mc.example_daily_environment(), mc.DailyTimeseries) and isinstance(mc.example_hourly_environment(), mc.HourlyWeather)
+    assert isinstance(mc.example_soil_properties_model(), mc.CampbelldeVriesSoilProperties) and isinstance(mc.example_soil_hydraulic_model(), mc.CampbellSoilHydraulics)
+    assert isinstance(mc.example_campbell_hydraulic_profile(), mc.CampbellHydraulicProfile) and isinstance(mc.example_soil_profile().hydraulics, mc.CampbellHydraulicProfile)
+    p = mc.example_microclimate_problem()
+    assert isinstance(p, mc.MicroProblem) and p.inputs.environment_hourly.reference_temperature is None and len(p.days) == 12
+    with pytest.raises(ValueError, match="clear_sky"):
+        sim.solve(p)
+    # stand-in clear sky from the built-in geometry: 900 W/m2 direct-normal, 12 % diffuse
+    z = W.WeatherOutBatch(12, 1, ("zenith_angle",))
+    O.populate_weather(W.weather_desc(), W.WeatherInBatch(np.asarray(p.days, dtype=np.int32), 1, {}), z, W.SolarSitesBatch([p.inputs.site.latitude]))
+    cz = np.cos(np.radians(z.zenith_angle[:, 0])) * (z.zenith_angle[:, 0] < 90.0)
+    out = sim.solve(p, clear_sky_direct=900.0 * cz, clear_sky_diffuse=0.12 * 900.0 * cz, engine_factory=engine_factory)
+    T = out.soil_temperature
+    assert T.shape == (12 * 24, 19) and not np.isnan(T).any() and np.all(T > 200.0) and np.all(T < 350.0)
+    assert T[:, 0].max() - T[:, 0].min() > 25.0 and np.ptp(T[:, -1]) < 1.0           # a Wisconsin year at the surface, a steady deep node
