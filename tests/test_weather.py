@@ -659,3 +659,72 @@ def check_example_problem(engine_factory):
     T = out.soil_temperature
     assert T.shape == (12 * 24, 19) and not np.isnan(T).any() and np.all(T > 200.0) and np.all(T < 350.0)
     assert T[:, 0].max() - T[:, 0].min() > 25.0 and np.ptp(T[:, -1]) < 1.0           # a Wisconsin year at the surface, a steady deep node
+
+
+def _random_curve(rng):
+    """A random structurally valid DielCurve: 1-4 bounded shapes on a shuffled cyclic arrangement of anchors (some of them aliases of the same instant through a
+    different TimeOfDay, so that seams chain through bounded shapes), an optional space-filling sine, a random subset of endpoints fed from outside."""
+    pool = [W.ClockTime(float(h)) for h in (2.0, 5.5, 9.0, 12.0, 15.25, 19.0, 22.5)] + [W.Sunrise(), W.Sunrise(1.5), W.Midday(), W.Midday(-2.0), W.Midday(3.0), W.Sunset(),
+                                                                                         W.Sunset(-1.0), W.Midnight(), W.Midnight(1.0)]
+    for _ in range(200):
+        k = int(rng.integers(1, 5))
+        anchors = sorted(rng.choice(len(pool), size=k + 1, replace=False), key=lambda i: W.nominal_hour(pool[i]))
+        anchors = [pool[i] for i in anchors]
+        shapes = []
+        for a, b in zip(anchors[:-1], anchors[1:]):
+            if rng.random() < 0.75:
+                # the next shape may start from an alias of this one's end (same nominal instant, different TimeOfDay): a seam handed off through a bounded shape
+                shapes.append((W.Linear if rng.random() < 0.5 else W.Decay)(a, b))
+        filler = rng.random() < 0.8
+        if filler:
+            t, p = rng.choice(len(pool), size=2, replace=False)
+            shapes.append(W.Sine(pool[t], pool[p]))
+        if not shapes:
+            continue
+        eps = [e for s in shapes for e in s.endpoints()]
+        inputs = tuple(dict.fromkeys(e for e in eps if rng.random() < 0.7))
+        if len(inputs) > A.MC_DIEL_MAX_INPUTS:
+            continue
+        try:
+            return W.DielCurve(tuple(shapes), inputs)
+        except ValueError:
+            continue
+    raise AssertionError("no valid curve drawn")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_curves_fixed_point_equals_recursion(seed):
+    """Randomly drawn curve structures (seams through fillers, through bounded shapes, chains of seams, cycles): the kernel body's once-per-day fixed-point resolution ==
+    the oracle's per-hour recursion, bit for bit incl. where both give NaN; and the oracle == the Python literal restatement wherever that terminates."""
+    rng = np.random.default_rng(100 + seed)
+    curves = {q: _random_curve(rng) for q in A.WEATHER_QUANTITIES}
+    w, win, sites, _ = _random_problem(200 + seed, S=12, D=3, curves=curves)
+    ref, got = W.WeatherOutBatch(win.ndays, win.S), W.WeatherOutBatch(win.ndays, win.S)
+    O.populate_weather(w, win, ref, sites)
+    HE.populate_weather(w, win, got, sites)
+    for k in ALL_OUT:
+        assert np.array_equal(getattr(ref, k), getattr(got, k), equal_nan=True), (k, [str(c.shapes) for c in curves.values()])
+    names = ("reference_temperature", "reference_wind_speed", "reference_humidity", "cloud_cover")
+    worst, checked, nans = 0.0, 0, 0
+    for s in range(win.S):
+        for d in range(win.ndays):
+            noon, ha = ref.hour_solar_noon[d, s], ref.hour_angle_sunrise[d, s]
+            day = {"noon": noon, "sunrise": noon - ha, "sunset": 2 * noon - (noon - ha)}
+            for q in names:
+                vals = [v[d, s] for v in win.forcings[q]]
+                for h in range(0, 24, 5):
+                    r = getattr(ref, q)[24 * d + h, s]
+                    try:
+                        v = _py_sample(curves[q], float(h), day, vals)
+                    except (RecursionError, AttributeError):          # a seam cycle / an uncovered hour: the literal algorithm does not return a value
+                        assert np.isnan(r)
+                        nans += 1
+                        continue
+                    if q in ("reference_humidity", "cloud_cover") and v > 1.0:
+                        v = 1.0
+                    if np.isnan(v):
+                        assert np.isnan(r)
+                        continue
+                    worst = max(worst, abs(v - r) / max(1.0, abs(v)))
+                    checked += 1
+    assert worst < 1e-12 and checked > 100, (worst, checked, nans)
