@@ -20,7 +20,12 @@
  *   - return value: 0 ok, <0 error (see mc_last_error), >0 number of sites whose status
  *     word is non-zero (numeric flag).
  *   - a handle is confined to one host thread at a time and drives ONE GPU; multi-GPU
- *     runs create one handle per GPU over disjoint, contiguous site ranges (no collective).
+ *     runs create one handle per GPU over disjoint, contiguous site ranges (no collective),
+ *     either one process per GPU or one process with a multi handle (mc_multi_*).
+ *
+ * Widened beyond solve_soil!, each selected / called separately: solve_air! (the
+ * profile members of mc_output_soa), populate_weather! + solar geometry (section "Widening":
+ * mc_populate_weather, mc_step_days_minmax, mc_multi_step_days_minmax).
  */
 #ifndef MICROCLIMATE_B200_H
 #define MICROCLIMATE_B200_H
