@@ -136,6 +136,57 @@ def load_forcing(path: str, d0: int = 0, d1: Optional[int] = None, lo: int = 0, 
     return b
 
 
+# ------------------------------------------------------------------------------------------------ min/max weather (populate_weather! inputs)
+def save_weather(path: str, win, solar_sites=None, curves=None, humidity_source: int = A.MC_HUMIDITY_CURVE, day0: int = 0, **meta) -> None:
+    """One container for what mc_populate_weather / mc_step_days_minmax read: the per-day value series of every curve input (`<quantity>_values_<i>`, [ndays][S]),
+    the per-day / hourly solar inputs, pressure, day_of_year, the solar site table ([S]) — and, in the header, the forcing model's structure (the DielCurves are
+    model-level: no data) so that a reader rebuilds mc_weather_desc without the writer's code."""
+    from . import weather as W
+    arrays = {}
+    for q in A.WEATHER_QUANTITIES:
+        for i, v in enumerate(win.forcings[q]):
+            arrays[f"{q}_values_{i}"] = v
+    for f in A.WEATHER_IN_DAILY + A.WEATHER_IN_HOURLY + ("pressure_site",):
+        arrays[f] = getattr(win, f)
+    arrays["day_of_year"] = np.asarray(win.days, dtype=np.int32)
+    if solar_sites is not None:
+        for f in A.SOLAR_SITE_FIELDS:
+            arrays[f] = getattr(solar_sites, f)
+    model = None if curves is None else {"curves": {q: W.curve_to_json(curves[q]) for q in A.WEATHER_QUANTITIES}, "humidity_source": int(humidity_source)}
+    write_container(path, "weather", arrays, S=win.S, ndays=win.ndays, day0=day0, forcing_model=model, meta=meta)
+
+
+def load_weather(path: str, d0: int = 0, d1: Optional[int] = None, lo: int = 0, hi: Optional[int] = None):
+    """Days [d0, d1) and sites [lo, hi) of a weather container: (WeatherInBatch, SolarSitesBatch or None, curves or None, humidity_source)."""
+    from . import weather as W
+    c = Container(path)
+    assert c.kind == "weather"
+    d1 = c.header["ndays"] if d1 is None else d1
+    hi = c.header["S"] if hi is None else hi
+
+    def cut(name, k):
+        a = c.get(name)
+        return None if a is None else _site_view(a[k * d0:k * d1], lo, hi, True)
+    forcings = {}
+    for q in A.WEATHER_QUANTITIES:
+        vals, i = [], 0
+        while c.get(f"{q}_values_{i}") is not None:
+            vals.append(cut(f"{q}_values_{i}", 1))
+            i += 1
+        forcings[q] = tuple(vals)
+    ps = c.get("pressure_site")
+    win = W.WeatherInBatch(np.ascontiguousarray(c.get("day_of_year")[d0:d1]), hi - lo, forcings,
+                           direct_horizontal=cut("direct_horizontal", 24), diffuse_horizontal=cut("diffuse_horizontal", 24),
+                           hour_solar_noon=cut("hour_solar_noon", 1), hour_angle_sunrise=cut("hour_angle_sunrise", 1),
+                           global_radiation_hourly=cut("global_radiation_hourly", 24), pressure_hourly=cut("pressure_hourly", 24),
+                           pressure_site=None if ps is None else np.ascontiguousarray(ps[lo:hi]))
+    lat = c.get("latitude")
+    solar = None if lat is None else W.SolarSitesBatch(*[None if c.get(f) is None else np.ascontiguousarray(c.get(f)[lo:hi]) for f in A.SOLAR_SITE_FIELDS])
+    fm = c.header.get("forcing_model")
+    curves = None if not fm else {q: W.curve_from_json(fm["curves"][q]) for q in A.WEATHER_QUANTITIES}
+    return win, solar, curves, (fm or {}).get("humidity_source", A.MC_HUMIDITY_CURVE)
+
+
 # ------------------------------------------------------------------------------------------------ outputs
 _OUT_FIELDS = A.OUTPUT_NODE_FIELDS + A.OUTPUT_SCALAR_FIELDS + ("snow_temperature",) + A.OUTPUT_PROFILE_FIELDS + A.OUTPUT_PROFILE_SCALARS
 

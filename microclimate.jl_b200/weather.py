@@ -421,6 +421,21 @@ class WeatherOutBatch:
         return c
 
 
+# ---- (de)serialisation of the forcing model for the on-disk containers (storage.py): structure only, no data ----
+_TOD = {"Sunrise": Sunrise, "Sunset": Sunset, "Midday": Midday, "Midnight": Midnight, "ClockTime": ClockTime}
+_SHAPES = {"Sine": Sine, "Decay": Decay, "Linear": Linear}
+
+
+def curve_to_json(c: DielCurve) -> dict:
+    tod = lambda t: [type(t).__name__, float(t.offset)]          # noqa: E731
+    return {"shapes": [[type(sh).__name__, tod(sh.endpoints()[0]), tod(sh.endpoints()[1])] for sh in c.shapes], "inputs": [tod(t) for t in c.inputs]}
+
+
+def curve_from_json(d: dict) -> DielCurve:
+    tod = lambda x: _TOD[x[0]](float(x[1]))                      # noqa: E731
+    return DielCurve(tuple(_SHAPES[k](tod(a), tod(b)) for k, a, b in d["shapes"]), tuple(tod(t) for t in d["inputs"]))
+
+
 def validate_weather(w: A.WeatherDesc) -> None:
     """mc_validate_weather: the DielCurve constructor checks as the library applies them to a flattened descriptor."""
     from . import _lib

@@ -129,3 +129,44 @@ def test_checkpoint_carries_the_status_word(tmp_path):
     # a shard of the checkpoint
     part = st.load_state(tmp_path / "state.mcb", 3, 9)
     assert np.array_equal(part.status, ck.status[3:9])
+
+
+def test_weather_container_round_trip_and_file_driven_minmax_run(tmp_path):
+    """The min/max weather of a grid (value series, clear-sky arrays, solar site table, forcing-model structure in the header) through a container: slices by day and by
+    site equal the in-memory batches, and a file-driven mc_step_days_minmax run in two day chunks over two site shards equals the in-memory run (host emulation)."""
+    import parity
+    from hostemu_engine import WeatherApiEmu
+    from microclimate_jl_b200 import weather as W
+    from test_weather import CUSTOM_CURVES, _soil_case
+    desc, sites, rest, win, solar = _soil_case(S=7, D=2, seed=5)
+    curves = dict({k: v.curve for k, v in W.MINMAX_FORCING_MODEL.items()}, reference_wind_speed=CUSTOM_CURVES["reference_wind_speed"])
+    # the custom wind curve has two inputs, the standard one three: rebuild the wind series accordingly
+    win.forcings["reference_wind_speed"] = win.forcings["reference_wind_speed"][1:]
+    st.save_weather(tmp_path / "weather.mcb", win, solar, curves, note="test")
+    st.save_forcing(tmp_path / "rest.mcb", rest)
+    st.save_sites(tmp_path / "sites.mcb", sites)
+    w_all, s_all, c_all, hs = st.load_weather(tmp_path / "weather.mcb")
+    assert hs == 0 and all(c_all[q].shapes == curves[q].shapes and c_all[q].inputs == curves[q].inputs for q in curves)
+    for q in win.forcings:
+        assert len(w_all.forcings[q]) == len(win.forcings[q]) and all(np.array_equal(a, b) for a, b in zip(w_all.forcings[q], win.forcings[q]))
+    assert np.array_equal(w_all.direct_horizontal, win.direct_horizontal) and np.array_equal(w_all.days, win.days) and w_all.hour_solar_noon is None
+    assert np.array_equal(s_all.latitude, solar.latitude) and np.array_equal(s_all.slope, solar.slope) and s_all.solar_noon_offset_h is None
+    fields = ("soil_temperature", "soil_moisture", "surface_water")
+    wdesc = W.weather_desc(curves)
+    ref_eng = WeatherApiEmu(desc, 7)
+    ref_eng.set_sites(sites)
+    ref = M.OutputBatch(2, desc.n_soil, 7, fields)
+    ref_eng.step_days_minmax(0, wdesc, win, rest, ref, solar)
+    ref_eng.close()
+    got = M.OutputBatch(2, desc.n_soil, 7, fields)
+    for lo, hi in ((0, 4), (4, 7)):
+        eng = WeatherApiEmu(desc, hi - lo)
+        eng.set_sites(st.load_sites(tmp_path / "sites.mcb", lo, hi))
+        for d in range(2):
+            wd, sd, cd, _ = st.load_weather(tmp_path / "weather.mcb", d, d + 1, lo, hi)
+            part = M.OutputBatch(1, desc.n_soil, hi - lo, fields)
+            eng.step_days_minmax(d, W.weather_desc(cd), wd, st.load_forcing(tmp_path / "rest.mcb", d, d + 1, lo, hi), part, sd)
+            for f in fields:
+                getattr(got, f)[24 * d:24 * d + 24, ..., lo:hi] = getattr(part, f)
+        eng.close()
+    parity.assert_bit_identical(got, ref, fields)
