@@ -119,6 +119,15 @@ def main():
     ref = W.WeatherOutBatch(D, n)
     O.populate_weather(w, sub, ref, W.SolarSitesBatch(lat[:n], slope[:n], aspect[:n]))
     identical = all(np.array_equal(getattr(ref, k), outs[k][:, :n].cpu().numpy(), equal_nan=True) for k in A.WEATHER_OUT_HOURLY + A.WEATHER_OUT_DAILY)
+    # the CPU path beside it: the oracle (OpenMP over sites, all host cores) on a bounded sample of the same workload
+    nc = min(S, 1024 if args.emulate else 32768)
+    subc = W.WeatherInBatch(days, nc, {q: tuple(np.ascontiguousarray(v[:, :nc]) for v in win.forcings[q]) for q in A.WEATHER_QUANTITIES},
+                            direct_horizontal=direct[:, :nc], diffuse_horizontal=diffuse[:, :nc], pressure_site=psite[:nc])
+    refc, sitesc = W.WeatherOutBatch(D, nc), W.SolarSitesBatch(lat[:nc], slope[:nc], aspect[:nc])
+    O.populate_weather(w, subc, refc, sitesc)                     # warm-up (page the output arrays in)
+    t0 = time.perf_counter()
+    O.populate_weather(w, subc, refc, sitesc)
+    cpu_s = time.perf_counter() - t0
 
     peak = 6536.0
     try:
@@ -135,7 +144,9 @@ def main():
                      "alg_bytes_per_site_day": (read_bytes + write_bytes) / (S * D), "how": "bytes the kernel must read + write per launch / host-timed launch duration "
                      "(back-to-back launches between two stream synchronisations); peak = MEASURED_PEAKS.json hbm_gbs"},
         "l2": "outputs_larger_than_L2 (%.1f GB written per launch)" % (write_bytes / 1e9),
-        "parity": {"sites_checked": n, "bit_identical_to_oracle": bool(identical)}}))
+        "parity": {"sites_checked": n, "bit_identical_to_oracle": bool(identical)},
+        "cpu_baseline": {"value": nc * D / cpu_s, "unit": "site-days/s", "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": "%d sites x %d days of the same workload, oracle/mc_weather_oracle.cpp with OpenMP over sites, %.2f s" % (nc, D, cpu_s)}}))
 
 
 if __name__ == "__main__":
