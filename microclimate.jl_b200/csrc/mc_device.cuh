@@ -22,7 +22,7 @@
  *   mc_coop_ode.cuh  block-cooperative ODE phase
  *   mc_moisture.cuh  freeze/thaw, Campbell (1985) soil water balance
  *   mc_site.cuh      solve_soil! / solve_air! per site, host-side model flattening
- *   mc_async.cuh     asynchronous shared-memory-resident solve_soil! (the default NoSnow kernel)
+ *   mc_async.cuh     asynchronous shared-memory-resident solve_soil! (opt-in, MC_KERNEL=async: bit-identical, measured slower)
  *
  * The functions are written against a tiny platform shim so the very same code can be compiled by g++ for tests/hostemu (a
  * development harness that runs the kernel body on the CPU where no GPU exists).  The shipped library (mc_api.cu) only ever
