@@ -9,7 +9,8 @@ Contents:
   monthly_*   config 1's min/max inputs (init_monthly/{TMINN,TMAXX,WNMINN,WNMAXX,RHMINN,RHMAXX,CCMINN,CCMAXX}.csv, as the reference's
         test reads them, test/micro_testrun_monthly.jl:93-102) and NicheMapR's own hourly expansion of them (metout_monthly.csv
         TAREF / RH / VREF / SOLR), which the reference's test compares the solved 2 m air temperature / humidity / wind against
-        (test/micro_testrun_monthly.jl:172-180).
+        (test/micro_testrun_monthly.jl:172-180);
+  scan329_*   config 4's daily min/max forcing (scan329/nmr_forcing.csv: Tmin / Tmax, RH min / max, one wind value, cloud max / min, 365 days).
 """
 import os
 
@@ -41,6 +42,13 @@ def main():
         g["monthly_" + k] = col(f"{d}/{f}.csv")[:12] * scale
     m = pd.read_csv(f"{REF}/metout_monthly.csv")
     g["monthly_TAREF_C"], g["monthly_RH_pct"], g["monthly_VREF"], g["monthly_SOLR"] = (m[c].to_numpy(float) for c in ("TAREF", "RH", "VREF", "SOLR"))
+    # config 4 (SCAN 329): the daily min/max forcing the reference's script feeds its DailyMinMaxEnvironment (test/micro_testrun_snow_scan329.jl:93-110;
+    # a single wind value is used for both min and max there)
+    f = pd.read_csv(f"{REF}/scan329/nmr_forcing.csv")
+    g["scan329_doy"] = f.doy.to_numpy(np.int32)
+    for k, c, scale in (("tmin_C", "Tmin_C", 1.0), ("tmax_C", "Tmax_C", 1.0), ("rh_min", "RHmin_pct", 0.01), ("rh_max", "RHmax_pct", 0.01), ("wind", "Wind_ms", 1.0),
+                        ("cloud_max", "CCmax_pct", 0.01), ("cloud_min", "CCmin_pct", 0.01)):
+        g["scan329_" + k] = f[c].to_numpy(float) * scale
     np.savez_compressed(os.path.join(OUT, "weather_golden.npz"), **g)
     print({k: np.shape(v) for k, v in g.items()})
 

@@ -728,3 +728,45 @@ def test_random_curves_fixed_point_equals_recursion(seed):
                     worst = max(worst, abs(v - r) / max(1.0, abs(v)))
                     checked += 1
     assert worst < 1e-12 and checked > 100, (worst, checked, nans)
+
+
+def test_config4_driven_from_its_daily_minmax_forcing():
+    """BASELINE config 4 (SCAN 329) the way the reference's script drives it (test/micro_testrun_snow_scan329.jl:93-180): a DailyMinMaxEnvironment of 365 days
+    (one wind value for min and max) -> populate_weather! -> solve_soil! with the 8-node SnowModel and dynamic moisture.  Weather and zenith from the oracle's
+    diel engine + geometry, clear sky stood in for by NicheMapR's SOLR over its own Angstrom factor; held to the bars of the hourly-driven config-4 test
+    (tests/test_oracle_golden.py): rtol 1e-1 on kelvin over the year, soil T rmse < 3.5 K (observed 2.9; 2.7 with NicheMapR's hourly weather), moisture rmse < 0.06
+    (0.047), snow-depth correlation > 0.85 (0.95), snowfall total within 15 % (0.94)."""
+    import copy
+    import configs
+    import parity
+    from microclimate_jl_b200 import marshal as M
+    from oracle.oracle import OracleEngine
+    p, g = configs.config4_scan329()
+    desc = M.model_desc(p.model, p.time_mode, inputs0=p.inputs)
+    sites, forcing = M.SitesBatch.from_inputs(p.model, [p.inputs]), M.ForcingBatch.from_inputs(p.model, [p.inputs], p.days)
+    assert np.array_equal(GOLD["scan329_doy"], np.asarray(p.days, dtype=np.int32))
+    env = W.DailyMinMaxEnvironment(W.minmax_forcings(
+        reference_temperature_min=GOLD["scan329_tmin_C"] + 273.15, reference_temperature_max=GOLD["scan329_tmax_C"] + 273.15,
+        reference_wind_speed_min=GOLD["scan329_wind"], reference_wind_speed_max=GOLD["scan329_wind"],
+        reference_humidity_min=GOLD["scan329_rh_min"], reference_humidity_max=GOLD["scan329_rh_max"],
+        cloud_cover_min=GOLD["scan329_cloud_min"], cloud_cover_max=GOLD["scan329_cloud_max"]))
+    clear = g["SOLR"] / (0.36 + 0.64 * (1.0 - g["cloud"]))
+    win = W.WeatherInBatch.from_environments(GOLD["scan329_doy"], [env], direct_horizontal=0.8 * clear[:, None], diffuse_horizontal=0.2 * clear[:, None],
+                                             pressure_site=[float(g["pressure"])])
+    wx = W.WeatherOutBatch(365, 1)
+    O.populate_weather(W.weather_desc(), win, wx, W.SolarSitesBatch([float(GOLD["zen_scan329_lat"])]))
+    assert np.abs(wx.zenith_angle[:, 0] - g["ZEN"]).max() < 1e-5
+    assert np.all(wx.reference_wind_speed[:, 0] == np.repeat(GOLD["scan329_wind"], 24))          # min == max: the three lines are flat
+    assert np.sqrt(np.mean((wx.reference_temperature[:, 0] - g["TAREF"]) ** 2)) < 1.0            # NicheMapR's own hourly expansion: 0.76 K rms apart
+    f2 = copy.deepcopy(forcing)
+    for k in A.WEATHER_OUT_HOURLY:
+        getattr(f2, k)[...] = getattr(wx, k)
+    out, eng = parity.run(OracleEngine, desc, sites, f2, fields=parity.ALL_FIELDS + parity.SNOW_FIELDS)
+    assert out.status[0] == 0 and eng.counters()["n_day_passes"] == 365
+    T, G = out.soil_temperature[:, ::2, 0], g["soil_nmr"].astype(float)
+    assert np.abs(T / G - 1).max() < 1e-1 and np.sqrt(((T - G) ** 2).mean()) < 3.5
+    th, GM = out.soil_moisture[:, ::2, 0], g["soilmoist_nmr"].astype(float)
+    assert np.sqrt(((th - GM) ** 2).mean()) < 0.06
+    sd, gsd = out.snow_depth[:, 0], g["SNOWDEP"].astype(float)
+    assert np.corrcoef(sd, gsd)[0, 1] > 0.85 and sd.max() > 20.0
+    assert abs(out.snow_fall[:, 0].sum() / g["SNOWFALL"].sum() - 1) < 0.15
