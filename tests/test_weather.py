@@ -770,3 +770,45 @@ def test_config4_driven_from_its_daily_minmax_forcing():
     sd, gsd = out.snow_depth[:, 0], g["SNOWDEP"].astype(float)
     assert np.corrcoef(sd, gsd)[0, 1] > 0.85 and sd.max() > 20.0
     assert abs(out.snow_fall[:, 0].sum() / g["SNOWFALL"].sum() - 1) < 0.15
+
+
+def check_minmax_snow_and_air_outputs(engine_factory):
+    """mc_step_days_minmax with every output family selected: the soil fields, the SnowModel's scalars and 8-node temperature profile, and solve_air!'s profiles at four
+    heights — config 3 (monthly, snow) driven from its min/max inputs for two sites, against oracle weather + oracle soil + oracle air."""
+    import copy
+    import configs
+    import parity
+    import microclimate_jl_b200 as mc
+    from microclimate_jl_b200 import marshal as M, simulation as sim
+    from oracle.oracle import OracleEngine
+    p, g = configs.config1_monthly(snow=True)
+    p = copy.deepcopy(p)
+    p.model.heights = np.array([0.002, 0.01, 0.5, 2.0])
+    days, env = _monthly_inputs()
+    inputs = []
+    for s in range(2):
+        i = copy.deepcopy(p.inputs)
+        f = W.minmax_forcings(reference_temperature_min=GOLD["monthly_tmin_C"] + 273.15 - 3.0 * s, reference_temperature_max=GOLD["monthly_tmax_C"] + 273.15 - 3.0 * s,
+                              reference_wind_speed_min=GOLD["monthly_wind_min"], reference_wind_speed_max=GOLD["monthly_wind_max"],
+                              reference_humidity_min=GOLD["monthly_rh_min"], reference_humidity_max=GOLD["monthly_rh_max"],
+                              cloud_cover_min=GOLD["monthly_cloud_min"], cloud_cover_max=GOLD["monthly_cloud_max"])
+        i.environment_minmax = W.MonthlyMinMaxEnvironment(f)
+        i.environment_hourly = mc.HourlyWeather(pressure=float(g["pressure"]))
+        i.site.latitude = float(GOLD["zen_monthly_lat"]) + 4.0 * s
+        inputs.append(i)
+    clear = np.stack([g["SOLR"], 1.1 * g["SOLR"]], axis=1)
+    fields = parity.ALL_FIELDS + parity.SNOW_FIELDS + parity.AIR_FIELDS
+    out, wx = sim.solve_minmax_batched(p.model, inputs, days=p.days, time_mode=p.time_mode, clear_sky_direct=0.75 * clear, clear_sky_diffuse=0.25 * clear,
+                                       fields=fields, return_weather=True, engine_factory=engine_factory)
+    desc = M.model_desc(p.model, p.time_mode, inputs0=inputs[0])
+    assert desc.n_snow == 8 and desc.n_heights == 4
+    hourly = M.ForcingBatch.from_inputs(p.model, inputs, p.days)
+    for k in A.WEATHER_OUT_HOURLY:
+        getattr(hourly, k)[...] = getattr(wx, k)
+    ref, _ = parity.run(OracleEngine, desc, M.SitesBatch.from_inputs(p.model, inputs), hourly, fields=fields)
+    parity.assert_bit_identical(out, ref, fields)
+    assert ref.snow_depth.max() > 1.0 and np.isfinite(ref.air_temperature).all() and ref.snow_temperature.shape[1] == 8
+
+
+def test_minmax_step_with_snow_and_air_outputs():
+    check_minmax_snow_and_air_outputs(HE.WeatherApiEmu)

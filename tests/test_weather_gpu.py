@@ -14,7 +14,7 @@ from microclimate_jl_b200 import synthetic as syn
 from microclimate_jl_b200 import weather as W
 from oracle import oracle as O
 from oracle.oracle import OracleEngine
-from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _derived_case, _random_problem, _soil_case, check_example_problem, check_solve_minmax_batched
+from test_weather import ALL_OUT, CUSTOM_CURVES, GOLD, _derived_case, _random_problem, _soil_case, check_example_problem, check_minmax_snow_and_air_outputs, check_solve_minmax_batched
 
 pytestmark = pytest.mark.gpu
 
@@ -146,3 +146,8 @@ def test_multi_device_minmax_step_on_the_b200(SoilEngine):
 def test_example_microclimate_problem_solves_on_the_b200(SoilEngine):
     """The reference's own example problem (test/example_constructors.jl: min/max-driven Madison year, N = 19) end to end through the CUDA library."""
     check_example_problem(None)
+
+
+def test_minmax_step_with_snow_and_air_outputs_on_the_b200(SoilEngine):
+    """Every output family through mc_step_days_minmax on the B200: soil fields, SnowModel scalars + 8-node profile, solve_air! profiles (config 3 from its min/max inputs)."""
+    check_minmax_snow_and_air_outputs(None)
