@@ -98,3 +98,9 @@ def test_product_does_not_reach_into_test_infrastructure():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "libmc_oracle" not in txt and "mc_oracle" not in txt and "libmc_hostemu" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_every_export_is_documented_against_the_reference_interface():
+    """INTEGRATION.md section 1 maps each C-ABI entry point to the reference interface it replaces: no exported symbol may be missing from it."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [e for e in _lib.EXPORTS if e not in doc] == []
