@@ -157,7 +157,8 @@ so `solve_air!` runs unchanged.
 
 `devices = [0, 1, ...]` shards the sites over several GPUs from this one process (`mc_multi_*`); `chunk_days` streams time in
 chunks through the asynchronous entry (`mc_step_days_async` / `mc_wait`): the H2D of chunk q+1 and the D2H of chunk q-1 overlap
-the kernel of chunk q, and the carried state stays on the device between chunks (identical results to one chunk).
+the kernel of chunk q, and the carried state stays on the device between chunks (identical results to one chunk, except the first
+`soil_humidity` row of every chunk after the first: `initialise_soil_humidity!` addresses row 1 of the whole run, which a later chunk does not hold).
 The initial snowpack (`initial_snow_*`) is model-level in the ABI: it must be the same for every cache of a batch.
 """
 function solve_soil_batched!(caches::AbstractVector{<:MicroCache}; device::Integer=0, devices=nothing, chunk_days=nothing)

@@ -277,7 +277,8 @@ def solve_soil_batched(model: T.MicroModel, inputs: Sequence[T.MicroInputs], *, 
     `site_result(s)` un-marshals a site into the reference's (nsteps, N) MicroResult layout.
 
     `chunk_days` streams time in chunks with the carried state resident on the GPU (results are identical
-    to a single chunk: the state carried between chunks is exactly what the reference carries between days).  `devices` shards the sites
+    to a single chunk: the state carried between chunks is exactly what the reference carries between days — with one exception, the first `soil_humidity`
+    row of every chunk after the first, see DESIGN.md "known limitations").  `devices` shards the sites
     over several GPUs from this one process (MultiSoilEngine); chunks are pipelined (H2D / kernel / D2H overlap) either way."""
     time_mode = time_mode if time_mode is not None else T.NonConsecutiveDayMode()
     if len(inputs) == 0:
