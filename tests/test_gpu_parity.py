@@ -103,7 +103,8 @@ def test_state_checkpoint_roundtrip(SoilEngine, synth):
     b = SoilEngine(desc, sites.S); b.set_sites(sites); b.set_state(st)
     oa = M.OutputBatch(1, desc.n_soil, sites.S, f); ob = M.OutputBatch(1, desc.n_soil, sites.S, f)
     a.step_days(1, forcing.day_slice(1, 2), oa); b.step_days(1, forcing.day_slice(1, 2), ob)
-    parity.assert_bit_identical(oa, ob, f)
+    for k in f:                                # (parity.assert_bit_identical would also compare the status words, which differ here by construction)
+        assert np.array_equal(getattr(oa, k), getattr(ob, k)), k
     assert np.all(ob.status[::5] & 4) and np.array_equal(ob.status & ~4, oa.status & ~4)
 
 
