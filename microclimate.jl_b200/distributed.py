@@ -43,6 +43,34 @@ def run_shard(engine_factory: Callable, desc, sites: M.SitesBatch, forcing: M.Fo
     return out, (lo, hi)
 
 
+def run_shard_minmax(engine_factory: Callable, desc, wdesc, sites: M.SitesBatch, win, rest: M.ForcingBatch, solar_sites, rank: int, world: int,
+                     fields: Sequence[str] = M.DEFAULT_OUTPUT_FIELDS, chunk_days: Optional[int] = None):
+    """run_shard for a min/max-driven problem: this rank expands the weather of, and integrates, its contiguous shard (mc_step_days_minmax); `win` / `rest` /
+    `solar_sites` are the whole batch's weather inputs, remaining forcing and solar site table, sliced here."""
+    lo, hi = site_shards(sites.S, world)[rank]
+    out = M.OutputBatch(win.ndays, desc.n_soil, hi - lo, fields, desc.n_snow, desc.n_heights)
+    if hi == lo:
+        return out, (lo, hi)
+    eng = engine_factory(desc, hi - lo)
+    try:
+        eng.set_sites(sites.slice(lo, hi))
+        w, f, ss = win.site_slice(lo, hi), rest.site_slice(lo, hi), (None if solar_sites is None else solar_sites.slice(lo, hi))
+        cd = win.ndays if not chunk_days else min(int(chunk_days), win.ndays)
+        d0 = 0
+        while d0 < win.ndays:
+            d1 = min(win.ndays, d0 + cd)
+            part = out if (d0 == 0 and d1 == win.ndays) else M.OutputBatch(d1 - d0, desc.n_soil, hi - lo, fields, desc.n_snow, desc.n_heights)
+            eng.step_days_minmax(d0, wdesc, w.day_slice(d0, d1), f.day_slice(d0, d1), part, ss)
+            if part is not out:
+                out.assign_rows(24 * d0, part)
+            d0 = d1
+    finally:
+        close = getattr(eng, "close", None)
+        if close:
+            close()
+    return out, (lo, hi)
+
+
 def gather_outputs(local: M.OutputBatch, n_sites_total: int, group=None, dst: int = 0) -> Optional[M.OutputBatch]:
     """Host gather of per-rank output shards into one OutputBatch on `dst` (None elsewhere).  `group` must be a
     CPU-capable (gloo) process group; with an nccl default group create one with `dist.new_group(backend="gloo")`."""

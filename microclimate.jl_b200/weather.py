@@ -354,6 +354,11 @@ class SolarSitesBatch:
         self.slope, self.aspect = _arr(slope, (S,), "slope"), _arr(aspect, (S,), "aspect")
         self.solar_noon_offset_h = _arr(solar_noon_offset_h, (S,), "solar_noon_offset_h")
 
+    def slice(self, lo: int, hi: int) -> "SolarSitesBatch":
+        """Contiguous site range [lo, hi) — the unit of multi-GPU sharding."""
+        cut = lambda a: None if a is None else np.ascontiguousarray(a[lo:hi])      # noqa: E731
+        return SolarSitesBatch(cut(self.latitude), cut(self.slope), cut(self.aspect), cut(self.solar_noon_offset_h))
+
     def c_struct(self) -> A.SolarSitesSoA:
         c = A.SolarSitesSoA()
         for f in A.SOLAR_SITE_FIELDS:
@@ -382,6 +387,15 @@ class WeatherInBatch:
         f = {q: tuple(np.stack([np.asarray(forcing_of(e.forcings, q).values[i], dtype=np.float64) for e in envs], axis=1)
                       for i in range(len(forcing_of(envs[0].forcings, q).values))) for q in A.WEATHER_QUANTITIES}
         return cls(days, S, f, **kw)
+
+    def site_slice(self, lo: int, hi: int) -> "WeatherInBatch":
+        """Sites [lo, hi) of this batch (multi-GPU shards)."""
+        cut = lambda a: None if a is None else np.ascontiguousarray(a[..., lo:hi])      # noqa: E731
+        return WeatherInBatch(self.days, hi - lo, {q: tuple(cut(v) for v in self.forcings[q]) for q in A.WEATHER_QUANTITIES},
+                              direct_horizontal=cut(self.direct_horizontal), diffuse_horizontal=cut(self.diffuse_horizontal),
+                              hour_solar_noon=cut(self.hour_solar_noon), hour_angle_sunrise=cut(self.hour_angle_sunrise),
+                              global_radiation_hourly=cut(self.global_radiation_hourly), pressure_hourly=cut(self.pressure_hourly),
+                              pressure_site=cut(self.pressure_site))
 
     def day_slice(self, d0: int, d1: int) -> "WeatherInBatch":
         """Days [d0, d1) of this batch (time-chunked runs)."""

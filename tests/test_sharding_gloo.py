@@ -112,3 +112,44 @@ def test_two_rank_gather_carries_snow_and_air_profile_outputs():
             assert got[k].shape == getattr(ref, k).shape, k
             assert np.array_equal(got[k], getattr(ref, k)), k
         assert np.array_equal(got["status"], ref.status)
+
+
+def _worker_minmax(rank, world, port, path):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    from hostemu_engine import WeatherApiEmu
+    from microclimate_jl_b200 import distributed as D, weather as W
+    from test_weather import _soil_case
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    desc, sites, rest, win, solar = _soil_case(S=9, D=2, seed=31)
+    f = ("soil_temperature", "soil_moisture", "surface_water")
+    local, _ = D.run_shard_minmax(WeatherApiEmu, desc, W.weather_desc(), sites, win, rest, solar, rank, world, fields=f, chunk_days=1)
+    full = D.gather_outputs(local, sites.S)
+    if rank == 0:
+        np.savez(path, T=full.soil_temperature, th=full.soil_moisture, pool=full.surface_water, status=full.status)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_minmax_run_equals_single_process():
+    """One process per GPU for a min/max-driven problem: each rank expands the weather of its shard and integrates it (mc_step_days_minmax, here the host emulation of
+    the weather unit over the soil host emulation), no data-path collective, host gather — equal to the single-handle run."""
+    from hostemu_engine import WeatherApiEmu
+    from microclimate_jl_b200 import marshal as M, weather as W
+    from test_weather import _soil_case
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.npz")
+        mp.spawn(_worker_minmax, args=(2, _free_port(), path), nprocs=2, join=True)
+        got = np.load(path)
+        desc, sites, rest, win, solar = _soil_case(S=9, D=2, seed=31)
+        eng = WeatherApiEmu(desc, 9)
+        try:
+            eng.set_sites(sites)
+            ref = M.OutputBatch(2, desc.n_soil, 9, ("soil_temperature", "soil_moisture", "surface_water"))
+            eng.step_days_minmax(0, W.weather_desc(), win, rest, ref, solar)
+        finally:
+            eng.close()
+        assert np.array_equal(got["T"], ref.soil_temperature) and np.array_equal(got["th"], ref.soil_moisture)
+        assert np.array_equal(got["pool"], ref.surface_water) and np.array_equal(got["status"], ref.status)
