@@ -812,3 +812,41 @@ def check_minmax_snow_and_air_outputs(engine_factory):
 
 def test_minmax_step_with_snow_and_air_outputs():
     check_minmax_snow_and_air_outputs(HE.WeatherApiEmu)
+
+
+def test_library_validation_agrees_with_the_constructor_checks_on_random_structures():
+    """mc_validate_weather (C++) and the host mirror's DielCurve constructor are two statements of diel.jl:182-222: on 400 randomly assembled shape / input sets —
+    overlapping, gapped, doubly space-filled, zero-length, with stray inputs — they accept and reject the same ones."""
+    import ctypes as C
+    from microclimate_jl_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(77)
+    pool = [W.ClockTime(float(h)) for h in (0.0, 3.0, 6.0, 9.5, 12.0, 18.0, 21.0)] + [W.Sunrise(), W.Sunrise(2.0), W.Midday(), W.Midday(-3.0), W.Sunset(), W.Sunset(1.0),
+                                                                                     W.Midnight(), W.Midnight(2.0)]
+    kinds = (W.Sine, W.Decay, W.Linear)
+    accepted = rejected = 0
+    for _ in range(400):
+        n = int(rng.integers(1, 5))
+        shapes = tuple(kinds[int(rng.integers(0, 3))](pool[int(rng.integers(len(pool)))], pool[int(rng.integers(len(pool)))]) for _ in range(n))
+        eps = [e for s in shapes for e in s.endpoints()]
+        inputs = tuple(dict.fromkeys([e for e in eps if rng.random() < 0.5] + ([pool[int(rng.integers(len(pool)))]] if rng.random() < 0.15 else [])))[:A.MC_DIEL_MAX_INPUTS]
+        try:
+            W.DielCurve(shapes, inputs)
+            ok_py = True
+        except ValueError:
+            ok_py = False
+        c = A.DielCurve()                                  # flattened by hand: the constructor must not be in the way of an invalid structure
+        c.n_shapes, c.n_inputs = len(shapes), len(inputs)
+        for i, s in enumerate(shapes):
+            a, b = s.endpoints()
+            c.shapes[i] = A.DielShape(s.KIND, 0, A.TimeOfDay(a.KIND, 0, float(a.offset)), A.TimeOfDay(b.KIND, 0, float(b.offset)))
+        for i, t in enumerate(inputs):
+            c.inputs[i] = A.TimeOfDay(t.KIND, 0, float(t.offset))
+        w = W.weather_desc()
+        w.reference_wind_speed = c
+        buf = C.create_string_buffer(256)
+        ok_c = L.mc_validate_weather(C.byref(w), buf, 256) == 0
+        assert ok_c == ok_py, (shapes, inputs, buf.value)
+        accepted += ok_py
+        rejected += not ok_py
+    assert accepted > 30 and rejected > 100, (accepted, rejected)
