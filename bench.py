@@ -105,13 +105,13 @@ def _probe(script, timeout_s):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def sand_probe(timeout_s=420):
+def sand_probe(timeout_s=300):
     """The same kernel on the six-class texture grid of SURVEY 8d (incl. pure sand) next to the headline grid, one wave of sites (tools/gpu_sand_probe.py), in a
     separate process after the headline measurement."""
     return _probe("gpu_sand_probe.py", timeout_s)
 
 
-def weather_probe(timeout_s=300):
+def weather_probe(timeout_s=240):
     """Throughput + HBM roofline + oracle parity of the weather kernel, measured by tools/gpu_weather_probe.py in a SEPARATE process
     after the headline measurement is complete: whatever happens there (a CUDA error included) cannot touch this process or its numbers."""
     return _probe("gpu_weather_probe.py", timeout_s)
