@@ -106,8 +106,8 @@ def _probe(script, timeout_s):
 
 
 def sand_probe(timeout_s=300):
-    """The same kernel on the six-class texture grid of SURVEY 8d (incl. pure sand) next to the headline grid, one wave of sites (tools/gpu_sand_probe.py), in a
-    separate process after the headline measurement."""
+    """The six-class texture grid of SURVEY 8d (incl. pure sand) and the SnowModel grid (per-site kernel) next to the headline grid, one wave of sites
+    (tools/gpu_sand_probe.py), in a separate process after the headline measurement."""
     return _probe("gpu_sand_probe.py", timeout_s)
 
 
@@ -365,7 +365,7 @@ def main():
                                 "sample": "%d sites (one full latitude sweep) x 1 day (day 1 after a 1-day warm-up), OpenMP over sites, %.1f s; C++ restatement of the reference (Julia not installable here)" % (n, times[1])}
     if world == 1 and not args.no_probes:
         eng.close()                       # the probes are separate processes on the same GPU: give the memory back first
-        line["with_sand"] = sand_probe()
+        line["grid_variants"] = sand_probe()
         line["widening"] = {"weather_kernel": weather_probe()}
     print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
