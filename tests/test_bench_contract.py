@@ -56,6 +56,7 @@ def test_weather_probe_self_test_and_bench_attachment():
     q = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert set(q) >= {"with_sand", "without_sand", "with_snow", "ratio", "snow_ratio", "workload"} and q["with_sand"]["work_per_site_day"]["n_infil_steps"] == 240.0
     assert "soil_chunk_kernel<19, 8>" in q["with_snow"]["kernel"] and q["with_snow"]["sites_with_snow_at_the_end"] >= 0
+    assert 1.0 <= q["with_tolerance_convergence"]["day_passes_per_site_day"] <= 6.0 and q["tolerance_ratio"] > 0
     sys.path.insert(0, root)
     import bench
     import torch

@@ -43,10 +43,17 @@ def main():
     # kernel soil_chunk_kernel<19, 8>; the year starts in January, so the high-latitude sites of the northern sweep carry snow from the first cold wet hour on
     snow_model = dataclasses.replace(syn.synthetic_model(), snow_model=T.SnowModel(density_function=(0.5979, 0.2178, 0.001, 0.0038)))
     desc_snow = M.model_desc(snow_model, syn.synthetic_time_mode())
+    # fourth variant: tolerance-based day-pass convergence (SoilTemperatureConvergenceTolerance, days repeated until the start-of-day profile moves < 0.5 K, at most 6
+    # passes, NonConsecutiveDayMode) — per-site pass counts diverge, so it runs the per-site kernel soil_chunk_kernel<19, 0> as well
+    base = syn.synthetic_model()
+    tol_model = dataclasses.replace(base, config=dataclasses.replace(base.config, convergence=T.SoilTemperatureConvergenceTolerance(tolerance=0.5, max_iterations_per_day=6)))
+    desc_tol = M.model_desc(tol_model, T.NonConsecutiveDayMode(iterations_per_day=6))
     days = [syn.make_forcing(0, S, S, d, 1, threads=os.cpu_count() or 1) for d in range(K + 1)]
     out = M.OutputBatch(1, desc.n_soil, S, ("soil_temperature", "soil_moisture"))
     res = {}
-    for key, sand, dsc in (("without_sand", False, desc), ("with_sand", True, desc), ("with_snow", False, desc_snow)):
+    for key, sand, dsc in (("without_sand", False, desc), ("with_sand", True, desc), ("with_snow", False, desc_snow), ("with_tolerance_convergence", False, desc_tol)):
+        if key == "with_tolerance_convergence":
+            out = M.OutputBatch(1, dsc.n_soil, S, ("soil_temperature", "soil_moisture"))
         if key == "with_snow":
             out = M.OutputBatch(1, dsc.n_soil, S, ("soil_temperature", "soil_moisture", "snow_depth"), dsc.n_snow)
         with SoilEngine(dsc, S) as eng:
@@ -63,13 +70,17 @@ def main():
             "site_days_per_s": S * K / (sum(ms) * 1e-3), "kernel_ms_per_day": ms,
             "flagged_by_bit": {name: int(((st & bit) != 0).sum()) for bit, name in STATUS_BITS.items()},
             "work_per_site_day": {k: (c[k] - c0[k]) / (S * K) for k in ("n_rhs", "n_accept", "n_reject", "n_obukhov_iter", "n_newton_iter", "n_infil_steps")}}
+        if key == "with_tolerance_convergence":
+            res[key]["kernel"] = "soil_chunk_kernel<19, 0> (per-site kernel: per-site pass counts are not on the cooperative kernel)"
+            res[key]["day_passes_per_site_day"] = (c["n_day_passes"] - c0["n_day_passes"]) / (S * K)
         if key == "with_snow":
             res[key]["kernel"] = "soil_chunk_kernel<19, 8> (per-site kernel: SnowModel is not on the cooperative kernel)"
             res[key]["sites_with_snow_at_the_end"] = int((out.snow_depth[-1] > 0.0).sum())
     res["snow_ratio"] = res["with_snow"]["site_days_per_s"] / res["without_sand"]["site_days_per_s"]
+    res["tolerance_ratio"] = res["with_tolerance_convergence"]["site_days_per_s"] / res["without_sand"]["site_days_per_s"]
     res["ratio"] = res["with_sand"]["site_days_per_s"] / res["without_sand"]["site_days_per_s"]
     res["workload"] = ("%d sites (one wave) x %d timed days after 1 warm-up day, same sites / forcing in all runs: the headline grid's five texture classes, the six incl. "
-                       "pure sand, and the headline textures with the SnowModel" % (S, K))
+                       "pure sand, the headline textures with the SnowModel, and with tolerance-based day-pass convergence (non-consecutive days)" % (S, K))
     if args.emulate:
         res["emulated"] = "host emulation - self-test of the probe, not a measurement"
     print(json.dumps(res))
