@@ -489,6 +489,15 @@ void mc_destroy(mc_handle* h)
     delete h;
 }
 
+/* [rows] x width bytes between a pitched and a packed array.  Contiguous on both sides (the single-handle case: the host arrays are exactly as wide as the handle)
+ * is ONE linear copy: round 1's linear copies of these buffers moved ~56 GB/s over PCIe, round 2's 2-D copies of the same contiguous buffers ~18 GB/s (the exposed
+ * copy time in the e2e figures of profiles/r1_bench_1gpu_v10.json vs r2_bench_1gpu_a.json); the 2-D form is kept for genuinely strided multi-device slices */
+static cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+}
+
 /* sites of this handle = columns [col0, col0 + S) of host arrays that are `host_pitch` doubles wide (a multi-device job shares one set of arrays) */
 static int set_sites_pitched(mc_handle* h, const mc_sites_soa* s, const mc_initial_soa* init, int64_t host_pitch, int64_t col0)
 {
@@ -502,10 +511,10 @@ static int set_sites_pitched(mc_handle* h, const mc_sites_soa* s, const mc_initi
                                  s->air_entry_water_potential, s->saturated_hydraulic_conductivity, s->campbell_b_parameter, s->root_density};
     double* node_dst[8] = {h->bd, h->md, h->lam_m, h->c_m, h->psi_e, h->ks, h->bb, h->rootd};
     for (int k = 0; k < 4; k++) { if (!site_src[k]) { h->err = "mc_sites_soa has a NULL site field"; return -1; } MC_CUDA(h, cudaMemcpyAsync(site_dst[k], site_src[k] + col0, bS, cudaMemcpyHostToDevice, h->stream)); }
-    for (int k = 0; k < 8; k++) { if (!node_src[k]) { h->err = "mc_sites_soa has a NULL node field"; return -1; } MC_CUDA(h, cudaMemcpy2DAsync(node_dst[k], bS, node_src[k] + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream)); }
+    for (int k = 0; k < 8; k++) { if (!node_src[k]) { h->err = "mc_sites_soa has a NULL node field"; return -1; } MC_CUDA(h, copy_rows(node_dst[k], bS, node_src[k] + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream)); }
     h->has_init_T = init->initial_soil_temperature != nullptr;
-    if (h->has_init_T) MC_CUDA(h, cudaMemcpy2DAsync(h->init_T, bS, init->initial_soil_temperature + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream));
-    MC_CUDA(h, cudaMemcpy2DAsync(h->init_theta, bS, init->initial_soil_moisture + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream));
+    if (h->has_init_T) MC_CUDA(h, copy_rows(h->init_T, bS, init->initial_soil_temperature + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream));
+    MC_CUDA(h, copy_rows(h->init_theta, bS, init->initial_soil_moisture + col0, hp, bS, N, cudaMemcpyHostToDevice, h->stream));
     mcd::KArgs a; fill_site_state_args(h, a);
     init_state_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(a, h->N, h->model.n_snow, h->model.snow);
     MC_CUDA(h, cudaGetLastError());
@@ -761,7 +770,7 @@ static int step_days_enqueue(mc_handle* h, int64_t day0, int32_t ndays, const mc
     const size_t w = S * sizeof(double), hp = (size_t)host_pitch * sizeof(double);
     /* copy-in */
     MC_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_k[b], 0));      /* kernel q-2 has finished reading this staging set (no-op for a never-recorded event) */
-    for (const Plane& pl : in_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.dev, w, pl.host_in + col0, hp, w, pl.rows, cudaMemcpyHostToDevice, h->s_in));
+    for (const Plane& pl : in_planes) MC_CUDA(h, copy_rows(pl.dev, w, pl.host_in + col0, hp, w, pl.rows, cudaMemcpyHostToDevice, h->s_in));
     MC_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->s_in));
     /* compute */
     MC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_h2d[b], 0));
@@ -780,7 +789,7 @@ static int step_days_enqueue(mc_handle* h, int64_t day0, int32_t ndays, const mc
     int32_t* status_host = o->status ? o->status + col0 : nullptr;
     if (!status_host) { h->status_own[b].resize(S); status_host = h->status_own[b].data(); }
     MC_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_k[b], 0));
-    for (const Plane& pl : out_planes) MC_CUDA(h, cudaMemcpy2DAsync(pl.host_out + col0, hp, pl.dev, w, w, pl.rows, cudaMemcpyDeviceToHost, h->s_out));
+    for (const Plane& pl : out_planes) MC_CUDA(h, copy_rows(pl.host_out + col0, hp, pl.dev, w, w, pl.rows, cudaMemcpyDeviceToHost, h->s_out));
     MC_CUDA(h, cudaMemcpyAsync(status_host, h->flags, S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out));
     MC_CUDA(h, cudaEventRecord(h->ev_d2h[b], h->s_out));
     h->status_dst[b] = status_host; h->busy[b] = true;
